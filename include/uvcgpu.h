@@ -1,0 +1,256 @@
+/* uvcgpu.h - C ABI of the B200 pileup-and-score library (libuvcgpu.so).
+ *
+ * This is the drop-in boundary for the reference's in-process seam
+ *     template<class T> int process_batch(std::string& uncompressed_vcf_string, ..., BatchArg& arg, const T& tkis)
+ * (reference main.cpp:458-464, called per tier-3 region at main.cpp:1508-1521). The reference has no
+ * plugin/FFI interface of its own (one statically linked executable, Makefile:33-38), so every entry
+ * point below names the reference code it replaces. Plain pointers and sizes only; no exceptions cross
+ * the boundary; every function returns 0 on success or a negative UVCGPU_E* code, with the message
+ * available from uvcgpu_last_error(). All buffers are caller-owned. The library fails loudly
+ * (UVCGPU_ENODEVICE) when no CUDA device is present: there is no CPU fallback.
+ */
+#ifndef UVCGPU_H_INCLUDED
+#define UVCGPU_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UVCGPU_ABI_VERSION 1
+
+enum uvcgpu_error {
+    UVCGPU_OK = 0,
+    UVCGPU_EINVAL = -1,      /* bad argument */
+    UVCGPU_ENODEVICE = -2,   /* no usable CUDA device (never falls back to the CPU) */
+    UVCGPU_ECUDA = -3,       /* a CUDA call failed */
+    UVCGPU_ENOMEM = -4,
+    UVCGPU_EUNSUPPORTED = -5 /* a reference code path this build does not cover (e.g. IonTorrent) */
+};
+
+/* AlignmentSymbol (reference main_conversion.hpp:316-334); VTI in the VCF carries these integers. */
+enum uvcgpu_symbol {
+    UVC_BASE_A = 0, UVC_BASE_C = 1, UVC_BASE_G = 2, UVC_BASE_T = 3, UVC_BASE_N = 4, UVC_BASE_NN = 5,
+    UVC_LINK_M = 6, UVC_LINK_D3P = 7, UVC_LINK_D2 = 8, UVC_LINK_D1 = 9,
+    UVC_LINK_I3P = 10, UVC_LINK_I2 = 11, UVC_LINK_I1 = 12, UVC_LINK_NN = 13,
+    UVC_NUM_SYMBOLS = 14
+};
+
+/* Flat POD mirror of the reference's CommandLineArgs AFTER its data-driven inference
+ * (CmdLineArgs.hpp:20-438; inference CmdLineArgs.cpp:36-136, 1003-1035). Field names follow the
+ * reference's option names. Filled by uvcgpu_params_default() and then overridden by the caller. */
+typedef struct uvcgpu_params {
+    int32_t abi_version;
+    /* inferred */
+    int32_t inferred_sequencing_platform; /* 1 = Illumina/BGI, 2 = IonTorrent (unsupported) */
+    int32_t central_readlen;
+    int32_t inferred_maxMQ;
+    int32_t is_tumor_vcf_provided;        /* IS_PROVIDED(vcf_tumor_fname): this run is the normal of a T/N pair */
+    int32_t assay_type;                   /* 0 auto, 1 capture, 2 amplicon */
+    int32_t molecule_tag;
+    int32_t pair_end_merge;               /* 0 = yes */
+    int32_t disable_duplex;
+    int32_t should_output_all;
+    uint32_t outvar_flag;
+    /* read filter, grouping (grouping.cpp:347-415, 608-997) */
+    int32_t kept_aln_min_aln_len, kept_aln_min_mapqual, kept_aln_min_isize, kept_aln_max_isize, kept_aln_is_zero_isize_discarded;
+    int32_t min_altdp_thres;
+    uint32_t dedup_flag;
+    double dedup_center_mult;
+    double dedup_amplicon_end2end_ratio;
+    double dedup_amplicon_border_to_insert_cov_weak_avgDP_ratio, dedup_amplicon_border_to_insert_cov_strong_avgDP_ratio;
+    double dedup_amplicon_border_to_insert_cov_weak_totDP_ratio, dedup_amplicon_border_to_insert_cov_strong_totDP_ratio;
+    double dedup_amplicon_border_weak_minDP, dedup_amplicon_border_strong_minDP;
+    int32_t assay_sequencing_BQ_max, assay_sequencing_BQ_inc;
+    /* primers */
+    int32_t primerlen, primerlen2;
+    uint32_t primer_flag;
+    int32_t tn_is_paired;
+    int32_t bq_phred_added_misma, bq_phred_added_indel;
+    /* bias thresholds (CmdLineArgs.hpp:137-198) */
+    int32_t bias_thres_highBQ, bias_thres_highBAQ, bias_thres_aLPxT_add, bias_thres_aLPxT_perc;
+    int32_t bias_thres_aLRP1t_minus, bias_thres_aLRP2t_minus, bias_thres_aLRB1t_minus, bias_thres_aLRB2t_minus;
+    int32_t bias_thres_aLRP1t_avgmul_perc, bias_thres_aLRP2t_avgmul_perc, bias_thres_aLRB1t_avgmul_perc, bias_thres_aLRB2t_avgmul_perc;
+    int32_t bias_thres_aLRP1Nt_avgmul_perc, bias_thres_aLRB1Nt_avgmul_perc;
+    int32_t bias_thres_aLRI1T_perc, bias_thres_aLRI2T_perc, bias_thres_aLRI1t_perc, bias_thres_aLRI2t_perc;
+    int32_t bias_thres_aLRI1NT_perc, bias_thres_aLRI1Nt_perc, bias_thres_aLRI1T_add, bias_thres_aLRI2T_add;
+    int32_t bias_thres_PFBQ1, bias_thres_PFBQ2;
+    int32_t bias_thres_interfering_indel, bias_thres_interfering_indel_BQ, bias_thres_BAQ1, bias_thres_BAQ2;
+    int32_t bias_thres_strict_c2LRP0;
+    /* families (CmdLineArgs.hpp:43-51, 235-273) */
+    int32_t fam_thres_highBQ_snv, fam_thres_highBQ_indel, fam_thres_dup1add, fam_thres_dup1perc, fam_thres_dup2add, fam_thres_dup2perc, fam_thres_qseqlen;
+    int32_t fam_thres_emperr_all_flat_snv, fam_thres_emperr_con_perc_snv, fam_thres_emperr_all_flat_indel, fam_thres_emperr_con_perc_indel;
+    int32_t fam_phred_indel_inc_before_barcode_labeling;
+    int32_t fam_phred_sscs_transition_CG_TA, fam_phred_sscs_transition_AT_GC, fam_phred_sscs_transversion_CG_AT, fam_phred_sscs_transversion_other;
+    int32_t fam_phred_sscs_indel_open, fam_phred_sscs_indel_ext;
+    uint32_t fam_flag;
+    int32_t syserr_mut_region_n_bases;
+    /* indels (CmdLineArgs.hpp:330-354) */
+    int32_t indel_BQ_max, indel_str_repeatsize_max, indel_vntr_repeatsize_max;
+    double indel_polymerase_size, indel_polymerase_slip_rate, indel_del_to_ins_err_ratio;
+    int32_t indel_adj_tracklen_dist, indel_adj_indellen_perc, indel_nonSTR_phred_per_base, indel_str_phred_per_region, indel_filter_edge_dist;
+    double powlaw_exponent;
+    /* micro-adjustments (CmdLineArgs.hpp:364-408) */
+    int32_t microadjust_xm, microadjust_cliplen, microadjust_delFAQmax, microadjust_nobias_pos_indel_maxlen;
+    int32_t microadjust_near_clip_dist, microadjust_alignment_clip_min_len, microadjust_padded_deletion_flag;
+    int32_t microadjust_median_readlen_thres, microadjust_BAQ_per_base_x1024;
+    /* phasing */
+    int32_t phasing_haplotype_max_count, phasing_haplotype_min_ad, phasing_haplotype_max_detail_cnt;
+    int32_t reserved[16];
+} uvcgpu_params;
+
+/* One tier-3 region (the reference's BedLine, iohts.hpp:14-35) plus the previous one, as process_batch receives
+ * them through BatchArg (main.cpp:143-144). Reads of the region are records [read_begin, read_end) of the batch. */
+typedef struct uvcgpu_tile {
+    int32_t tid;
+    int32_t beg_pos, end_pos;       /* BedLine.beg_pos / end_pos */
+    uint32_t region_flag;           /* BedLine.region_flag (0x1 = END_TO_END) */
+    int32_t prev_tid, prev_beg_pos, prev_end_pos;
+    int32_t contig_len;             /* target_len of tid */
+    int64_t read_begin, read_end;   /* slice of uvcgpu_reads_soa */
+} uvcgpu_tile;
+
+/* BAM records of all tiles of a batch, structure-of-arrays. For every tile the caller supplies what the reference
+ * fetches with sam_itr_queryi(tid, beg-2000, end+2000) (grouping.cpp:664, 730), in file order, already decoded:
+ * the fields of bam1_core_t, the NM aux tag (or -1), 4-bit packed bases, base qualities, CIGAR words, NUL-terminated qname.
+ * Offsets are in bytes (seq, qual, qname) or 32-bit words (cigar). */
+typedef struct uvcgpu_reads_soa {
+    int64_t n_reads;
+    const int32_t *pos, *mpos, *isize, *mtid, *l_qseq, *n_cigar, *nm;
+    const uint16_t *flag;
+    const uint8_t *mapq;
+    const uint64_t *seq_off, *qual_off, *cigar_off, *qname_off; /* n_reads + 1 entries each */
+    const uint8_t *seq;      /* (l_qseq+1)/2 bytes per read */
+    const uint8_t *qual;     /* l_qseq bytes per read */
+    const uint32_t *cigar;   /* n_cigar words per read */
+    const char *qname;       /* l_qname bytes per read incl. NUL */
+} uvcgpu_reads_soa;
+
+/* Per-position counter records, byte-compatible with the reference's structs so that a dump can be compared
+ * with the oracle by memcmp: SegFormatPrepSet (main_conversion.hpp:541-605, 208 B), SegFormatThresSet (:614-643, 72 B),
+ * SegFormatInfoSet (:645-691, 152 B), FamFormatInfoSet (:701-720, 72 B), RegionalTandemRepeat (common.hpp:150-160, 28 B). */
+typedef struct uvcgpu_prep_set {
+    int32_t a_dp, a_near_ins_dp, a_near_del_dp, a_near_RTR_ins_dp, a_near_RTR_del_dp;
+    int32_t a_pcr_dp, a_umi_dp, a_snv_dp, a_dnv_dp, a_highBQ_dp;
+    int32_t a_near_pcr_clip_dp, a_near_long_clip_dp, a_at_ins_dp, a_at_del_dp;
+    int32_t a_XM1500, a_GO1500, a_GAPLEN, a_qlen;
+    int64_t a_near_ins_pow2len, a_near_del_pow2len;
+    int32_t a_near_ins_inv100len, a_near_del_inv100len;
+    int64_t a_near_ins_l_pow2len, a_near_ins_r_pow2len, a_near_del_l_pow2len, a_near_del_r_pow2len;
+    int64_t a_LI; int32_t a_LIDP;
+    int64_t a_RI; int32_t a_RIDP;
+    int32_t a_l_dist_sum, a_r_dist_sum, a_inslen_sum, a_dellen_sum;
+    int64_t a_l_BAQ_sum, a_r_BAQ_sum, a_insBAQ_sum, a_delBAQ_sum;
+} uvcgpu_prep_set;
+
+typedef struct uvcgpu_thres_set {
+    int32_t aLPxT, aRPxT;
+    int32_t aLI1T, aLI2T, aRI1T, aRI2T, aLI1t, aLI2t, aRI1t, aRI2t;
+    int32_t aLP1t, aLP2t, aRP1t, aRP2t;
+    int32_t aLB1t, aLB2t, aRB1t, aRB2t;
+} uvcgpu_thres_set;
+
+typedef struct uvcgpu_seginfo_set {
+    int32_t a2XM2, a2BM2, aPF1, aPF2, aBQ2, aMQs, aP1, aP2, aP3, aNC;
+    int32_t aDPff, aDPfr, aDPrf, aDPrr;
+    int32_t aLP1, aLP2, aLPL, aRP1, aRP2, aRPL;
+    int32_t aLB1, aLB2; int64_t aLBL;
+    int32_t aRB1, aRB2; int64_t aRBL;
+    int32_t aLI1, aLI2, aRI1, aRI2, aRIf, aLIr;
+    int64_t aLIT, aRIT;
+} uvcgpu_seginfo_set;
+
+typedef struct uvcgpu_faminfo_set {
+    int32_t c2LP1, c2LP2, c2LPL, c2RP1, c2RP2, c2RPL, c2LP0, c2RP0;
+    int32_t c2LB1, c2LB2; int64_t c2LBL;
+    int32_t c2RB1, c2RB2; int64_t c2RBL;
+    int32_t c2BQ2;
+} uvcgpu_faminfo_set;
+
+typedef struct uvcgpu_rtr {
+    int32_t begpos, tracklen, unitlen, indelphred, anyTR_begpos, anyTR_tracklen, anyTR_unitlen;
+} uvcgpu_rtr;
+
+#define UVCGPU_NUM_FRAG_DEPTHS 3   /* FRAG_bDP, bTA, bTB (main_conversion.hpp:693-698) */
+#define UVCGPU_NUM_FAM_DEPTHS 8    /* FAM_cDP1, cDP12, cDP2, cDP3, cDPM, cDPm, cDP21, cDPD (:722-733) */
+#define UVCGPU_NUM_DUPLEX_DEPTHS 2 /* DUPLEX_dDP1, dDP2 (:736-740) */
+#define UVCGPU_NUM_VQ_TAGS 27      /* VQFormatTagSet (:743-782) */
+
+/* Sections of the per-position state that uvcgpu_dump_counters can return (element = one reference struct/array per
+ * position of the tile's extended range [ext_beg, ext_end)). */
+enum uvcgpu_section {
+    UVCGPU_SEC_META = 0,       /* int64[16]: see uvcgpu_tile_meta below */
+    UVCGPU_SEC_RTR = 1,        /* uvcgpu_rtr per position (after the threshold pass adjusted indelphred) */
+    UVCGPU_SEC_BAQ = 2,        /* int64 per position */
+    UVCGPU_SEC_BAQ2 = 3,
+    UVCGPU_SEC_PREP = 4,       /* uvcgpu_prep_set */
+    UVCGPU_SEC_THRES = 5,      /* uvcgpu_thres_set */
+    UVCGPU_SEC_SEGINFO = 6,    /* uvcgpu_seginfo_set[14] */
+    UVCGPU_SEC_FAMINFO = 7,    /* uvcgpu_faminfo_set[14] */
+    UVCGPU_SEC_FRAGDEPTH0 = 8, /* int32[14][3], strand 0 */
+    UVCGPU_SEC_FRAGDEPTH1 = 9,
+    UVCGPU_SEC_FAMDEPTH0 = 10, /* int32[14][8], strand 0 */
+    UVCGPU_SEC_FAMDEPTH1 = 11,
+    UVCGPU_SEC_DUPLEX = 12,    /* int32[14][2] */
+    UVCGPU_SEC_VQ = 13,        /* int32[14][27] */
+    UVCGPU_SEC_FAMILIES = 14,  /* text: family grouping, same format as the oracle harness */
+    UVCGPU_SEC_RTR_INITIAL = 15,
+    UVCGPU_NUM_SECTIONS
+};
+
+/* Per-tile scalars computed on the way (indices into the META section). */
+enum uvcgpu_tile_meta {
+    UVCGPU_META_NUM_PASSED = 0, UVCGPU_META_NUM_PCRPASSED = 1, UVCGPU_META_BAM_BEG = 2, UVCGPU_META_BAM_END = 3,
+    UVCGPU_META_RPOS_BEG = 4, UVCGPU_META_RPOS_END = 5, UVCGPU_META_EXT_BEG = 6, UVCGPU_META_EXT_END = 7,
+    UVCGPU_META_NUM_FAMILIES = 8
+};
+
+typedef struct uvcgpu_ctx uvcgpu_ctx;
+typedef int64_t uvcgpu_ticket;
+
+/* Throughput/timing record of one submitted batch (device times from CUDA events on the context's stream). */
+typedef struct uvcgpu_batch_stats {
+    int64_t n_tiles, n_reads_in, n_reads_kept, n_positions, n_ext_positions, n_families, n_fragments;
+    int64_t h2d_bytes, d2h_bytes, gpu_launches;
+    double host_prep_ms, h2d_ms, kernel_ms, d2h_ms;
+    double kernel_ms_by_stage[16];
+} uvcgpu_batch_stats;
+
+/* CommandLineArgs defaults (CmdLineArgs.hpp) with the Illumina inference applied (CmdLineArgs.cpp:127-134). */
+void uvcgpu_params_default(uvcgpu_params *p);
+
+/* Replaces the per-thread handle set-up of main() (main.cpp:1297-1319). device = CUDA ordinal. */
+int uvcgpu_create(uvcgpu_ctx **out, int device, const uvcgpu_params *params);
+void uvcgpu_destroy(uvcgpu_ctx *ctx);
+const char *uvcgpu_last_error(const uvcgpu_ctx *ctx);
+
+/* Replaces load_refstring/faidx_fetch_seq (main.cpp:54-70, 553): the contig's bases are uploaded once and stay in HBM.
+ * bases = ASCII, any case; NULL means "reference not available" (all 'n', main.cpp:57-59). */
+int uvcgpu_set_contig(uvcgpu_ctx *ctx, int32_t tid, const char *bases, int64_t len);
+
+/* Replaces the body of process_batch up to scoring for a batch of tiles (main.cpp:481-591:
+ * grouping.cpp:608-997 read filter + family grouping, :459-567 BQ fix-ups, main.hpp:803-874 repeat context,
+ * main.cpp:400-429 BAQ offsets, main.hpp:3665-3742 updateByRegion3Aln). Asynchronous on the context's stream. */
+int uvcgpu_submit(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, const uvcgpu_reads_soa *reads, uvcgpu_ticket *ticket);
+
+/* Waits for the batch; fills stats. */
+int uvcgpu_collect(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, uvcgpu_batch_stats *stats);
+
+/* Test hook: raw per-position arrays of one tile of a collected batch for bit-exact parity against the oracle.
+ * Returns the number of bytes the section needs in *needed; copies min(cap, needed) bytes into dst (dst may be NULL). */
+int uvcgpu_dump_counters(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_index, int32_t section, void *dst, size_t cap, size_t *needed);
+
+/* Frees the device/host state of a collected batch. */
+int uvcgpu_release(uvcgpu_ctx *ctx, uvcgpu_ticket ticket);
+
+int uvcgpu_device_count(void);
+
+/* sizeof(uvcgpu_params) as the library was compiled, so that foreign-language bindings can verify their mirror of the struct. */
+size_t uvcgpu_sizeof_params(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,54 @@
+"""Parity of the pileup stages against the oracle (the unmodified reference run through oracle/_ref/uvc_ref_dump).
+
+Bar: bit-exact (all sections are integer counters). The ``gpu`` tests run the CUDA path through the C ABI; the others
+run the same kernel bodies in the test-only emulation build so that the logic is covered in a container without a GPU.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+
+SECTIONS = ["meta", "families", "rtr_initial", "baq", "baq2", "prep", "thres", "rtr", "seginfo", "vq"]
+IMPLEMENTED_VQ_TAGS = 4   # VQ_a1BQf, a1BQr, a2BQf, a2BQr
+
+
+def _check(info, tiles, emulate, tmp_path, extra=()):
+    if not pu.have_oracle():
+        pytest.skip("oracle/_ref not built")
+    ours, stats = pu.run_tiles(info["bam"], info["fasta"], tiles, emulate, SECTIONS)
+    assert emulate or stats.gpu_launches > 0
+    prev = (-1, 0, 0)
+    for ti, (tid, beg, end, flag) in enumerate(tiles):
+        ref = pu.run_oracle_dump(info["bam"], info["fasta"], tid, beg, end, flag, str(tmp_path / ("t%d.dump" % ti)), prev, extra)
+        prev = (tid, beg, end)
+        o = ours[ti]
+        assert list(o["meta"][:9]) == list(ref["meta"][:9])
+        assert o["families"] == ref["families"]
+        ext_beg = int(ref["meta"][6])
+        msgs = []
+        for ours_name, ref_name in [("rtr_initial", "rtr_initial"), ("baq", "baq"), ("baq2", "baq2"), ("prep", "prep"),
+                                    ("thres", "thres"), ("rtr", "rtr_final"), ("seginfo", "seginfo")]:
+            msgs += pu.diff_section(ours_name, o[ours_name], ref[ref_name], ext_beg)
+        msgs += pu.diff_section("vq", o["vq"][:, :, :IMPLEMENTED_VQ_TAGS], ref["vq"][:, :, :IMPLEMENTED_VQ_TAGS], ext_beg)
+        assert not msgs, "\n".join(msgs[:40])
+    return stats
+
+
+def test_emulated_pileup_matches_oracle_small(synth_small, tmp_path):
+    _check(synth_small, [(0, 0, 6000, 4), (0, 6000, 11995, 2)], True, tmp_path)
+
+
+def test_emulated_pileup_matches_oracle_umi(synth_umi, tmp_path):
+    _check(synth_umi, [(0, 1000, 2500, 4), (0, 2500, 4000, 2)], True, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cuda_pileup_matches_oracle_small(synth_small, tmp_path):
+    _check(synth_small, [(0, 0, 6000, 4), (0, 6000, 11995, 2)], False, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cuda_pileup_matches_oracle_umi(synth_umi, tmp_path):
+    _check(synth_umi, [(0, 1000, 2500, 4), (0, 2500, 4000, 2)], False, tmp_path)

@@ -1,0 +1,154 @@
+// batch.h - data model of one submitted batch of tiles.
+//
+// HostBatch owns the host-side staging vectors; BatchView is the flat pointer view that the kernels read
+// (device pointers in the CUDA build, host pointers in the test-only emulation build).
+//
+// HBM layout: every per-position array is the concatenation of the tiles' extended ranges
+// [ext_beg, ext_end) (ext_end = the reference's extended_exclu_end_pos + 1, main.cpp:529-530, 569), so one
+// launch covers all tiles of the batch; per-position records are array-of-structs in the reference's own
+// struct layout (include/uvcgpu.h), which makes a dump comparable with the oracle by memcmp and makes the
+// write-out of a position a single contiguous burst.
+#ifndef UVC_BATCH_H_INCLUDED
+#define UVC_BATCH_H_INCLUDED
+
+#include "../../include/uvcgpu.h"
+
+#include <stdint.h>
+
+#define UVC_NSYM 14
+#define UVC_MAX_INSERT_SIZE 2000   // common.hpp:64
+#define UVC_MAX_STR_N_BASES 100    // common.hpp:63
+#define UVC_SQR_QUAL_DIV 32        // main_conversion.hpp:20
+#define UVC_NUM_BUCKETS 16         // main_conversion.hpp:920
+#define UVC_SLIP_MAXUNIT 8
+#define UVC_SLIP_NMAX 1024
+
+// BAM CIGAR operators
+#define UVC_CMATCH 0
+#define UVC_CINS 1
+#define UVC_CDEL 2
+#define UVC_CREF_SKIP 3
+#define UVC_CSOFT_CLIP 4
+#define UVC_CHARD_CLIP 5
+#define UVC_CPAD 6
+#define UVC_CEQUAL 7
+#define UVC_CDIFF 8
+
+struct TileInfo {
+    int32_t tid, beg_pos, end_pos;
+    uint32_t region_flag;
+    int32_t prev_tid, prev_beg_pos, prev_end_pos;
+    int32_t ext_beg, ext_end;        // per-position arrays cover [ext_beg, ext_end); refstring covers [ext_beg, ext_end - 1)
+    int32_t rpos_inclu_beg, rpos_exclu_end;
+    int32_t bam_inclu_beg, bam_exclu_end;
+    int64_t pos_off;                 // offset of ext_beg in the concatenated per-position arrays
+    int64_t read_off; int32_t n_reads;
+    int64_t frag_off; int32_t n_frags;
+    int64_t fam_off; int32_t n_fams;
+    int64_t num_passed, num_pcrpassed;
+    int32_t is_amplicon_inferred;    // !is_by_capture (main.cpp:510-511)
+    int32_t max_read_span;           // max(rend - pos) over the tile's kept reads
+    int32_t skipped;                 // process_batch returned -1 (main.cpp:520-523)
+};
+
+// Per kept read (BAM order inside a tile, i.e. sorted by pos).
+struct ReadRec {
+    int32_t pos, rend, mpos, isize;
+    int32_t l_qseq, n_cigar, nm;
+    uint16_t flag; uint8_t mapq; uint8_t strand;       // strand = bam_get_strand (common.hpp:90)
+    uint32_t dflag;                                    // duplexflag of its family (grouping.cpp:932)
+    int32_t tile;
+    int32_t frag, fam;                                 // batch-global fragment / family index
+    uint64_t seq_off, qual_off, cigar_off;             // into the packed blobs (bytes, bytes, words)
+    // read is "simple" if its CIGAR is [S|H] M [S|H] with a single M/=/X run
+    int32_t simple, m_qoff, cx_off;                    // cx_off: offset of its per-reference-base expansion (complex reads), -1 otherwise
+    int32_t ev_off, n_ev;                              // indel events of this read
+    int32_t fragprev_maxrend, famprev_maxrend;         // max rend over earlier reads of the same fragment / (family,strand); INT32_MIN if none
+};
+
+// Derived per-read constants (kernel K0).
+struct ReadDerived {
+    int32_t xm1500, go1500, avg_gaplen, nge_cnt, ngo_cnt, clip_cnt, lclip, rclip;
+    int32_t inslen_sum, dellen_sum, insbaq_sum, delbaq_sum;
+    int32_t bm1500[5];
+    int32_t micro_indel_penal, micro_nogap_penal;
+    int32_t ibeg, iend;                                // amplicon primer window (main.hpp:1872-1875)
+};
+
+// Per-reference-base expansion entry of a complex read: what the read shows at reference offset o = p - pos.
+struct CxEntry {
+    int32_t prev_rpos, next_rpos; // aligned bases: neighbouring entries of the low-quality-indel list (main.hpp:1902-1903);
+                                  // deleted bases: the distance passed for the BASE_NN / LINK_NN padding updates (main.hpp:2245)
+    int16_t qpos;      // query index of the aligned base, -1 if the reference base is deleted/skipped
+    uint8_t flags;     // bit0: M base; bit1: M base that is not the first of its run (i2 > 0); bit2: deleted base (D op)
+    uint8_t pad;
+};
+
+// One I or D cigar operation of a read, evaluated once (kernel K2e) and reused by all later walks.
+struct IndelEvent {
+    int32_t read, rpos, oplen, qpos;
+    int32_t is_del;
+    int32_t symbol;        // LINK_I1/I2/I3P/D1/D2/D3P
+    int32_t incvalue;      // value passed to inc()/dealwith_segbias (already MAX(1, incvalue))
+    int32_t incvalue2;     // count added to the inserted-sequence map (MAX(1, incvalue2))
+    int32_t counted;       // nbases2end >= indel_filter_edge_dist and not primer-masked
+    int32_t cigar_idx;
+};
+
+struct FragRec {
+    int32_t tile, fam, strand;
+    int32_t read_off, n_reads;     // into frag_reads
+    int32_t beg, end;              // fillTidBegEndFromAlns1 (main.hpp:659-673)
+    int32_t n_cov, n_near_mut;     // bTA / bTB numerators (main.hpp:2747-2756), kernel K3a
+    int32_t normMQ;
+};
+
+struct FamRec {
+    int32_t tile;
+    uint32_t duplexflag, dedup_idflag;
+    int32_t frag_off[2], n_frags[2];   // fragments of each strand, contiguous in frag order
+    int32_t beg2[2], end2[2];          // fillTidBegEndFromAlns2 per strand (main.hpp:675-685)
+    int32_t beg_both, end_both;        // over both strands (main.hpp:3378-3381)
+    int32_t l2r_end_median[2], r2l_end_median[2];
+    int32_t qlen_ok[2];                // alns2.size() >= fam_thres_dup1add && qseqlen_sum >= n_qseqs * fam_thres_qseqlen
+    int32_t nsb_min[2], nsb_max[2];    // no_strict_bias_pos_min/max (main.hpp:2959-2998), kernel K4a
+    int32_t beg_tid, beg_pos, end_tid, end_pos;
+};
+
+struct BatchView {
+    uvcgpu_params par;
+    double center_pow[4];          // pow(dedup_center_mult, d) computed with the host libm
+    int32_t indelphred_half;       // (int)round(numstates2phred(indel_del_to_ins_err_ratio)) / 2 (main.hpp:1244)
+    double ten_over_ln10;          // 10.0 / log(10.0) as the host libm evaluates it
+    const int32_t *slip_tab;       // [2][UVC_SLIP_MAXUNIT][UVC_SLIP_NMAX] indel_phred (main.hpp:794-801) evaluated with the host libm
+    int32_t n_tiles;
+    int64_t n_pos, n_reads, n_frags, n_fams, n_cx, n_ev;
+    const TileInfo *tiles;
+    const int32_t *pos_tile;       // tile of each concatenated position
+    // reference context
+    const uint8_t *refsym;         // AlignmentSymbol of the reference base (CHAR_TO_SYMBOL, main_conversion.hpp:473-486)
+    uvcgpu_rtr *rtr;
+    const int32_t *baq, *baq2;     // BAQ prefix sums (main.cpp:400-429); values fit 32 bits
+    // reads
+    const ReadRec *reads;
+    ReadDerived *rd;
+    const uint8_t *seq, *qual;
+    const uint32_t *cigar;
+    CxEntry *cx;
+    IndelEvent *ev;
+    const FragRec *frags_in; FragRec *frags;
+    const int32_t *frag_reads;
+    FamRec *fams;
+    // per-position state
+    uvcgpu_prep_set *prep;
+    uvcgpu_thres_set *thres;
+    uvcgpu_seginfo_set *seginfo;   // [n_pos][14]
+    int32_t *bqsum;                // [n_pos][14]  bg_seg_bqsum_conslogo (main.hpp:2566)
+    int32_t *vq;                   // [n_pos][14][27]
+    int32_t *fragdepth;            // [2][n_pos][14][3]
+    int32_t *famdepth;             // [2][n_pos][14][8]
+    uvcgpu_faminfo_set *faminfo;   // [n_pos][14]
+    int32_t *duplex;               // [n_pos][14][2]
+};
+
+#endif

@@ -1,0 +1,353 @@
+// bam_reader.cpp - BGZF/BAM/BAI and FASTA/FAI decoding into SoA buffers (see bam_reader.h).
+// Formats follow the SAM/BAM specification (sections 4.1 BGZF, 4.2 BAM, 5.2 BAI) and the samtools faidx five-column index.
+#include "bam_reader.h"
+
+#include <zlib.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace {
+
+const int kMaxBlock = 0x10000;
+
+struct BgzfIn {
+    FILE *fp = NULL;
+    std::vector<uint8_t> cbuf, ubuf;
+    int64_t block_addr = 0;   // compressed offset of the block in ubuf
+    int block_clen = 0;       // 0 = nothing loaded
+    int ulen = 0, uoff = 0;
+    z_stream zs;
+    bool zs_init = false;
+
+    // 0 ok, 1 end of file, -1 error
+    int load(int64_t caddr) {
+        uint8_t h[18];
+        if (fseeko(fp, caddr, SEEK_SET) != 0) { return -1; }
+        const size_t n = fread(h, 1, 18, fp);
+        if (0 == n) { block_addr = caddr; block_clen = 0; ulen = uoff = 0; return 1; }
+        if (n != 18 || h[0] != 31 || h[1] != 139 || !(h[3] & 4)) { return -1; }
+        const int xlen = h[10] | (h[11] << 8);
+        int bsize = -1;
+        cbuf.resize(kMaxBlock + 64);
+        memcpy(cbuf.data(), h + 12, 6);
+        if (xlen > 6 && fread(cbuf.data() + 6, 1, xlen - 6, fp) != (size_t)(xlen - 6)) { return -1; }
+        for (int off = 0; off + 4 <= xlen;) {
+            const int slen = cbuf[off + 2] | (cbuf[off + 3] << 8);
+            if (cbuf[off] == 'B' && cbuf[off + 1] == 'C' && slen == 2) { bsize = (cbuf[off + 4] | (cbuf[off + 5] << 8)) + 1; }
+            off += 4 + slen;
+        }
+        if (bsize < 0) { return -1; }
+        const int clen = bsize - 12 - xlen - 8;
+        if (fread(cbuf.data(), 1, clen + 8, fp) != (size_t)(clen + 8)) { return -1; }
+        ubuf.resize(kMaxBlock);
+        if (!zs_init) { memset(&zs, 0, sizeof(zs)); if (inflateInit2(&zs, -15) != Z_OK) { return -1; } zs_init = true; } else { inflateReset(&zs); }
+        zs.next_in = cbuf.data(); zs.avail_in = clen; zs.next_out = ubuf.data(); zs.avail_out = kMaxBlock;
+        if (inflate(&zs, Z_FINISH) != Z_STREAM_END) { return -1; }
+        ulen = (int)zs.total_out; uoff = 0; block_addr = caddr; block_clen = bsize;
+        return 0;
+    }
+    int seek(int64_t voff) {
+        const int64_t caddr = voff >> 16;
+        if (!(block_clen > 0 && block_addr == caddr)) { if (load(caddr) < 0) { return -1; } }
+        uoff = (int)(voff & 0xffff);
+        return 0;
+    }
+    // returns bytes read (less than n only at end of file), -1 on error
+    int64_t read(void *dst, int64_t n) {
+        uint8_t *out = (uint8_t*)dst;
+        int64_t done = 0;
+        while (done < n) {
+            if (uoff >= ulen) {
+                const int r = load(block_addr + block_clen);
+                if (r < 0) { return -1; }
+                if (r == 1) { break; }
+                if (0 == ulen) { continue; }
+            }
+            int64_t k = ulen - uoff;
+            if (k > n - done) { k = n - done; }
+            memcpy(out + done, ubuf.data() + uoff, (size_t)k);
+            uoff += (int)k; done += k;
+        }
+        return done;
+    }
+    ~BgzfIn() { if (zs_init) { inflateEnd(&zs); } if (fp) { fclose(fp); } }
+};
+
+inline uint32_t le32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+} // namespace
+
+struct uvchost_bam {
+    BgzfIn in;
+    std::vector<std::string> names;
+    std::vector<int64_t> lens;
+    std::vector<std::vector<uint64_t>> lidx;   // linear index per reference
+    int64_t first_record_voff = 0;
+    std::vector<uint8_t> rec;
+};
+
+struct uvchost_readbuf {
+    std::vector<int32_t> pos, mpos, isize, mtid, l_qseq, n_cigar, nm;
+    std::vector<uint16_t> flag;
+    std::vector<uint8_t> mapq;
+    std::vector<uint64_t> seq_off, qual_off, cigar_off, qname_off;
+    std::vector<uint8_t> seq, qual;
+    std::vector<uint32_t> cigar;
+    std::vector<char> qname;
+};
+
+struct uvchost_fasta {
+    FILE *fp = NULL;
+    struct Entry { int64_t len, offset; int32_t linebases, linewidth; };
+    std::map<std::string, Entry> entries;
+};
+
+extern "C" {
+
+uvchost_bam *uvchost_bam_open(const char *path) {
+    uvchost_bam *b = new uvchost_bam();
+    b->in.fp = fopen(path, "rb");
+    if (NULL == b->in.fp) { delete b; return NULL; }
+    uint8_t w[8];
+    if (b->in.seek(0) != 0 || b->in.read(w, 8) != 8 || memcmp(w, "BAM\1", 4) != 0) { delete b; return NULL; }
+    const int32_t l_text = (int32_t)le32(w + 4);
+    std::vector<char> text((size_t)l_text);
+    if (b->in.read(text.data(), l_text) != l_text || b->in.read(w, 4) != 4) { delete b; return NULL; }
+    const int32_t n_ref = (int32_t)le32(w);
+    for (int32_t i = 0; i < n_ref; i++) {
+        if (b->in.read(w, 4) != 4) { delete b; return NULL; }
+        const int32_t l_name = (int32_t)le32(w);
+        std::vector<char> nm((size_t)l_name);
+        if (b->in.read(nm.data(), l_name) != l_name || b->in.read(w, 4) != 4) { delete b; return NULL; }
+        b->names.push_back(std::string(nm.data()));
+        b->lens.push_back((int32_t)le32(w));
+    }
+    b->first_record_voff = (b->in.uoff >= b->in.ulen ? ((b->in.block_addr + b->in.block_clen) << 16) : ((b->in.block_addr << 16) | b->in.uoff));
+    // index: <path>.bai or <path minus .bam>.bai
+    std::string idx = std::string(path) + ".bai";
+    FILE *f = fopen(idx.c_str(), "rb");
+    if (NULL == f) {
+        std::string alt(path);
+        if (alt.size() > 4 && alt.substr(alt.size() - 4) == ".bam") { alt = alt.substr(0, alt.size() - 4) + ".bai"; f = fopen(alt.c_str(), "rb"); }
+    }
+    if (f) {
+        fseek(f, 0, SEEK_END);
+        const long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        std::vector<uint8_t> d((size_t)sz);
+        if (fread(d.data(), 1, (size_t)sz, f) == (size_t)sz && sz >= 8 && memcmp(d.data(), "BAI\1", 4) == 0) {
+            size_t o = 4;
+            const uint32_t nr = le32(&d[o]); o += 4;
+            b->lidx.resize(nr);
+            for (uint32_t r = 0; r < nr && o + 4 <= d.size(); r++) {
+                const uint32_t n_bin = le32(&d[o]); o += 4;
+                for (uint32_t bi = 0; bi < n_bin; bi++) { const uint32_t n_chunk = le32(&d[o + 4]); o += 8 + (size_t)n_chunk * 16; }
+                const uint32_t n_intv = le32(&d[o]); o += 4;
+                b->lidx[r].resize(n_intv);
+                for (uint32_t i = 0; i < n_intv; i++) { b->lidx[r][i] = (uint64_t)le32(&d[o]) | ((uint64_t)le32(&d[o + 4]) << 32); o += 8; }
+            }
+        }
+        fclose(f);
+    }
+    return b;
+}
+
+void uvchost_bam_close(uvchost_bam *b) { delete b; }
+int32_t uvchost_bam_n_targets(const uvchost_bam *b) { return (int32_t)b->names.size(); }
+const char *uvchost_bam_target_name(const uvchost_bam *b, int32_t tid) { return b->names[tid].c_str(); }
+int64_t uvchost_bam_target_len(const uvchost_bam *b, int32_t tid) { return b->lens[tid]; }
+
+uvchost_readbuf *uvchost_readbuf_new(void) {
+    uvchost_readbuf *rb = new uvchost_readbuf();
+    uvchost_readbuf_clear(rb);
+    return rb;
+}
+void uvchost_readbuf_free(uvchost_readbuf *rb) { delete rb; }
+void uvchost_readbuf_clear(uvchost_readbuf *rb) {
+    rb->pos.clear(); rb->mpos.clear(); rb->isize.clear(); rb->mtid.clear(); rb->l_qseq.clear(); rb->n_cigar.clear(); rb->nm.clear();
+    rb->flag.clear(); rb->mapq.clear();
+    rb->seq_off.assign(1, 0); rb->qual_off.assign(1, 0); rb->cigar_off.assign(1, 0); rb->qname_off.assign(1, 0);
+    rb->seq.clear(); rb->qual.clear(); rb->cigar.clear(); rb->qname.clear();
+}
+int64_t uvchost_readbuf_size(const uvchost_readbuf *rb) { return (int64_t)rb->pos.size(); }
+void uvchost_readbuf_view(const uvchost_readbuf *rb, uvcgpu_reads_soa *out) {
+    out->n_reads = (int64_t)rb->pos.size();
+    out->pos = rb->pos.data(); out->mpos = rb->mpos.data(); out->isize = rb->isize.data(); out->mtid = rb->mtid.data();
+    out->l_qseq = rb->l_qseq.data(); out->n_cigar = rb->n_cigar.data(); out->nm = rb->nm.data();
+    out->flag = rb->flag.data(); out->mapq = rb->mapq.data();
+    out->seq_off = rb->seq_off.data(); out->qual_off = rb->qual_off.data(); out->cigar_off = rb->cigar_off.data(); out->qname_off = rb->qname_off.data();
+    out->seq = rb->seq.data(); out->qual = rb->qual.data(); out->cigar = rb->cigar.data(); out->qname = rb->qname.data();
+}
+
+} // extern "C"
+
+namespace {
+
+struct Core { int32_t tid, pos, l_qname, mapq, n_cigar, flag, l_qseq, mtid, mpos, isize, endpos; };
+
+// reads the next record into b->rec; returns 1 ok, 0 end of file, -1 error
+int next_record(uvchost_bam *b, Core & c) {
+    uint8_t w[4];
+    const int64_t n = b->in.read(w, 4);
+    if (0 == n) { return 0; }
+    if (n != 4) { return -1; }
+    const int32_t bs = (int32_t)le32(w);
+    if (bs < 32) { return -1; }
+    b->rec.resize((size_t)bs);
+    if (b->in.read(b->rec.data(), bs) != bs) { return -1; }
+    const uint8_t *x = b->rec.data();
+    c.tid = (int32_t)le32(x); c.pos = (int32_t)le32(x + 4);
+    c.l_qname = x[8]; c.mapq = x[9];
+    c.n_cigar = x[12] | (x[13] << 8); c.flag = x[14] | (x[15] << 8);
+    c.l_qseq = (int32_t)le32(x + 16); c.mtid = (int32_t)le32(x + 20); c.mpos = (int32_t)le32(x + 24); c.isize = (int32_t)le32(x + 28);
+    int64_t rlen = 0;
+    if (!(c.flag & 4)) {
+        const uint8_t *cg = x + 32 + c.l_qname;
+        for (int k = 0; k < c.n_cigar; k++) {
+            const uint32_t v = le32(cg + 4 * k);
+            const int op = v & 0xf;
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) { rlen += v >> 4; }
+        }
+    }
+    if (0 == rlen) { rlen = 1; }
+    c.endpos = (int32_t)(c.pos + rlen);
+    return 1;
+}
+
+void append_record(uvchost_readbuf *rb, const uvchost_bam *b, const Core & c) {
+    const uint8_t *x = b->rec.data();
+    const size_t total = b->rec.size();
+    rb->pos.push_back(c.pos); rb->mpos.push_back(c.mpos); rb->isize.push_back(c.isize); rb->mtid.push_back(c.mtid);
+    rb->l_qseq.push_back(c.l_qseq); rb->n_cigar.push_back(c.n_cigar); rb->flag.push_back((uint16_t)c.flag); rb->mapq.push_back((uint8_t)c.mapq);
+    const uint8_t *qn = x + 32;
+    const uint8_t *cg = qn + c.l_qname;
+    const uint8_t *sq = cg + 4 * (size_t)c.n_cigar;
+    const uint8_t *ql = sq + (size_t)((c.l_qseq + 1) / 2);
+    const uint8_t *aux = ql + c.l_qseq;
+    rb->qname.insert(rb->qname.end(), (const char*)qn, (const char*)qn + c.l_qname);
+    for (int k = 0; k < c.n_cigar; k++) { rb->cigar.push_back(le32(cg + 4 * k)); }
+    rb->seq.insert(rb->seq.end(), sq, ql);
+    rb->qual.insert(rb->qual.end(), ql, aux);
+    rb->qname_off.push_back(rb->qname.size()); rb->cigar_off.push_back(rb->cigar.size());
+    rb->seq_off.push_back(rb->seq.size()); rb->qual_off.push_back(rb->qual.size());
+    // NM aux tag (bam_aux_get + bam_aux2i); -1 if absent
+    int32_t nm = -1;
+    const uint8_t *end = x + total;
+    const uint8_t *s = aux;
+    while (end - s >= 3) {
+        const bool hit = (s[0] == 'N' && s[1] == 'M');
+        const uint8_t type = s[2];
+        const uint8_t *val = s + 3;
+        int sz = 0;
+        if (type == 'A' || type == 'c' || type == 'C') { sz = 1; } else if (type == 's' || type == 'S') { sz = 2; }
+        else if (type == 'i' || type == 'I' || type == 'f') { sz = 4; } else if (type == 'd') { sz = 8; }
+        if (sz) {
+            if (hit) {
+                if (type == 'c') { nm = (int8_t)val[0]; } else if (type == 'C') { nm = val[0]; }
+                else if (type == 's') { nm = (int16_t)(val[0] | (val[1] << 8)); } else if (type == 'S') { nm = (uint16_t)(val[0] | (val[1] << 8)); }
+                else if (type == 'i' || type == 'I') { nm = (int32_t)le32(val); } else { nm = 0; }
+                break;
+            }
+            s = val + sz;
+        } else if (type == 'Z' || type == 'H') {
+            if (hit) { nm = 0; break; }
+            s = val;
+            while (s < end && *s) { s++; }
+            s++;
+        } else if (type == 'B') {
+            if (end - val < 5) { break; }
+            const uint8_t st = val[0];
+            const int esz = ((st == 'c' || st == 'C') ? 1 : ((st == 's' || st == 'S') ? 2 : 4));
+            s = val + 5 + (size_t)esz * le32(val + 1);
+        } else {
+            break;
+        }
+    }
+    rb->nm.push_back(nm);
+}
+
+} // namespace
+
+extern "C" {
+
+int64_t uvchost_bam_fetch(uvchost_bam *b, int32_t tid, int64_t beg, int64_t end, uvchost_readbuf *rb) {
+    if (beg < 0) { beg = 0; }
+    if (tid < 0 || (size_t)tid >= b->lidx.size() || beg >= end) { return 0; }
+    const std::vector<uint64_t> & l = b->lidx[tid];
+    size_t w = (size_t)(beg >> 14);
+    while (w < l.size() && 0 == l[w]) { w++; }
+    if (w >= l.size()) { return 0; }
+    if (b->in.seek((int64_t)l[w]) != 0) { return -1; }
+    int64_t n = 0;
+    Core c;
+    for (;;) {
+        const int r = next_record(b, c);
+        if (r < 0) { return -1; }
+        if (0 == r) { break; }
+        if (c.tid != tid || c.pos >= end) {
+            if (c.tid >= 0 && c.tid < tid) { continue; }
+            break;
+        }
+        if (c.endpos > beg) { append_record(rb, b, c); n++; }
+    }
+    return n;
+}
+
+int uvchost_bam_scan(uvchost_bam *b, uvchost_scan_cb cb, void *user) {
+    if (b->in.seek(b->first_record_voff) != 0) { return -1; }
+    Core c;
+    for (;;) {
+        const int r = next_record(b, c);
+        if (r < 0) { return -1; }
+        if (0 == r) { break; }
+        if (cb(c.tid, c.pos, c.endpos, (uint16_t)c.flag, c.isize, c.l_qseq, (uint8_t)c.mapq, user)) { break; }
+    }
+    return 0;
+}
+
+uvchost_fasta *uvchost_fasta_open(const char *path) {
+    const std::string fai = std::string(path) + ".fai";
+    FILE *fi = fopen(fai.c_str(), "r");
+    if (NULL == fi) { return NULL; }
+    uvchost_fasta *f = new uvchost_fasta();
+    f->fp = fopen(path, "rb");
+    if (NULL == f->fp) { fclose(fi); delete f; return NULL; }
+    char line[4096];
+    while (fgets(line, sizeof(line), fi)) {
+        char name[2048];
+        long long len, off; int lb, lw;
+        if (sscanf(line, "%2047s\t%lld\t%lld\t%d\t%d", name, &len, &off, &lb, &lw) == 5) {
+            uvchost_fasta::Entry e; e.len = len; e.offset = off; e.linebases = lb; e.linewidth = lw;
+            f->entries[name] = e;
+        }
+    }
+    fclose(fi);
+    return f;
+}
+
+void uvchost_fasta_close(uvchost_fasta *f) { if (f) { if (f->fp) { fclose(f->fp); } delete f; } }
+
+char *uvchost_fasta_fetch_contig(uvchost_fasta *f, const char *name, int64_t *len) {
+    auto it = f->entries.find(name);
+    if (it == f->entries.end()) { *len = 0; return NULL; }
+    const uvchost_fasta::Entry & e = it->second;
+    char *out = (char*)malloc((size_t)e.len + 1);
+    const int64_t nlines = (e.len + e.linebases - 1) / e.linebases;
+    const int64_t nbytes = e.len + nlines * (e.linewidth - e.linebases);
+    std::vector<char> raw((size_t)nbytes + 16);
+    fseeko(f->fp, e.offset, SEEK_SET);
+    const size_t got = fread(raw.data(), 1, (size_t)nbytes, f->fp);
+    int64_t k = 0;
+    for (size_t i = 0; i < got && k < e.len; i++) { if ((unsigned char)raw[i] > ' ') { out[k++] = raw[i]; } }
+    out[k] = 0;
+    *len = k;
+    return out;
+}
+
+} // extern "C"

@@ -1,0 +1,50 @@
+// bam_reader.h - host-side input substrate of the B200 uvc1 host: BGZF/BAM/BAI and FASTA/FAI readers that decode
+// straight into the structure-of-arrays record layout of include/uvcgpu.h (uvcgpu_reads_soa).
+// Replaces the reference's use of htslib (sam_open/sam_hdr_read/sam_index_load/sam_itr_queryi/sam_itr_next,
+// grouping.cpp:179-193, 664-666, 730-731; fai_load/faidx_fetch_seq, main.cpp:54-70).
+#ifndef UVC_BAM_READER_H_INCLUDED
+#define UVC_BAM_READER_H_INCLUDED
+
+#include "../../../include/uvcgpu.h"
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct uvchost_bam uvchost_bam;
+typedef struct uvchost_readbuf uvchost_readbuf;
+typedef struct uvchost_fasta uvchost_fasta;
+
+uvchost_bam *uvchost_bam_open(const char *path);          /* also loads <path>.bai */
+void uvchost_bam_close(uvchost_bam *b);
+int32_t uvchost_bam_n_targets(const uvchost_bam *b);
+const char *uvchost_bam_target_name(const uvchost_bam *b, int32_t tid);
+int64_t uvchost_bam_target_len(const uvchost_bam *b, int32_t tid);
+
+uvchost_readbuf *uvchost_readbuf_new(void);
+void uvchost_readbuf_free(uvchost_readbuf *rb);
+void uvchost_readbuf_clear(uvchost_readbuf *rb);
+int64_t uvchost_readbuf_size(const uvchost_readbuf *rb);
+/* Fills out with pointers into rb (valid until the next append/clear/free). */
+void uvchost_readbuf_view(const uvchost_readbuf *rb, uvcgpu_reads_soa *out);
+
+/* Appends, in file order, every record with this tid, pos < end and bam_endpos > beg (the records htslib's
+ * sam_itr_queryi(idx, tid, beg, end) iterates). Returns the number appended or a negative error. */
+int64_t uvchost_bam_fetch(uvchost_bam *b, int32_t tid, int64_t beg, int64_t end, uvchost_readbuf *rb);
+
+/* Sequential scan of core fields (for the region tiler): calls cb(tid, pos, endpos, flag, isize, user) for every record in file order
+ * until cb returns non-zero or the file ends. */
+typedef int (*uvchost_scan_cb)(int32_t tid, int32_t pos, int32_t endpos, uint16_t flag, int32_t isize, int32_t l_qseq, uint8_t mapq, void *user);
+int uvchost_bam_scan(uvchost_bam *b, uvchost_scan_cb cb, void *user);
+
+uvchost_fasta *uvchost_fasta_open(const char *path);      /* needs <path>.fai */
+void uvchost_fasta_close(uvchost_fasta *f);
+/* Returns a malloc'ed buffer with the whole sequence of the named contig (caller frees), length in *len; NULL if absent. */
+char *uvchost_fasta_fetch_contig(uvchost_fasta *f, const char *name, int64_t *len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

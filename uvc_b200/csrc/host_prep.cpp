@@ -1,0 +1,601 @@
+// host_prep.cpp - host-side staging of a batch of tiles.
+//
+// Stage P0 (read filter, dedup centres, family key, grouping) restates reference grouping.cpp:347-442, 608-997
+// and MolecularID.hpp:20-69 with sort-based containers; the base-quality fix-ups restate grouping.cpp:459-543;
+// stage P1 (repeat context, BAQ offsets) restates main.hpp:699-721, 794-874 and main.cpp:400-429.
+// Reference quirks that change results are kept on purpose and marked QUIRK.
+#include "host_prep.h"
+
+#include <algorithm>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <unordered_set>
+
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace {
+
+const int ARRPOS_MARGIN = UVC_MAX_INSERT_SIZE;   // grouping.cpp:22
+const int ARRPOS_OUTER_RANGE = 10;               // grouping.cpp:23
+const int ARRPOS_INNER_RANGE = 3;                // grouping.cpp:24
+
+inline int64_t nnminus(int64_t a, int64_t b) { return (a > b ? a - b : 0); }
+
+inline int cigar_op(uint32_t c) { return (int)(c & 0xf); }
+inline int cigar_len(uint32_t c) { return (int)(c >> 4); }
+inline bool op_consumes_ref(int op) { return op == UVC_CMATCH || op == UVC_CDEL || op == UVC_CREF_SKIP || op == UVC_CEQUAL || op == UVC_CDIFF; }
+inline bool op_is_match(int op) { return op == UVC_CMATCH || op == UVC_CEQUAL || op == UVC_CDIFF; }
+
+struct Raw {
+    int32_t pos, rend, mpos, isize, mtid, l_qseq, n_cigar, nm;
+    uint16_t flag; uint8_t mapq;
+    const uint8_t *seq, *qual; const uint32_t *cigar; const char *qname;
+};
+
+inline Raw get_raw(const uvcgpu_reads_soa & rs, int64_t i) {
+    Raw r;
+    r.pos = rs.pos[i]; r.mpos = rs.mpos[i]; r.isize = rs.isize[i]; r.mtid = rs.mtid[i];
+    r.l_qseq = rs.l_qseq[i]; r.n_cigar = rs.n_cigar[i]; r.nm = rs.nm[i]; r.flag = rs.flag[i]; r.mapq = rs.mapq[i];
+    r.seq = rs.seq + rs.seq_off[i]; r.qual = rs.qual + rs.qual_off[i]; r.cigar = rs.cigar + rs.cigar_off[i]; r.qname = rs.qname + rs.qname_off[i];
+    // bam_endpos: reference length of the alignment, 1 if it is zero or the read is unmapped
+    int64_t rlen = 0;
+    if (!(r.flag & 0x4)) { for (int k = 0; k < r.n_cigar; k++) { if (op_consumes_ref(cigar_op(r.cigar[k]))) { rlen += cigar_len(r.cigar[k]); } } }
+    if (0 == rlen) { rlen = 1; }
+    r.rend = (int32_t)(r.pos + rlen);
+    // NORM_INSERT_SIZE (common.hpp:75)
+    if (abs(r.isize) >= UVC_MAX_INSERT_SIZE) { r.isize = 0; }
+    return r;
+}
+
+inline int read_strand(uint16_t flag) { return (((flag & 0x81) == 0x81) ? (!!(flag & 0x20)) : (!!(flag & 0x10))); }
+
+enum Filt { KEEP, NOT_MAPPED, NOT_PRIMARY, LOW_MAPQ, LOW_ALN_LEN, LOW_ISIZE, HIGH_ISIZE, ZERO_ISIZE, OUT_OF_RANGE, NOT_END_TO_END };
+
+// grouping.cpp:347-415
+Filt classify(bool & isrc, bool & isr2, int32_t & tBeg, int32_t & tEnd, const Raw & r, int32_t fetch_tbeg, int32_t fetch_tend,
+        const uvcgpu_params & par, bool end2end, bool pem) {
+    if (r.flag & 0x4) { return NOT_MAPPED; }
+    if (r.flag & 0x900) { return NOT_PRIMARY; }
+    // QUIRK: the reference's call sites pass (min_aln_len, min_mapqual) in swapped order (grouping.cpp:676-677 vs :351-352)
+    const int32_t min_mapqual = par.kept_aln_min_aln_len;
+    const int32_t min_aln_len = par.kept_aln_min_mapqual;
+    if ((int32_t)r.mapq < min_mapqual) { return LOW_MAPQ; }
+    if ((r.rend - r.pos) < min_aln_len) { return LOW_ALN_LEN; }
+    if (0 == r.isize) {
+        if (par.kept_aln_is_zero_isize_discarded) { return ZERO_ISIZE; }
+    } else {
+        if (abs(r.isize) < par.kept_aln_min_isize) { return LOW_ISIZE; }
+        if (abs(r.isize) > par.kept_aln_max_isize) { return HIGH_ISIZE; }
+    }
+    isrc = ((r.flag & 0x10) == 0x10);
+    isr2 = ((r.flag & 0x80) == 0x80 && (r.flag & 0x1) == 0x1);
+    if (!pem) { isr2 = false; }
+    const int32_t begpos = r.pos, endpos = r.rend - 1;
+    if ((!pem) || ((r.flag & 0x1) == 0) || (r.flag & 0x8) || (0 == r.isize) || (abs(r.isize) >= ARRPOS_MARGIN)) {
+        tBeg = (isrc ? endpos : begpos);
+        tEnd = (isrc ? begpos : endpos);
+    } else {
+        const int32_t b1 = std::min(begpos, r.mpos);
+        const int32_t e1 = b1 + abs(r.isize) - 1;
+        const bool strand = read_strand(r.flag);
+        tBeg = (strand ? e1 : b1);
+        tEnd = (strand ? b1 : e1);
+    }
+    const int32_t ob = std::min(tBeg, tEnd), oe = std::max(tBeg, tEnd);
+    if (ob + (ARRPOS_MARGIN - ARRPOS_OUTER_RANGE) <= fetch_tbeg || fetch_tend - 1 + (ARRPOS_MARGIN - ARRPOS_OUTER_RANGE) <= oe) { return OUT_OF_RANGE; }
+    if (end2end && !(ob <= fetch_tbeg && oe >= fetch_tend)) { return NOT_END_TO_END; }
+    return KEEP;
+}
+
+// grouping.cpp:422-442; pos_to_center_pos starts as all zeros, exactly like the reference's inicount copy
+void snap_to_centers(std::vector<int32_t> & center, const std::vector<int32_t> & cnt, const double *center_pow) {
+    const int32_t n = (int32_t)cnt.size();
+    for (int32_t lo = ARRPOS_INNER_RANGE; lo < n - ARRPOS_INNER_RANGE; lo++) {
+        const int32_t lo_cnt = cnt[lo];
+        center[lo] = lo;
+        int32_t max_cnt = lo_cnt;
+        for (int32_t hi = lo - ARRPOS_INNER_RANGE; hi < lo + ARRPOS_INNER_RANGE + 1; hi++) {
+            const int32_t hi_cnt = cnt[hi];
+            const int d = abs(lo - hi);
+            if ((hi_cnt > max_cnt) && ((hi_cnt + 1) > (lo_cnt + 1) * center_pow[d])) {
+                center[lo] = hi;
+                max_cnt = hi_cnt;
+            }
+        }
+    }
+}
+
+inline uint64_t str_hash(const char *s, uint64_t base) {
+    uint64_t h = 0;
+    for (size_t i = 0; s[i]; i++) { h = h * base + (uint64_t)(int64_t)s[i]; }
+    return h;
+}
+
+typedef std::pair<int32_t, int32_t> tidpos_t;
+
+struct FamKey {
+    tidpos_t beg, end;
+    std::string qname, umi;
+    uint32_t duplexflag, dedup_idflag;
+    bool operator<(const FamKey & o) const { // MolecularID.hpp:52-68 (the hash tie-break can never decide: equal fields give equal hashes)
+        if (beg != o.beg) { return beg < o.beg; }
+        if (end != o.end) { return end < o.end; }
+        if (qname != o.qname) { return qname < o.qname; }
+        if (umi != o.umi) { return umi < o.umi; }
+        if (duplexflag != o.duplexflag) { return duplexflag < o.duplexflag; }
+        return dedup_idflag < o.dedup_idflag;
+    }
+    bool operator==(const FamKey & o) const {
+        return beg == o.beg && end == o.end && qname == o.qname && umi == o.umi && duplexflag == o.duplexflag && dedup_idflag == o.dedup_idflag;
+    }
+};
+
+struct Kept {
+    int64_t raw;          // index into the caller's SoA
+    Raw r;
+    FamKey key;
+    std::string umi_full;
+    tidpos_t begpair, endpair;   // the read's own (non-key) MolecularBarcode ends
+    int strand;
+    uint64_t qhash2;
+    int32_t fam_local, frag_local;
+};
+
+// grouping.cpp:459-543 on a private copy of the qualities
+void fix_base_qualities(uint8_t *q, const Raw & r, const uvcgpu_params & par) {
+    const int32_t l = r.l_qseq;
+    if ((0 == l) || (r.flag & 0x4)) { return; }
+    for (int32_t i = 0; i < l; i++) { q[i] = (uint8_t)std::min((int32_t)q[i] + par.assay_sequencing_BQ_inc, par.assay_sequencing_BQ_max); }
+    const int isrc = ((r.flag & 0x10) ? 1 : 0);
+    int32_t inclu_beg[2] = {0, l - 1};
+    int32_t exclu_end[2] = {l, -1};
+    int32_t end_clip_len = 0;
+    if (r.n_cigar > 0) {
+        uint32_t c = r.cigar[0];
+        if (cigar_op(c) == UVC_CSOFT_CLIP) {
+            if (0 == isrc) { inclu_beg[0] += cigar_len(c); } else { exclu_end[1] += cigar_len(c); end_clip_len = cigar_len(c); }
+        }
+        c = r.cigar[r.n_cigar - 1];
+        if (cigar_op(c) == UVC_CSOFT_CLIP) {
+            if (1 == isrc) { inclu_beg[1] -= cigar_len(c); } else { exclu_end[0] -= cigar_len(c); end_clip_len = cigar_len(c); }
+        }
+    }
+    const int32_t inc = (isrc ? -1 : 1);
+    auto seqi = [&](int32_t i) { return (int)((r.seq[i >> 1] >> ((~i & 1) << 2)) & 0xf); };
+    {   // 3'-tail penalty: long end clip and/or homopolymer-like tail until the 2nd distinct high-quality base
+        int prev_b = 0;
+        int distinct = 0;
+        const int32_t start = exclu_end[isrc] - inc;
+        int32_t termpos = start;
+        for (; termpos != inclu_beg[isrc] - inc; termpos -= inc) {
+            const int b = seqi(termpos);
+            if (b != prev_b && q[termpos] >= 20) {
+                prev_b = b;
+                distinct++;
+                if (2 == distinct) { break; }
+            }
+        }
+        const int32_t tracklen = abs(termpos - start);
+        const int32_t tail_penal = (end_clip_len >= 20 ? 1 : 0) + (tracklen >= 15 ? 2 : (tracklen >= 10 ? 1 : 0));
+        if (tail_penal > 0) {
+            for (int32_t p = start; p != (inclu_beg[isrc] - inc) && p != termpos; p -= inc) {
+                q[p] = (uint8_t)(std::max((int32_t)q[p], tail_penal + 1) - tail_penal);
+            }
+        }
+    }
+    {   // poly-G (>= 4) minus one
+        int32_t homopol = 0;
+        int prev_b = 0;
+        for (int32_t p = inclu_beg[isrc]; p != exclu_end[isrc]; p += inc) {
+            const int b = seqi(p);
+            if (b == prev_b) {
+                homopol++;
+                if (homopol >= 4 && b == 4 /* nt16 code of G */) { q[p] = (uint8_t)(std::max((int32_t)q[p], 2) - 1); }
+            } else {
+                prev_b = b;
+                homopol = 1;
+            }
+        }
+    }
+}
+
+// main.hpp:699-721. QUIRK: rank2 is computed with rulen1 when rc2 <= 1.
+bool more_str(int32_t rulen1, int32_t rc1, int32_t rulen2, int32_t rc2, int32_t repeatsize_max) {
+    if (rulen2 * rc2 == 0) { return true; }
+    if (rulen1 > repeatsize_max || rulen2 > repeatsize_max) { return (rulen1 < rulen2 || (rulen1 == rulen2 && rc1 > rc2)); }
+    int rank1 = (rc1 <= 1 ? (-rc1 * rulen1) : ((rc1 - 1) * rulen1));
+    int rank2 = (rc2 <= 1 ? (-rc2 * rulen1) : ((rc2 - 1) * rulen2));
+    if (0 == rc1 || 0 == rulen1) { rank1 = -100; }
+    if (0 == rc2 || 0 == rulen2) { rank2 = -100; }
+    return rank1 > rank2;
+}
+
+// main.hpp:794-801 with prob2phred (main_conversion.hpp:890-893)
+int32_t slip_phred(double ampfact, int32_t unit, int32_t nunits) {
+    const int32_t region = unit * nunits;
+    const double num_slips = (region > 64 ? (double)(region - 8) : log1p(exp((double)region - (double)8))) * ampfact / ((double)(unit * unit));
+    return (int32_t)floor(-10 * log((1.0 - DBL_EPSILON) / (num_slips + 1.0)) / log(10));
+}
+
+// main.hpp:803-874: best short-tandem-repeat (unit <= str_max) and any-tandem-repeat (unit <= vntr_max) track per reference base
+void repeat_context(std::vector<uvcgpu_rtr> & out, const char *ref, int32_t n, const uvcgpu_params & par) {
+    out.assign((size_t)n + 1, uvcgpu_rtr());
+    for (auto & t : out) { t.begpos = 0; t.tracklen = 0; t.unitlen = 0; t.indelphred = par.indel_BQ_max; t.anyTR_begpos = 0; t.anyTR_tracklen = 0; t.anyTR_unitlen = 0; }
+    const int32_t str_max = par.indel_str_repeatsize_max, vntr_max = par.indel_vntr_repeatsize_max;
+    for (int32_t refpos = 0; refpos < n;) {
+        int32_t best_unit = 0, best_num = 0, best_end = refpos;
+        int32_t any_unit = 0, any_num = 0, any_end = refpos;
+        for (int32_t unit = 1; unit <= vntr_max; unit++) {
+            int32_t q = refpos;
+            while (q + unit < n && ref[q] == ref[q + unit]) { q++; }
+            const int32_t num = (q - refpos) / unit + 1;
+            if (unit <= str_max && more_str(unit, num, best_unit, best_num, str_max)) { best_unit = unit; best_num = num; best_end = q + unit; }
+            if (more_str(unit, num, any_unit, any_num, vntr_max)) { any_unit = unit; any_num = num; any_end = q + unit; }
+        }
+        {
+            const int32_t stop = std::min(best_end, n);
+            const int32_t tl = stop - refpos;
+            const int32_t dec = slip_phred(par.indel_polymerase_slip_rate * par.indel_del_to_ins_err_ratio, best_unit, tl / best_unit);
+            for (int32_t i = refpos; i != stop; i++) {
+                if (tl > out[i].tracklen) {
+                    out[i].begpos = refpos; out[i].tracklen = tl; out[i].unitlen = best_unit;
+                    out[i].indelphred = par.indel_BQ_max - std::min(par.indel_BQ_max - 1, dec);
+                }
+            }
+        }
+        {
+            const int32_t stop = std::min(any_end, n);
+            const int32_t tl = stop - refpos;
+            for (int32_t i = refpos; i != stop; i++) {
+                if (tl > out[i].anyTR_tracklen) { out[i].anyTR_begpos = refpos; out[i].anyTR_tracklen = tl; out[i].anyTR_unitlen = any_unit; }
+            }
+        }
+        const int32_t nb = str_max + best_unit;
+        refpos += std::max(best_unit * best_num, nb + 1) - nb;
+    }
+    if (n > 0) { out[n] = out[n - 1]; }
+}
+
+// main.cpp:400-429. QUIRK: the any-tandem-repeat variant still divides by the STR unit length.
+void baq_prefix(std::vector<int32_t> & dst, size_t off, const std::vector<uvcgpu_rtr> & rtr, bool any_tr, const uvcgpu_params & par) {
+    int64_t sum = 0;
+    const int32_t polsize = (int32_t)round(par.indel_polymerase_size);
+    for (size_t i = 0; i < rtr.size(); i++) {
+        const int32_t tl = (any_tr ? rtr[i].anyTR_tracklen : rtr[i].tracklen);
+        const int32_t ul = rtr[i].unitlen;
+        if (tl / ul >= 3 || (tl / ul >= 2 && tl >= polsize)) {
+            sum += (par.indel_str_phred_per_region * 10) / tl + 1;
+        } else {
+            sum += par.indel_nonSTR_phred_per_base * 10;
+        }
+        dst[off + i] = (int32_t)sum;
+    }
+    for (size_t i = 0; i < rtr.size(); i++) { dst[off + i] = (int32_t)((int64_t)dst[off + i] / 10); }
+}
+
+inline uint8_t char_to_symbol(char c) { // CHAR_TO_SYMBOL (main_conversion.hpp:473-486)
+    switch (c) {
+        case 'A': case 'a': return UVC_BASE_A;
+        case 'C': case 'c': return UVC_BASE_C;
+        case 'G': case 'g': return UVC_BASE_G;
+        case 'T': case 't': return UVC_BASE_T;
+        case 'I': case 'i': return UVC_LINK_M;
+        case '-': case '_': return UVC_LINK_D1;
+        default: return UVC_BASE_N;
+    }
+}
+
+} // namespace
+
+void uvc_fill_view_constants(BatchView & v, const uvcgpu_params & par) {
+    v.par = par;
+    for (int d = 0; d < 4; d++) { v.center_pow[d] = pow(par.dedup_center_mult, (double)d); }
+    v.indelphred_half = ((int32_t)round((10.0 / log(10.0)) * log(par.indel_del_to_ins_err_ratio))) / 2;
+}
+
+int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::map<int32_t, HostContig> & contigs,
+        int32_t n_tiles, const uvcgpu_tile *tiles, const uvcgpu_reads_soa & rs, std::string & msg) {
+    if (par.inferred_sequencing_platform != 1) { msg = "only the Illumina/BGI platform path is implemented"; return UVCGPU_EUNSUPPORTED; }
+    const bool pem = (0 == par.pair_end_merge);
+    double center_pow[4];
+    for (int d = 0; d < 4; d++) { center_pow[d] = pow(par.dedup_center_mult, (double)d); }
+    hb = HostBatch();
+    hb.tiles.resize(n_tiles);
+    for (int32_t ti = 0; ti < n_tiles; ti++) {
+        const uvcgpu_tile & ut = tiles[ti];
+        TileInfo & T = hb.tiles[ti];
+        memset(&T, 0, sizeof(T));
+        T.tid = ut.tid; T.beg_pos = ut.beg_pos; T.end_pos = ut.end_pos; T.region_flag = ut.region_flag;
+        T.prev_tid = ut.prev_tid; T.prev_beg_pos = ut.prev_beg_pos; T.prev_end_pos = ut.prev_end_pos;
+        T.pos_off = hb.n_pos; T.read_off = (int64_t)hb.reads.size(); T.frag_off = (int64_t)hb.frags.size(); T.fam_off = (int64_t)hb.fams.size();
+        if (ut.read_begin < 0 || ut.read_end > rs.n_reads || ut.read_begin > ut.read_end || ut.beg_pos >= ut.end_pos) { msg = "invalid tile"; return UVCGPU_EINVAL; }
+        auto cit = contigs.find(ut.tid);
+        hb.n_reads_in += ut.read_end - ut.read_begin;
+        const int32_t fetch_tbeg = ut.beg_pos, fetch_tend = ut.end_pos;
+        const bool end2end = (ut.region_flag & 0x1);
+        const int32_t fetch_size = fetch_tend - fetch_tbeg + (ARRPOS_MARGIN + ARRPOS_OUTER_RANGE) * 2;
+        std::vector<int32_t> beg_cnt[4], end_cnt[4];
+        std::vector<int64_t> border_psum[4];
+        for (int c = 0; c < 4; c++) { beg_cnt[c].assign(fetch_size, 0); end_cnt[c].assign(fetch_size, 0); border_psum[c].assign((size_t)fetch_size + 1, 0); }
+
+        // pass 1 (grouping.cpp:666-695): end histograms and the set of fragment names that touch the tile
+        std::unordered_set<std::string> visited;
+        for (int64_t i = ut.read_begin; i < ut.read_end; i++) {
+            const Raw r = get_raw(rs, i);
+            bool isrc = false, isr2 = false; int32_t tBeg = 0, tEnd = 0;
+            if (KEEP != classify(isrc, isr2, tBeg, tEnd, r, fetch_tbeg, fetch_tend, par, end2end, pem)) { continue; }
+            const int c = isrc * 2 + isr2;
+            const int32_t bi = tBeg + ARRPOS_MARGIN - fetch_tbeg, ei = tEnd + ARRPOS_MARGIN - fetch_tbeg;
+            if (bi >= 0 && bi < fetch_size) { beg_cnt[c][bi] += 1; }
+            if (ei >= 0 && ei < fetch_size) { end_cnt[c][ei] += 1; }
+            const int32_t lo = std::min(tBeg, tEnd), hi = std::max(tBeg, tEnd) + 2;
+            if (!((hi <= fetch_tbeg) || (fetch_tend <= lo))) { visited.insert(r.qname); }
+        }
+        std::vector<int32_t> beg_center[4], end_center[4];
+        for (int c = 0; c < 4; c++) {
+            int64_t bs = 0, es = 0;
+            for (int32_t i = 0; i < fetch_size; i++) { bs += beg_cnt[c][i]; es += end_cnt[c][i]; border_psum[c][i + 1] = bs + es; }
+            beg_center[c].assign(fetch_size, 0); end_center[c].assign(fetch_size, 0);
+            snap_to_centers(beg_center[c], beg_cnt[c], center_pow);
+            snap_to_centers(end_center[c], end_cnt[c], center_pow);
+        }
+
+        // pass 2 (grouping.cpp:731-977): family key of every kept read
+        std::vector<Kept> kept;
+        int32_t bam_beg = INT32_MAX, bam_end = 0;
+        int64_t pcrpassed = 0;
+        for (int64_t i = ut.read_begin; i < ut.read_end; i++) {
+            Raw r = get_raw(rs, i);
+            if (r.pos < nnminus(fetch_tbeg, UVC_MAX_INSERT_SIZE + 1) || r.rend > (fetch_tend + UVC_MAX_INSERT_SIZE + 1)) { continue; }
+            if (visited.find(r.qname) == visited.end()) { continue; }
+            bool isrc = false, isr2 = false; int32_t tBeg = 0, tEnd = 0;
+            if (KEEP != classify(isrc, isr2, tBeg, tEnd, r, fetch_tbeg, fetch_tend, par, end2end, pem)) { continue; }
+            bam_beg = std::min(bam_beg, r.pos);
+            bam_end = std::max(bam_end, r.rend);
+            const char *qname = r.qname;
+            const size_t qlen = strlen(qname);
+            const char *umi_beg1 = strchr(qname, '#');
+            const char *umi_beg = (umi_beg1 ? umi_beg1 + 1 : qname + qlen);
+            const char *umi_end1 = strchr(umi_beg, '#');
+            const char *umi_end = (umi_end1 ? umi_end1 : qname + qlen);
+            const bool umi_found = ((umi_beg + 1 < umi_end) && (1 /* MOLECULE_TAG_NONE */ != par.molecule_tag));
+            bool duplex_found = false;
+            const size_t umi_len = umi_end - umi_beg;
+            if (umi_found) {
+                const size_t half = (umi_len - 1) / 2;
+                if ((umi_len % 2 == 1) && ('+' == umi_beg[half]) && (!par.disable_duplex)) { duplex_found = true; }
+            }
+            const int c = isrc * 2 + isr2;
+            const int32_t beg1 = tBeg + ARRPOS_MARGIN - fetch_tbeg, end1 = tEnd + ARRPOS_MARGIN - fetch_tbeg;
+            const int32_t beg2 = beg_center[c][beg1], end2 = end_center[c][end1];
+            const int64_t beg2count = beg_cnt[c][beg2], end2count = end_cnt[c][end2];
+            const int32_t insL = std::min(beg2 + 6, end2);
+            const int32_t insR = std::max((int64_t)beg2, nnminus(end2, 6));
+            const int64_t tot = border_psum[c][insR] - border_psum[c][insL];
+            const double begratio = (double)(beg2count * (insR - insL) + 1) / (double)(tot + (insR - insL) + 1);
+            const double endratio = (double)(end2count * (insR - insL) + 1) / (double)(tot + (insR - insL) + 1);
+            const bool beg_amp = (begratio > par.dedup_amplicon_border_to_insert_cov_weak_avgDP_ratio
+                    && (beg2count >= par.dedup_amplicon_border_weak_minDP) && (beg2count >= tot * par.dedup_amplicon_border_to_insert_cov_weak_totDP_ratio));
+            const bool end_amp = (endratio > par.dedup_amplicon_border_to_insert_cov_weak_avgDP_ratio
+                    && (end2count >= par.dedup_amplicon_border_weak_minDP) && (end2count >= tot * par.dedup_amplicon_border_to_insert_cov_weak_totDP_ratio));
+            const bool beg_strong = (begratio > par.dedup_amplicon_border_to_insert_cov_strong_avgDP_ratio
+                    && (beg2count >= par.dedup_amplicon_border_strong_minDP) && (beg2count >= tot * par.dedup_amplicon_border_to_insert_cov_strong_totDP_ratio));
+            const bool end_strong = (endratio > par.dedup_amplicon_border_to_insert_cov_strong_avgDP_ratio
+                    && (end2count >= par.dedup_amplicon_border_strong_minDP) && (end2count >= tot * par.dedup_amplicon_border_to_insert_cov_strong_totDP_ratio));
+            const bool assay_amplicon = (beg_strong || end_strong || (beg_amp && end_amp));
+            pcrpassed += assay_amplicon;
+            uint32_t idflag = 0;
+            if (par.dedup_flag != 0) {
+                idflag = par.dedup_flag;
+            } else if (umi_found) {
+                if (beg_strong && end_amp && beg2count > end2count * par.dedup_amplicon_end2end_ratio) { idflag = 0x9; }
+                else if (end_strong && beg_amp && end2count > beg2count * par.dedup_amplicon_end2end_ratio) { idflag = 0xA; }
+                else { idflag = 0xB; }
+            } else if (assay_amplicon) {
+                idflag = 0x7;
+            } else {
+                idflag = 0x3;
+            }
+            const bool preserved = ((r.flag & 0x1) && (!(r.flag & 0x4)) && (!(r.flag & 0x8)) && (abs(r.isize) >= (UVC_MAX_INSERT_SIZE * 3 / 4) || r.isize == 0));
+            const int32_t begtid = ut.tid;
+            const int32_t endtid = (((r.flag & 0x1) && !(r.flag & 0x8)) ? r.mtid : (INT32_MAX - 1));
+            const tidpos_t begpair(begtid, preserved ? r.pos : (beg2 - ARRPOS_MARGIN + fetch_tbeg));
+            const tidpos_t endpair(endtid, preserved ? r.mpos : (end2 - ARRPOS_MARGIN + fetch_tbeg));
+            Kept k;
+            k.raw = i; k.r = r; k.strand = read_strand(r.flag); k.qhash2 = str_hash(qname, 17);
+            k.umi_full = (umi_found ? std::string(umi_beg, umi_len) : std::string());
+            k.begpair = begpair; k.endpair = endpair;
+            // MolecularBarcode::createKey (MolecularID.hpp:20-51)
+            k.key.beg = tidpos_t(-1, -1); k.key.end = tidpos_t(-1, -1);
+            if (0x3 == (0x3 & idflag)) { k.key.beg = std::min(begpair, endpair); k.key.end = std::max(begpair, endpair); }
+            else if (0x1 & idflag) { k.key.beg = begpair; }
+            else if (0x2 & idflag) { k.key.end = endpair; }
+            if (0x4 & idflag) { k.key.qname = qname; }
+            if (0x8 & idflag) { k.key.umi = k.umi_full; }
+            k.key.duplexflag = (umi_found ? 0x1 : 0) + (duplex_found ? 0x2 : 0) + (assay_amplicon ? 0x4 : 0) + (preserved ? 0x8 : 0);
+            k.key.dedup_idflag = idflag;
+            k.fam_local = k.frag_local = -1;
+            kept.push_back(k);
+        }
+        T.num_passed = (int64_t)kept.size();
+        T.num_pcrpassed = pcrpassed;
+        T.bam_inclu_beg = bam_beg; T.bam_exclu_end = bam_end;
+        T.is_amplicon_inferred = !((pcrpassed) * 2 <= (int64_t)kept.size());
+        if (kept.empty()) { T.skipped = 1; T.ext_beg = T.ext_end = 0; continue; }
+        if (cit == contigs.end()) { msg = "contig of a tile was not set with uvcgpu_set_contig"; return UVCGPU_EINVAL; }
+        const HostContig & contig = cit->second;
+        T.rpos_inclu_beg = std::max(ut.beg_pos, bam_beg);
+        T.rpos_exclu_end = std::min(ut.end_pos, bam_end);
+        T.ext_beg = (int32_t)std::max((int64_t)0, nnminus(std::min(ut.beg_pos, bam_beg), UVC_MAX_STR_N_BASES));
+        const int32_t ext_end_ref = (int32_t)std::min((int64_t)ut.contig_len, (int64_t)std::max(ut.end_pos, bam_end) + UVC_MAX_STR_N_BASES);
+        T.ext_end = ext_end_ref + 1;
+
+        // families in MolecularBarcode order; fragments by qname hash inside (family, strand); reads in file order inside a fragment
+        std::vector<int32_t> order(kept.size());
+        for (size_t i = 0; i < kept.size(); i++) { order[i] = (int32_t)i; }
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+            if (!(kept[a].key == kept[b].key)) { return kept[a].key < kept[b].key; }
+            if (kept[a].strand != kept[b].strand) { return kept[a].strand < kept[b].strand; }
+            return kept[a].qhash2 < kept[b].qhash2;
+        });
+        const int64_t read_base = (int64_t)hb.reads.size();
+        for (size_t oi = 0; oi < order.size();) {
+            size_t oj = oi;
+            while (oj < order.size() && kept[order[oj]].key == kept[order[oi]].key) { oj++; }
+            FamRec F;
+            memset(&F, 0, sizeof(F));
+            F.tile = ti;
+            const FamKey & key = kept[order[oi]].key;
+            F.duplexflag = key.duplexflag; F.dedup_idflag = key.dedup_idflag;
+            const int32_t fam_index = (int32_t)hb.fams.size();
+            // the reference keeps the MolecularBarcode of the first inserted read (file order) as the family's non-key data
+            int32_t first_in_file = order[oi];
+            for (size_t o = oi; o < oj; o++) { first_in_file = std::min(first_in_file, order[o]); }
+            hb.fam_umi.push_back(kept[first_in_file].umi_full);
+            F.beg_tid = kept[first_in_file].begpair.first; F.beg_pos = kept[first_in_file].begpair.second;
+            F.end_tid = kept[first_in_file].endpair.first; F.end_pos = kept[first_in_file].endpair.second;
+            int32_t both_beg = INT32_MAX, both_end = 0;
+            size_t o = oi;
+            for (int strand = 0; strand < 2; strand++) {
+                F.frag_off[strand] = (int32_t)hb.frags.size();
+                int32_t s_beg = INT32_MAX, s_end = 0;
+                std::vector<int32_t> l2r_end, r2l_end;
+                int64_t qseqlen_sum = 0, n_qseqs = 0;
+                while (o < oj && kept[order[o]].strand == strand) {
+                    size_t p = o;
+                    while (p < oj && kept[order[p]].strand == strand && kept[order[p]].qhash2 == kept[order[o]].qhash2) { p++; }
+                    FragRec G;
+                    memset(&G, 0, sizeof(G));
+                    G.tile = ti; G.fam = fam_index; G.strand = strand;
+                    G.read_off = (int32_t)hb.frag_reads.size(); G.n_reads = (int32_t)(p - o);
+                    int32_t f_beg = INT32_MAX, f_end = 0;
+                    for (size_t q = o; q < p; q++) { // stable sort kept file order inside the fragment
+                        Kept & k = kept[order[q]];
+                        k.fam_local = fam_index; k.frag_local = (int32_t)hb.frags.size();
+                        hb.frag_reads.push_back((int32_t)(read_base + order[q]));
+                        // fillTidBegEndFromAlns1 (main.hpp:659-673). QUIRK: the exclusive end grows by one per alignment visited.
+                        f_beg = std::min(f_beg, k.r.pos); f_end = std::max(f_end, k.r.rend) + 1;
+                        s_beg = std::min(s_beg, k.r.pos); s_end = std::max(s_end, k.r.rend) + 1;
+                        both_beg = std::min(both_beg, k.r.pos); both_end = std::max(both_end, k.r.rend) + 1;
+                        G.normMQ = std::max(G.normMQ, (int32_t)k.r.mapq);
+                        if (k.r.flag & 0x10) { r2l_end.push_back(k.r.pos); } else { l2r_end.push_back(k.r.rend); }
+                        qseqlen_sum += k.r.l_qseq; n_qseqs += 1;
+                    }
+                    G.beg = f_beg; G.end = f_end;
+                    hb.frags.push_back(G);
+                    o = p;
+                }
+                F.n_frags[strand] = (int32_t)hb.frags.size() - F.frag_off[strand];
+                F.beg2[strand] = s_beg; F.end2[strand] = s_end;
+                // MEDIAN of the unsorted vectors (main_conversion.hpp:24-28, main.hpp:2939-2940)
+                F.l2r_end_median[strand] = (l2r_end.size() ? (l2r_end[(l2r_end.size() - 1) / 2] + l2r_end[l2r_end.size() / 2]) / 2 : s_end);
+                F.r2l_end_median[strand] = (r2l_end.size() ? (r2l_end[(r2l_end.size() - 1) / 2] + r2l_end[r2l_end.size() / 2]) / 2 : s_beg);
+                F.qlen_ok[strand] = ((F.n_frags[strand] >= par.fam_thres_dup1add) && (qseqlen_sum >= n_qseqs * par.fam_thres_qseqlen));
+                F.nsb_min[strand] = s_end; F.nsb_max[strand] = s_beg;
+            }
+            F.beg_both = both_beg; F.end_both = both_end;
+            hb.fams.push_back(F);
+            oi = oj;
+        }
+
+        // pack reads in file order
+        int32_t max_span = 0;
+        std::unordered_map<int32_t, int32_t> frag_maxrend;
+        std::unordered_map<int64_t, int32_t> fam_maxrend;
+        for (size_t i = 0; i < kept.size(); i++) {
+            const Kept & k = kept[i];
+            ReadRec R;
+            memset(&R, 0, sizeof(R));
+            R.pos = k.r.pos; R.rend = k.r.rend; R.mpos = k.r.mpos; R.isize = k.r.isize;
+            R.l_qseq = k.r.l_qseq; R.n_cigar = k.r.n_cigar; R.nm = k.r.nm;
+            R.flag = k.r.flag; R.mapq = k.r.mapq; R.strand = (uint8_t)k.strand;
+            R.dflag = k.key.duplexflag; R.tile = ti; R.frag = k.frag_local; R.fam = k.fam_local;
+            R.seq_off = hb.seq.size(); R.qual_off = hb.qual.size(); R.cigar_off = hb.cigar.size();
+            hb.seq.insert(hb.seq.end(), k.r.seq, k.r.seq + (k.r.l_qseq + 1) / 2);
+            hb.qual.insert(hb.qual.end(), k.r.qual, k.r.qual + k.r.l_qseq);
+            fix_base_qualities(hb.qual.data() + R.qual_off, k.r, par);
+            hb.cigar.insert(hb.cigar.end(), k.r.cigar, k.r.cigar + k.r.n_cigar);
+            // simple = [S|H|P]* (M|=|X) [S|H|P]*
+            int lead = 0, a = 0, b = k.r.n_cigar;
+            while (a < b && (cigar_op(k.r.cigar[a]) == UVC_CSOFT_CLIP || cigar_op(k.r.cigar[a]) == UVC_CHARD_CLIP || cigar_op(k.r.cigar[a]) == UVC_CPAD)) {
+                if (cigar_op(k.r.cigar[a]) == UVC_CSOFT_CLIP) { lead += cigar_len(k.r.cigar[a]); }
+                a++;
+            }
+            while (b > a && (cigar_op(k.r.cigar[b - 1]) == UVC_CSOFT_CLIP || cigar_op(k.r.cigar[b - 1]) == UVC_CHARD_CLIP || cigar_op(k.r.cigar[b - 1]) == UVC_CPAD)) { b--; }
+            R.simple = ((b - a == 1) && op_is_match(cigar_op(k.r.cigar[a])));
+            R.m_qoff = lead;
+            R.cx_off = -1; R.ev_off = (int32_t)hb.n_ev; R.n_ev = 0;
+            if (!R.simple) {
+                R.cx_off = (int32_t)hb.n_cx;
+                hb.n_cx += (R.rend - R.pos);
+                for (int c = 0; c < k.r.n_cigar; c++) { if (cigar_op(k.r.cigar[c]) == UVC_CINS || cigar_op(k.r.cigar[c]) == UVC_CDEL) { R.n_ev++; } }
+                hb.n_ev += R.n_ev;
+            }
+            auto fit = frag_maxrend.find(R.frag);
+            R.fragprev_maxrend = (fit == frag_maxrend.end() ? INT32_MIN : fit->second);
+            if (fit == frag_maxrend.end()) { frag_maxrend[R.frag] = R.rend; } else { fit->second = std::max(fit->second, R.rend); }
+            const int64_t fkey = (int64_t)R.fam * 2 + R.strand;
+            auto mit = fam_maxrend.find(fkey);
+            R.famprev_maxrend = (mit == fam_maxrend.end() ? INT32_MIN : mit->second);
+            if (mit == fam_maxrend.end()) { fam_maxrend[fkey] = R.rend; } else { mit->second = std::max(mit->second, R.rend); }
+            max_span = std::max(max_span, R.rend - R.pos);
+            hb.reads.push_back(R);
+            hb.read_raw_index.push_back(k.raw);
+        }
+        T.n_reads = (int32_t)kept.size();
+        T.n_frags = (int32_t)((int64_t)hb.frags.size() - T.frag_off);
+        T.n_fams = (int32_t)((int64_t)hb.fams.size() - T.fam_off);
+        T.max_read_span = max_span;
+
+        // stage P1: reference symbols, repeat context, BAQ prefix sums over [ext_beg, ext_end)
+        const int32_t npos = T.ext_end - T.ext_beg;
+        const int32_t nref = npos - 1;
+        std::string refstring;
+        if (contig.available) {
+            if ((int64_t)ext_end_ref > contig.len) { msg = "tile extends beyond the contig that was set"; return UVCGPU_EINVAL; }
+            refstring.assign(contig.bases.data() + T.ext_beg, (size_t)nref);
+        } else {
+            refstring.assign((size_t)nref, 'n');
+        }
+        const size_t poff = (size_t)hb.n_pos;
+        hb.refsym.resize(poff + npos); hb.pos_tile.resize(poff + npos, ti); hb.baq.resize(poff + npos); hb.baq2.resize(poff + npos);
+        for (int32_t i = 0; i < nref; i++) { hb.refsym[poff + i] = char_to_symbol(refstring[i]); }
+        hb.refsym[poff + nref] = UVC_BASE_N;
+        std::vector<uvcgpu_rtr> rtr;
+        repeat_context(rtr, refstring.data(), nref, par);
+        hb.rtr.insert(hb.rtr.end(), rtr.begin(), rtr.end());
+        baq_prefix(hb.baq, poff, rtr, false, par);
+        baq_prefix(hb.baq2, poff, rtr, true, par);
+        hb.n_pos += npos;
+    }
+    return 0;
+}
+
+std::string uvc_families_text(const HostBatch & hb, int32_t tile_index, const uvcgpu_reads_soa & rs) {
+    std::string out;
+    const TileInfo & T = hb.tiles[tile_index];
+    for (int64_t fi = T.fam_off; fi < T.fam_off + T.n_fams; fi++) {
+        const FamRec & F = hb.fams[fi];
+        out += "F\t" + std::to_string(F.beg_tid) + "\t" + std::to_string(F.beg_pos) + "\t" + std::to_string(F.end_tid) + "\t" + std::to_string(F.end_pos)
+            + "\t" + std::to_string(F.duplexflag) + "\t" + std::to_string(F.dedup_idflag) + "\t" + hb.fam_umi[fi]
+            + "\t" + std::to_string(F.n_frags[0]) + "\t" + std::to_string(F.n_frags[1]) + "\n";
+        for (int strand = 0; strand < 2; strand++) {
+            for (int32_t g = F.frag_off[strand]; g < F.frag_off[strand] + F.n_frags[strand]; g++) {
+                const FragRec & G = hb.frags[g];
+                out += "f\t" + std::to_string(strand);
+                for (int32_t q = G.read_off; q < G.read_off + G.n_reads; q++) {
+                    const ReadRec & R = hb.reads[hb.frag_reads[q]];
+                    const int64_t raw = hb.read_raw_index[hb.frag_reads[q]];
+                    out += std::string("\t") + (rs.qname + rs.qname_off[raw]) + "/" + std::to_string(R.flag) + "/" + std::to_string(R.pos);
+                }
+                out += "\n";
+            }
+        }
+    }
+    return out;
+}

@@ -1,0 +1,45 @@
+// host_prep.h - host-side staging of a batch: read filter + family grouping (stage P0), base-quality fix-ups,
+// reference repeat context (stage P1) and SoA packing. Shared by the CUDA library and the test-only emulation.
+#ifndef UVC_HOST_PREP_H_INCLUDED
+#define UVC_HOST_PREP_H_INCLUDED
+
+#include "batch.h"
+
+#include <map>
+#include <string>
+#include <vector>
+
+struct HostContig {
+    std::string bases;   // upper-cased; empty if not available
+    int64_t len = 0;
+    bool available = false;
+};
+
+struct HostBatch {
+    std::vector<TileInfo> tiles;
+    std::vector<int32_t> pos_tile;
+    std::vector<uint8_t> refsym;
+    std::vector<uvcgpu_rtr> rtr;          // as computed from the reference string (before the threshold pass adjusts indelphred)
+    std::vector<int32_t> baq, baq2;
+    std::vector<ReadRec> reads;
+    std::vector<int64_t> read_raw_index;  // index into the caller's uvcgpu_reads_soa
+    std::vector<uint8_t> seq, qual;
+    std::vector<uint32_t> cigar;
+    std::vector<FragRec> frags;
+    std::vector<int32_t> frag_reads;
+    std::vector<FamRec> fams;
+    std::vector<std::string> fam_umi;     // umistring of each family (for the grouping dump)
+    int64_t n_pos = 0, n_cx = 0, n_ev = 0;
+    int64_t n_reads_in = 0;
+};
+
+// Builds the staging arrays of one batch. Returns 0 or a negative uvcgpu_error; msg receives the reason.
+int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::map<int32_t, HostContig> & contigs,
+        int32_t n_tiles, const uvcgpu_tile *tiles, const uvcgpu_reads_soa & rs, std::string & msg);
+
+// Text form of the family grouping of one tile (same format as oracle/harness_dump.cpp writes).
+std::string uvc_families_text(const HostBatch & hb, int32_t tile_index, const uvcgpu_reads_soa & rs);
+
+void uvc_fill_view_constants(BatchView & v, const uvcgpu_params & par);
+
+#endif

@@ -1,0 +1,810 @@
+// kernels_core.cuh - per-work-item bodies of the pileup kernels.
+//
+// Execution model ("pileup columns"): the reference walks every read and scatters ~130 read-modify-writes per aligned
+// base into a 6 KB-per-position state (main.hpp:925-1204, 1762-2296, 1363-1595). Here every reference position is
+// owned by one thread that GATHERS the reads covering it (reads are sorted by start position, so they form a window
+// found by binary search) and keeps the hot counters (the reference-matching base symbol and LINK_M) in registers;
+// the position's records are then written once, as contiguous bursts, in the reference's own struct layout.
+// No atomics are needed on the dense path because each position's counters have exactly one writer; only the rare
+// per-CIGAR-operation events (indels, clips, mismatch runs) use global atomics, from the per-read kernels.
+//
+// Every body is a plain function of (view, index), compiled for the device by nvcc and - for the CPU-only unit tests
+// of the host logic (tests/ only, never shipped as a fallback) - as ordinary C++.
+#ifndef UVC_KERNELS_CORE_CUH_INCLUDED
+#define UVC_KERNELS_CORE_CUH_INCLUDED
+
+#include "batch.h"
+
+#include <limits.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define UVC_HD __host__ __device__ __forceinline__
+#else
+#define UVC_HD inline
+#endif
+
+namespace uvc {
+
+template <class T> UVC_HD T tmin(T a, T b) { return a < b ? a : b; }
+template <class T> UVC_HD T tmax(T a, T b) { return a > b ? a : b; }
+UVC_HD int32_t nnminus(int32_t a, int32_t b) { return (a > b ? a - b : 0); }
+UVC_HD int32_t iabs(int32_t a) { return a < 0 ? -a : a; }
+UVC_HD int32_t between(int32_t v, int32_t lo, int32_t hi) { return tmin(tmax(lo, v), hi); }
+
+UVC_HD void atomic_add(int32_t *p, int32_t v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+UVC_HD void atomic_add(int64_t *p, int64_t v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd((unsigned long long*)p, (unsigned long long)v);
+#else
+    *p += v;
+#endif
+}
+
+UVC_HD int cig_op(uint32_t c) { return (int)(c & 0xf); }
+UVC_HD int32_t cig_len(uint32_t c) { return (int32_t)(c >> 4); }
+UVC_HD bool is_match_op(int op) { return op == UVC_CMATCH || op == UVC_CEQUAL || op == UVC_CDIFF; }
+UVC_HD bool is_ins_symbol(int s) { return s == UVC_LINK_I1 || s == UVC_LINK_I2 || s == UVC_LINK_I3P; }
+UVC_HD bool is_del_symbol(int s) { return s == UVC_LINK_D1 || s == UVC_LINK_D2 || s == UVC_LINK_D3P; }
+
+// seq_nt16_int of the 4-bit base at query index i: A,C,G,T -> 0..3, anything else -> 4 (BASE_N) (main.hpp:1829-1833)
+UVC_HD int base3(const uint8_t *seq, int32_t i) {
+    const int b4 = (seq[i >> 1] >> ((~i & 1) << 2)) & 0xf;
+    return (b4 == 1 ? 0 : (b4 == 2 ? 1 : (b4 == 4 ? 2 : (b4 == 8 ? 3 : 4))));
+}
+UVC_HD int base4(const uint8_t *seq, int32_t i) { return (seq[i >> 1] >> ((~i & 1) << 2)) & 0xf; }
+
+UVC_HD int read_strand(uint16_t flag) { return (((flag & 0x81) == 0x81) ? (!!(flag & 0x20)) : (!!(flag & 0x10))); }
+
+// Range [lo, hi) of the tile's reads whose start lies in (p - max_span, p]: the only reads that can cover p.
+UVC_HD void read_window(const BatchView & v, const TileInfo & T, int32_t p, int64_t & lo, int64_t & hi) {
+    const int64_t r0 = T.read_off, r1 = T.read_off + T.n_reads;
+    const int32_t minpos = p - T.max_read_span;  // reads with pos <= minpos cannot reach p
+    int64_t a = r0, b = r1;
+    while (a < b) { const int64_t m = (a + b) >> 1; if (v.reads[m].pos <= minpos) { a = m + 1; } else { b = m; } }
+    lo = a;
+    b = r1;
+    while (a < b) { const int64_t m = (a + b) >> 1; if (v.reads[m].pos <= p) { a = m + 1; } else { b = m; } }
+    hi = a;
+}
+
+// What read R shows at reference position p (pos <= p < rend).
+struct Locus {
+    int32_t qpos;       // query index, -1 if not an aligned base
+    bool is_m;          // aligned (M/=/X) base
+    bool not_first;     // not the first base of its M run (the junction before it carries LINK_M)
+    bool is_del;        // deleted base
+    int32_t prev_rpos, next_rpos; // neighbouring low-quality indels (main.hpp:1902-1903); for deleted bases: the two precomputed distances
+};
+
+UVC_HD Locus locate(const BatchView & v, const ReadRec & R, int32_t p) {
+    Locus L;
+    if (R.simple) {
+        const int32_t o = p - R.pos;
+        L.qpos = R.m_qoff + o; L.is_m = true; L.not_first = (o > 0); L.is_del = false; L.prev_rpos = 0; L.next_rpos = INT32_MAX;
+    } else {
+        const CxEntry e = v.cx[R.cx_off + (p - R.pos)];
+        L.qpos = e.qpos; L.is_m = (e.flags & 1); L.not_first = (e.flags & 2); L.is_del = (e.flags & 4); L.prev_rpos = e.prev_rpos; L.next_rpos = e.next_rpos;
+    }
+    return L;
+}
+
+UVC_HD bool primer_masked(const BatchView & v, const ReadRec & R, const ReadDerived & D, int32_t rpos) {
+    // main.hpp:1895: a base counts if the assay is not an amplicon (or the normal is used to filter primers) or it lies inside the insert minus primers
+    const bool is_assay_amplicon = ((R.dflag & 0x4) || ((v.par.primerlen > 0) && !(0x2 & v.par.primer_flag)));
+    const bool normal_filters_primers = (v.par.tn_is_paired && (0x1 & v.par.primer_flag));
+    return !((normal_filters_primers || !is_assay_amplicon) || (D.ibeg <= rpos && rpos < D.iend));
+}
+
+// ------------------------------------------------------------------------------------------------ K0: one thread per read
+// Read-level constants (main.hpp:937-998, 1789-1885), the per-reference-base expansion and the low-quality-indel
+// neighbours of complex reads (main.hpp:1817-1859, 1897-1916, 2219-2252), the list of indel events, and the rare
+// per-operation contributions to the prep sets (insertions, deletions, clips, mismatch runs; main.hpp:1025-1046, 1069-1199).
+UVC_HD void k0_read(const BatchView & v, int64_t ri) {
+    const ReadRec & R = v.reads[ri];
+    ReadDerived D;
+    const TileInfo & T = v.tiles[R.tile];
+    const uint32_t *cigar = v.cigar + R.cigar_off;
+    const uint8_t *seq = v.seq + R.seq_off;
+    const uint8_t *qual = v.qual + R.qual_off;
+    const int64_t po = T.pos_off - T.ext_beg;        // concatenated index of reference position x is po + x
+    const int32_t npos = T.ext_end - T.ext_beg;
+    const int32_t *baq = v.baq + po;
+    const uint8_t *refsym = v.refsym + po;
+    const uvcgpu_params & par = v.par;
+    const int32_t pos = R.pos, rend = R.rend;
+
+    int32_t nge = 0, ngo = 0, clip_cnt = 0, insbaq = 0, delbaq = 0, inslen = 0, dellen = 0;
+    {
+        int32_t rpos = pos;
+        for (int32_t i = 0; i < R.n_cigar; i++) {
+            const int op = cig_op(cigar[i]); const int32_t len = cig_len(cigar[i]);
+            if (op == UVC_CINS || op == UVC_CDEL) {
+                nge += len; ngo++;
+                const int32_t d = baq[tmin(rpos + len, T.ext_end - 1)] - baq[rpos];
+                if (op == UVC_CINS) { insbaq += d; inslen += len; } else { delbaq += d; dellen += len; rpos += len; }
+            } else if (is_match_op(op) || op == UVC_CREF_SKIP) {
+                rpos += len;
+            }
+            if (op == UVC_CSOFT_CLIP || op == UVC_CHARD_CLIP) { clip_cnt++; }
+        }
+    }
+    const int32_t nm_cnt = (R.nm >= 0 ? R.nm : nge);
+    const int32_t xm_cnt = nm_cnt - nge;
+    const int32_t span = rend - pos;
+    D.xm1500 = xm_cnt * 1500 / span;
+    D.go1500 = ngo * 1500 / span;
+    D.avg_gaplen = nge / tmax(1, ngo);
+    D.nge_cnt = nge; D.ngo_cnt = ngo; D.clip_cnt = clip_cnt;
+    D.inslen_sum = inslen; D.dellen_sum = dellen; D.insbaq_sum = insbaq; D.delbaq_sum = delbaq;
+    D.lclip = ((R.n_cigar > 0 && cig_op(cigar[0]) == UVC_CSOFT_CLIP) ? cig_len(cigar[0]) : 0);
+    D.rclip = ((R.n_cigar > 0 && cig_op(cigar[R.n_cigar - 1]) == UVC_CSOFT_CLIP) ? cig_len(cigar[R.n_cigar - 1]) : 0);
+    const int32_t penal_clip = tmax(D.lclip, D.rclip) / 6;
+    const int32_t penal_nm = (D.xm1500 + D.go1500) / 30;
+    D.micro_indel_penal = tmin(1, penal_nm + penal_clip);
+    D.micro_nogap_penal = tmin(4, penal_nm + penal_clip) + 1;
+    const bool isrc = ((R.flag & 0x10) == 0x10);
+    D.ibeg = ((R.isize != 0) ? (tmin(pos, R.mpos) + par.primerlen)
+            : ((isrc && (0x0 == (0x1 & R.flag))) ? 0 : (pos + par.primerlen)));
+    D.iend = ((R.isize != 0) ? nnminus(tmin(pos, R.mpos) + iabs(R.isize), par.primerlen)
+            : ((isrc && (0x0 == (0x1 & R.flag))) ? nnminus(rend, par.primerlen) : INT32_MAX));
+
+    const int32_t pcr_inc = ((R.dflag & 0x4) ? 1 : 0);
+    const int32_t umi_inc = ((R.dflag & 0x1) ? 1 : 0);
+    const int32_t frag_pos_L = tmin(pos, R.mpos);
+    const int32_t frag_pos_R = frag_pos_L + iabs(R.isize);
+    const int32_t adj = par.indel_adj_tracklen_dist;
+    const uvcgpu_rtr *rtr = v.rtr + T.pos_off;          // indexed by p - ext_beg
+    uvcgpu_prep_set *prep = v.prep + po;
+
+    int32_t bm_cnt[5] = {0, 0, 0, 0, 0};
+    int32_t n_ev = 0;
+    // low-quality indels of this read in reference order: lowq[0] = 0, ..., INT32_MAX (main.hpp:1817-1858)
+    // kept implicitly: we only need, while replaying the walk, the current "previous" and "next" entries.
+    {
+        int32_t qpos = 0, rpos = pos;
+        // first pass: mismatch counts per base type, indel event records, prep-set events
+        for (int32_t i = 0; i < R.n_cigar; i++) {
+            const int op = cig_op(cigar[i]); const int32_t len = cig_len(cigar[i]);
+            if (is_match_op(op)) {
+                for (int32_t j = 0; j < len; j++) {
+                    const int b = base3(seq, qpos);
+                    if ((int)refsym[rpos] != b) {
+                        bm_cnt[b] += 1;
+                        // mismatch-run detection exactly as written (main.hpp:1025-1046): the look-ahead runs over raw query and
+                        // reference indices regardless of the CIGAR, bounded by l_qseq and rend
+                        int32_t nq = qpos + 1, nr = rpos + 1;
+                        bool mism = true;
+                        while (mism && nq < R.l_qseq && nr < rend) {
+                            mism = ((int)refsym[nr] != base3(seq, nq));
+                            nq++; nr++;
+                        }
+                        if (nr == rpos + 2) {
+                            for (int32_t r = tmax(pos, rpos - 1); r < tmin(nr, rend); r++) { atomic_add(&prep[r].a_snv_dp, 1); }
+                        }
+                        if (nr > rpos + 2) {
+                            for (int32_t r = tmax(pos, rpos - 1); r < tmin(nr, rend); r++) { atomic_add(&prep[r].a_dnv_dp, 1); }
+                        }
+                    }
+                    qpos++; rpos++;
+                }
+            } else if (op == UVC_CINS || op == UVC_CDEL) {
+                const int32_t ridx = rpos - T.ext_beg;
+                const uvcgpu_rtr rtr1 = rtr[tmax(adj, ridx) - adj];
+                const uvcgpu_rtr rtr2 = rtr[tmin(ridx + adj, npos - 1)];
+                const int32_t unitlen2 = tmax(1, (rtr1.tracklen > rtr2.tracklen) ? rtr1.unitlen : rtr2.unitlen);
+                const int32_t inv100 = 100 / ((0 == len % unitlen2) ? (len / unitlen2) : 4);
+                const int32_t rtr_lo = tmax((T.ext_beg + rtr1.begpos) - adj, pos);
+                const int32_t rtr_hi = tmin((T.ext_beg + rtr2.begpos + rtr2.tracklen) + adj, rend);
+                if (op == UVC_CINS) {
+                    const int32_t nbases = (int32_t)(((uint32_t)len * (uint32_t)par.indel_adj_indellen_perc) / 100u);
+                    for (int32_t r2 = tmax(rpos - nbases, pos); r2 < tmin(rpos + nbases, rend); r2++) {
+                        atomic_add(&prep[r2].a_near_ins_dp, 1);
+                        atomic_add(&prep[r2].a_near_ins_pow2len, (int64_t)((uint32_t)len * (uint32_t)len));
+                        atomic_add(&prep[r2].a_near_ins_l_pow2len, (int64_t)((r2 + 1 - (rpos - nbases)) * (r2 + 1 - (rpos - nbases))));
+                        atomic_add(&prep[r2].a_near_ins_r_pow2len, (int64_t)(((rpos + nbases) - r2) * ((rpos + nbases) - r2)));
+                        atomic_add(&prep[r2].a_near_ins_inv100len, inv100);
+                    }
+                    for (int32_t r2 = rtr_lo; r2 < rtr_hi; r2++) { atomic_add(&prep[r2].a_near_RTR_ins_dp, 1); }
+                    atomic_add(&prep[rpos].a_at_ins_dp, 1);
+                } else {
+                    // every deleted base gets the dense per-base counters (main.hpp:1127-1161)
+                    const int32_t ldist = rpos - pos + 1, rdist = rend - rpos;
+                    const int32_t lbaq = baq[rpos] - baq[pos] + 1, rbaq = baq[rend - 1] - baq[rpos] + 1;
+                    for (int32_t r2 = rpos; r2 < rpos + len; r2++) {
+                        uvcgpu_prep_set & q = prep[r2];
+                        atomic_add(&q.a_pcr_dp, pcr_inc); atomic_add(&q.a_umi_dp, umi_inc); atomic_add(&q.a_dp, 1);
+                        atomic_add(&q.a_qlen, span); atomic_add(&q.a_highBQ_dp, 1);
+                        atomic_add(&q.a_XM1500, D.xm1500); atomic_add(&q.a_GO1500, D.go1500); atomic_add(&q.a_GAPLEN, D.avg_gaplen);
+                        if (R.isize != 0) {
+                            // QUIRK: distances are taken at the deletion start rpos, not at r2 (main.hpp:1139-1142)
+                            if (isrc) { atomic_add(&q.a_LI, (int64_t)tmin(rpos - frag_pos_L + 1, UVC_MAX_INSERT_SIZE)); atomic_add(&q.a_LIDP, 1); }
+                            else { atomic_add(&q.a_RI, (int64_t)tmin(frag_pos_R - rpos, UVC_MAX_INSERT_SIZE)); atomic_add(&q.a_RIDP, 1); }
+                        }
+                        atomic_add(&q.a_l_dist_sum, ldist); atomic_add(&q.a_r_dist_sum, rdist);
+                        atomic_add(&q.a_inslen_sum, inslen); atomic_add(&q.a_dellen_sum, dellen);
+                        // QUIRK: the BAQ sums go to the deletion start once per deleted base (main.hpp:1156-1157)
+                        atomic_add(&prep[rpos].a_l_BAQ_sum, (int64_t)lbaq); atomic_add(&prep[rpos].a_r_BAQ_sum, (int64_t)rbaq);
+                        atomic_add(&q.a_insBAQ_sum, (int64_t)insbaq); atomic_add(&q.a_delBAQ_sum, (int64_t)delbaq);
+                    }
+                    const int32_t nb_l = (int32_t)(((uint32_t)len * (uint32_t)(par.indel_adj_indellen_perc - 100)) / 100u);
+                    const int32_t nb_r = (int32_t)(((uint32_t)len * (uint32_t)par.indel_adj_indellen_perc) / 100u);
+                    const int32_t lp = tmax(rpos - nb_l, pos);
+                    const int32_t rp = tmin(rpos + nb_r, rend) - 1;
+                    for (int32_t r2 = lp; r2 <= rp; r2++) {
+                        atomic_add(&prep[r2].a_near_del_dp, 1);
+                        atomic_add(&prep[r2].a_near_del_pow2len, (int64_t)((uint32_t)len * (uint32_t)len));
+                        atomic_add(&prep[r2].a_near_del_l_pow2len, (int64_t)((r2 - lp + 1) * (r2 - lp + 1)));
+                        atomic_add(&prep[r2].a_near_del_r_pow2len, (int64_t)((rp - r2 + 1) * (rp - r2 + 1)));
+                        atomic_add(&prep[r2].a_near_del_inv100len, inv100);
+                    }
+                    for (int32_t r2 = rtr_lo; r2 < rtr_hi; r2++) { atomic_add(&prep[r2].a_near_RTR_del_dp, 1); }
+                    atomic_add(&prep[rpos].a_at_del_dp, 1);
+                }
+                if (!R.simple) {
+                    IndelEvent & E = v.ev[R.ev_off + n_ev];
+                    E.read = (int32_t)ri; E.rpos = rpos; E.oplen = len; E.qpos = qpos; E.is_del = (op == UVC_CDEL); E.cigar_idx = i;
+                    E.symbol = -1; E.incvalue = 0; E.incvalue2 = 0; E.counted = 0;
+                    n_ev++;
+                }
+                if (op == UVC_CINS) { qpos += len; } else { rpos += len; }
+            } else {
+                const int32_t rdelta = ((0 == i) ? 0 : -1);
+                if ((op == UVC_CSOFT_CLIP || op == UVC_CHARD_CLIP) && pcr_inc) {
+                    for (int32_t r2 = rpos + rdelta - par.microadjust_near_clip_dist; r2 <= rpos + rdelta + par.microadjust_near_clip_dist; r2++) {
+                        if (T.ext_beg <= r2 && r2 < T.ext_end) { atomic_add(&prep[r2].a_near_pcr_clip_dp, pcr_inc); }
+                    }
+                }
+                if ((op == UVC_CSOFT_CLIP || op == UVC_CHARD_CLIP) && (0 == pcr_inc) && (len >= par.microadjust_alignment_clip_min_len)) {
+                    atomic_add(&prep[rpos + rdelta].a_near_long_clip_dp, 1);
+                }
+                if (op == UVC_CREF_SKIP) { rpos += len; } else if (op == UVC_CSOFT_CLIP) { qpos += len; }
+            }
+        }
+    }
+    for (int b = 0; b < 5; b++) { D.bm1500[b] = bm_cnt[b] * 1500 / span; }
+    v.rd[ri] = D;
+
+    if (!R.simple) {
+        // Replay of the bias walk's bookkeeping (main.hpp:1817-1859, 1886-2257): for every reference base of the read, what it
+        // aligns to and which low-quality indels surround it according to the reference's one-step-per-base cursor.
+        CxEntry *cx = v.cx + R.cx_off;
+        for (int32_t o = 0; o < span; o++) { cx[o].qpos = -1; cx[o].flags = 0; cx[o].pad = 0; cx[o].prev_rpos = 0; cx[o].next_rpos = INT32_MAX; }
+        // the list of low-quality indel positions, materialised in the events' scratch (symbol field) as flags
+        int32_t n_low = 0;
+        {
+            int32_t qpos = 0, rpos = pos, e = 0;
+            for (int32_t i = 0; i < R.n_cigar; i++) {
+                const int op = cig_op(cigar[i]); const int32_t len = cig_len(cigar[i]);
+                if (is_match_op(op)) { qpos += len; rpos += len; }
+                else if (op == UVC_CINS) {
+                    bool low = false;
+                    // QUIRK: the upper bound mixes a query index with the reference coordinate rend (main.hpp:1841)
+                    for (int32_t q2 = qpos - tmin(qpos, 1); q2 < tmin(qpos + len + 1, rend); q2++) {
+                        if (q2 < R.l_qseq && (int32_t)qual[q2] < par.bias_thres_interfering_indel_BQ) { low = true; }
+                    }
+                    v.ev[R.ev_off + e].counted = (low ? 1 : 0); if (low) { n_low++; }
+                    e++; qpos += len;
+                } else if (op == UVC_CDEL) {
+                    const int32_t qa = tmax(1, qpos) - 1;
+                    const int32_t qb = tmin(qpos, R.l_qseq - 1);
+                    const bool low = (tmin((int32_t)qual[qa], (int32_t)qual[qb]) <= par.bias_thres_interfering_indel_BQ);
+                    v.ev[R.ev_off + e].counted = (low ? 1 : 0); if (low) { n_low++; }
+                    e++; rpos += len;
+                } else if (op == UVC_CREF_SKIP) { rpos += len; } else if (op == UVC_CSOFT_CLIP) { qpos += len; }
+            }
+        }
+        // cursor replay: list = {0, low-quality indel rposs..., INT32_MAX}; idx starts at 0
+        int32_t idx = 0;           // index into the list
+        int32_t ev_cursor = 0;     // event index of list[idx] - 1 bookkeeping is done through the helper below
+        (void)ev_cursor;
+        // helper: value of list[k]
+        #define UVC_LOWQ_LIST(k, out) { \
+            if ((k) <= 0) { (out) = 0; } else if ((k) > n_low) { (out) = INT32_MAX; } else { \
+                int32_t seen_ = 0; (out) = INT32_MAX; \
+                for (int32_t e_ = 0; e_ < R.n_ev; e_++) { if (v.ev[R.ev_off + e_].counted) { seen_++; if (seen_ == (k)) { (out) = v.ev[R.ev_off + e_].rpos; break; } } } } }
+        int32_t qpos = 0, rpos = pos;
+        for (int32_t i = 0; i < R.n_cigar; i++) {
+            const int op = cig_op(cigar[i]); const int32_t len = cig_len(cigar[i]);
+            if (is_match_op(op)) {
+                for (int32_t j = 0; j < len; j++) {
+                    CxEntry & c = cx[rpos - pos];
+                    c.qpos = (int16_t)qpos; c.flags = (uint8_t)(1 | (j > 0 ? 2 : 0));
+                    if (!primer_masked(v, R, D, rpos) && nge > 0) {
+                        int32_t cur; UVC_LOWQ_LIST(idx, cur);
+                        if (cur <= rpos) { idx++; }
+                        int32_t a, b; UVC_LOWQ_LIST(idx - 1, a); UVC_LOWQ_LIST(idx, b);
+                        c.prev_rpos = a; c.next_rpos = b;
+                    }
+                    qpos++; rpos++;
+                }
+            } else if (op == UVC_CINS) {
+                qpos += len;
+            } else if (op == UVC_CDEL) {
+                const int32_t nbases2end = tmin(qpos, R.l_qseq - qpos);
+                const bool counted = (!primer_masked(v, R, D, rpos)) && (nbases2end >= par.indel_filter_edge_dist);
+                for (int32_t r2 = rpos; r2 < rpos + len; r2++) {
+                    CxEntry & c = cx[r2 - pos];
+                    c.flags = 4;
+                    if (counted && r2 < tmin(rpos + len, rend)) {
+                        // BASE_NN at r2, then LINK_NN at r2 + 1 (main.hpp:2219-2252); each visit advances the cursor at most once
+                        for (int s = 0; s < 2; s++) {
+                            const int32_t pp = (s == 0 ? r2 : r2 + 1);
+                            if (pp >= rend) { continue; }
+                            int32_t cur; UVC_LOWQ_LIST(idx, cur);
+                            if (cur <= rpos) { idx++; }
+                            int32_t a, b; UVC_LOWQ_LIST(idx - 1, a); UVC_LOWQ_LIST(idx, b);
+                            const uint32_t d1 = (uint32_t)rpos - (uint32_t)a, d2 = (uint32_t)b - (uint32_t)rpos;
+                            const int32_t dist = (int32_t)(d1 < d2 ? d1 : d2);
+                            if (s == 0) { c.prev_rpos = dist; } else { c.next_rpos = dist; }
+                        }
+                    }
+                }
+                rpos += len;
+            } else if (op == UVC_CREF_SKIP) { rpos += len; } else if (op == UVC_CSOFT_CLIP) { qpos += len; }
+        }
+        #undef UVC_LOWQ_LIST
+        for (int32_t e = 0; e < R.n_ev; e++) { v.ev[R.ev_off + e].counted = 0; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K1: one thread per position
+// Dense part of walk #1 (main.hpp:1006-1068) gathered per position, then the threshold pass (main.hpp:1206-1299).
+UVC_HD void k1_position(const BatchView & v, int64_t gp) {
+    const TileInfo & T = v.tiles[v.pos_tile[gp]];
+    const int32_t p = (int32_t)(gp - T.pos_off) + T.ext_beg;
+    const uvcgpu_params & par = v.par;
+    const int32_t *baq = v.baq + (T.pos_off - T.ext_beg);
+    uvcgpu_prep_set a = v.prep[gp];     // starts from the rare-event contributions of K0
+    int64_t lo, hi;
+    read_window(v, T, p, lo, hi);
+    for (int64_t ri = lo; ri < hi; ri++) {
+        const ReadRec & R = v.reads[ri];
+        if (R.rend <= p) { continue; }
+        const Locus L = locate(v, R, p);
+        if (!L.is_m) { continue; }
+        const ReadDerived & D = v.rd[ri];
+        const int32_t span = R.rend - R.pos;
+        a.a_pcr_dp += ((R.dflag & 0x4) ? 1 : 0);
+        a.a_umi_dp += ((R.dflag & 0x1) ? 1 : 0);
+        a.a_dp += 1;
+        a.a_qlen += span;
+        a.a_XM1500 += D.xm1500; a.a_GO1500 += D.go1500; a.a_GAPLEN += D.avg_gaplen;
+        if (R.isize != 0) {
+            const int32_t fl = tmin(R.pos, R.mpos);
+            if (R.flag & 0x10) { a.a_LI += tmin(p - fl + 1, UVC_MAX_INSERT_SIZE); a.a_LIDP += 1; }
+            else { a.a_RI += tmin(fl + iabs(R.isize) - p, UVC_MAX_INSERT_SIZE); a.a_RIDP += 1; }
+        }
+        if ((int32_t)v.qual[R.qual_off + L.qpos] >= par.bias_thres_highBQ) {
+            a.a_l_dist_sum += p - R.pos + 1;
+            a.a_r_dist_sum += R.rend - p;
+            a.a_inslen_sum += D.inslen_sum; a.a_dellen_sum += D.dellen_sum;
+            a.a_l_BAQ_sum += baq[p] - baq[R.pos] + 1;
+            a.a_r_BAQ_sum += baq[R.rend - 1] - baq[p] + 1;
+            a.a_insBAQ_sum += D.insbaq_sum; a.a_delBAQ_sum += D.delbaq_sum;
+            a.a_highBQ_dp += 1;
+        }
+    }
+    v.prep[gp] = a;
+
+    uvcgpu_thres_set t;
+    const int32_t segLIDP = tmax(a.a_LIDP, 1), segRIDP = tmax(a.a_RIDP, 1);
+    const double ins_l = ceil(sqrt((double)(a.a_near_ins_l_pow2len / tmax(a.a_near_ins_dp, 1))));
+    const double del_l = ceil(sqrt((double)(a.a_near_del_l_pow2len / tmax(a.a_near_del_dp, 1))));
+    const double ins_r = ceil(sqrt((double)(a.a_near_ins_r_pow2len / tmax(a.a_near_ins_dp, 1))));
+    const double del_r = ceil(sqrt((double)(a.a_near_del_r_pow2len / tmax(a.a_near_del_dp, 1))));
+    const double dnv_border = 0; // the 10-base DNV border applies to IonTorrent only (main.hpp:1234-1235)
+    t.aLPxT = (int32_t)(tmax(ins_l, tmax(del_l, dnv_border)) + par.bias_thres_aLPxT_add);
+    t.aRPxT = (int32_t)(tmax(ins_r, tmax(del_r, dnv_border)) + par.bias_thres_aLPxT_add);
+    int32_t indelphred = v.rtr[gp].indelphred;
+    if (a.a_near_ins_dp * par.indel_del_to_ins_err_ratio < a.a_near_del_dp) { indelphred += v.indelphred_half; }
+    if (a.a_near_del_dp * par.indel_del_to_ins_err_ratio < a.a_near_ins_dp) { indelphred -= v.indelphred_half; }
+    const int32_t pc_inc1 = (int32_t)(3 * 100 * tmax(1, a.a_near_ins_dp + a.a_near_del_dp) / (tmax(1, a.a_near_ins_inv100len + a.a_near_del_inv100len))) - 3;
+    indelphred += between(pc_inc1, 0, 6);
+    indelphred = tmax(indelphred, 0);
+    v.rtr[gp].indelphred = indelphred;
+    const bool is_normal = par.is_tumor_vcf_provided;
+    const int64_t LI1T = (is_normal ? par.bias_thres_aLRI1NT_perc : par.bias_thres_aLRI1T_perc);
+    const int64_t LI1t = (is_normal ? par.bias_thres_aLRI1Nt_perc : par.bias_thres_aLRI1t_perc);
+    t.aLI1T = (int32_t)(a.a_LI * LI1T / (segLIDP * 100) + par.bias_thres_aLRI1T_add);
+    t.aLI2T = (int32_t)(a.a_LI * (int64_t)par.bias_thres_aLRI2T_perc / (segLIDP * 100) + par.bias_thres_aLRI2T_add);
+    t.aLI1t = (int32_t)(a.a_LI * LI1t / (segLIDP * 100));
+    t.aLI2t = (int32_t)(a.a_LI * (int64_t)par.bias_thres_aLRI2t_perc / (segLIDP * 100));
+    t.aRI1T = (int32_t)(a.a_RI * LI1T / (segRIDP * 100) + par.bias_thres_aLRI1T_add);
+    t.aRI2T = (int32_t)(a.a_RI * (int64_t)par.bias_thres_aLRI2T_perc / (segRIDP * 100) + par.bias_thres_aLRI2T_add);
+    t.aRI1t = (int32_t)(a.a_RI * LI1t / (segRIDP * 100));
+    t.aRI2t = (int32_t)(a.a_RI * (int64_t)par.bias_thres_aLRI2t_perc / (segRIDP * 100));
+    const int64_t P1 = (is_normal ? par.bias_thres_aLRP1Nt_avgmul_perc : par.bias_thres_aLRP1t_avgmul_perc);
+    const int64_t P2 = par.bias_thres_aLRP2t_avgmul_perc;
+    const int64_t B1 = (is_normal ? par.bias_thres_aLRB1Nt_avgmul_perc : par.bias_thres_aLRB1t_avgmul_perc);
+    const int64_t B2 = par.bias_thres_aLRB2t_avgmul_perc;
+    const int64_t hb100 = tmax(1, a.a_highBQ_dp * 100);
+    #define UVC_NNM64(x, y) ((x) > (y) ? ((x) - (y)) : 0)
+    t.aLP1t = (int32_t)UVC_NNM64((int64_t)a.a_l_dist_sum * P1 / hb100, (int64_t)par.bias_thres_aLRP1t_minus);
+    t.aLP2t = (int32_t)UVC_NNM64((int64_t)a.a_l_dist_sum * P2 / hb100, (int64_t)par.bias_thres_aLRP2t_minus);
+    t.aRP1t = (int32_t)UVC_NNM64((int64_t)a.a_r_dist_sum * P1 / hb100, (int64_t)par.bias_thres_aLRP1t_minus);
+    t.aRP2t = (int32_t)UVC_NNM64((int64_t)a.a_r_dist_sum * P2 / hb100, (int64_t)par.bias_thres_aLRP2t_minus);
+    const int64_t pdel = a.a_delBAQ_sum / tmax(1, a.a_highBQ_dp);
+    t.aLB1t = (int32_t)UVC_NNM64(a.a_l_BAQ_sum * B1 / hb100, par.bias_thres_aLRB1t_minus + pdel);
+    t.aLB2t = (int32_t)UVC_NNM64(a.a_l_BAQ_sum * B2 / hb100, (int64_t)par.bias_thres_aLRB2t_minus);
+    t.aRB1t = (int32_t)UVC_NNM64(a.a_r_BAQ_sum * B1 / hb100, par.bias_thres_aLRB1t_minus + pdel);
+    t.aRB2t = (int32_t)UVC_NNM64(a.a_r_BAQ_sum * B2 / hb100, (int64_t)par.bias_thres_aLRB2t_minus);
+    #undef UVC_NNM64
+    v.thres[gp] = t;
+}
+
+// ------------------------------------------------------------------------------------------------ segment bias (dealwith_segbias)
+struct SegAcc {
+    uvcgpu_seginfo_set s;
+    int32_t a1BQf, a1BQr, a2BQf, a2BQr;
+    int32_t bqsum;
+};
+
+UVC_HD void segacc_zero(SegAcc & a) {
+    a.s.a2XM2 = a.s.a2BM2 = a.s.aPF1 = a.s.aPF2 = a.s.aBQ2 = a.s.aMQs = a.s.aP1 = a.s.aP2 = a.s.aP3 = a.s.aNC = 0;
+    a.s.aDPff = a.s.aDPfr = a.s.aDPrf = a.s.aDPrr = 0;
+    a.s.aLP1 = a.s.aLP2 = a.s.aLPL = a.s.aRP1 = a.s.aRP2 = a.s.aRPL = 0;
+    a.s.aLB1 = a.s.aLB2 = 0; a.s.aLBL = 0; a.s.aRB1 = a.s.aRB2 = 0; a.s.aRBL = 0;
+    a.s.aLI1 = a.s.aLI2 = a.s.aRI1 = a.s.aRI2 = a.s.aRIf = a.s.aLIr = 0; a.s.aLIT = 0; a.s.aRIT = 0;
+    a.a1BQf = a.a1BQr = a.a2BQf = a.a2BQr = 0; a.bqsum = 0;
+}
+
+// adds an accumulator to the global records of (position gp, symbol sym); kAtomic for the per-read event kernels
+template <bool kAtomic>
+UVC_HD void segacc_flush(const BatchView & v, int64_t gp, int sym, const SegAcc & a) {
+    uvcgpu_seginfo_set & g = v.seginfo[gp * UVC_NSYM + sym];
+    int32_t *vq = v.vq + (gp * UVC_NSYM + sym) * UVCGPU_NUM_VQ_TAGS;
+    int32_t *bq = v.bqsum + gp * UVC_NSYM + sym;
+    #define UVC_ADD(dst, val) { if ((val) != 0) { if (kAtomic) { atomic_add(&(dst), (val)); } else { (dst) += (val); } } }
+    UVC_ADD(g.a2XM2, a.s.a2XM2) UVC_ADD(g.a2BM2, a.s.a2BM2) UVC_ADD(g.aPF1, a.s.aPF1) UVC_ADD(g.aPF2, a.s.aPF2) UVC_ADD(g.aBQ2, a.s.aBQ2)
+    UVC_ADD(g.aMQs, a.s.aMQs) UVC_ADD(g.aP1, a.s.aP1) UVC_ADD(g.aP2, a.s.aP2) UVC_ADD(g.aP3, a.s.aP3) UVC_ADD(g.aNC, a.s.aNC)
+    UVC_ADD(g.aDPff, a.s.aDPff) UVC_ADD(g.aDPfr, a.s.aDPfr) UVC_ADD(g.aDPrf, a.s.aDPrf) UVC_ADD(g.aDPrr, a.s.aDPrr)
+    UVC_ADD(g.aLP1, a.s.aLP1) UVC_ADD(g.aLP2, a.s.aLP2) UVC_ADD(g.aLPL, a.s.aLPL) UVC_ADD(g.aRP1, a.s.aRP1) UVC_ADD(g.aRP2, a.s.aRP2) UVC_ADD(g.aRPL, a.s.aRPL)
+    UVC_ADD(g.aLB1, a.s.aLB1) UVC_ADD(g.aLB2, a.s.aLB2) UVC_ADD(g.aLBL, a.s.aLBL) UVC_ADD(g.aRB1, a.s.aRB1) UVC_ADD(g.aRB2, a.s.aRB2) UVC_ADD(g.aRBL, a.s.aRBL)
+    UVC_ADD(g.aLI1, a.s.aLI1) UVC_ADD(g.aLI2, a.s.aLI2) UVC_ADD(g.aRI1, a.s.aRI1) UVC_ADD(g.aRI2, a.s.aRI2) UVC_ADD(g.aRIf, a.s.aRIf) UVC_ADD(g.aLIr, a.s.aLIr)
+    UVC_ADD(g.aLIT, a.s.aLIT) UVC_ADD(g.aRIT, a.s.aRIT)
+    UVC_ADD(vq[0], a.a1BQf) UVC_ADD(vq[1], a.a1BQr) UVC_ADD(vq[2], a.a2BQf) UVC_ADD(vq[3], a.a2BQr)
+    UVC_ADD(*bq, a.bqsum)
+    #undef UVC_ADD
+}
+
+UVC_HD void bidir_bias(int32_t & lp1, int32_t & lp2, int32_t & rp1, int32_t & rp2, int64_t & lpl, int64_t & rpl,
+        int32_t L1, int32_t L2, int32_t R1, int32_t R2, int32_t nl, int32_t nr, bool tier2, int32_t n_indel) {
+    // update_bidirectional_bias (main.hpp:1318-1358)
+    if (nl + n_indel >= L1) { lp1 += 1; }
+    if ((nl + n_indel >= L2) && tier2) { lp2 += 1; }
+    if (nr >= R1) { rp1 += 1; }
+    if ((nr >= R2) && tier2) { rp2 += 1; }
+    lpl += nl; rpl += nr;
+}
+
+// One call of dealwith_segbias<isGap> (main.hpp:1360-1595) for read R at position rpos with quality bq, into accumulator a.
+template <bool isGap>
+UVC_HD void segbias(SegAcc & a, const BatchView & v, const ReadRec & R, const ReadDerived & D, const uvcgpu_thres_set & th,
+        const int32_t *baq, const int32_t *baq2, int32_t bq, int32_t rpos, int32_t bm1500, bool is_ins_op, int32_t indel_len, int32_t dist_indel) {
+    const uvcgpu_params & par = v.par;
+    const bool is_assay_amplicon = ((R.dflag & 0x4) || ((par.primerlen > 0) && !(0x2 & par.primer_flag)));
+    const bool normal_filters_primers = (par.tn_is_paired && (0x1 & par.primer_flag));
+    const bool is_assay_UMI = (R.dflag & 0x1);
+    const int32_t pos = R.pos, rend = R.rend;
+    const int32_t seg_l_baq1 = baq[rpos] - baq[pos] + 1;
+    const int32_t seg_r_baq0 = baq[rend - 1] - baq[rpos] + 1;
+    const int32_t seg_r_baq1 = (isGap ? tmin(seg_r_baq0, baq2[rend - 1] - baq2[rpos] + 7) : seg_r_baq0);
+    const int32_t seg_l_nbases = rpos - pos + 1;
+    const int32_t seg_r_nbases = rend - rpos;
+    const bool is_high_readlen = (par.central_readlen >= par.microadjust_median_readlen_thres);
+    const int32_t seg_l_baq = (is_high_readlen ? seg_l_baq1 : tmax(seg_l_baq1, seg_l_nbases * par.microadjust_BAQ_per_base_x1024 / 1024));
+    const int32_t seg_r_baq = (is_high_readlen ? seg_r_baq1 : tmax(seg_r_baq1, seg_r_nbases * par.microadjust_BAQ_per_base_x1024 / 1024));
+    const int32_t frag_pos_L = tmin(pos, R.mpos);
+    const int32_t frag_pos_R = frag_pos_L + iabs(R.isize);
+    const int32_t frag_l_nb = ((R.isize != 0) ? tmin(rpos - frag_pos_L + 1, UVC_MAX_INSERT_SIZE) : UVC_MAX_INSERT_SIZE);
+    const int32_t frag_r_nb = ((R.isize != 0) ? tmin(frag_pos_R - rpos, UVC_MAX_INSERT_SIZE) : UVC_MAX_INSERT_SIZE);
+    const bool is_normal = ((R.isize != 0) || (0 == (R.flag & 0x1)));
+    const bool isrc = ((R.flag & 0x10) == 0x10);
+    const bool strand = R.strand;
+
+    if (isrc) { a.a1BQr += bq; a.a2BQr += bq * bq / UVC_SQR_QUAL_DIV; } else { a.a1BQf += bq; a.a2BQf += bq * bq / UVC_SQR_QUAL_DIV; }
+    a.s.aMQs += R.mapq;
+    if (strand) { if (isrc) { a.s.aDPrr += 1; } else { a.s.aDPrf += 1; } } else { if (isrc) { a.s.aDPfr += 1; } else { a.s.aDPff += 1; } }
+    if (tmin(dist_indel, tmin(seg_l_nbases, seg_r_nbases)) >= par.bias_thres_interfering_indel) { a.s.aP3 += 1; }
+    if (0 == D.clip_cnt) { a.s.aNC += 1; }
+    if (isrc) { a.s.aLIT += ((R.isize != 0) ? frag_l_nb : 0); } else { a.s.aRIT += ((R.isize != 0) ? frag_r_nb : 0); }
+
+    const int32_t LPxT0 = th.aLPxT, RPxT = th.aRPxT;
+    const int32_t LPxT = (isGap ? LPxT0 : tmin(LPxT0, RPxT));
+    const bool far_from_edge = (seg_l_nbases + (is_ins_op ? nnminus(indel_len, par.microadjust_nobias_pos_indel_maxlen) : 0) >= LPxT) && (seg_r_nbases >= RPxT);
+    const int32_t highBAQ = par.bias_thres_highBAQ + (isGap ? 0 : 3);
+    const bool unaffected_by_edge = (seg_l_baq >= highBAQ && seg_r_baq >= highBAQ);
+    const int32_t min_dist2iend = ((R.flag & 0x1) ? tmin(frag_l_nb, frag_r_nb) : (isrc ? seg_r_nbases : seg_l_nbases));
+    if (far_from_edge && unaffected_by_edge && (min_dist2iend > par.primerlen2 || !is_assay_amplicon)) { a.s.aP1 += 1; }
+    if (is_assay_UMI || !is_assay_amplicon) { a.s.aP2 += 1; }
+
+    const int32_t f1 = ((bq < par.bias_thres_PFBQ1) ? (100 * (bq * bq) / (par.bias_thres_PFBQ1 * par.bias_thres_PFBQ1)) : 100);
+    const int32_t f2 = ((bq < par.bias_thres_PFBQ2) ? (100 * (bq * bq) / (par.bias_thres_PFBQ2 * par.bias_thres_PFBQ2)) : 100);
+    if (isGap) {
+        a.s.aPF1 += tmin(100, f1);
+        a.s.aPF2 += tmin(100, f2);
+    } else {
+        a.s.aPF1 += (100 * f1 / 100);
+        a.s.aPF2 += (100 * f2 / 100);
+        a.s.a2XM2 += (D.xm1500 > 20 ? (100 * 400 / (D.xm1500 * D.xm1500)) : 100);
+        a.s.a2BM2 += (bm1500 > 20 ? (100 * 400 / (bm1500 * bm1500)) : 100);
+    }
+    if (((!isGap) && bq >= par.bias_thres_highBQ) || (isGap && dist_indel >= par.bias_thres_interfering_indel)) {
+        const bool tier2 = (isGap || bq >= par.bias_thres_highBQ);
+        if (far_from_edge) {
+            int64_t lpl = 0, rpl = 0;
+            bidir_bias(a.s.aLP1, a.s.aLP2, a.s.aRP1, a.s.aRP2, lpl, rpl, th.aLP1t, th.aLP2t, th.aRP1t, th.aRP2t, seg_l_nbases, seg_r_nbases, tier2, indel_len);
+            a.s.aLPL += (int32_t)lpl; a.s.aRPL += (int32_t)rpl;
+        }
+        if (unaffected_by_edge) {
+            bidir_bias(a.s.aLB1, a.s.aLB2, a.s.aRB1, a.s.aRB2, a.s.aLBL, a.s.aRBL, par.bias_thres_BAQ1, par.bias_thres_BAQ2, par.bias_thres_BAQ1, par.bias_thres_BAQ2,
+                    seg_l_baq, seg_r_baq, tier2, 0);
+        }
+        a.s.aBQ2 += 1;
+    }
+    const bool mate_ok = ((0 == (R.flag & 0x8)) || (0 == (R.flag & 0x1)));
+    const bool l_nonbiased = (mate_ok && seg_l_nbases > seg_r_nbases);
+    const bool r_nonbiased = (mate_ok && seg_l_nbases < seg_r_nbases);
+    const bool pos_good = ((!is_assay_amplicon) || (!normal_filters_primers) || (far_from_edge && unaffected_by_edge));
+    if (isrc) {
+        const int32_t d = frag_l_nb;
+        if ((d >= th.aLI1t) && (d <= th.aLI1T || isGap) && (is_normal || (isGap && l_nonbiased))) { a.s.aLI1 += 1; }
+        if ((d >= th.aLI2t) && (d <= th.aLI2T || isGap) && (is_normal || (isGap && l_nonbiased))) { if (pos_good) { a.s.aLI2 += 1; } }
+        if (pos_good) { a.s.aLIr += 1; }
+    } else {
+        const int32_t d = frag_r_nb;
+        if ((d >= th.aRI1t) && (d <= th.aRI1T || isGap) && (is_normal || (isGap && r_nonbiased))) { a.s.aRI1 += 1; }
+        if ((d >= th.aRI2t) && (d <= th.aRI2T || isGap) && (is_normal || (isGap && r_nonbiased))) { if (pos_good) { a.s.aRI2 += 1; } }
+        if (pos_good) { a.s.aRIf += 1; }
+    }
+}
+
+// distance of an aligned base to the nearest low-quality indel of its own read (main.hpp:1897-1916)
+UVC_HD int32_t dist_to_interfering_indel(const BatchView & v, const TileInfo & T, const ReadDerived & D, const Locus & L, const uvcgpu_thres_set & th, int32_t rpos) {
+    if (D.nge_cnt <= 0) { return 10000; }
+    const int32_t adj = v.par.indel_adj_tracklen_dist;
+    const int32_t npos = T.ext_end - T.ext_beg;
+    const uvcgpu_rtr *rtr = v.rtr + T.pos_off;
+    const int32_t ridx = rpos - T.ext_beg;
+    const uvcgpu_rtr rtr1 = rtr[tmax(ridx, adj) - adj];
+    const uvcgpu_rtr rtr2 = rtr[tmin(ridx + adj, npos - 1)];
+    const int32_t prevlen = nnminus(rpos - L.prev_rpos, tmax(rpos - (T.ext_beg + rtr1.begpos), th.aLP1t));
+    const int32_t nextlen = nnminus(L.next_rpos - rpos, tmax((T.ext_beg + rtr2.begpos + rtr2.tracklen) - rpos, th.aRP1t));
+    return tmin(prevlen, nextlen);
+}
+
+// quality weight of "no indel" at the junction before an aligned base (main.hpp:1918-1924)
+UVC_HD int32_t nogap_weight(const BatchView & v, int64_t gp, const ReadDerived & D) {
+    const int32_t noindel = tmin(v.rtr[gp - 1].indelphred, v.rtr[gp].indelphred);
+    return nnminus(tmin(80, noindel), D.micro_nogap_penal) + 1;
+}
+
+// ------------------------------------------------------------------------------------------------ K2: two threads per position
+// Walk #2 (updateByAln<SUM, bias> over aligned bases, main.hpp:1890-2008) gathered per position. role 0 owns the six base symbols,
+// role 1 owns LINK_M. The symbol that matches the reference (role 0) / LINK_M (role 1) is accumulated in registers.
+UVC_HD void k2_position(const BatchView & v, int64_t gp, int role) {
+    const TileInfo & T = v.tiles[v.pos_tile[gp]];
+    const int32_t p = (int32_t)(gp - T.pos_off) + T.ext_beg;
+    const int32_t *baq = v.baq + (T.pos_off - T.ext_beg);
+    const int32_t *baq2 = v.baq2 + (T.pos_off - T.ext_beg);
+    const uvcgpu_thres_set th = v.thres[gp];
+    const int major = (role == 0 ? (int)v.refsym[gp] : UVC_LINK_M);
+    SegAcc acc;
+    segacc_zero(acc);
+    int64_t lo, hi;
+    read_window(v, T, p, lo, hi);
+    for (int64_t ri = lo; ri < hi; ri++) {
+        const ReadRec & R = v.reads[ri];
+        if (R.rend <= p) { continue; }
+        const Locus L = locate(v, R, p);
+        if (!L.is_m) { continue; }
+        const ReadDerived & D = v.rd[ri];
+        if (primer_masked(v, R, D, p)) { continue; }
+        const int32_t dist = dist_to_interfering_indel(v, T, D, L, th, p);
+        if (role == 1) {
+            if (!L.not_first) { continue; }
+            const int32_t w = nogap_weight(v, gp, D);
+            acc.bqsum += w;
+            segbias<true>(acc, v, R, D, th, baq, baq2, w, p, 0 /* bm1500s[LINK_M] */, false, 0, dist);
+        } else {
+            const int sym = base3(v.seq + R.seq_off, L.qpos);
+            const int32_t bq = (int32_t)v.qual[R.qual_off + L.qpos] + v.par.bq_phred_added_misma;
+            if (sym == major) {
+                acc.bqsum += bq;
+                segbias<false>(acc, v, R, D, th, baq, baq2, bq, p, D.bm1500[sym], false, 0, dist);
+            } else {
+                SegAcc one;
+                segacc_zero(one);
+                one.bqsum = bq;
+                segbias<false>(one, v, R, D, th, baq, baq2, bq, p, D.bm1500[sym], false, 0, dist);
+                segacc_flush<false>(v, gp, sym, one);
+            }
+        }
+    }
+    if (major < UVC_NSYM) { segacc_flush<false>(v, gp, major, acc); }
+}
+
+// ------------------------------------------------------------------------------------------------ K2e: one thread per indel event
+// indel_len_rusize_phred (main.hpp:757-790): round(10*log10(i)) for i = 0..18
+UVC_HD int32_t units_phred(int32_t indel_len, int32_t unit) {
+    const int32_t tab[19] = {0, 0, 3, 5, 6, 7, 8, 8, 9, 10, 10, 10, 11, 11, 11, 12, 12, 12, 13};
+    if (0 == (indel_len % unit)) { return tab[tmin(indel_len / unit, 18)]; }
+    return tab[tmin(indel_len, 18)];
+}
+
+UVC_HD int32_t slip_phred_lookup(const BatchView & v, int variant, int32_t unit, int32_t nunits) {
+    // indel_phred (main.hpp:794-801) from the host-evaluated table; beyond the table the closed form is evaluated here
+    if (unit >= 1 && unit <= UVC_SLIP_MAXUNIT && nunits >= 0 && nunits < UVC_SLIP_NMAX) {
+        return v.slip_tab[(variant * UVC_SLIP_MAXUNIT + (unit - 1)) * UVC_SLIP_NMAX + nunits];
+    }
+    const double ampfact = (variant ? v.par.indel_polymerase_slip_rate * v.par.indel_del_to_ins_err_ratio : v.par.indel_polymerase_slip_rate);
+    const int32_t region = unit * nunits;
+    const double num_slips = (region > 64 ? (double)(region - 8) : log1p(exp((double)region - 8.0))) * ampfact / ((double)(unit * unit));
+    return (int32_t)floor(-10 * log((1.0 - 2.220446049250313e-16) / (num_slips + 1.0)) / log(10.0));
+}
+
+// ref_to_phredvalue (main.hpp:876-922): repeat context right of the junction decides the prior quality of an indel there
+UVC_HD int32_t indel_prior_phred(int32_t & n_units, int32_t & max_num, int32_t & best_unit, const BatchView & v, const TileInfo & T,
+        int32_t rpos, int32_t oplen, bool is_del) {
+    const uint8_t *ref = v.refsym + T.pos_off;
+    const int32_t n = (T.ext_end - T.ext_beg) - 1;
+    const int32_t refpos = rpos - T.ext_beg;
+    const int32_t str_max = v.par.indel_str_repeatsize_max;
+    max_num = 0; best_unit = 0;
+    for (int32_t unit = 1; unit <= str_max; unit++) {
+        int32_t q = refpos;
+        while (q + unit < n && ref[q] == ref[q + unit]) { q++; }
+        const int32_t num = (q - refpos) / unit + 1;
+        // is_indel_context_more_STR (main.hpp:699-721) with its rank2 quirk
+        bool better;
+        if (best_unit * max_num == 0) { better = true; }
+        else if (unit > str_max || best_unit > str_max) { better = (unit < best_unit || (unit == best_unit && num > max_num)); }
+        else {
+            int rank1 = (num <= 1 ? (-num * unit) : ((num - 1) * unit));
+            int rank2 = (max_num <= 1 ? (-max_num * unit) : ((max_num - 1) * best_unit));
+            if (0 == num || 0 == unit) { rank1 = -100; }
+            if (0 == max_num || 0 == best_unit) { rank2 = -100; }
+            better = (rank1 > rank2);
+        }
+        if (better) { max_num = num; best_unit = unit; }
+    }
+    const int variant = ((oplen == best_unit && is_del) ? 1 : 0);
+    const int32_t decphred = slip_phred_lookup(v, variant, best_unit, max_num);
+    if (best_unit * (max_num - 1) >= 6 - 1) {
+        n_units = ((0 == oplen % best_unit) ? (oplen / best_unit) : ((1 == oplen) ? 1 : 0));
+    } else {
+        n_units = 1 + (oplen / 6);
+    }
+    const int32_t max_phred = v.par.indel_BQ_max;
+    return max_phred - tmin(max_phred, decphred) + units_phred(oplen, best_unit);
+}
+
+// Evaluates one insertion/deletion of one read (main.hpp:2009-2257) once: its symbol and quality weights are stored in the event for the
+// fragment/family kernels, and the bias walk's contributions (including the BASE_NN/LINK_NN paddings of a deletion) are added here.
+UVC_HD void k2e_event(const BatchView & v, int64_t ei) {
+    IndelEvent & E = v.ev[ei];
+    const ReadRec & R = v.reads[E.read];
+    const ReadDerived & D = v.rd[E.read];
+    const TileInfo & T = v.tiles[R.tile];
+    const uvcgpu_params & par = v.par;
+    const int64_t po = T.pos_off - T.ext_beg;
+    const int32_t *baq = v.baq + po;
+    const int32_t *baq2 = v.baq2 + po;
+    const uint8_t *qual = v.qual + R.qual_off;
+    const int32_t rpos = E.rpos, qpos = E.qpos, oplen = E.oplen, rend = R.rend, pos = R.pos;
+    const bool isrc = ((R.flag & 0x10) == 0x10);
+    E.counted = 0; E.symbol = -1; E.incvalue = 0; E.incvalue2 = 0;
+    if (primer_masked(v, R, D, rpos)) { return; }
+    const uvcgpu_prep_set & pp = v.prep[po + rpos];
+    const int32_t added = par.bq_phred_added_indel;
+    const int32_t ratiothres = (par.is_tumor_vcf_provided ? 4 : 2);
+    int32_t incvalue = 1;
+    int32_t n_units = oplen;
+    int32_t nbases2end;
+    if (!E.is_del) {
+        nbases2end = tmin(qpos, R.l_qseq - (qpos + oplen));
+        if (nbases2end <= 0) {
+            incvalue = (0 != qpos ? (int32_t)qual[qpos - 1] : ((qpos + oplen < R.l_qseq) ? (int32_t)qual[qpos + oplen] : 1)) + added;
+        } else {
+            int32_t max_num, unit;
+            int32_t phredvalue = indel_prior_phred(n_units, max_num, unit, v, T, rpos, oplen, false);
+            const int32_t phredinc = (int32_t)round(2 * (v.ten_over_ln10 * log((double)pp.a_dp / (double)(1.0 + nnminus(pp.a_dp, pp.a_at_ins_dp + pp.a_at_del_dp)))));
+            const bool multiallelic = (pp.a_near_ins_pow2len * ratiothres > (int64_t)tmax(1, pp.a_near_ins_dp) * (int64_t)((uint32_t)oplen * 3u));
+            if (1 == n_units && !multiallelic) { phredvalue += between(phredinc - 3, 0, 4); }
+            const int32_t thisdp = pp.a_at_ins_dp;
+            const int32_t neardp = tmax(pp.a_near_ins_dp, pp.a_near_RTR_ins_dp);
+            int32_t ins_min = 80;
+            for (int32_t q2 = qpos; q2 < qpos + oplen; q2++) { ins_min = tmin(ins_min, (int32_t)qual[q2]); }
+            int32_t anc_min = 80;
+            if (qpos > 0) { anc_min = tmin(anc_min, (int32_t)qual[qpos - 1]); }
+            if (qpos + oplen + 1 < R.l_qseq) { anc_min = tmin(anc_min, (int32_t)qual[qpos + oplen + 1]); } // QUIRK: + 1 (main.hpp:2055-2056)
+            const int32_t q1 = tmin(anc_min, ins_min);
+            const bool lenient = (thisdp * ratiothres <= neardp || (1 == oplen && (D.xm1500 >= par.microadjust_xm
+                    || ((D.lclip + par.microadjust_cliplen >= rpos - pos) && isrc)
+                    || ((D.rclip + par.microadjust_cliplen >= rend - pos) && !isrc))));
+            const int32_t q2v = (lenient ? q1 : 80);
+            incvalue = nnminus(tmin(q2v, phredvalue + added), D.micro_indel_penal) + 1;
+        }
+        if (nbases2end >= par.indel_filter_edge_dist) {
+            E.symbol = (1 == n_units ? UVC_LINK_I1 : ((2 == n_units) ? UVC_LINK_I2 : UVC_LINK_I3P));
+            E.incvalue = tmax(1, incvalue);
+            int32_t inc2 = incvalue;
+            for (int32_t q2 = qpos; q2 < qpos + oplen; q2++) { inc2 = tmin(inc2, (int32_t)qual[q2] + added); }
+            E.incvalue2 = tmax(1, inc2);
+            E.counted = 1;
+            SegAcc a; segacc_zero(a);
+            a.bqsum = E.incvalue;
+            segbias<true>(a, v, R, D, v.thres[po + rpos], baq, baq2, E.incvalue, rpos, 0, true, oplen, 10000);
+            segacc_flush<true>(v, po + rpos, E.symbol, a);
+        }
+    } else {
+        nbases2end = tmin(qpos, R.l_qseq - qpos);
+        if (nbases2end <= 0) {
+            incvalue = (0 != qpos ? (int32_t)qual[qpos - 1] : ((qpos < R.l_qseq) ? (int32_t)qual[qpos] : 1)) + added;
+        } else {
+            int32_t max_num, unit;
+            int32_t phredvalue = indel_prior_phred(n_units, max_num, unit, v, T, rpos, oplen, true);
+            const int32_t phredinc = (int32_t)round(2 * (v.ten_over_ln10 * log((double)pp.a_dp / (double)(1.0 + nnminus(pp.a_dp, pp.a_at_ins_dp + pp.a_at_del_dp)))));
+            if (1 == n_units) { phredvalue += between(phredinc - 3, 0, 4); }
+            const int32_t thisdp = pp.a_at_del_dp;
+            const int32_t neardp = tmax(pp.a_near_del_dp, pp.a_near_RTR_del_dp);
+            const int32_t q1 = tmin(tmin((int32_t)qual[qpos], (int32_t)qual[qpos - 1]), 80);
+            const int32_t q2v = ((thisdp * ratiothres <= neardp) ? nnminus(q1, 1) : 80);
+            const double delFA = ((double)(thisdp + 0.5) / (double)(pp.a_dp + 1));
+            const int32_t delFAQ = tmax(0, par.microadjust_delFAQmax + (int32_t)round(par.powlaw_exponent * (v.ten_over_ln10 * log(delFA))));
+            const uint32_t *cigar = v.cigar + R.cigar_off;
+            // flanking BAQ up to an insertion of the same length, or else to the read ends (main.hpp:2167-2186)
+            int32_t pc = E.cigar_idx, prev_rpos = rpos;
+            while ((0 != pc) && (UVC_CINS != cig_op(cigar[pc]) || oplen != cig_len(cigar[pc]))) {
+                pc--;
+                const int op2 = cig_op(cigar[pc]);
+                if (is_match_op(op2) || op2 == UVC_CDEL || op2 == UVC_CREF_SKIP) { prev_rpos -= cig_len(cigar[pc]); }
+            }
+            int32_t nc = E.cigar_idx, next_rpos = rpos + oplen;
+            while ((R.n_cigar - 1 != nc) && (UVC_CINS != cig_op(cigar[nc]) || oplen != cig_len(cigar[nc]))) {
+                nc++;
+                const int op2 = cig_op(cigar[nc]);
+                if (is_match_op(op2) || op2 == UVC_CDEL || op2 == UVC_CREF_SKIP) { next_rpos += cig_len(cigar[nc]); }
+            }
+            const int32_t baq_l = baq[rpos] - baq[prev_rpos];
+            const int32_t baq_r = baq[next_rpos] - baq[rpos + oplen];
+            const int32_t qbaq = tmax(delFAQ, tmax(q1, tmin(baq_l, baq_r)));
+            incvalue = nnminus(tmin(q2v, tmin(qbaq, phredvalue + added)), D.micro_indel_penal) + 1;
+        }
+        if (nbases2end >= par.indel_filter_edge_dist) {
+            E.symbol = (1 == n_units ? UVC_LINK_D1 : ((2 == n_units) ? UVC_LINK_D2 : UVC_LINK_D3P));
+            E.incvalue = tmax(1, incvalue);
+            E.incvalue2 = E.incvalue;
+            E.counted = 1;
+            {
+                SegAcc a; segacc_zero(a);
+                a.bqsum = E.incvalue;
+                segbias<true>(a, v, R, D, v.thres[po + rpos], baq, baq2, E.incvalue, rpos, 0, false, oplen, 10000);
+                segacc_flush<true>(v, po + rpos, E.symbol, a);
+            }
+            // padded-deletion symbols: BASE_NN on every deleted base, LINK_NN on the junction after it (main.hpp:2219-2253)
+            for (int32_t r2 = rpos; r2 < tmin(rpos + oplen, rend); r2++) {
+                const CxEntry c = v.cx[R.cx_off + (r2 - pos)];
+                for (int s = 0; s < 2; s++) {
+                    const int32_t p2 = (s == 0 ? r2 : r2 + 1);
+                    if (p2 >= rend) { continue; }
+                    SegAcc a; segacc_zero(a);
+                    a.bqsum = E.incvalue;
+                    segbias<true>(a, v, R, D, v.thres[po + p2], baq, baq2, E.incvalue, p2, 0, false, oplen, (s == 0 ? c.prev_rpos : c.next_rpos));
+                    segacc_flush<true>(v, po + p2, (s == 0 ? UVC_BASE_NN : UVC_LINK_NN), a);
+                }
+            }
+        }
+    }
+}
+
+} // namespace uvc
+
+#endif
