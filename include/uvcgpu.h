@@ -98,7 +98,8 @@ typedef struct uvcgpu_params {
     int32_t microadjust_median_readlen_thres, microadjust_BAQ_per_base_x1024;
     /* phasing */
     int32_t phasing_haplotype_max_count, phasing_haplotype_min_ad, phasing_haplotype_max_detail_cnt;
-    int32_t reserved[16];
+    int32_t tumor_vcf_fname_nonempty;     /* vcf_tumor_fname.size() > 0: true even for the default "." (QUIRK, main.hpp:2564, 2858) */
+    int32_t reserved[15];
 } uvcgpu_params;
 
 /* One tier-3 region (the reference's BedLine, iohts.hpp:14-35) plus the previous one, as process_batch receives

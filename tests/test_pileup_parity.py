@@ -10,8 +10,9 @@ import pytest
 
 import parity_util as pu
 
-SECTIONS = ["meta", "families", "rtr_initial", "baq", "baq2", "prep", "thres", "rtr", "seginfo", "vq"]
-IMPLEMENTED_VQ_TAGS = 4   # VQ_a1BQf, a1BQr, a2BQf, a2BQr
+SECTIONS = ["meta", "families", "rtr_initial", "baq", "baq2", "prep", "thres", "rtr", "seginfo", "vq", "fragdepth0", "fragdepth1",
+            "famdepth0", "famdepth1", "faminfo", "duplex"]
+IMPLEMENTED_VQ_TAGS = 14   # VQ_a1BQf .. VQ_cIDQr: everything updateByRegion3Aln fills (main_conversion.hpp:743-762)
 
 
 def _check(info, tiles, emulate, tmp_path, extra=()):
@@ -29,7 +30,9 @@ def _check(info, tiles, emulate, tmp_path, extra=()):
         ext_beg = int(ref["meta"][6])
         msgs = []
         for ours_name, ref_name in [("rtr_initial", "rtr_initial"), ("baq", "baq"), ("baq2", "baq2"), ("prep", "prep"),
-                                    ("thres", "thres"), ("rtr", "rtr_final"), ("seginfo", "seginfo")]:
+                                    ("thres", "thres"), ("rtr", "rtr_final"), ("seginfo", "seginfo"), ("fragdepth0", "fragdepth0"),
+                                    ("fragdepth1", "fragdepth1"), ("famdepth0", "famdepth0"), ("famdepth1", "famdepth1"),
+                                    ("faminfo", "faminfo"), ("duplex", "duplex")]:
             msgs += pu.diff_section(ours_name, o[ours_name], ref[ref_name], ext_beg)
         msgs += pu.diff_section("vq", o["vq"][:, :, :IMPLEMENTED_VQ_TAGS], ref["vq"][:, :, :IMPLEMENTED_VQ_TAGS], ext_beg)
         assert not msgs, "\n".join(msgs[:40])

@@ -64,6 +64,7 @@ struct ReadRec {
     int32_t simple, m_qoff, cx_off;                    // cx_off: offset of its per-reference-base expansion (complex reads), -1 otherwise
     int32_t ev_off, n_ev;                              // indel events of this read
     int32_t fragprev_maxrend, famprev_maxrend;         // max rend over earlier reads of the same fragment / (family,strand); INT32_MIN if none
+    int32_t fambothprev_maxrend;                       // same over both strands of the family
 };
 
 // Derived per-read constants (kernel K0).
@@ -120,6 +121,8 @@ struct BatchView {
     double center_pow[4];          // pow(dedup_center_mult, d) computed with the host libm
     int32_t indelphred_half;       // (int)round(numstates2phred(indel_del_to_ins_err_ratio)) / 2 (main.hpp:1244)
     double ten_over_ln10;          // 10.0 / log(10.0) as the host libm evaluates it
+    double ln10;                   // log(10)
+    const double *phred2prob_tab;  // [128] phred2prob(q) = pow(10, -((float)q) / 10) (main_conversion.hpp:885-888) evaluated with the host libm
     const int32_t *slip_tab;       // [2][UVC_SLIP_MAXUNIT][UVC_SLIP_NMAX] indel_phred (main.hpp:794-801) evaluated with the host libm
     int32_t n_tiles;
     int64_t n_pos, n_reads, n_frags, n_fams, n_cx, n_ev;
@@ -149,6 +152,18 @@ struct BatchView {
     int32_t *famdepth;             // [2][n_pos][14][8]
     uvcgpu_faminfo_set *faminfo;   // [n_pos][14]
     int32_t *duplex;               // [n_pos][14][2]
+    // sparse outputs (indel identities, haplotype strings): a stream of int32 records appended with one atomic cursor
+    int32_t *rec_buf; int32_t *rec_cursor; int32_t rec_cap;
 };
+
+// record stream entry kinds; fixed records are 6 words {kind, strand, symbol, pos, event index, count}
+#define UVC_REC_FRAG_INDEL 1     // fragment-level indel identity   -> symbol_to_frag_format_depth_sets[strand] maps (main.hpp:2710-2717)
+#define UVC_REC_FAM_INDEL 2      // family-level                    -> symbol_to_fam_format_depth_sets_2strand[strand] maps (main.hpp:3327-3336)
+#define UVC_REC_CDP2_INDEL 3     // tier-2 consensus families       -> pos2iseq2data_cDP2 / pos2dlen2data_cDP2 (main.hpp:3197-3206)
+#define UVC_REC_C2D_INDEL 4      // single-strand / duplex consensus -> pos2iseq2data_c2dDP / pos2dlen2data_c2dDP (main.hpp:3460-3469, 3536-3545)
+// haplotype strings are variable-length: {kind, strand, n, owner} followed by n pairs {pos, symbol}
+#define UVC_REC_HAP_BQ 10
+#define UVC_REC_HAP_FQ 11
+#define UVC_REC_HAP_F2Q 12
 
 #endif

@@ -10,6 +10,7 @@
 #include "host_prep.h"
 #include "kernels_core.cuh"
 
+#include <algorithm>
 #include <chrono>
 #include <map>
 #include <memory>
@@ -44,7 +45,7 @@ struct BatchState {
     uvcgpu_batch_stats stats;
     bool collected = false;
 #if UVC_CUDA
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[12];
     bool have_events = false;
 #endif
 };
@@ -84,6 +85,10 @@ __device__ __forceinline__ void k2_item(const BatchView & v, int64_t i) {
     if (gp < v.n_pos) { uvc::k2_position(v, gp, within / 64); }
 }
 __device__ __forceinline__ void k2e_item(const BatchView & v, int64_t i) { uvc::k2e_event(v, i); }
+__device__ __forceinline__ void k3a_item(const BatchView & v, int64_t i) { uvc::k3a_fragment(v, i); }
+__device__ __forceinline__ void k3b_item(const BatchView & v, int64_t i) { uvc::k3b_position(v, i); }
+__device__ __forceinline__ void k4a_item(const BatchView & v, int64_t i) { uvc::k4a_family_strand(v, i); }
+__device__ __forceinline__ void k4_item(const BatchView & v, int64_t i) { uvc::k4_position(v, i); }
 
 template <void (*F)(const BatchView &, int64_t)>
 static void launch(cudaStream_t s, const BatchView & v, int64_t n, int64_t & launches) {
@@ -113,7 +118,7 @@ static void backend_free(BatchState & bs) { for (void *p : bs.allocs) { cudaFree
 static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     const BatchView & v = bs.view;
     int64_t launches = 0;
-    for (int i = 0; i < 8; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreate(&bs.ev[i])); }
+    for (int i = 0; i < 12; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreate(&bs.ev[i])); }
     bs.have_events = true;
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[0], ctx->stream));
     launch<k0_item>(ctx->stream, v, v.n_reads, launches);
@@ -124,6 +129,14 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[3], ctx->stream));
     launch<k2e_item>(ctx->stream, v, v.n_ev, launches);
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[4], ctx->stream));
+    launch<k3a_item>(ctx->stream, v, v.n_frags, launches);
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[5], ctx->stream));
+    launch<k3b_item>(ctx->stream, v, v.n_pos, launches);
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[6], ctx->stream));
+    launch<k4a_item>(ctx->stream, v, 2 * v.n_fams, launches);
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[7], ctx->stream));
+    launch<k4_item>(ctx->stream, v, v.n_pos, launches);
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[8], ctx->stream));
     UVC_CUDA_CHECK(ctx, cudaGetLastError());
     bs.stats.gpu_launches = launches;
     return 0;
@@ -134,13 +147,13 @@ static int backend_wait(uvcgpu_ctx *ctx, BatchState & bs) {
     if (bs.have_events) {
         float ms = 0;
         double total = 0;
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < 8; i++) {
             UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, bs.ev[i], bs.ev[i + 1]));
             bs.stats.kernel_ms_by_stage[i] = ms;
             total += ms;
         }
         bs.stats.kernel_ms = total;
-        for (int i = 0; i < 8; i++) { cudaEventDestroy(bs.ev[i]); }
+        for (int i = 0; i < 12; i++) { cudaEventDestroy(bs.ev[i]); }
         bs.have_events = false;
     }
     return 0;
@@ -167,6 +180,10 @@ static int backend_run(uvcgpu_ctx *, BatchState & bs) {
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::k1_position(v, i); }
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::k2_position(v, i, 0); uvc::k2_position(v, i, 1); }
     for (int64_t i = 0; i < v.n_ev; i++) { uvc::k2e_event(v, i); }
+    for (int64_t i = 0; i < v.n_frags; i++) { uvc::k3a_fragment(v, i); }
+    for (int64_t i = 0; i < v.n_pos; i++) { uvc::k3b_position(v, i); }
+    for (int64_t i = 0; i < 2 * v.n_fams; i++) { uvc::k4a_family_strand(v, i); }
+    for (int64_t i = 0; i < v.n_pos; i++) { uvc::k4_position(v, i); }
     bs.stats.gpu_launches = 0;
     return 0;
 }
@@ -219,6 +236,7 @@ void uvcgpu_params_default(uvcgpu_params *p) {
     p->microadjust_xm = 7; p->microadjust_cliplen = 5; p->microadjust_delFAQmax = 49; p->microadjust_nobias_pos_indel_maxlen = 16;
     p->microadjust_near_clip_dist = 2; p->microadjust_alignment_clip_min_len = 12; p->microadjust_padded_deletion_flag = 0x2;
     p->microadjust_median_readlen_thres = 125; p->microadjust_BAQ_per_base_x1024 = 1024;
+    p->tumor_vcf_fname_nonempty = 1;
     p->phasing_haplotype_max_count = 8; p->phasing_haplotype_min_ad = 1; p->phasing_haplotype_max_detail_cnt = 3;
 }
 
@@ -306,6 +324,7 @@ int uvcgpu_submit(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, co
     memset(&v, 0, sizeof(v));
     uvc_fill_view_constants(v, ctx->par);
     v.ten_over_ln10 = 10.0 / log(10.0);
+    v.ln10 = log(10);
     v.n_tiles = n_tiles;
     v.n_pos = hb.n_pos; v.n_reads = (int64_t)hb.reads.size(); v.n_frags = (int64_t)hb.frags.size(); v.n_fams = (int64_t)hb.fams.size();
     v.n_cx = hb.n_cx; v.n_ev = hb.n_ev;
@@ -313,6 +332,11 @@ int uvcgpu_submit(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, co
 #define UVC_UP(field, type, vec) { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (vec).size() * sizeof(type), false)); \
         UVC_TRY(backend_upload(ctx, *bs, d_, (vec).data(), (vec).size() * sizeof(type))); v.field = (type*)d_; }
 #define UVC_ZERO(field, type, count) { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)(count) * sizeof(type), true)); v.field = (type*)d_; }
+    {
+        std::vector<double> tab(128);
+        for (int q = 0; q < 128; q++) { tab[q] = pow(10, -((float)q) / 10); }   // phred2prob (main_conversion.hpp:885-888): float exponent, double pow
+        UVC_UP(phred2prob_tab, double, tab)
+    }
     UVC_UP(tiles, TileInfo, hb.tiles)
     UVC_UP(pos_tile, int32_t, hb.pos_tile)
     UVC_UP(refsym, uint8_t, hb.refsym)
@@ -340,6 +364,9 @@ int uvcgpu_submit(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, co
     UVC_ZERO(faminfo, uvcgpu_faminfo_set, v.n_pos * UVC_NSYM)
     UVC_ZERO(duplex, int32_t, v.n_pos * UVC_NSYM * UVCGPU_NUM_DUPLEX_DEPTHS)
     v.frags_in = v.frags;
+    v.rec_cap = (int32_t)std::min<int64_t>((int64_t)1 << 30, 16 * v.n_reads + (1 << 20));
+    UVC_ZERO(rec_buf, int32_t, v.rec_cap)
+    UVC_ZERO(rec_cursor, int32_t, 4)
     const double t2 = now_ms();
     UVC_TRY(backend_run(ctx, *bs));
     uvcgpu_batch_stats & st = bs->stats;

@@ -507,6 +507,7 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
         int32_t max_span = 0;
         std::unordered_map<int32_t, int32_t> frag_maxrend;
         std::unordered_map<int64_t, int32_t> fam_maxrend;
+        std::unordered_map<int32_t, int32_t> famboth_maxrend;
         for (size_t i = 0; i < kept.size(); i++) {
             const Kept & k = kept[i];
             ReadRec R;
@@ -543,6 +544,9 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
             auto mit = fam_maxrend.find(fkey);
             R.famprev_maxrend = (mit == fam_maxrend.end() ? INT32_MIN : mit->second);
             if (mit == fam_maxrend.end()) { fam_maxrend[fkey] = R.rend; } else { mit->second = std::max(mit->second, R.rend); }
+            auto bit = famboth_maxrend.find(R.fam);
+            R.fambothprev_maxrend = (bit == famboth_maxrend.end() ? INT32_MIN : bit->second);
+            if (bit == famboth_maxrend.end()) { famboth_maxrend[R.fam] = R.rend; } else { bit->second = std::max(bit->second, R.rend); }
             max_span = std::max(max_span, R.rend - R.pos);
             hb.reads.push_back(R);
             hb.read_raw_index.push_back(k.raw);

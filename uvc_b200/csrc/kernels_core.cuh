@@ -805,6 +805,581 @@ UVC_HD void k2e_event(const BatchView & v, int64_t ei) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ fragment-level helpers
+UVC_HD void votes_zero(int32_t c[UVC_NSYM]) { for (int s = 0; s < UVC_NSYM; s++) { c[s] = 0; } }
+
+// What one read asserts at position p, max-merged into c: updateByAln<BASE_QUALITY_MAX, false, *> (main.hpp:1886-2257, walks #3-#5)
+UVC_HD void read_votes(const BatchView & v, int64_t ri, int32_t p, int64_t gp, int32_t c[UVC_NSYM]) {
+    const ReadRec & R = v.reads[ri];
+    if (p < R.pos || p >= R.rend) { return; }
+    const ReadDerived & D = v.rd[ri];
+    const Locus L = locate(v, R, p);
+    if (L.is_m && !primer_masked(v, R, D, p)) {
+        if (L.not_first) { c[UVC_LINK_M] = tmax(c[UVC_LINK_M], nogap_weight(v, gp, D)); }
+        const int sym = base3(v.seq + R.seq_off, L.qpos);
+        c[sym] = tmax(c[sym], (int32_t)v.qual[R.qual_off + L.qpos] + v.par.bq_phred_added_misma);
+    }
+    if (!R.simple) {
+        for (int32_t e = 0; e < R.n_ev; e++) {
+            const IndelEvent & E = v.ev[R.ev_off + e];
+            if (!E.counted) { continue; }
+            if (E.rpos == p) { c[E.symbol] = tmax(c[E.symbol], E.incvalue); }
+            if (E.is_del) {
+                const int32_t del_end = tmin(E.rpos + E.oplen, R.rend);
+                if (p >= E.rpos && p < del_end) { c[UVC_BASE_NN] = tmax(c[UVC_BASE_NN], E.incvalue); }
+                if (p - 1 >= E.rpos && p - 1 < del_end) { c[UVC_LINK_NN] = tmax(c[UVC_LINK_NN], E.incvalue); }
+            }
+        }
+    }
+}
+
+UVC_HD bool frag_covers(const BatchView & v, const FragRec & G, int32_t p) {
+    for (int32_t k = 0; k < G.n_reads; k++) { const ReadRec & R = v.reads[v.frag_reads[G.read_off + k]]; if (R.pos <= p && p < R.rend) { return true; } }
+    return false;
+}
+
+UVC_HD void frag_votes(const BatchView & v, const FragRec & G, int32_t p, int64_t gp, int32_t c[UVC_NSYM]) {
+    votes_zero(c);
+    for (int32_t k = 0; k < G.n_reads; k++) { read_votes(v, v.frag_reads[G.read_off + k], p, gp, c); }
+}
+
+// _fillConsensusCounts (main.hpp:374-402). ref_once = TIsRefCountedOnlyOnce (link symbols only).
+UVC_HD void consensus(const int32_t c[UVC_NSYM], int lo, int hi, bool ref_once, int & argmax, int32_t & cmax, int32_t & csum) {
+    argmax = hi; cmax = 0; csum = 0;
+    for (int s = lo; s <= hi; s++) {
+        if (ref_once) {
+            if (cmax < c[s] || (UVC_LINK_M == argmax && (0 < c[s]))) { argmax = s; cmax = c[s]; csum = cmax; }
+        } else {
+            if (cmax < c[s]) { argmax = s; cmax = c[s]; }
+            csum += c[s];
+        }
+    }
+}
+UVC_HD void link_consensus(const int32_t c[UVC_NSYM], bool ref_once, int & argmax, int32_t & cmax, int32_t & csum) { consensus(c, UVC_LINK_M, UVC_LINK_NN, ref_once, argmax, cmax, csum); }
+UVC_HD void base_consensus(const int32_t c[UVC_NSYM], bool ignore_padded_del, int & argmax, int32_t & cmax, int32_t & csum) {
+    consensus(c, UVC_BASE_A, (ignore_padded_del ? UVC_BASE_T : UVC_BASE_NN), false, argmax, cmax, csum);
+}
+
+UVC_HD bool symbols_mutated(int ref, int alt) { // areSymbolsMutated (main_conversion.hpp:364-371)
+    if (alt <= UVC_BASE_NN) { return ref != alt && ref < UVC_BASE_N && alt < UVC_BASE_N; }
+    return alt != UVC_LINK_M && alt != UVC_LINK_NN;
+}
+
+UVC_HD int32_t avg_bq(const BatchView & v, int64_t gp, int s) { // get_avgBQ (main_conversion.hpp:791-796)
+    const uvcgpu_seginfo_set & g = v.seginfo[gp * UVC_NSYM + s];
+    return v.bqsum[gp * UVC_NSYM + s] / tmax(1, g.aDPff + g.aDPfr + g.aDPrf + g.aDPrr);
+}
+
+// PhredMutationTable::toPhredErrRate (main.hpp:238-261)
+UVC_HD int32_t sscs_phred(const uvcgpu_params & par, int con, int alt) {
+    int32_t r;
+    if (is_ins_symbol(con) || is_del_symbol(con)) { r = par.fam_phred_sscs_indel_open; }
+    else if (con == UVC_LINK_M) {
+        if (alt == UVC_LINK_D1 || alt == UVC_LINK_I1) { r = par.fam_phred_sscs_indel_open; }
+        else if (alt == UVC_LINK_D2 || alt == UVC_LINK_I2) { r = par.fam_phred_sscs_indel_open + par.fam_phred_sscs_indel_ext; }
+        else { r = par.fam_phred_sscs_indel_open + par.fam_phred_sscs_indel_ext * 2; }
+    }
+    else if ((con == UVC_BASE_C && alt == UVC_BASE_T) || (con == UVC_BASE_G && alt == UVC_BASE_A)) { r = par.fam_phred_sscs_transition_CG_TA; }
+    else if ((con == UVC_BASE_A && alt == UVC_BASE_G) || (con == UVC_BASE_T && alt == UVC_BASE_C)) { r = par.fam_phred_sscs_transition_AT_GC; }
+    else if ((con == UVC_BASE_C && alt == UVC_BASE_A) || (con == UVC_BASE_G && alt == UVC_BASE_T)) { r = par.fam_phred_sscs_transversion_CG_AT; }
+    else { r = par.fam_phred_sscs_transversion_other; }
+    return r + (par.tumor_vcf_fname_nonempty ? 3 : 0); // all_mutation_inc (main.hpp:236)
+}
+
+// appends n words to the record stream; returns the write offset or -1 if the stream is full (the cursor keeps growing so the host sees the overflow)
+UVC_HD int32_t rec_alloc(const BatchView & v, int32_t n) {
+#if defined(__CUDA_ARCH__)
+    const int32_t off = atomicAdd(v.rec_cursor, n);
+#else
+    const int32_t off = *v.rec_cursor; *v.rec_cursor += n;
+#endif
+    return (off + n <= v.rec_cap ? off : -1);
+}
+UVC_HD void rec_put6(const BatchView & v, int32_t kind, int32_t strand, int32_t symbol, int32_t pos, int32_t evidx, int32_t cnt) {
+    const int32_t off = rec_alloc(v, 6);
+    if (off < 0) { return; }
+    int32_t *w = v.rec_buf + off;
+    w[0] = kind; w[1] = strand; w[2] = symbol; w[3] = pos; w[4] = evidx; w[5] = cnt;
+}
+
+// ASCII letter of a 4-bit base code ("=ACMGRSVTWYHKDBN"), used to order inserted sequences like std::string does
+UVC_HD int nt16_ascii(int b4) { const char *t = "=ACMGRSVTWYHKDBN"; return (int)t[b4 & 0xf]; }
+
+// -1 / 0 / +1 comparison of the identities of two indel events of the same symbol class: deletion length, or inserted sequence as a string
+UVC_HD int indel_cmp(const BatchView & v, const IndelEvent & A, const IndelEvent & B) {
+    if (A.is_del) { return (A.oplen < B.oplen ? -1 : (A.oplen > B.oplen ? 1 : 0)); }
+    const uint8_t *sa = v.seq + v.reads[A.read].seq_off, *sb = v.seq + v.reads[B.read].seq_off;
+    const int32_t n = tmin(A.oplen, B.oplen);
+    for (int32_t i = 0; i < n; i++) {
+        const int ca = nt16_ascii(base4(sa, A.qpos + i)), cb = nt16_ascii(base4(sb, B.qpos + i));
+        if (ca != cb) { return (ca < cb ? -1 : 1); }
+    }
+    return (A.oplen < B.oplen ? -1 : (A.oplen > B.oplen ? 1 : 0));
+}
+
+// posToIndelToCount_updateByConsensus + indelToData_getMajority (main.hpp:50-63, 83-95) over the indel events of class `symbol` that the
+// reads [reads, reads + n) show at position p: the identity with the largest summed weight wins, ties go to the larger key.
+// Returns the global index of a representative event, or -1.
+UVC_HD int32_t indel_majority_of_reads(const BatchView & v, const int32_t *reads, int32_t n, int32_t p, int symbol) {
+    int32_t best = -1; int64_t best_w = 0;
+    for (int32_t k = 0; k < n; k++) {
+        const ReadRec & R = v.reads[reads[k]];
+        if (R.simple || p < R.pos || p >= R.rend) { continue; }
+        for (int32_t e = 0; e < R.n_ev; e++) {
+            const IndelEvent & E = v.ev[R.ev_off + e];
+            if (!E.counted || E.rpos != p || E.symbol != symbol) { continue; }
+            // summed weight of this identity over all reads
+            int64_t w = 0;
+            bool is_first = true;
+            for (int32_t k2 = 0; k2 < n; k2++) {
+                const ReadRec & R2 = v.reads[reads[k2]];
+                if (R2.simple || p < R2.pos || p >= R2.rend) { continue; }
+                for (int32_t e2 = 0; e2 < R2.n_ev; e2++) {
+                    const IndelEvent & E2 = v.ev[R2.ev_off + e2];
+                    if (!E2.counted || E2.rpos != p || E2.symbol != symbol) { continue; }
+                    if (0 == indel_cmp(v, E, E2)) {
+                        w += (E2.is_del ? E2.incvalue : E2.incvalue2);
+                        if (k2 < k || (k2 == k && e2 < e)) { is_first = false; }
+                    }
+                }
+            }
+            if (!is_first) { continue; }
+            if (best < 0 || w > best_w || (w == best_w && indel_cmp(v, E, v.ev[best]) > 0)) { best = R.ev_off + e; best_w = w; }
+        }
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------------ K3a: one thread per fragment
+// Whole-fragment statistics of updateByAlns3UsingBQ (main.hpp:2650-2756): number of covered positions, number of covered positions within
+// +-syserr_mut_region_n_bases of a high-quality mutation, and the fragment's string of mutations (haplotype evidence).
+UVC_HD void k3a_fragment(const BatchView & v, int64_t fi) {
+    FragRec & G = v.frags[fi];
+    const TileInfo & T = v.tiles[G.tile];
+    const uvcgpu_params & par = v.par;
+    const int64_t po = T.pos_off - T.ext_beg;
+    int32_t lo = INT32_MAX, hi = 0;
+    for (int32_t k = 0; k < G.n_reads; k++) { const ReadRec & R = v.reads[v.frag_reads[G.read_off + k]]; lo = tmin(lo, R.pos); hi = tmax(hi, R.rend); }
+    const int32_t nb = par.syserr_mut_region_n_bases;
+    int32_t n_cov = 0, n_near = 0, n_mut_entries = 0;
+    uint32_t hist = 0;                 // coverage flags of the previous nb positions (bit k = position p-1-k)
+    int32_t near_until = lo - nb - 2;  // positions <= near_until are within nb to the right of a mutation
+    for (int pass = 0; pass < 2; pass++) {
+        int32_t out = -1;
+        if (pass == 1) {
+            if (n_mut_entries <= 1) { break; }
+            out = rec_alloc(v, 4 + 2 * n_mut_entries);
+            if (out < 0) { break; }
+            v.rec_buf[out] = UVC_REC_HAP_BQ; v.rec_buf[out + 1] = G.strand; v.rec_buf[out + 2] = n_mut_entries; v.rec_buf[out + 3] = (int32_t)fi;
+            out += 4;
+        }
+        for (int32_t p = lo; p < hi; p++) {
+            const bool any = frag_covers(v, G, p);
+            bool cov = false, mut = false;
+            if (any) {
+                int32_t c[UVC_NSYM];
+                frag_votes(v, G, p, po + p, c);
+                const int ref = v.refsym[po + p];
+                for (int type = 1; type >= 0; type--) { // SYMBOL_TYPES_IN_VCF_ORDER: link first
+                    int con; int32_t cc, tc;
+                    if (type == 1) { link_consensus(c, true, con, cc, tc); } else { base_consensus(c, false, con, cc, tc); }
+                    if (0 == tc) { continue; }
+                    cov = true;
+                    const int32_t con_qual = cc * 2 - tc;
+                    const bool high = ((type == 1) || con_qual >= par.bias_thres_highBQ);
+                    if (symbols_mutated(ref, con) && high) {
+                        mut = true;
+                        if (pass == 0) { n_mut_entries++; } else { v.rec_buf[out] = p; v.rec_buf[out + 1] = con; out += 2; }
+                    }
+                }
+            }
+            if (pass == 0) {
+                if (mut) {
+                    const int32_t uncounted = tmin(nb, tmax(0, p - 1 - near_until));   // left neighbours not yet counted
+                    if (uncounted > 0) {
+                        const uint32_t m = hist & ((uncounted >= 32) ? 0xffffffffu : ((1u << uncounted) - 1u));
+                        int32_t pc = 0; for (uint32_t x = m; x; x &= (x - 1)) { pc++; }
+                        n_near += pc;
+                    }
+                    near_until = p + nb;
+                }
+                if (cov) { n_cov++; if (p <= near_until) { n_near++; } }
+                hist = ((hist << 1) | (cov ? 1u : 0u)) & ((nb >= 32) ? 0xffffffffu : ((1u << nb) - 1u));
+            }
+        }
+    }
+    G.n_cov = n_cov; G.n_near_mut = n_near;
+}
+
+// infer_max_qual_assuming_independence (main_conversion.hpp:943-974)
+UVC_HD void infer_max_qual(int32_t & maxvqual, int32_t & argmaxAD, int32_t & argmaxBQ, const BatchView & v, int32_t max_qual, int32_t dec_qual, const int32_t *distr, int32_t totDP) {
+    int32_t currAD = 0;
+    maxvqual = 0; argmaxAD = 0; argmaxBQ = 0;
+    const int32_t n = tmin(UVC_NUM_BUCKETS, max_qual / dec_qual);
+    for (int32_t idx = 0; idx < n; idx++) {
+        const int32_t q = distr[idx];
+        if (0 == q) { continue; }
+        currAD += q;
+        const int32_t currBQ = max_qual - (dec_qual * idx);
+        const double expBQ = v.ten_over_ln10 * log(((double)totDP / (double)currAD) + 2.220446049250313e-16);
+        const int32_t currvqual = (int32_t)(currAD * (currBQ - expBQ));
+        if (currvqual > maxvqual) { argmaxAD = currAD; argmaxBQ = currBQ; maxvqual = currvqual; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K3b: one thread per position
+// Fragment-level consensus gathered per position (main.hpp:2620-2733, 2757-2828): bDP, bTA, bTB, bMQ, the quality-bucket histogram and its
+// reduction to bIAQb/bIADb/bIDQb, and the indel identities of fragments whose link consensus is an insertion or deletion.
+UVC_HD void k3b_position(const BatchView & v, int64_t gp) {
+    const TileInfo & T = v.tiles[v.pos_tile[gp]];
+    const int32_t p = (int32_t)(gp - T.pos_off) + T.ext_beg;
+    const uvcgpu_params & par = v.par;
+    int32_t bucket[UVC_NSYM * UVC_NUM_BUCKETS];
+    for (int i = 0; i < UVC_NSYM * UVC_NUM_BUCKETS; i++) { bucket[i] = 0; }
+    int32_t *fd0 = v.fragdepth + ((0 * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FRAG_DEPTHS;
+    int32_t *fd1 = v.fragdepth + ((1 * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FRAG_DEPTHS;
+    int32_t *vq = v.vq + gp * UVC_NSYM * UVCGPU_NUM_VQ_TAGS;
+    const int ref = v.refsym[gp];
+    int64_t lo, hi;
+    read_window(v, T, p, lo, hi);
+    for (int64_t ri = lo; ri < hi; ri++) {
+        const ReadRec & R = v.reads[ri];
+        if (R.rend <= p || R.fragprev_maxrend > p) { continue; }   // not covering, or an earlier read of the same fragment already handled p
+        const FragRec & G = v.frags[R.frag];
+        int32_t c[UVC_NSYM];
+        frag_votes(v, G, p, gp, c);
+        int32_t *fd = (G.strand ? fd1 : fd0);
+        for (int type = 1; type >= 0; type--) {
+            int con; int32_t cc, tc;
+            if (type == 1) { link_consensus(c, true, con, cc, tc); } else { base_consensus(c, false, con, cc, tc); }
+            if (0 == tc) { continue; }
+            const int32_t max_qual = 8 + avg_bq(v, gp, con);
+            int32_t phredlike = tmin(cc * 2 - tc, max_qual);
+            if (0x1 & par.fam_flag) { phredlike = tmin(phredlike, sscs_phred(par, ref, con)); }
+            const int32_t pb = tmax(0, max_qual - phredlike);
+            if (pb < UVC_NUM_BUCKETS) { bucket[con * UVC_NUM_BUCKETS + pb] += 1; }
+            fd[con * UVCGPU_NUM_FRAG_DEPTHS + 0] += 1;
+            fd[con * UVCGPU_NUM_FRAG_DEPTHS + 1] += G.n_cov;
+            fd[con * UVCGPU_NUM_FRAG_DEPTHS + 2] += G.n_near_mut;
+            vq[con * UVCGPU_NUM_VQ_TAGS + 4] += (G.normMQ * G.normMQ) / UVC_SQR_QUAL_DIV;
+            if (is_ins_symbol(con) || is_del_symbol(con)) {
+                const int32_t e = indel_majority_of_reads(v, v.frag_reads + G.read_off, G.n_reads, p, con);
+                if (e >= 0) { rec_put6(v, UVC_REC_FRAG_INDEL, G.strand, con, p, e, 1); }
+            }
+        }
+    }
+    for (int type = 0; type < 2; type++) {
+        const int s0 = (type == 0 ? UVC_BASE_A : UVC_LINK_M), s1 = (type == 0 ? UVC_BASE_NN : UVC_LINK_NN);
+        int32_t totDP = 0;
+        for (int s = s0; s <= s1; s++) { totDP += fd0[s * UVCGPU_NUM_FRAG_DEPTHS] + fd1[s * UVCGPU_NUM_FRAG_DEPTHS]; }
+        for (int s = s0; s <= s1; s++) {
+            int32_t q, ad, bq;
+            infer_max_qual(q, ad, bq, v, 8 + avg_bq(v, gp, s), 1, bucket + s * UVC_NUM_BUCKETS, totDP);
+            vq[s * UVCGPU_NUM_VQ_TAGS + 5] += q; vq[s * UVCGPU_NUM_VQ_TAGS + 6] += ad; vq[s * UVCGPU_NUM_VQ_TAGS + 7] += bq;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ family-level helpers
+// Per (family, strand, position): number of fragments voting for each symbol after the base-quality filter (read_family_con_ampl,
+// GenericSymbol2Count::updateByFiltering, main.hpp:466-495) and, optionally, the major-minus-minor quality sums (read_family_mmm_ampl,
+// updateByMajorMinusMinor, main.hpp:497-520).
+UVC_HD void fam_counts(const BatchView & v, const FamRec & F, int strand, int32_t p, int64_t gp, int32_t con[UVC_NSYM], int32_t *mmm) {
+    votes_zero(con);
+    if (mmm) { votes_zero(mmm); }
+    const bool ignore_padded_del = (v.par.microadjust_padded_deletion_flag & 0x1); // Illumina/BGI branch of main.hpp:2908
+    for (int32_t g = F.frag_off[strand]; g < F.frag_off[strand] + F.n_frags[strand]; g++) {
+        const FragRec & G = v.frags[g];
+        if (!frag_covers(v, G, p)) { continue; }
+        int32_t c[UVC_NSYM];
+        frag_votes(v, G, p, gp, c);
+        int a; int32_t cc, tc;
+        link_consensus(c, true, a, cc, tc);
+        int32_t adj = tmax(cc * 2, tc) - tc;
+        if (adj > 0) { con[a] += 1; if (mmm) { mmm[a] += adj; } }
+        base_consensus(c, ignore_padded_del, a, cc, tc);
+        adj = tmax(cc * 2, tc) - tc;
+        if (adj >= v.par.fam_thres_highBQ_snv && adj > 0) { con[a] += 1; }
+        if (mmm) {
+            base_consensus(c, false, a, cc, tc);
+            adj = tmax(cc * 2, tc) - tc;
+            if (adj > 0) { mmm[a] += adj; }
+        }
+    }
+}
+
+// majority indel event of fragment G at p if its link consensus is `symbol`, else -1
+UVC_HD int32_t frag_link_indel_event(const BatchView & v, const FragRec & G, int32_t p, int64_t gp, int symbol) {
+    if (!frag_covers(v, G, p)) { return -1; }
+    int32_t c[UVC_NSYM];
+    frag_votes(v, G, p, gp, c);
+    int a; int32_t cc, tc;
+    link_consensus(c, true, a, cc, tc);
+    if (a != symbol || 0 == cc) { return -1; }
+    return indel_majority_of_reads(v, v.frag_reads + G.read_off, G.n_reads, p, symbol);
+}
+
+// Majority identity of the family's indel map for `symbol` at p (each fragment whose link consensus is `symbol` adds its own majority identity
+// once, main.hpp:1679-1685); *count receives the number of fragments behind the winner.
+UVC_HD int32_t fam_indel_majority(const BatchView & v, const FamRec & F, int strand, int32_t p, int64_t gp, int symbol, int32_t *count) {
+    int32_t best = -1, best_n = 0;
+    const int32_t g0 = F.frag_off[strand], g1 = F.frag_off[strand] + F.n_frags[strand];
+    for (int32_t g = g0; g < g1; g++) {
+        const int32_t e = frag_link_indel_event(v, v.frags[g], p, gp, symbol);
+        if (e < 0) { continue; }
+        int32_t n = 0; bool first = true;
+        for (int32_t g2 = g0; g2 < g1; g2++) {
+            const int32_t e2 = (g2 == g ? e : frag_link_indel_event(v, v.frags[g2], p, gp, symbol));
+            if (e2 < 0) { continue; }
+            if (0 == indel_cmp(v, v.ev[e], v.ev[e2])) { n++; if (g2 < g) { first = false; } }
+        }
+        if (!first) { continue; }
+        if (best < 0 || n > best_n || (n == best_n && indel_cmp(v, v.ev[e], v.ev[best]) > 0)) { best = e; best_n = n; }
+    }
+    if (count) { *count = best_n; }
+    return best;
+}
+
+UVC_HD void plain_consensus(const int32_t c[UVC_NSYM], int type, int & a, int32_t & cc, int32_t & tc) {
+    if (type == 1) { link_consensus(c, false, a, cc, tc); } else { base_consensus(c, false, a, cc, tc); }
+}
+
+UVC_HD bool fam_is_good(const uvcgpu_params & par, const FamRec & F, int32_t cc, int32_t tc) {
+    return (par.fam_thres_dup1add <= tc) && (cc * 100 >= tc * par.fam_thres_dup1perc) && ((F.duplexflag & 0x1) || (par.fam_flag & 0x2));
+}
+
+// ------------------------------------------------------------------------------------------------ K4a: one thread per (family, strand)
+// no_strict_bias_pos_min/max (main.hpp:2959-2998): the outermost positions, from either end, at which the family forms a tier-2 base consensus.
+UVC_HD void k4a_family_strand(const BatchView & v, int64_t i) {
+    FamRec & F = v.fams[i >> 1];
+    const int strand = (int)(i & 1);
+    if (0 == F.n_frags[strand]) { return; }
+    const TileInfo & T = v.tiles[F.tile];
+    const int64_t po = T.pos_off - T.ext_beg;
+    F.nsb_min[strand] = F.end2[strand]; F.nsb_max[strand] = F.beg2[strand];
+    if (!F.qlen_ok[strand] || !((F.duplexflag & 0x1) || (v.par.fam_flag & 0x2))) { return; }
+    int32_t lo = INT32_MAX, hi = 0;   // covered extent (positions outside have no votes)
+    for (int32_t g = F.frag_off[strand]; g < F.frag_off[strand] + F.n_frags[strand]; g++) {
+        const FragRec & G = v.frags[g];
+        for (int32_t k = 0; k < G.n_reads; k++) { const ReadRec & R = v.reads[v.frag_reads[G.read_off + k]]; lo = tmin(lo, R.pos); hi = tmax(hi, R.rend); }
+    }
+    for (int dir = 0; dir < 2; dir++) {
+        for (int32_t p = (dir ? hi - 1 : lo); (dir ? p >= lo : p < hi); p += (dir ? -1 : 1)) {
+            int32_t con[UVC_NSYM];
+            fam_counts(v, F, strand, p, po + p, con, NULL);
+            int a; int32_t cc, tc;
+            base_consensus(con, false, a, cc, tc);
+            if (0 == tc) { continue; }
+            if (fam_is_good(v.par, F, cc, tc) && (UVC_BASE_N != a) && (UVC_BASE_NN != a)) {
+                if (dir) { F.nsb_max[strand] = p; } else { F.nsb_min[strand] = p; }
+                break;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4: one thread per position
+// updateByAlns3UsingFQ gathered per position: family loop 1 (main.hpp:2999-3355), then - because its only cross-family dependence, cDPM/cDPm,
+// is per position - family loop 2 (main.hpp:3392-3551) and the per-strand reduction of the quality buckets (main.hpp:3552-3591).
+UVC_HD void k4_position(const BatchView & v, int64_t gp) {
+    const TileInfo & T = v.tiles[v.pos_tile[gp]];
+    const int32_t p = (int32_t)(gp - T.pos_off) + T.ext_beg;
+    const uvcgpu_params & par = v.par;
+    const int64_t po = T.pos_off - T.ext_beg;
+    const int32_t *baq = v.baq + po;
+    const int32_t *baq2 = v.baq2 + po;
+    const int ref = v.refsym[gp];
+    int32_t *fam0 = v.famdepth + ((0 * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FAM_DEPTHS;
+    int32_t *fam1 = v.famdepth + ((1 * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FAM_DEPTHS;
+    uvcgpu_faminfo_set *finfo = v.faminfo + gp * UVC_NSYM;
+    int32_t *dup = v.duplex + gp * UVC_NSYM * UVCGPU_NUM_DUPLEX_DEPTHS;
+    int32_t *vq = v.vq + gp * UVC_NSYM * UVCGPU_NUM_VQ_TAGS;
+    const uvcgpu_thres_set th = v.thres[gp];
+    const int32_t baq_last = T.ext_end - 1;
+    enum { cDP1 = 0, cDP12 = 1, cDP2 = 2, cDP3 = 3, cDPM = 4, cDPm = 5, cDP21 = 6, cDPD = 7 };
+    int64_t lo, hi;
+    read_window(v, T, p, lo, hi);
+
+    // ---- loop 1
+    for (int64_t ri = lo; ri < hi; ri++) {
+        const ReadRec & R = v.reads[ri];
+        if (R.rend <= p || R.famprev_maxrend > p) { continue; }
+        const FamRec & F = v.fams[R.fam];
+        const int strand = R.strand;
+        int32_t *fd = (strand ? fam1 : fam0);
+        int32_t con[UVC_NSYM];
+        fam_counts(v, F, strand, p, gp, con, NULL);
+        for (int type = 1; type >= 0; type--) {
+            int a; int32_t cc, tc;
+            plain_consensus(con, type, a, cc, tc);
+            if (0 == tc) { continue; }
+            fd[a * UVCGPU_NUM_FAM_DEPTHS + cDP12] += 1;
+            if (1 == tc) { fd[a * UVCGPU_NUM_FAM_DEPTHS + cDP21] += 1; }
+            const bool is_indel = (is_ins_symbol(a) || is_del_symbol(a));
+            int32_t fam_ev = -2;   // family-majority indel event, computed lazily
+            if (fam_is_good(par, F, cc, tc)) {
+                fd[a * UVCGPU_NUM_FAM_DEPTHS + cDP2] += 1;
+                if (is_indel) {
+                    fam_ev = fam_indel_majority(v, F, strand, p, gp, a, NULL);
+                    if (fam_ev >= 0) { rec_put6(v, UVC_REC_CDP2_INDEL, strand, a, p, fam_ev, 1); }
+                }
+                // family-level position / BAQ bias (main.hpp:3208-3318)
+                int32_t rbeg = tmin(F.nsb_min[strand], p);
+                int32_t rend = tmax(F.nsb_max[strand], p);
+                const int32_t l2r = F.l2r_end_median[strand], r2l = F.r2l_end_median[strand];
+                const bool nonconf_middle = (l2r <= (r2l + par.indel_adj_tracklen_dist));
+                if (nonconf_middle && p < r2l) { rend = tmax(tmin(l2r, tmin(r2l, rend)), p); }
+                if (nonconf_middle && l2r < p) { rbeg = tmin(tmax(l2r, tmax(r2l, rbeg)), p); }
+                uvcgpu_faminfo_set & fi = finfo[a];
+                const bool isGap = (type == 1);
+                const int32_t l_nb = nnminus(p + 1, rbeg);
+                const int32_t r_nb = nnminus(rend, p);
+                const int32_t LPxT = (isGap ? th.aLPxT : tmin(th.aLPxT, th.aRPxT));
+                int32_t indel_len = 0;
+                if (is_ins_symbol(a)) {
+                    // QUIRK: the reference takes the majority COUNT of the family's inserted sequences as "indel_len" (main.hpp:3238-3244)
+                    for (int sym = UVC_LINK_I3P; sym <= UVC_LINK_I1; sym++) { int32_t n = 0; fam_indel_majority(v, F, strand, p, gp, sym, &n); indel_len = tmax(indel_len, n); }
+                } else if (is_del_symbol(a)) {
+                    for (int sym = UVC_LINK_D3P; sym <= UVC_LINK_D1; sym++) { int32_t n = 0; fam_indel_majority(v, F, strand, p, gp, sym, &n); indel_len = tmax(indel_len, n); }
+                }
+                const bool far_from_edge = (l_nb + (is_ins_symbol(a) ? nnminus(indel_len, par.microadjust_nobias_pos_indel_maxlen) : 0) >= LPxT) && (r_nb >= th.aRPxT);
+                if (far_from_edge) {
+                    int64_t lpl = 0, rpl = 0;
+                    bidir_bias(fi.c2LP1, fi.c2LP2, fi.c2RP1, fi.c2RP2, lpl, rpl, th.aLP1t, th.aLP2t, th.aRP1t, th.aRP2t, l_nb, r_nb, true, 0);
+                    fi.c2LPL += (int32_t)lpl; fi.c2RPL += (int32_t)rpl;
+                }
+                if (nnminus(p + 1, F.nsb_min[strand]) >= par.bias_thres_strict_c2LRP0) { fi.c2LP0 += 1; }
+                if (nnminus(F.nsb_max[strand], p) >= par.bias_thres_strict_c2LRP0) { fi.c2RP0 += 1; }
+                const int32_t seg_l_baq = baq[p] - baq[tmax(rbeg, nnminus(p, UVC_MAX_STR_N_BASES))] + 1;
+                const int32_t ridx = tmin(rend - 1, tmin(p + UVC_MAX_STR_N_BASES, baq_last));
+                const int32_t seg_r_baq0 = baq[ridx] - baq[p] + 1;
+                const int32_t seg_r_baq = (isGap ? tmin(seg_r_baq0, baq2[ridx] - baq2[p] + 7) : seg_r_baq0);
+                const int32_t highBAQ = par.bias_thres_highBAQ + (isGap ? 0 : 3);
+                if (seg_l_baq >= highBAQ && seg_r_baq >= highBAQ) {
+                    bidir_bias(fi.c2LB1, fi.c2LB2, fi.c2RB1, fi.c2RB2, fi.c2LBL, fi.c2RBL, par.bias_thres_BAQ1, par.bias_thres_BAQ2, par.bias_thres_BAQ1, par.bias_thres_BAQ2,
+                            seg_l_baq, seg_r_baq, true, 0);
+                }
+                fi.c2BQ2 += 1;
+            }
+            if (par.fam_thres_dup2add <= tc && (cc * 100 >= tc * par.fam_thres_dup2perc)) { fd[a * UVCGPU_NUM_FAM_DEPTHS + cDP3] += 1; }
+            if (is_indel) {
+                if (fam_ev == -2) { fam_ev = fam_indel_majority(v, F, strand, p, gp, a, NULL); }
+                if (fam_ev >= 0) { rec_put6(v, UVC_REC_FAM_INDEL, strand, a, p, fam_ev, 1); }
+            }
+            const bool is_subst = (a <= UVC_BASE_NN);
+            const int32_t flat = (is_subst ? par.fam_thres_emperr_all_flat_snv : par.fam_thres_emperr_all_flat_indel);
+            const int32_t perc = (is_subst ? par.fam_thres_emperr_con_perc_snv : par.fam_thres_emperr_con_perc_indel);
+            if (tc < flat) { continue; }
+            if (cc * 100 < tc * perc) { continue; }
+            const int s0 = (type == 0 ? UVC_BASE_A : UVC_LINK_M), s1 = (type == 0 ? UVC_BASE_NN : UVC_LINK_NN);
+            for (int s = s0; s <= s1; s++) {
+                if (s != a) { fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPm] += con[s]; fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPM] += tc; } // QUIRK: tc once per other symbol
+            }
+        }
+    }
+
+    // ---- loop 2
+    int32_t bucket[2 * UVC_NSYM * UVC_NUM_BUCKETS];
+    for (int i = 0; i < 2 * UVC_NSYM * UVC_NUM_BUCKETS; i++) { bucket[i] = 0; }
+    const int32_t tn_add = (par.is_tumor_vcf_provided ? 4 : 0);
+    for (int64_t ri = lo; ri < hi; ri++) {
+        const ReadRec & R = v.reads[ri];
+        if (R.rend <= p) { continue; }
+        const FamRec & F = v.fams[R.fam];
+        const bool is_duplex_umi = (0x2 == (F.duplexflag & 0x2));
+        const bool will_inc_dscs = (is_duplex_umi && F.n_frags[0] > 0 && F.n_frags[1] > 0);
+        const bool will_inc_sscs = (is_duplex_umi && !will_inc_dscs);
+        if (R.famprev_maxrend <= p) {   // first read of its (family, strand) that covers p
+            const int strand = R.strand;
+            int32_t *fd = (strand ? fam1 : fam0);
+            int32_t con[UVC_NSYM], mmm[UVC_NSYM];
+            fam_counts(v, F, strand, p, gp, con, mmm);
+            for (int type = 1; type >= 0; type--) {
+                int a; int32_t con_sumBQs, tot_sumBQs;
+                plain_consensus(mmm, type, a, con_sumBQs, tot_sumBQs);
+                if (0 == tot_sumBQs) { continue; }
+                const int s0 = (type == 0 ? UVC_BASE_A : UVC_LINK_M), s1 = (type == 0 ? UVC_BASE_NN : UVC_LINK_NN);
+                const int32_t con_nfrags = con[a];
+                int32_t tot_nfrags = 0;
+                for (int s = s0; s <= s1; s++) { tot_nfrags += con[s]; }
+                fd[a * UVCGPU_NUM_FAM_DEPTHS + cDP1] += 1;
+                if (will_inc_sscs && (tot_nfrags >= par.fam_thres_dup1add) && (con_nfrags * 100 >= tot_nfrags * par.fam_thres_dup1perc)) {
+                    fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPD] += 1;
+                    if (is_ins_symbol(a) || is_del_symbol(a)) {
+                        const int32_t e = fam_indel_majority(v, F, strand, p, gp, a, NULL);
+                        if (e >= 0) { rec_put6(v, UVC_REC_C2D_INDEL, strand, a, p, e, 1); }
+                    }
+                }
+                const int32_t avgBQ = ((0 == tot_nfrags) ? 1 : (con_sumBQs / tot_nfrags));
+                const int32_t majorcount = fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPM];
+                const int32_t minorcount = fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPm];
+                const double prior_weight = 1.0 / (minorcount + 1.0);
+                const double p2p = v.phred2prob_tab[tmin(tmax(avgBQ, 0), 127)];
+                const double realphred = -10 * log((minorcount + prior_weight) / (majorcount + minorcount + prior_weight / p2p)) / v.ln10;
+                const int32_t indep_frag_phred = (int32_t)round(((con_nfrags * 2) - tot_nfrags) * realphred);
+                int32_t confam_qual;
+                if (type == 1) {
+                    confam_qual = tmax(1, tmin(indep_frag_phred, par.fam_phred_indel_inc_before_barcode_labeling + (int32_t)round(realphred)));
+                } else {
+                    confam_qual = tmax(1, tmin(indep_frag_phred, (con_sumBQs * 2) - tot_sumBQs));
+                }
+                const int32_t max_qual = sscs_phred(par, ref, a) + tn_add;
+                const int32_t confam_qual2 = tmin(confam_qual, max_qual);
+                if (tot_nfrags >= par.fam_thres_dup1add) {
+                    const int32_t pb = (max_qual - confam_qual2 + 2) / 4;
+                    if (pb >= 0 && pb < UVC_NUM_BUCKETS) { bucket[(strand * UVC_NSYM + a) * UVC_NUM_BUCKETS + pb] += 1; }
+                }
+            }
+        }
+        if (will_inc_dscs && R.fambothprev_maxrend <= p) {   // first read of the duplex family that covers p
+            int32_t dcount[UVC_NSYM];
+            votes_zero(dcount);
+            int link_con[2] = {-1, -1};
+            for (int strand = 0; strand < 2; strand++) {
+                int32_t con[UVC_NSYM];
+                fam_counts(v, F, strand, p, gp, con, NULL);
+                for (int type = 1; type >= 0; type--) {
+                    int a; int32_t cc, tc;
+                    plain_consensus(con, type, a, cc, tc);
+                    const int32_t adj = tmax(cc * 2, tc) - tc;
+                    if (adj >= 1 && adj > 0) { dcount[a] += 1; }
+                    if (type == 1 && cc > 0) { link_con[strand] = a; }
+                }
+            }
+            for (int type = 0; type < 2; type++) {
+                int a; int32_t cc, tc;
+                plain_consensus(dcount, type, a, cc, tc);
+                if (0 < tc) { dup[a * UVCGPU_NUM_DUPLEX_DEPTHS + 0] += 1; }
+                if (1 < tc) {
+                    dup[a * UVCGPU_NUM_DUPLEX_DEPTHS + 1] += 1;
+                    if (is_ins_symbol(a) || is_del_symbol(a)) {
+                        // majority identity of the duplex map: one entry per strand whose family link consensus is this symbol
+                        int32_t e0 = (link_con[0] == a ? fam_indel_majority(v, F, 0, p, gp, a, NULL) : -1);
+                        int32_t e1 = (link_con[1] == a ? fam_indel_majority(v, F, 1, p, gp, a, NULL) : -1);
+                        int32_t e = (e0 < 0 ? e1 : (e1 < 0 ? e0 : ((indel_cmp(v, v.ev[e0], v.ev[e1]) >= 0) ? e0 : e1)));
+                        if (e >= 0) { rec_put6(v, UVC_REC_C2D_INDEL, 0, a, p, e, 1); rec_put6(v, UVC_REC_C2D_INDEL, 1, a, p, e, 1); }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- per-strand reduction of the family quality buckets (main.hpp:3552-3591)
+    for (int strand = 0; strand < 2; strand++) {
+        const int32_t *fd = (strand ? fam1 : fam0);
+        for (int type = 0; type < 2; type++) {
+            const int s0 = (type == 0 ? UVC_BASE_A : UVC_LINK_M), s1 = (type == 0 ? UVC_BASE_NN : UVC_LINK_NN);
+            int32_t totDP = 0;
+            for (int s = s0; s <= s1; s++) { totDP += fd[s * UVCGPU_NUM_FAM_DEPTHS + cDP1]; }
+            for (int s = s0; s <= s1; s++) {
+                int32_t q, ad, bq;
+                infer_max_qual(q, ad, bq, v, sscs_phred(par, ref, s) + tn_add, 4, bucket + (strand * UVC_NSYM + s) * UVC_NUM_BUCKETS, totDP);
+                vq[s * UVCGPU_NUM_VQ_TAGS + 8 + 3 * strand] += q; vq[s * UVCGPU_NUM_VQ_TAGS + 9 + 3 * strand] += ad; vq[s * UVCGPU_NUM_VQ_TAGS + 10 + 3 * strand] += bq;
+            }
+        }
+    }
+}
+
 } // namespace uvc
 
 #endif
