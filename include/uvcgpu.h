@@ -198,6 +198,8 @@ enum uvcgpu_section {
     UVCGPU_SEC_VQ = 13,        /* int32[14][27] */
     UVCGPU_SEC_FAMILIES = 14,  /* text: family grouping, same format as the oracle harness */
     UVCGPU_SEC_RTR_INITIAL = 15,
+    UVCGPU_SEC_INDELMAPS = 16, /* text: indel identity maps, same format as the oracle harness */
+    UVCGPU_SEC_HAPLINKS = 17,  /* text: haplotype links (updateHapMap), same format as the oracle harness */
     UVCGPU_NUM_SECTIONS
 };
 

@@ -52,7 +52,7 @@ def run_tiles(bam: str, fasta: str, tiles: Sequence[Tuple[int, int, int, int]], 
         d: Dict[str, object] = {}
         for sec in sections:
             raw = ctx.dump(ticket, ti, sec)
-            if sec == "families":
+            if sec in ("families", "indelmaps", "haplinks"):
                 d[sec] = raw.decode()
             else:
                 d[sec] = np.frombuffer(raw, dtype=refdump.section_dtype(sec)).copy()

@@ -11,7 +11,7 @@ import pytest
 import parity_util as pu
 
 SECTIONS = ["meta", "families", "rtr_initial", "baq", "baq2", "prep", "thres", "rtr", "seginfo", "vq", "fragdepth0", "fragdepth1",
-            "famdepth0", "famdepth1", "faminfo", "duplex"]
+            "famdepth0", "famdepth1", "faminfo", "duplex", "indelmaps", "haplinks"]
 IMPLEMENTED_VQ_TAGS = 14   # VQ_a1BQf .. VQ_cIDQr: everything updateByRegion3Aln fills (main_conversion.hpp:743-762)
 
 
@@ -27,6 +27,8 @@ def _check(info, tiles, emulate, tmp_path, extra=()):
         o = ours[ti]
         assert list(o["meta"][:9]) == list(ref["meta"][:9])
         assert o["families"] == ref["families"]
+        assert sorted(o["indelmaps"].split("\n")) == sorted(ref["indelmaps"].split("\n"))
+        assert sorted(o["haplinks"].split("\n")) == sorted(ref["haplinks"].split("\n"))
         ext_beg = int(ref["meta"][6])
         msgs = []
         for ours_name, ref_name in [("rtr_initial", "rtr_initial"), ("baq", "baq"), ("baq2", "baq2"), ("prep", "prep"),

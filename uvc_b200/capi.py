@@ -77,7 +77,7 @@ class ReadsSoA(C.Structure):
 
 
 SECTIONS = {"meta": 0, "rtr": 1, "baq": 2, "baq2": 3, "prep": 4, "thres": 5, "seginfo": 6, "faminfo": 7, "fragdepth0": 8,
-            "fragdepth1": 9, "famdepth0": 10, "famdepth1": 11, "duplex": 12, "vq": 13, "families": 14, "rtr_initial": 15}
+            "fragdepth1": 9, "famdepth0": 10, "famdepth1": 11, "duplex": 12, "vq": 13, "families": 14, "rtr_initial": 15, "indelmaps": 16, "haplinks": 17}
 
 _gpu_libs: Dict[bool, C.CDLL] = {}
 _host_lib: Optional[C.CDLL] = None

@@ -9,6 +9,7 @@
 #include "batch.h"
 #include "host_prep.h"
 #include "kernels_core.cuh"
+#include "sparse_out.h"
 
 #include <algorithm>
 #include <chrono>
@@ -44,6 +45,9 @@ struct BatchState {
     uvcgpu_reads_soa reads;               // caller's SoA (borrowed until release)
     uvcgpu_batch_stats stats;
     bool collected = false;
+    bool sparse_built = false;
+    std::vector<TileSparse> sparse;
+    std::vector<IndelEvent> ev_host;
 #if UVC_CUDA
     cudaEvent_t ev[12];
     bool have_events = false;
@@ -89,6 +93,7 @@ __device__ __forceinline__ void k3a_item(const BatchView & v, int64_t i) { uvc::
 __device__ __forceinline__ void k3b_item(const BatchView & v, int64_t i) { uvc::k3b_position(v, i); }
 __device__ __forceinline__ void k4a_item(const BatchView & v, int64_t i) { uvc::k4a_family_strand(v, i); }
 __device__ __forceinline__ void k4_item(const BatchView & v, int64_t i) { uvc::k4_position(v, i); }
+__device__ __forceinline__ void k4c_item(const BatchView & v, int64_t i) { uvc::k4c_family_strand(v, i); }
 
 template <void (*F)(const BatchView &, int64_t)>
 static void launch(cudaStream_t s, const BatchView & v, int64_t n, int64_t & launches) {
@@ -137,6 +142,8 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[7], ctx->stream));
     launch<k4_item>(ctx->stream, v, v.n_pos, launches);
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[8], ctx->stream));
+    launch<k4c_item>(ctx->stream, v, 2 * v.n_fams, launches);
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[9], ctx->stream));
     UVC_CUDA_CHECK(ctx, cudaGetLastError());
     bs.stats.gpu_launches = launches;
     return 0;
@@ -147,7 +154,7 @@ static int backend_wait(uvcgpu_ctx *ctx, BatchState & bs) {
     if (bs.have_events) {
         float ms = 0;
         double total = 0;
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < 9; i++) {
             UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, bs.ev[i], bs.ev[i + 1]));
             bs.stats.kernel_ms_by_stage[i] = ms;
             total += ms;
@@ -184,6 +191,7 @@ static int backend_run(uvcgpu_ctx *, BatchState & bs) {
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::k3b_position(v, i); }
     for (int64_t i = 0; i < 2 * v.n_fams; i++) { uvc::k4a_family_strand(v, i); }
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::k4_position(v, i); }
+    for (int64_t i = 0; i < 2 * v.n_fams; i++) { uvc::k4c_family_strand(v, i); }
     bs.stats.gpu_launches = 0;
     return 0;
 }
@@ -394,6 +402,25 @@ int uvcgpu_collect(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, uvcgpu_batch_stats *st
     return UVCGPU_OK;
 }
 
+static int ensure_sparse(uvcgpu_ctx *ctx, BatchState & bs) {
+    if (bs.sparse_built) { return 0; }
+    const BatchView & v = bs.view;
+    int32_t cursor[4] = {0, 0, 0, 0};
+    int rc = backend_download(ctx, cursor, v.rec_cursor, sizeof(cursor));
+    if (rc != 0) { return rc; }
+    if (cursor[0] > v.rec_cap) { ctx->err = "sparse record stream overflow: submit a smaller batch"; return UVCGPU_ENOMEM; }
+    std::vector<int32_t> rec((size_t)cursor[0]);
+    rc = backend_download(ctx, rec.data(), v.rec_buf, rec.size() * sizeof(int32_t));
+    if (rc != 0) { return rc; }
+    bs.ev_host.resize((size_t)v.n_ev);
+    rc = backend_download(ctx, bs.ev_host.data(), v.ev, bs.ev_host.size() * sizeof(IndelEvent));
+    if (rc != 0) { return rc; }
+    bs.stats.d2h_bytes += (int64_t)(rec.size() * sizeof(int32_t) + bs.ev_host.size() * sizeof(IndelEvent));
+    uvc_build_sparse(bs.sparse, bs.hb, ctx->par, rec.data(), (int64_t)rec.size(), bs.ev_host.data());
+    bs.sparse_built = true;
+    return 0;
+}
+
 int uvcgpu_release(uvcgpu_ctx *ctx, uvcgpu_ticket ticket) {
     if (NULL == ctx) { return UVCGPU_EINVAL; }
     auto it = ctx->batches.find(ticket);
@@ -433,6 +460,13 @@ int uvcgpu_dump_counters(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_ind
         }
         case UVCGPU_SEC_FAMILIES: {
             const std::string s = uvc_families_text(bs.hb, tile_index, bs.reads);
+            tmp.assign(s.begin(), s.end());
+            host_side = true; break;
+        }
+        case UVCGPU_SEC_INDELMAPS: case UVCGPU_SEC_HAPLINKS: {
+            int rc = ensure_sparse(ctx, bs);
+            if (rc != 0) { return rc; }
+            const std::string s = (section == UVCGPU_SEC_INDELMAPS ? uvc_indelmaps_text(bs.sparse[tile_index]) : uvc_haplinks_text(bs.sparse[tile_index]));
             tmp.assign(s.begin(), s.end());
             host_side = true; break;
         }

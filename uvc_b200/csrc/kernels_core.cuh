@@ -1380,6 +1380,75 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K4c: one thread per (family, strand)
+// Haplotype evidence of families (main.hpp:3434-3521): the string of high-quality mutated consensus symbols of a single-strand family, and
+// the sub-string that is also a tier-2 family consensus. Needs the complete cDPM/cDPm counters, hence runs after K4.
+UVC_HD void k4c_family_strand(const BatchView & v, int64_t i) {
+    const FamRec & F = v.fams[i >> 1];
+    const int strand = (int)(i & 1);
+    if (0 == F.n_frags[strand]) { return; }
+    const TileInfo & T = v.tiles[F.tile];
+    const uvcgpu_params & par = v.par;
+    const int64_t po = T.pos_off - T.ext_beg;
+    enum { cDPM = 4, cDPm = 5 };
+    int32_t lo = INT32_MAX, hi = 0;
+    for (int32_t g = F.frag_off[strand]; g < F.frag_off[strand] + F.n_frags[strand]; g++) {
+        const FragRec & G = v.frags[g];
+        for (int32_t k = 0; k < G.n_reads; k++) { const ReadRec & R = v.reads[v.frag_reads[G.read_off + k]]; lo = tmin(lo, R.pos); hi = tmax(hi, R.rend); }
+    }
+    int32_t n_fq = 0, n_f2q = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        int32_t out_fq = -1, out_f2q = -1;
+        if (pass == 1) {
+            if (n_fq <= 1 && n_f2q <= 1) { break; }
+            if (n_fq > 1) {
+                out_fq = rec_alloc(v, 4 + 2 * n_fq);
+                if (out_fq >= 0) { int32_t *w = v.rec_buf + out_fq; w[0] = UVC_REC_HAP_FQ; w[1] = strand; w[2] = n_fq; w[3] = (int32_t)(i >> 1); out_fq += 4; }
+            }
+            if (n_f2q > 1) {
+                out_f2q = rec_alloc(v, 4 + 2 * n_f2q);
+                if (out_f2q >= 0) { int32_t *w = v.rec_buf + out_f2q; w[0] = UVC_REC_HAP_F2Q; w[1] = strand; w[2] = n_f2q; w[3] = (int32_t)(i >> 1); out_f2q += 4; }
+            }
+        }
+        for (int32_t p = lo; p < hi; p++) {
+            const int64_t gp = po + p;
+            const int ref = v.refsym[gp];
+            int32_t con[UVC_NSYM], mmm[UVC_NSYM];
+            fam_counts(v, F, strand, p, gp, con, mmm);
+            const int32_t *fd = v.famdepth + ((strand * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FAM_DEPTHS;
+            for (int type = 1; type >= 0; type--) {
+                int a; int32_t con_sumBQs, tot_sumBQs;
+                plain_consensus(mmm, type, a, con_sumBQs, tot_sumBQs);
+                if (0 == tot_sumBQs || !symbols_mutated(ref, a)) { continue; }
+                bool high = (type == 1);
+                if (!high) {
+                    const int s0 = UVC_BASE_A, s1 = UVC_BASE_NN;
+                    const int32_t con_nfrags = con[a];
+                    int32_t tot_nfrags = 0;
+                    for (int s = s0; s <= s1; s++) { tot_nfrags += con[s]; }
+                    const int32_t avgBQ = ((0 == tot_nfrags) ? 1 : (con_sumBQs / tot_nfrags));
+                    const int32_t majorcount = fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPM], minorcount = fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPm];
+                    const double prior_weight = 1.0 / (minorcount + 1.0);
+                    const double p2p = v.phred2prob_tab[tmin(tmax(avgBQ, 0), 127)];
+                    const double realphred = -10 * log((minorcount + prior_weight) / (majorcount + minorcount + prior_weight / p2p)) / v.ln10;
+                    const int32_t indep_frag_phred = (int32_t)round(((con_nfrags * 2) - tot_nfrags) * realphred);
+                    const int32_t confam_qual = tmax(1, tmin(indep_frag_phred, (con_sumBQs * 2) - tot_sumBQs));
+                    high = (confam_qual >= par.bias_thres_highBQ);
+                }
+                if (!high) { continue; }
+                int a1; int32_t cc1, tc1;
+                plain_consensus(con, type, a1, cc1, tc1);
+                const bool confam = (a == a1 && par.fam_thres_dup1add <= tc1 && (cc1 * 100 >= tc1 * par.fam_thres_dup1perc));
+                if (pass == 0) { n_fq++; if (confam) { n_f2q++; } }
+                else {
+                    if (out_fq >= 0) { v.rec_buf[out_fq] = p; v.rec_buf[out_fq + 1] = a; out_fq += 2; }
+                    if (confam && out_f2q >= 0) { v.rec_buf[out_f2q] = p; v.rec_buf[out_f2q + 1] = a; out_f2q += 2; }
+                }
+            }
+        }
+    }
+}
+
 } // namespace uvc
 
 #endif
