@@ -249,7 +249,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     dom = max(range(16), key=lambda i: stage_ms[i])
-    STAGE_NAMES = ["K0 per-read", "K1 prep+thres", "K2 bias pileup", "K2e indel events", "K3a fragment stats", "K3b fragment consensus", "K4a family ends", "K4 family+duplex consensus"]
+    STAGE_NAMES = ["K0 per-read", "K1 prep+thres", "K2 bias pileup", "K2e indel events", "K3a fragment stats", "K3b fragment consensus", "K4a family ends", "K4 family+duplex consensus", "K4c family haplotypes"]
     dom_name = STAGE_NAMES[dom] if dom < len(STAGE_NAMES) else "stage%d" % dom
     bytes_alg = n_reads * (1.5 * 150 + 64) + last.n_ext_positions * 2 * 6272
     achieved = bytes_alg / (stage_ms[dom] / args.steps / 1e3) / 1e9

@@ -74,32 +74,28 @@ struct uvcgpu_ctx {
 
 #define UVC_CUDA_CHECK(ctx, call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return UVCGPU_ECUDA; } }
 
-template <void (*F)(const BatchView &, int64_t)>
-__global__ void __launch_bounds__(128) per_item_kernel(const BatchView v, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { F(v, i); }
-}
-
-__device__ __forceinline__ void k0_item(const BatchView & v, int64_t i) { uvc::k0_read(v, i); }
-__device__ __forceinline__ void k1_item(const BatchView & v, int64_t i) { uvc::k1_position(v, i); }
+// One named __global__ per stage (so that profiles list them by name); every thread handles one work item.
+#define UVC_DEFINE_KERNEL(name, call) \
+    __global__ void __launch_bounds__(128) name(const BatchView v, int64_t n) { \
+        const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; \
+        if (i < n) { call; } \
+    }
+UVC_DEFINE_KERNEL(uvc_k0_read_consts, uvc::k0_read(v, i))
+UVC_DEFINE_KERNEL(uvc_k1_prep_thres, uvc::k1_position(v, i))
 // both roles of a position sit in different warps of the same block: block = 64 positions x 2 roles
-__device__ __forceinline__ void k2_item(const BatchView & v, int64_t i) {
-    const int64_t blk = i / 128; const int within = (int)(i % 128);
-    const int64_t gp = blk * 64 + (within % 64);
-    if (gp < v.n_pos) { uvc::k2_position(v, gp, within / 64); }
-}
-__device__ __forceinline__ void k2e_item(const BatchView & v, int64_t i) { uvc::k2e_event(v, i); }
-__device__ __forceinline__ void k3a_item(const BatchView & v, int64_t i) { uvc::k3a_fragment(v, i); }
-__device__ __forceinline__ void k3b_item(const BatchView & v, int64_t i) { uvc::k3b_position(v, i); }
-__device__ __forceinline__ void k4a_item(const BatchView & v, int64_t i) { uvc::k4a_family_strand(v, i); }
-__device__ __forceinline__ void k4_item(const BatchView & v, int64_t i) { uvc::k4_position(v, i); }
-__device__ __forceinline__ void k4c_item(const BatchView & v, int64_t i) { uvc::k4c_family_strand(v, i); }
+UVC_DEFINE_KERNEL(uvc_k2_bias_pileup, { const int64_t gp = (i / 128) * 64 + (i % 64); if (gp < v.n_pos) { uvc::k2_position(v, gp, (int)((i % 128) / 64)); } })
+UVC_DEFINE_KERNEL(uvc_k2e_indel_events, uvc::k2e_event(v, i))
+UVC_DEFINE_KERNEL(uvc_k3a_fragment_stats, uvc::k3a_fragment(v, i))
+UVC_DEFINE_KERNEL(uvc_k3b_fragment_consensus, uvc::k3b_position(v, i))
+UVC_DEFINE_KERNEL(uvc_k4a_family_ends, uvc::k4a_family_strand(v, i))
+UVC_DEFINE_KERNEL(uvc_k4_family_consensus, uvc::k4_position(v, i))
+UVC_DEFINE_KERNEL(uvc_k4c_family_haplotypes, uvc::k4c_family_strand(v, i))
 
-template <void (*F)(const BatchView &, int64_t)>
-static void launch(cudaStream_t s, const BatchView & v, int64_t n, int64_t & launches) {
+typedef void (*uvc_kernel_t)(const BatchView, int64_t);
+static void launch(uvc_kernel_t k, cudaStream_t s, const BatchView & v, int64_t n, int64_t & launches) {
     if (n <= 0) { return; }
     const int threads = 128;
-    per_item_kernel<F><<<(unsigned)((n + threads - 1) / threads), threads, 0, s>>>(v, n);
+    k<<<(unsigned)((n + threads - 1) / threads), threads, 0, s>>>(v, n);
     launches++;
 }
 
@@ -126,23 +122,23 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     for (int i = 0; i < 12; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreate(&bs.ev[i])); }
     bs.have_events = true;
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[0], ctx->stream));
-    launch<k0_item>(ctx->stream, v, v.n_reads, launches);
+    launch(uvc_k0_read_consts, ctx->stream, v, v.n_reads, launches);
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[1], ctx->stream));
-    launch<k1_item>(ctx->stream, v, v.n_pos, launches);
+    launch(uvc_k1_prep_thres, ctx->stream, v, v.n_pos, launches);
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[2], ctx->stream));
-    launch<k2_item>(ctx->stream, v, ((v.n_pos + 63) / 64) * 128, launches);
+    launch(uvc_k2_bias_pileup, ctx->stream, v, ((v.n_pos + 63) / 64) * 128, launches);
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[3], ctx->stream));
-    launch<k2e_item>(ctx->stream, v, v.n_ev, launches);
+    launch(uvc_k2e_indel_events, ctx->stream, v, v.n_ev, launches);
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[4], ctx->stream));
-    launch<k3a_item>(ctx->stream, v, v.n_frags, launches);
+    launch(uvc_k3a_fragment_stats, ctx->stream, v, v.n_frags, launches);
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[5], ctx->stream));
-    launch<k3b_item>(ctx->stream, v, v.n_pos, launches);
+    launch(uvc_k3b_fragment_consensus, ctx->stream, v, v.n_pos, launches);
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[6], ctx->stream));
-    launch<k4a_item>(ctx->stream, v, 2 * v.n_fams, launches);
+    launch(uvc_k4a_family_ends, ctx->stream, v, 2 * v.n_fams, launches);
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[7], ctx->stream));
-    launch<k4_item>(ctx->stream, v, v.n_pos, launches);
+    launch(uvc_k4_family_consensus, ctx->stream, v, v.n_pos, launches);
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[8], ctx->stream));
-    launch<k4c_item>(ctx->stream, v, 2 * v.n_fams, launches);
+    launch(uvc_k4c_family_haplotypes, ctx->stream, v, 2 * v.n_fams, launches);
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[9], ctx->stream));
     UVC_CUDA_CHECK(ctx, cudaGetLastError());
     bs.stats.gpu_launches = launches;
