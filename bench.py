@@ -22,7 +22,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-STAGES_IMPLEMENTED = "P0 grouping(host)+P1 refctx(host)+K0 read consts+K1 prep/thres+K2 bias pileup+K2e indel events+K3 fragment consensus+K4 family/duplex consensus (= updateByRegion3Aln; scoring not yet)"
+STAGES_IMPLEMENTED = "P0 grouping(host)+P1 refctx(host)+K0 read consts+K1 prep/thres+K2 bias pileup+K2e indel events+K3 fragment consensus+K4 family/duplex consensus (= updateByRegion3Aln)+K6 block-line inputs+K5 candidate scoring+VCF text(host) = process_batch"
 
 
 def parse_args():
@@ -192,6 +192,7 @@ def main():
     ctx = capi.Context(local_rank)
     for tid, (cname, _) in enumerate(ds["contigs"]):
         ctx.set_contig(tid, capi.read_fasta_contig(ds["fasta"], cname))
+        ctx.set_contig_name(tid, cname)
     ctiles = []
     prev = (-1, 0, 0)
     t_dec0 = time.time()
@@ -205,9 +206,13 @@ def main():
 
     def step():
         ticket = ctx.submit(ctiles, view)
-        st = ctx.collect(ticket)
-        _ = ctx.dump(ticket, 0, "meta")      # device->host read of the step's (tiny) result handle
+        ctx.collect(ticket)
+        st = ctx.score(ticket)               # candidate scoring on the device (K5/K6) + D2H of the kept records
+        nbytes = 0
+        for ti in range(len(ctiles)):        # the step's result: every tile's VCF body text
+            nbytes += len(ctx.tile_vcf(ticket, ti))
         ctx.release(ticket)
+        st.vcf_bytes = nbytes
         return st
 
     sampler = ClockSampler(local_rank)
@@ -249,7 +254,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     dom = max(range(16), key=lambda i: stage_ms[i])
-    STAGE_NAMES = ["K0 per-read", "K1 prep+thres", "K2 bias pileup", "K2e indel events", "K3a fragment stats", "K3b fragment consensus", "K4a family ends", "K4 family+duplex consensus", "K4c family haplotypes"]
+    STAGE_NAMES = ["K0 per-read", "K1 prep+thres", "K2 bias pileup", "K2e indel events", "K3a fragment stats", "K3b fragment consensus", "K4a family ends", "K4 family+duplex consensus", "K4c family haplotypes", "K6 block-line inputs", "K5 candidate scoring"]
     dom_name = STAGE_NAMES[dom] if dom < len(STAGE_NAMES) else "stage%d" % dom
     bytes_alg = n_reads * (1.5 * 150 + 64) + last.n_ext_positions * 2 * 6272
     achieved = bytes_alg / (stage_ms[dom] / args.steps / 1e3) / 1e9
@@ -261,7 +266,8 @@ def main():
             "config": {"workload": workload, "tiles": len(ctiles), "tile_len": args.tile, "reads_per_step": int(n_reads), "positions_per_step": int(n_positions),
                        "ext_positions_per_step": int(last.n_ext_positions), "stages": STAGES_IMPLEMENTED, "l2": "inputs (%.0f MB counters) larger than L2" % (last.n_ext_positions * 6272 / 1e6),
                        "host_decode_s_untimed": decode_s},
-            "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(last.h2d_bytes), "d2h_bytes_per_step": 128,
+            "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(last.h2d_bytes), "d2h_bytes_per_step": int(last.d2h_bytes), "vcf_bytes_per_step": int(last.vcf_bytes), "vcf_records_per_step": int(last.n_vcf_records),
+                    "host_score_ms_per_step": last.host_score_ms,
                     "host_prep_ms_per_step": last.host_prep_ms, "wall_ms_per_step": wall_s * 1e3 / args.steps},
             "gpu_launches": int(last.gpu_launches) * args.steps,
             "stage_ms_per_step": {n: stage_ms[i] / args.steps for i, n in enumerate(STAGE_NAMES)},

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define UVCGPU_ABI_VERSION 1
+#define UVCGPU_ABI_VERSION 3
 
 enum uvcgpu_error {
     UVCGPU_OK = 0,
@@ -100,6 +100,52 @@ typedef struct uvcgpu_params {
     int32_t phasing_haplotype_max_count, phasing_haplotype_min_ad, phasing_haplotype_max_detail_cnt;
     int32_t tumor_vcf_fname_nonempty;     /* vcf_tumor_fname.size() > 0: true even for the default "." (QUIRK, main.hpp:2564, 2858) */
     int32_t reserved[15];
+    /* ---- scoring (BcfFormat_symbol_calc_DPv / calc_qual / output_germline / append_vcf_record, main.hpp:4274-6272) ---- */
+    double vqual, vfa1, vfa2;
+    int32_t vdp1, vad1, vdp2, vad2, min_r_ad, min_a_ad;
+    int32_t syserr_minABQ_pcr_snv, syserr_minABQ_pcr_indel, syserr_minABQ_cap_snv, syserr_minABQ_cap_indel;   /* after the platform inference */
+    int32_t syserr_BQ_prior, syserr_BQ_sbratio_q_add, syserr_BQ_sbratio_q_max, syserr_BQ_xmratio_q_add, syserr_BQ_xmratio_q_max;
+    int32_t syserr_BQ_bmratio_q_add, syserr_BQ_bmratio_q_max, syserr_BQ_strand_favor_mul, syserr_MQ_min, syserr_MQ_max;
+    double syserr_MQ_NMR_expfrac, syserr_MQ_NMR_altfrac_coef, syserr_MQ_NMR_nonaltfrac_coef, syserr_MQ_NMR_pl_exponent, syserr_MQ_nonref_base;
+    double powlaw_anyvar_base, powlaw_amplicon_allele_fraction_coef;
+    int32_t penal4lowdep;
+    uint32_t nobias_flag;
+    double nobias_pos_indel_lenfrac_thres;
+    int32_t nobias_pos_indel_str_track_len;
+    int32_t bias_prior_DPadd_perc;
+    double bias_priorfreq_pos, bias_priorfreq_indel_in_read_div, bias_priorfreq_indel_in_var_div2, bias_priorfreq_indel_in_str_div2, bias_priorfreq_var_in_str_div2;
+    double bias_prior_var_DP_mul;
+    int32_t bias_priorfreq_ipos_snv, bias_priorfreq_ipos_indel, bias_priorfreq_strand_snv_base, bias_priorfreq_strand_indel;
+    double bias_FA_pseudocount_indel_in_read, bias_priorfreq_orientation_snv_base, bias_priorfreq_orientation_indel_base;
+    int32_t bias_FA_powerlaw_noUMI_phred_inc_snv, bias_FA_powerlaw_noUMI_phred_inc_indel, bias_FA_powerlaw_withUMI_phred_inc_snv, bias_FA_powerlaw_withUMI_phred_inc_indel;
+    int32_t bias_reduction_by_high_sequencingDP_min_n_totDepth, bias_reduction_by_high_sequencingDP_min_n_altDepth;
+    double bias_thres_FTS_FA, bias_orientation_min_effective_allelefrac;
+    int32_t bias_is_orientation_artifact_mixed_with_sequencing_error;
+    int32_t fam_min_n_copies, fam_min_n_copies_DPxAD, fam_min_overseq_perc, fam_bias_overseq_perc, fam_tier3DP_bias_overseq_perc, fam_indel_nonUMI_phred_dec_per_fold_overseq;
+    int32_t fam_phred_dscs_all, fam_phred_dscs_max, fam_phred_dscs_inc_max, fam_phred_pow_sscs_transversion_AT_TA_origin;
+    double fam_phred_pow_sscs_snv_origin, fam_phred_pow_sscs_indel_origin, fam_phred_pow_dscs_all_origin;
+    double germ_hetero_FA;
+    int32_t germ_phred_hetero_snp, germ_phred_hetero_indel, germ_phred_homalt_snp, germ_phred_homalt_indel, germ_phred_het3al_snp, germ_phred_het3al_indel;
+    int32_t tn_q_inc_max, tn_q_inc_max_sscs_CG_AT, tn_q_inc_max_sscs_other;
+    double tn_syserr_norm_devqual;
+    double indel_multiallele_samepos_penal, indel_multiallele_diffpos_penal, indel_multiallele_soma_penal_thres;
+    double indel_tetraallele_germline_penal_value, indel_tetraallele_germline_penal_thres;
+    int32_t indel_ins_penal_pseudocount;
+    double contam_any_mul_frac, contam_t2n_mul_frac;
+    double microadjust_bias_pos_indel_fold, microadjust_bias_pos_indel_misma_to_indel_ratio, microadjust_nobias_pos_indel_misma_to_indel_ratio;
+    int32_t microadjust_nobias_pos_indel_bMQ, microadjust_nobias_pos_indel_perc;
+    double microadjust_nobias_strand_all_fold, microadjust_refbias_indel_max, microadjust_counterbias_pos_odds_ratio, microadjust_counterbias_pos_fold_ratio;
+    int32_t microadjust_fam_binom_qual_halving_thres, microadjust_ref_MQ_dec_max;
+    int32_t microadjust_syserr_MQ_NMR_tn_syserr_no_penal_qual_min, microadjust_syserr_MQ_NMR_tn_syserr_no_penal_qual_max;
+    int32_t microadjust_longfrag_sidelength_min, microadjust_longfrag_sidelength_max;
+    double microadjust_longfrag_sidelength_zeroMQpenalty;
+    int32_t microadjust_alignment_clip_min_count, microadjust_alignment_tracklen_min;
+    double microadjust_alignment_clip_min_frac;
+    int32_t microadjust_germline_mix_with_del_snv_penalty, microadjust_strand_orientation_absence_DP_fold, microadjust_orientation_absence_snv_penalty;
+    int32_t microadjust_strand_absence_snv_penalty, microadjust_dedup_absence_indel_penalty;
+    int32_t lib_wgs_min_avg_fraglen, lib_nonwgs_clip_penal_min_indelsize, lib_nonwgs_normal_max_rescued_MQ, lib_wgs_normal_max_rescued_MQ;
+    double lib_nonwgs_ad_pseudocount, lib_nonwgs_normal_full_self_rescue_fa, lib_nonwgs_normal_min_self_rescue_fa_ratio, lib_nonwgs_normal_add_mul_ad;
+    int32_t should_output_all_germline, reserved2[7];
 } uvcgpu_params;
 
 /* One tier-3 region (the reference's BedLine, iohts.hpp:14-35) plus the previous one, as process_batch receives
@@ -200,6 +246,7 @@ enum uvcgpu_section {
     UVCGPU_SEC_RTR_INITIAL = 15,
     UVCGPU_SEC_INDELMAPS = 16, /* text: indel identity maps, same format as the oracle harness */
     UVCGPU_SEC_HAPLINKS = 17,  /* text: haplotype links (updateHapMap), same format as the oracle harness */
+    UVCGPU_SEC_VCF = 18,       /* text: the tile's VCF body lines (same as uvcgpu_tile_vcf) */
     UVCGPU_NUM_SECTIONS
 };
 
@@ -218,7 +265,10 @@ typedef struct uvcgpu_batch_stats {
     int64_t n_tiles, n_reads_in, n_reads_kept, n_positions, n_ext_positions, n_families, n_fragments;
     int64_t h2d_bytes, d2h_bytes, gpu_launches;
     double host_prep_ms, h2d_ms, kernel_ms, d2h_ms;
-    double kernel_ms_by_stage[16];
+    double kernel_ms_by_stage[16];   /* 0-8: pileup stages K0..K4c; 9: K6 block-line inputs; 10: K5 candidate scoring */
+    int64_t n_vcf_records;           /* candidate records the scoring stage kept */
+    double host_score_ms;            /* host part of the scoring stage (indel allele table, record ordering) */
+    double reserved[6];
 } uvcgpu_batch_stats;
 
 /* CommandLineArgs defaults (CmdLineArgs.hpp) with the Illumina inference applied (CmdLineArgs.cpp:127-134). */
@@ -233,6 +283,9 @@ const char *uvcgpu_last_error(const uvcgpu_ctx *ctx);
  * bases = ASCII, any case; NULL means "reference not available" (all 'n', main.cpp:57-59). */
 int uvcgpu_set_contig(uvcgpu_ctx *ctx, int32_t tid, const char *bases, int64_t len);
 
+/* Name of the contig as it is printed in the CHROM column (bam_hdr->target_name[tid], main.cpp:1462). */
+int uvcgpu_set_contig_name(uvcgpu_ctx *ctx, int32_t tid, const char *name);
+
 /* Replaces the body of process_batch up to scoring for a batch of tiles (main.cpp:481-591:
  * grouping.cpp:608-997 read filter + family grouping, :459-567 BQ fix-ups, main.hpp:803-874 repeat context,
  * main.cpp:400-429 BAQ offsets, main.hpp:3665-3742 updateByRegion3Aln). Asynchronous on the context's stream. */
@@ -240,6 +293,16 @@ int uvcgpu_submit(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, co
 
 /* Waits for the batch; fills stats. */
 int uvcgpu_collect(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, uvcgpu_batch_stats *stats);
+
+/* Replaces the scoring half of process_batch for a collected batch (main.cpp:593-1172: BcfFormat_symboltype_init, BcfFormat_symbol_init,
+ * BcfFormat_symbol_calc_DPv, BcfFormat_symbol_sum_DPv, BcfFormat_symbol_calc_qual, output_germline, append_vcf_record keep decision):
+ * the indel identity streams are aggregated on the host, candidates are scored on the device. Synchronous. stats may be NULL. */
+int uvcgpu_score(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, uvcgpu_batch_stats *stats);
+
+/* The uncompressed VCF body of one tile, exactly the bytes process_batch appends to its output string (main.cpp:1184): MGVCF block lines,
+ * additional-indel-candidate lines and variant records in the reference's order. Runs uvcgpu_score first if it has not run.
+ * Returns the number of bytes in *needed; copies min(cap, needed) bytes into dst (dst may be NULL). */
+int uvcgpu_tile_vcf(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_index, char *dst, size_t cap, size_t *needed);
 
 /* Test hook: raw per-position arrays of one tile of a collected batch for bit-exact parity against the oracle.
  * Returns the number of bytes the section needs in *needed; copies min(cap, needed) bytes into dst (dst may be NULL). */

@@ -37,6 +37,7 @@ def run_tiles(bam: str, fasta: str, tiles: Sequence[Tuple[int, int, int, int]], 
     for tid in tids:
         name, _ = bf.targets[tid]
         ctx.set_contig(tid, capi.read_fasta_contig(fasta, name))
+        ctx.set_contig_name(tid, name)
     ctiles = []
     prev = (-1, 0, 0)
     for (tid, beg, end, flag) in tiles:
@@ -52,7 +53,7 @@ def run_tiles(bam: str, fasta: str, tiles: Sequence[Tuple[int, int, int, int]], 
         d: Dict[str, object] = {}
         for sec in sections:
             raw = ctx.dump(ticket, ti, sec)
-            if sec in ("families", "indelmaps", "haplinks"):
+            if sec in ("families", "indelmaps", "haplinks", "vcf"):
                 d[sec] = raw.decode()
             else:
                 d[sec] = np.frombuffer(raw, dtype=refdump.section_dtype(sec)).copy()

@@ -1,0 +1,88 @@
+"""Scoring-stage parity (SURVEY.md rows a-13 ... a-19): the VCF body our C ABI returns for a tile must equal, byte for byte, what the
+reference prints for the same region - every FORMAT value, INFO field, QUAL and FILTER, the MGVCF block lines and the
+additional-indel-candidate lines, in the same order. (The stated tolerance for the floating-point scoring is 0.01 phred with identical
+FILTER calls; identical text is stricter, and it is what we get.)
+
+Checked against (1) the committed golden fixtures generated from the unmodified reference binary, and (2) where oracle/_ref exists,
+the reference itself on freshly generated data."""
+import gzip
+import importlib.util
+import os
+
+import pytest
+
+import parity_util as pu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location("make_golden_vcf", os.path.join(HERE, "golden", "make_golden_vcf.py"))
+mgv = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(mgv)
+
+
+def _our_lines(bam, fasta, tiles, emulate, **params):
+    out, stats = pu.run_tiles(bam, fasta, tiles, emulate, ["vcf"], **params)
+    return [l for o in out for l in o["vcf"].split("\n") if l], stats
+
+
+def _assert_same(ours, ref):
+    assert len(ref) > 0
+    for i, (a, b) in enumerate(zip(ours, ref)):
+        if a != b:
+            fa, fb = a.split("\t"), b.split("\t")
+            detail = [(j, x, y) for j, (x, y) in enumerate(zip(fa, fb)) if x != y and j != 9]
+            if len(fa) > 9 and len(fb) > 9 and fa[9] != fb[9]:
+                detail += [(t, x, y) for t, x, y in zip(fb[8].split(":"), fa[9].split(":"), fb[9].split(":")) if x != y]
+            raise AssertionError("line %d (%s) differs: %s" % (i, "\t".join(fb[:5]), detail[:12]))
+    assert len(ours) == len(ref)
+
+
+def _golden_case(case_index, emulate, tmp_path):
+    fname, tile, _, params = mgv.CASES[case_index]
+    info = mgv.mg.golden_inputs(str(tmp_path))
+    with gzip.open(os.path.join(HERE, "golden", fname), "rt") as f:
+        ref = [l for l in f.read().split("\n") if l]
+    ours, stats = _our_lines(info["bam"], info["fasta"], [tile], emulate, **params)
+    _assert_same(ours, ref)
+    return stats
+
+
+@pytest.mark.parametrize("case_index", range(len(mgv.CASES)))
+def test_emulation_matches_golden_vcf(case_index, tmp_path):
+    _golden_case(case_index, True, tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case_index", range(len(mgv.CASES)))
+def test_cuda_matches_golden_vcf(case_index, tmp_path):
+    st = _golden_case(case_index, False, tmp_path)
+    assert st.gpu_launches > 0
+
+
+def _vs_reference(paths, contig, tiles, opts, params, emulate, tmp_path):
+    ref = []
+    for k, t in enumerate(tiles):
+        d = tmp_path / ("r%d" % k)
+        d.mkdir()
+        ref += mgv.reference_vcf_lines(paths["bam"], paths["fasta"], contig, t, opts, str(d))
+    ours, stats = _our_lines(paths["bam"], paths["fasta"], tiles, emulate, **params)
+    _assert_same(ours, ref)
+    return stats
+
+
+@pytest.mark.skipif(not os.path.exists(pu.REF_UVC1), reason="oracle/_ref/uvc1 not built")
+def test_emulation_vcf_vs_reference_small(synth_small, tmp_path):
+    _vs_reference(synth_small, "chrA", [(0, 0, 6000, 0), (0, 6000, 12000, 0)], [], {}, True, tmp_path)
+
+
+@pytest.mark.skipif(not os.path.exists(pu.REF_UVC1), reason="oracle/_ref/uvc1 not built")
+def test_emulation_vcf_vs_reference_umi_allout(synth_umi, tmp_path):
+    _vs_reference(synth_umi, "chrU", [(0, 2000, 2400, 0)], ["-A"], {"should_output_all": 1}, True, tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(pu.REF_UVC1), reason="oracle/_ref/uvc1 not built")
+def test_cuda_vcf_vs_reference(synth_small, synth_umi, tmp_path):
+    st = _vs_reference(synth_small, "chrA", [(0, 0, 6000, 0), (0, 6000, 12000, 0)], ["-A"], {"should_output_all": 1}, False, tmp_path)
+    assert st.gpu_launches > 0
+    (tmp_path / "u").mkdir()
+    _vs_reference(synth_umi, "chrU", [(0, 1000, 4000, 0)], [], {}, False, tmp_path / "u")

@@ -77,7 +77,7 @@ class ReadsSoA(C.Structure):
 
 
 SECTIONS = {"meta": 0, "rtr": 1, "baq": 2, "baq2": 3, "prep": 4, "thres": 5, "seginfo": 6, "faminfo": 7, "fragdepth0": 8,
-            "fragdepth1": 9, "famdepth0": 10, "famdepth1": 11, "duplex": 12, "vq": 13, "families": 14, "rtr_initial": 15, "indelmaps": 16, "haplinks": 17}
+            "fragdepth1": 9, "famdepth0": 10, "famdepth1": 11, "duplex": 12, "vq": 13, "families": 14, "rtr_initial": 15, "indelmaps": 16, "haplinks": 17, "vcf": 18}
 
 _gpu_libs: Dict[bool, C.CDLL] = {}
 _host_lib: Optional[C.CDLL] = None
@@ -98,6 +98,9 @@ def load_gpu(emulate: bool = False) -> C.CDLL:
     lib.uvcgpu_last_error.argtypes = [C.c_void_p]
     lib.uvcgpu_last_error.restype = C.c_char_p
     lib.uvcgpu_set_contig.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int64]
+    lib.uvcgpu_set_contig_name.argtypes = [C.c_void_p, C.c_int32, C.c_char_p]
+    lib.uvcgpu_score.argtypes = [C.c_void_p, C.c_int64, C.POINTER(BatchStats)]
+    lib.uvcgpu_tile_vcf.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.uvcgpu_submit.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Tile), C.POINTER(ReadsSoA), C.POINTER(C.c_int64)]
     lib.uvcgpu_collect.argtypes = [C.c_void_p, C.c_int64, C.POINTER(BatchStats)]
     lib.uvcgpu_release.argtypes = [C.c_void_p, C.c_int64]
@@ -174,6 +177,21 @@ class Context:
 
     def set_contig(self, tid: int, bases: Optional[bytes]) -> None:
         self._check(self.lib.uvcgpu_set_contig(self.handle, tid, bases, len(bases) if bases is not None else 0), "uvcgpu_set_contig")
+
+    def set_contig_name(self, tid: int, name: str) -> None:
+        self._check(self.lib.uvcgpu_set_contig_name(self.handle, tid, name.encode()), "uvcgpu_set_contig_name")
+
+    def score(self, ticket: int) -> BatchStats:
+        st = BatchStats()
+        self._check(self.lib.uvcgpu_score(self.handle, ticket, C.byref(st)), "uvcgpu_score")
+        return st
+
+    def tile_vcf(self, ticket: int, tile_index: int) -> bytes:
+        need = C.c_size_t()
+        self._check(self.lib.uvcgpu_tile_vcf(self.handle, ticket, tile_index, None, 0, C.byref(need)), "uvcgpu_tile_vcf")
+        buf = C.create_string_buffer(max(1, need.value))
+        self._check(self.lib.uvcgpu_tile_vcf(self.handle, ticket, tile_index, buf, need.value, C.byref(need)), "uvcgpu_tile_vcf")
+        return buf.raw[:need.value]
 
     def submit(self, tiles: Sequence[Tile], reads: ReadsSoA) -> int:
         arr = (Tile * len(tiles))(*tiles)

@@ -9,7 +9,9 @@
 #include "batch.h"
 #include "host_prep.h"
 #include "kernels_core.cuh"
+#include "score_core.cuh"
 #include "sparse_out.h"
+#include "vcf_emit.h"
 
 #include <algorithm>
 #include <chrono>
@@ -48,6 +50,11 @@ struct BatchState {
     bool sparse_built = false;
     std::vector<TileSparse> sparse;
     std::vector<IndelEvent> ev_host;
+    bool scored = false;
+    std::vector<TileIndelSites> sites;
+    std::vector<std::vector<VarRec>> recs_by_tile;
+    std::vector<GvcfPos> gvcf;
+    std::vector<GvcfExtra> gextra;
 #if UVC_CUDA
     cudaEvent_t ev[12];
     bool have_events = false;
@@ -61,6 +68,7 @@ struct uvcgpu_ctx {
     uvcgpu_params par;
     std::string err;
     std::map<int32_t, HostContig> contigs;
+    std::map<int32_t, std::string> contig_names;
     std::map<uvcgpu_ticket, std::unique_ptr<BatchState>> batches;
     uvcgpu_ticket next_ticket = 1;
     std::vector<int32_t> slip_tab;
@@ -90,6 +98,16 @@ UVC_DEFINE_KERNEL(uvc_k3b_fragment_consensus, uvc::k3b_position(v, i))
 UVC_DEFINE_KERNEL(uvc_k4a_family_ends, uvc::k4a_family_strand(v, i))
 UVC_DEFINE_KERNEL(uvc_k4_family_consensus, uvc::k4_position(v, i))
 UVC_DEFINE_KERNEL(uvc_k4c_family_haplotypes, uvc::k4c_family_strand(v, i))
+
+// scoring stage: K6 one thread per extended position, K5 one thread per zero-based position (heavy local state: 64 threads per block)
+__global__ void __launch_bounds__(128) uvc_k6_gvcf_inputs(const BatchView v, const ScoreView sv, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { uvc::k6_gvcf_position(v, sv, i); }
+}
+__global__ void __launch_bounds__(64) uvc_k5_score_candidates(const BatchView v, const ScoreView sv, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { uvc::k5_score_position(v, sv, i); }
+}
 
 typedef void (*uvc_kernel_t)(const BatchView, int64_t);
 static void launch(uvc_kernel_t k, cudaStream_t s, const BatchView & v, int64_t n, int64_t & launches) {
@@ -162,6 +180,25 @@ static int backend_wait(uvcgpu_ctx *ctx, BatchState & bs) {
     return 0;
 }
 
+static int backend_score(uvcgpu_ctx *ctx, BatchState & bs, const ScoreView & sv) {
+    const BatchView & v = bs.view;
+    cudaEvent_t e[3];
+    for (int i = 0; i < 3; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreate(&e[i])); }
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(e[0], ctx->stream));
+    if (v.n_pos > 0) { uvc_k6_gvcf_inputs<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, ctx->stream>>>(v, sv, v.n_pos); }
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(e[1], ctx->stream));
+    if (v.n_pos > 0) { uvc_k5_score_candidates<<<(unsigned)((v.n_pos + 63) / 64), 64, 0, ctx->stream>>>(v, sv, v.n_pos); }
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(e[2], ctx->stream));
+    UVC_CUDA_CHECK(ctx, cudaGetLastError());
+    UVC_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, e[0], e[1])); bs.stats.kernel_ms_by_stage[9] = ms; bs.stats.kernel_ms += ms;
+    UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, e[1], e[2])); bs.stats.kernel_ms_by_stage[10] = ms; bs.stats.kernel_ms += ms;
+    for (int i = 0; i < 3; i++) { cudaEventDestroy(e[i]); }
+    if (v.n_pos > 0) { bs.stats.gpu_launches += 2; }
+    return 0;
+}
+
 #else // ------------------------------------------------------------------------------------------- emulation (tests only)
 
 static int backend_alloc(uvcgpu_ctx *, BatchState & bs, void **out, size_t bytes, bool) {
@@ -192,6 +229,12 @@ static int backend_run(uvcgpu_ctx *, BatchState & bs) {
     return 0;
 }
 static int backend_wait(uvcgpu_ctx *, BatchState &) { return 0; }
+static int backend_score(uvcgpu_ctx *, BatchState & bs, const ScoreView & sv) {
+    const BatchView & v = bs.view;
+    for (int64_t i = 0; i < v.n_pos; i++) { uvc::k6_gvcf_position(v, sv, i); }
+    for (int64_t i = 0; i < v.n_pos; i++) { uvc::k5_score_position(v, sv, i); }
+    return 0;
+}
 
 #endif
 
@@ -241,6 +284,44 @@ void uvcgpu_params_default(uvcgpu_params *p) {
     p->microadjust_near_clip_dist = 2; p->microadjust_alignment_clip_min_len = 12; p->microadjust_padded_deletion_flag = 0x2;
     p->microadjust_median_readlen_thres = 125; p->microadjust_BAQ_per_base_x1024 = 1024;
     p->tumor_vcf_fname_nonempty = 1;
+    // scoring defaults (CmdLineArgs.hpp:39, 72-82, 106-108, 110, 196-232, 242-247, 263-272, 277-303, 309-326, 341-347, 361-417) with the
+    // Illumina inference of CmdLineArgs.cpp:127-134 applied to syserr_minABQ_*
+    p->vqual = 15; p->vfa1 = 0.002; p->vfa2 = 0.0002; p->vdp1 = 1000; p->vad1 = 4; p->vdp2 = 10000; p->vad2 = 8; p->min_r_ad = 0; p->min_a_ad = 0;
+    p->syserr_minABQ_pcr_snv = 200; p->syserr_minABQ_pcr_indel = 100; p->syserr_minABQ_cap_snv = 200; p->syserr_minABQ_cap_indel = 100;
+    p->syserr_BQ_prior = 30; p->syserr_BQ_sbratio_q_add = 5; p->syserr_BQ_sbratio_q_max = 40; p->syserr_BQ_xmratio_q_add = 5; p->syserr_BQ_xmratio_q_max = 40;
+    p->syserr_BQ_bmratio_q_add = 5; p->syserr_BQ_bmratio_q_max = 40; p->syserr_BQ_strand_favor_mul = 3; p->syserr_MQ_min = 0; p->syserr_MQ_max = 60;
+    p->syserr_MQ_NMR_expfrac = 0.03; p->syserr_MQ_NMR_altfrac_coef = 2.0; p->syserr_MQ_NMR_nonaltfrac_coef = 2.0; p->syserr_MQ_NMR_pl_exponent = 3.0; p->syserr_MQ_nonref_base = 40;
+    p->powlaw_anyvar_base = (double)(60 + 25 + 5); p->powlaw_amplicon_allele_fraction_coef = (5.0 / 8.0);
+    p->penal4lowdep = 37; p->nobias_flag = 0x2; p->nobias_pos_indel_lenfrac_thres = 2.0; p->nobias_pos_indel_str_track_len = 16;
+    p->bias_prior_DPadd_perc = 50;
+    p->bias_priorfreq_pos = 40; p->bias_priorfreq_indel_in_read_div = 20; p->bias_priorfreq_indel_in_var_div2 = 15; p->bias_priorfreq_indel_in_str_div2 = 10; p->bias_priorfreq_var_in_str_div2 = 5;
+    p->bias_prior_var_DP_mul = 1.25 + (double)FLT_EPSILON;
+    p->bias_priorfreq_ipos_snv = 45; p->bias_priorfreq_ipos_indel = 45; p->bias_priorfreq_strand_snv_base = 10; p->bias_priorfreq_strand_indel = 45;
+    p->bias_FA_pseudocount_indel_in_read = 0.5 / 10.0; p->bias_priorfreq_orientation_snv_base = 45; p->bias_priorfreq_orientation_indel_base = 45;
+    p->bias_FA_powerlaw_noUMI_phred_inc_snv = 5; p->bias_FA_powerlaw_noUMI_phred_inc_indel = 7; p->bias_FA_powerlaw_withUMI_phred_inc_snv = 8; p->bias_FA_powerlaw_withUMI_phred_inc_indel = 7;
+    p->bias_reduction_by_high_sequencingDP_min_n_totDepth = 800; p->bias_reduction_by_high_sequencingDP_min_n_altDepth = 3;
+    p->bias_thres_FTS_FA = 0.6; p->bias_orientation_min_effective_allelefrac = 0.004; p->bias_is_orientation_artifact_mixed_with_sequencing_error = 0;
+    p->fam_min_n_copies = 800; p->fam_min_n_copies_DPxAD = 20 * 1000; p->fam_min_overseq_perc = 200; p->fam_bias_overseq_perc = 150; p->fam_tier3DP_bias_overseq_perc = 350;
+    p->fam_indel_nonUMI_phred_dec_per_fold_overseq = 9;
+    p->fam_phred_dscs_all = 58; p->fam_phred_dscs_max = 68; p->fam_phred_dscs_inc_max = (68 - 48); p->fam_phred_pow_sscs_transversion_AT_TA_origin = 44 - (41 - 6) + 4;
+    p->fam_phred_pow_sscs_snv_origin = 44 - (41 - 6); p->fam_phred_pow_sscs_indel_origin = 58 - 9 * 3; p->fam_phred_pow_dscs_all_origin = 0;
+    p->germ_hetero_FA = 0.47;
+    p->germ_phred_hetero_snp = 31; p->germ_phred_hetero_indel = 40; p->germ_phred_homalt_snp = 33; p->germ_phred_homalt_indel = 42; p->germ_phred_het3al_snp = 59; p->germ_phred_het3al_indel = 49;
+    p->tn_q_inc_max = 9; p->tn_q_inc_max_sscs_CG_AT = 0; p->tn_q_inc_max_sscs_other = 5; p->tn_syserr_norm_devqual = 15.0;
+    p->indel_multiallele_samepos_penal = 11.0; p->indel_multiallele_diffpos_penal = 8.0; p->indel_multiallele_soma_penal_thres = 11.0;
+    p->indel_tetraallele_germline_penal_value = 8.0 * 2; p->indel_tetraallele_germline_penal_thres = 22.0; p->indel_ins_penal_pseudocount = 16;
+    p->contam_any_mul_frac = 0.02; p->contam_t2n_mul_frac = 0.05;
+    p->microadjust_bias_pos_indel_fold = 2; p->microadjust_bias_pos_indel_misma_to_indel_ratio = 4 * (1.0 - DBL_EPSILON); p->microadjust_nobias_pos_indel_misma_to_indel_ratio = 4 * (1.0 - DBL_EPSILON);
+    p->microadjust_nobias_pos_indel_bMQ = 50; p->microadjust_nobias_pos_indel_perc = 50;
+    p->microadjust_nobias_strand_all_fold = 5; p->microadjust_refbias_indel_max = 2.0; p->microadjust_counterbias_pos_odds_ratio = 3.5; p->microadjust_counterbias_pos_fold_ratio = 5.0;
+    p->microadjust_fam_binom_qual_halving_thres = 70; p->microadjust_ref_MQ_dec_max = 15;
+    p->microadjust_syserr_MQ_NMR_tn_syserr_no_penal_qual_min = 30; p->microadjust_syserr_MQ_NMR_tn_syserr_no_penal_qual_max = 30 + 12;
+    p->microadjust_longfrag_sidelength_min = 300; p->microadjust_longfrag_sidelength_max = 600; p->microadjust_longfrag_sidelength_zeroMQpenalty = 300;
+    p->microadjust_alignment_clip_min_count = 2; p->microadjust_alignment_tracklen_min = 25; p->microadjust_alignment_clip_min_frac = 0.05;
+    p->microadjust_germline_mix_with_del_snv_penalty = 9; p->microadjust_strand_orientation_absence_DP_fold = 5; p->microadjust_orientation_absence_snv_penalty = 4;
+    p->microadjust_strand_absence_snv_penalty = 4; p->microadjust_dedup_absence_indel_penalty = 1;
+    p->lib_wgs_min_avg_fraglen = 300; p->lib_nonwgs_clip_penal_min_indelsize = 8; p->lib_nonwgs_normal_max_rescued_MQ = 30; p->lib_wgs_normal_max_rescued_MQ = 0;
+    p->lib_nonwgs_ad_pseudocount = 0.1; p->lib_nonwgs_normal_full_self_rescue_fa = 0.1; p->lib_nonwgs_normal_min_self_rescue_fa_ratio = 0.2; p->lib_nonwgs_normal_add_mul_ad = 1.0;
     p->phasing_haplotype_max_count = 8; p->phasing_haplotype_min_ad = 1; p->phasing_haplotype_max_detail_cnt = 3;
 }
 
@@ -308,6 +389,12 @@ int uvcgpu_set_contig(uvcgpu_ctx *ctx, int32_t tid, const char *bases, int64_t l
         c.bases.assign(bases, (size_t)len);
         for (auto & ch : c.bases) { ch = (char)toupper(ch); } // load_refstring (main.cpp:65-67)
     }
+    return UVCGPU_OK;
+}
+
+int uvcgpu_set_contig_name(uvcgpu_ctx *ctx, int32_t tid, const char *name) {
+    if (NULL == ctx || tid < 0 || NULL == name) { return UVCGPU_EINVAL; }
+    ctx->contig_names[tid] = name;
     return UVCGPU_OK;
 }
 
@@ -417,6 +504,96 @@ static int ensure_sparse(uvcgpu_ctx *ctx, BatchState & bs) {
     return 0;
 }
 
+static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
+    if (bs.scored) { return 0; }
+    int rc = ensure_sparse(ctx, bs);
+    if (rc != 0) { return rc; }
+    const double t0 = now_ms();
+    BatchView & v = bs.view;
+    std::vector<IndelAllele> table;
+    uvc_build_indel_sites(bs.sites, table, bs.hb, bs.sparse, ctx->contigs, bs.ev_host);
+    const double t1 = now_ms();
+    ScoreView sv;
+    memset(&sv, 0, sizeof(sv));
+    void *d = NULL;
+    if ((rc = backend_alloc(ctx, bs, &d, table.size() * sizeof(IndelAllele), false)) != 0) { return rc; }
+    if ((rc = backend_upload(ctx, bs, d, table.data(), table.size() * sizeof(IndelAllele))) != 0) { return rc; }
+    sv.alleles = (const IndelAllele*)d; sv.n_alleles = (int64_t)table.size();
+    if ((rc = backend_alloc(ctx, bs, &d, (size_t)v.n_pos * sizeof(GvcfPos), true)) != 0) { return rc; }
+    sv.gvcf = (GvcfPos*)d;
+    if ((rc = backend_alloc(ctx, bs, &d, (size_t)v.n_pos * sizeof(GvcfExtra), true)) != 0) { return rc; }
+    sv.gextra = (GvcfExtra*)d;
+    if ((rc = backend_alloc(ctx, bs, &d, 16, true)) != 0) { return rc; }
+    sv.out_cursor = (int32_t*)d;
+    int64_t cap = v.n_pos / 16 + 4096;
+    std::vector<VarRec> recs;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if ((rc = backend_alloc(ctx, bs, &d, (size_t)cap * sizeof(VarRec), false)) != 0) { return rc; }
+        sv.out = (VarRec*)d; sv.out_cap = (int32_t)cap;
+        const int32_t zero4[4] = {0, 0, 0, 0};
+        if ((rc = backend_upload(ctx, bs, sv.out_cursor, zero4, sizeof(zero4))) != 0) { return rc; }
+        if ((rc = backend_score(ctx, bs, sv)) != 0) { return rc; }
+        int32_t n = 0;
+        if ((rc = backend_download(ctx, &n, sv.out_cursor, sizeof(n))) != 0) { return rc; }
+        if (n <= cap) {
+            recs.resize((size_t)n);
+            if ((rc = backend_download(ctx, recs.data(), sv.out, recs.size() * sizeof(VarRec))) != 0) { return rc; }
+            break;
+        }
+        if (attempt == 1) { ctx->err = "candidate record buffer overflow"; return UVCGPU_ENOMEM; }
+        cap = n;   // the kernel counted every record it wanted to write: run again with room for all of them
+    }
+    bs.gvcf.resize((size_t)v.n_pos); bs.gextra.resize((size_t)v.n_pos);
+    if ((rc = backend_download(ctx, bs.gvcf.data(), sv.gvcf, bs.gvcf.size() * sizeof(GvcfPos))) != 0) { return rc; }
+    if ((rc = backend_download(ctx, bs.gextra.data(), sv.gextra, bs.gextra.size() * sizeof(GvcfExtra))) != 0) { return rc; }
+    bs.stats.d2h_bytes += (int64_t)(recs.size() * sizeof(VarRec) + bs.gvcf.size() * sizeof(GvcfPos) + bs.gextra.size() * sizeof(GvcfExtra));
+    const double t2 = now_ms();
+    bs.recs_by_tile.assign(bs.hb.tiles.size(), std::vector<VarRec>());
+    for (const auto & r : recs) { bs.recs_by_tile[(size_t)r.tile].push_back(r); }
+    bs.stats.n_vcf_records = (int64_t)recs.size();
+    bs.stats.host_score_ms = (t1 - t0) + (now_ms() - t2);
+    bs.scored = true;
+    return 0;
+}
+
+int uvcgpu_score(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, uvcgpu_batch_stats *stats) {
+    if (NULL == ctx) { return UVCGPU_EINVAL; }
+    auto it = ctx->batches.find(ticket);
+    if (it == ctx->batches.end()) { ctx->err = "unknown ticket"; return UVCGPU_EINVAL; }
+    BatchState & bs = *it->second;
+    if (!bs.collected) { ctx->err = "batch not collected yet"; return UVCGPU_EINVAL; }
+    int rc = ensure_scored(ctx, bs);
+    if (rc != 0) { return rc; }
+    if (stats) { *stats = bs.stats; }
+    return UVCGPU_OK;
+}
+
+static int tile_vcf_text(uvcgpu_ctx *ctx, BatchState & bs, int32_t tile_index, std::string & out) {
+    int rc = ensure_scored(ctx, bs);
+    if (rc != 0) { return rc; }
+    const TileInfo & T = bs.hb.tiles[tile_index];
+    auto nm = ctx->contig_names.find(T.tid);
+    const std::string tname = (nm == ctx->contig_names.end() ? std::to_string(T.tid) : nm->second);
+    out = uvc_tile_vcf_text(bs.hb, tile_index, ctx->par, tname, ctx->contigs.at(T.tid), bs.recs_by_tile[tile_index], bs.sites[tile_index],
+            bs.sparse[tile_index], bs.ev_host, bs.gvcf.data(), bs.gextra.data());
+    return 0;
+}
+
+int uvcgpu_tile_vcf(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_index, char *dst, size_t cap, size_t *needed) {
+    if (NULL == ctx || NULL == needed) { return UVCGPU_EINVAL; }
+    auto it = ctx->batches.find(ticket);
+    if (it == ctx->batches.end()) { ctx->err = "unknown ticket"; return UVCGPU_EINVAL; }
+    BatchState & bs = *it->second;
+    if (!bs.collected) { ctx->err = "batch not collected yet"; return UVCGPU_EINVAL; }
+    if (tile_index < 0 || tile_index >= (int32_t)bs.hb.tiles.size()) { return UVCGPU_EINVAL; }
+    std::string s;
+    int rc = tile_vcf_text(ctx, bs, tile_index, s);
+    if (rc != 0) { return rc; }
+    *needed = s.size();
+    if (dst && cap) { memcpy(dst, s.data(), s.size() < cap ? s.size() : cap); }
+    return UVCGPU_OK;
+}
+
 int uvcgpu_release(uvcgpu_ctx *ctx, uvcgpu_ticket ticket) {
     if (NULL == ctx) { return UVCGPU_EINVAL; }
     auto it = ctx->batches.find(ticket);
@@ -463,6 +640,13 @@ int uvcgpu_dump_counters(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_ind
             int rc = ensure_sparse(ctx, bs);
             if (rc != 0) { return rc; }
             const std::string s = (section == UVCGPU_SEC_INDELMAPS ? uvc_indelmaps_text(bs.sparse[tile_index]) : uvc_haplinks_text(bs.sparse[tile_index]));
+            tmp.assign(s.begin(), s.end());
+            host_side = true; break;
+        }
+        case UVCGPU_SEC_VCF: {
+            std::string s;
+            int rc = tile_vcf_text(ctx, bs, tile_index, s);
+            if (rc != 0) { return rc; }
             tmp.assign(s.begin(), s.end());
             host_side = true; break;
         }

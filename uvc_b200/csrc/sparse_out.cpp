@@ -59,12 +59,12 @@ void uvc_build_sparse(std::vector<TileSparse> & out, const HostBatch & hb, const
             IndelKey k; k.kind = kind; k.strand = rec[o + 1]; k.symbol = rec[o + 2]; k.pos = rec[o + 3];
             TileSparse & ts = out[R.tile];
             if (E.is_del) {
-                ts.del[k][E.oplen] += rec[o + 5];
+                IdCount & ic = ts.del[k][E.oplen]; ic.count += rec[o + 5]; if (ic.ev < 0) { ic.ev = rec[o + 4]; }
             } else {
                 std::string seq;
                 const uint8_t *s = hb.seq.data() + R.seq_off;
                 for (int32_t i = 0; i < E.oplen; i++) { const int32_t q = E.qpos + i; seq.push_back(nt16[(s[q >> 1] >> ((~q & 1) << 2)) & 0xf]); }
-                ts.ins[k][seq] += rec[o + 5];
+                IdCount & ic = ts.ins[k][seq]; ic.count += rec[o + 5]; if (ic.ev < 0) { ic.ev = rec[o + 4]; }
             }
             o += 6;
         } else if (kind >= UVC_REC_HAP_BQ && kind <= UVC_REC_HAP_F2Q) {
@@ -96,13 +96,13 @@ std::string uvc_indelmaps_text(const TileSparse & ts) {
     for (const auto & kv : ts.ins) {
         for (const auto & sc : kv.second) {
             out += std::string(labels_ins[kv.first.kind]) + "\t" + std::to_string(kv.first.strand) + "\t" + std::to_string(kv.first.symbol) + "\t"
-                + std::to_string(kv.first.pos) + "\t" + sc.first + "\t" + std::to_string(sc.second) + "\n";
+                + std::to_string(kv.first.pos) + "\t" + sc.first + "\t" + std::to_string(sc.second.count) + "\n";
         }
     }
     for (const auto & kv : ts.del) {
         for (const auto & sc : kv.second) {
             out += std::string(labels_del[kv.first.kind]) + "\t" + std::to_string(kv.first.strand) + "\t" + std::to_string(kv.first.symbol) + "\t"
-                + std::to_string(kv.first.pos) + "\t" + std::to_string(sc.first) + "\t" + std::to_string(sc.second) + "\n";
+                + std::to_string(kv.first.pos) + "\t" + std::to_string(sc.first) + "\t" + std::to_string(sc.second.count) + "\n";
         }
     }
     return out;

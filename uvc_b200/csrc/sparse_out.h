@@ -29,10 +29,12 @@ struct HapLinkOut {
     std::array<int32_t, 2> other_hap_cnts;
 };
 
+struct IdCount { int32_t count = 0; int32_t ev = -1; };   // count of an indel identity and one representative device event
+
 struct TileSparse {
     // insertions keyed by inserted sequence, deletions keyed by length (kept separately like the reference)
-    std::map<IndelKey, std::map<std::string, int32_t>> ins;
-    std::map<IndelKey, std::map<int32_t, int32_t>> del;
+    std::map<IndelKey, std::map<std::string, IdCount>> ins;
+    std::map<IndelKey, std::map<int32_t, IdCount>> del;
     std::vector<HapLinkOut> hap_bq, hap_fq, hap_f2q;
 };
 
