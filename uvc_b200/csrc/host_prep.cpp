@@ -7,7 +7,9 @@
 #include "host_prep.h"
 
 #include <algorithm>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <unordered_map>
 #include <unordered_set>
@@ -298,21 +300,18 @@ void uvc_fill_view_constants(BatchView & v, const uvcgpu_params & par) {
     v.indelphred_half = ((int32_t)round((10.0 / log(10.0)) * log(par.indel_del_to_ins_err_ratio))) / 2;
 }
 
-int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::map<int32_t, HostContig> & contigs,
-        int32_t n_tiles, const uvcgpu_tile *tiles, const uvcgpu_reads_soa & rs, std::string & msg) {
-    if (par.inferred_sequencing_platform != 1) { msg = "only the Illumina/BGI platform path is implemented"; return UVCGPU_EUNSUPPORTED; }
-    const bool pem = (0 == par.pair_end_merge);
-    double center_pow[4];
-    for (int d = 0; d < 4; d++) { center_pow[d] = pow(par.dedup_center_mult, (double)d); }
-    hb = HostBatch();
-    hb.tiles.resize(n_tiles);
-    for (int32_t ti = 0; ti < n_tiles; ti++) {
-        const uvcgpu_tile & ut = tiles[ti];
-        TileInfo & T = hb.tiles[ti];
+// Stages ONE tile into a private HostBatch whose offsets are all tile-local (the tile keeps its global index ti in the
+// records). Tiles are independent (the reference runs them on different threads, main.cpp:1479), so the batch builder
+// below stages them on all host cores and then concatenates.
+static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<int32_t, HostContig> & contigs,
+        int32_t ti, const uvcgpu_tile & ut, const uvcgpu_reads_soa & rs, const double *center_pow, bool pem, std::string & msg) {
+    hb.tiles.resize(1);
+    {
+        TileInfo & T = hb.tiles[0];
         memset(&T, 0, sizeof(T));
         T.tid = ut.tid; T.beg_pos = ut.beg_pos; T.end_pos = ut.end_pos; T.region_flag = ut.region_flag;
         T.prev_tid = ut.prev_tid; T.prev_beg_pos = ut.prev_beg_pos; T.prev_end_pos = ut.prev_end_pos;
-        T.pos_off = hb.n_pos; T.read_off = (int64_t)hb.reads.size(); T.frag_off = (int64_t)hb.frags.size(); T.fam_off = (int64_t)hb.fams.size();
+        T.pos_off = 0; T.read_off = 0; T.frag_off = 0; T.fam_off = 0;
         if (ut.read_begin < 0 || ut.read_end > rs.n_reads || ut.read_begin > ut.read_end || ut.beg_pos >= ut.end_pos) { msg = "invalid tile"; return UVCGPU_EINVAL; }
         auto cit = contigs.find(ut.tid);
         hb.n_reads_in += ut.read_end - ut.read_begin;
@@ -426,7 +425,7 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
         T.num_pcrpassed = pcrpassed;
         T.bam_inclu_beg = bam_beg; T.bam_exclu_end = bam_end;
         T.is_amplicon_inferred = !((pcrpassed) * 2 <= (int64_t)kept.size());
-        if (kept.empty()) { T.skipped = 1; T.ext_beg = T.ext_end = 0; continue; }
+        if (kept.empty()) { T.skipped = 1; T.ext_beg = T.ext_end = 0; return 0; }
         if (cit == contigs.end()) { msg = "contig of a tile was not set with uvcgpu_set_contig"; return UVCGPU_EINVAL; }
         const HostContig & contig = cit->second;
         T.rpos_inclu_beg = std::max(ut.beg_pos, bam_beg);
@@ -577,6 +576,101 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
         baq_prefix(hb.baq2, poff, rtr, true, par);
         hb.n_pos += npos;
     }
+    return 0;
+}
+
+static int host_threads(int32_t n_tiles) {
+    int n = (int)std::thread::hardware_concurrency();
+    const char *e = getenv("UVC_HOST_THREADS");
+    if (e && atoi(e) > 0) { n = atoi(e); }
+    if (n < 1) { n = 1; }
+    if (n > 64) { n = 64; }
+    return std::min<int>(n, n_tiles);
+}
+
+template <class F> static void parallel_for(int32_t n, int n_threads, F body) {
+    if (n_threads <= 1) { for (int32_t i = 0; i < n; i++) { body(i); } return; }
+    std::atomic<int32_t> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; t++) {
+        pool.emplace_back([&]() { for (;;) { const int32_t i = next.fetch_add(1); if (i >= n) { break; } body(i); } });
+    }
+    for (auto & th : pool) { th.join(); }
+}
+
+int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::map<int32_t, HostContig> & contigs,
+        int32_t n_tiles, const uvcgpu_tile *tiles, const uvcgpu_reads_soa & rs, std::string & msg) {
+    if (par.inferred_sequencing_platform != 1) { msg = "only the Illumina/BGI platform path is implemented"; return UVCGPU_EUNSUPPORTED; }
+    const bool pem = (0 == par.pair_end_merge);
+    double center_pow[4];
+    for (int d = 0; d < 4; d++) { center_pow[d] = pow(par.dedup_center_mult, (double)d); }
+    hb = HostBatch();
+    const int n_threads = host_threads(n_tiles);
+    // 1. every tile staged privately, on all host cores
+    std::vector<HostBatch> part((size_t)n_tiles);
+    std::vector<int> rcs((size_t)n_tiles, 0);
+    std::vector<std::string> msgs((size_t)n_tiles);
+    parallel_for(n_tiles, n_threads, [&](int32_t ti) { rcs[ti] = build_tile(part[ti], par, contigs, ti, tiles[ti], rs, center_pow, pem, msgs[ti]); });
+    for (int32_t ti = 0; ti < n_tiles; ti++) { if (rcs[ti] != 0) { msg = msgs[ti]; return rcs[ti]; } }
+    // 2. offsets of every tile in the concatenated arrays
+    struct Off { int64_t pos, read, frag, fam, fragread, seq, qual, cigar, cx, ev; };
+    std::vector<Off> off((size_t)n_tiles + 1);
+    memset(&off[0], 0, sizeof(Off));
+    for (int32_t ti = 0; ti < n_tiles; ti++) {
+        const HostBatch & b = part[ti];
+        Off o = off[ti];
+        o.pos += b.n_pos; o.read += (int64_t)b.reads.size(); o.frag += (int64_t)b.frags.size(); o.fam += (int64_t)b.fams.size();
+        o.fragread += (int64_t)b.frag_reads.size(); o.seq += (int64_t)b.seq.size(); o.qual += (int64_t)b.qual.size(); o.cigar += (int64_t)b.cigar.size();
+        o.cx += b.n_cx; o.ev += b.n_ev;
+        off[ti + 1] = o;
+        hb.n_reads_in += b.n_reads_in;
+    }
+    const Off & tot = off[n_tiles];
+    if (tot.read > INT32_MAX || tot.frag > INT32_MAX || tot.cx > INT32_MAX || tot.ev > INT32_MAX || tot.fragread > INT32_MAX) { msg = "batch too large: submit fewer tiles"; return UVCGPU_EINVAL; }
+    hb.tiles.resize((size_t)n_tiles);
+    hb.pos_tile.resize((size_t)tot.pos); hb.refsym.resize((size_t)tot.pos); hb.rtr.resize((size_t)tot.pos); hb.baq.resize((size_t)tot.pos); hb.baq2.resize((size_t)tot.pos);
+    hb.reads.resize((size_t)tot.read); hb.read_raw_index.resize((size_t)tot.read);
+    hb.seq.resize((size_t)tot.seq); hb.qual.resize((size_t)tot.qual); hb.cigar.resize((size_t)tot.cigar);
+    hb.frags.resize((size_t)tot.frag); hb.frag_reads.resize((size_t)tot.fragread); hb.fams.resize((size_t)tot.fam); hb.fam_umi.resize((size_t)tot.fam);
+    hb.n_pos = tot.pos; hb.n_cx = tot.cx; hb.n_ev = tot.ev;
+    // 3. concatenation with the tile-local indices rebased, again on all cores (disjoint destination ranges)
+    parallel_for(n_tiles, n_threads, [&](int32_t ti) {
+        HostBatch & b = part[ti];
+        const Off & o = off[ti];
+        TileInfo T = b.tiles[0];
+        T.pos_off = o.pos; T.read_off = o.read; T.frag_off = o.frag; T.fam_off = o.fam;
+        hb.tiles[ti] = T;
+        std::fill(hb.pos_tile.begin() + o.pos, hb.pos_tile.begin() + o.pos + b.n_pos, ti);
+        std::copy(b.refsym.begin(), b.refsym.end(), hb.refsym.begin() + o.pos);
+        std::copy(b.rtr.begin(), b.rtr.end(), hb.rtr.begin() + o.pos);
+        std::copy(b.baq.begin(), b.baq.end(), hb.baq.begin() + o.pos);
+        std::copy(b.baq2.begin(), b.baq2.end(), hb.baq2.begin() + o.pos);
+        std::copy(b.seq.begin(), b.seq.end(), hb.seq.begin() + o.seq);
+        std::copy(b.qual.begin(), b.qual.end(), hb.qual.begin() + o.qual);
+        std::copy(b.cigar.begin(), b.cigar.end(), hb.cigar.begin() + o.cigar);
+        std::copy(b.read_raw_index.begin(), b.read_raw_index.end(), hb.read_raw_index.begin() + o.read);
+        for (size_t i = 0; i < b.reads.size(); i++) {
+            ReadRec R = b.reads[i];
+            R.frag += (int32_t)o.frag; R.fam += (int32_t)o.fam;
+            R.seq_off += (uint64_t)o.seq; R.qual_off += (uint64_t)o.qual; R.cigar_off += (uint64_t)o.cigar;
+            if (R.cx_off >= 0) { R.cx_off += (int32_t)o.cx; }
+            R.ev_off += (int32_t)o.ev;
+            hb.reads[(size_t)o.read + i] = R;
+        }
+        for (size_t i = 0; i < b.frags.size(); i++) {
+            FragRec G = b.frags[i];
+            G.fam += (int32_t)o.fam; G.read_off += (int32_t)o.fragread;
+            hb.frags[(size_t)o.frag + i] = G;
+        }
+        for (size_t i = 0; i < b.frag_reads.size(); i++) { hb.frag_reads[(size_t)o.fragread + i] = b.frag_reads[i] + (int32_t)o.read; }
+        for (size_t i = 0; i < b.fams.size(); i++) {
+            FamRec F = b.fams[i];
+            F.frag_off[0] += (int32_t)o.frag; F.frag_off[1] += (int32_t)o.frag;
+            hb.fams[(size_t)o.fam + i] = F;
+            hb.fam_umi[(size_t)o.fam + i].swap(b.fam_umi[i]);
+        }
+        b = HostBatch();   // release the private copy
+    });
     return 0;
 }
 

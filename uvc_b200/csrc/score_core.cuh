@@ -92,6 +92,23 @@ namespace uvc {
 
 UVC_HD double dmin(double a, double b) { return a < b ? a : b; }
 UVC_HD double dmax(double a, double b) { return a > b ? a : b; }
+// double -> integer conversion with x86-64 semantics (cvttsd2si): NaN and out-of-range values give the most negative integer
+// ("integer indefinite"). The reference runs on x86-64 and several of its intermediate allele fractions are NaN or infinite for
+// zero-depth alleles (0/0); its results therefore depend on this behaviour, while CUDA's cvt.rzi saturates (NaN -> 0, +inf -> INT_MAX).
+UVC_HD int32_t d2i(double x) {
+#if defined(__CUDA_ARCH__)
+    return ((x > -2147483649.0 && x < 2147483648.0) ? (int32_t)x : INT32_MIN);
+#else
+    return (int32_t)x;
+#endif
+}
+UVC_HD int64_t d2l(double x) {
+#if defined(__CUDA_ARCH__)
+    return ((x >= -9223372036854775808.0 && x < 9223372036854775808.0) ? (int64_t)x : INT64_MIN);
+#else
+    return (int64_t)x;
+#endif
+}
 UVC_HD bool is_subst(int s) { return s >= UVC_BASE_A && s <= UVC_BASE_NN; }
 
 // SYMBOL_TYPE_TO_SYMBOLS order (main_conversion.hpp:397-400)
@@ -195,9 +212,9 @@ UVC_HD void cand_init(CandFmt & c, const GroupFmt & g, const BatchView & v, cons
     const int32_t rssDPrBQ = (int32_t)(aDPr * sqrt((double)(((int64_t)a2BQr * UVC_SQR_QUAL_DIV) / tmax(1, aDPr))));
     const int32_t rssDPbBQ = (int32_t)((aDPf + aDPr) * sqrt((double)((a2BQf + a2BQr) * UVC_SQR_QUAL_DIV / tmax(1, aDPf + aDPr))));
     const double excess = dmax(0.0, ((aDPf + aDPr + 0.5) * 2.0 / (ADP + 1.0) - 1.0));
-    int32_t minABQa = minABQ - (int32_t)(5 * 10.0 * (excess * excess));
+    int32_t minABQa = minABQ - d2i((5 * 10.0 * (excess * excess)));
     const double sbratio = (double)(tmax(aDPf, aDPr) * 10 + 10) / (double)(tmin(aDPf, aDPr) * 10 + 10);
-    minABQa += between((int32_t)(sbratio * sbratio) - par.syserr_BQ_sbratio_q_add, 0, par.syserr_BQ_sbratio_q_max);
+    minABQa += between(d2i((sbratio * sbratio)) - par.syserr_BQ_sbratio_q_add, 0, par.syserr_BQ_sbratio_q_max);
     const int32_t xmratio = (par.syserr_BQ_xmratio_q_max * 10 * (aDPf + aDPr) / tmax(1, c.a2XM2));
     const int32_t bmratio = (par.syserr_BQ_bmratio_q_max * 10 * (aDPf + aDPr) / tmax(1, c.a2BM2));
     minABQa += between(xmratio - par.syserr_BQ_xmratio_q_add, 0, par.syserr_BQ_xmratio_q_max) + between(bmratio - par.syserr_BQ_bmratio_q_add, 0, par.syserr_BQ_bmratio_q_max);
@@ -248,7 +265,7 @@ UVC_HD double prob2odds(double p) { return p / (1.0 - p); }
 UVC_HD double logit2(double a, double b) { return log(prob2odds((a + DBL_EPSILON) / (a + b + 2.0 * DBL_EPSILON))); }
 UVC_HD double phred2nat(const BatchView & v, double x) { return (v.ln10 / 10.0) * x; }
 UVC_HD double numstates2phred(const BatchView & v, double x) { return v.ten_over_ln10 * log(x); }
-UVC_HD int32_t numstates2deciphred(const BatchView & v, double x) { return (int32_t)round((100.0 / v.ln10) * log(x)); }
+UVC_HD int32_t numstates2deciphred(const BatchView & v, double x) { return d2i(round((100.0 / v.ln10) * log(x))); }
 
 // calc_binom_10log10_likeratio<false,false> (main_conversion.hpp:222-237)
 UVC_HD double binom_10log10_likeratio(const BatchView & v, double prob, double a, double b) {
@@ -269,7 +286,7 @@ UVC_HD double norm_fa_refbias(double FA, double refbias) { return (FA + FA * ref
 UVC_HD int32_t bias_push(CandFmt & c, const BatchView & v, int fts_index, double refFA, double biasFA) {
     if (biasFA < refFA * v.par.bias_thres_FTS_FA) {
         c.fts_mask |= (1u << fts_index);
-        c.fts_pct[fts_index] = (int32_t)round(100.0 * biasFA / refFA);
+        c.fts_pct[fts_index] = d2i(round(100.0 * biasFA / refFA));
     }
     return -numstates2deciphred(v, biasFA);
 }
@@ -357,7 +374,7 @@ UVC_HD void calc_DPv(CandFmt & c, const GroupFmt & g, const BatchView & v, const
     }
     const double aPpriorfreq = aPpriorfreq0 + allbias_allprior;
     const double aBpriorfreq = aBpriorfreq0 + allbias_allprior;
-    c.nPF[0] = (int32_t)round(aPpriorfreq); c.nPF[1] = (int32_t)round(aBpriorfreq);
+    c.nPF[0] = d2i(round(aPpriorfreq)); c.nPF[1] = d2i(round(aBpriorfreq));
     const double aIpriorfreq = (subst ? par.bias_priorfreq_ipos_snv : par.bias_priorfreq_ipos_indel) + allbias_allprior;
     const double aSBpriorfreq = (subst ? (tmin(nnminus(c.aBQ, 0), c.bMQ) + par.bias_priorfreq_strand_snv_base) : (par.bias_priorfreq_strand_indel)) + allbias_allprior;
     const double dedup_A2C1_frac = dmin(1.0, (double)tmax(CDP1, par.bias_reduction_by_high_sequencingDP_min_n_totDepth) / (double)tmax(ADP1, 1));
@@ -478,8 +495,8 @@ UVC_HD void calc_DPv(CandFmt & c, const GroupFmt & g, const BatchView & v, const
     const double alt_frac = (is_nmore_amplicon ? (dmax(0, alt_frac0 - 0.2) * 1.25) : alt_frac0);
     const double nonalt_frac = (fBTB + par.contam_any_mul_frac * fbTB - fbTB) / (fBTA + par.contam_any_mul_frac * fbTA - fbTA);
     const double frac_mut = dmax(par.syserr_MQ_NMR_expfrac, par.syserr_MQ_NMR_altfrac_coef * alt_frac * frag_sidelen_frac - par.syserr_MQ_NMR_nonaltfrac_coef * nonalt_frac);
-    c.bNMQ = (int32_t)round(numstates2phred(v, pow(frac_mut / par.syserr_MQ_NMR_expfrac, (par.syserr_MQ_NMR_pl_exponent))) * (frac_mut));
-    c.bNMa = (int32_t)round(100 * alt_frac); c.bNMb = (int32_t)round(100 * nonalt_frac);
+    c.bNMQ = d2i(round(numstates2phred(v, pow(frac_mut / par.syserr_MQ_NMR_expfrac, (par.syserr_MQ_NMR_pl_exponent))) * (frac_mut)));
+    c.bNMa = d2i(round(100 * alt_frac)); c.bNMb = d2i(round(100 * nonalt_frac));
     const bool tmore_with_primerlen = (is_tmore_amplicon || ((par.primerlen > 0) && !(0x4 & par.primer_flag)));
     const double bFAa = bFA;
     double t1only = dmin(cROFA1, dmin(aLPFA2, dmin(aRPFA2, dmin(aLBFA2, dmin(aRBFA2, cFA0)))));
@@ -509,21 +526,21 @@ UVC_HD void calc_DPv(CandFmt & c, const GroupFmt & g, const BatchView & v, const
     const double refbias = 0;
     const int32_t CDP1sum = g.CDP1b[0] + g.CDP1b[1], CDP2sum = g.CDP2b[0] + g.CDP2b[1];
     const double min_abcFA_v = dmax(dmin(dmin(t1plus, t1only), aNCFA), counterbias_FA);
-    c.cDP1v = (int32_t)(norm_fa_refbias(min_abcFA_v, refbias) * CDP1sum * 100);
+    c.cDP1v = d2i((norm_fa_refbias(min_abcFA_v, refbias) * CDP1sum * 100));
     const double min_abcFA_w = dmax(dmin(aLPFA2, dmin(aRPFA2, dmin(aLBFA2, dmin(aRBFA2, dmin(bFA, aNCFA))))), counterbias_FA);
-    c.cDP1w = (int32_t)(norm_fa_refbias(min_abcFA_w, refbias) * CDP1sum * 100);
+    c.cDP1w = d2i((norm_fa_refbias(min_abcFA_w, refbias) * CDP1sum * 100));
     const double min_abcFA_x = dmin(aPFFA, dedup_FA);
-    c.cDP1x = 1 + (int32_t)(min_abcFA_x * CDP1sum * 100);
+    c.cDP1x = 1 + d2i((min_abcFA_x * CDP1sum * 100));
     const double cube = cFA2 * cFA2 * cFA2;
     const double c2XBFA2 = dmin(dmax(3.0 * c2LBFA2 * c2RBFA2 * aSSFA2 / cube, dmin(c2LBFA2, c2RBFA2) / 8.0), dmin(c2LBFA2, c2RBFA2));
     const double c2XPFA2 = dmin(dmax(3.0 * c2LPFA2 * c2RPFA2 * aSSFA2 / cube, dmin(c2LPFA2, c2RPFA2) / 8.0), dmin(c2LPFA2, c2RPFA2));
     const double c2XXFA2 = dmin(c2XBFA2, c2XPFA2);
     const double min_c23FA_v = dmax(dmin(dmin(t1plus, dmin(t2only, c2XXFA2)), aNCFA), counterbias_FA * frac_umi2seg);
-    c.cDP2v = (int32_t)(norm_fa_refbias(min_c23FA_v, refbias) * CDP2sum * 100);
+    c.cDP2v = d2i((norm_fa_refbias(min_c23FA_v, refbias) * CDP2sum * 100));
     const double min_c23FA_w = dmax(dmin(c2LPFA2, dmin(c2RPFA2, dmin(c2XXFA2, dmin(c2LBFA2, dmin(c2RBFA2, dmin(cFA2, aNCFA)))))), counterbias_FA * frac_umi2seg);
-    c.cDP2w = (int32_t)(norm_fa_refbias(min_c23FA_w, refbias) * CDP2sum * 100);
+    c.cDP2w = d2i((norm_fa_refbias(min_c23FA_w, refbias) * CDP2sum * 100));
     const double min_c23FA_x = dmin(aPFFA, c23FA);
-    c.cDP2x = 1 + (int32_t)(min_c23FA_x * CDP2sum * 100);
+    c.cDP2x = 1 + d2i((min_c23FA_x * CDP2sum * 100));
 }
 
 // indelpos_to_context (main.hpp:733-755): best short tandem repeat starting at reference index refidx of the tile's reference string
@@ -586,13 +603,13 @@ UVC_HD void calc_qual(CandFmt & c, const GroupFmt & g, const BatchView & v, cons
     const double pl_withUMI_phred_inc = par.powlaw_anyvar_base + (subst ? withUMI_bias_inc : par.bias_FA_powerlaw_withUMI_phred_inc_indel);
     const double prior_weight = 1.0 / (c.cDPmf + c.cDPmr + 1.0);
     const int32_t fam_thres_highBQ = (subst ? par.fam_thres_highBQ_snv : par.fam_thres_highBQ_indel);
-    const int32_t cMmQ = (int32_t)round(numstates2phred(v, (c.cDPMf + c.cDPmf + c.cDPMr + c.cDPmr + pow(10, fam_thres_highBQ / 10.0) * prior_weight) / (c.cDPmf + c.cDPmr + prior_weight)));
+    const int32_t cMmQ = d2i(round(numstates2phred(v, (c.cDPMf + c.cDPmf + c.cDPMr + c.cDPmr + pow(10, fam_thres_highBQ / 10.0) * prior_weight) / (c.cDPmf + c.cDPmr + prior_weight))));
     const int32_t nbases_x100_1 = c.bIADb * 100 + 1;
     const int32_t nbases_x100_2 = tmin(nbases_x100_1, c.cDP1v + 1);
     const int64_t perbase_q_x10_1 = 10 * c.bIAQb / tmax(1, c.bIADb);
-    const int64_t perbase_q_x10_2 = perbase_q_x10_1 + (int64_t)round(10 * numstates2phred(v, (double)nbases_x100_2 / (double)nbases_x100_1));
+    const int64_t perbase_q_x10_2 = perbase_q_x10_1 + d2l(round(10 * numstates2phred(v, (double)nbases_x100_2 / (double)nbases_x100_1)));
     int64_t duped_frag_binom_qual = ((isins || isdel) ? perbase_q_x10_1 : perbase_q_x10_2) * nbases_x100_2 / (10 * 100);
-    const int64_t contam_frag_withmin_qual = (int64_t)round(binom_10log10_likeratio(v, t2n_contam_frac, cDP0, CDP0 - cDP0)) + 9 - 3;
+    const int64_t contam_frag_withmin_qual = d2l(round(binom_10log10_likeratio(v, t2n_contam_frac, cDP0, CDP0 - cDP0))) + 9 - 3;
     const int32_t inc_snp = tmax(0, 2 * par.germ_phred_hetero_snp - par.germ_phred_het3al_snp - 0);
     const int32_t inc_indel = tmax(0, 2 * par.germ_phred_hetero_indel - par.germ_phred_het3al_indel - 0);
     int32_t phred_het3al_chance_inc = (subst ? inc_snp : inc_indel);
@@ -609,36 +626,36 @@ UVC_HD void calc_qual(CandFmt & c, const GroupFmt & g, const BatchView & v, cons
     const int64_t cIADmincnt = tmin(cIADnormcnt, (int64_t)(c.cDP2v + 1));
     const int64_t sscs_binom_qual_fw = c.cIAQf + ((int64_t)c.cIAQr * (int64_t)tmin(par.fam_phred_dscs_all - c.cIDQf, c.cIDQr)) / tmax(c.cIDQr, 1);
     const int64_t sscs_binom_qual_rv = c.cIAQr + ((int64_t)c.cIAQf * (int64_t)tmin(par.fam_phred_dscs_all - c.cIDQr, c.cIDQf)) / tmax(c.cIDQf, 1);
-    const int64_t contam_sscs_withmin_qual = (int64_t)round(binom_10log10_likeratio(v, t2n_contam_frac, cDP2, CDP2 - cDP2)) + 9 - 3;
+    const int64_t contam_sscs_withmin_qual = d2l(round(binom_10log10_likeratio(v, t2n_contam_frac, cDP2, CDP2 - cDP2))) + 9 - 3;
     const int64_t sscs_max = tmax(sscs_binom_qual_fw, sscs_binom_qual_rv);
     // non_neg_minus(int64, double) evaluated in double, then int64mul(double -> int64, cIADmincnt)
     const double sub_d = numstates2phred(v, cIADnormcnt / (double)cIADmincnt) * cIADnormcnt / 100.0;
     const double nnm_d = (((double)sscs_max > sub_d) ? ((double)sscs_max - sub_d) : 0);
-    int64_t sscs_binom_qual = ((int64_t)nnm_d * cIADmincnt) / (cIADnormcnt);
+    int64_t sscs_binom_qual = (d2l(nnm_d) * cIADmincnt) / (cIADnormcnt);
     if (sscs_max > par.microadjust_fam_binom_qual_halving_thres && subst) {
         sscs_binom_qual = tmin(sscs_binom_qual, (int64_t)(par.microadjust_fam_binom_qual_halving_thres + (sscs_max - par.microadjust_fam_binom_qual_halving_thres) / 2));
     }
     sscs_binom_qual -= sscs_dec1 + sscs_dec2;
     const double min_bcFA_v = (((double)(c.cDP1v) + 0.5) / (double)(CDP1sum * 100 + 1.0));
-    int32_t dedup_frag_powlaw_qual_v = (int32_t)round(par.powlaw_exponent * numstates2phred(v, min_bcFA_v) + (pl_noUMI_phred_inc));
+    int32_t dedup_frag_powlaw_qual_v = d2i(round(par.powlaw_exponent * numstates2phred(v, min_bcFA_v) + (pl_noUMI_phred_inc)));
     const double min_bcFA_w = (((double)(c.cDP1w) + 0.5) / (double)(CDP1sum * 100 + 1.0));
-    int32_t dedup_frag_powlaw_qual_w = (int32_t)round(par.powlaw_exponent * numstates2phred(v, min_bcFA_w) + (pl_noUMI_phred_inc) + tn_q_inc_max);
-    const int32_t ds_vq_inc_powlaw = (int32_t)round(10 / v.ln10 * dmin(log((c.cDP12f + 0.5) / (g.CDP12b[0] + 1.0)), log((c.cDP12r + 0.5) / (g.CDP12b[1] + 1.0)))) + (powlaw_sscs_phrederr);
+    int32_t dedup_frag_powlaw_qual_w = d2i(round(par.powlaw_exponent * numstates2phred(v, min_bcFA_w) + (pl_noUMI_phred_inc) + tn_q_inc_max));
+    const int32_t ds_vq_inc_powlaw = d2i(round(10 / v.ln10 * dmin(log((c.cDP12f + 0.5) / (g.CDP12b[0] + 1.0)), log((c.cDP12r + 0.5) / (g.CDP12b[1] + 1.0))))) + (powlaw_sscs_phrederr);
     const int32_t ds_vq_inc_binom = 3 * tmin(c.cDP2f, c.cDP2r);
     const int64_t m5 = tmin(tmin(sscs_binom_qual_fw, sscs_binom_qual_rv), tmin((int64_t)ds_vq_inc_powlaw, tmin((int64_t)ds_vq_inc_binom, (int64_t)3)));
     const int32_t powlaw_sscs_inc2 = (int32_t)(tmax((int64_t)0, m5) * ((cFA2 > 0.002) ? 1 : 0));
     const int32_t sscs_dec3 = ((cFA2 >= 0.003) ? 0 : 5);
     const int32_t sscs_base_2 = (int32_t)(pl_withUMI_phred_inc + powlaw_sscs_inc1 + powlaw_sscs_inc2 - sscs_dec1 - sscs_dec2 - sscs_dec3);
     const int32_t sscs_base_2tn = (int32_t)(pl_withUMI_phred_inc + powlaw_sscs_inc4tn + powlaw_sscs_inc2 - sscs_dec1 - sscs_dec2 - sscs_dec3);
-    int32_t sscs_powlaw_qual_v = (int32_t)round((par.powlaw_exponent * numstates2phred(v, umi_cFA) + sscs_base_2));
-    int32_t sscs_powlaw_qual_w = (int32_t)round((par.powlaw_exponent * numstates2phred(v, umi_cFA_w) + sscs_base_2tn));
+    int32_t sscs_powlaw_qual_v = d2i(round((par.powlaw_exponent * numstates2phred(v, umi_cFA) + sscs_base_2)));
+    int32_t sscs_powlaw_qual_w = d2i(round((par.powlaw_exponent * numstates2phred(v, umi_cFA_w) + sscs_base_2tn)));
     const double dFA = (double)(c.dDP2 + 0.5) / (double)(g.DDP1[0] + 1.0);
     const double dSNR = (double)(c.dDP2 + 0.5) / (double)(c.dDP1 + 1.0);
     const double dnormFA = dFA * pow(dSNR, 1.0 / par.powlaw_exponent);
-    const int64_t fam_phred_dscs_estimated = (int64_t)round((par.fam_phred_dscs_max + powlaw_sscs_phrederr) / 2.0);
-    const int64_t dFA_vq_binom = (fam_phred_dscs_estimated - (int64_t)round(numstates2phred(v, 1.0 / (dnormFA)))) * (int64_t)c.dDP2 * (int64_t)cIADmincnt / (int64_t)cIADnormcnt;
-    const int32_t dFA_vq_powlaw = (int32_t)(par.powlaw_anyvar_base + (fam_phred_dscs_estimated - par.fam_phred_pow_dscs_all_origin)
-            + (int32_t)round(numstates2phred(v, (dnormFA) * dmin(1.0, (double)((c.cDP1v) + 0.5) / (double)(CDP1sum * 100 + 1.0)))));
+    const int64_t fam_phred_dscs_estimated = d2l(round((par.fam_phred_dscs_max + powlaw_sscs_phrederr) / 2.0));
+    const int64_t dFA_vq_binom = (fam_phred_dscs_estimated - d2l(round(numstates2phred(v, 1.0 / (dnormFA))))) * (int64_t)c.dDP2 * (int64_t)cIADmincnt / (int64_t)cIADnormcnt;
+    const int32_t dFA_vq_powlaw = d2i((par.powlaw_anyvar_base + (fam_phred_dscs_estimated - par.fam_phred_pow_dscs_all_origin)
+            + d2i(round(numstates2phred(v, (dnormFA) * dmin(1.0, (double)((c.cDP1v) + 0.5) / (double)(CDP1sum * 100 + 1.0)))))));
     c.cMmQ = cMmQ;
     const double eps = (double)FLT_EPSILON;
     const int32_t indel_penal_base = 0;     // IonTorrent only
@@ -652,13 +669,13 @@ UVC_HD void calc_qual(CandFmt & c, const GroupFmt & g, const BatchView & v, cons
         double indelcdepth = (isins ? ins_cdepth : del_cdepth);
         int32_t indelcdepth_i = (isins ? ins_cdepth : del_cdepth);
         if (UVC_LINK_D1 == symbol) { indelcdepth_i += ins1_cdepth; }
-        if (UVC_LINK_I1 == symbol) { indelcdepth_i += (int32_t)(del1_cdepth / par.indel_del_to_ins_err_ratio); } // auto is int: += double truncates
+        if (UVC_LINK_I1 == symbol) { indelcdepth_i += d2i((del1_cdepth / par.indel_del_to_ins_err_ratio)); } // auto is int: += double truncates
         indelcdepth = indelcdepth_i;
         const int32_t nearInDelDP = (isins ? g.APDP[1] : g.APDP[2]);
-        const int32_t penal1 = (int32_t)round(par.indel_multiallele_samepos_penal / log(2.0) * log((double)(indelcdepth + eps) / (double)(c.cDP0a + eps)));
-        const int32_t penal2 = (int32_t)round(par.indel_multiallele_diffpos_penal / log(2.0) * log((double)(nearInDelDP + eps) / (double)(tmax(aDP, nearInDelDP) + eps)));
-        indel_penal4multialleles_g = (int32_t)((int32_t)round(par.indel_tetraallele_germline_penal_value / log(2.0) * log((double)(ins_cdepth + del_cdepth + eps) / (double)(c.cDP0a + eps)))
-                - par.indel_tetraallele_germline_penal_thres);
+        const int32_t penal1 = d2i(round(par.indel_multiallele_samepos_penal / log(2.0) * log((double)(indelcdepth + eps) / (double)(c.cDP0a + eps))));
+        const int32_t penal2 = d2i(round(par.indel_multiallele_diffpos_penal / log(2.0) * log((double)(nearInDelDP + eps) / (double)(tmax(aDP, nearInDelDP) + eps))));
+        indel_penal4multialleles_g = d2i((d2i(round(par.indel_tetraallele_germline_penal_value / log(2.0) * log((double)(ins_cdepth + del_cdepth + eps) / (double)(c.cDP0a + eps))))
+                - par.indel_tetraallele_germline_penal_thres));
         if (isins) {
             indel_penal4multialleles = (penal1 * par.indel_ins_penal_pseudocount / (int32_t)(par.indel_ins_penal_pseudocount + c.gap_len));
             indel_penal4multialleles_soma = indel_penal4multialleles;
@@ -666,21 +683,21 @@ UVC_HD void calc_qual(CandFmt & c, const GroupFmt & g, const BatchView & v, cons
             indel_penal4multialleles = tmax(penal1, penal2);
             indel_penal4multialleles_soma = penal1;
         }
-        dedup_frag_powlaw_qual_v += (int32_t)round(indel_ic);
-        dedup_frag_powlaw_qual_w += (int32_t)round(indel_ic);
-        duped_frag_binom_qual += (int64_t)round(indel_pq);
+        dedup_frag_powlaw_qual_v += d2i(round(indel_ic));
+        dedup_frag_powlaw_qual_w += d2i(round(indel_ic));
+        duped_frag_binom_qual += d2l(round(indel_pq));
         const uint32_t gl = (uint32_t)tmax(c.gap_len, 1);
         const double sscs_indel_ic = numstates2phred(v, (double)(gl * gl) / (double)(tmax(eff_tracklen1, eff_tracklen2) + 1));
-        const int32_t sscs_ins_vs_del_inc = (int32_t)round(par.powlaw_exponent * numstates2phred(v, par.indel_del_to_ins_err_ratio));
+        const int32_t sscs_ins_vs_del_inc = d2i(round(par.powlaw_exponent * numstates2phred(v, par.indel_del_to_ins_err_ratio)));
         const double rhs = sscs_indel_ic * (isins ? 0 : tmax(eff_tracklen1, eff_tracklen2)) / round(par.indel_polymerase_size);
-        const int32_t extra_reward = (int32_t)((((double)sscs_ins_vs_del_inc > rhs) ? ((double)sscs_ins_vs_del_inc - rhs) : 0) - sscs_ins_vs_del_inc / 2);
-        sscs_powlaw_qual_v += (int32_t)(round(sscs_indel_ic) + extra_reward);
-        sscs_powlaw_qual_w += (int32_t)(round(sscs_indel_ic) + extra_reward);
-        sscs_binom_qual += (int64_t)(round(indel_pq) + extra_reward);
+        const int32_t extra_reward = d2i(((((double)sscs_ins_vs_del_inc > rhs) ? ((double)sscs_ins_vs_del_inc - rhs) : 0) - sscs_ins_vs_del_inc / 2));
+        sscs_powlaw_qual_v += d2i((round(sscs_indel_ic) + extra_reward));
+        sscs_powlaw_qual_w += d2i((round(sscs_indel_ic) + extra_reward));
+        sscs_binom_qual += d2l((round(indel_pq) + extra_reward));
         if (c.enable_tier2) {
             const double lhs = (g.BDPb[0] + g.BDPb[1] + 1.0) / (double)(CDP1sum + 1.0) * par.fam_indel_nonUMI_phred_dec_per_fold_overseq;
             const double rr = (par.fam_thres_emperr_all_flat_indel + 1) * par.fam_indel_nonUMI_phred_dec_per_fold_overseq;
-            indel_UMI_penal = (int32_t)((lhs > rr) ? (lhs - rr) : 0);
+            indel_UMI_penal = d2i(((lhs > rr) ? (lhs - rr) : 0));
         }
     }
     c.aAaMQ = diffAaMQs;
@@ -702,8 +719,8 @@ UVC_HD void calc_qual(CandFmt & c, const GroupFmt & g, const BatchView & v, cons
             diffMQ2 = tmax(diffMQ2, 20 - tmin(c.bMQ, 20));
         }
     }
-    const int32_t sysMQ_base = (int32_t)((c.bMQ * (par.syserr_MQ_max - par.syserr_MQ_nonref_base) / par.syserr_MQ_max + par.syserr_MQ_nonref_base)) - (int32_t)(diffMQ2) - (int32_t)(c.bNMQ);
-    const int32_t sysMQ = (((refsymbol == symbol) && (ADP > aDP * 2)) ? c.bMQ : (sysMQ_base - (int32_t)(numstates2phred(v, (ADP + 1.0) / (aDP + 0.5)))));
+    const int32_t sysMQ_base = d2i(((c.bMQ * (par.syserr_MQ_max - par.syserr_MQ_nonref_base) / par.syserr_MQ_max + par.syserr_MQ_nonref_base))) - (int32_t)(diffMQ2) - (int32_t)(c.bNMQ);
+    const int32_t sysMQ = (((refsymbol == symbol) && (ADP > aDP * 2)) ? c.bMQ : (sysMQ_base - d2i((numstates2phred(v, (ADP + 1.0) / (aDP + 0.5))))));
     const bool is_nonWGS = implies_short_frag(g, par.lib_wgs_min_avg_fraglen);
     const int32_t normal_rescued_MQ = tmin(nnminus(readlenMQcap, 60), (is_nonWGS ? par.lib_nonwgs_normal_max_rescued_MQ : par.lib_wgs_normal_max_rescued_MQ));
     int32_t sysMQVQ1 = tmin((tmax(sysMQ, par.syserr_MQ_min) + sysMQVQadd), readlenMQcap);
@@ -746,14 +763,14 @@ UVC_HD void calc_qual(CandFmt & c, const GroupFmt & g, const BatchView & v, cons
     const int32_t penal4BQerr = (subst ? (5 + (int32_t)(((int64_t)par.penal4lowdep) / (dd * dd))) : 0);
     const int32_t indel_q_inc = (((!isins) && (!isdel)) ? 0 : units_phred(c.gap_len, repeatnum));
     c.gVQ1 = tmax(0, indel_q_inc + tmin(tmin(sysBQVQ, nnminus(sysMQVQ, sysMQVQminus)), tmin(c.bIAQ - penal4BQerr, c.cPLQ1))
-            - 2 * tmax(0, tmax((int32_t)(indel_penal4multialleles - par.indel_multiallele_soma_penal_thres), indel_penal4multialleles_g)));
+            - 2 * tmax(0, tmax(d2i((indel_penal4multialleles - par.indel_multiallele_soma_penal_thres)), indel_penal4multialleles_g)));
     const int32_t sysVQsomatic_minus = (15 - tmin(tmin(ADP * 15 / 100, aDP), 15));
     const int32_t sysVQsomatic = nnminus(tmin(sysBQVQ, sysMQVQ + sysMQVQadd_somatic), sysVQsomatic_minus);
     const int32_t bcVQ1 = tmin(tmin(sysVQsomatic, c.bIAQ - penal4BQerr), c.cPLQ1) - indel_penal4multialleles_soma;
     c.cVQ1 = tmax(0, tmin(bcVQ1, c.bTINQ) - indel_UMI_penal);
     int32_t mincVQ2 = 0;
     if (isins || isdel) {
-        const int32_t floor_v = (int32_t)(dmin(par.germ_phred_homalt_indel + numstates2phred(v, umi_cFA), (double)(c.cDP2v * 3 / 100)) + ((isins ? 1 : 0) - 1) * 3);
+        const int32_t floor_v = d2i((dmin(par.germ_phred_homalt_indel + numstates2phred(v, umi_cFA), (double)(c.cDP2v * 3 / 100)) + ((isins ? 1 : 0) - 1) * 3));
         mincVQ2 = tmax(mincVQ2, floor_v);
     }
     const int64_t dVQinc = tmin(tmin(dFA_vq_binom, (int64_t)dFA_vq_powlaw) - tmax(0, tmin(c.cIAQ, c.cPLQ2)), (int64_t)par.fam_phred_dscs_inc_max);
@@ -763,13 +780,13 @@ UVC_HD void calc_qual(CandFmt & c, const GroupFmt & g, const BatchView & v, cons
     // CONTQ uses this candidate's cDP1v and the group's CDP1v[0]
     const double binom_contam = binom_10log10_likeratio(v, contamfrac, c.cDP1v, g.CDP1v[0]);
     const double power_contam = round(10.0 / v.ln10 * par.powlaw_exponent * dmax(logit2((c.cDP1v + 1) / (double)(g.CDP1v[0] + 1), contamfrac), 0.0));
-    c.CONTQ = (int32_t)dmin(binom_contam, power_contam);
+    c.CONTQ = d2i(dmin(binom_contam, power_contam));
 }
 
 // hetLODQ (main.hpp:5457-5462)
 UVC_HD int32_t het_lodq(const BatchView & v, double a1, double a2, double expfrac, double pl_exponent) {
-    const int32_t binomLODQ = (int32_t)binom_10log10_likeratio(v, expfrac, a1, a2);
-    const int32_t powerLODQ = (int32_t)round(10.0 / v.ln10 * pl_exponent * dmax(logit2((a1 + 0.5) * 0.5 / expfrac, (a2 + 0.5) * 0.5 / (1.0 - expfrac)), 0.0));
+    const int32_t binomLODQ = d2i(binom_10log10_likeratio(v, expfrac, a1, a2));
+    const int32_t powerLODQ = d2i(round(10.0 / v.ln10 * pl_exponent * dmax(logit2((a1 + 0.5) * 0.5 / expfrac, (a2 + 0.5) * 0.5 / (1.0 - expfrac)), 0.0)));
     return tmin(binomLODQ, powerLODQ);
 }
 
@@ -845,13 +862,13 @@ UVC_HD int32_t germline_nlodq(const BatchView & v, const CandFmt *cands, int n, 
 // calc_binom_powlaw_syserr_normv_quals (main.hpp:5982-6010)
 UVC_HD void tn_quals(int32_t out[4], const BatchView & v, double tAD, double tDP, int32_t tVQ, int32_t tnVQcap, double nAD, double nDP, int32_t nVQ,
         double penal_dimret_coef, int32_t prior_phred, int32_t tn_dec_by_xm, double pl_exponent) {
-    const int32_t binom = (int32_t)binom_10log10_likeratio(v, (tDP - tAD) / (tDP), nDP - nAD, nAD);
+    const int32_t binom = d2i(binom_10log10_likeratio(v, (tDP - tAD) / (tDP), nDP - nAD, nAD));
     const double nADplus = nAD * dmin(dmax(nDP / tDP - 1.0, 0), 1);
     const double bjpfrac = ((tAD + 0.5) / (tDP + 1.0)) / ((nAD + 0.5 + nADplus) / (nDP + 1.0 + nADplus));
-    const int32_t powlaw = (int32_t)round(pl_exponent * numstates2phred(v, bjpfrac));
-    const int32_t tnVQinc = tmax(-prior_phred, tmax((-(int32_t)nAD) * 3, tmin(binom - prior_phred, powlaw - prior_phred)));
+    const int32_t powlaw = d2i(round(pl_exponent * numstates2phred(v, bjpfrac)));
+    const int32_t tnVQinc = tmax(-prior_phred, tmax((-d2i(nAD)) * 3, tmin(binom - prior_phred, powlaw - prior_phred)));
     const double lg = log(dmax(bjpfrac, 1.001)) / log(2.0);
-    int32_t tnVQdec = tmax(0, nVQ - tmax(0, tmin(binom - prior_phred, (int32_t)((lg * lg) * penal_dimret_coef))));
+    int32_t tnVQdec = tmax(0, nVQ - tmax(0, tmin(binom - prior_phred, d2i(((lg * lg) * penal_dimret_coef)))));
     tnVQdec = tmax(tnVQdec, tmin(nVQ + 9, tn_dec_by_xm));
     const int32_t tnVQ = tmin(tnVQcap, tVQ + tnVQinc) - tnVQdec;
     out[0] = binom; out[1] = powlaw; out[2] = tnVQdec; out[3] = tnVQ;
@@ -1113,7 +1130,7 @@ UVC_HD void k6_gvcf_position(const BatchView & v, const ScoreView & sv, int64_t 
         const double nonref_like_binom = -binom_10log10_likeratio(v, par.germ_hetero_FA, ref_cdepth + 0.5, c + 1.0);
         const double nonref_like_powlaw = -dmax(0, par.powlaw_exponent * (10 / v.ln10) * logit2((ref_cdepth + 0.5) / (c + 1.0), par.germ_hetero_FA));
         o.bdepth[k] = b; o.cdepth[k] = c; o.cdep12[k] = c12;
-        o.refQ[k] = par.germ_phred_hetero_snp + (int32_t)round(dmax(ref_like_binom, ref_like_powlaw) - (int32_t)round(dmax(nonref_like_binom, nonref_like_powlaw)));
+        o.refQ[k] = par.germ_phred_hetero_snp + d2i(round(dmax(ref_like_binom, ref_like_powlaw) - d2i(round(dmax(nonref_like_binom, nonref_like_powlaw)))));
     }
     int32_t unit = 0, num = 0;
     repeat_at(unit, num, v, T, off);
