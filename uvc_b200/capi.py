@@ -87,6 +87,7 @@ def load_gpu(emulate: bool = False) -> C.CDLL:
     if emulate in _gpu_libs:
         return _gpu_libs[emulate]
     path = (os.path.join(ROOT, "tests", "emu", "libuvcgpu_emu.so") if emulate else os.path.join(LIBDIR, "libuvcgpu.so"))
+    path = os.environ.get("UVCGPU_EMU_LIB" if emulate else "UVCGPU_LIB", path)   # developer override of the library file (debug builds)
     if not os.path.exists(path):
         raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)" % path)
     lib = C.CDLL(path)

@@ -848,15 +848,17 @@ UVC_HD int32_t germline_nlodq(const BatchView & v, const CandFmt *cands, int n, 
         const int32_t n1 = nunits[symb1], n2 = nunits[symb2];
         if (n1 != 0 && n2 != 0) { tri_al_penal -= between(iabs(n1 - n2) * 3 - 5, 0, 9); }
     }
+    // Genotype log-likelihoods GL4raw (main.hpp:5601-5607). The three alternative ones are kept NEGATED (n_k = -GL_k) and reduced with a minimum:
+    // ptxas 12.9 for sm_100a drops the sign of one operand when it fuses max(-x, -y, -z) into VIMNMX3 (found with the parity tests).
     const int32_t gl0 = (-phred_homref - a1 - a2penal - a3penal);
-    const int32_t gl1 = (-phred_hetero - tmax(a01hetp, a2) - tmax(tmin(a01hetp, a2) - phred_hetero, 0) - a3penal);
-    const int32_t gl2 = (-phred_homalt - tmax(a0, a2) - tmax(tmin(a0, a2) - phred_hetero, 0) - a3penal);
-    const int32_t gl3 = (-phred_tri_al - tmax(a12hetp, a03trip) - tmax(tmin(a12hetp, a03trip) - phred_hetero, 0) - tmax(tmin(a12hetp, tmin(a0, a3)) - phred_hetero, 0) - tri_al_penal);
+    const int32_t n1 = (phred_hetero + tmax(a01hetp, a2) + tmax(tmin(a01hetp, a2) - phred_hetero, 0) + a3penal);
+    const int32_t n2 = (phred_homalt + tmax(a0, a2) + tmax(tmin(a0, a2) - phred_hetero, 0) + a3penal);
+    const int32_t n3 = (phred_tri_al + tmax(a12hetp, a03trip) + tmax(tmin(a12hetp, a03trip) - phred_hetero, 0) + tmax(tmin(a12hetp, tmin(a0, a3)) - phred_hetero, 0) + tri_al_penal);
     #undef UVC_G
     #undef UVC_SYM
     #undef UVC_V
     (void)type;
-    return gl0 - tmax(gl1, tmax(gl2, gl3));
+    return gl0 + tmin(n1, tmin(n2, n3));
 }
 
 // calc_binom_powlaw_syserr_normv_quals (main.hpp:5982-6010)

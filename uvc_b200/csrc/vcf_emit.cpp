@@ -8,6 +8,7 @@
 #include <tuple>
 
 #include <limits.h>
+#include <math.h>
 #include <stdio.h>
 
 namespace {
@@ -273,7 +274,10 @@ std::string uvc_tile_vcf_text(const HostBatch & hb, int32_t tile_index, const uv
                     else { vcfpos = refpos; vcfref = (regionpos > 0 ? refstring.substr(regionpos - 1, 1) : "n"); }
                     vcfalt = SYMBOL_DESC[symbol];
                 }
-                const float vq = r.vcfqual;
+                // QUAL (main.hpp:6206): calc_non_negative<float> is re-evaluated here with the host libm from the device's integers, so that the
+                // printed value does not depend on the last bit of the device's powf/log1pf (the keep decision on the device only compares with vqual)
+                float vq = ((float)r.tlodq > r.lowestVAQ ? (float)r.tlodq : r.lowestVAQ);
+                if (vq < 10.0f) { const float base = (float)pow(10.0, 0.1); vq = log1pf(powf(base, vq)) / logf(base); }
                 const char *filter = (vq < 10 ? "Q10" : (vq < 20 ? "Q20" : (vq < 30 ? "Q30" : (vq < 40 ? "Q40" : (vq < 50 ? "Q50" : (vq < 60 ? "Q60" : "PASS"))))));
                 // t2AD of an indel allele: sum of gc2dAD over the entries with this sequence (indelstring_gapSeq_gapAD_to_AD, main.hpp:5930-5939)
                 int32_t t2AD1 = r.t2AD[1];
