@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define UVCGPU_ABI_VERSION 3
+#define UVCGPU_ABI_VERSION 4
 
 enum uvcgpu_error {
     UVCGPU_OK = 0,
@@ -283,6 +283,13 @@ const char *uvcgpu_last_error(const uvcgpu_ctx *ctx);
  * bases = ASCII, any case; NULL means "reference not available" (all 'n', main.cpp:57-59). */
 int uvcgpu_set_contig(uvcgpu_ctx *ctx, int32_t tid, const char *bases, int64_t len);
 
+/* Drops the bases of a contig that no later tile needs (the uvc1 host walks the genome in order). */
+int uvcgpu_unset_contig(uvcgpu_ctx *ctx, int32_t tid);
+
+/* Number of host threads the context may use for staging (stage P0/P1 of uvcgpu_submit) and for VCF text (uvcgpu_tile_vcf); 0 = all cores.
+ * Replaces the reference's -t for these two stages (main.cpp:1479: one OpenMP thread per tier-2 region). */
+int uvcgpu_set_host_threads(uvcgpu_ctx *ctx, int32_t n_threads);
+
 /* Name of the contig as it is printed in the CHROM column (bam_hdr->target_name[tid], main.cpp:1462). */
 int uvcgpu_set_contig_name(uvcgpu_ctx *ctx, int32_t tid, const char *name);
 
@@ -290,6 +297,11 @@ int uvcgpu_set_contig_name(uvcgpu_ctx *ctx, int32_t tid, const char *name);
  * grouping.cpp:608-997 read filter + family grouping, :459-567 BQ fix-ups, main.hpp:803-874 repeat context,
  * main.cpp:400-429 BAQ offsets, main.hpp:3665-3742 updateByRegion3Aln). Asynchronous on the context's stream. */
 int uvcgpu_submit(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, const uvcgpu_reads_soa *reads, uvcgpu_ticket *ticket);
+
+/* Same as uvcgpu_submit, but the records of the tiles come from several SoA buffers (the uvc1 host decodes the tiles of a batch on several
+ * threads, each into its own buffer): tile k's [read_begin, read_end) indexes sources[tile_source[k]]. */
+int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, int32_t n_sources, const uvcgpu_reads_soa *sources,
+                        const int32_t *tile_source, uvcgpu_ticket *ticket);
 
 /* Waits for the batch; fills stats. */
 int uvcgpu_collect(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, uvcgpu_batch_stats *stats);

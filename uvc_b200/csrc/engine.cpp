@@ -44,7 +44,10 @@ struct BatchState {
     BatchView view;                       // pointers valid on the compute side (device or, in the emulation, host)
     std::vector<void*> allocs;            // compute-side allocations
     std::vector<std::pair<void*, size_t>> alloc_sizes;
-    uvcgpu_reads_soa reads;               // caller's SoA (borrowed until release)
+    std::vector<uvcgpu_reads_soa> sources; // caller's SoA buffers (borrowed until release)
+    std::vector<int32_t> tile_source;
+    std::vector<std::string> vcf_text;     // per-tile VCF body, formatted once on all host threads
+    bool vcf_built = false;
     uvcgpu_batch_stats stats;
     bool collected = false;
     bool sparse_built = false;
@@ -72,6 +75,7 @@ struct uvcgpu_ctx {
     std::map<uvcgpu_ticket, std::unique_ptr<BatchState>> batches;
     uvcgpu_ticket next_ticket = 1;
     std::vector<int32_t> slip_tab;
+    int host_threads = 0;
 #if UVC_CUDA
     cudaStream_t stream = nullptr;
 #endif
@@ -392,6 +396,18 @@ int uvcgpu_set_contig(uvcgpu_ctx *ctx, int32_t tid, const char *bases, int64_t l
     return UVCGPU_OK;
 }
 
+int uvcgpu_unset_contig(uvcgpu_ctx *ctx, int32_t tid) {
+    if (NULL == ctx) { return UVCGPU_EINVAL; }
+    ctx->contigs.erase(tid);
+    return UVCGPU_OK;
+}
+
+int uvcgpu_set_host_threads(uvcgpu_ctx *ctx, int32_t n_threads) {
+    if (NULL == ctx || n_threads < 0) { return UVCGPU_EINVAL; }
+    ctx->host_threads = n_threads;
+    return UVCGPU_OK;
+}
+
 int uvcgpu_set_contig_name(uvcgpu_ctx *ctx, int32_t tid, const char *name) {
     if (NULL == ctx || tid < 0 || NULL == name) { return UVCGPU_EINVAL; }
     ctx->contig_names[tid] = name;
@@ -401,13 +417,25 @@ int uvcgpu_set_contig_name(uvcgpu_ctx *ctx, int32_t tid, const char *name) {
 #define UVC_TRY(expr) { int rc_ = (expr); if (rc_ != 0) { backend_free(*bs); return rc_; } }
 
 int uvcgpu_submit(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, const uvcgpu_reads_soa *reads, uvcgpu_ticket *ticket) {
-    if (NULL == ctx || NULL == tiles || NULL == reads || NULL == ticket || n_tiles <= 0) { return UVCGPU_EINVAL; }
+    return uvcgpu_submit_multi(ctx, n_tiles, tiles, 1, reads, NULL, ticket);
+}
+
+int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, int32_t n_sources, const uvcgpu_reads_soa *sources,
+        const int32_t *tile_source, uvcgpu_ticket *ticket) {
+    if (NULL == ctx || NULL == tiles || NULL == sources || NULL == ticket || n_tiles <= 0 || n_sources <= 0) { return UVCGPU_EINVAL; }
     std::unique_ptr<BatchState> bs(new BatchState());
     memset(&bs->stats, 0, sizeof(bs->stats));
-    bs->reads = *reads;
+    bs->sources.assign(sources, sources + n_sources);
+    bs->tile_source.assign((size_t)n_tiles, 0);
+    if (tile_source) {
+        for (int32_t k = 0; k < n_tiles; k++) {
+            if (tile_source[k] < 0 || tile_source[k] >= n_sources) { ctx->err = "tile_source out of range"; return UVCGPU_EINVAL; }
+            bs->tile_source[(size_t)k] = tile_source[k];
+        }
+    }
     const double t0 = now_ms();
     std::string msg;
-    int rc = uvc_build_host_batch(bs->hb, ctx->par, ctx->contigs, n_tiles, tiles, *reads, msg);
+    int rc = uvc_build_host_batch(bs->hb, ctx->par, ctx->contigs, n_tiles, tiles, bs->sources.data(), bs->tile_source.data(), ctx->host_threads, msg);
     if (rc != 0) { ctx->err = msg; return rc; }
     const double t1 = now_ms();
     HostBatch & hb = bs->hb;
@@ -568,14 +596,33 @@ int uvcgpu_score(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, uvcgpu_batch_stats *stat
     return UVCGPU_OK;
 }
 
-static int tile_vcf_text(uvcgpu_ctx *ctx, BatchState & bs, int32_t tile_index, std::string & out) {
+// VCF body of every tile of the batch, formatted once on the context's host threads (tiles are independent)
+static int ensure_vcf_text(uvcgpu_ctx *ctx, BatchState & bs) {
+    if (bs.vcf_built) { return 0; }
     int rc = ensure_scored(ctx, bs);
     if (rc != 0) { return rc; }
-    const TileInfo & T = bs.hb.tiles[tile_index];
-    auto nm = ctx->contig_names.find(T.tid);
-    const std::string tname = (nm == ctx->contig_names.end() ? std::to_string(T.tid) : nm->second);
-    out = uvc_tile_vcf_text(bs.hb, tile_index, ctx->par, tname, ctx->contigs.at(T.tid), bs.recs_by_tile[tile_index], bs.sites[tile_index],
-            bs.sparse[tile_index], bs.ev_host, bs.gvcf.data(), bs.gextra.data());
+    const int32_t n_tiles = (int32_t)bs.hb.tiles.size();
+    bs.vcf_text.assign((size_t)n_tiles, std::string());
+    for (int32_t ti = 0; ti < n_tiles; ti++) {
+        const TileInfo & T = bs.hb.tiles[ti];
+        if (!T.skipped && ctx->contigs.find(T.tid) == ctx->contigs.end()) { ctx->err = "contig of a tile was unset before its VCF text was requested"; return UVCGPU_EINVAL; }
+    }
+    uvc_parallel_for(n_tiles, ctx->host_threads, [&](int32_t ti) {
+        const TileInfo & T = bs.hb.tiles[ti];
+        if (T.skipped) { return; }
+        auto nm = ctx->contig_names.find(T.tid);
+        const std::string tname = (nm == ctx->contig_names.end() ? std::to_string(T.tid) : nm->second);
+        bs.vcf_text[ti] = uvc_tile_vcf_text(bs.hb, ti, ctx->par, tname, ctx->contigs.at(T.tid), bs.recs_by_tile[ti], bs.sites[ti],
+                bs.sparse[ti], bs.ev_host, bs.gvcf.data(), bs.gextra.data());
+    });
+    bs.vcf_built = true;
+    return 0;
+}
+
+static int tile_vcf_text(uvcgpu_ctx *ctx, BatchState & bs, int32_t tile_index, std::string & out) {
+    int rc = ensure_vcf_text(ctx, bs);
+    if (rc != 0) { return rc; }
+    out = bs.vcf_text[tile_index];
     return 0;
 }
 
@@ -632,7 +679,7 @@ int uvcgpu_dump_counters(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_ind
             host_side = true; break;
         }
         case UVCGPU_SEC_FAMILIES: {
-            const std::string s = uvc_families_text(bs.hb, tile_index, bs.reads);
+            const std::string s = uvc_families_text(bs.hb, tile_index, bs.sources[(size_t)bs.tile_source[(size_t)tile_index]]);
             tmp.assign(s.begin(), s.end());
             host_side = true; break;
         }

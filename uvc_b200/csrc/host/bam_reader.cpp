@@ -4,6 +4,7 @@
 
 #include <zlib.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -308,6 +309,67 @@ int uvchost_bam_scan(uvchost_bam *b, uvchost_scan_cb cb, void *user) {
         if (0 == r) { break; }
         if (cb(c.tid, c.pos, c.endpos, (uint16_t)c.flag, c.isize, c.l_qseq, (uint8_t)c.mapq, user)) { break; }
     }
+    return 0;
+}
+
+int uvchost_bam_rewind(uvchost_bam *b) { return b->in.seek(b->first_record_voff); }
+
+int uvchost_bam_next_core(uvchost_bam *b, uvchost_core *out) {
+    Core c;
+    const int r = next_record(b, c);
+    if (r <= 0) { return r; }
+    out->tid = c.tid; out->pos = c.pos; out->endpos = c.endpos; out->isize = c.isize; out->l_qseq = c.l_qseq; out->flag = (uint16_t)c.flag; out->mapq = (uint8_t)c.mapq;
+    return 1;
+}
+
+int uvchost_bam_seek_region(uvchost_bam *b, int32_t tid, int64_t beg) {
+    if (beg < 0) { beg = 0; }
+    if (tid < 0 || (size_t)tid >= b->lidx.size()) { return 1; }
+    const std::vector<uint64_t> & l = b->lidx[tid];
+    size_t w = (size_t)(beg >> 14);
+    while (w < l.size() && 0 == l[w]) { w++; }
+    if (w >= l.size()) { return 1; }
+    return (b->in.seek((int64_t)l[w]) != 0 ? -1 : 0);
+}
+
+int64_t uvchost_bam_count(uvchost_bam *b, int32_t tid, int64_t beg, int64_t end) {
+    if (uvchost_bam_seek_region(b, tid, beg) != 0) { return 0; }
+    int64_t n = 0;
+    Core c;
+    for (;;) {
+        const int r = next_record(b, c);
+        if (r <= 0) { break; }
+        if (c.tid != tid || c.pos >= end) {
+            if (c.tid >= 0 && c.tid < tid) { continue; }
+            break;
+        }
+        if (c.endpos > beg) { n++; }
+    }
+    return n;
+}
+
+int uvchost_bam_infer(uvchost_bam *b, int64_t max_records, uvchost_infer_stats *out) {
+    memset(out, 0, sizeof(*out));
+    if (b->in.seek(b->first_record_voff) != 0) { return -1; }
+    std::vector<int32_t> qlens;
+    qlens.push_back(150);
+    Core c;
+    while ((out->count_pe + out->count_se) < max_records) {
+        const int r = next_record(b, c);
+        if (r < 0) { return -1; }
+        if (0 == r) { break; }
+        if (c.mapq > out->max_mapq) { out->max_mapq = c.mapq; }
+        if (c.flag & 0x1) { out->count_pe++; } else { out->count_se++; }
+        qlens.push_back(c.l_qseq);
+        const uint8_t *ql = b->rec.data() + 32 + c.l_qname + 4 * (size_t)c.n_cigar + (size_t)((c.l_qseq + 1) / 2);
+        for (int32_t i = 0; i < c.l_qseq; i++) {
+            if (ql[i] < 30) { out->q30_n_fail_bases++; } else { out->q30_n_pass_bases++; }
+            if (ql[i] < 20) { out->q20_n_fail_bases++; }
+        }
+    }
+    std::sort(qlens.begin(), qlens.end());
+    out->median_qlen = qlens[qlens.size() / 2];
+    out->max_qlen = qlens.back();
     return 0;
 }
 

@@ -39,6 +39,24 @@ int64_t uvchost_bam_fetch(uvchost_bam *b, int32_t tid, int64_t beg, int64_t end,
 typedef int (*uvchost_scan_cb)(int32_t tid, int32_t pos, int32_t endpos, uint16_t flag, int32_t isize, int32_t l_qseq, uint8_t mapq, void *user);
 int uvchost_bam_scan(uvchost_bam *b, uvchost_scan_cb cb, void *user);
 
+/* Resumable sequential reader of core fields (used by the region tiler, tiler.h): rewind to the first record, then pull records one by one.
+ * next returns 1 and fills *c, 0 at end of file (*c untouched, like htslib's sam_read1), negative on error. */
+typedef struct uvchost_core { int32_t tid, pos, endpos, isize, l_qseq; uint16_t flag; uint8_t mapq; } uvchost_core;
+int uvchost_bam_rewind(uvchost_bam *b);
+int uvchost_bam_next_core(uvchost_bam *b, uvchost_core *c);
+/* Positions the sequential reader at the first record that can overlap [beg, end) of tid (sam_itr_queryi); records are then pulled with
+ * uvchost_bam_next_core and filtered by the caller. Returns 0, or 1 if the index has no data for the region. */
+int uvchost_bam_seek_region(uvchost_bam *b, int32_t tid, int64_t beg);
+/* Number of records of tid that overlap [beg, end) (the count SamIter::iternext takes per BED line, grouping.cpp:178-195). */
+int64_t uvchost_bam_count(uvchost_bam *b, int32_t tid, int64_t beg, int64_t end);
+
+/* Statistics of the first max_records records, as CommandLineArgs::selfUpdateByPlatform gathers them (CmdLineArgs.cpp:36-108). */
+typedef struct uvchost_infer_stats {
+    int64_t count_pe, count_se, q20_n_fail_bases, q30_n_fail_bases, q30_n_pass_bases;
+    int32_t max_mapq, median_qlen, max_qlen;   /* median/max over {150} + the records' l_qseq */
+} uvchost_infer_stats;
+int uvchost_bam_infer(uvchost_bam *b, int64_t max_records, uvchost_infer_stats *out);
+
 uvchost_fasta *uvchost_fasta_open(const char *path);      /* needs <path>.fai */
 void uvchost_fasta_close(uvchost_fasta *f);
 /* Returns a malloc'ed buffer with the whole sequence of the named contig (caller frees), length in *len; NULL if absent. */

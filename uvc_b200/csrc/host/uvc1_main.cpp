@@ -1,0 +1,452 @@
+// uvc1_main.cpp - the uvc1 command line on B200: same positional argument, options, per-region batching and block-gzipped VCF output as
+// the reference's main() (main.cpp:1219-1602), with process_batch (main.cpp:458-1193) replaced by the C ABI of include/uvcgpu.h.
+//
+//   tiler thread      : tier-3 tile list, bit-identical to SamIter::iternext for the same -t / --mem-per-thread (tiler.h)
+//   lanes (>= 1 / GPU): each lane owns a uvcgpu context (one CUDA stream) and BAM/FASTA handles; it takes the next batch of consecutive tiles,
+//                       decodes the tiles' fetch windows on its decode threads, submits, collects, scores, formats and block-compresses.
+//                       Several lanes per GPU overlap host staging / text formatting of one batch with the kernels of another.
+//   writer            : concatenates the compressed batches in tile order, so the output is identical for any number of GPUs or lanes
+//                       (main.cpp:1541-1551 semantics).
+// Genomic regions are independent, so GPUs never exchange data: no collective is used.
+#include "../../../include/uvcgpu.h"
+#include "bam_reader.h"
+#include "bgzf_writer.h"
+#include "tiler.h"
+#include "vcf_header.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <fstream>
+#include <map>
+#include <mutex>
+#include <set>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <stddef.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "params_table.inc"
+
+#define UVC_B200_VERSION "uvc-b200 0.1 (drop-in for the pileup-and-score path of UVC 0.15.1)"
+
+namespace {
+
+struct Options {
+    std::string bam, fasta = "NA", out = "-", sample = "-", bed, targets, bed_out;
+    int threads = 8;               // reference default (CmdLineArgs.hpp:33)
+    int64_t mem_per_thread = 1536; // CmdLineArgs.hpp:34
+    int64_t bed_in_avg_sequencing_DP = -1;
+    int gpus = 0;                  // 0 = all visible
+    int lanes_per_gpu = 0;         // 0 = automatic
+    int64_t batch_positions = 320 * 1000, batch_reads = 1500 * 1000;
+    int compress_level = 5;
+    bool stats = false;
+};
+
+struct Batch {
+    int64_t seq = -1;
+    std::vector<uvchost_bedline> tiles, prevs;
+};
+
+template <class T> class Channel {
+public:
+    explicit Channel(size_t cap) : cap_(cap) {}
+    void push(T && v) {
+        std::unique_lock<std::mutex> lk(m_);
+        not_full_.wait(lk, [&]() { return q_.size() < cap_ || aborted_; });
+        q_.push_back(std::move(v));
+        not_empty_.notify_one();
+    }
+    bool pop(T & v) {
+        std::unique_lock<std::mutex> lk(m_);
+        not_empty_.wait(lk, [&]() { return !q_.empty() || closed_ || aborted_; });
+        if (aborted_ || q_.empty()) { return false; }
+        v = std::move(q_.front());
+        q_.pop_front();
+        not_full_.notify_one();
+        return true;
+    }
+    void close() { std::lock_guard<std::mutex> lk(m_); closed_ = true; not_empty_.notify_all(); }
+    void abort() { std::lock_guard<std::mutex> lk(m_); aborted_ = true; not_empty_.notify_all(); not_full_.notify_all(); }
+private:
+    std::mutex m_;
+    std::condition_variable not_full_, not_empty_;
+    std::deque<T> q_;
+    size_t cap_;
+    bool closed_ = false, aborted_ = false;
+};
+
+struct Shared {
+    Options opt;
+    uvcgpu_params par;
+    std::vector<std::pair<std::string, int64_t>> contigs;
+    Channel<Batch> batches{8};
+    std::mutex out_mutex;
+    std::condition_variable out_cv;
+    std::map<int64_t, std::string> done;     // seq -> bytes to write
+    std::atomic<int> failed{0};
+    std::string fail_msg;
+    std::mutex fail_mutex;
+    // totals
+    std::atomic<int64_t> n_reads_kept{0}, n_positions{0}, n_records{0}, n_batches{0}, n_launches{0};
+    std::atomic<int64_t> us_fetch{0}, us_prep{0}, us_gpu_wait{0}, us_score{0}, us_text{0}, us_compress{0};
+    std::mutex kernel_ms_mutex;
+    double kernel_ms = 0;
+    void fail(const std::string & msg) {
+        std::lock_guard<std::mutex> lk(fail_mutex);
+        if (!failed.exchange(1)) { fail_msg = msg; }
+        batches.abort();
+        out_cv.notify_all();
+    }
+};
+
+int64_t now_us() { return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+void usage(const char *prog) {
+    fprintf(stderr,
+        "%s\nusage: %s <inputBAM> -f <ref.fa|NA> -o <out.vcf.gz|-> [-t threads] [-s sample] [-R regions.bed] [--targets chr:beg-end,...]\n"
+        "        [-q vqual] [-A] [--outvar-flag N] [--mem-per-thread MB] [--bed-out-fname f] [--gpus N] [--lanes-per-gpu N]\n"
+        "        [--gpu-batch-positions N] [--gpu-batch-reads N] [--<parameter-name> value ...]\n"
+        "  <inputBAM> must be coordinate-sorted with <inputBAM>.bai next to it; <ref.fa> needs <ref.fa>.fai.\n"
+        "  Every numeric field of uvcgpu_params (include/uvcgpu.h) is an option named like the reference's, e.g. --fam-thres-dup1add 2.\n",
+        UVC_B200_VERSION, prog);
+}
+
+bool file_exists(const std::string & f) { std::ifstream s(f.c_str()); return (bool)s; }
+
+// returns 0, or an exit code
+int parse_args(Options & o, uvcgpu_params & par, int argc, char **argv) {
+    bool have_bam = false;
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        auto need = [&](const char *name) -> const char* { if (i + 1 >= argc) { fprintf(stderr, "option %s needs a value\n", name); exit(109); } return argv[++i]; };
+        if (a == "-h" || a == "--help") { usage(argv[0]); exit(0); }
+        else if (a == "-v" || a == "--version") { printf("%s\n", UVC_B200_VERSION); exit(0); }
+        else if (a == "-f" || a == "--fasta") { o.fasta = need("-f"); }
+        else if (a == "-o" || a == "--output") { o.out = need("-o"); }
+        else if (a == "-R" || a == "--regions-file" || a == "--bed-in-fname") { o.bed = need("-R"); }
+        else if (a == "--targets") { o.targets = need("--targets"); }
+        else if (a == "-s" || a == "--sample") { o.sample = need("-s"); }
+        else if (a == "-t" || a == "--threads") { o.threads = atoi(need("-t")); }
+        else if (a == "--mem-per-thread") { o.mem_per_thread = atoll(need(a.c_str())); }
+        else if (a == "--bed-out-fname") { o.bed_out = need(a.c_str()); }
+        else if (a == "--bed-in-avg-sequencing-DP") { o.bed_in_avg_sequencing_DP = atoll(need(a.c_str())); }
+        else if (a == "-A" || a == "--all-out") { par.should_output_all = 1; }
+        else if (a == "--all-germline-out") { par.should_output_all_germline = 1; }
+        else if (a == "-q") { par.vqual = atof(need("-q")); }
+        else if (a == "--gpus") { o.gpus = atoi(need(a.c_str())); }
+        else if (a == "--lanes-per-gpu") { o.lanes_per_gpu = atoi(need(a.c_str())); }
+        else if (a == "--gpu-batch-positions") { o.batch_positions = atoll(need(a.c_str())); }
+        else if (a == "--gpu-batch-reads") { o.batch_reads = atoll(need(a.c_str())); }
+        else if (a == "--compress-level") { o.compress_level = atoi(need(a.c_str())); }
+        else if (a == "--stats") { o.stats = true; }
+        else if (a == "--tumor-vcf") { fprintf(stderr, "--tumor-vcf (the normal pass of a tumor-normal pair) is not implemented in this build\n"); return 105; }
+        else if (a == "--fam-consensus-out-fastq") { fprintf(stderr, "--fam-consensus-out-fastq is not implemented in this build\n"); return 105; }
+        else if (a.size() > 2 && a[0] == '-' && a[1] == '-') {
+            bool found = false;
+            for (const auto & e : UVC_PARAM_OPTS) {
+                if (a == e.opt) {
+                    const char *v = need(e.opt);
+                    char *base = (char*)&par + e.off;
+                    if (e.type == 'i') { *(int32_t*)base = (int32_t)strtol(v, NULL, 0); } else if (e.type == 'u') { *(uint32_t*)base = (uint32_t)strtoul(v, NULL, 0); } else { *(double*)base = atof(v); }
+                    found = true;
+                    break;
+                }
+            }
+            if (!found) { fprintf(stderr, "unknown option %s\n", a.c_str()); return 109; }
+        }
+        else if (a.size() > 1 && a[0] == '-') { fprintf(stderr, "unknown option %s\n", a.c_str()); return 109; }
+        else if (!have_bam) { o.bam = a; have_bam = true; }
+        else { fprintf(stderr, "unexpected argument %s\n", a.c_str()); return 109; }
+    }
+    if (!have_bam) { usage(argv[0]); return 106; }
+    return 0;
+}
+
+// The reference's tier-2 split of one tier-1 iteration (main.cpp:1372-1399): only used to print the same --bed-out-fname columns.
+std::string bed_out_text(const std::vector<uvchost_bedline> & lines, const std::vector<std::pair<std::string, int64_t>> & contigs, int nthreads, int64_t tier1_idx) {
+    int64_t nreads = 0, npositions = 0;
+    for (const auto & l : lines) { nreads += l.n_reads; npositions += l.end_pos - l.beg_pos; }
+    std::vector<std::pair<size_t, size_t>> pairs;
+    int32_t last_tid = (lines.empty() ? -1 : lines[0].tid);
+    int64_t cr = 0; int32_t cp = 0; size_t cur = 0;
+    for (size_t j = 0; j < lines.size(); j++) {
+        cr += lines[j].n_reads; cp += lines[j].end_pos - lines[j].beg_pos;
+        if ((j > 0) && ((last_tid != lines[j].tid) || ((size_t)cr * (size_t)nthreads * 8 > (size_t)nreads) || ((size_t)(int64_t)cp * (size_t)nthreads * 8 > (size_t)npositions))) {
+            pairs.push_back(std::make_pair(cur, j));
+            cur = j; last_tid = lines[j].tid; cr = 0; cp = 0;
+        }
+    }
+    pairs.push_back(std::make_pair(cur, lines.size()));
+    std::string s;
+    for (size_t t2 = 0; t2 < pairs.size(); t2++) {
+        for (size_t t3 = pairs[t2].first; t3 < pairs[t2].second; t3++) {
+            const auto & l = lines[t3];
+            s += contigs[(size_t)l.tid].first + "\t" + std::to_string(l.beg_pos) + "\t" + std::to_string(l.end_pos) + "\tBedLineFlag\t" + std::to_string(l.region_flag)
+               + "\tNumberOfReadsInThisInterval\t" + std::to_string(l.n_reads) + "\tNumberOfRefBasesInThisInterval\t" + std::to_string(l.end_pos - l.beg_pos)
+               + "\tTier1regionIndex\t" + std::to_string(tier1_idx) + "\tTier2regionIndex\t" + std::to_string(t2) + "\tTier3regionIndex\t" + std::to_string(t3) + "\n";
+        }
+    }
+    return s;
+}
+
+void tiler_thread(Shared *sh) {
+    const Options & o = sh->opt;
+    uvchost_tiler *t = uvchost_tiler_open(o.bam.c_str(), o.bed.c_str(), o.targets.c_str(), o.threads, o.mem_per_thread, o.bed_in_avg_sequencing_DP, 0);
+    if (uvchost_tiler_error(t)[0]) { sh->fail(std::string("tiler: ") + uvchost_tiler_error(t)); uvchost_tiler_close(t); sh->batches.close(); return; }
+    std::ofstream bed_out;
+    if (!o.bed_out.empty() && o.bed_out != ".") { bed_out.open(o.bed_out.c_str(), std::ios::out); }
+    uvchost_bedline prev; prev.tid = -1; prev.beg_pos = 0; prev.end_pos = 0; prev.region_flag = 0; prev.n_reads = 0;
+    int64_t seq = 0, iter = 0;
+    for (;;) {
+        const uvchost_bedline *lines = NULL; int64_t n = 0;
+        const int64_t nreads = uvchost_tiler_next(t, &lines, &n);
+        if (nreads < 0) { sh->fail(std::string("tiler: ") + uvchost_tiler_error(t)); break; }
+        if (!(nreads > 0 || n > 0)) { break; }     // main.cpp:1339
+        std::vector<uvchost_bedline> v(lines, lines + n);
+        if (bed_out.is_open()) { bed_out << bed_out_text(v, sh->contigs, o.threads, iter); }
+        Batch b;
+        int64_t bp = 0, br = 0;
+        for (const auto & l : v) {
+            const int64_t lp = (int64_t)(l.end_pos - l.beg_pos) + 4200, lr = l.n_reads;
+            if (!b.tiles.empty() && (bp + lp > o.batch_positions || br + lr > o.batch_reads || b.tiles.back().tid != l.tid)) {
+                b.seq = seq++; sh->batches.push(std::move(b)); b = Batch(); bp = 0; br = 0;
+            }
+            b.tiles.push_back(l); b.prevs.push_back(prev);
+            prev = l; bp += lp; br += lr;
+        }
+        if (!b.tiles.empty()) { b.seq = seq++; sh->batches.push(std::move(b)); }
+        iter++;
+        if (sh->failed.load()) { break; }
+    }
+    uvchost_tiler_close(t);
+    sh->batches.close();
+}
+
+struct Lane {
+    Shared *sh = NULL;
+    int device = 0, n_threads = 1, index = 0;
+};
+
+void lane_thread(Lane lane) {
+    Shared *sh = lane.sh;
+    const Options & o = sh->opt;
+    uvcgpu_ctx *ctx = NULL;
+    int rc = uvcgpu_create(&ctx, lane.device, &sh->par);
+    if (rc != 0) { sh->fail("uvcgpu_create failed on device " + std::to_string(lane.device) + " with code " + std::to_string(rc) + (rc == UVCGPU_ENODEVICE ? " (no CUDA device; there is no CPU fallback)" : "")); return; }
+    uvcgpu_set_host_threads(ctx, lane.n_threads);
+    const int n_dec = std::max(1, lane.n_threads);
+    std::vector<uvchost_bam*> bams((size_t)n_dec, NULL);
+    std::vector<uvchost_readbuf*> rbs((size_t)n_dec, NULL);
+    for (int k = 0; k < n_dec; k++) { bams[k] = uvchost_bam_open(o.bam.c_str()); rbs[k] = uvchost_readbuf_new(); if (NULL == bams[k]) { sh->fail("failed to open " + o.bam); } }
+    uvchost_fasta *fa = NULL;
+    if (!o.fasta.empty()) { fa = uvchost_fasta_open(o.fasta.c_str()); if (NULL == fa) { sh->fail("failed to open " + o.fasta + " (or its .fai)"); } }
+    std::set<int32_t> loaded;
+    Batch b;
+    while (!sh->failed.load() && sh->batches.pop(b)) {
+        const int32_t n_tiles = (int32_t)b.tiles.size();
+        // reference bases of the contigs this batch touches (load_refstring, main.cpp:54-70)
+        std::set<int32_t> needed;
+        for (const auto & l : b.tiles) { needed.insert(l.tid); }
+        for (auto it = loaded.begin(); it != loaded.end();) { if (!needed.count(*it)) { uvcgpu_unset_contig(ctx, *it); it = loaded.erase(it); } else { ++it; } }
+        for (int32_t tid : needed) {
+            if (loaded.count(tid)) { continue; }
+            int64_t len = 0;
+            char *bases = (fa ? uvchost_fasta_fetch_contig(fa, sh->contigs[(size_t)tid].first.c_str(), &len) : NULL);
+            if (fa && NULL == bases) { sh->fail("contig " + sh->contigs[(size_t)tid].first + " is not in " + o.fasta); break; }
+            uvcgpu_set_contig(ctx, tid, bases, bases ? len : sh->contigs[(size_t)tid].second);
+            uvcgpu_set_contig_name(ctx, tid, sh->contigs[(size_t)tid].first.c_str());
+            free(bases);
+            loaded.insert(tid);
+        }
+        if (sh->failed.load()) { break; }
+        // decode: the tiles are cut into n_dec runs of consecutive tiles, one decode thread and one SoA buffer per run
+        const int64_t t0 = now_us();
+        std::vector<uvcgpu_tile> tiles((size_t)n_tiles);
+        std::vector<int32_t> tile_source((size_t)n_tiles, 0);
+        const int n_src = std::min(n_dec, (int)n_tiles);
+        std::vector<std::thread> pool;
+        std::atomic<int> dec_failed(0);
+        for (int s = 0; s < n_src; s++) {
+            pool.emplace_back([&, s]() {
+                uvchost_readbuf_clear(rbs[s]);
+                const int32_t k0 = (int32_t)((int64_t)n_tiles * s / n_src), k1 = (int32_t)((int64_t)n_tiles * (s + 1) / n_src);
+                for (int32_t k = k0; k < k1; k++) {
+                    const uvchost_bedline & l = b.tiles[k];
+                    uvcgpu_tile & T = tiles[k];
+                    T.tid = l.tid; T.beg_pos = l.beg_pos; T.end_pos = l.end_pos; T.region_flag = l.region_flag;
+                    T.prev_tid = b.prevs[k].tid; T.prev_beg_pos = b.prevs[k].beg_pos; T.prev_end_pos = b.prevs[k].end_pos;
+                    T.contig_len = (int32_t)sh->contigs[(size_t)l.tid].second;
+                    T.read_begin = uvchost_readbuf_size(rbs[s]);
+                    // sam_itr_queryi(tid, beg - MAX_INSERT_SIZE, end + MAX_INSERT_SIZE) (grouping.cpp:664, 730)
+                    if (uvchost_bam_fetch(bams[s], l.tid, std::max(0, l.beg_pos - 2000), (int64_t)l.end_pos + 2000, rbs[s]) < 0) { dec_failed.store(1); }
+                    T.read_end = uvchost_readbuf_size(rbs[s]);
+                    tile_source[k] = s;
+                }
+            });
+        }
+        for (auto & th : pool) { th.join(); }
+        if (dec_failed.load()) { sh->fail("error while reading " + o.bam); break; }
+        std::vector<uvcgpu_reads_soa> sources((size_t)n_src);
+        for (int s = 0; s < n_src; s++) { uvchost_readbuf_view(rbs[s], &sources[s]); }
+        const int64_t t1 = now_us();
+        uvcgpu_ticket ticket = 0;
+        uvcgpu_batch_stats st;
+        rc = uvcgpu_submit_multi(ctx, n_tiles, tiles.data(), n_src, sources.data(), tile_source.data(), &ticket);
+        const int64_t t2 = now_us();
+        if (0 == rc) { rc = uvcgpu_collect(ctx, ticket, &st); }
+        const int64_t t3 = now_us();
+        if (0 == rc) { rc = uvcgpu_score(ctx, ticket, &st); }
+        const int64_t t4 = now_us();
+        std::string text;
+        if (0 == rc) {
+            std::vector<size_t> need((size_t)n_tiles, 0);
+            size_t total = 0;
+            for (int32_t k = 0; k < n_tiles && 0 == rc; k++) { rc = uvcgpu_tile_vcf(ctx, ticket, k, NULL, 0, &need[k]); total += need[k]; }
+            text.resize(total);
+            size_t off = 0;
+            for (int32_t k = 0; k < n_tiles && 0 == rc; k++) { size_t n2 = 0; rc = uvcgpu_tile_vcf(ctx, ticket, k, &text[off], need[k], &n2); off += need[k]; }
+        }
+        const int64_t t5 = now_us();
+        if (rc != 0) { sh->fail(std::string("batch ") + std::to_string(b.seq) + " failed (" + std::to_string(rc) + "): " + uvcgpu_last_error(ctx)); break; }
+        uvcgpu_release(ctx, ticket);
+        std::string outbytes;
+        if (o.out == "-") { outbytes.swap(text); }
+        else if (uvchost_bgzf_compress(outbytes, text.data(), text.size(), o.compress_level, lane.n_threads) != 0) { sh->fail("BGZF compression failed"); break; }
+        const int64_t t6 = now_us();
+        sh->n_reads_kept += st.n_reads_kept; sh->n_positions += st.n_positions; sh->n_records += st.n_vcf_records; sh->n_batches += 1; sh->n_launches += st.gpu_launches;
+        sh->us_fetch += t1 - t0; sh->us_prep += t2 - t1; sh->us_gpu_wait += t3 - t2; sh->us_score += t4 - t3; sh->us_text += t5 - t4; sh->us_compress += t6 - t5;
+        { std::lock_guard<std::mutex> lk(sh->kernel_ms_mutex); sh->kernel_ms += st.kernel_ms; }
+        {
+            std::lock_guard<std::mutex> lk(sh->out_mutex);
+            sh->done[b.seq].swap(outbytes);
+        }
+        sh->out_cv.notify_all();
+    }
+    for (int k = 0; k < n_dec; k++) { if (bams[k]) { uvchost_bam_close(bams[k]); } uvchost_readbuf_free(rbs[k]); }
+    if (fa) { uvchost_fasta_close(fa); }
+    uvcgpu_destroy(ctx);
+}
+
+} // namespace
+
+int main(int argc, char **argv) {
+    const clock_t c_start = clock();
+    const int64_t t_start = now_us();
+    Shared sh;
+    uvcgpu_params_default(&sh.par);
+    sh.par.central_readlen = 0;   // 0 = estimate from the data (CmdLineArgs.hpp:100)
+    Options & o = sh.opt;
+    int rc = parse_args(o, sh.par, argc, argv);
+    if (rc != 0) { return rc; }
+    // CmdLineArgs.cpp:1015-1022
+    if (!file_exists(o.bam)) { fprintf(stderr, "The file %s of type (BAM) does not exist. \n", o.bam.c_str()); return -4; }
+    if (!file_exists(o.bam + ".bai")) { fprintf(stderr, "The file %s.bai of type (BAM index) does not exist. \n", o.bam.c_str()); return -4; }
+    if (o.fasta != "NA") {
+        if (!file_exists(o.fasta)) { fprintf(stderr, "The file %s of type (FASTA) does not exist. \n", o.fasta.c_str()); return -4; }
+        if (!file_exists(o.fasta + ".fai")) { fprintf(stderr, "The file %s.fai of type (FASTA index) does not exist. \n", o.fasta.c_str()); return -4; }
+    } else { o.fasta = ""; }
+    if (o.threads < 1) { o.threads = 1; }
+
+    // data-driven inference (CommandLineArgs::selfUpdateByPlatform, CmdLineArgs.cpp:36-136)
+    {
+        uvchost_bam *b = uvchost_bam_open(o.bam.c_str());
+        if (NULL == b) { fprintf(stderr, "Failed to load BAM file %s\n", o.bam.c_str()); return -3; }
+        for (int32_t i = 0; i < uvchost_bam_n_targets(b); i++) { sh.contigs.push_back(std::make_pair(std::string(uvchost_bam_target_name(b, i)), uvchost_bam_target_len(b, i))); }
+        uvchost_infer_stats is;
+        if (uvchost_bam_infer(b, 5000, &is) != 0) { fprintf(stderr, "Failed to read %s\n", o.bam.c_str()); return -3; }
+        uvchost_bam_close(b);
+        sh.par.inferred_maxMQ = std::max(0, is.max_mapq);
+        if (0 == sh.par.central_readlen) { sh.par.central_readlen = is.median_qlen; }
+        const bool is_pe = (is.count_pe > 0);
+        const bool q2x = (2 * (uint64_t)(is.q30_n_fail_bases - is.q20_n_fail_bases) < (uint64_t)is.q30_n_pass_bases);
+        const bool q4x = (4 * (uint64_t)(is.q30_n_fail_bases - is.q20_n_fail_bases) < (uint64_t)is.q30_n_pass_bases);
+        const bool fixqlen = ((int64_t)is.median_qlen * 100 > (int64_t)is.max_qlen * 95);
+        const bool illumina = (is_pe || q4x || (q2x && fixqlen));
+        fprintf(stderr, "Inferred_sequencing_platform=%s\n IsPairedEnd=%d\n", illumina ? "Illumina/BGI" : "IonTorrent/LifeTechnologies/ThermoFisher", (int)is_pe);
+        if (!illumina) { fprintf(stderr, "The IonTorrent-specific code path (TIsProton) is not implemented in this build.\n"); return 105; }
+        sh.par.inferred_sequencing_platform = 1;
+    }
+
+    const int n_dev = uvcgpu_device_count();
+#ifdef UVC_EMU_HOST
+    const int n_gpus = 1;
+    (void)n_dev;
+#else
+    if (n_dev <= 0) { fprintf(stderr, "no CUDA device found: uvc1 (B200 build) has no CPU fallback\n"); return 107; }
+    const int n_gpus = (o.gpus > 0 ? std::min(o.gpus, n_dev) : n_dev);
+#endif
+    const int hw = std::max(1, (int)std::thread::hardware_concurrency());
+    const int cpu_budget = std::min(std::max(o.threads, 1), hw);
+    int lanes_per_gpu = (o.lanes_per_gpu > 0 ? o.lanes_per_gpu : std::max(1, std::min(3, cpu_budget / (2 * n_gpus))));
+    const int n_lanes = lanes_per_gpu * n_gpus;
+    const int threads_per_lane = std::max(1, (cpu_budget + n_lanes - 1) / n_lanes);
+
+    FILE *fout = NULL;
+    const bool to_stdout = (o.out == "-");
+    if (!to_stdout && !o.out.empty()) {
+        fout = fopen(o.out.c_str(), "wb");
+        if (NULL == fout) { fprintf(stderr, "Unable to open the bgzip file %s\n", o.out.c_str()); return -8; }
+    }
+    {
+        const std::string header = uvc_vcf_header(argc, argv, sh.contigs, o.fasta, o.sample, sh.par, UVC_B200_VERSION);
+        if (to_stdout) { fwrite(header.data(), 1, header.size(), stdout); }
+        else if (fout) { std::string z; uvchost_bgzf_compress(z, header.data(), header.size(), o.compress_level, 1); fwrite(z.data(), 1, z.size(), fout); }
+    }
+
+    std::thread tiler(tiler_thread, &sh);
+    std::vector<std::thread> lanes;
+    for (int k = 0; k < n_lanes; k++) {
+        Lane l; l.sh = &sh; l.device = k % n_gpus; l.n_threads = threads_per_lane; l.index = k;
+        lanes.emplace_back(lane_thread, l);
+    }
+    // writer: batches in tile order
+    std::atomic<int> lanes_done(0);
+    std::thread joiner([&]() { for (auto & th : lanes) { th.join(); } lanes_done.store(1); sh.out_cv.notify_all(); });
+    int64_t next_seq = 0, bytes_written = 0;
+    for (;;) {
+        std::string chunk;
+        {
+            std::unique_lock<std::mutex> lk(sh.out_mutex);
+            sh.out_cv.wait(lk, [&]() { return sh.done.count(next_seq) || lanes_done.load() || sh.failed.load(); });
+            auto it = sh.done.find(next_seq);
+            if (it == sh.done.end()) { break; }
+            chunk.swap(it->second);
+            sh.done.erase(it);
+        }
+        if (!chunk.empty()) {
+            if (to_stdout) { fwrite(chunk.data(), 1, chunk.size(), stdout); } else if (fout) { fwrite(chunk.data(), 1, chunk.size(), fout); }
+            bytes_written += (int64_t)chunk.size();
+        }
+        next_seq++;
+    }
+    tiler.join();
+    joiner.join();
+    if (sh.failed.load()) {
+        fprintf(stderr, "uvc1: %s\n", sh.fail_msg.c_str());
+        if (fout) { fclose(fout); }
+        return 110;
+    }
+    if (fout) { std::string z; uvchost_bgzf_eof(z); fwrite(z.data(), 1, z.size(), fout); fclose(fout); }
+    if (to_stdout) { fflush(stdout); }
+    const double wall = (now_us() - t_start) / 1e6;
+    if (o.stats) {
+        fprintf(stderr, "uvc1-b200 stats: gpus=%d lanes=%d threads_per_lane=%d batches=%lld reads_kept=%lld positions=%lld records=%lld launches=%lld kernel_ms=%.1f\n"
+                        "uvc1-b200 stage seconds summed over lanes: decode=%.2f stage+h2d=%.2f gpu_wait=%.2f score=%.2f text=%.2f compress=%.2f\n"
+                        "uvc1-b200 throughput: %.0f reads/s %.0f positions/s\n",
+                n_gpus, n_lanes, threads_per_lane, (long long)sh.n_batches.load(), (long long)sh.n_reads_kept.load(), (long long)sh.n_positions.load(), (long long)sh.n_records.load(),
+                (long long)sh.n_launches.load(), sh.kernel_ms,
+                sh.us_fetch / 1e6, sh.us_prep / 1e6, sh.us_gpu_wait / 1e6, sh.us_score / 1e6, sh.us_text / 1e6, sh.us_compress / 1e6,
+                sh.n_reads_kept.load() / wall, sh.n_positions.load() / wall);
+    }
+    fprintf(stderr, "CPU time used: %.2f seconds\nWall clock time passed: %.2f seconds\n", (double)(clock() - c_start) / CLOCKS_PER_SEC, wall);
+    return 0;
+}

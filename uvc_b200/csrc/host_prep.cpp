@@ -579,8 +579,8 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
     return 0;
 }
 
-static int host_threads(int32_t n_tiles) {
-    int n = (int)std::thread::hardware_concurrency();
+int uvc_host_threads(int32_t n_tiles, int requested) {
+    int n = (requested > 0 ? requested : (int)std::thread::hardware_concurrency());
     const char *e = getenv("UVC_HOST_THREADS");
     if (e && atoi(e) > 0) { n = atoi(e); }
     if (n < 1) { n = 1; }
@@ -588,29 +588,20 @@ static int host_threads(int32_t n_tiles) {
     return std::min<int>(n, n_tiles);
 }
 
-template <class F> static void parallel_for(int32_t n, int n_threads, F body) {
-    if (n_threads <= 1) { for (int32_t i = 0; i < n; i++) { body(i); } return; }
-    std::atomic<int32_t> next(0);
-    std::vector<std::thread> pool;
-    for (int t = 0; t < n_threads; t++) {
-        pool.emplace_back([&]() { for (;;) { const int32_t i = next.fetch_add(1); if (i >= n) { break; } body(i); } });
-    }
-    for (auto & th : pool) { th.join(); }
-}
 
 int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::map<int32_t, HostContig> & contigs,
-        int32_t n_tiles, const uvcgpu_tile *tiles, const uvcgpu_reads_soa & rs, std::string & msg) {
+        int32_t n_tiles, const uvcgpu_tile *tiles, const uvcgpu_reads_soa *sources, const int32_t *tile_source, int n_threads_req, std::string & msg) {
     if (par.inferred_sequencing_platform != 1) { msg = "only the Illumina/BGI platform path is implemented"; return UVCGPU_EUNSUPPORTED; }
     const bool pem = (0 == par.pair_end_merge);
     double center_pow[4];
     for (int d = 0; d < 4; d++) { center_pow[d] = pow(par.dedup_center_mult, (double)d); }
     hb = HostBatch();
-    const int n_threads = host_threads(n_tiles);
+    const int n_threads = n_threads_req;
     // 1. every tile staged privately, on all host cores
     std::vector<HostBatch> part((size_t)n_tiles);
     std::vector<int> rcs((size_t)n_tiles, 0);
     std::vector<std::string> msgs((size_t)n_tiles);
-    parallel_for(n_tiles, n_threads, [&](int32_t ti) { rcs[ti] = build_tile(part[ti], par, contigs, ti, tiles[ti], rs, center_pow, pem, msgs[ti]); });
+    uvc_parallel_for(n_tiles, n_threads, [&](int32_t ti) { rcs[ti] = build_tile(part[ti], par, contigs, ti, tiles[ti], sources[tile_source ? tile_source[ti] : 0], center_pow, pem, msgs[ti]); });
     for (int32_t ti = 0; ti < n_tiles; ti++) { if (rcs[ti] != 0) { msg = msgs[ti]; return rcs[ti]; } }
     // 2. offsets of every tile in the concatenated arrays
     struct Off { int64_t pos, read, frag, fam, fragread, seq, qual, cigar, cx, ev; };
@@ -634,7 +625,7 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
     hb.frags.resize((size_t)tot.frag); hb.frag_reads.resize((size_t)tot.fragread); hb.fams.resize((size_t)tot.fam); hb.fam_umi.resize((size_t)tot.fam);
     hb.n_pos = tot.pos; hb.n_cx = tot.cx; hb.n_ev = tot.ev;
     // 3. concatenation with the tile-local indices rebased, again on all cores (disjoint destination ranges)
-    parallel_for(n_tiles, n_threads, [&](int32_t ti) {
+    uvc_parallel_for(n_tiles, n_threads, [&](int32_t ti) {
         HostBatch & b = part[ti];
         const Off & o = off[ti];
         TileInfo T = b.tiles[0];

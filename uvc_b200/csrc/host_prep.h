@@ -34,12 +34,34 @@ struct HostBatch {
 };
 
 // Builds the staging arrays of one batch. Returns 0 or a negative uvcgpu_error; msg receives the reason.
+// Tile k reads its records from sources[tile_source[k]] (tile_source == NULL: all tiles use sources[0]). n_threads <= 0: all cores.
 int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::map<int32_t, HostContig> & contigs,
-        int32_t n_tiles, const uvcgpu_tile *tiles, const uvcgpu_reads_soa & rs, std::string & msg);
+        int32_t n_tiles, const uvcgpu_tile *tiles, const uvcgpu_reads_soa *sources, const int32_t *tile_source, int n_threads, std::string & msg);
 
 // Text form of the family grouping of one tile (same format as oracle/harness_dump.cpp writes).
 std::string uvc_families_text(const HostBatch & hb, int32_t tile_index, const uvcgpu_reads_soa & rs);
 
 void uvc_fill_view_constants(BatchView & v, const uvcgpu_params & par);
+
+// Number of host threads to use for n independent items (requested <= 0: all cores; the UVC_HOST_THREADS environment variable overrides).
+int uvc_host_threads(int32_t n_items, int requested);
+
+// Dynamic parallel loop over [0, n) on n_threads host threads (requested semantics as above).
+template <class F> void uvc_parallel_for(int32_t n, int requested_threads, F body);
+
+
+#include <atomic>
+#include <thread>
+
+template <class F> void uvc_parallel_for(int32_t n, int requested_threads, F body) {
+    const int n_threads = uvc_host_threads(n, requested_threads);
+    if (n_threads <= 1) { for (int32_t i = 0; i < n; i++) { body(i); } return; }
+    std::atomic<int32_t> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; t++) {
+        pool.emplace_back([&]() { for (;;) { const int32_t i = next.fetch_add(1); if (i >= n) { break; } body(i); } });
+    }
+    for (auto & th : pool) { th.join(); }
+}
 
 #endif
