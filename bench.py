@@ -22,7 +22,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-STAGES_IMPLEMENTED = "P0 grouping(host)+P1 refctx(host)+K0 read consts+K1 prep/thres+K2 bias pileup+K2e indel events+K3 fragment consensus+K4 family/duplex consensus (= updateByRegion3Aln)+K6 block-line inputs+K5 candidate scoring+VCF text(host) = process_batch"
+STAGES_IMPLEMENTED = "P0 grouping(host)+P1 refctx(host)+K0 read consts+K1 prep/thres+K2 bias pileup+K2e indel events+KF fragment columns+K3 fragment consensus+KM family columns+K4 family/duplex consensus (= updateByRegion3Aln)+K6 block-line inputs+K5 candidate scoring+VCF text(host) = process_batch"
 
 
 def parse_args():
@@ -254,7 +254,8 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     dom = max(range(16), key=lambda i: stage_ms[i])
-    STAGE_NAMES = ["K0 per-read", "K1 prep+thres", "K2 bias pileup", "K2e indel events", "K3a fragment stats", "K3b fragment consensus", "K4a family ends", "K4 family+duplex consensus", "K4c family haplotypes", "K6 block-line inputs", "K5 candidate scoring"]
+    STAGE_NAMES = ["K0 per-read", "K1 prep+thres", "K2 bias pileup", "K2e indel events", "KF fragment columns", "K3a fragment stats", "K3b fragment consensus", "KM family columns",
+                   "K4a family ends", "K4 family+duplex consensus", "K4c family haplotypes", "K6 block-line inputs", "K5 candidate scoring"]
     dom_name = STAGE_NAMES[dom] if dom < len(STAGE_NAMES) else "stage%d" % dom
     bytes_alg = n_reads * (1.5 * 150 + 64) + last.n_ext_positions * 2 * 6272
     achieved = bytes_alg / (stage_ms[dom] / args.steps / 1e3) / 1e9

@@ -102,7 +102,30 @@ struct FragRec {
     int32_t beg, end;              // fillTidBegEndFromAlns1 (main.hpp:659-673)
     int32_t n_cov, n_near_mut;     // bTA / bTB numerators (main.hpp:2747-2756), kernel K3a
     int32_t normMQ;
+    int32_t lo, hi;                // covered extent: min pos, max rend over the fragment's reads
+    int64_t col_off;               // first entry of the fragment's column in fcol (multiple of 32)
 };
+
+// What one fragment (R1+R2 max-merged) asserts at one reference position: the result of the reference's per-fragment walks #3, #4 and #5
+// (updateByAln<BASE_QUALITY_MAX>, main.hpp:2629, 2887, 3403; they rebuild the same array three times) reduced by fillConsensusCounts
+// (main.hpp:374-417) for both symbol types. Computed once per (fragment, position) by kernel KF and read by every fragment/family kernel.
+struct FragCol {
+    uint16_t link_cc;              // link consensus with the reference counted once: its count (0 = the fragment says nothing here)
+    uint16_t base_cc, base_tc;     // base consensus over A..NN: largest count and sum of counts
+    uint8_t link_sym;              // low 4 bits: symbol; bit 7: the fragment votes for BASE_N or BASE_NN here (consensus over A..T may differ)
+    uint8_t base_sym;
+};
+
+// Per (family, strand, position): the fragment votes of the family after the base-quality filter (updateByFiltering, main.hpp:466-495) and the
+// major-minus-minor quality sums (updateByMajorMinusMinor, main.hpp:497-520), reduced to what the family loops consume. Index [0] = base, [1] = link.
+struct FamCol {
+    uint8_t a1[2], a2[2];          // consensus symbol over the fragment counts / over the quality sums
+    uint16_t cc1[2], tc1[2];       // count of a1 and total count
+    uint16_t con_a2[2];            // fragment count of a2
+    uint32_t mmm_cc[2], mmm_tot[2];
+};
+
+#define UVC_COL_CHUNK 32           // column entries are laid out in chunks of one warp; a chunk belongs to one fragment / (family, strand)
 
 struct FamRec {
     int32_t tile;
@@ -114,6 +137,8 @@ struct FamRec {
     int32_t qlen_ok[2];                // alns2.size() >= fam_thres_dup1add && qseqlen_sum >= n_qseqs * fam_thres_qseqlen
     int32_t nsb_min[2], nsb_max[2];    // no_strict_bias_pos_min/max (main.hpp:2959-2998), kernel K4a
     int32_t beg_tid, beg_pos, end_tid, end_pos;
+    int32_t lo[2], hi[2];              // covered extent of each strand: min pos, max rend over its reads (lo >= hi: no reads)
+    int64_t col_off[2];                // first entry of each strand's column in mcol (multiple of 32)
 };
 
 struct BatchView {
@@ -142,6 +167,12 @@ struct BatchView {
     const FragRec *frags_in; FragRec *frags;
     const int32_t *frag_reads;
     FamRec *fams;
+    // per-fragment and per-(family, strand) columns
+    int64_t n_fcol, n_mcol;        // padded entry counts (multiples of UVC_COL_CHUNK)
+    FragCol *fcol;
+    FamCol *mcol;
+    const int32_t *fchunk_frag;    // [n_fcol / 32] fragment that owns each chunk of fcol
+    const int32_t *mchunk_fs;      // [n_mcol / 32] 2 * family + strand that owns each chunk of mcol
     // per-position state
     uvcgpu_prep_set *prep;
     uvcgpu_thres_set *thres;

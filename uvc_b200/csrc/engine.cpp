@@ -33,6 +33,8 @@
 #define UVC_CUDA 0
 #endif
 
+#define UVC_N_PILEUP_STAGES 11   // K0, K1, K2, K2e, KF, K3a, K3b, KM, K4a, K4, K4c (kernel_ms_by_stage[0..10]); [11] = K6, [12] = K5
+
 namespace {
 
 double now_ms() {
@@ -59,7 +61,7 @@ struct BatchState {
     std::vector<GvcfPos> gvcf;
     std::vector<GvcfExtra> gextra;
 #if UVC_CUDA
-    cudaEvent_t ev[12];
+    cudaEvent_t ev[UVC_N_PILEUP_STAGES + 1];
     bool have_events = false;
 #endif
 };
@@ -92,15 +94,39 @@ struct uvcgpu_ctx {
         const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; \
         if (i < n) { call; } \
     }
+// Position kernels: every thread owns one reference position; the 32 lanes of a warp walk the UNION of their read windows in lock-step
+// (kernels_core.cuh, struct Win), which turns the per-read loads into warp-wide broadcasts and the per-position loads into consecutive addresses.
+__device__ __forceinline__ void uvc_warp_window(const BatchView & v, int64_t gp, bool active, uvc::Win & w) {
+    w.lo = 0; w.hi = 0;
+    if (active) { uvc::position_window(v, gp, w); }
+    const int32_t lo32 = (active && w.hi > w.lo ? (int32_t)w.lo : INT32_MAX), hi32 = (active && w.hi > w.lo ? (int32_t)w.hi : 0);
+    w.ulo = (int64_t)__reduce_min_sync(0xffffffffu, lo32);
+    w.uhi = (int64_t)__reduce_max_sync(0xffffffffu, hi32);
+}
+#define UVC_DEFINE_POS_KERNEL(name, call) \
+    __global__ void __launch_bounds__(128) name(const BatchView v, int64_t n) { \
+        const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; \
+        uvc::Win w; \
+        uvc_warp_window(v, i, i < n, w); \
+        if (i < n) { call; } \
+    }
 UVC_DEFINE_KERNEL(uvc_k0_read_consts, uvc::k0_read(v, i))
-UVC_DEFINE_KERNEL(uvc_k1_prep_thres, uvc::k1_position(v, i))
+UVC_DEFINE_POS_KERNEL(uvc_k1_prep_thres, uvc::k1_position(v, i, w))
 // both roles of a position sit in different warps of the same block: block = 64 positions x 2 roles
-UVC_DEFINE_KERNEL(uvc_k2_bias_pileup, { const int64_t gp = (i / 128) * 64 + (i % 64); if (gp < v.n_pos) { uvc::k2_position(v, gp, (int)((i % 128) / 64)); } })
+__global__ void __launch_bounds__(128) uvc_k2_bias_pileup(const BatchView v, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gp = (i / 128) * 64 + (i % 64);
+    uvc::Win w;
+    uvc_warp_window(v, gp, gp < v.n_pos, w);
+    if (gp < v.n_pos) { uvc::k2_position(v, gp, (int)((i % 128) / 64), w); }
+}
 UVC_DEFINE_KERNEL(uvc_k2e_indel_events, uvc::k2e_event(v, i))
+UVC_DEFINE_KERNEL(uvc_kf_fragment_columns, uvc::kf_fragment_column(v, i))
 UVC_DEFINE_KERNEL(uvc_k3a_fragment_stats, uvc::k3a_fragment(v, i))
-UVC_DEFINE_KERNEL(uvc_k3b_fragment_consensus, uvc::k3b_position(v, i))
+UVC_DEFINE_POS_KERNEL(uvc_k3b_fragment_consensus, uvc::k3b_position(v, i, w))
+UVC_DEFINE_KERNEL(uvc_km_family_columns, uvc::km_family_column(v, i))
 UVC_DEFINE_KERNEL(uvc_k4a_family_ends, uvc::k4a_family_strand(v, i))
-UVC_DEFINE_KERNEL(uvc_k4_family_consensus, uvc::k4_position(v, i))
+UVC_DEFINE_POS_KERNEL(uvc_k4_family_consensus, uvc::k4_position(v, i, w))
 UVC_DEFINE_KERNEL(uvc_k4c_family_haplotypes, uvc::k4c_family_strand(v, i))
 
 // scoring stage: K6 one thread per extended position, K5 one thread per zero-based position (heavy local state: 64 threads per block)
@@ -108,9 +134,14 @@ __global__ void __launch_bounds__(128) uvc_k6_gvcf_inputs(const BatchView v, con
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { uvc::k6_gvcf_position(v, sv, i); }
 }
+__global__ void __launch_bounds__(128) uvc_k5a_flag_candidates(const BatchView v, const ScoreView sv, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { uvc::k5a_flag_position(v, sv, i); }
+}
+// runs over the compacted list of candidate positions (the grid is sized for the worst case; threads beyond the list exit at once)
 __global__ void __launch_bounds__(64) uvc_k5_score_candidates(const BatchView v, const ScoreView sv, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { uvc::k5_score_position(v, sv, i); }
+    if (i < n && i < (int64_t)*sv.cand_cursor) { uvc::k5_score_position(v, sv, (int64_t)sv.cand_list[i]); }
 }
 
 typedef void (*uvc_kernel_t)(const BatchView, int64_t);
@@ -141,27 +172,23 @@ static void backend_free(BatchState & bs) { for (void *p : bs.allocs) { cudaFree
 static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     const BatchView & v = bs.view;
     int64_t launches = 0;
-    for (int i = 0; i < 12; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreate(&bs.ev[i])); }
+    for (int i = 0; i < UVC_N_PILEUP_STAGES + 1; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreate(&bs.ev[i])); }
     bs.have_events = true;
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[0], ctx->stream));
-    launch(uvc_k0_read_consts, ctx->stream, v, v.n_reads, launches);
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[1], ctx->stream));
-    launch(uvc_k1_prep_thres, ctx->stream, v, v.n_pos, launches);
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[2], ctx->stream));
-    launch(uvc_k2_bias_pileup, ctx->stream, v, ((v.n_pos + 63) / 64) * 128, launches);
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[3], ctx->stream));
-    launch(uvc_k2e_indel_events, ctx->stream, v, v.n_ev, launches);
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[4], ctx->stream));
-    launch(uvc_k3a_fragment_stats, ctx->stream, v, v.n_frags, launches);
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[5], ctx->stream));
-    launch(uvc_k3b_fragment_consensus, ctx->stream, v, v.n_pos, launches);
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[6], ctx->stream));
-    launch(uvc_k4a_family_ends, ctx->stream, v, 2 * v.n_fams, launches);
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[7], ctx->stream));
-    launch(uvc_k4_family_consensus, ctx->stream, v, v.n_pos, launches);
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[8], ctx->stream));
-    launch(uvc_k4c_family_haplotypes, ctx->stream, v, 2 * v.n_fams, launches);
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[9], ctx->stream));
+    int e = 0;
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
+    #define UVC_STAGE(kernel, n) { launch(kernel, ctx->stream, v, (n), launches); UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream)); }
+    UVC_STAGE(uvc_k0_read_consts, v.n_reads)
+    UVC_STAGE(uvc_k1_prep_thres, v.n_pos)
+    UVC_STAGE(uvc_k2_bias_pileup, ((v.n_pos + 63) / 64) * 128)
+    UVC_STAGE(uvc_k2e_indel_events, v.n_ev)
+    UVC_STAGE(uvc_kf_fragment_columns, v.n_fcol)
+    UVC_STAGE(uvc_k3a_fragment_stats, v.n_frags)
+    UVC_STAGE(uvc_k3b_fragment_consensus, v.n_pos)
+    UVC_STAGE(uvc_km_family_columns, v.n_mcol)
+    UVC_STAGE(uvc_k4a_family_ends, 2 * v.n_fams)
+    UVC_STAGE(uvc_k4_family_consensus, v.n_pos)
+    UVC_STAGE(uvc_k4c_family_haplotypes, 2 * v.n_fams)
+    #undef UVC_STAGE
     UVC_CUDA_CHECK(ctx, cudaGetLastError());
     bs.stats.gpu_launches = launches;
     return 0;
@@ -172,13 +199,13 @@ static int backend_wait(uvcgpu_ctx *ctx, BatchState & bs) {
     if (bs.have_events) {
         float ms = 0;
         double total = 0;
-        for (int i = 0; i < 9; i++) {
+        for (int i = 0; i < UVC_N_PILEUP_STAGES; i++) {
             UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, bs.ev[i], bs.ev[i + 1]));
             bs.stats.kernel_ms_by_stage[i] = ms;
             total += ms;
         }
         bs.stats.kernel_ms = total;
-        for (int i = 0; i < 12; i++) { cudaEventDestroy(bs.ev[i]); }
+        for (int i = 0; i < UVC_N_PILEUP_STAGES + 1; i++) { cudaEventDestroy(bs.ev[i]); }
         bs.have_events = false;
     }
     return 0;
@@ -191,15 +218,16 @@ static int backend_score(uvcgpu_ctx *ctx, BatchState & bs, const ScoreView & sv)
     UVC_CUDA_CHECK(ctx, cudaEventRecord(e[0], ctx->stream));
     if (v.n_pos > 0) { uvc_k6_gvcf_inputs<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, ctx->stream>>>(v, sv, v.n_pos); }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(e[1], ctx->stream));
+    if (v.n_pos > 0) { uvc_k5a_flag_candidates<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, ctx->stream>>>(v, sv, v.n_pos); }
     if (v.n_pos > 0) { uvc_k5_score_candidates<<<(unsigned)((v.n_pos + 63) / 64), 64, 0, ctx->stream>>>(v, sv, v.n_pos); }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(e[2], ctx->stream));
     UVC_CUDA_CHECK(ctx, cudaGetLastError());
     UVC_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0;
-    UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, e[0], e[1])); bs.stats.kernel_ms_by_stage[9] = ms; bs.stats.kernel_ms += ms;
-    UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, e[1], e[2])); bs.stats.kernel_ms_by_stage[10] = ms; bs.stats.kernel_ms += ms;
+    UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, e[0], e[1])); bs.stats.kernel_ms_by_stage[11] = ms; bs.stats.kernel_ms += ms;
+    UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, e[1], e[2])); bs.stats.kernel_ms_by_stage[12] = ms; bs.stats.kernel_ms += ms;
     for (int i = 0; i < 3; i++) { cudaEventDestroy(e[i]); }
-    if (v.n_pos > 0) { bs.stats.gpu_launches += 2; }
+    if (v.n_pos > 0) { bs.stats.gpu_launches += 3; }
     return 0;
 }
 
@@ -221,13 +249,16 @@ static void backend_free(BatchState & bs) { for (void *p : bs.allocs) { free(p);
 static int backend_run(uvcgpu_ctx *, BatchState & bs) {
     const BatchView & v = bs.view;
     for (int64_t i = 0; i < v.n_reads; i++) { uvc::k0_read(v, i); }
-    for (int64_t i = 0; i < v.n_pos; i++) { uvc::k1_position(v, i); }
-    for (int64_t i = 0; i < v.n_pos; i++) { uvc::k2_position(v, i, 0); uvc::k2_position(v, i, 1); }
+    uvc::Win w;
+    for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k1_position(v, i, w); }
+    for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k2_position(v, i, 0, w); uvc::k2_position(v, i, 1, w); }
     for (int64_t i = 0; i < v.n_ev; i++) { uvc::k2e_event(v, i); }
+    for (int64_t i = 0; i < v.n_fcol; i++) { uvc::kf_fragment_column(v, i); }
     for (int64_t i = 0; i < v.n_frags; i++) { uvc::k3a_fragment(v, i); }
-    for (int64_t i = 0; i < v.n_pos; i++) { uvc::k3b_position(v, i); }
+    for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k3b_position(v, i, w); }
+    for (int64_t i = 0; i < v.n_mcol; i++) { uvc::km_family_column(v, i); }
     for (int64_t i = 0; i < 2 * v.n_fams; i++) { uvc::k4a_family_strand(v, i); }
-    for (int64_t i = 0; i < v.n_pos; i++) { uvc::k4_position(v, i); }
+    for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k4_position(v, i, w); }
     for (int64_t i = 0; i < 2 * v.n_fams; i++) { uvc::k4c_family_strand(v, i); }
     bs.stats.gpu_launches = 0;
     return 0;
@@ -236,7 +267,8 @@ static int backend_wait(uvcgpu_ctx *, BatchState &) { return 0; }
 static int backend_score(uvcgpu_ctx *, BatchState & bs, const ScoreView & sv) {
     const BatchView & v = bs.view;
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::k6_gvcf_position(v, sv, i); }
-    for (int64_t i = 0; i < v.n_pos; i++) { uvc::k5_score_position(v, sv, i); }
+    for (int64_t i = 0; i < v.n_pos; i++) { uvc::k5a_flag_position(v, sv, i); }
+    for (int64_t i = 0; i < (int64_t)*sv.cand_cursor; i++) { uvc::k5_score_position(v, sv, (int64_t)sv.cand_list[i]); }
     return 0;
 }
 
@@ -470,6 +502,11 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
     UVC_UP(frag_reads, int32_t, hb.frag_reads)
     UVC_UP(fams, FamRec, hb.fams)
     UVC_UP(slip_tab, int32_t, ctx->slip_tab)
+    UVC_UP(fchunk_frag, int32_t, hb.fchunk_frag)
+    UVC_UP(mchunk_fs, int32_t, hb.mchunk_fs)
+    v.n_fcol = hb.n_fcol; v.n_mcol = hb.n_mcol;
+    { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_fcol * sizeof(FragCol), false)); v.fcol = (FragCol*)d_; }
+    { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_mcol * sizeof(FamCol), false)); v.mcol = (FamCol*)d_; }
     UVC_ZERO(rd, ReadDerived, v.n_reads)
     UVC_ZERO(cx, CxEntry, v.n_cx)
     UVC_ZERO(ev, IndelEvent, v.n_ev)
@@ -553,6 +590,10 @@ static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
     sv.gextra = (GvcfExtra*)d;
     if ((rc = backend_alloc(ctx, bs, &d, 16, true)) != 0) { return rc; }
     sv.out_cursor = (int32_t*)d;
+    sv.cand_cursor = sv.out_cursor + 1;
+    if (v.n_pos > INT32_MAX) { ctx->err = "batch too large: submit fewer tiles"; return UVCGPU_EINVAL; }
+    if ((rc = backend_alloc(ctx, bs, &d, (size_t)v.n_pos * sizeof(int32_t), false)) != 0) { return rc; }
+    sv.cand_list = (int32_t*)d;
     int64_t cap = v.n_pos / 16 + 4096;
     std::vector<VarRec> recs;
     for (int attempt = 0; attempt < 2; attempt++) {

@@ -462,7 +462,7 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
             size_t o = oi;
             for (int strand = 0; strand < 2; strand++) {
                 F.frag_off[strand] = (int32_t)hb.frags.size();
-                int32_t s_beg = INT32_MAX, s_end = 0;
+                int32_t s_beg = INT32_MAX, s_end = 0, s_hi = 0;
                 std::vector<int32_t> l2r_end, r2l_end;
                 int64_t qseqlen_sum = 0, n_qseqs = 0;
                 while (o < oj && kept[order[o]].strand == strand) {
@@ -472,25 +472,32 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
                     memset(&G, 0, sizeof(G));
                     G.tile = ti; G.fam = fam_index; G.strand = strand;
                     G.read_off = (int32_t)hb.frag_reads.size(); G.n_reads = (int32_t)(p - o);
-                    int32_t f_beg = INT32_MAX, f_end = 0;
+                    int32_t f_beg = INT32_MAX, f_end = 0, f_hi = 0;
                     for (size_t q = o; q < p; q++) { // stable sort kept file order inside the fragment
                         Kept & k = kept[order[q]];
                         k.fam_local = fam_index; k.frag_local = (int32_t)hb.frags.size();
                         hb.frag_reads.push_back((int32_t)(read_base + order[q]));
                         // fillTidBegEndFromAlns1 (main.hpp:659-673). QUIRK: the exclusive end grows by one per alignment visited.
-                        f_beg = std::min(f_beg, k.r.pos); f_end = std::max(f_end, k.r.rend) + 1;
-                        s_beg = std::min(s_beg, k.r.pos); s_end = std::max(s_end, k.r.rend) + 1;
+                        f_beg = std::min(f_beg, k.r.pos); f_end = std::max(f_end, k.r.rend) + 1; f_hi = std::max(f_hi, k.r.rend);
+                        s_beg = std::min(s_beg, k.r.pos); s_end = std::max(s_end, k.r.rend) + 1; s_hi = std::max(s_hi, k.r.rend);
                         both_beg = std::min(both_beg, k.r.pos); both_end = std::max(both_end, k.r.rend) + 1;
                         G.normMQ = std::max(G.normMQ, (int32_t)k.r.mapq);
                         if (k.r.flag & 0x10) { r2l_end.push_back(k.r.pos); } else { l2r_end.push_back(k.r.rend); }
                         qseqlen_sum += k.r.l_qseq; n_qseqs += 1;
                     }
                     G.beg = f_beg; G.end = f_end;
+                    G.lo = f_beg; G.hi = f_hi;
+                    G.col_off = hb.n_fcol;
+                    hb.n_fcol += ((int64_t)(G.hi - G.lo) + UVC_COL_CHUNK - 1) / UVC_COL_CHUNK * UVC_COL_CHUNK;
                     hb.frags.push_back(G);
                     o = p;
                 }
                 F.n_frags[strand] = (int32_t)hb.frags.size() - F.frag_off[strand];
+                if (F.n_frags[strand] > 65535) { msg = "a molecule family has more than 65535 fragments on one strand (FamCol counts are 16-bit)"; return UVCGPU_EUNSUPPORTED; }
                 F.beg2[strand] = s_beg; F.end2[strand] = s_end;
+                F.lo[strand] = (F.n_frags[strand] > 0 ? s_beg : 0); F.hi[strand] = (F.n_frags[strand] > 0 ? s_hi : 0);
+                F.col_off[strand] = hb.n_mcol;
+                hb.n_mcol += ((int64_t)(F.hi[strand] - F.lo[strand]) + UVC_COL_CHUNK - 1) / UVC_COL_CHUNK * UVC_COL_CHUNK;
                 // MEDIAN of the unsorted vectors (main_conversion.hpp:24-28, main.hpp:2939-2940)
                 F.l2r_end_median[strand] = (l2r_end.size() ? (l2r_end[(l2r_end.size() - 1) / 2] + l2r_end[l2r_end.size() / 2]) / 2 : s_end);
                 F.r2l_end_median[strand] = (r2l_end.size() ? (r2l_end[(r2l_end.size() - 1) / 2] + r2l_end[r2l_end.size() / 2]) / 2 : s_beg);
@@ -604,7 +611,7 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
     uvc_parallel_for(n_tiles, n_threads, [&](int32_t ti) { rcs[ti] = build_tile(part[ti], par, contigs, ti, tiles[ti], sources[tile_source ? tile_source[ti] : 0], center_pow, pem, msgs[ti]); });
     for (int32_t ti = 0; ti < n_tiles; ti++) { if (rcs[ti] != 0) { msg = msgs[ti]; return rcs[ti]; } }
     // 2. offsets of every tile in the concatenated arrays
-    struct Off { int64_t pos, read, frag, fam, fragread, seq, qual, cigar, cx, ev; };
+    struct Off { int64_t pos, read, frag, fam, fragread, seq, qual, cigar, cx, ev, fcol, mcol; };
     std::vector<Off> off((size_t)n_tiles + 1);
     memset(&off[0], 0, sizeof(Off));
     for (int32_t ti = 0; ti < n_tiles; ti++) {
@@ -612,18 +619,19 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
         Off o = off[ti];
         o.pos += b.n_pos; o.read += (int64_t)b.reads.size(); o.frag += (int64_t)b.frags.size(); o.fam += (int64_t)b.fams.size();
         o.fragread += (int64_t)b.frag_reads.size(); o.seq += (int64_t)b.seq.size(); o.qual += (int64_t)b.qual.size(); o.cigar += (int64_t)b.cigar.size();
-        o.cx += b.n_cx; o.ev += b.n_ev;
+        o.cx += b.n_cx; o.ev += b.n_ev; o.fcol += b.n_fcol; o.mcol += b.n_mcol;
         off[ti + 1] = o;
         hb.n_reads_in += b.n_reads_in;
     }
     const Off & tot = off[n_tiles];
-    if (tot.read > INT32_MAX || tot.frag > INT32_MAX || tot.cx > INT32_MAX || tot.ev > INT32_MAX || tot.fragread > INT32_MAX) { msg = "batch too large: submit fewer tiles"; return UVCGPU_EINVAL; }
+    if (tot.read > INT32_MAX || tot.frag > INT32_MAX || tot.cx > INT32_MAX || tot.ev > INT32_MAX || tot.fragread > INT32_MAX || tot.fam > INT32_MAX / 2) { msg = "batch too large: submit fewer tiles"; return UVCGPU_EINVAL; }
     hb.tiles.resize((size_t)n_tiles);
     hb.pos_tile.resize((size_t)tot.pos); hb.refsym.resize((size_t)tot.pos); hb.rtr.resize((size_t)tot.pos); hb.baq.resize((size_t)tot.pos); hb.baq2.resize((size_t)tot.pos);
     hb.reads.resize((size_t)tot.read); hb.read_raw_index.resize((size_t)tot.read);
     hb.seq.resize((size_t)tot.seq); hb.qual.resize((size_t)tot.qual); hb.cigar.resize((size_t)tot.cigar);
     hb.frags.resize((size_t)tot.frag); hb.frag_reads.resize((size_t)tot.fragread); hb.fams.resize((size_t)tot.fam); hb.fam_umi.resize((size_t)tot.fam);
-    hb.n_pos = tot.pos; hb.n_cx = tot.cx; hb.n_ev = tot.ev;
+    hb.n_pos = tot.pos; hb.n_cx = tot.cx; hb.n_ev = tot.ev; hb.n_fcol = tot.fcol; hb.n_mcol = tot.mcol;
+    hb.fchunk_frag.resize((size_t)(tot.fcol / UVC_COL_CHUNK)); hb.mchunk_fs.resize((size_t)(tot.mcol / UVC_COL_CHUNK));
     // 3. concatenation with the tile-local indices rebased, again on all cores (disjoint destination ranges)
     uvc_parallel_for(n_tiles, n_threads, [&](int32_t ti) {
         HostBatch & b = part[ti];
@@ -650,14 +658,21 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
         }
         for (size_t i = 0; i < b.frags.size(); i++) {
             FragRec G = b.frags[i];
-            G.fam += (int32_t)o.fam; G.read_off += (int32_t)o.fragread;
+            G.fam += (int32_t)o.fam; G.read_off += (int32_t)o.fragread; G.col_off += o.fcol;
             hb.frags[(size_t)o.frag + i] = G;
+            const int64_t c1 = G.col_off / UVC_COL_CHUNK + ((int64_t)(G.hi - G.lo) + UVC_COL_CHUNK - 1) / UVC_COL_CHUNK;
+            for (int64_t c = G.col_off / UVC_COL_CHUNK; c < c1; c++) { hb.fchunk_frag[(size_t)c] = (int32_t)(o.frag + (int64_t)i); }
         }
         for (size_t i = 0; i < b.frag_reads.size(); i++) { hb.frag_reads[(size_t)o.fragread + i] = b.frag_reads[i] + (int32_t)o.read; }
         for (size_t i = 0; i < b.fams.size(); i++) {
             FamRec F = b.fams[i];
             F.frag_off[0] += (int32_t)o.frag; F.frag_off[1] += (int32_t)o.frag;
+            F.col_off[0] += o.mcol; F.col_off[1] += o.mcol;
             hb.fams[(size_t)o.fam + i] = F;
+            for (int strand = 0; strand < 2; strand++) {
+                const int64_t c1 = F.col_off[strand] / UVC_COL_CHUNK + ((int64_t)(F.hi[strand] - F.lo[strand]) + UVC_COL_CHUNK - 1) / UVC_COL_CHUNK;
+                for (int64_t c = F.col_off[strand] / UVC_COL_CHUNK; c < c1; c++) { hb.mchunk_fs[(size_t)c] = (int32_t)(2 * (o.fam + (int64_t)i) + strand); }
+            }
             hb.fam_umi[(size_t)o.fam + i].swap(b.fam_umi[i]);
         }
         b = HostBatch();   // release the private copy

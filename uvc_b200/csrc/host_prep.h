@@ -29,6 +29,8 @@ struct HostBatch {
     std::vector<int32_t> frag_reads;
     std::vector<FamRec> fams;
     std::vector<std::string> fam_umi;     // umistring of each family (for the grouping dump)
+    std::vector<int32_t> fchunk_frag, mchunk_fs;   // owner of every 32-entry chunk of the fragment / family-strand columns
+    int64_t n_fcol = 0, n_mcol = 0;       // padded column entries
     int64_t n_pos = 0, n_cx = 0, n_ev = 0;
     int64_t n_reads_in = 0;
 };

@@ -74,6 +74,17 @@ UVC_HD void read_window(const BatchView & v, const TileInfo & T, int32_t p, int6
     hi = a;
 }
 
+// Read window of a position thread. [lo, hi) is the position's own window; [ulo, uhi) is the union over the 32 positions of its warp: every
+// lane walks the union in lock-step (skipping reads outside its own window), so that at each step all lanes look at the SAME read - its
+// record is one broadcast load and the per-position data of that read (column entries, base qualities) are consecutive addresses.
+struct Win { int64_t lo, hi, ulo, uhi; };
+
+UVC_HD void position_window(const BatchView & v, int64_t gp, Win & w) {
+    const TileInfo & T = v.tiles[v.pos_tile[gp]];
+    read_window(v, T, (int32_t)(gp - T.pos_off) + T.ext_beg, w.lo, w.hi);
+    w.ulo = w.lo; w.uhi = w.hi;
+}
+
 // What read R shows at reference position p (pos <= p < rend).
 struct Locus {
     int32_t qpos;       // query index, -1 if not an aligned base
@@ -356,15 +367,14 @@ UVC_HD void k0_read(const BatchView & v, int64_t ri) {
 
 // ------------------------------------------------------------------------------------------------ K1: one thread per position
 // Dense part of walk #1 (main.hpp:1006-1068) gathered per position, then the threshold pass (main.hpp:1206-1299).
-UVC_HD void k1_position(const BatchView & v, int64_t gp) {
+UVC_HD void k1_position(const BatchView & v, int64_t gp, const Win & w) {
     const TileInfo & T = v.tiles[v.pos_tile[gp]];
     const int32_t p = (int32_t)(gp - T.pos_off) + T.ext_beg;
     const uvcgpu_params & par = v.par;
     const int32_t *baq = v.baq + (T.pos_off - T.ext_beg);
     uvcgpu_prep_set a = v.prep[gp];     // starts from the rare-event contributions of K0
-    int64_t lo, hi;
-    read_window(v, T, p, lo, hi);
-    for (int64_t ri = lo; ri < hi; ri++) {
+    for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
+        if (ri < w.lo || ri >= w.hi) { continue; }
         const ReadRec & R = v.reads[ri];
         if (R.rend <= p) { continue; }
         const Locus L = locate(v, R, p);
@@ -589,7 +599,7 @@ UVC_HD int32_t nogap_weight(const BatchView & v, int64_t gp, const ReadDerived &
 // ------------------------------------------------------------------------------------------------ K2: two threads per position
 // Walk #2 (updateByAln<SUM, bias> over aligned bases, main.hpp:1890-2008) gathered per position. role 0 owns the six base symbols,
 // role 1 owns LINK_M. The symbol that matches the reference (role 0) / LINK_M (role 1) is accumulated in registers.
-UVC_HD void k2_position(const BatchView & v, int64_t gp, int role) {
+UVC_HD void k2_position(const BatchView & v, int64_t gp, int role, const Win & w) {
     const TileInfo & T = v.tiles[v.pos_tile[gp]];
     const int32_t p = (int32_t)(gp - T.pos_off) + T.ext_beg;
     const int32_t *baq = v.baq + (T.pos_off - T.ext_beg);
@@ -598,9 +608,8 @@ UVC_HD void k2_position(const BatchView & v, int64_t gp, int role) {
     const int major = (role == 0 ? (int)v.refsym[gp] : UVC_LINK_M);
     SegAcc acc;
     segacc_zero(acc);
-    int64_t lo, hi;
-    read_window(v, T, p, lo, hi);
-    for (int64_t ri = lo; ri < hi; ri++) {
+    for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
+        if (ri < w.lo || ri >= w.hi) { continue; }
         const ReadRec & R = v.reads[ri];
         if (R.rend <= p) { continue; }
         const Locus L = locate(v, R, p);
@@ -950,6 +959,36 @@ UVC_HD int32_t indel_majority_of_reads(const BatchView & v, const int32_t *reads
     return best;
 }
 
+// ------------------------------------------------------------------------------------------------ KF: one thread per fragment-column entry
+// The reference rebuilds the per-fragment symbol array three times (walks #3, #4, #5). Here it is evaluated once per (fragment, position):
+// a warp owns 32 consecutive positions of ONE fragment, so the fragment's read records are warp-uniform and its base qualities are read
+// as consecutive bytes; the entry keeps only what fillConsensusCounts (main.hpp:374-417) yields for the two symbol types.
+UVC_HD void kf_fragment_column(const BatchView & v, int64_t i) {
+    const FragRec & G = v.frags[v.fchunk_frag[i / UVC_COL_CHUNK]];
+    const int32_t o = (int32_t)(i - G.col_off);
+    if (o >= G.hi - G.lo) { return; }
+    const int32_t p = G.lo + o;
+    const TileInfo & T = v.tiles[G.tile];
+    FragCol e;
+    e.link_cc = 0; e.base_cc = 0; e.base_tc = 0; e.link_sym = UVC_LINK_NN; e.base_sym = UVC_BASE_NN;
+    if (frag_covers(v, G, p)) {
+        int32_t c[UVC_NSYM];
+        frag_votes(v, G, p, T.pos_off + (p - T.ext_beg), c);
+        int a; int32_t cc, tc;
+        link_consensus(c, true, a, cc, tc);
+        e.link_sym = (uint8_t)(a | ((c[UVC_BASE_N] | c[UVC_BASE_NN]) ? 0x80 : 0)); e.link_cc = (uint16_t)cc;
+        base_consensus(c, false, a, cc, tc);
+        e.base_sym = (uint8_t)a; e.base_cc = (uint16_t)cc; e.base_tc = (uint16_t)tc;
+    }
+    v.fcol[i] = e;
+}
+
+// the fragment's entry at p (zero entry outside its covered extent)
+UVC_HD FragCol frag_entry(const BatchView & v, const FragRec & G, int32_t p) {
+    if (p < G.lo || p >= G.hi) { FragCol z; z.link_cc = 0; z.base_cc = 0; z.base_tc = 0; z.link_sym = UVC_LINK_NN; z.base_sym = UVC_BASE_NN; return z; }
+    return v.fcol[G.col_off + (p - G.lo)];
+}
+
 // ------------------------------------------------------------------------------------------------ K3a: one thread per fragment
 // Whole-fragment statistics of updateByAlns3UsingBQ (main.hpp:2650-2756): number of covered positions, number of covered positions within
 // +-syserr_mut_region_n_bases of a high-quality mutation, and the fragment's string of mutations (haplotype evidence).
@@ -958,8 +997,7 @@ UVC_HD void k3a_fragment(const BatchView & v, int64_t fi) {
     const TileInfo & T = v.tiles[G.tile];
     const uvcgpu_params & par = v.par;
     const int64_t po = T.pos_off - T.ext_beg;
-    int32_t lo = INT32_MAX, hi = 0;
-    for (int32_t k = 0; k < G.n_reads; k++) { const ReadRec & R = v.reads[v.frag_reads[G.read_off + k]]; lo = tmin(lo, R.pos); hi = tmax(hi, R.rend); }
+    const int32_t lo = G.lo, hi = G.hi;
     const int32_t nb = par.syserr_mut_region_n_bases;
     int32_t n_cov = 0, n_near = 0, n_mut_entries = 0;
     uint32_t hist = 0;                 // coverage flags of the previous nb positions (bit k = position p-1-k)
@@ -974,15 +1012,13 @@ UVC_HD void k3a_fragment(const BatchView & v, int64_t fi) {
             out += 4;
         }
         for (int32_t p = lo; p < hi; p++) {
-            const bool any = frag_covers(v, G, p);
+            const FragCol e = v.fcol[G.col_off + (p - lo)];
             bool cov = false, mut = false;
-            if (any) {
-                int32_t c[UVC_NSYM];
-                frag_votes(v, G, p, po + p, c);
+            if (e.link_cc | e.base_tc) {
                 const int ref = v.refsym[po + p];
                 for (int type = 1; type >= 0; type--) { // SYMBOL_TYPES_IN_VCF_ORDER: link first
-                    int con; int32_t cc, tc;
-                    if (type == 1) { link_consensus(c, true, con, cc, tc); } else { base_consensus(c, false, con, cc, tc); }
+                    const int con = (type == 1 ? (e.link_sym & 0xf) : e.base_sym);
+                    const int32_t cc = (type == 1 ? e.link_cc : e.base_cc), tc = (type == 1 ? e.link_cc : e.base_tc);
                     if (0 == tc) { continue; }
                     cov = true;
                     const int32_t con_qual = cc * 2 - tc;
@@ -1030,30 +1066,30 @@ UVC_HD void infer_max_qual(int32_t & maxvqual, int32_t & argmaxAD, int32_t & arg
 // ------------------------------------------------------------------------------------------------ K3b: one thread per position
 // Fragment-level consensus gathered per position (main.hpp:2620-2733, 2757-2828): bDP, bTA, bTB, bMQ, the quality-bucket histogram and its
 // reduction to bIAQb/bIADb/bIDQb, and the indel identities of fragments whose link consensus is an insertion or deletion.
-UVC_HD void k3b_position(const BatchView & v, int64_t gp) {
+UVC_HD void k3b_position(const BatchView & v, int64_t gp, const Win & w) {
     const TileInfo & T = v.tiles[v.pos_tile[gp]];
     const int32_t p = (int32_t)(gp - T.pos_off) + T.ext_beg;
     const uvcgpu_params & par = v.par;
+    // thread-private accumulators (this thread is the only writer of the position's records): counted here, stored once at the end
     int32_t bucket[UVC_NSYM * UVC_NUM_BUCKETS];
+    int32_t acc[2 * UVC_NSYM * UVCGPU_NUM_FRAG_DEPTHS];
+    int32_t mq[UVC_NSYM], maxq[UVC_NSYM];
     for (int i = 0; i < UVC_NSYM * UVC_NUM_BUCKETS; i++) { bucket[i] = 0; }
-    int32_t *fd0 = v.fragdepth + ((0 * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FRAG_DEPTHS;
-    int32_t *fd1 = v.fragdepth + ((1 * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FRAG_DEPTHS;
-    int32_t *vq = v.vq + gp * UVC_NSYM * UVCGPU_NUM_VQ_TAGS;
+    for (int i = 0; i < 2 * UVC_NSYM * UVCGPU_NUM_FRAG_DEPTHS; i++) { acc[i] = 0; }
+    for (int s = 0; s < UVC_NSYM; s++) { mq[s] = 0; maxq[s] = 8 + avg_bq(v, gp, s); }
     const int ref = v.refsym[gp];
-    int64_t lo, hi;
-    read_window(v, T, p, lo, hi);
-    for (int64_t ri = lo; ri < hi; ri++) {
+    for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
+        if (ri < w.lo || ri >= w.hi) { continue; }
         const ReadRec & R = v.reads[ri];
         if (R.rend <= p || R.fragprev_maxrend > p) { continue; }   // not covering, or an earlier read of the same fragment already handled p
         const FragRec & G = v.frags[R.frag];
-        int32_t c[UVC_NSYM];
-        frag_votes(v, G, p, gp, c);
-        int32_t *fd = (G.strand ? fd1 : fd0);
+        const FragCol e = v.fcol[G.col_off + (p - G.lo)];
+        int32_t *fd = acc + (G.strand ? UVC_NSYM * UVCGPU_NUM_FRAG_DEPTHS : 0);
         for (int type = 1; type >= 0; type--) {
-            int con; int32_t cc, tc;
-            if (type == 1) { link_consensus(c, true, con, cc, tc); } else { base_consensus(c, false, con, cc, tc); }
+            const int con = (type == 1 ? (e.link_sym & 0xf) : e.base_sym);
+            const int32_t cc = (type == 1 ? e.link_cc : e.base_cc), tc = (type == 1 ? e.link_cc : e.base_tc);
             if (0 == tc) { continue; }
-            const int32_t max_qual = 8 + avg_bq(v, gp, con);
+            const int32_t max_qual = maxq[con];
             int32_t phredlike = tmin(cc * 2 - tc, max_qual);
             if (0x1 & par.fam_flag) { phredlike = tmin(phredlike, sscs_phred(par, ref, con)); }
             const int32_t pb = tmax(0, max_qual - phredlike);
@@ -1061,21 +1097,28 @@ UVC_HD void k3b_position(const BatchView & v, int64_t gp) {
             fd[con * UVCGPU_NUM_FRAG_DEPTHS + 0] += 1;
             fd[con * UVCGPU_NUM_FRAG_DEPTHS + 1] += G.n_cov;
             fd[con * UVCGPU_NUM_FRAG_DEPTHS + 2] += G.n_near_mut;
-            vq[con * UVCGPU_NUM_VQ_TAGS + 4] += (G.normMQ * G.normMQ) / UVC_SQR_QUAL_DIV;
+            mq[con] += (G.normMQ * G.normMQ) / UVC_SQR_QUAL_DIV;
             if (is_ins_symbol(con) || is_del_symbol(con)) {
                 const int32_t e = indel_majority_of_reads(v, v.frag_reads + G.read_off, G.n_reads, p, con);
                 if (e >= 0) { rec_put6(v, UVC_REC_FRAG_INDEL, G.strand, con, p, e, 1); }
             }
         }
     }
+    int32_t *vq = v.vq + gp * UVC_NSYM * UVCGPU_NUM_VQ_TAGS;
+    for (int strand = 0; strand < 2; strand++) {
+        int32_t *g = v.fragdepth + ((strand * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FRAG_DEPTHS;
+        const int32_t *a = acc + strand * UVC_NSYM * UVCGPU_NUM_FRAG_DEPTHS;
+        for (int k = 0; k < UVC_NSYM * UVCGPU_NUM_FRAG_DEPTHS; k++) { if (a[k]) { g[k] = a[k]; } }
+    }
     for (int type = 0; type < 2; type++) {
         const int s0 = (type == 0 ? UVC_BASE_A : UVC_LINK_M), s1 = (type == 0 ? UVC_BASE_NN : UVC_LINK_NN);
         int32_t totDP = 0;
-        for (int s = s0; s <= s1; s++) { totDP += fd0[s * UVCGPU_NUM_FRAG_DEPTHS] + fd1[s * UVCGPU_NUM_FRAG_DEPTHS]; }
+        for (int s = s0; s <= s1; s++) { totDP += acc[s * UVCGPU_NUM_FRAG_DEPTHS] + acc[(UVC_NSYM + s) * UVCGPU_NUM_FRAG_DEPTHS]; }
         for (int s = s0; s <= s1; s++) {
+            if (mq[s]) { vq[s * UVCGPU_NUM_VQ_TAGS + 4] = mq[s]; }
             int32_t q, ad, bq;
-            infer_max_qual(q, ad, bq, v, 8 + avg_bq(v, gp, s), 1, bucket + s * UVC_NUM_BUCKETS, totDP);
-            vq[s * UVCGPU_NUM_VQ_TAGS + 5] += q; vq[s * UVCGPU_NUM_VQ_TAGS + 6] += ad; vq[s * UVCGPU_NUM_VQ_TAGS + 7] += bq;
+            infer_max_qual(q, ad, bq, v, maxq[s], 1, bucket + s * UVC_NUM_BUCKETS, totDP);
+            if (q | ad | bq) { vq[s * UVCGPU_NUM_VQ_TAGS + 5] = q; vq[s * UVCGPU_NUM_VQ_TAGS + 6] = ad; vq[s * UVCGPU_NUM_VQ_TAGS + 7] = bq; }
         }
     }
 }
@@ -1090,32 +1133,31 @@ UVC_HD void fam_counts(const BatchView & v, const FamRec & F, int strand, int32_
     const bool ignore_padded_del = (v.par.microadjust_padded_deletion_flag & 0x1); // Illumina/BGI branch of main.hpp:2908
     for (int32_t g = F.frag_off[strand]; g < F.frag_off[strand] + F.n_frags[strand]; g++) {
         const FragRec & G = v.frags[g];
-        if (!frag_covers(v, G, p)) { continue; }
-        int32_t c[UVC_NSYM];
-        frag_votes(v, G, p, gp, c);
-        int a; int32_t cc, tc;
-        link_consensus(c, true, a, cc, tc);
+        if (p < G.lo || p >= G.hi) { continue; }
+        const FragCol e = v.fcol[G.col_off + (p - G.lo)];
+        if (0 == (e.link_cc | e.base_tc)) { continue; }
+        // link: the reference is counted once, so count_sum == count_max and the adjusted quality is the count itself
+        if (e.link_cc > 0) { con[e.link_sym & 0xf] += 1; if (mmm) { mmm[e.link_sym & 0xf] += e.link_cc; } }
+        int a = e.base_sym; int32_t cc = e.base_cc, tc = e.base_tc;
+        if (ignore_padded_del && (e.link_sym & 0x80)) {   // consensus over A..T differs only when N / padded-deletion votes exist: recompute
+            int32_t c[UVC_NSYM];
+            frag_votes(v, G, p, gp, c);
+            base_consensus(c, true, a, cc, tc);
+        }
         int32_t adj = tmax(cc * 2, tc) - tc;
-        if (adj > 0) { con[a] += 1; if (mmm) { mmm[a] += adj; } }
-        base_consensus(c, ignore_padded_del, a, cc, tc);
-        adj = tmax(cc * 2, tc) - tc;
         if (adj >= v.par.fam_thres_highBQ_snv && adj > 0) { con[a] += 1; }
         if (mmm) {
-            base_consensus(c, false, a, cc, tc);
-            adj = tmax(cc * 2, tc) - tc;
-            if (adj > 0) { mmm[a] += adj; }
+            adj = tmax((int32_t)e.base_cc * 2, (int32_t)e.base_tc) - (int32_t)e.base_tc;
+            if (adj > 0) { mmm[e.base_sym] += adj; }
         }
     }
 }
 
 // majority indel event of fragment G at p if its link consensus is `symbol`, else -1
 UVC_HD int32_t frag_link_indel_event(const BatchView & v, const FragRec & G, int32_t p, int64_t gp, int symbol) {
-    if (!frag_covers(v, G, p)) { return -1; }
-    int32_t c[UVC_NSYM];
-    frag_votes(v, G, p, gp, c);
-    int a; int32_t cc, tc;
-    link_consensus(c, true, a, cc, tc);
-    if (a != symbol || 0 == cc) { return -1; }
+    (void)gp;
+    const FragCol e = frag_entry(v, G, p);
+    if ((e.link_sym & 0xf) != symbol || 0 == e.link_cc) { return -1; }
     return indel_majority_of_reads(v, v.frag_reads + G.read_off, G.n_reads, p, symbol);
 }
 
@@ -1148,27 +1190,54 @@ UVC_HD bool fam_is_good(const uvcgpu_params & par, const FamRec & F, int32_t cc,
     return (par.fam_thres_dup1add <= tc) && (cc * 100 >= tc * par.fam_thres_dup1perc) && ((F.duplexflag & 0x1) || (par.fam_flag & 0x2));
 }
 
+// ------------------------------------------------------------------------------------------------ KM: one thread per family-column entry
+// Per (family, strand, position): the fragment votes of the family (read_family_con_ampl / read_family_mmm_ampl of main.hpp:2999-3040, 3392-3420)
+// reduced to the consensus triples that family loop 1, loop 2, the duplex step, the family end scan and the haplotype strings consume.
+// A warp owns 32 consecutive positions of one (family, strand): the fragment entries it reads are consecutive in memory.
+UVC_HD void km_family_column(const BatchView & v, int64_t i) {
+    const int32_t fs = v.mchunk_fs[i / UVC_COL_CHUNK];
+    const FamRec & F = v.fams[fs >> 1];
+    const int strand = (fs & 1);
+    const int32_t o = (int32_t)(i - F.col_off[strand]);
+    if (o >= F.hi[strand] - F.lo[strand]) { return; }
+    const int32_t p = F.lo[strand] + o;
+    const TileInfo & T = v.tiles[F.tile];
+    int32_t con[UVC_NSYM], mmm[UVC_NSYM];
+    fam_counts(v, F, strand, p, T.pos_off + (p - T.ext_beg), con, mmm);
+    FamCol m;
+    for (int type = 0; type < 2; type++) {
+        int a; int32_t cc, tc;
+        plain_consensus(con, type, a, cc, tc);
+        m.a1[type] = (uint8_t)a; m.cc1[type] = (uint16_t)tmin(cc, 65535); m.tc1[type] = (uint16_t)tmin(tc, 65535);
+        plain_consensus(mmm, type, a, cc, tc);
+        m.a2[type] = (uint8_t)a; m.mmm_cc[type] = (uint32_t)cc; m.mmm_tot[type] = (uint32_t)tc; m.con_a2[type] = (uint16_t)tmin(con[a], 65535);
+    }
+    v.mcol[i] = m;
+}
+
+// the entry of (family, strand) at p; all-zero counts outside the strand's covered extent
+UVC_HD FamCol fam_entry(const BatchView & v, const FamRec & F, int strand, int32_t p) {
+    if (p < F.lo[strand] || p >= F.hi[strand]) {
+        FamCol z;
+        for (int t = 0; t < 2; t++) { z.a1[t] = z.a2[t] = (uint8_t)(t ? UVC_LINK_NN : UVC_BASE_NN); z.cc1[t] = z.tc1[t] = z.con_a2[t] = 0; z.mmm_cc[t] = z.mmm_tot[t] = 0; }
+        return z;
+    }
+    return v.mcol[F.col_off[strand] + (p - F.lo[strand])];
+}
+
 // ------------------------------------------------------------------------------------------------ K4a: one thread per (family, strand)
 // no_strict_bias_pos_min/max (main.hpp:2959-2998): the outermost positions, from either end, at which the family forms a tier-2 base consensus.
 UVC_HD void k4a_family_strand(const BatchView & v, int64_t i) {
     FamRec & F = v.fams[i >> 1];
     const int strand = (int)(i & 1);
     if (0 == F.n_frags[strand]) { return; }
-    const TileInfo & T = v.tiles[F.tile];
-    const int64_t po = T.pos_off - T.ext_beg;
     F.nsb_min[strand] = F.end2[strand]; F.nsb_max[strand] = F.beg2[strand];
     if (!F.qlen_ok[strand] || !((F.duplexflag & 0x1) || (v.par.fam_flag & 0x2))) { return; }
-    int32_t lo = INT32_MAX, hi = 0;   // covered extent (positions outside have no votes)
-    for (int32_t g = F.frag_off[strand]; g < F.frag_off[strand] + F.n_frags[strand]; g++) {
-        const FragRec & G = v.frags[g];
-        for (int32_t k = 0; k < G.n_reads; k++) { const ReadRec & R = v.reads[v.frag_reads[G.read_off + k]]; lo = tmin(lo, R.pos); hi = tmax(hi, R.rend); }
-    }
+    const int32_t lo = F.lo[strand], hi = F.hi[strand];   // covered extent (positions outside have no votes)
     for (int dir = 0; dir < 2; dir++) {
         for (int32_t p = (dir ? hi - 1 : lo); (dir ? p >= lo : p < hi); p += (dir ? -1 : 1)) {
-            int32_t con[UVC_NSYM];
-            fam_counts(v, F, strand, p, po + p, con, NULL);
-            int a; int32_t cc, tc;
-            base_consensus(con, false, a, cc, tc);
+            const FamCol m = v.mcol[F.col_off[strand] + (p - lo)];
+            const int a = m.a1[0]; const int32_t cc = m.cc1[0], tc = m.tc1[0];
             if (0 == tc) { continue; }
             if (fam_is_good(v.par, F, cc, tc) && (UVC_BASE_N != a) && (UVC_BASE_NN != a)) {
                 if (dir) { F.nsb_max[strand] = p; } else { F.nsb_min[strand] = p; }
@@ -1181,7 +1250,7 @@ UVC_HD void k4a_family_strand(const BatchView & v, int64_t i) {
 // ------------------------------------------------------------------------------------------------ K4: one thread per position
 // updateByAlns3UsingFQ gathered per position: family loop 1 (main.hpp:2999-3355), then - because its only cross-family dependence, cDPM/cDPm,
 // is per position - family loop 2 (main.hpp:3392-3551) and the per-strand reduction of the quality buckets (main.hpp:3552-3591).
-UVC_HD void k4_position(const BatchView & v, int64_t gp) {
+UVC_HD void k4_position(const BatchView & v, int64_t gp, const Win & w) {
     const TileInfo & T = v.tiles[v.pos_tile[gp]];
     const int32_t p = (int32_t)(gp - T.pos_off) + T.ext_beg;
     const uvcgpu_params & par = v.par;
@@ -1189,29 +1258,28 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp) {
     const int32_t *baq = v.baq + po;
     const int32_t *baq2 = v.baq2 + po;
     const int ref = v.refsym[gp];
-    int32_t *fam0 = v.famdepth + ((0 * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FAM_DEPTHS;
-    int32_t *fam1 = v.famdepth + ((1 * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FAM_DEPTHS;
+    // thread-private family depth counters (this thread is the position's only writer): stored once at the end
+    int32_t facc[2 * UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS];
+    for (int i = 0; i < 2 * UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS; i++) { facc[i] = 0; }
+    int32_t *fam0 = facc, *fam1 = facc + UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS;
     uvcgpu_faminfo_set *finfo = v.faminfo + gp * UVC_NSYM;
     int32_t *dup = v.duplex + gp * UVC_NSYM * UVCGPU_NUM_DUPLEX_DEPTHS;
     int32_t *vq = v.vq + gp * UVC_NSYM * UVCGPU_NUM_VQ_TAGS;
     const uvcgpu_thres_set th = v.thres[gp];
     const int32_t baq_last = T.ext_end - 1;
     enum { cDP1 = 0, cDP12 = 1, cDP2 = 2, cDP3 = 3, cDPM = 4, cDPm = 5, cDP21 = 6, cDPD = 7 };
-    int64_t lo, hi;
-    read_window(v, T, p, lo, hi);
 
     // ---- loop 1
-    for (int64_t ri = lo; ri < hi; ri++) {
+    for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
+        if (ri < w.lo || ri >= w.hi) { continue; }
         const ReadRec & R = v.reads[ri];
         if (R.rend <= p || R.famprev_maxrend > p) { continue; }
         const FamRec & F = v.fams[R.fam];
         const int strand = R.strand;
         int32_t *fd = (strand ? fam1 : fam0);
-        int32_t con[UVC_NSYM];
-        fam_counts(v, F, strand, p, gp, con, NULL);
+        const FamCol m = v.mcol[F.col_off[strand] + (p - F.lo[strand])];
         for (int type = 1; type >= 0; type--) {
-            int a; int32_t cc, tc;
-            plain_consensus(con, type, a, cc, tc);
+            const int a = m.a1[type]; const int32_t cc = m.cc1[type], tc = m.tc1[type];
             if (0 == tc) { continue; }
             fd[a * UVCGPU_NUM_FAM_DEPTHS + cDP12] += 1;
             if (1 == tc) { fd[a * UVCGPU_NUM_FAM_DEPTHS + cDP21] += 1; }
@@ -1271,10 +1339,10 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp) {
             const int32_t perc = (is_subst ? par.fam_thres_emperr_con_perc_snv : par.fam_thres_emperr_con_perc_indel);
             if (tc < flat) { continue; }
             if (cc * 100 < tc * perc) { continue; }
-            const int s0 = (type == 0 ? UVC_BASE_A : UVC_LINK_M), s1 = (type == 0 ? UVC_BASE_NN : UVC_LINK_NN);
-            for (int s = s0; s <= s1; s++) {
-                if (s != a) { fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPm] += con[s]; fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPM] += tc; } // QUIRK: tc once per other symbol
-            }
+            // every other symbol of the type adds its own count to cDPm and, QUIRK, the whole total to cDPM (main.hpp:3343-3352)
+            const int32_t n_other = (type == 0 ? (UVC_BASE_NN - UVC_BASE_A) : (UVC_LINK_NN - UVC_LINK_M));
+            fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPm] += tc - cc;
+            fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPM] += tc * n_other;
         }
     }
 
@@ -1282,7 +1350,8 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp) {
     int32_t bucket[2 * UVC_NSYM * UVC_NUM_BUCKETS];
     for (int i = 0; i < 2 * UVC_NSYM * UVC_NUM_BUCKETS; i++) { bucket[i] = 0; }
     const int32_t tn_add = (par.is_tumor_vcf_provided ? 4 : 0);
-    for (int64_t ri = lo; ri < hi; ri++) {
+    for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
+        if (ri < w.lo || ri >= w.hi) { continue; }
         const ReadRec & R = v.reads[ri];
         if (R.rend <= p) { continue; }
         const FamRec & F = v.fams[R.fam];
@@ -1292,16 +1361,12 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp) {
         if (R.famprev_maxrend <= p) {   // first read of its (family, strand) that covers p
             const int strand = R.strand;
             int32_t *fd = (strand ? fam1 : fam0);
-            int32_t con[UVC_NSYM], mmm[UVC_NSYM];
-            fam_counts(v, F, strand, p, gp, con, mmm);
+            const FamCol m = v.mcol[F.col_off[strand] + (p - F.lo[strand])];
             for (int type = 1; type >= 0; type--) {
-                int a; int32_t con_sumBQs, tot_sumBQs;
-                plain_consensus(mmm, type, a, con_sumBQs, tot_sumBQs);
+                const int a = m.a2[type]; const int32_t con_sumBQs = (int32_t)m.mmm_cc[type], tot_sumBQs = (int32_t)m.mmm_tot[type];
                 if (0 == tot_sumBQs) { continue; }
-                const int s0 = (type == 0 ? UVC_BASE_A : UVC_LINK_M), s1 = (type == 0 ? UVC_BASE_NN : UVC_LINK_NN);
-                const int32_t con_nfrags = con[a];
-                int32_t tot_nfrags = 0;
-                for (int s = s0; s <= s1; s++) { tot_nfrags += con[s]; }
+                const int32_t con_nfrags = m.con_a2[type];
+                const int32_t tot_nfrags = m.tc1[type];
                 fd[a * UVCGPU_NUM_FAM_DEPTHS + cDP1] += 1;
                 if (will_inc_sscs && (tot_nfrags >= par.fam_thres_dup1add) && (con_nfrags * 100 >= tot_nfrags * par.fam_thres_dup1perc)) {
                     fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPD] += 1;
@@ -1336,11 +1401,9 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp) {
             votes_zero(dcount);
             int link_con[2] = {-1, -1};
             for (int strand = 0; strand < 2; strand++) {
-                int32_t con[UVC_NSYM];
-                fam_counts(v, F, strand, p, gp, con, NULL);
+                const FamCol m = fam_entry(v, F, strand, p);
                 for (int type = 1; type >= 0; type--) {
-                    int a; int32_t cc, tc;
-                    plain_consensus(con, type, a, cc, tc);
+                    const int a = m.a1[type]; const int32_t cc = m.cc1[type], tc = m.tc1[type];
                     const int32_t adj = tmax(cc * 2, tc) - tc;
                     if (adj >= 1 && adj > 0) { dcount[a] += 1; }
                     if (type == 1 && cc > 0) { link_con[strand] = a; }
@@ -1374,9 +1437,11 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp) {
             for (int s = s0; s <= s1; s++) {
                 int32_t q, ad, bq;
                 infer_max_qual(q, ad, bq, v, sscs_phred(par, ref, s) + tn_add, 4, bucket + (strand * UVC_NSYM + s) * UVC_NUM_BUCKETS, totDP);
-                vq[s * UVCGPU_NUM_VQ_TAGS + 8 + 3 * strand] += q; vq[s * UVCGPU_NUM_VQ_TAGS + 9 + 3 * strand] += ad; vq[s * UVCGPU_NUM_VQ_TAGS + 10 + 3 * strand] += bq;
+                if (q | ad | bq) { vq[s * UVCGPU_NUM_VQ_TAGS + 8 + 3 * strand] = q; vq[s * UVCGPU_NUM_VQ_TAGS + 9 + 3 * strand] = ad; vq[s * UVCGPU_NUM_VQ_TAGS + 10 + 3 * strand] = bq; }
             }
         }
+        int32_t *g = v.famdepth + ((strand * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FAM_DEPTHS;
+        for (int k = 0; k < UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS; k++) { if (fd[k]) { g[k] = fd[k]; } }
     }
 }
 
@@ -1391,11 +1456,7 @@ UVC_HD void k4c_family_strand(const BatchView & v, int64_t i) {
     const uvcgpu_params & par = v.par;
     const int64_t po = T.pos_off - T.ext_beg;
     enum { cDPM = 4, cDPm = 5 };
-    int32_t lo = INT32_MAX, hi = 0;
-    for (int32_t g = F.frag_off[strand]; g < F.frag_off[strand] + F.n_frags[strand]; g++) {
-        const FragRec & G = v.frags[g];
-        for (int32_t k = 0; k < G.n_reads; k++) { const ReadRec & R = v.reads[v.frag_reads[G.read_off + k]]; lo = tmin(lo, R.pos); hi = tmax(hi, R.rend); }
-    }
+    const int32_t lo = F.lo[strand], hi = F.hi[strand];
     int32_t n_fq = 0, n_f2q = 0;
     for (int pass = 0; pass < 2; pass++) {
         int32_t out_fq = -1, out_f2q = -1;
@@ -1413,19 +1474,15 @@ UVC_HD void k4c_family_strand(const BatchView & v, int64_t i) {
         for (int32_t p = lo; p < hi; p++) {
             const int64_t gp = po + p;
             const int ref = v.refsym[gp];
-            int32_t con[UVC_NSYM], mmm[UVC_NSYM];
-            fam_counts(v, F, strand, p, gp, con, mmm);
+            const FamCol m = v.mcol[F.col_off[strand] + (p - lo)];
             const int32_t *fd = v.famdepth + ((strand * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FAM_DEPTHS;
             for (int type = 1; type >= 0; type--) {
-                int a; int32_t con_sumBQs, tot_sumBQs;
-                plain_consensus(mmm, type, a, con_sumBQs, tot_sumBQs);
+                const int a = m.a2[type]; const int32_t con_sumBQs = (int32_t)m.mmm_cc[type], tot_sumBQs = (int32_t)m.mmm_tot[type];
                 if (0 == tot_sumBQs || !symbols_mutated(ref, a)) { continue; }
                 bool high = (type == 1);
                 if (!high) {
-                    const int s0 = UVC_BASE_A, s1 = UVC_BASE_NN;
-                    const int32_t con_nfrags = con[a];
-                    int32_t tot_nfrags = 0;
-                    for (int s = s0; s <= s1; s++) { tot_nfrags += con[s]; }
+                    const int32_t con_nfrags = m.con_a2[type];
+                    const int32_t tot_nfrags = m.tc1[type];
                     const int32_t avgBQ = ((0 == tot_nfrags) ? 1 : (con_sumBQs / tot_nfrags));
                     const int32_t majorcount = fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPM], minorcount = fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPm];
                     const double prior_weight = 1.0 / (minorcount + 1.0);
@@ -1436,8 +1493,7 @@ UVC_HD void k4c_family_strand(const BatchView & v, int64_t i) {
                     high = (confam_qual >= par.bias_thres_highBQ);
                 }
                 if (!high) { continue; }
-                int a1; int32_t cc1, tc1;
-                plain_consensus(con, type, a1, cc1, tc1);
+                const int a1 = m.a1[type]; const int32_t cc1 = m.cc1[type], tc1 = m.tc1[type];
                 const bool confam = (a == a1 && par.fam_thres_dup1add <= tc1 && (cc1 * 100 >= tc1 * par.fam_thres_dup1perc));
                 if (pass == 0) { n_fq++; if (confam) { n_f2q++; } }
                 else {

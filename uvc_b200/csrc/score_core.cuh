@@ -86,6 +86,8 @@ struct ScoreView {
     VarRec *out; int32_t *out_cursor; int32_t out_cap;
     GvcfPos *gvcf;          // [n_pos]
     GvcfExtra *gextra;      // [n_pos]
+    int32_t *cand_list;     // [n_pos] zero-based positions that have at least one candidate allele (compacted by K5a; order is irrelevant)
+    int32_t *cand_cursor;   // out_cursor[1]
 };
 
 namespace uvc {
@@ -904,6 +906,48 @@ UVC_HD int allele_string_cmp(const BatchView & v, const CandFmt & a, const CandF
     return (ea.oplen > eb.oplen) - (ea.oplen < eb.oplen);
 }
 
+// ------------------------------------------------------------------------------------------------ K5a: one thread per zero-based position
+// The candidate test of the reference's per-position loop (main.cpp:832-837): a symbol is a candidate if it is an alternative allele with at
+// least min_altdp_thres fragments, or the reference allele next to at least that many non-reference fragments. Most positions have none, so
+// the positions that do are compacted into a list and the heavy scoring kernel (K5) runs on full warps of candidate positions only.
+UVC_HD bool symbol_is_candidate(const uvcgpu_params & par, int refsymbol, int symbol, int32_t bdepth, int32_t BDP, int32_t ref_bdepth) {
+    return !((((refsymbol != symbol) && (bdepth < par.min_altdp_thres)) || ((refsymbol == symbol) && (BDP - ref_bdepth < par.min_altdp_thres))) && (!par.should_output_all));
+}
+
+UVC_HD void k5a_flag_position(const BatchView & v, const ScoreView & sv, int64_t gp_zb) {
+    const TileInfo & T = v.tiles[v.pos_tile[gp_zb]];
+    if (T.skipped) { return; }
+    const int32_t zb = (int32_t)(gp_zb - T.pos_off) + T.ext_beg;
+    if (zb < T.rpos_inclu_beg || zb > T.rpos_exclu_end) { return; }
+    const uvcgpu_params & par = v.par;
+    const int32_t nref = (T.ext_end - T.ext_beg) - 1;
+    const uint8_t *refsyms = v.refsym + T.pos_off;
+    const int refsym_base = ((nref == (zb - 1 - T.ext_beg)) || (-1 == (zb - 1 - T.ext_beg))) ? UVC_BASE_NN : (int)refsyms[zb - 1 - T.ext_beg];
+    bool any = false;
+    for (int type = 0; type < 2 && !any; type++) {
+        if (zb == T.rpos_inclu_beg && type == 0) { continue; }
+        const int32_t refpos = (type == 0 ? zb - 1 : zb);
+        const int64_t gp = T.pos_off + (refpos - T.ext_beg);
+        const int refsymbol = (type == 0 ? refsym_base : UVC_LINK_M);
+        const int32_t *fd0 = v.fragdepth + ((0 * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FRAG_DEPTHS;
+        const int32_t *fd1 = v.fragdepth + ((1 * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FRAG_DEPTHS;
+        int32_t BDP = 0;
+        for (int k = 0; k < type_nsym(type); k++) { const int sy = type_symbol(type, k); BDP += fd0[sy * 3] + fd1[sy * 3]; }
+        const int32_t ref_bdepth = fd0[refsymbol * 3] + fd1[refsymbol * 3];
+        for (int k = 0; k < type_nsym(type); k++) {
+            const int sy = type_symbol(type, k);
+            if (symbol_is_candidate(par, refsymbol, sy, fd0[sy * 3] + fd1[sy * 3], BDP, ref_bdepth)) { any = true; break; }
+        }
+    }
+    if (!any) { return; }
+#if defined(__CUDA_ARCH__)
+    const int32_t slot = atomicAdd(sv.cand_cursor, 1);
+#else
+    const int32_t slot = *sv.cand_cursor; *sv.cand_cursor += 1;
+#endif
+    sv.cand_list[slot] = (int32_t)gp_zb;
+}
+
 // ------------------------------------------------------------------------------------------------ K5: one thread per zero-based position
 // One iteration of the reference's per-position loop (main.cpp:608-1172) without the text.
 UVC_HD void k5_score_position(const BatchView & v, const ScoreView & sv, int64_t gp_zb) {
@@ -955,7 +999,7 @@ UVC_HD void k5_score_position(const BatchView & v, const ScoreView & sv, int64_t
                                  + tmax(P.fm1[symbol * UVCGPU_NUM_FAM_DEPTHS + 0], P.fm1[symbol * UVCGPU_NUM_FAM_DEPTHS + 1]);
             if (is_ins_symbol(symbol)) { ins_cdepth += cdepth; if (UVC_LINK_I1 == symbol) { ins1_cdepth += cdepth; } }
             else if (is_del_symbol(symbol)) { del_cdepth += cdepth; if (UVC_LINK_D1 == symbol) { del1_cdepth += cdepth; } }
-            if ((((refsymbol != symbol) && (bdepth < par.min_altdp_thres)) || ((refsymbol == symbol) && (BDP - ref_bdepth < par.min_altdp_thres))) && (!par.should_output_all)) { continue; }
+            if (!symbol_is_candidate(par, refsymbol, symbol, bdepth, BDP, ref_bdepth)) { continue; }
             const bool is_homopol_1bp = (prev_base1 == refsymbol && next_base1 == refsymbol);
             const bool is_homopol_2bp = (prev_base2 == refsymbol && next_base2 == refsymbol);
             const int32_t minABQ = (is_subst(symbol) ? nnminus(minABQ_snv, (is_homopol_1bp ? (is_homopol_2bp ? 20 : 10) : 0)) : minABQ_indel);
