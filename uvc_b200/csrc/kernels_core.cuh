@@ -1071,12 +1071,12 @@ UVC_HD void k3b_position(const BatchView & v, int64_t gp, const Win & w) {
     const int32_t p = (int32_t)(gp - T.pos_off) + T.ext_beg;
     const uvcgpu_params & par = v.par;
     // thread-private accumulators (this thread is the only writer of the position's records): counted here, stored once at the end
+    // Only a few of the 14 symbols ever occur at one position, so the private arrays are zeroed lazily, per symbol, on first touch
+    // (bit s of `touched`), and only touched symbols are reduced and stored: the local-memory traffic follows the data, not the array size.
     int32_t bucket[UVC_NSYM * UVC_NUM_BUCKETS];
     int32_t acc[2 * UVC_NSYM * UVCGPU_NUM_FRAG_DEPTHS];
     int32_t mq[UVC_NSYM], maxq[UVC_NSYM];
-    for (int i = 0; i < UVC_NSYM * UVC_NUM_BUCKETS; i++) { bucket[i] = 0; }
-    for (int i = 0; i < 2 * UVC_NSYM * UVCGPU_NUM_FRAG_DEPTHS; i++) { acc[i] = 0; }
-    for (int s = 0; s < UVC_NSYM; s++) { mq[s] = 0; maxq[s] = 8 + avg_bq(v, gp, s); }
+    uint32_t touched = 0;
     const int ref = v.refsym[gp];
     for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
         if (ri < w.lo || ri >= w.hi) { continue; }
@@ -1089,6 +1089,12 @@ UVC_HD void k3b_position(const BatchView & v, int64_t gp, const Win & w) {
             const int con = (type == 1 ? (e.link_sym & 0xf) : e.base_sym);
             const int32_t cc = (type == 1 ? e.link_cc : e.base_cc), tc = (type == 1 ? e.link_cc : e.base_tc);
             if (0 == tc) { continue; }
+            if (!((touched >> con) & 1u)) {
+                touched |= (1u << con);
+                for (int k = 0; k < UVC_NUM_BUCKETS; k++) { bucket[con * UVC_NUM_BUCKETS + k] = 0; }
+                for (int k = 0; k < UVCGPU_NUM_FRAG_DEPTHS; k++) { acc[con * UVCGPU_NUM_FRAG_DEPTHS + k] = 0; acc[(UVC_NSYM + con) * UVCGPU_NUM_FRAG_DEPTHS + k] = 0; }
+                mq[con] = 0; maxq[con] = 8 + avg_bq(v, gp, con);
+            }
             const int32_t max_qual = maxq[con];
             int32_t phredlike = tmin(cc * 2 - tc, max_qual);
             if (0x1 & par.fam_flag) { phredlike = tmin(phredlike, sscs_phred(par, ref, con)); }
@@ -1105,20 +1111,20 @@ UVC_HD void k3b_position(const BatchView & v, int64_t gp, const Win & w) {
         }
     }
     int32_t *vq = v.vq + gp * UVC_NSYM * UVCGPU_NUM_VQ_TAGS;
-    for (int strand = 0; strand < 2; strand++) {
-        int32_t *g = v.fragdepth + ((strand * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FRAG_DEPTHS;
-        const int32_t *a = acc + strand * UVC_NSYM * UVCGPU_NUM_FRAG_DEPTHS;
-        for (int k = 0; k < UVC_NSYM * UVCGPU_NUM_FRAG_DEPTHS; k++) { if (a[k]) { g[k] = a[k]; } }
-    }
     for (int type = 0; type < 2; type++) {
         const int s0 = (type == 0 ? UVC_BASE_A : UVC_LINK_M), s1 = (type == 0 ? UVC_BASE_NN : UVC_LINK_NN);
         int32_t totDP = 0;
-        for (int s = s0; s <= s1; s++) { totDP += acc[s * UVCGPU_NUM_FRAG_DEPTHS] + acc[(UVC_NSYM + s) * UVCGPU_NUM_FRAG_DEPTHS]; }
+        for (int s = s0; s <= s1; s++) { if ((touched >> s) & 1u) { totDP += acc[s * UVCGPU_NUM_FRAG_DEPTHS] + acc[(UVC_NSYM + s) * UVCGPU_NUM_FRAG_DEPTHS]; } }
         for (int s = s0; s <= s1; s++) {
-            if (mq[s]) { vq[s * UVCGPU_NUM_VQ_TAGS + 4] = mq[s]; }
+            if (!((touched >> s) & 1u)) { continue; }
+            for (int strand = 0; strand < 2; strand++) {
+                int32_t *g = v.fragdepth + ((strand * v.n_pos + gp) * UVC_NSYM + s) * UVCGPU_NUM_FRAG_DEPTHS;
+                for (int k = 0; k < UVCGPU_NUM_FRAG_DEPTHS; k++) { g[k] = acc[(strand * UVC_NSYM + s) * UVCGPU_NUM_FRAG_DEPTHS + k]; }
+            }
+            vq[s * UVCGPU_NUM_VQ_TAGS + 4] = mq[s];
             int32_t q, ad, bq;
             infer_max_qual(q, ad, bq, v, maxq[s], 1, bucket + s * UVC_NUM_BUCKETS, totDP);
-            if (q | ad | bq) { vq[s * UVCGPU_NUM_VQ_TAGS + 5] = q; vq[s * UVCGPU_NUM_VQ_TAGS + 6] = ad; vq[s * UVCGPU_NUM_VQ_TAGS + 7] = bq; }
+            vq[s * UVCGPU_NUM_VQ_TAGS + 5] = q; vq[s * UVCGPU_NUM_VQ_TAGS + 6] = ad; vq[s * UVCGPU_NUM_VQ_TAGS + 7] = bq;
         }
     }
 }
@@ -1259,8 +1265,13 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp, const Win & w) {
     const int32_t *baq2 = v.baq2 + po;
     const int ref = v.refsym[gp];
     // thread-private family depth counters (this thread is the position's only writer): stored once at the end
+    // zeroed lazily per (strand, symbol) on first touch (bit strand * 14 + symbol of `touched`), see K3b
     int32_t facc[2 * UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS];
-    for (int i = 0; i < 2 * UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS; i++) { facc[i] = 0; }
+    int32_t bucket[2 * UVC_NSYM * UVC_NUM_BUCKETS];
+    uint32_t touched = 0;
+    #define UVC_K4_TOUCH(strand_, sym_) { const int ix_ = (strand_) * UVC_NSYM + (sym_); if (!((touched >> ix_) & 1u)) { touched |= (1u << ix_); \
+        for (int k_ = 0; k_ < UVCGPU_NUM_FAM_DEPTHS; k_++) { facc[ix_ * UVCGPU_NUM_FAM_DEPTHS + k_] = 0; } \
+        for (int k_ = 0; k_ < UVC_NUM_BUCKETS; k_++) { bucket[ix_ * UVC_NUM_BUCKETS + k_] = 0; } } }
     int32_t *fam0 = facc, *fam1 = facc + UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS;
     uvcgpu_faminfo_set *finfo = v.faminfo + gp * UVC_NSYM;
     int32_t *dup = v.duplex + gp * UVC_NSYM * UVCGPU_NUM_DUPLEX_DEPTHS;
@@ -1281,6 +1292,7 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp, const Win & w) {
         for (int type = 1; type >= 0; type--) {
             const int a = m.a1[type]; const int32_t cc = m.cc1[type], tc = m.tc1[type];
             if (0 == tc) { continue; }
+            UVC_K4_TOUCH(strand, a)
             fd[a * UVCGPU_NUM_FAM_DEPTHS + cDP12] += 1;
             if (1 == tc) { fd[a * UVCGPU_NUM_FAM_DEPTHS + cDP21] += 1; }
             const bool is_indel = (is_ins_symbol(a) || is_del_symbol(a));
@@ -1347,8 +1359,6 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp, const Win & w) {
     }
 
     // ---- loop 2
-    int32_t bucket[2 * UVC_NSYM * UVC_NUM_BUCKETS];
-    for (int i = 0; i < 2 * UVC_NSYM * UVC_NUM_BUCKETS; i++) { bucket[i] = 0; }
     const int32_t tn_add = (par.is_tumor_vcf_provided ? 4 : 0);
     for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
         if (ri < w.lo || ri >= w.hi) { continue; }
@@ -1367,6 +1377,7 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp, const Win & w) {
                 if (0 == tot_sumBQs) { continue; }
                 const int32_t con_nfrags = m.con_a2[type];
                 const int32_t tot_nfrags = m.tc1[type];
+                UVC_K4_TOUCH(strand, a)
                 fd[a * UVCGPU_NUM_FAM_DEPTHS + cDP1] += 1;
                 if (will_inc_sscs && (tot_nfrags >= par.fam_thres_dup1add) && (con_nfrags * 100 >= tot_nfrags * par.fam_thres_dup1perc)) {
                     fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPD] += 1;
@@ -1433,16 +1444,18 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp, const Win & w) {
         for (int type = 0; type < 2; type++) {
             const int s0 = (type == 0 ? UVC_BASE_A : UVC_LINK_M), s1 = (type == 0 ? UVC_BASE_NN : UVC_LINK_NN);
             int32_t totDP = 0;
-            for (int s = s0; s <= s1; s++) { totDP += fd[s * UVCGPU_NUM_FAM_DEPTHS + cDP1]; }
+            for (int s = s0; s <= s1; s++) { if ((touched >> (strand * UVC_NSYM + s)) & 1u) { totDP += fd[s * UVCGPU_NUM_FAM_DEPTHS + cDP1]; } }
             for (int s = s0; s <= s1; s++) {
+                if (!((touched >> (strand * UVC_NSYM + s)) & 1u)) { continue; }
                 int32_t q, ad, bq;
                 infer_max_qual(q, ad, bq, v, sscs_phred(par, ref, s) + tn_add, 4, bucket + (strand * UVC_NSYM + s) * UVC_NUM_BUCKETS, totDP);
-                if (q | ad | bq) { vq[s * UVCGPU_NUM_VQ_TAGS + 8 + 3 * strand] = q; vq[s * UVCGPU_NUM_VQ_TAGS + 9 + 3 * strand] = ad; vq[s * UVCGPU_NUM_VQ_TAGS + 10 + 3 * strand] = bq; }
+                vq[s * UVCGPU_NUM_VQ_TAGS + 8 + 3 * strand] = q; vq[s * UVCGPU_NUM_VQ_TAGS + 9 + 3 * strand] = ad; vq[s * UVCGPU_NUM_VQ_TAGS + 10 + 3 * strand] = bq;
+                int32_t *g = v.famdepth + ((strand * v.n_pos + gp) * UVC_NSYM + s) * UVCGPU_NUM_FAM_DEPTHS;
+                for (int k = 0; k < UVCGPU_NUM_FAM_DEPTHS; k++) { g[k] = fd[s * UVCGPU_NUM_FAM_DEPTHS + k]; }
             }
         }
-        int32_t *g = v.famdepth + ((strand * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FAM_DEPTHS;
-        for (int k = 0; k < UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS; k++) { if (fd[k]) { g[k] = fd[k]; } }
     }
+    #undef UVC_K4_TOUCH
 }
 
 // ------------------------------------------------------------------------------------------------ K4c: one thread per (family, strand)
