@@ -54,12 +54,12 @@ struct BatchState {
     bool collected = false;
     bool sparse_built = false;
     std::vector<TileSparse> sparse;
-    std::vector<IndelEvent> ev_host;
+    StageVec<IndelEvent> ev_host;
     bool scored = false;
     std::vector<TileIndelSites> sites;
     std::vector<std::vector<VarRec>> recs_by_tile;
-    std::vector<GvcfPos> gvcf;
-    std::vector<GvcfExtra> gextra;
+    StageVec<GvcfPos> gvcf;
+    StageVec<GvcfExtra> gextra;
 #if UVC_CUDA
     cudaEvent_t ev[UVC_N_PILEUP_STAGES + 1];
     bool have_events = false;
@@ -82,6 +82,88 @@ struct uvcgpu_ctx {
     cudaStream_t stream = nullptr;
 #endif
 };
+
+// ------------------------------------------------------------------------------------------------ staging memory (see host_prep.h)
+// Page-locking memory is slow (~1 GB/s), so it is never done on the critical path: a request that finds no cached page-locked block of its
+// size class is served from pageable memory at once, and a background thread page-locks a block of that class for the NEXT batch. Short
+// runs therefore start immediately, long runs converge to fully page-locked staging (asynchronous DMA both ways).
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <unordered_map>
+namespace {
+const size_t kStageSmall = (size_t)1 << 20;
+const size_t kStageMaxPinned = (size_t)24 << 30;
+struct StageState {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::multimap<size_t, void*> free_blocks;         // size class -> cached page-locked blocks
+    std::unordered_map<void*, size_t> pinned;         // every page-locked block (handed out or cached) -> its size class
+    std::deque<size_t> wanted;                        // size classes the provisioning thread should page-lock
+    size_t total_pinned = 0;
+    bool thread_started = false;
+};
+StageState & stage_state() { static StageState *s = new StageState(); return *s; }   // leaked on purpose: used by a detached thread
+size_t stage_class(size_t bytes) {                    // next of {1, 1.25, 1.5, 1.75} x 2^k
+    size_t p2 = kStageSmall;
+    while (p2 * 2 <= bytes) { p2 *= 2; }
+    for (int q = 4; q <= 8; q++) { const size_t c = p2 / 4 * q; if (c >= bytes) { return c; } }
+    return p2 * 2;
+}
+#if UVC_CUDA
+void stage_provision_loop() {
+    StageState & st = stage_state();
+    for (;;) {
+        size_t cls = 0;
+        {
+            std::unique_lock<std::mutex> lk(st.mu);
+            st.cv.wait(lk, [&]() { return !st.wanted.empty(); });
+            cls = st.wanted.front(); st.wanted.pop_front();
+            if (st.total_pinned + cls > kStageMaxPinned) { continue; }
+            st.total_pinned += cls;
+        }
+        void *p = NULL;
+        if (cudaHostAlloc(&p, cls, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); std::lock_guard<std::mutex> lk(st.mu); st.total_pinned -= cls; continue; }
+        std::lock_guard<std::mutex> lk(st.mu);
+        st.pinned[p] = cls;
+        st.free_blocks.insert(std::make_pair(cls, p));
+    }
+}
+#endif
+}
+static thread_local bool g_stage_pinning = true;
+void uvc_stage_thread_pinning(bool enabled) { g_stage_pinning = enabled; }
+void *uvc_stage_alloc(size_t bytes) {
+    if (0 == bytes) { bytes = 1; }
+    if (bytes < kStageSmall || !g_stage_pinning) { return malloc(bytes); }
+#if UVC_CUDA
+    StageState & st = stage_state();
+    const size_t cls = stage_class(bytes);
+    {
+        std::lock_guard<std::mutex> lk(st.mu);
+        auto it = st.free_blocks.find(cls);
+        if (it != st.free_blocks.end()) { void *p = it->second; st.free_blocks.erase(it); return p; }
+        st.wanted.push_back(cls);
+        if (!st.thread_started) { st.thread_started = true; std::thread(stage_provision_loop).detach(); }
+    }
+    st.cv.notify_one();
+#endif
+    return malloc(bytes);
+}
+void uvc_stage_free(void *p, size_t bytes) {
+    if (NULL == p) { return; }
+    (void)bytes;
+#if UVC_CUDA
+    {
+        StageState & st = stage_state();
+        std::lock_guard<std::mutex> lk(st.mu);
+        auto it = st.pinned.find(p);
+        if (it != st.pinned.end()) { st.free_blocks.insert(std::make_pair(it->second, p)); return; }
+    }
+#endif
+    free(p);
+}
 
 // ------------------------------------------------------------------------------------------------ compute backend
 #if UVC_CUDA
@@ -154,7 +236,7 @@ static void launch(uvc_kernel_t k, cudaStream_t s, const BatchView & v, int64_t 
 
 static int backend_alloc(uvcgpu_ctx *ctx, BatchState & bs, void **out, size_t bytes, bool zero) {
     if (0 == bytes) { bytes = 16; }
-    UVC_CUDA_CHECK(ctx, cudaMalloc(out, bytes));
+    UVC_CUDA_CHECK(ctx, cudaMallocAsync(out, bytes, ctx->stream));   // stream-ordered pool: no device synchronisation, blocks are reused across batches
     bs.allocs.push_back(*out);
     if (zero) { UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, 0, bytes, ctx->stream)); }
     return 0;
@@ -164,10 +246,10 @@ static int backend_upload(uvcgpu_ctx *ctx, BatchState & bs, void *dst, const voi
     return 0;
 }
 static int backend_download(uvcgpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
-    if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); }
+    if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream)); UVC_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); }
     return 0;
 }
-static void backend_free(BatchState & bs) { for (void *p : bs.allocs) { cudaFree(p); } bs.allocs.clear(); }
+static void backend_free(uvcgpu_ctx *ctx, BatchState & bs) { for (void *p : bs.allocs) { cudaFreeAsync(p, ctx->stream); } bs.allocs.clear(); }
 
 static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     const BatchView & v = bs.view;
@@ -245,7 +327,7 @@ static int backend_upload(uvcgpu_ctx *, BatchState & bs, void *dst, const void *
     return 0;
 }
 static int backend_download(uvcgpu_ctx *, void *dst, const void *src, size_t bytes) { if (bytes) { memcpy(dst, src, bytes); } return 0; }
-static void backend_free(BatchState & bs) { for (void *p : bs.allocs) { free(p); } bs.allocs.clear(); }
+static void backend_free(uvcgpu_ctx *, BatchState & bs) { for (void *p : bs.allocs) { free(p); } bs.allocs.clear(); }
 static int backend_run(uvcgpu_ctx *, BatchState & bs) {
     const BatchView & v = bs.view;
     for (int64_t i = 0; i < v.n_reads; i++) { uvc::k0_read(v, i); }
@@ -399,6 +481,10 @@ int uvcgpu_create(uvcgpu_ctx **out, int device, const uvcgpu_params *params) {
     }
 #if UVC_CUDA
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return UVCGPU_ECUDA; }
+    {   // keep freed device blocks in the stream-ordered pool instead of returning them to the driver after every batch
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { uint64_t keep = UINT64_MAX; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
+    }
 #endif
     *out = ctx;
     return UVCGPU_OK;
@@ -406,7 +492,7 @@ int uvcgpu_create(uvcgpu_ctx **out, int device, const uvcgpu_params *params) {
 
 void uvcgpu_destroy(uvcgpu_ctx *ctx) {
     if (NULL == ctx) { return; }
-    for (auto & kv : ctx->batches) { backend_free(*kv.second); }
+    for (auto & kv : ctx->batches) { backend_free(ctx, *kv.second); }
 #if UVC_CUDA
     if (ctx->stream) { cudaStreamDestroy(ctx->stream); }
 #endif
@@ -446,7 +532,7 @@ int uvcgpu_set_contig_name(uvcgpu_ctx *ctx, int32_t tid, const char *name) {
     return UVCGPU_OK;
 }
 
-#define UVC_TRY(expr) { int rc_ = (expr); if (rc_ != 0) { backend_free(*bs); return rc_; } }
+#define UVC_TRY(expr) { int rc_ = (expr); if (rc_ != 0) { backend_free(ctx, *bs); return rc_; } }
 
 int uvcgpu_submit(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, const uvcgpu_reads_soa *reads, uvcgpu_ticket *ticket) {
     return uvcgpu_submit_multi(ctx, n_tiles, tiles, 1, reads, NULL, ticket);
@@ -557,7 +643,7 @@ static int ensure_sparse(uvcgpu_ctx *ctx, BatchState & bs) {
     int rc = backend_download(ctx, cursor, v.rec_cursor, sizeof(cursor));
     if (rc != 0) { return rc; }
     if (cursor[0] > v.rec_cap) { ctx->err = "sparse record stream overflow: submit a smaller batch"; return UVCGPU_ENOMEM; }
-    std::vector<int32_t> rec((size_t)cursor[0]);
+    StageVec<int32_t> rec((size_t)cursor[0]);
     rc = backend_download(ctx, rec.data(), v.rec_buf, rec.size() * sizeof(int32_t));
     if (rc != 0) { return rc; }
     bs.ev_host.resize((size_t)v.n_ev);
@@ -595,7 +681,7 @@ static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
     if ((rc = backend_alloc(ctx, bs, &d, (size_t)v.n_pos * sizeof(int32_t), false)) != 0) { return rc; }
     sv.cand_list = (int32_t*)d;
     int64_t cap = v.n_pos / 16 + 4096;
-    std::vector<VarRec> recs;
+    StageVec<VarRec> recs;
     for (int attempt = 0; attempt < 2; attempt++) {
         if ((rc = backend_alloc(ctx, bs, &d, (size_t)cap * sizeof(VarRec), false)) != 0) { return rc; }
         sv.out = (VarRec*)d; sv.out_cap = (int32_t)cap;
@@ -687,7 +773,7 @@ int uvcgpu_release(uvcgpu_ctx *ctx, uvcgpu_ticket ticket) {
     auto it = ctx->batches.find(ticket);
     if (it == ctx->batches.end()) { return UVCGPU_EINVAL; }
     backend_wait(ctx, *it->second);
-    backend_free(*it->second);
+    backend_free(ctx, *it->second);
     ctx->batches.erase(it);
     return UVCGPU_OK;
 }
@@ -743,7 +829,7 @@ int uvcgpu_dump_counters(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_ind
             host_side = true; break;
         }
         case UVCGPU_SEC_BAQ: case UVCGPU_SEC_BAQ2: {
-            const std::vector<int32_t> & b = (section == UVCGPU_SEC_BAQ ? bs.hb.baq : bs.hb.baq2);
+            const StageVec<int32_t> & b = (section == UVCGPU_SEC_BAQ ? bs.hb.baq : bs.hb.baq2);
             std::vector<int64_t> w(npos);
             for (size_t i = 0; i < npos; i++) { w[i] = b[off + i]; }
             tmp.assign((uint8_t*)w.data(), (uint8_t*)(w.data() + npos));

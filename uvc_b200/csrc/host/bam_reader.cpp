@@ -13,9 +13,120 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
 namespace {
 
 const int kMaxBlock = 0x10000;
+
+// Sequential read-ahead for whole-file scans (the region tiler): compressed BGZF members are read in file order in groups of kGroup and
+// inflated on a small pool of threads (members are independent deflate streams); the consumer then takes them in order.
+struct SeqInflater {
+    static const int kGroup = 96;
+    struct Slot { std::vector<uint8_t> c, u; int clen = 0, ulen = 0, bsize = 0; int64_t addr = 0; bool ok = true; };
+    FILE *fp = NULL;
+    int64_t next_addr = 0;
+    std::vector<Slot> slots;
+    int n_filled = 0, n_taken = 0;
+    bool eof = false, failed = false;
+    std::vector<std::thread> pool;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    int generation = 0, pending = 0;
+    std::atomic<int> next_job{0};
+    bool stop = false;
+
+    void start(const char *path, int64_t addr, int n_threads) {
+        fp = fopen(path, "rb");
+        next_addr = addr;
+        slots.resize(kGroup);
+        for (auto & s : slots) { s.c.resize(kMaxBlock + 64); s.u.resize(kMaxBlock); }
+        for (int t = 0; t < n_threads; t++) { pool.emplace_back([this]() { worker(); }); }
+    }
+    static void inflate_slot(Slot & s) {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) { s.ok = false; return; }
+        zs.next_in = s.c.data(); zs.avail_in = s.clen; zs.next_out = s.u.data(); zs.avail_out = kMaxBlock;
+        s.ok = (inflate(&zs, Z_FINISH) == Z_STREAM_END);
+        s.ulen = (int)zs.total_out;
+        inflateEnd(&zs);
+    }
+    void worker() {
+        int seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&]() { return stop || generation != seen; });
+                if (stop) { return; }
+                seen = generation;
+            }
+            for (;;) {
+                const int j = next_job.fetch_add(1);
+                if (j >= n_filled) { break; }
+                inflate_slot(slots[j]);
+                std::lock_guard<std::mutex> lk(mu);
+                if (--pending == 0) { cv_done.notify_all(); }
+            }
+        }
+    }
+    // reads and inflates the next group; returns false at end of file / on error
+    bool fill() {
+        n_filled = 0; n_taken = 0;
+        if (eof || failed || NULL == fp) { return false; }
+        if (fseeko(fp, next_addr, SEEK_SET) != 0) { failed = true; return false; }
+        while (n_filled < kGroup) {
+            Slot & s = slots[n_filled];
+            uint8_t h[18];
+            const size_t n = fread(h, 1, 18, fp);
+            if (0 == n) { eof = true; break; }
+            if (n != 18 || h[0] != 31 || h[1] != 139 || !(h[3] & 4)) { failed = true; break; }
+            const int xlen = h[10] | (h[11] << 8);
+            uint8_t extra[512];
+            memcpy(extra, h + 12, 6);
+            if (xlen > 512 || (xlen > 6 && fread(extra + 6, 1, xlen - 6, fp) != (size_t)(xlen - 6))) { failed = true; break; }
+            int bsize = -1;
+            for (int off = 0; off + 4 <= xlen;) {
+                const int slen = extra[off + 2] | (extra[off + 3] << 8);
+                if (extra[off] == 'B' && extra[off + 1] == 'C' && slen == 2) { bsize = (extra[off + 4] | (extra[off + 5] << 8)) + 1; }
+                off += 4 + slen;
+            }
+            if (bsize < 0) { failed = true; break; }
+            s.clen = bsize - 12 - xlen - 8;
+            if (fread(s.c.data(), 1, s.clen + 8, fp) != (size_t)(s.clen + 8)) { failed = true; break; }
+            s.addr = next_addr; s.bsize = bsize;
+            next_addr += bsize;
+            n_filled++;
+        }
+        if (0 == n_filled) { return false; }
+        if (pool.empty()) { for (int j = 0; j < n_filled; j++) { inflate_slot(slots[j]); } }
+        else {
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                pending = n_filled; next_job.store(0); generation++;
+            }
+            cv_work.notify_all();
+            std::unique_lock<std::mutex> lk(mu);
+            cv_done.wait(lk, [&]() { return 0 == pending; });
+        }
+        for (int j = 0; j < n_filled; j++) { if (!slots[j].ok) { failed = true; return false; } }
+        return true;
+    }
+    // next block in file order; NULL at end of file or on error
+    Slot *take() {
+        if (n_taken >= n_filled && !fill()) { return NULL; }
+        return &slots[n_taken++];
+    }
+    ~SeqInflater() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv_work.notify_all();
+        for (auto & th : pool) { th.join(); }
+        if (fp) { fclose(fp); }
+    }
+};
 
 struct BgzfIn {
     FILE *fp = NULL;
@@ -25,9 +136,18 @@ struct BgzfIn {
     int ulen = 0, uoff = 0;
     z_stream zs;
     bool zs_init = false;
+    SeqInflater *seq = NULL;    // when set, blocks come from the parallel sequential read-ahead
 
     // 0 ok, 1 end of file, -1 error
     int load(int64_t caddr) {
+        if (seq) {
+            SeqInflater::Slot *s = seq->take();
+            if (NULL == s) { if (seq->failed) { return -1; } block_addr = caddr; block_clen = 0; ulen = uoff = 0; return 1; }
+            ubuf.swap(s->u);
+            if ((int)s->u.size() < kMaxBlock) { s->u.resize(kMaxBlock); }
+            ulen = s->ulen; uoff = 0; block_addr = s->addr; block_clen = s->bsize;
+            return 0;
+        }
         uint8_t h[18];
         if (fseeko(fp, caddr, SEEK_SET) != 0) { return -1; }
         const size_t n = fread(h, 1, 18, fp);
@@ -54,6 +174,7 @@ struct BgzfIn {
         return 0;
     }
     int seek(int64_t voff) {
+        stop_seq();
         const int64_t caddr = voff >> 16;
         if (!(block_clen > 0 && block_addr == caddr)) { if (load(caddr) < 0) { return -1; } }
         uoff = (int)(voff & 0xffff);
@@ -77,7 +198,8 @@ struct BgzfIn {
         }
         return done;
     }
-    ~BgzfIn() { if (zs_init) { inflateEnd(&zs); } if (fp) { fclose(fp); } }
+    void stop_seq() { if (seq) { delete seq; seq = NULL; block_clen = 0; ulen = uoff = 0; } }
+    ~BgzfIn() { stop_seq(); if (zs_init) { inflateEnd(&zs); } if (fp) { fclose(fp); } }
 };
 
 inline uint32_t le32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
@@ -86,6 +208,7 @@ inline uint32_t le32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1]
 
 struct uvchost_bam {
     BgzfIn in;
+    std::string path;
     std::vector<std::string> names;
     std::vector<int64_t> lens;
     std::vector<std::vector<uint64_t>> lidx;   // linear index per reference
@@ -113,6 +236,7 @@ extern "C" {
 
 uvchost_bam *uvchost_bam_open(const char *path) {
     uvchost_bam *b = new uvchost_bam();
+    b->path = path;
     b->in.fp = fopen(path, "rb");
     if (NULL == b->in.fp) { delete b; return NULL; }
     uint8_t w[8];
@@ -313,6 +437,17 @@ int uvchost_bam_scan(uvchost_bam *b, uvchost_scan_cb cb, void *user) {
 }
 
 int uvchost_bam_rewind(uvchost_bam *b) { return b->in.seek(b->first_record_voff); }
+
+int uvchost_bam_rewind_parallel(uvchost_bam *b, int n_threads) {
+    if (b->in.seek(b->first_record_voff) != 0) { return -1; }
+    if (n_threads <= 1) { return 0; }
+    // the block that holds the first record is already inflated: the read-ahead continues with the block after it
+    SeqInflater *q = new SeqInflater();
+    q->start(b->path.c_str(), b->in.block_addr + b->in.block_clen, n_threads);
+    if (NULL == q->fp) { delete q; return 0; }
+    b->in.seq = q;
+    return 0;
+}
 
 int uvchost_bam_next_core(uvchost_bam *b, uvchost_core *out) {
     Core c;

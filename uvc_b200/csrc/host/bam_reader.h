@@ -43,6 +43,8 @@ int uvchost_bam_scan(uvchost_bam *b, uvchost_scan_cb cb, void *user);
  * next returns 1 and fills *c, 0 at end of file (*c untouched, like htslib's sam_read1), negative on error. */
 typedef struct uvchost_core { int32_t tid, pos, endpos, isize, l_qseq; uint16_t flag; uint8_t mapq; } uvchost_core;
 int uvchost_bam_rewind(uvchost_bam *b);
+/* Same, with the following blocks inflated ahead on n_threads threads (whole-file scans); any later seek returns to on-demand inflation. */
+int uvchost_bam_rewind_parallel(uvchost_bam *b, int n_threads);
 int uvchost_bam_next_core(uvchost_bam *b, uvchost_core *c);
 /* Positions the sequential reader at the first record that can overlap [beg, end) of tid (sam_itr_queryi); records are then pulled with
  * uvchost_bam_next_core and filtered by the caller. Returns 0, or 1 if the index has no data for the region. */

@@ -57,11 +57,17 @@ struct uvchost_tiler {
     uvchost_core rec;                       // the reference's single alnrecord: keeps its content at end of file
     bool started = false;
     std::vector<uvchost_bedline> out;
+    uvchost_tile_cb cb = NULL;
+    void *cb_user = NULL;
+    int32_t scan_threads = 1;
+    void emit(const uvchost_bedline & l) { out.push_back(l); if (cb) { cb(&l, cb_user); } }
 };
 
 extern "C" {
 
 const char *uvchost_tiler_error(const uvchost_tiler *t) { return t->err.c_str(); }
+void uvchost_tiler_set_callback(uvchost_tiler *t, uvchost_tile_cb cb, void *user) { t->cb = cb; t->cb_user = user; }
+void uvchost_tiler_set_scan_threads(uvchost_tiler *t, int32_t scan_threads) { t->scan_threads = scan_threads; }
 
 void uvchost_tiler_close(uvchost_tiler *t) {
     if (NULL == t) { return; }
@@ -137,7 +143,7 @@ int64_t uvchost_tiler_next(uvchost_tiler *t, const uvchost_bedline **lines, int6
             uvchost_bedline l = t->given[t->given_idx];
             int64_t region_n_reads = t->bed_dp * (int64_t)(l.end_pos - l.beg_pos);
             if (-1 == t->bed_dp) { region_n_reads = uvchost_bam_count(t->bam, l.tid, l.beg_pos, l.end_pos); }
-            t->out.push_back(l);
+            t->emit(l);
             const int64_t region_n_rposs = l.end_pos - l.beg_pos;
             total_n_reads += region_n_reads; total_n_rposs += region_n_rposs;
             total_n_reads_sq += (int64_t)square_big(region_n_reads); total_n_rposs_sq += (int64_t)square_big(region_n_rposs);
@@ -148,7 +154,7 @@ int64_t uvchost_tiler_next(uvchost_tiler *t, const uvchost_bedline **lines, int6
         }
     } else {
         // grouping.cpp:214-310
-        if (!t->started) { if (uvchost_bam_rewind(t->bam) != 0) { t->err = "seek failed"; return -1; } t->started = true; }
+        if (!t->started) { if (uvchost_bam_rewind_parallel(t->bam, t->scan_threads) != 0) { t->err = "seek failed"; return -1; } t->started = true; }
         int32_t block_tid = t->last_tid, block_beg = t->last_beg, block_running_end = t->last_end;
         int64_t region_n_reads = 0, region_n_rposs = 0, region_n_rposs_add = 0;
         int ret = -1;
@@ -170,7 +176,7 @@ int64_t uvchost_tiler_next(uvchost_tiler *t, const uvchost_bedline **lines, int6
                 const bool zero_sized = ((int64_t)block_beg >= block_norm_end);
                 if ((!is_1st_read) && (!zero_sized)) {
                     uvchost_bedline l; l.tid = block_tid; l.beg_pos = block_beg; l.end_pos = (int32_t)block_norm_end; l.region_flag = region_flag; l.n_reads = region_n_reads;
-                    t->out.push_back(l);
+                    t->emit(l);
                     const int64_t region_s_rposs = region_n_rposs + region_n_rposs_add;
                     total_n_reads += region_n_reads; total_n_rposs += region_s_rposs;
                     total_n_reads_sq += (int64_t)square_big(region_n_reads); total_n_rposs_sq += (int64_t)square_big(region_s_rposs);

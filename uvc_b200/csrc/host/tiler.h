@@ -33,6 +33,12 @@ uvchost_tiler *uvchost_tiler_open(const char *bam_path, const char *bed_fname, c
 void uvchost_tiler_close(uvchost_tiler *t);
 const char *uvchost_tiler_error(const uvchost_tiler *t);   /* non-empty after a failed open/next */
 
+/* Optional: cb(line, user) is called for every tile the moment it is cut, before uvchost_tiler_next returns the whole iteration, so that the
+ * caller can start working on the first tiles while the scan continues. scan_threads > 1 inflates the BAM ahead on that many threads. */
+typedef void (*uvchost_tile_cb)(const uvchost_bedline *line, void *user);
+void uvchost_tiler_set_callback(uvchost_tiler *t, uvchost_tile_cb cb, void *user);
+void uvchost_tiler_set_scan_threads(uvchost_tiler *t, int32_t scan_threads);
+
 /* One tier-1 iteration. Returns the iteration's total number of reads (the reference's iternext return value) or a negative error;
  * *lines / *n_lines point into the tiler and stay valid until the next call. */
 int64_t uvchost_tiler_next(uvchost_tiler *t, const uvchost_bedline **lines, int64_t *n_lines);

@@ -198,32 +198,41 @@ std::string bed_out_text(const std::vector<uvchost_bedline> & lines, const std::
     return s;
 }
 
-void tiler_thread(Shared *sh) {
+// Tiles are handed to the lanes the moment the tiler cuts them (the scan of the rest of the BAM continues meanwhile): consecutive tiles are
+// packed into batches bounded by positions and reads; a batch never spans two contigs.
+struct BatchPacker {
+    Shared *sh;
+    Batch cur;
+    uvchost_bedline prev;
+    int64_t seq = 0, bp = 0, br = 0;
+    explicit BatchPacker(Shared *s) : sh(s) { prev.tid = -1; prev.beg_pos = 0; prev.end_pos = 0; prev.region_flag = 0; prev.n_reads = 0; }
+    void flush() { if (!cur.tiles.empty()) { cur.seq = seq++; sh->batches.push(std::move(cur)); cur = Batch(); bp = 0; br = 0; } }
+    void add(const uvchost_bedline & l) {
+        const int64_t lp = (int64_t)(l.end_pos - l.beg_pos) + 4200, lr = l.n_reads;
+        if (!cur.tiles.empty() && (bp + lp > sh->opt.batch_positions || br + lr > sh->opt.batch_reads || cur.tiles.back().tid != l.tid)) { flush(); }
+        cur.tiles.push_back(l); cur.prevs.push_back(prev);
+        prev = l; bp += lp; br += lr;
+    }
+    static void on_tile(const uvchost_bedline *l, void *user) { ((BatchPacker*)user)->add(*l); }
+};
+
+void tiler_thread(Shared *sh, int scan_threads) {
     const Options & o = sh->opt;
     uvchost_tiler *t = uvchost_tiler_open(o.bam.c_str(), o.bed.c_str(), o.targets.c_str(), o.threads, o.mem_per_thread, o.bed_in_avg_sequencing_DP, 0);
     if (uvchost_tiler_error(t)[0]) { sh->fail(std::string("tiler: ") + uvchost_tiler_error(t)); uvchost_tiler_close(t); sh->batches.close(); return; }
     std::ofstream bed_out;
     if (!o.bed_out.empty() && o.bed_out != ".") { bed_out.open(o.bed_out.c_str(), std::ios::out); }
-    uvchost_bedline prev; prev.tid = -1; prev.beg_pos = 0; prev.end_pos = 0; prev.region_flag = 0; prev.n_reads = 0;
-    int64_t seq = 0, iter = 0;
+    BatchPacker packer(sh);
+    uvchost_tiler_set_callback(t, BatchPacker::on_tile, &packer);
+    uvchost_tiler_set_scan_threads(t, scan_threads);
+    int64_t iter = 0;
     for (;;) {
         const uvchost_bedline *lines = NULL; int64_t n = 0;
         const int64_t nreads = uvchost_tiler_next(t, &lines, &n);
         if (nreads < 0) { sh->fail(std::string("tiler: ") + uvchost_tiler_error(t)); break; }
         if (!(nreads > 0 || n > 0)) { break; }     // main.cpp:1339
-        std::vector<uvchost_bedline> v(lines, lines + n);
-        if (bed_out.is_open()) { bed_out << bed_out_text(v, sh->contigs, o.threads, iter); }
-        Batch b;
-        int64_t bp = 0, br = 0;
-        for (const auto & l : v) {
-            const int64_t lp = (int64_t)(l.end_pos - l.beg_pos) + 4200, lr = l.n_reads;
-            if (!b.tiles.empty() && (bp + lp > o.batch_positions || br + lr > o.batch_reads || b.tiles.back().tid != l.tid)) {
-                b.seq = seq++; sh->batches.push(std::move(b)); b = Batch(); bp = 0; br = 0;
-            }
-            b.tiles.push_back(l); b.prevs.push_back(prev);
-            prev = l; bp += lp; br += lr;
-        }
-        if (!b.tiles.empty()) { b.seq = seq++; sh->batches.push(std::move(b)); }
+        packer.flush();
+        if (bed_out.is_open()) { bed_out << bed_out_text(std::vector<uvchost_bedline>(lines, lines + n), sh->contigs, o.threads, iter); }
         iter++;
         if (sh->failed.load()) { break; }
     }
@@ -402,7 +411,7 @@ int main(int argc, char **argv) {
         else if (fout) { std::string z; uvchost_bgzf_compress(z, header.data(), header.size(), o.compress_level, 1); fwrite(z.data(), 1, z.size(), fout); }
     }
 
-    std::thread tiler(tiler_thread, &sh);
+    std::thread tiler(tiler_thread, &sh, std::max(1, std::min(4, cpu_budget / 2)));
     std::vector<std::thread> lanes;
     for (int k = 0; k < n_lanes; k++) {
         Lane l; l.sh = &sh; l.device = k % n_gpus; l.n_threads = threads_per_lane; l.index = k;

@@ -225,7 +225,7 @@ int32_t slip_phred(double ampfact, int32_t unit, int32_t nunits) {
 }
 
 // main.hpp:803-874: best short-tandem-repeat (unit <= str_max) and any-tandem-repeat (unit <= vntr_max) track per reference base
-void repeat_context(std::vector<uvcgpu_rtr> & out, const char *ref, int32_t n, const uvcgpu_params & par) {
+void repeat_context(StageVec<uvcgpu_rtr> & out, const char *ref, int32_t n, const uvcgpu_params & par) {
     out.assign((size_t)n + 1, uvcgpu_rtr());
     for (auto & t : out) { t.begpos = 0; t.tracklen = 0; t.unitlen = 0; t.indelphred = par.indel_BQ_max; t.anyTR_begpos = 0; t.anyTR_tracklen = 0; t.anyTR_unitlen = 0; }
     const int32_t str_max = par.indel_str_repeatsize_max, vntr_max = par.indel_vntr_repeatsize_max;
@@ -264,7 +264,7 @@ void repeat_context(std::vector<uvcgpu_rtr> & out, const char *ref, int32_t n, c
 }
 
 // main.cpp:400-429. QUIRK: the any-tandem-repeat variant still divides by the STR unit length.
-void baq_prefix(std::vector<int32_t> & dst, size_t off, const std::vector<uvcgpu_rtr> & rtr, bool any_tr, const uvcgpu_params & par) {
+void baq_prefix(StageVec<int32_t> & dst, size_t off, const StageVec<uvcgpu_rtr> & rtr, bool any_tr, const uvcgpu_params & par) {
     int64_t sum = 0;
     const int32_t polsize = (int32_t)round(par.indel_polymerase_size);
     for (size_t i = 0; i < rtr.size(); i++) {
@@ -576,7 +576,7 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
         hb.refsym.resize(poff + npos); hb.pos_tile.resize(poff + npos, ti); hb.baq.resize(poff + npos); hb.baq2.resize(poff + npos);
         for (int32_t i = 0; i < nref; i++) { hb.refsym[poff + i] = char_to_symbol(refstring[i]); }
         hb.refsym[poff + nref] = UVC_BASE_N;
-        std::vector<uvcgpu_rtr> rtr;
+        StageVec<uvcgpu_rtr> rtr;
         repeat_context(rtr, refstring.data(), nref, par);
         hb.rtr.insert(hb.rtr.end(), rtr.begin(), rtr.end());
         baq_prefix(hb.baq, poff, rtr, false, par);
@@ -608,7 +608,11 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
     std::vector<HostBatch> part((size_t)n_tiles);
     std::vector<int> rcs((size_t)n_tiles, 0);
     std::vector<std::string> msgs((size_t)n_tiles);
-    uvc_parallel_for(n_tiles, n_threads, [&](int32_t ti) { rcs[ti] = build_tile(part[ti], par, contigs, ti, tiles[ti], sources[tile_source ? tile_source[ti] : 0], center_pow, pem, msgs[ti]); });
+    uvc_parallel_for(n_tiles, n_threads, [&](int32_t ti) {
+        uvc_stage_thread_pinning(false);
+        rcs[ti] = build_tile(part[ti], par, contigs, ti, tiles[ti], sources[tile_source ? tile_source[ti] : 0], center_pow, pem, msgs[ti]);
+        uvc_stage_thread_pinning(true);
+    });
     for (int32_t ti = 0; ti < n_tiles; ti++) { if (rcs[ti] != 0) { msg = msgs[ti]; return rcs[ti]; } }
     // 2. offsets of every tile in the concatenated arrays
     struct Off { int64_t pos, read, frag, fam, fragread, seq, qual, cigar, cx, ev, fcol, mcol; };

@@ -9,6 +9,22 @@
 #include <string>
 #include <vector>
 
+// Staging memory. Large blocks come from a process-wide cache of page-locked host memory (CUDA build; plain malloc in the emulation build), so
+// that the uploads and downloads of a batch are true asynchronous DMA transfers and no page-locking cost is paid per batch; small blocks are malloc'ed.
+void *uvc_stage_alloc(size_t bytes);
+void uvc_stage_free(void *p, size_t bytes);
+void uvc_stage_thread_pinning(bool enabled);   // per thread: the tile-private scratch of the staging workers is not worth page-locking
+template <class T> struct UvcStageAlloc {
+    typedef T value_type;
+    UvcStageAlloc() {}
+    template <class U> UvcStageAlloc(const UvcStageAlloc<U> &) {}
+    T *allocate(size_t n) { return (T*)uvc_stage_alloc(n * sizeof(T)); }
+    void deallocate(T *p, size_t n) { uvc_stage_free((void*)p, n * sizeof(T)); }
+    template <class U> bool operator==(const UvcStageAlloc<U> &) const { return true; }
+    template <class U> bool operator!=(const UvcStageAlloc<U> &) const { return false; }
+};
+template <class T> using StageVec = std::vector<T, UvcStageAlloc<T>>;
+
 struct HostContig {
     std::string bases;   // upper-cased; empty if not available
     int64_t len = 0;
@@ -16,20 +32,20 @@ struct HostContig {
 };
 
 struct HostBatch {
-    std::vector<TileInfo> tiles;
-    std::vector<int32_t> pos_tile;
-    std::vector<uint8_t> refsym;
-    std::vector<uvcgpu_rtr> rtr;          // as computed from the reference string (before the threshold pass adjusts indelphred)
-    std::vector<int32_t> baq, baq2;
-    std::vector<ReadRec> reads;
+    StageVec<TileInfo> tiles;
+    StageVec<int32_t> pos_tile;
+    StageVec<uint8_t> refsym;
+    StageVec<uvcgpu_rtr> rtr;          // as computed from the reference string (before the threshold pass adjusts indelphred)
+    StageVec<int32_t> baq, baq2;
+    StageVec<ReadRec> reads;
     std::vector<int64_t> read_raw_index;  // index into the caller's uvcgpu_reads_soa
-    std::vector<uint8_t> seq, qual;
-    std::vector<uint32_t> cigar;
-    std::vector<FragRec> frags;
-    std::vector<int32_t> frag_reads;
-    std::vector<FamRec> fams;
+    StageVec<uint8_t> seq, qual;
+    StageVec<uint32_t> cigar;
+    StageVec<FragRec> frags;
+    StageVec<int32_t> frag_reads;
+    StageVec<FamRec> fams;
     std::vector<std::string> fam_umi;     // umistring of each family (for the grouping dump)
-    std::vector<int32_t> fchunk_frag, mchunk_fs;   // owner of every 32-entry chunk of the fragment / family-strand columns
+    StageVec<int32_t> fchunk_frag, mchunk_fs;   // owner of every 32-entry chunk of the fragment / family-strand columns
     int64_t n_fcol = 0, n_mcol = 0;       // padded column entries
     int64_t n_pos = 0, n_cx = 0, n_ev = 0;
     int64_t n_reads_in = 0;

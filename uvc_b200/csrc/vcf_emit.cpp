@@ -28,7 +28,7 @@ inline int char_to_symbol(char c) {
     }
 }
 
-std::string event_string(const HostBatch & hb, const std::vector<IndelEvent> & ev, int32_t e, const std::string & refstring, int32_t ext_beg) {
+std::string event_string(const HostBatch & hb, const StageVec<IndelEvent> & ev, int32_t e, const std::string & refstring, int32_t ext_beg) {
     static const char *nt16 = "=ACMGRSVTWYHKDBN";
     if (e < 0) { return ""; }
     const IndelEvent & E = ev[e];
@@ -88,7 +88,7 @@ std::string fts_string(const CandFmt & c) {
 } // namespace
 
 void uvc_build_indel_sites(std::vector<TileIndelSites> & sites, std::vector<IndelAllele> & table, const HostBatch & hb,
-        const std::vector<TileSparse> & sparse, const std::map<int32_t, HostContig> & contigs, const std::vector<IndelEvent> & ev) {
+        const std::vector<TileSparse> & sparse, const std::map<int32_t, HostContig> & contigs, const StageVec<IndelEvent> & ev) {
     sites.assign(hb.tiles.size(), TileIndelSites());
     table.clear();
     for (size_t ti = 0; ti < hb.tiles.size(); ti++) {
@@ -196,7 +196,7 @@ void uvc_build_indel_sites(std::vector<TileIndelSites> & sites, std::vector<Inde
 }
 
 std::string uvc_tile_vcf_text(const HostBatch & hb, int32_t tile_index, const uvcgpu_params & par, const std::string & tname, const HostContig & contig,
-        const std::vector<VarRec> & recs, const TileIndelSites & sites, const TileSparse & sparse, const std::vector<IndelEvent> & ev,
+        const std::vector<VarRec> & recs, const TileIndelSites & sites, const TileSparse & sparse, const StageVec<IndelEvent> & ev,
         const GvcfPos *gvcf, const GvcfExtra *gextra) {
     std::string out;
     const TileInfo & T = hb.tiles[tile_index];

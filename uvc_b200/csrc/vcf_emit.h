@@ -25,11 +25,11 @@ typedef std::map<std::pair<int32_t, int32_t>, IndelSite> TileIndelSites;   // (r
 
 // Builds, for every tile, the indel sites and the flat device table (sorted by key = gp * 16 + symbol).
 void uvc_build_indel_sites(std::vector<TileIndelSites> & sites, std::vector<IndelAllele> & table, const HostBatch & hb,
-        const std::vector<TileSparse> & sparse, const std::map<int32_t, HostContig> & contigs, const std::vector<IndelEvent> & ev);
+        const std::vector<TileSparse> & sparse, const std::map<int32_t, HostContig> & contigs, const StageVec<IndelEvent> & ev);
 
 // The uncompressed VCF fragment of one tile (what process_batch appends to uncompressed_vcf_string, main.cpp:1184).
 std::string uvc_tile_vcf_text(const HostBatch & hb, int32_t tile_index, const uvcgpu_params & par, const std::string & tname, const HostContig & contig,
-        const std::vector<VarRec> & recs_of_tile, const TileIndelSites & sites, const TileSparse & sparse, const std::vector<IndelEvent> & ev,
+        const std::vector<VarRec> & recs_of_tile, const TileIndelSites & sites, const TileSparse & sparse, const StageVec<IndelEvent> & ev,
         const GvcfPos *gvcf, const GvcfExtra *gextra);
 
 #endif
