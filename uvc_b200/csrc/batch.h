@@ -160,7 +160,8 @@ struct BatchView {
     // reads
     const ReadRec *reads;
     ReadDerived *rd;
-    const uint8_t *seq, *qual;
+    const uint8_t *seq;
+    uint8_t *qual;                 // raw base qualities on upload; K0 applies the reference's quality fix-ups in place (grouping.cpp:459-543)
     const uint32_t *cigar;
     CxEntry *cx;
     IndelEvent *ev;

@@ -19,6 +19,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
 
 namespace {
 
@@ -94,22 +95,30 @@ Filt classify(bool & isrc, bool & isr2, int32_t & tBeg, int32_t & tEnd, const Ra
     return KEEP;
 }
 
-// grouping.cpp:422-442; pos_to_center_pos starts as all zeros, exactly like the reference's inicount copy
-void snap_to_centers(std::vector<int32_t> & center, const std::vector<int32_t> & cnt, const double *center_pow) {
+// poscounter_to_pos2pcenter (grouping.cpp:422-442) evaluated on demand for one position: the local maximum within +-3 that the end
+// position snaps to. The reference fills the whole array, which starts as all zeros (its inicount copy), hence 0 outside the loop range.
+int32_t center_at(const std::vector<int32_t> & cnt, int32_t lo, const double *center_pow) {
     const int32_t n = (int32_t)cnt.size();
-    for (int32_t lo = ARRPOS_INNER_RANGE; lo < n - ARRPOS_INNER_RANGE; lo++) {
-        const int32_t lo_cnt = cnt[lo];
-        center[lo] = lo;
-        int32_t max_cnt = lo_cnt;
-        for (int32_t hi = lo - ARRPOS_INNER_RANGE; hi < lo + ARRPOS_INNER_RANGE + 1; hi++) {
-            const int32_t hi_cnt = cnt[hi];
-            const int d = abs(lo - hi);
-            if ((hi_cnt > max_cnt) && ((hi_cnt + 1) > (lo_cnt + 1) * center_pow[d])) {
-                center[lo] = hi;
-                max_cnt = hi_cnt;
-            }
+    if (lo < ARRPOS_INNER_RANGE || lo >= n - ARRPOS_INNER_RANGE) { return 0; }
+    const int32_t lo_cnt = cnt[lo];
+    int32_t center = lo;
+    int32_t max_cnt = lo_cnt;
+    for (int32_t hi = lo - ARRPOS_INNER_RANGE; hi < lo + ARRPOS_INNER_RANGE + 1; hi++) {
+        const int32_t hi_cnt = cnt[hi];
+        const int d = abs(lo - hi);
+        if ((hi_cnt > max_cnt) && ((hi_cnt + 1) > (lo_cnt + 1) * center_pow[d])) {
+            center = hi;
+            max_cnt = hi_cnt;
         }
     }
+    return center;
+}
+
+// FNV-1a over a NUL-terminated name (only used to bucket names in the per-tile name set; equality is always checked on the strings)
+inline uint64_t name_hash(const char *s) {
+    uint64_t h = 1469598103934665603ULL;
+    for (; *s; s++) { h = (h ^ (uint64_t)(uint8_t)*s) * 1099511628211ULL; }
+    return h;
 }
 
 inline uint64_t str_hash(const char *s, uint64_t base) {
@@ -120,9 +129,20 @@ inline uint64_t str_hash(const char *s, uint64_t base) {
 
 typedef std::pair<int32_t, int32_t> tidpos_t;
 
+// a string that lives in the caller's qname buffer; ordered like std::string (bytewise, then by length)
+struct StrView {
+    const char *p; size_t n;
+    StrView() : p(""), n(0) {}
+    StrView(const char *p_, size_t n_) : p(p_), n(n_) {}
+    int cmp(const StrView & o) const { const int r = memcmp(p, o.p, n < o.n ? n : o.n); return (r != 0 ? r : (n < o.n ? -1 : (n > o.n ? 1 : 0))); }
+    bool operator==(const StrView & o) const { return n == o.n && 0 == memcmp(p, o.p, n); }
+    bool operator!=(const StrView & o) const { return !(*this == o); }
+    bool operator<(const StrView & o) const { return cmp(o) < 0; }
+};
+
 struct FamKey {
     tidpos_t beg, end;
-    std::string qname, umi;
+    StrView qname, umi;
     uint32_t duplexflag, dedup_idflag;
     bool operator<(const FamKey & o) const { // MolecularID.hpp:52-68 (the hash tie-break can never decide: equal fields give equal hashes)
         if (beg != o.beg) { return beg < o.beg; }
@@ -141,70 +161,12 @@ struct Kept {
     int64_t raw;          // index into the caller's SoA
     Raw r;
     FamKey key;
-    std::string umi_full;
+    StrView umi_full;
     tidpos_t begpair, endpair;   // the read's own (non-key) MolecularBarcode ends
     int strand;
     uint64_t qhash2;
     int32_t fam_local, frag_local;
 };
-
-// grouping.cpp:459-543 on a private copy of the qualities
-void fix_base_qualities(uint8_t *q, const Raw & r, const uvcgpu_params & par) {
-    const int32_t l = r.l_qseq;
-    if ((0 == l) || (r.flag & 0x4)) { return; }
-    for (int32_t i = 0; i < l; i++) { q[i] = (uint8_t)std::min((int32_t)q[i] + par.assay_sequencing_BQ_inc, par.assay_sequencing_BQ_max); }
-    const int isrc = ((r.flag & 0x10) ? 1 : 0);
-    int32_t inclu_beg[2] = {0, l - 1};
-    int32_t exclu_end[2] = {l, -1};
-    int32_t end_clip_len = 0;
-    if (r.n_cigar > 0) {
-        uint32_t c = r.cigar[0];
-        if (cigar_op(c) == UVC_CSOFT_CLIP) {
-            if (0 == isrc) { inclu_beg[0] += cigar_len(c); } else { exclu_end[1] += cigar_len(c); end_clip_len = cigar_len(c); }
-        }
-        c = r.cigar[r.n_cigar - 1];
-        if (cigar_op(c) == UVC_CSOFT_CLIP) {
-            if (1 == isrc) { inclu_beg[1] -= cigar_len(c); } else { exclu_end[0] -= cigar_len(c); end_clip_len = cigar_len(c); }
-        }
-    }
-    const int32_t inc = (isrc ? -1 : 1);
-    auto seqi = [&](int32_t i) { return (int)((r.seq[i >> 1] >> ((~i & 1) << 2)) & 0xf); };
-    {   // 3'-tail penalty: long end clip and/or homopolymer-like tail until the 2nd distinct high-quality base
-        int prev_b = 0;
-        int distinct = 0;
-        const int32_t start = exclu_end[isrc] - inc;
-        int32_t termpos = start;
-        for (; termpos != inclu_beg[isrc] - inc; termpos -= inc) {
-            const int b = seqi(termpos);
-            if (b != prev_b && q[termpos] >= 20) {
-                prev_b = b;
-                distinct++;
-                if (2 == distinct) { break; }
-            }
-        }
-        const int32_t tracklen = abs(termpos - start);
-        const int32_t tail_penal = (end_clip_len >= 20 ? 1 : 0) + (tracklen >= 15 ? 2 : (tracklen >= 10 ? 1 : 0));
-        if (tail_penal > 0) {
-            for (int32_t p = start; p != (inclu_beg[isrc] - inc) && p != termpos; p -= inc) {
-                q[p] = (uint8_t)(std::max((int32_t)q[p], tail_penal + 1) - tail_penal);
-            }
-        }
-    }
-    {   // poly-G (>= 4) minus one
-        int32_t homopol = 0;
-        int prev_b = 0;
-        for (int32_t p = inclu_beg[isrc]; p != exclu_end[isrc]; p += inc) {
-            const int b = seqi(p);
-            if (b == prev_b) {
-                homopol++;
-                if (homopol >= 4 && b == 4 /* nt16 code of G */) { q[p] = (uint8_t)(std::max((int32_t)q[p], 2) - 1); }
-            } else {
-                prev_b = b;
-                homopol = 1;
-            }
-        }
-    }
-}
 
 // main.hpp:699-721. QUIRK: rank2 is computed with rulen1 when rc2 <= 1.
 bool more_str(int32_t rulen1, int32_t rc1, int32_t rulen2, int32_t rc2, int32_t repeatsize_max) {
@@ -294,6 +256,11 @@ inline uint8_t char_to_symbol(char c) { // CHAR_TO_SYMBOL (main_conversion.hpp:4
 
 } // namespace
 
+#include <chrono>
+static std::atomic<int64_t> g_prof[8];
+static inline int64_t prof_now() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define PROF(i) { const int64_t n_ = prof_now(); g_prof[i] += n_ - prof_t; prof_t = n_; }
+
 void uvc_fill_view_constants(BatchView & v, const uvcgpu_params & par) {
     v.par = par;
     for (int d = 0; d < 4; d++) { v.center_pow[d] = pow(par.dedup_center_mult, (double)d); }
@@ -322,10 +289,31 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
         std::vector<int64_t> border_psum[4];
         for (int c = 0; c < 4; c++) { beg_cnt[c].assign(fetch_size, 0); end_cnt[c].assign(fetch_size, 0); border_psum[c].assign((size_t)fetch_size + 1, 0); }
 
+        int64_t prof_t = prof_now();
         // pass 1 (grouping.cpp:666-695): end histograms and the set of fragment names that touch the tile
-        std::unordered_set<std::string> visited;
+        // set of qnames (grouping.cpp:648 visited_qnames): open addressing over read indices, names compared as strings
+        const int64_t n_in = ut.read_end - ut.read_begin;
+        size_t vcap = 16;
+        while ((int64_t)vcap < 2 * n_in) { vcap *= 2; }
+        std::vector<int32_t> vslot(vcap, -1);                 // tile-local read index of the first read that carries the name
+        std::vector<uint64_t> vhash((size_t)n_in);            // name hash of every read of the tile
+        auto visited_find = [&](const char *name, uint64_t h) -> bool {
+            for (size_t k = (size_t)h & (vcap - 1);; k = (k + 1) & (vcap - 1)) {
+                const int32_t j = vslot[k];
+                if (j < 0) { return false; }
+                if (vhash[(size_t)j] == h && 0 == strcmp(rs.qname + rs.qname_off[ut.read_begin + j], name)) { return true; }
+            }
+        };
+        auto visited_insert = [&](const char *name, uint64_t h, int32_t j_new) {
+            for (size_t k = (size_t)h & (vcap - 1);; k = (k + 1) & (vcap - 1)) {
+                const int32_t j = vslot[k];
+                if (j < 0) { vslot[k] = j_new; return; }
+                if (vhash[(size_t)j] == h && 0 == strcmp(rs.qname + rs.qname_off[ut.read_begin + j], name)) { return; }
+            }
+        };
         for (int64_t i = ut.read_begin; i < ut.read_end; i++) {
             const Raw r = get_raw(rs, i);
+            vhash[(size_t)(i - ut.read_begin)] = name_hash(r.qname);
             bool isrc = false, isr2 = false; int32_t tBeg = 0, tEnd = 0;
             if (KEEP != classify(isrc, isr2, tBeg, tEnd, r, fetch_tbeg, fetch_tend, par, end2end, pem)) { continue; }
             const int c = isrc * 2 + isr2;
@@ -333,17 +321,15 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
             if (bi >= 0 && bi < fetch_size) { beg_cnt[c][bi] += 1; }
             if (ei >= 0 && ei < fetch_size) { end_cnt[c][ei] += 1; }
             const int32_t lo = std::min(tBeg, tEnd), hi = std::max(tBeg, tEnd) + 2;
-            if (!((hi <= fetch_tbeg) || (fetch_tend <= lo))) { visited.insert(r.qname); }
+            if (!((hi <= fetch_tbeg) || (fetch_tend <= lo))) { visited_insert(r.qname, vhash[(size_t)(i - ut.read_begin)], (int32_t)(i - ut.read_begin)); }
         }
-        std::vector<int32_t> beg_center[4], end_center[4];
+        PROF(0)
         for (int c = 0; c < 4; c++) {
             int64_t bs = 0, es = 0;
             for (int32_t i = 0; i < fetch_size; i++) { bs += beg_cnt[c][i]; es += end_cnt[c][i]; border_psum[c][i + 1] = bs + es; }
-            beg_center[c].assign(fetch_size, 0); end_center[c].assign(fetch_size, 0);
-            snap_to_centers(beg_center[c], beg_cnt[c], center_pow);
-            snap_to_centers(end_center[c], end_cnt[c], center_pow);
         }
 
+        PROF(1)
         // pass 2 (grouping.cpp:731-977): family key of every kept read
         std::vector<Kept> kept;
         int32_t bam_beg = INT32_MAX, bam_end = 0;
@@ -351,7 +337,7 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
         for (int64_t i = ut.read_begin; i < ut.read_end; i++) {
             Raw r = get_raw(rs, i);
             if (r.pos < nnminus(fetch_tbeg, UVC_MAX_INSERT_SIZE + 1) || r.rend > (fetch_tend + UVC_MAX_INSERT_SIZE + 1)) { continue; }
-            if (visited.find(r.qname) == visited.end()) { continue; }
+            if (!visited_find(r.qname, vhash[(size_t)(i - ut.read_begin)])) { continue; }
             bool isrc = false, isr2 = false; int32_t tBeg = 0, tEnd = 0;
             if (KEEP != classify(isrc, isr2, tBeg, tEnd, r, fetch_tbeg, fetch_tend, par, end2end, pem)) { continue; }
             bam_beg = std::min(bam_beg, r.pos);
@@ -371,7 +357,7 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
             }
             const int c = isrc * 2 + isr2;
             const int32_t beg1 = tBeg + ARRPOS_MARGIN - fetch_tbeg, end1 = tEnd + ARRPOS_MARGIN - fetch_tbeg;
-            const int32_t beg2 = beg_center[c][beg1], end2 = end_center[c][end1];
+            const int32_t beg2 = center_at(beg_cnt[c], beg1, center_pow), end2 = center_at(end_cnt[c], end1, center_pow);
             const int64_t beg2count = beg_cnt[c][beg2], end2count = end_cnt[c][end2];
             const int32_t insL = std::min(beg2 + 6, end2);
             const int32_t insR = std::max((int64_t)beg2, nnminus(end2, 6));
@@ -407,20 +393,21 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
             const tidpos_t endpair(endtid, preserved ? r.mpos : (end2 - ARRPOS_MARGIN + fetch_tbeg));
             Kept k;
             k.raw = i; k.r = r; k.strand = read_strand(r.flag); k.qhash2 = str_hash(qname, 17);
-            k.umi_full = (umi_found ? std::string(umi_beg, umi_len) : std::string());
+            k.umi_full = (umi_found ? StrView(umi_beg, umi_len) : StrView());
             k.begpair = begpair; k.endpair = endpair;
             // MolecularBarcode::createKey (MolecularID.hpp:20-51)
             k.key.beg = tidpos_t(-1, -1); k.key.end = tidpos_t(-1, -1);
             if (0x3 == (0x3 & idflag)) { k.key.beg = std::min(begpair, endpair); k.key.end = std::max(begpair, endpair); }
             else if (0x1 & idflag) { k.key.beg = begpair; }
             else if (0x2 & idflag) { k.key.end = endpair; }
-            if (0x4 & idflag) { k.key.qname = qname; }
+            if (0x4 & idflag) { k.key.qname = StrView(qname, qlen); }
             if (0x8 & idflag) { k.key.umi = k.umi_full; }
             k.key.duplexflag = (umi_found ? 0x1 : 0) + (duplex_found ? 0x2 : 0) + (assay_amplicon ? 0x4 : 0) + (preserved ? 0x8 : 0);
             k.key.dedup_idflag = idflag;
             k.fam_local = k.frag_local = -1;
             kept.push_back(k);
         }
+        PROF(2)
         T.num_passed = (int64_t)kept.size();
         T.num_pcrpassed = pcrpassed;
         T.bam_inclu_beg = bam_beg; T.bam_exclu_end = bam_end;
@@ -442,6 +429,7 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
             if (kept[a].strand != kept[b].strand) { return kept[a].strand < kept[b].strand; }
             return kept[a].qhash2 < kept[b].qhash2;
         });
+        PROF(3)
         const int64_t read_base = (int64_t)hb.reads.size();
         for (size_t oi = 0; oi < order.size();) {
             size_t oj = oi;
@@ -455,7 +443,7 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
             // the reference keeps the MolecularBarcode of the first inserted read (file order) as the family's non-key data
             int32_t first_in_file = order[oi];
             for (size_t o = oi; o < oj; o++) { first_in_file = std::min(first_in_file, order[o]); }
-            hb.fam_umi.push_back(kept[first_in_file].umi_full);
+            hb.fam_umi.push_back(std::string(kept[first_in_file].umi_full.p, kept[first_in_file].umi_full.n));
             F.beg_tid = kept[first_in_file].begpair.first; F.beg_pos = kept[first_in_file].begpair.second;
             F.end_tid = kept[first_in_file].endpair.first; F.end_pos = kept[first_in_file].endpair.second;
             int32_t both_beg = INT32_MAX, both_end = 0;
@@ -509,11 +497,10 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
             oi = oj;
         }
 
+        PROF(4)
         // pack reads in file order
         int32_t max_span = 0;
-        std::unordered_map<int32_t, int32_t> frag_maxrend;
-        std::unordered_map<int64_t, int32_t> fam_maxrend;
-        std::unordered_map<int32_t, int32_t> famboth_maxrend;
+        std::vector<int32_t> frag_maxrend(hb.frags.size(), INT32_MIN), fam_maxrend(2 * hb.fams.size(), INT32_MIN), famboth_maxrend(hb.fams.size(), INT32_MIN);
         for (size_t i = 0; i < kept.size(); i++) {
             const Kept & k = kept[i];
             ReadRec R;
@@ -525,7 +512,6 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
             R.seq_off = hb.seq.size(); R.qual_off = hb.qual.size(); R.cigar_off = hb.cigar.size();
             hb.seq.insert(hb.seq.end(), k.r.seq, k.r.seq + (k.r.l_qseq + 1) / 2);
             hb.qual.insert(hb.qual.end(), k.r.qual, k.r.qual + k.r.l_qseq);
-            fix_base_qualities(hb.qual.data() + R.qual_off, k.r, par);
             hb.cigar.insert(hb.cigar.end(), k.r.cigar, k.r.cigar + k.r.n_cigar);
             // simple = [S|H|P]* (M|=|X) [S|H|P]*
             int lead = 0, a = 0, b = k.r.n_cigar;
@@ -543,16 +529,13 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
                 for (int c = 0; c < k.r.n_cigar; c++) { if (cigar_op(k.r.cigar[c]) == UVC_CINS || cigar_op(k.r.cigar[c]) == UVC_CDEL) { R.n_ev++; } }
                 hb.n_ev += R.n_ev;
             }
-            auto fit = frag_maxrend.find(R.frag);
-            R.fragprev_maxrend = (fit == frag_maxrend.end() ? INT32_MIN : fit->second);
-            if (fit == frag_maxrend.end()) { frag_maxrend[R.frag] = R.rend; } else { fit->second = std::max(fit->second, R.rend); }
-            const int64_t fkey = (int64_t)R.fam * 2 + R.strand;
-            auto mit = fam_maxrend.find(fkey);
-            R.famprev_maxrend = (mit == fam_maxrend.end() ? INT32_MIN : mit->second);
-            if (mit == fam_maxrend.end()) { fam_maxrend[fkey] = R.rend; } else { mit->second = std::max(mit->second, R.rend); }
-            auto bit = famboth_maxrend.find(R.fam);
-            R.fambothprev_maxrend = (bit == famboth_maxrend.end() ? INT32_MIN : bit->second);
-            if (bit == famboth_maxrend.end()) { famboth_maxrend[R.fam] = R.rend; } else { bit->second = std::max(bit->second, R.rend); }
+            R.fragprev_maxrend = frag_maxrend[(size_t)R.frag];
+            frag_maxrend[(size_t)R.frag] = std::max(frag_maxrend[(size_t)R.frag], R.rend);
+            const size_t fkey = (size_t)R.fam * 2 + R.strand;
+            R.famprev_maxrend = fam_maxrend[fkey];
+            fam_maxrend[fkey] = std::max(fam_maxrend[fkey], R.rend);
+            R.fambothprev_maxrend = famboth_maxrend[(size_t)R.fam];
+            famboth_maxrend[(size_t)R.fam] = std::max(famboth_maxrend[(size_t)R.fam], R.rend);
             max_span = std::max(max_span, R.rend - R.pos);
             hb.reads.push_back(R);
             hb.read_raw_index.push_back(k.raw);
@@ -562,6 +545,7 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
         T.n_fams = (int32_t)((int64_t)hb.fams.size() - T.fam_off);
         T.max_read_span = max_span;
 
+        PROF(5)
         // stage P1: reference symbols, repeat context, BAQ prefix sums over [ext_beg, ext_end)
         const int32_t npos = T.ext_end - T.ext_beg;
         const int32_t nref = npos - 1;
@@ -582,6 +566,7 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
         baq_prefix(hb.baq, poff, rtr, false, par);
         baq_prefix(hb.baq2, poff, rtr, true, par);
         hb.n_pos += npos;
+        PROF(6)
     }
     return 0;
 }
@@ -681,6 +666,7 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
         }
         b = HostBatch();   // release the private copy
     });
+    if (getenv("UVC_PREP_PROFILE")) { fprintf(stderr, "prep ms: pass1 %.1f centers %.1f pass2 %.1f sort %.1f families %.1f pack %.1f P1 %.1f\n", g_prof[0] / 1e6, g_prof[1] / 1e6, g_prof[2] / 1e6, g_prof[3] / 1e6, g_prof[4] / 1e6, g_prof[5] / 1e6, g_prof[6] / 1e6); for (auto & x : g_prof) { x = 0; } }
     return 0;
 }
 

@@ -60,6 +60,7 @@ UVC_HD int base3(const uint8_t *seq, int32_t i) {
 }
 UVC_HD int base4(const uint8_t *seq, int32_t i) { return (seq[i >> 1] >> ((~i & 1) << 2)) & 0xf; }
 
+UVC_HD const uvcgpu_params & par_of(const BatchView & v) { return v.par; }
 UVC_HD int read_strand(uint16_t flag) { return (((flag & 0x81) == 0x81) ? (!!(flag & 0x20)) : (!!(flag & 0x10))); }
 
 // Range [lo, hi) of the tile's reads whose start lies in (p - max_span, p]: the only reads that can cover p.
@@ -113,6 +114,64 @@ UVC_HD bool primer_masked(const BatchView & v, const ReadRec & R, const ReadDeri
     return !((normal_filters_primers || !is_assay_amplicon) || (D.ibeg <= rpos && rpos < D.iend));
 }
 
+// apply_bq_err_correction3 (grouping.cpp:459-543) on the read's own copy of its base qualities: the platform increment and cap, the 3'-tail
+// penalty (long end clip and/or a low-complexity tail up to the 2nd distinct base of quality >= 20), and poly-G (>= 4) minus one.
+UVC_HD void fix_base_qualities(uint8_t *q, const uint8_t *seq, const uint32_t *cigar, const ReadRec & R, const uvcgpu_params & par) {
+    const int32_t l = R.l_qseq;
+    if ((0 == l) || (R.flag & 0x4)) { return; }
+    for (int32_t i = 0; i < l; i++) { q[i] = (uint8_t)tmin((int32_t)q[i] + par.assay_sequencing_BQ_inc, par.assay_sequencing_BQ_max); }
+    const int isrc = ((R.flag & 0x10) ? 1 : 0);
+    int32_t inclu_beg[2] = {0, l - 1};
+    int32_t exclu_end[2] = {l, -1};
+    int32_t end_clip_len = 0;
+    if (R.n_cigar > 0) {
+        uint32_t c = cigar[0];
+        if (cig_op(c) == UVC_CSOFT_CLIP) {
+            if (0 == isrc) { inclu_beg[0] += cig_len(c); } else { exclu_end[1] += cig_len(c); end_clip_len = cig_len(c); }
+        }
+        c = cigar[R.n_cigar - 1];
+        if (cig_op(c) == UVC_CSOFT_CLIP) {
+            if (1 == isrc) { inclu_beg[1] -= cig_len(c); } else { exclu_end[0] -= cig_len(c); end_clip_len = cig_len(c); }
+        }
+    }
+    const int32_t inc = (isrc ? -1 : 1);
+    {
+        int prev_b = 0;
+        int distinct = 0;
+        const int32_t start = exclu_end[isrc] - inc;
+        int32_t termpos = start;
+        for (; termpos != inclu_beg[isrc] - inc; termpos -= inc) {
+            const int b = base4(seq, termpos);
+            if (b != prev_b && q[termpos] >= 20) {
+                prev_b = b;
+                distinct++;
+                if (2 == distinct) { break; }
+            }
+        }
+        const int32_t tracklen = iabs(termpos - start);
+        const int32_t tail_penal = (end_clip_len >= 20 ? 1 : 0) + (tracklen >= 15 ? 2 : (tracklen >= 10 ? 1 : 0));
+        if (tail_penal > 0) {
+            for (int32_t p = start; p != (inclu_beg[isrc] - inc) && p != termpos; p -= inc) {
+                q[p] = (uint8_t)(tmax((int32_t)q[p], tail_penal + 1) - tail_penal);
+            }
+        }
+    }
+    {
+        int32_t homopol = 0;
+        int prev_b = 0;
+        for (int32_t p = inclu_beg[isrc]; p != exclu_end[isrc]; p += inc) {
+            const int b = base4(seq, p);
+            if (b == prev_b) {
+                homopol++;
+                if (homopol >= 4 && b == 4 /* nt16 code of G */) { q[p] = (uint8_t)(tmax((int32_t)q[p], 2) - 1); }
+            } else {
+                prev_b = b;
+                homopol = 1;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K0: one thread per read
 // Read-level constants (main.hpp:937-998, 1789-1885), the per-reference-base expansion and the low-quality-indel
 // neighbours of complex reads (main.hpp:1817-1859, 1897-1916, 2219-2252), the list of indel events, and the rare
@@ -123,6 +182,7 @@ UVC_HD void k0_read(const BatchView & v, int64_t ri) {
     const TileInfo & T = v.tiles[R.tile];
     const uint32_t *cigar = v.cigar + R.cigar_off;
     const uint8_t *seq = v.seq + R.seq_off;
+    fix_base_qualities(v.qual + R.qual_off, seq, cigar, R, par_of(v));
     const uint8_t *qual = v.qual + R.qual_off;
     const int64_t po = T.pos_off - T.ext_beg;        // concatenated index of reference position x is po + x
     const int32_t npos = T.ext_end - T.ext_beg;
