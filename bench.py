@@ -1,15 +1,21 @@
 #!/usr/bin/env python
-"""bench.py - throughput of the pileup-and-score hot path on synthetic input (contract: see DESIGN.md section "Measurement").
+"""bench.py - throughput of the pileup-and-score hot path on synthetic input (contract: DESIGN.md section "Measurement").
 
-A "step" is one pass of the hot path over one batch of synthetic tiles. Metric (BASELINE.json): aligned reads/sec
-(`value`) and genomic positions/sec (`positions_per_s`). `value` is kernel throughput with inputs resident in HBM (CUDA
-events on the library's stream); `e2e` is the same metric through the C ABI from HOST buffers (host staging + H2D + kernels
-+ D2H of the per-batch result inside the timed region). `--impl reference` times the unmodified reference `uvc1` (built
-under oracle/_ref) on the box's host cores on a bounded sample of the same workload.
+A "step" is one pass of the hot path over one batch of synthetic input: all tier-3 tiles of the named workload (tile list from the
+reference-identical tiler, -t 16). Metric (BASELINE.json): aligned reads/sec (`value`) and genomic positions/sec (`positions_per_s`).
+
+* `value`    - device throughput with the inputs resident in HBM: sum of the CUDA-event times of every kernel of the step (events on the
+               library's own stream), one context, whole batch per launch.
+* `e2e`      - the same metric through the C ABI from HOST buffers (decoded BAM records in SoA form): host staging, H2D, kernels, D2H and
+               VCF text inside the timed wall clock. The batch is cut into sub-batches that run on a few contexts (one CUDA stream each),
+               so that staging, copies and kernels of different sub-batches overlap - the same schedule the uvc1 host uses.
+* `roofline` - the kernel with the largest share of the step, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+* `cpu_baseline` / `--impl reference` - the unmodified reference uvc1 (oracle/_ref) with all host threads on the same BAM.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import hashlib
 import json
 import os
@@ -22,7 +28,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-STAGES_IMPLEMENTED = "P0 grouping(host)+P1 refctx(host)+K0 read consts+K1 prep/thres+K2 bias pileup+K2e indel events+KF fragment columns+K3 fragment consensus+KM family columns+K4 family/duplex consensus (= updateByRegion3Aln)+K6 block-line inputs+K5 candidate scoring+VCF text(host) = process_batch"
+STAGE_NAMES = ["K0 per-read", "K1 prep+thres", "K2 bias pileup", "K2e indel events", "KF fragment columns", "K3a fragment stats", "K3b fragment consensus",
+               "KM family columns", "K4a family ends", "K4 family+duplex consensus", "K4c family haplotypes", "K6 block-line inputs", "K5 candidate scoring"]
+STAGES_IMPLEMENTED = ("P0 read filter+family grouping (host), P1 repeat context (host), K0..K4c = updateByRegion3Aln, K6 block-line inputs, "
+                      "K5a/K5 candidate scoring, VCF text (host) = process_batch")
+WORKLOADS = {"c1": "uvc1 tumor-only, synthetic 1 Mbp @100x, non-UMI (BASELINE.json configs[0])",
+             "c2": "targeted panel 2 Mbp @2000x non-UMI, low-VAF spikes (BASELINE.json configs[1])",
+             "c3": "UMI duplex panel 1 Mbp @20000x (BASELINE.json configs[2])"}
+# c2 and c3 are run on a fraction of their region (same depth, same tile shapes): the pure-Python generator needs minutes per million reads,
+# and the default run has to finish within minutes on a fresh box. The fraction is part of `config.workload`.
+DEFAULT_SCALE = {"c1": 1.0, "c2": 0.05, "c3": 0.002}
+TILER_THREADS = 16
 
 
 def parse_args():
@@ -33,15 +49,11 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2")
     ap.add_argument("--scale", type=float, default=None, help="fraction of the named config's region (default: per-config)")
-    ap.add_argument("--tile", type=int, default=20000, help="tier-3 tile length used until the reference tiler is ported")
     ap.add_argument("--workdir", default=os.environ.get("UVC_BENCH_DIR", "/tmp/uvc_bench"))
-    ap.add_argument("--ref-scale", type=float, default=None, help="sample of the workload for the CPU reference")
+    ap.add_argument("--contexts", type=int, default=3, help="contexts (CUDA streams) the e2e step pipelines its sub-batches over")
+    ap.add_argument("--sub-batches", type=int, default=6)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()
-
-
-DEFAULT_SCALE = {"c1": 1.0, "c2": 0.05, "c3": 0.02}
-DEFAULT_REF_SCALE = {"c1": 0.1, "c2": 0.003, "c3": 0.001}
 
 
 def dataset(workdir: str, name: str, scale: float):
@@ -62,28 +74,30 @@ def dataset(workdir: str, name: str, scale: float):
     return out
 
 
-def make_tiles(ds, tile_len: int):
+class _BedLine(C.Structure):
+    _fields_ = [("tid", C.c_int32), ("beg_pos", C.c_int32), ("end_pos", C.c_int32), ("region_flag", C.c_uint32), ("n_reads", C.c_int64)]
+
+
+def tile_list(ds, nthreads: int = TILER_THREADS):
+    """Tier-3 tiles exactly as the uvc1 host cuts them (uvc_b200/csrc/host/tiler.cpp = the reference's SamIter for -t nthreads)."""
+    from uvc_b200 import capi
+    lib = capi.load_host()
+    lib.uvchost_tiler_open.restype = C.c_void_p
+    lib.uvchost_tiler_open.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32]
+    lib.uvchost_tiler_next.restype = C.c_int64
+    lib.uvchost_tiler_next.argtypes = [C.c_void_p, C.POINTER(C.POINTER(_BedLine)), C.POINTER(C.c_int64)]
+    lib.uvchost_tiler_close.argtypes = [C.c_void_p]
+    t = lib.uvchost_tiler_open(ds["bam"].encode(), (ds.get("bed") or "").encode(), b"", nthreads, 1536, -1, 0)
     tiles = []
-    for tid, (name, length) in enumerate(ds["contigs"]):
-        if ds.get("targets"):
-            # panel: contiguous runs of targets, cut every tile_len
-            beg = None
-            last = None
-            for (ci, b, e) in ds["targets"]:
-                if ci != tid:
-                    continue
-                if beg is None:
-                    beg, last = max(0, b - 200), e + 200
-                elif b - 200 - last > 200 or (e + 200 - beg) > tile_len:
-                    tiles.append((tid, beg, min(last, length), 8))
-                    beg, last = b - 200, e + 200
-                else:
-                    last = e + 200
-            if beg is not None:
-                tiles.append((tid, beg, min(last, length), 2))
-        else:
-            for b in range(0, length, tile_len):
-                tiles.append((tid, b, min(length, b + tile_len), 4))
+    while True:
+        p, n = C.POINTER(_BedLine)(), C.c_int64()
+        nreads = lib.uvchost_tiler_next(t, C.byref(p), C.byref(n))
+        if nreads < 0:
+            raise RuntimeError("tiler failed")
+        if nreads == 0 and n.value == 0:
+            break
+        tiles += [(p[i].tid, p[i].beg_pos, p[i].end_pos, p[i].region_flag) for i in range(n.value)]
+    lib.uvchost_tiler_close(t)
     return tiles
 
 
@@ -111,20 +125,20 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def run_reference(args, name, ref_scale):
-    """Times the unmodified reference uvc1 (oracle/_ref) with all host threads on a bounded sample of the workload."""
+def run_reference(args, ds, name):
+    """Times the unmodified reference uvc1 (oracle/_ref) with all host threads on the bench workload's own BAM (bounded: the c2/c3 workloads
+    are already fractions of the named configs; c1 takes a few seconds)."""
     uvc1 = os.path.join(ROOT, "oracle", "_ref", "uvc1")
-    ds = dataset(args.workdir, name, ref_scale)
     cores = os.cpu_count() or 1
     best = None
-    runs = max(1, min(args.steps, 3))
+    runs = max(1, min(args.steps, 2))
     for _ in range(runs):
         out_vcf = os.path.join(args.workdir, "ref_%s.vcf.gz" % name)
         cmd = [uvc1, ds["bam"], "-f", ds["fasta"], "-o", out_vcf, "-s", "S", "-t", str(cores)]
@@ -140,25 +154,46 @@ def run_reference(args, name, ref_scale):
         best = wall_ref if best is None else min(best, wall_ref)
     npos = sum(l for _, l in ds["contigs"]) if not ds.get("targets") else sum(e - b for _, b, e in ds["targets"])
     return dict(value=ds["n_reads"] / best, unit="reads/s", cores=cores, kind="reference",
-                sample="%s at scale %g: %d reads, %d positions, uvc1 -t %d, best of %d, %.2f s" % (name, ref_scale, ds["n_reads"], npos, cores, runs, best),
+                sample="the bench workload itself: %d reads, %d positions; uvc1 -t %d (BAM decode, tiling and BGZF output included), best of %d, %.2f s" % (
+                    ds["n_reads"], npos, cores, runs, best),
                 positions_per_s=npos / best, seconds=best)
+
+
+def kernel_algorithmic_bytes(stage: int, st, n_reads: int) -> float:
+    """Compulsory bytes of one launch of a kernel: its inputs read once plus its outputs written once."""
+    P, R = float(st.n_ext_positions), float(n_reads)
+    read_rec = 1.5 * 150 + 64                      # SURVEY 8d: packed bases + qualities + cigar + scalars of one read
+    table = {
+        1: R * read_rec + P * (208 + 72),                                   # K1: reads -> prep + thres
+        2: R * read_rec + P * (72 + 14 * 152 + 14 * 4 + 14 * 4 * 4),        # K2: reads + thres -> seginfo, bqsum, 4 VQ tags
+        4: R * read_rec + R * 150 * 8 / 2,                                  # KF: reads -> 8 B column entry per fragment base (2 reads per fragment)
+        5: R * 150 * 8 / 2,                                                 # K3a: fragment columns
+        6: R * 150 * 8 / 2 + P * (2 * 14 * 3 * 4 + 14 * 4 * 4),             # K3b: fragment columns -> fragdepth + 4 VQ tags
+        7: R * 150 * (8 + 32) / 2,                                          # KM: fragment columns -> family columns
+        9: R * 150 * 32 / 2 + P * (72 + 2 * 14 * 8 * 4 + 14 * 72 + 14 * 2 * 4 + 14 * 6 * 4),   # K4: family columns + thres -> famdepth, faminfo, duplex, 6 VQ tags
+        10: R * 150 * 32 / 2,                                               # K4c
+        11: P * 6272,                                                       # K6 reads the depth arrays of every position
+        12: P * 6272,                                                       # K5a/K5 read the position state once
+    }
+    return table.get(stage, P * 6272)
 
 
 def main():
     args = parse_args()
     name = args.config
     scale = args.scale if args.scale is not None else DEFAULT_SCALE.get(name, 1.0)
-    ref_scale = args.ref_scale if args.ref_scale is not None else DEFAULT_REF_SCALE.get(name, 0.01)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = "%s scale %g (BASELINE.json configs: %s)" % (name, scale, {"c1": "1 Mbp @100x non-UMI", "c2": "targeted panel 2 Mbp @2000x", "c3": "UMI duplex 1 Mbp @20000x"}.get(name, name))
+    workload = "%s; region fraction %g" % (WORKLOADS.get(name, name), scale)
+    metric = "aligned reads/sec (and positions/sec) called"
 
     if args.impl == "reference":
         if rank != 0:
             return
-        res = run_reference(args, name, ref_scale)
-        line = {"impl": "reference", "metric": "aligned reads/sec (and positions/sec) called", "value": res["value"], "unit": "reads/s",
+        ds = dataset(args.workdir, name, scale)
+        res = run_reference(args, ds, name)
+        line = {"impl": "reference", "metric": metric, "value": res["value"], "unit": "reads/s",
                 "positions_per_s": res["positions_per_s"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": res["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64 counters, f64 scoring",
                 "data": "synthetic", "config": {"workload": workload, "reference_sample": res["sample"]},
@@ -181,56 +216,119 @@ def main():
         dist.barrier()
         if rank != 0:
             ds = dataset(args.workdir, name, scale)
-    tiles = make_tiles(ds, args.tile)
-    my_tiles = tiles[rank::world] if world > 1 else tiles   # regions are independent: weak scaling = every rank gets its own copy below
-    if world > 1:
-        my_tiles = tiles  # weak scaling: each rank processes the whole per-GPU workload (independent tiles, no collective on the path)
+    # Regions are independent: no data-path collective. Weak scaling: every rank (GPU) processes its own copy of the per-GPU workload.
+    tiles = tile_list(ds)
+    host_threads = max(1, (os.cpu_count() or 1) // world)
 
-    # host-side decode (untimed): BAM -> SoA records of every tile's fetch window
+    # host-side decode (untimed): BAM -> SoA records of every tile's fetch window (what sam_itr_queryi(tid, beg - 2000, end + 2000) yields)
     bf = capi.BamFile(ds["bam"])
     rb = capi.ReadBuf()
-    ctx = capi.Context(local_rank)
-    for tid, (cname, _) in enumerate(ds["contigs"]):
-        ctx.set_contig(tid, capi.read_fasta_contig(ds["fasta"], cname))
-        ctx.set_contig_name(tid, cname)
     ctiles = []
     prev = (-1, 0, 0)
     t_dec0 = time.time()
-    for (tid, beg, end, flag) in my_tiles:
+    for (tid, beg, end, flag) in tiles:
         r0 = len(rb)
         bf.fetch_into(rb, tid, max(0, beg - 2000), end + 2000)
         ctiles.append(capi.make_tile(tid, beg, end, flag, ds["contigs"][tid][1], r0, len(rb), prev))
         prev = (tid, beg, end)
     decode_s = time.time() - t_dec0
     view = rb.view()
+    contig_bases = {tid: capi.read_fasta_contig(ds["fasta"], cname) for tid, (cname, _) in enumerate(ds["contigs"])}
 
-    def step():
-        ticket = ctx.submit(ctiles, view)
+    def make_ctx(threads):
+        ctx = capi.Context(local_rank)
+        ctx.lib.uvcgpu_set_host_threads.argtypes = [C.c_void_p, C.c_int32]
+        ctx.lib.uvcgpu_set_host_threads(ctx.handle, threads)
+        for tid, (cname, _) in enumerate(ds["contigs"]):
+            ctx.set_contig(tid, contig_bases[tid])
+            ctx.set_contig_name(tid, cname)
+        return ctx
+
+    def run_tiles(ctx, sub):
+        ticket = ctx.submit(sub, view)
         ctx.collect(ticket)
-        st = ctx.score(ticket)               # candidate scoring on the device (K5/K6) + D2H of the kept records
+        st = ctx.score(ticket)               # candidate scoring on the device + D2H of the kept records and block-line inputs
         nbytes = 0
-        for ti in range(len(ctiles)):        # the step's result: every tile's VCF body text
+        for ti in range(len(sub)):           # the step's result: every tile's VCF body text
             nbytes += len(ctx.tile_vcf(ticket, ti))
         ctx.release(ticket)
         st.vcf_bytes = nbytes
         return st
 
-    sampler = ClockSampler(local_rank)
-    for _ in range(max(args.warmup, 3)):
-        step()
+    # ---- phase 1: device-resident throughput (`value`): one context, the whole batch per launch, CUDA-event time of every kernel
+    ctx0 = make_ctx(host_threads)
+    n_warm = max(args.warmup, 3)
+    for _ in range(n_warm):
+        run_tiles(ctx0, ctiles)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
     sampler.start()
     kernel_ms = 0.0
     stage_ms = [0.0] * 16
-    t0 = time.time()
+    launches = 0
     last = None
     for _ in range(args.steps):
-        last = step()
+        last = run_tiles(ctx0, ctiles)
         kernel_ms += last.kernel_ms
+        launches += int(last.gpu_launches)
         for i in range(16):
             stage_ms[i] += last.kernel_ms_by_stage[i]
+    torch.cuda.synchronize()
+
+    # ---- phase 2: end to end from host buffers: sub-batches pipelined over a few contexts (streams)
+    n_ctx = max(1, min(args.contexts, len(ctiles)))
+    n_sub = max(n_ctx, min(args.sub_batches, len(ctiles)))
+    subs = [ctiles[len(ctiles) * k // n_sub: len(ctiles) * (k + 1) // n_sub] for k in range(n_sub)]
+    subs = [s for s in subs if s]
+    ctxs = [ctx0] + [make_ctx(max(1, host_threads // n_ctx + 1)) for _ in range(n_ctx - 1)]
+    ctx0.lib.uvcgpu_set_host_threads(ctx0.handle, max(1, host_threads // n_ctx + 1))
+    totals = {"h2d": 0, "d2h": 0, "vcf": 0, "rec": 0, "launch": 0, "prep_ms": 0.0}
+
+    def e2e_step():
+        nxt = [0]
+        lock = threading.Lock()
+        acc = {"h2d": 0, "d2h": 0, "vcf": 0, "rec": 0, "launch": 0, "prep_ms": 0.0}
+        errs = []
+
+        def work(ctx):
+            try:
+                while True:
+                    with lock:
+                        k = nxt[0]
+                        nxt[0] += 1
+                    if k >= len(subs):
+                        return
+                    st = run_tiles(ctx, subs[k])
+                    with lock:
+                        acc["h2d"] += int(st.h2d_bytes)
+                        acc["d2h"] += int(st.d2h_bytes)
+                        acc["vcf"] += int(st.vcf_bytes)
+                        acc["rec"] += int(st.n_vcf_records)
+                        acc["launch"] += int(st.gpu_launches)
+                        acc["prep_ms"] += st.host_prep_ms
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        ths = [threading.Thread(target=work, args=(c,)) for c in ctxs]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            raise errs[0]
+        return acc
+
+    for _ in range(n_warm):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for _ in range(args.steps):
+        acc = e2e_step()
+        for k in totals:
+            totals[k] += acc[k]
     torch.cuda.synchronize()
     wall_s = time.time() - t0
     sampler.stop_flag = True
@@ -241,12 +339,11 @@ def main():
         dist.barrier()
     if rank != 0:
         return
-    n_reads = last.n_reads_kept
-    n_positions = last.n_positions
+    n_reads = int(ds["n_reads"])             # primary mapped records of the BAM, each counted once, not once per overlapping tile
+    n_positions = int(last.n_positions)
     units = world
     value = units * n_reads * args.steps / (kernel_ms / 1e3)
     e2e = units * n_reads * args.steps / wall_s
-    # roofline of the dominant kernel: algorithmic bytes of the stages it implements / its event time
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -254,31 +351,46 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     dom = max(range(16), key=lambda i: stage_ms[i])
-    STAGE_NAMES = ["K0 per-read", "K1 prep+thres", "K2 bias pileup", "K2e indel events", "KF fragment columns", "K3a fragment stats", "K3b fragment consensus", "KM family columns",
-                   "K4a family ends", "K4 family+duplex consensus", "K4c family haplotypes", "K6 block-line inputs", "K5 candidate scoring"]
     dom_name = STAGE_NAMES[dom] if dom < len(STAGE_NAMES) else "stage%d" % dom
-    bytes_alg = n_reads * (1.5 * 150 + 64) + last.n_ext_positions * 2 * 6272
-    achieved = bytes_alg / (stage_ms[dom] / args.steps / 1e3) / 1e9
-    line = {"metric": "aligned reads/sec (and positions/sec) called", "value": value, "unit": "reads/s",
+    dom_ms = stage_ms[dom] / args.steps
+    dom_bytes = kernel_algorithmic_bytes(dom, last, int(last.n_reads_kept))
+    achieved = dom_bytes / (dom_ms / 1e3) / 1e9
+    step_ms = kernel_ms / args.steps
+    path_bytes = last.n_reads_kept * (1.5 * 150 + 64) + last.n_ext_positions * 2 * 6272
+    traffic = None
+    try:   # dram bytes of that kernel from the committed ncu --set full capture of the same workload (profiles/), per launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        ent = tj.get("%s@%g" % (name, scale), {}).get(dom_name)
+        if ent:
+            traffic = ent["dram_bytes"]
+    except Exception:
+        pass
+    line = {"metric": metric, "value": value, "unit": "reads/s",
             "positions_per_s": units * n_positions * args.steps / (kernel_ms / 1e3),
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64 counters",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": n_warm, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64 counters, f64 scoring",
             "data": "synthetic",
-            "config": {"workload": workload, "tiles": len(ctiles), "tile_len": args.tile, "reads_per_step": int(n_reads), "positions_per_step": int(n_positions),
-                       "ext_positions_per_step": int(last.n_ext_positions), "stages": STAGES_IMPLEMENTED, "l2": "inputs (%.0f MB counters) larger than L2" % (last.n_ext_positions * 6272 / 1e6),
-                       "host_decode_s_untimed": decode_s},
-            "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(last.h2d_bytes), "d2h_bytes_per_step": int(last.d2h_bytes), "vcf_bytes_per_step": int(last.vcf_bytes), "vcf_records_per_step": int(last.n_vcf_records),
-                    "host_score_ms_per_step": last.host_score_ms,
-                    "host_prep_ms_per_step": last.host_prep_ms, "wall_ms_per_step": wall_s * 1e3 / args.steps},
-            "gpu_launches": int(last.gpu_launches) * args.steps,
+            "config": {"workload": workload, "tiles": len(ctiles), "tiler": "reference SamIter semantics, -t %d" % TILER_THREADS,
+                       "reads_per_step": n_reads, "read_records_per_step_incl_tile_halos": int(last.n_reads_kept),
+                       "positions_per_step": n_positions, "ext_positions_per_step": int(last.n_ext_positions), "stages": STAGES_IMPLEMENTED,
+                       "l2": "per-position state of a step (%.0f MB) is larger than L2, no flush needed" % (last.n_ext_positions * 6272 / 1e6),
+                       "host_decode_s_untimed": decode_s, "dataset_generation_s_untimed": ds.get("gen_s"),
+                       "e2e_schedule": "%d sub-batches over %d contexts (streams), %d host threads" % (len(subs), len(ctxs), host_threads)},
+            "e2e": {"value": e2e, "unit": "reads/s", "positions_per_s": units * n_positions * args.steps / wall_s,
+                    "h2d_bytes_per_step": totals["h2d"] // args.steps, "d2h_bytes_per_step": totals["d2h"] // args.steps,
+                    "vcf_bytes_per_step": totals["vcf"] // args.steps, "vcf_records_per_step": totals["rec"] // args.steps,
+                    "host_prep_ms_per_step_summed_over_contexts": totals["prep_ms"] / args.steps, "wall_ms_per_step": wall_s * 1e3 / args.steps},
+            "gpu_launches": launches + totals["launch"],
             "stage_ms_per_step": {n: stage_ms[i] / args.steps for i, n in enumerate(STAGE_NAMES)},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": dom_name, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                         "algorithmic_bytes": bytes_alg},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": dom_name, "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / step_ms, "algorithmic_bytes": dom_bytes,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "whole_path": {"algorithmic_bytes": path_bytes, "achieved": path_bytes / (step_ms / 1e3) / 1e9,
+                                        "frac": path_bytes / (step_ms / 1e3) / 1e9 / peak}},
             "clocks": sampler.summary()}
     if not args.skip_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "uvc1")):
         try:
-            res = run_reference(args, name, ref_scale)
+            res = run_reference(args, ds, name)
             line["cpu_baseline"] = {"value": res["value"], "unit": "reads/s", "cores": res["cores"], "kind": "reference", "sample": res["sample"],
                                     "positions_per_s": res["positions_per_s"]}
         except Exception as e:  # noqa: BLE001
