@@ -138,8 +138,22 @@ struct FamRec {
     int32_t nsb_min[2], nsb_max[2];    // no_strict_bias_pos_min/max (main.hpp:2959-2998), kernel K4a
     int32_t beg_tid, beg_pos, end_tid, end_pos;
     int32_t lo[2], hi[2];              // covered extent of each strand: min pos, max rend over its reads (lo >= hi: no reads)
-    int64_t col_off[2];                // first entry of each strand's column in mcol (multiple of 32)
+    int64_t col_off[2];                // first entry of each strand's column in mcol (multiple of 32); unused when direct_frag >= 0
+    int32_t direct_frag[2];            // a strand with a single fragment has no column of its own: its entries are derived on the fly
+                                       // from that fragment's column (8 B instead of 32 B per position); -1 = materialised in mcol
 };
+
+// What the position kernels of the family stage need from a read, 32 B (instead of chasing ReadRec -> FamRec): built on the host.
+struct ReadFam {
+    int32_t rend, famprev_maxrend, fambothprev_maxrend, fam;
+    int64_t col_base;                  // index of the (family, strand) entry at position p is col_base + p (mcol, or fcol when UVC_RF_DIRECT)
+    uint32_t flags;                    // UVC_RF_*
+    int32_t pad;
+};
+#define UVC_RF_STRAND 1u
+#define UVC_RF_DIRECT 2u               // col_base points into fcol (single-fragment family-strand)
+#define UVC_RF_DUPLEX_UMI 4u           // family has a duplex UMI (duplexflag & 0x2)
+#define UVC_RF_BOTH_STRANDS 8u         // family has fragments on both strands
 
 struct BatchView {
     uvcgpu_params par;
@@ -168,6 +182,7 @@ struct BatchView {
     const FragRec *frags_in; FragRec *frags;
     const int32_t *frag_reads;
     FamRec *fams;
+    const ReadFam *rfam;           // [n_reads]
     // per-fragment and per-(family, strand) columns
     int64_t n_fcol, n_mcol;        // padded entry counts (multiples of UVC_COL_CHUNK)
     FragCol *fcol;

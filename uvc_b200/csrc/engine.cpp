@@ -587,6 +587,7 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
     UVC_UP(frags, FragRec, hb.frags)
     UVC_UP(frag_reads, int32_t, hb.frag_reads)
     UVC_UP(fams, FamRec, hb.fams)
+    UVC_UP(rfam, ReadFam, hb.rfam)
     UVC_UP(slip_tab, int32_t, ctx->slip_tab)
     UVC_UP(fchunk_frag, int32_t, hb.fchunk_frag)
     UVC_UP(mchunk_fs, int32_t, hb.mchunk_fs)

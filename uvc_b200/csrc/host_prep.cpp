@@ -485,7 +485,9 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
                 F.beg2[strand] = s_beg; F.end2[strand] = s_end;
                 F.lo[strand] = (F.n_frags[strand] > 0 ? s_beg : 0); F.hi[strand] = (F.n_frags[strand] > 0 ? s_hi : 0);
                 F.col_off[strand] = hb.n_mcol;
-                hb.n_mcol += ((int64_t)(F.hi[strand] - F.lo[strand]) + UVC_COL_CHUNK - 1) / UVC_COL_CHUNK * UVC_COL_CHUNK;
+                F.direct_frag[strand] = -1;
+                if (1 == F.n_frags[strand] && !(par.microadjust_padded_deletion_flag & 0x1)) { F.direct_frag[strand] = F.frag_off[strand]; }
+                else { hb.n_mcol += ((int64_t)(F.hi[strand] - F.lo[strand]) + UVC_COL_CHUNK - 1) / UVC_COL_CHUNK * UVC_COL_CHUNK; }
                 // MEDIAN of the unsorted vectors (main_conversion.hpp:24-28, main.hpp:2939-2940)
                 F.l2r_end_median[strand] = (l2r_end.size() ? (l2r_end[(l2r_end.size() - 1) / 2] + l2r_end[l2r_end.size() / 2]) / 2 : s_end);
                 F.r2l_end_median[strand] = (r2l_end.size() ? (r2l_end[(r2l_end.size() - 1) / 2] + r2l_end[r2l_end.size() / 2]) / 2 : s_beg);
@@ -616,7 +618,7 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
     if (tot.read > INT32_MAX || tot.frag > INT32_MAX || tot.cx > INT32_MAX || tot.ev > INT32_MAX || tot.fragread > INT32_MAX || tot.fam > INT32_MAX / 2) { msg = "batch too large: submit fewer tiles"; return UVCGPU_EINVAL; }
     hb.tiles.resize((size_t)n_tiles);
     hb.pos_tile.resize((size_t)tot.pos); hb.refsym.resize((size_t)tot.pos); hb.rtr.resize((size_t)tot.pos); hb.baq.resize((size_t)tot.pos); hb.baq2.resize((size_t)tot.pos);
-    hb.reads.resize((size_t)tot.read); hb.read_raw_index.resize((size_t)tot.read);
+    hb.reads.resize((size_t)tot.read); hb.read_raw_index.resize((size_t)tot.read); hb.rfam.resize((size_t)tot.read);
     hb.seq.resize((size_t)tot.seq); hb.qual.resize((size_t)tot.qual); hb.cigar.resize((size_t)tot.cigar);
     hb.frags.resize((size_t)tot.frag); hb.frag_reads.resize((size_t)tot.fragread); hb.fams.resize((size_t)tot.fam); hb.fam_umi.resize((size_t)tot.fam);
     hb.n_pos = tot.pos; hb.n_cx = tot.cx; hb.n_ev = tot.ev; hb.n_fcol = tot.fcol; hb.n_mcol = tot.mcol;
@@ -657,12 +659,29 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
             FamRec F = b.fams[i];
             F.frag_off[0] += (int32_t)o.frag; F.frag_off[1] += (int32_t)o.frag;
             F.col_off[0] += o.mcol; F.col_off[1] += o.mcol;
+            for (int strand = 0; strand < 2; strand++) { if (F.direct_frag[strand] >= 0) { F.direct_frag[strand] += (int32_t)o.frag; } }
             hb.fams[(size_t)o.fam + i] = F;
             for (int strand = 0; strand < 2; strand++) {
+                if (F.direct_frag[strand] >= 0) { continue; }
                 const int64_t c1 = F.col_off[strand] / UVC_COL_CHUNK + ((int64_t)(F.hi[strand] - F.lo[strand]) + UVC_COL_CHUNK - 1) / UVC_COL_CHUNK;
                 for (int64_t c = F.col_off[strand] / UVC_COL_CHUNK; c < c1; c++) { hb.mchunk_fs[(size_t)c] = (int32_t)(2 * (o.fam + (int64_t)i) + strand); }
             }
             hb.fam_umi[(size_t)o.fam + i].swap(b.fam_umi[i]);
+        }
+        for (size_t i = 0; i < b.reads.size(); i++) {
+            const ReadRec & R = hb.reads[(size_t)o.read + i];
+            const FamRec & F = hb.fams[(size_t)R.fam];
+            ReadFam q;
+            q.rend = R.rend; q.famprev_maxrend = R.famprev_maxrend; q.fambothprev_maxrend = R.fambothprev_maxrend; q.fam = R.fam; q.pad = 0;
+            q.flags = (R.strand ? UVC_RF_STRAND : 0u) | ((F.duplexflag & 0x2) ? UVC_RF_DUPLEX_UMI : 0u) | ((F.n_frags[0] > 0 && F.n_frags[1] > 0) ? UVC_RF_BOTH_STRANDS : 0u);
+            if (F.direct_frag[R.strand] >= 0) {
+                const FragRec & G = hb.frags[(size_t)F.direct_frag[R.strand]];
+                q.flags |= UVC_RF_DIRECT;
+                q.col_base = G.col_off - G.lo;
+            } else {
+                q.col_base = F.col_off[R.strand] - F.lo[R.strand];
+            }
+            hb.rfam[(size_t)o.read + i] = q;
         }
         b = HostBatch();   // release the private copy
     });

@@ -44,6 +44,7 @@ struct HostBatch {
     StageVec<FragRec> frags;
     StageVec<int32_t> frag_reads;
     StageVec<FamRec> fams;
+    StageVec<ReadFam> rfam;               // per read, see batch.h
     std::vector<std::string> fam_umi;     // umistring of each family (for the grouping dump)
     StageVec<int32_t> fchunk_frag, mchunk_fs;   // owner of every 32-entry chunk of the fragment / family-strand columns
     int64_t n_fcol = 0, n_mcol = 0;       // padded column entries

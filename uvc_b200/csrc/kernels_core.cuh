@@ -1281,6 +1281,24 @@ UVC_HD void km_family_column(const BatchView & v, int64_t i) {
     v.mcol[i] = m;
 }
 
+// The family entry of a strand that holds a single fragment, derived from that fragment's entry: at most one vote per symbol type
+// (read_family_con_ampl / read_family_mmm_ampl with one fragment, main.hpp:466-520), so nothing needs to be materialised.
+UVC_HD FamCol famcol_from_frag(const FragCol & e, const uvcgpu_params & par) {
+    FamCol m;
+    m.a1[0] = m.a2[0] = (uint8_t)UVC_BASE_NN; m.a1[1] = m.a2[1] = (uint8_t)UVC_LINK_NN;   // consensus over all-zero counts returns the last symbol of the type
+    m.cc1[0] = m.tc1[0] = m.con_a2[0] = 0; m.cc1[1] = m.tc1[1] = m.con_a2[1] = 0;
+    m.mmm_cc[0] = m.mmm_tot[0] = 0; m.mmm_cc[1] = m.mmm_tot[1] = 0;
+    if (e.link_cc > 0) {
+        m.a1[1] = m.a2[1] = (uint8_t)(e.link_sym & 0xf); m.cc1[1] = m.tc1[1] = m.con_a2[1] = 1; m.mmm_cc[1] = m.mmm_tot[1] = e.link_cc;
+    }
+    const int32_t adj = tmax((int32_t)e.base_cc * 2, (int32_t)e.base_tc) - (int32_t)e.base_tc;
+    if (adj > 0) {
+        m.a2[0] = e.base_sym; m.mmm_cc[0] = m.mmm_tot[0] = (uint32_t)adj;
+        if (adj >= par.fam_thres_highBQ_snv) { m.a1[0] = e.base_sym; m.cc1[0] = m.tc1[0] = m.con_a2[0] = 1; }
+    }
+    return m;
+}
+
 // the entry of (family, strand) at p; all-zero counts outside the strand's covered extent
 UVC_HD FamCol fam_entry(const BatchView & v, const FamRec & F, int strand, int32_t p) {
     if (p < F.lo[strand] || p >= F.hi[strand]) {
@@ -1288,7 +1306,14 @@ UVC_HD FamCol fam_entry(const BatchView & v, const FamRec & F, int strand, int32
         for (int t = 0; t < 2; t++) { z.a1[t] = z.a2[t] = (uint8_t)(t ? UVC_LINK_NN : UVC_BASE_NN); z.cc1[t] = z.tc1[t] = z.con_a2[t] = 0; z.mmm_cc[t] = z.mmm_tot[t] = 0; }
         return z;
     }
+    if (F.direct_frag[strand] >= 0) { return famcol_from_frag(frag_entry(v, v.frags[F.direct_frag[strand]], p), v.par); }
     return v.mcol[F.col_off[strand] + (p - F.lo[strand])];
+}
+
+// the entry a read's (family, strand) has at p, through the read's compact record (p is covered by the read, hence inside the extent)
+UVC_HD FamCol fam_entry_of_read(const BatchView & v, const ReadFam & q, int32_t p) {
+    if (q.flags & UVC_RF_DIRECT) { return famcol_from_frag(v.fcol[q.col_base + p], v.par); }
+    return v.mcol[q.col_base + p];
 }
 
 // ------------------------------------------------------------------------------------------------ K4a: one thread per (family, strand)
@@ -1302,7 +1327,7 @@ UVC_HD void k4a_family_strand(const BatchView & v, int64_t i) {
     const int32_t lo = F.lo[strand], hi = F.hi[strand];   // covered extent (positions outside have no votes)
     for (int dir = 0; dir < 2; dir++) {
         for (int32_t p = (dir ? hi - 1 : lo); (dir ? p >= lo : p < hi); p += (dir ? -1 : 1)) {
-            const FamCol m = v.mcol[F.col_off[strand] + (p - lo)];
+            const FamCol m = fam_entry(v, F, strand, p);
             const int a = m.a1[0]; const int32_t cc = m.cc1[0], tc = m.tc1[0];
             if (0 == tc) { continue; }
             if (fam_is_good(v.par, F, cc, tc) && (UVC_BASE_N != a) && (UVC_BASE_NN != a)) {
@@ -1343,12 +1368,13 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp, const Win & w) {
     // ---- loop 1
     for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
         if (ri < w.lo || ri >= w.hi) { continue; }
-        const ReadRec & R = v.reads[ri];
-        if (R.rend <= p || R.famprev_maxrend > p) { continue; }
-        const FamRec & F = v.fams[R.fam];
-        const int strand = R.strand;
+        const ReadFam q = v.rfam[ri];
+        if (q.rend <= p || q.famprev_maxrend > p) { continue; }
+        const FamRec & F = v.fams[q.fam];      // only dereferenced on the tier-2 (UMI family) path
+        const int strand = (int)(q.flags & UVC_RF_STRAND);
         int32_t *fd = (strand ? fam1 : fam0);
-        const FamCol m = v.mcol[F.col_off[strand] + (p - F.lo[strand])];
+        const FamCol m = fam_entry_of_read(v, q, p);
+        #pragma unroll
         for (int type = 1; type >= 0; type--) {
             const int a = m.a1[type]; const int32_t cc = m.cc1[type], tc = m.tc1[type];
             if (0 == tc) { continue; }
@@ -1422,16 +1448,17 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp, const Win & w) {
     const int32_t tn_add = (par.is_tumor_vcf_provided ? 4 : 0);
     for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
         if (ri < w.lo || ri >= w.hi) { continue; }
-        const ReadRec & R = v.reads[ri];
-        if (R.rend <= p) { continue; }
-        const FamRec & F = v.fams[R.fam];
-        const bool is_duplex_umi = (0x2 == (F.duplexflag & 0x2));
-        const bool will_inc_dscs = (is_duplex_umi && F.n_frags[0] > 0 && F.n_frags[1] > 0);
+        const ReadFam q = v.rfam[ri];
+        if (q.rend <= p) { continue; }
+        const FamRec & F = v.fams[q.fam];      // only dereferenced for indel identities and duplex families
+        const bool is_duplex_umi = (0 != (q.flags & UVC_RF_DUPLEX_UMI));
+        const bool will_inc_dscs = (is_duplex_umi && (q.flags & UVC_RF_BOTH_STRANDS));
         const bool will_inc_sscs = (is_duplex_umi && !will_inc_dscs);
-        if (R.famprev_maxrend <= p) {   // first read of its (family, strand) that covers p
-            const int strand = R.strand;
+        if (q.famprev_maxrend <= p) {   // first read of its (family, strand) that covers p
+            const int strand = (int)(q.flags & UVC_RF_STRAND);
             int32_t *fd = (strand ? fam1 : fam0);
-            const FamCol m = v.mcol[F.col_off[strand] + (p - F.lo[strand])];
+            const FamCol m = fam_entry_of_read(v, q, p);
+            #pragma unroll
             for (int type = 1; type >= 0; type--) {
                 const int a = m.a2[type]; const int32_t con_sumBQs = (int32_t)m.mmm_cc[type], tot_sumBQs = (int32_t)m.mmm_tot[type];
                 if (0 == tot_sumBQs) { continue; }
@@ -1467,7 +1494,7 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp, const Win & w) {
                 }
             }
         }
-        if (will_inc_dscs && R.fambothprev_maxrend <= p) {   // first read of the duplex family that covers p
+        if (will_inc_dscs && q.fambothprev_maxrend <= p) {   // first read of the duplex family that covers p
             int32_t dcount[UVC_NSYM];
             votes_zero(dcount);
             int link_con[2] = {-1, -1};
@@ -1547,7 +1574,7 @@ UVC_HD void k4c_family_strand(const BatchView & v, int64_t i) {
         for (int32_t p = lo; p < hi; p++) {
             const int64_t gp = po + p;
             const int ref = v.refsym[gp];
-            const FamCol m = v.mcol[F.col_off[strand] + (p - lo)];
+            const FamCol m = fam_entry(v, F, strand, p);
             const int32_t *fd = v.famdepth + ((strand * v.n_pos + gp) * UVC_NSYM) * UVCGPU_NUM_FAM_DEPTHS;
             for (int type = 1; type >= 0; type--) {
                 const int a = m.a2[type]; const int32_t con_sumBQs = (int32_t)m.mmm_cc[type], tot_sumBQs = (int32_t)m.mmm_tot[type];
