@@ -50,8 +50,8 @@ def parse_args():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--scale", type=float, default=None, help="fraction of the named config's region (default: per-config)")
     ap.add_argument("--workdir", default=os.environ.get("UVC_BENCH_DIR", "/tmp/uvc_bench"))
-    ap.add_argument("--contexts", type=int, default=3, help="contexts (CUDA streams) the e2e step pipelines its sub-batches over")
-    ap.add_argument("--sub-batches", type=int, default=6)
+    ap.add_argument("--contexts", type=int, default=6, help="contexts (CUDA streams) the e2e step pipelines its sub-batches over")
+    ap.add_argument("--sub-batches", type=int, default=12)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -245,14 +245,20 @@ def main():
         return ctx
 
     def run_tiles(ctx, sub):
+        t0 = time.time()
         ticket = ctx.submit(sub, view)
+        t1 = time.time()
         ctx.collect(ticket)
+        t2 = time.time()
         st = ctx.score(ticket)               # candidate scoring on the device + D2H of the kept records and block-line inputs
+        t3 = time.time()
         nbytes = 0
         for ti in range(len(sub)):           # the step's result: every tile's VCF body text
             nbytes += len(ctx.tile_vcf(ticket, ti))
+        t4 = time.time()
         ctx.release(ticket)
         st.vcf_bytes = nbytes
+        st.phase_s = (t1 - t0, t2 - t1, t3 - t2, t4 - t3, time.time() - t4)   # submit (staging + H2D enqueue), wait, score, text, release
         return st
 
     # ---- phase 1: device-resident throughput (`value`): one context, the whole batch per launch, CUDA-event time of every kernel
@@ -284,12 +290,12 @@ def main():
     subs = [s for s in subs if s]
     ctxs = [ctx0] + [make_ctx(max(1, host_threads // n_ctx + 1)) for _ in range(n_ctx - 1)]
     ctx0.lib.uvcgpu_set_host_threads(ctx0.handle, max(1, host_threads // n_ctx + 1))
-    totals = {"h2d": 0, "d2h": 0, "vcf": 0, "rec": 0, "launch": 0, "prep_ms": 0.0}
+    totals = {"h2d": 0, "d2h": 0, "vcf": 0, "rec": 0, "launch": 0, "prep_ms": 0.0, "submit_s": 0.0, "wait_s": 0.0, "score_s": 0.0, "text_s": 0.0, "release_s": 0.0}
 
     def e2e_step():
         nxt = [0]
         lock = threading.Lock()
-        acc = {"h2d": 0, "d2h": 0, "vcf": 0, "rec": 0, "launch": 0, "prep_ms": 0.0}
+        acc = {k: 0 for k in totals}
         errs = []
 
         def work(ctx):
@@ -308,6 +314,8 @@ def main():
                         acc["rec"] += int(st.n_vcf_records)
                         acc["launch"] += int(st.gpu_launches)
                         acc["prep_ms"] += st.host_prep_ms
+                        for key, val in zip(("submit_s", "wait_s", "score_s", "text_s", "release_s"), st.phase_s):
+                            acc[key] += val
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
         ths = [threading.Thread(target=work, args=(c,)) for c in ctxs]
@@ -379,7 +387,9 @@ def main():
             "e2e": {"value": e2e, "unit": "reads/s", "positions_per_s": units * n_positions * args.steps / wall_s,
                     "h2d_bytes_per_step": totals["h2d"] // args.steps, "d2h_bytes_per_step": totals["d2h"] // args.steps,
                     "vcf_bytes_per_step": totals["vcf"] // args.steps, "vcf_records_per_step": totals["rec"] // args.steps,
-                    "host_prep_ms_per_step_summed_over_contexts": totals["prep_ms"] / args.steps, "wall_ms_per_step": wall_s * 1e3 / args.steps},
+                    "host_prep_ms_per_step_summed_over_contexts": totals["prep_ms"] / args.steps,
+                    "call_ms_per_step_summed_over_contexts": {k[:-2]: totals[k] * 1e3 / args.steps for k in ("submit_s", "wait_s", "score_s", "text_s", "release_s")},
+                    "wall_ms_per_step": wall_s * 1e3 / args.steps},
             "gpu_launches": launches + totals["launch"],
             "stage_ms_per_step": {n: stage_ms[i] / args.steps for i, n in enumerate(STAGE_NAMES)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -194,13 +194,45 @@ __device__ __forceinline__ void uvc_warp_window(const BatchView & v, int64_t gp,
     }
 UVC_DEFINE_KERNEL(uvc_k0_read_consts, uvc::k0_read(v, i))
 UVC_DEFINE_POS_KERNEL(uvc_k1_prep_thres, uvc::k1_position(v, i, w))
-// both roles of a position sit in different warps of the same block: block = 64 positions x 2 roles
+// Cooperative copy of n records of T from global to this warp's shared-memory slot (16-byte words, all 32 lanes).
+template <class T> __device__ __forceinline__ void uvc_warp_stage(T *dst, const T *src, int n, int lane) {
+    static_assert(sizeof(T) % 4 == 0, "records are word multiples");
+    const int n_words = n * (int)(sizeof(T) / 4);
+    const uint32_t *s = (const uint32_t*)src;
+    uint32_t *d = (uint32_t*)dst;
+    for (int k = lane; k < n_words; k += 32) { d[k] = s[k]; }
+}
+
+// both roles of a position sit in different warps of the same block: block = 64 positions x 2 roles.
+// Each warp stages the records (ReadRec + ReadDerived) of 32 reads of its union window in shared memory with one coalesced copy and then
+// walks them from there: the per-read loads of the inner loop become shared-memory broadcasts instead of dependent global loads.
+#define UVC_STAGE_READS 32
 __global__ void __launch_bounds__(128) uvc_k2_bias_pileup(const BatchView v, int64_t n) {
+    __shared__ ReadRec sR[4][UVC_STAGE_READS];
+    __shared__ ReadDerived sD[4][UVC_STAGE_READS];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gp = (i / 128) * 64 + (i % 64);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool active = (gp < v.n_pos);
     uvc::Win w;
-    uvc_warp_window(v, gp, gp < v.n_pos, w);
-    if (gp < v.n_pos) { uvc::k2_position(v, gp, (int)((i % 128) / 64), w); }
+    uvc_warp_window(v, gp, active, w);
+    uvc::K2State st;
+    if (active) { uvc::k2_begin(st, v, gp, (int)((i % 128) / 64)); }
+    for (int64_t cb = w.ulo; cb < w.uhi; cb += UVC_STAGE_READS) {
+        const int nc = (int)(w.uhi - cb < UVC_STAGE_READS ? w.uhi - cb : UVC_STAGE_READS);
+        __syncwarp();
+        uvc_warp_stage(sR[warp], v.reads + cb, nc, lane);
+        uvc_warp_stage(sD[warp], v.rd + cb, nc, lane);
+        __syncwarp();
+        if (active) {
+            for (int k = 0; k < nc; k++) {
+                const int64_t ri = cb + k;
+                if (ri < w.lo || ri >= w.hi) { continue; }
+                uvc::k2_read(st, v, sR[warp][k], sD[warp][k]);
+            }
+        }
+    }
+    if (active) { uvc::k2_end(st, v); }
 }
 UVC_DEFINE_KERNEL(uvc_k2e_indel_events, uvc::k2e_event(v, i))
 UVC_DEFINE_KERNEL(uvc_kf_fragment_columns, uvc::kf_fragment_column(v, i))

@@ -659,45 +659,68 @@ UVC_HD int32_t nogap_weight(const BatchView & v, int64_t gp, const ReadDerived &
 // ------------------------------------------------------------------------------------------------ K2: two threads per position
 // Walk #2 (updateByAln<SUM, bias> over aligned bases, main.hpp:1890-2008) gathered per position. role 0 owns the six base symbols,
 // role 1 owns LINK_M. The symbol that matches the reference (role 0) / LINK_M (role 1) is accumulated in registers.
-UVC_HD void k2_position(const BatchView & v, int64_t gp, int role, const Win & w) {
-    const TileInfo & T = v.tiles[v.pos_tile[gp]];
-    const int32_t p = (int32_t)(gp - T.pos_off) + T.ext_beg;
-    const int32_t *baq = v.baq + (T.pos_off - T.ext_beg);
-    const int32_t *baq2 = v.baq2 + (T.pos_off - T.ext_beg);
-    const uvcgpu_thres_set th = v.thres[gp];
-    const int major = (role == 0 ? (int)v.refsym[gp] : UVC_LINK_M);
+struct K2State {
+    const TileInfo *T;
+    int64_t gp;
+    int32_t p;
+    int role, major;
+    const int32_t *baq, *baq2;
+    uvcgpu_thres_set th;
     SegAcc acc;
-    segacc_zero(acc);
-    for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
-        if (ri < w.lo || ri >= w.hi) { continue; }
-        const ReadRec & R = v.reads[ri];
-        if (R.rend <= p) { continue; }
-        const Locus L = locate(v, R, p);
-        if (!L.is_m) { continue; }
-        const ReadDerived & D = v.rd[ri];
-        if (primer_masked(v, R, D, p)) { continue; }
-        const int32_t dist = dist_to_interfering_indel(v, T, D, L, th, p);
-        if (role == 1) {
-            if (!L.not_first) { continue; }
-            const int32_t w = nogap_weight(v, gp, D);
-            acc.bqsum += w;
-            segbias<true>(acc, v, R, D, th, baq, baq2, w, p, 0 /* bm1500s[LINK_M] */, false, 0, dist);
+};
+
+UVC_HD void k2_begin(K2State & s, const BatchView & v, int64_t gp, int role) {
+    const TileInfo & T = v.tiles[v.pos_tile[gp]];
+    s.T = &T; s.gp = gp; s.role = role;
+    s.p = (int32_t)(gp - T.pos_off) + T.ext_beg;
+    s.baq = v.baq + (T.pos_off - T.ext_beg);
+    s.baq2 = v.baq2 + (T.pos_off - T.ext_beg);
+    s.th = v.thres[gp];
+    s.major = (role == 0 ? (int)v.refsym[gp] : UVC_LINK_M);
+    segacc_zero(s.acc);
+}
+
+// one read of the position's window (R, D may live in shared memory: the CUDA kernel stages the records of 32 reads per warp at a time)
+UVC_HD void k2_read(K2State & s, const BatchView & v, const ReadRec & R, const ReadDerived & D) {
+    const int32_t p = s.p;
+    if (R.rend <= p) { return; }
+    const Locus L = locate(v, R, p);
+    if (!L.is_m) { return; }
+    if (primer_masked(v, R, D, p)) { return; }
+    const int32_t dist = dist_to_interfering_indel(v, *s.T, D, L, s.th, p);
+    if (s.role == 1) {
+        if (!L.not_first) { return; }
+        const int32_t w = nogap_weight(v, s.gp, D);
+        s.acc.bqsum += w;
+        segbias<true>(s.acc, v, R, D, s.th, s.baq, s.baq2, w, p, 0 /* bm1500s[LINK_M] */, false, 0, dist);
+    } else {
+        const int sym = base3(v.seq + R.seq_off, L.qpos);
+        const int32_t bq = (int32_t)v.qual[R.qual_off + L.qpos] + v.par.bq_phred_added_misma;
+        if (sym == s.major) {
+            s.acc.bqsum += bq;
+            segbias<false>(s.acc, v, R, D, s.th, s.baq, s.baq2, bq, p, D.bm1500[sym], false, 0, dist);
         } else {
-            const int sym = base3(v.seq + R.seq_off, L.qpos);
-            const int32_t bq = (int32_t)v.qual[R.qual_off + L.qpos] + v.par.bq_phred_added_misma;
-            if (sym == major) {
-                acc.bqsum += bq;
-                segbias<false>(acc, v, R, D, th, baq, baq2, bq, p, D.bm1500[sym], false, 0, dist);
-            } else {
-                SegAcc one;
-                segacc_zero(one);
-                one.bqsum = bq;
-                segbias<false>(one, v, R, D, th, baq, baq2, bq, p, D.bm1500[sym], false, 0, dist);
-                segacc_flush<false>(v, gp, sym, one);
-            }
+            SegAcc one;
+            segacc_zero(one);
+            one.bqsum = bq;
+            segbias<false>(one, v, R, D, s.th, s.baq, s.baq2, bq, p, D.bm1500[sym], false, 0, dist);
+            segacc_flush<false>(v, s.gp, sym, one);
         }
     }
-    if (major < UVC_NSYM) { segacc_flush<false>(v, gp, major, acc); }
+}
+
+UVC_HD void k2_end(K2State & s, const BatchView & v) {
+    if (s.major < UVC_NSYM) { segacc_flush<false>(v, s.gp, s.major, s.acc); }
+}
+
+UVC_HD void k2_position(const BatchView & v, int64_t gp, int role, const Win & w) {
+    K2State s;
+    k2_begin(s, v, gp, role);
+    for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
+        if (ri < w.lo || ri >= w.hi) { continue; }
+        k2_read(s, v, v.reads[ri], v.rd[ri]);
+    }
+    k2_end(s, v);
 }
 
 // ------------------------------------------------------------------------------------------------ K2e: one thread per indel event
