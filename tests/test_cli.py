@@ -87,6 +87,20 @@ def test_cli_bed_regions_umi(synth_umi, tmp_path):
 
 
 @needs_ref
+def test_cli_dense_panel_bed(synth_cli, tmp_path):
+    """40 small targets 500 bp apart: the tiler counts their reads in one sweep over the BAM and every lane decodes its run of targets once
+    (span fetch) - both must give what the reference's per-target index queries give. Also an unsorted BED (falls back to per-target queries)."""
+    bed = tmp_path / "panel.bed"
+    bed.write_text("".join("chrA\t%d\t%d\n" % (1000 + 500 * i, 1150 + 500 * i) for i in range(40)) + "chrB\t2000\t2300\n")
+    (tmp_path / "s").mkdir()
+    _compare(EMU, synth_cli, tmp_path / "s", ["-t", "3", "-R", str(bed)])
+    bed2 = tmp_path / "unsorted.bed"
+    bed2.write_text("".join("chrA\t%d\t%d\n" % (1000 + 500 * i, 1150 + 500 * i) for i in reversed(range(36))))
+    (tmp_path / "u").mkdir()
+    _compare(EMU, synth_cli, tmp_path / "u", ["-t", "2", "-R", str(bed2)])
+
+
+@needs_ref
 def test_cli_targets(synth_cli, tmp_path):
     _compare(EMU, synth_cli, tmp_path, ["-t", "2", "--targets", "chrA:5000-7000,chrB:100-900"])
 

@@ -74,6 +74,9 @@ struct ReadDerived {
     int32_t bm1500[5];
     int32_t micro_indel_penal, micro_nogap_penal;
     int32_t ibeg, iend;                                // amplicon primer window (main.hpp:1872-1875)
+    // per-read terms of dealwith_segbias (main.hpp:1360-1595) that do not depend on the position: hoisted out of the per-base work
+    int32_t baq_pos, baq_rend1, baq2_rend1;            // baq[pos], baq[rend - 1], baq2[rend - 1]
+    int32_t xm_term, bm_term[5];                       // (x > 20 ? 100 * 400 / (x * x) : 100) for x = xm1500, bm1500[b]
 };
 
 // Per-reference-base expansion entry of a complex read: what the read shows at reference offset o = p - pos.
@@ -163,6 +166,7 @@ struct BatchView {
     double ln10;                   // log(10)
     const double *phred2prob_tab;  // [128] phred2prob(q) = pow(10, -((float)q) / 10) (main_conversion.hpp:885-888) evaluated with the host libm
     const int32_t *slip_tab;       // [2][UVC_SLIP_MAXUNIT][UVC_SLIP_NMAX] indel_phred (main.hpp:794-801) evaluated with the host libm
+    const int32_t *pf_tab;         // [2][128] passing-filter weight of a base quality: bq < PFBQk ? 100 * bq^2 / PFBQk^2 : 100 (main.hpp:1452-1455)
     int32_t n_tiles;
     int64_t n_pos, n_reads, n_frags, n_fams, n_cx, n_ev;
     const TileInfo *tiles;

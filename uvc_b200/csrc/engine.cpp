@@ -388,6 +388,15 @@ static int backend_score(uvcgpu_ctx *, BatchState & bs, const ScoreView & sv) {
 
 #endif
 
+// Entry points may be called from any host thread: the context's device is made current first (CUDA's current device is per thread).
+static inline void enter_ctx(const uvcgpu_ctx *ctx) {
+#if UVC_CUDA
+    if (ctx) { cudaSetDevice(ctx->device); }
+#else
+    (void)ctx;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------ C ABI
 extern "C" {
 
@@ -524,6 +533,7 @@ int uvcgpu_create(uvcgpu_ctx **out, int device, const uvcgpu_params *params) {
 
 void uvcgpu_destroy(uvcgpu_ctx *ctx) {
     if (NULL == ctx) { return; }
+    enter_ctx(ctx);
     for (auto & kv : ctx->batches) { backend_free(ctx, *kv.second); }
 #if UVC_CUDA
     if (ctx->stream) { cudaStreamDestroy(ctx->stream); }
@@ -572,6 +582,7 @@ int uvcgpu_submit(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, co
 
 int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, int32_t n_sources, const uvcgpu_reads_soa *sources,
         const int32_t *tile_source, uvcgpu_ticket *ticket) {
+    enter_ctx(ctx);
     if (NULL == ctx || NULL == tiles || NULL == sources || NULL == ticket || n_tiles <= 0 || n_sources <= 0) { return UVCGPU_EINVAL; }
     std::unique_ptr<BatchState> bs(new BatchState());
     memset(&bs->stats, 0, sizeof(bs->stats));
@@ -605,6 +616,12 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
         std::vector<double> tab(128);
         for (int q = 0; q < 128; q++) { tab[q] = pow(10, -((float)q) / 10); }   // phred2prob (main_conversion.hpp:885-888): float exponent, double pow
         UVC_UP(phred2prob_tab, double, tab)
+        std::vector<int32_t> pf(256);
+        for (int k = 0; k < 2; k++) {
+            const int32_t t = (k ? ctx->par.bias_thres_PFBQ2 : ctx->par.bias_thres_PFBQ1);
+            for (int bq = 0; bq < 128; bq++) { pf[k * 128 + bq] = ((bq < t) ? (100 * (bq * bq) / (t * t)) : 100); }
+        }
+        UVC_UP(pf_tab, int32_t, pf)
     }
     UVC_UP(tiles, TileInfo, hb.tiles)
     UVC_UP(pos_tile, int32_t, hb.pos_tile)
@@ -656,6 +673,7 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
 }
 
 int uvcgpu_collect(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, uvcgpu_batch_stats *stats) {
+    enter_ctx(ctx);
     if (NULL == ctx) { return UVCGPU_EINVAL; }
     auto it = ctx->batches.find(ticket);
     if (it == ctx->batches.end()) { ctx->err = "unknown ticket"; return UVCGPU_EINVAL; }
@@ -745,6 +763,7 @@ static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
 }
 
 int uvcgpu_score(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, uvcgpu_batch_stats *stats) {
+    enter_ctx(ctx);
     if (NULL == ctx) { return UVCGPU_EINVAL; }
     auto it = ctx->batches.find(ticket);
     if (it == ctx->batches.end()) { ctx->err = "unknown ticket"; return UVCGPU_EINVAL; }
@@ -787,6 +806,7 @@ static int tile_vcf_text(uvcgpu_ctx *ctx, BatchState & bs, int32_t tile_index, s
 }
 
 int uvcgpu_tile_vcf(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_index, char *dst, size_t cap, size_t *needed) {
+    enter_ctx(ctx);
     if (NULL == ctx || NULL == needed) { return UVCGPU_EINVAL; }
     auto it = ctx->batches.find(ticket);
     if (it == ctx->batches.end()) { ctx->err = "unknown ticket"; return UVCGPU_EINVAL; }
@@ -802,6 +822,7 @@ int uvcgpu_tile_vcf(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_index, c
 }
 
 int uvcgpu_release(uvcgpu_ctx *ctx, uvcgpu_ticket ticket) {
+    enter_ctx(ctx);
     if (NULL == ctx) { return UVCGPU_EINVAL; }
     auto it = ctx->batches.find(ticket);
     if (it == ctx->batches.end()) { return UVCGPU_EINVAL; }
@@ -812,6 +833,7 @@ int uvcgpu_release(uvcgpu_ctx *ctx, uvcgpu_ticket ticket) {
 }
 
 int uvcgpu_dump_counters(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_index, int32_t section, void *dst, size_t cap, size_t *needed) {
+    enter_ctx(ctx);
     if (NULL == ctx || NULL == needed) { return UVCGPU_EINVAL; }
     auto it = ctx->batches.find(ticket);
     if (it == ctx->batches.end()) { ctx->err = "unknown ticket"; return UVCGPU_EINVAL; }

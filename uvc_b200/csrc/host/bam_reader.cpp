@@ -209,6 +209,7 @@ inline uint32_t le32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1]
 struct uvchost_bam {
     BgzfIn in;
     std::string path;
+    uvchost_readbuf *span = NULL;              // reusable span buffer of uvchost_bam_fetch_tiles
     std::vector<std::string> names;
     std::vector<int64_t> lens;
     std::vector<std::vector<uint64_t>> lidx;   // linear index per reference
@@ -217,6 +218,7 @@ struct uvchost_bam {
 };
 
 struct uvchost_readbuf {
+    std::vector<int32_t> endpos_scratch;   // only filled for the span buffer of uvchost_bam_fetch_tiles
     std::vector<int32_t> pos, mpos, isize, mtid, l_qseq, n_cigar, nm;
     std::vector<uint16_t> flag;
     std::vector<uint8_t> mapq;
@@ -283,7 +285,7 @@ uvchost_bam *uvchost_bam_open(const char *path) {
     return b;
 }
 
-void uvchost_bam_close(uvchost_bam *b) { delete b; }
+void uvchost_bam_close(uvchost_bam *b) { if (b) { delete b->span; } delete b; }
 int32_t uvchost_bam_n_targets(const uvchost_bam *b) { return (int32_t)b->names.size(); }
 const char *uvchost_bam_target_name(const uvchost_bam *b, int32_t tid) { return b->names[tid].c_str(); }
 int64_t uvchost_bam_target_len(const uvchost_bam *b, int32_t tid) { return b->lens[tid]; }
@@ -422,6 +424,77 @@ int64_t uvchost_bam_fetch(uvchost_bam *b, int32_t tid, int64_t beg, int64_t end,
         if (c.endpos > beg) { append_record(rb, b, c); n++; }
     }
     return n;
+}
+
+// appends record j of src to dst
+static void copy_record(uvchost_readbuf *dst, const uvchost_readbuf *src, size_t j) {
+    dst->pos.push_back(src->pos[j]); dst->mpos.push_back(src->mpos[j]); dst->isize.push_back(src->isize[j]); dst->mtid.push_back(src->mtid[j]);
+    dst->l_qseq.push_back(src->l_qseq[j]); dst->n_cigar.push_back(src->n_cigar[j]); dst->nm.push_back(src->nm[j]);
+    dst->flag.push_back(src->flag[j]); dst->mapq.push_back(src->mapq[j]);
+    dst->qname.insert(dst->qname.end(), src->qname.begin() + src->qname_off[j], src->qname.begin() + src->qname_off[j + 1]);
+    dst->cigar.insert(dst->cigar.end(), src->cigar.begin() + src->cigar_off[j], src->cigar.begin() + src->cigar_off[j + 1]);
+    dst->seq.insert(dst->seq.end(), src->seq.begin() + src->seq_off[j], src->seq.begin() + src->seq_off[j + 1]);
+    dst->qual.insert(dst->qual.end(), src->qual.begin() + src->qual_off[j], src->qual.begin() + src->qual_off[j + 1]);
+    dst->qname_off.push_back(dst->qname.size()); dst->cigar_off.push_back(dst->cigar.size());
+    dst->seq_off.push_back(dst->seq.size()); dst->qual_off.push_back(dst->qual.size());
+}
+
+int64_t uvchost_bam_fetch_tiles(uvchost_bam *b, int32_t tid, int32_t n, const int64_t *begs, const int64_t *ends, uvchost_readbuf *rb,
+        int64_t *read_begin, int64_t *read_end) {
+    if (n <= 0) { return 0; }
+    int64_t span_beg = begs[0], span_end = ends[0], sum_len = 0;
+    for (int32_t k = 0; k < n; k++) {
+        if (begs[k] < span_beg) { span_beg = begs[k]; }
+        if (ends[k] > span_end) { span_end = ends[k]; }
+        sum_len += (ends[k] - begs[k]) + 8192;   // a separate query also parses, on average, half an index window before its start
+    }
+    bool ascending = true;
+    for (int32_t k = 0; k + 1 < n; k++) { if (begs[k] > begs[k + 1]) { ascending = false; } }
+    int64_t total = 0;
+    if (1 == n || !ascending || span_end - span_beg > sum_len) {   // sparse (or unsorted) windows: one index query each
+        for (int32_t k = 0; k < n; k++) {
+            read_begin[k] = uvchost_readbuf_size(rb);
+            const int64_t r = uvchost_bam_fetch(b, tid, begs[k], ends[k], rb);
+            if (r < 0) { return r; }
+            read_end[k] = uvchost_readbuf_size(rb);
+            total += r;
+        }
+        return total;
+    }
+    if (NULL == b->span) { b->span = uvchost_readbuf_new(); }
+    uvchost_readbuf *sp = b->span;
+    uvchost_readbuf_clear(sp);
+    sp->endpos_scratch.clear();
+    {   // one pass over the span, keeping every record's end position
+        int64_t beg = (span_beg < 0 ? 0 : span_beg);
+        if (uvchost_bam_seek_region(b, tid, beg) == 0) {
+            Core c;
+            for (;;) {
+                const int r = next_record(b, c);
+                if (r < 0) { return -1; }
+                if (0 == r) { break; }
+                if (c.tid != tid || c.pos >= span_end) {
+                    if (c.tid >= 0 && c.tid < tid) { continue; }
+                    break;
+                }
+                if (c.endpos > beg) { append_record(sp, b, c); sp->endpos_scratch.push_back(c.endpos); }
+            }
+        }
+    }
+    const size_t m = sp->pos.size();
+    size_t lo = 0;
+    for (int32_t k = 0; k < n; k++) {
+        const int64_t beg = (begs[k] < 0 ? 0 : begs[k]), end = ends[k];
+        read_begin[k] = uvchost_readbuf_size(rb);
+        if (beg < end) {
+            while (lo < m && sp->endpos_scratch[lo] <= beg) { lo++; }   // ascending windows: such a record overlaps no later window either
+            for (size_t j = lo; j < m && sp->pos[j] < end; j++) {
+                if (sp->endpos_scratch[j] > beg) { copy_record(rb, sp, j); total++; }
+            }
+        }
+        read_end[k] = uvchost_readbuf_size(rb);
+    }
+    return total;
 }
 
 int uvchost_bam_scan(uvchost_bam *b, uvchost_scan_cb cb, void *user) {

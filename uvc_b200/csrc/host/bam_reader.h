@@ -34,6 +34,13 @@ void uvchost_readbuf_view(const uvchost_readbuf *rb, uvcgpu_reads_soa *out);
  * sam_itr_queryi(idx, tid, beg, end) iterates). Returns the number appended or a negative error. */
 int64_t uvchost_bam_fetch(uvchost_bam *b, int32_t tid, int64_t beg, int64_t end, uvchost_readbuf *rb);
 
+/* The fetch windows [begs[k], ends[k]) of n tiles of one contig, given in ascending order of begs: fills, for every tile, the records that
+ * uvchost_bam_fetch would append for it, in the same order, and reports their slice [read_begin[k], read_end[k]) of rb. When the windows are
+ * dense (small panel targets, tile halos) the span is inflated and parsed ONCE and the records are copied to every tile that they overlap,
+ * instead of once per tile from the start of its 16 kbp index window. Returns the number of records appended or a negative error. */
+int64_t uvchost_bam_fetch_tiles(uvchost_bam *b, int32_t tid, int32_t n, const int64_t *begs, const int64_t *ends, uvchost_readbuf *rb,
+                                int64_t *read_begin, int64_t *read_end);
+
 /* Sequential scan of core fields (for the region tiler): calls cb(tid, pos, endpos, flag, isize, user) for every record in file order
  * until cb returns non-zero or the file ends. */
 typedef int (*uvchost_scan_cb)(int32_t tid, int32_t pos, int32_t endpos, uint16_t flag, int32_t isize, int32_t l_qseq, uint8_t mapq, void *user);

@@ -2,6 +2,7 @@
 // and unsigned 64-bit arithmetic (grouping.cpp:28-67).
 #include "tiler.h"
 
+#include <algorithm>
 #include <fstream>
 #include <map>
 #include <sstream>
@@ -52,6 +53,7 @@ struct uvchost_tiler {
     int64_t bed_dp = -1;
     bool is_fastq_gen = false;
     std::vector<uvchost_bedline> given;     // -R / --targets intervals
+    std::vector<int64_t> given_counts;      // reads overlapping each interval, when counted by one sweep over the BAM
     size_t given_idx = 0;
     int32_t last_tid = -1, last_beg = -1, last_end = -1;
     uvchost_core rec;                       // the reference's single alnrecord: keeps its content at end of file
@@ -62,6 +64,41 @@ struct uvchost_tiler {
     int32_t scan_threads = 1;
     void emit(const uvchost_bedline & l) { out.push_back(l); if (cb) { cb(&l, cb_user); } }
 };
+
+// Number of records overlapping each given interval, for all intervals in ONE sequential pass over the BAM (read-ahead inflation on
+// scan_threads threads). Gives exactly the per-interval counts of SamIter::iternext (grouping.cpp:178-195), which queries the index once
+// per interval and re-reads, for dense panels, the same 16 kbp index window for every target inside it.
+static void count_by_sweep(uvchost_tiler *t) {
+    struct Iv { int32_t beg, end; size_t idx; };
+    std::map<int32_t, std::vector<Iv>> by_tid;
+    for (size_t i = 0; i < t->given.size(); i++) { Iv v; v.beg = t->given[i].beg_pos; v.end = t->given[i].end_pos; v.idx = i; by_tid[t->given[i].tid].push_back(v); }
+    std::map<int32_t, std::vector<int32_t>> prefmax;
+    for (auto & kv : by_tid) {
+        std::sort(kv.second.begin(), kv.second.end(), [](const Iv & a, const Iv & b) { return a.beg < b.beg; });
+        std::vector<int32_t> & pm = prefmax[kv.first];
+        int32_t m = INT_MIN;
+        for (const auto & v : kv.second) { m = (v.end > m ? v.end : m); pm.push_back(m); }
+    }
+    t->given_counts.assign(t->given.size(), 0);
+    if (uvchost_bam_rewind_parallel(t->bam, t->scan_threads > 1 ? t->scan_threads : 2) != 0) { return; }
+    uvchost_core c;
+    int32_t cur_tid = -2; const std::vector<Iv> *ivs = NULL; const std::vector<int32_t> *pm = NULL;
+    while (uvchost_bam_next_core(t->bam, &c) > 0) {
+        if (c.tid != cur_tid) {
+            cur_tid = c.tid;
+            auto it = by_tid.find(c.tid);
+            ivs = (it == by_tid.end() ? NULL : &it->second);
+            pm = (it == by_tid.end() ? NULL : &prefmax[c.tid]);
+        }
+        if (NULL == ivs) { continue; }
+        // intervals with beg < endpos, walked from the last one down while any earlier interval can still end after pos
+        size_t hi = std::lower_bound(ivs->begin(), ivs->end(), c.endpos, [](const Iv & a, int32_t e) { return a.beg < e; }) - ivs->begin();
+        while (hi > 0 && (*pm)[hi - 1] > c.pos) {
+            if ((*ivs)[hi - 1].end > c.pos) { t->given_counts[(*ivs)[hi - 1].idx] += 1; }
+            hi--;
+        }
+    }
+}
 
 extern "C" {
 
@@ -139,10 +176,11 @@ int64_t uvchost_tiler_next(uvchost_tiler *t, const uvchost_bedline **lines, int6
     int64_t total_n_reads = 0, total_n_rposs = 0, total_n_reads_sq = 0, total_n_rposs_sq = 0;
     if (!t->given.empty()) {
         // grouping.cpp:170-213
+        if (-1 == t->bed_dp && t->given_counts.empty() && t->given.size() >= 32) { count_by_sweep(t); }
         for (; t->given_idx < t->given.size(); t->given_idx++) {
             uvchost_bedline l = t->given[t->given_idx];
             int64_t region_n_reads = t->bed_dp * (int64_t)(l.end_pos - l.beg_pos);
-            if (-1 == t->bed_dp) { region_n_reads = uvchost_bam_count(t->bam, l.tid, l.beg_pos, l.end_pos); }
+            if (-1 == t->bed_dp) { region_n_reads = (t->given_counts.empty() ? uvchost_bam_count(t->bam, l.tid, l.beg_pos, l.end_pos) : t->given_counts[t->given_idx]); }
             t->emit(l);
             const int64_t region_n_rposs = l.end_pos - l.beg_pos;
             total_n_reads += region_n_reads; total_n_rposs += region_n_rposs;

@@ -288,16 +288,17 @@ void lane_thread(Lane lane) {
             pool.emplace_back([&, s]() {
                 uvchost_readbuf_clear(rbs[s]);
                 const int32_t k0 = (int32_t)((int64_t)n_tiles * s / n_src), k1 = (int32_t)((int64_t)n_tiles * (s + 1) / n_src);
+                // sam_itr_queryi(tid, beg - MAX_INSERT_SIZE, end + MAX_INSERT_SIZE) of every tile (grouping.cpp:664, 730); a batch holds one contig
+                std::vector<int64_t> begs, ends, rb0((size_t)(k1 - k0)), rb1((size_t)(k1 - k0));
+                for (int32_t k = k0; k < k1; k++) { begs.push_back(std::max(0, b.tiles[k].beg_pos - 2000)); ends.push_back((int64_t)b.tiles[k].end_pos + 2000); }
+                if (k1 > k0 && uvchost_bam_fetch_tiles(bams[s], b.tiles[k0].tid, k1 - k0, begs.data(), ends.data(), rbs[s], rb0.data(), rb1.data()) < 0) { dec_failed.store(1); }
                 for (int32_t k = k0; k < k1; k++) {
                     const uvchost_bedline & l = b.tiles[k];
                     uvcgpu_tile & T = tiles[k];
                     T.tid = l.tid; T.beg_pos = l.beg_pos; T.end_pos = l.end_pos; T.region_flag = l.region_flag;
                     T.prev_tid = b.prevs[k].tid; T.prev_beg_pos = b.prevs[k].beg_pos; T.prev_end_pos = b.prevs[k].end_pos;
                     T.contig_len = (int32_t)sh->contigs[(size_t)l.tid].second;
-                    T.read_begin = uvchost_readbuf_size(rbs[s]);
-                    // sam_itr_queryi(tid, beg - MAX_INSERT_SIZE, end + MAX_INSERT_SIZE) (grouping.cpp:664, 730)
-                    if (uvchost_bam_fetch(bams[s], l.tid, std::max(0, l.beg_pos - 2000), (int64_t)l.end_pos + 2000, rbs[s]) < 0) { dec_failed.store(1); }
-                    T.read_end = uvchost_readbuf_size(rbs[s]);
+                    T.read_begin = rb0[(size_t)(k - k0)]; T.read_end = rb1[(size_t)(k - k0)];
                     tile_source[k] = s;
                 }
             });

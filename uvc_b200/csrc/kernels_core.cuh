@@ -339,7 +339,9 @@ UVC_HD void k0_read(const BatchView & v, int64_t ri) {
             }
         }
     }
-    for (int b = 0; b < 5; b++) { D.bm1500[b] = bm_cnt[b] * 1500 / span; }
+    for (int b = 0; b < 5; b++) { D.bm1500[b] = bm_cnt[b] * 1500 / span; D.bm_term[b] = (D.bm1500[b] > 20 ? (100 * 400 / (D.bm1500[b] * D.bm1500[b])) : 100); }
+    D.xm_term = (D.xm1500 > 20 ? (100 * 400 / (D.xm1500 * D.xm1500)) : 100);
+    D.baq_pos = baq[pos]; D.baq_rend1 = baq[rend - 1]; D.baq2_rend1 = (v.baq2 + po)[rend - 1];
     v.rd[ri] = D;
 
     if (!R.simple) {
@@ -433,6 +435,7 @@ UVC_HD void k1_position(const BatchView & v, int64_t gp, const Win & w) {
     const uvcgpu_params & par = v.par;
     const int32_t *baq = v.baq + (T.pos_off - T.ext_beg);
     uvcgpu_prep_set a = v.prep[gp];     // starts from the rare-event contributions of K0
+    const int32_t baq_p = baq[p];
     for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
         if (ri < w.lo || ri >= w.hi) { continue; }
         const ReadRec & R = v.reads[ri];
@@ -455,8 +458,8 @@ UVC_HD void k1_position(const BatchView & v, int64_t gp, const Win & w) {
             a.a_l_dist_sum += p - R.pos + 1;
             a.a_r_dist_sum += R.rend - p;
             a.a_inslen_sum += D.inslen_sum; a.a_dellen_sum += D.dellen_sum;
-            a.a_l_BAQ_sum += baq[p] - baq[R.pos] + 1;
-            a.a_r_BAQ_sum += baq[R.rend - 1] - baq[p] + 1;
+            a.a_l_BAQ_sum += baq_p - D.baq_pos + 1;
+            a.a_r_BAQ_sum += D.baq_rend1 - baq_p + 1;
             a.a_insBAQ_sum += D.insbaq_sum; a.a_delBAQ_sum += D.delbaq_sum;
             a.a_highBQ_dp += 1;
         }
@@ -557,15 +560,15 @@ UVC_HD void bidir_bias(int32_t & lp1, int32_t & lp2, int32_t & rp1, int32_t & rp
 // One call of dealwith_segbias<isGap> (main.hpp:1360-1595) for read R at position rpos with quality bq, into accumulator a.
 template <bool isGap>
 UVC_HD void segbias(SegAcc & a, const BatchView & v, const ReadRec & R, const ReadDerived & D, const uvcgpu_thres_set & th,
-        const int32_t *baq, const int32_t *baq2, int32_t bq, int32_t rpos, int32_t bm1500, bool is_ins_op, int32_t indel_len, int32_t dist_indel) {
+        int32_t baq_rpos, int32_t baq2_rpos, int32_t bq, int32_t rpos, int32_t bm_term, bool is_ins_op, int32_t indel_len, int32_t dist_indel) {
     const uvcgpu_params & par = v.par;
     const bool is_assay_amplicon = ((R.dflag & 0x4) || ((par.primerlen > 0) && !(0x2 & par.primer_flag)));
     const bool normal_filters_primers = (par.tn_is_paired && (0x1 & par.primer_flag));
     const bool is_assay_UMI = (R.dflag & 0x1);
     const int32_t pos = R.pos, rend = R.rend;
-    const int32_t seg_l_baq1 = baq[rpos] - baq[pos] + 1;
-    const int32_t seg_r_baq0 = baq[rend - 1] - baq[rpos] + 1;
-    const int32_t seg_r_baq1 = (isGap ? tmin(seg_r_baq0, baq2[rend - 1] - baq2[rpos] + 7) : seg_r_baq0);
+    const int32_t seg_l_baq1 = baq_rpos - D.baq_pos + 1;
+    const int32_t seg_r_baq0 = D.baq_rend1 - baq_rpos + 1;
+    const int32_t seg_r_baq1 = (isGap ? tmin(seg_r_baq0, D.baq2_rend1 - baq2_rpos + 7) : seg_r_baq0);
     const int32_t seg_l_nbases = rpos - pos + 1;
     const int32_t seg_r_nbases = rend - rpos;
     const bool is_high_readlen = (par.central_readlen >= par.microadjust_median_readlen_thres);
@@ -595,16 +598,20 @@ UVC_HD void segbias(SegAcc & a, const BatchView & v, const ReadRec & R, const Re
     if (far_from_edge && unaffected_by_edge && (min_dist2iend > par.primerlen2 || !is_assay_amplicon)) { a.s.aP1 += 1; }
     if (is_assay_UMI || !is_assay_amplicon) { a.s.aP2 += 1; }
 
-    const int32_t f1 = ((bq < par.bias_thres_PFBQ1) ? (100 * (bq * bq) / (par.bias_thres_PFBQ1 * par.bias_thres_PFBQ1)) : 100);
-    const int32_t f2 = ((bq < par.bias_thres_PFBQ2) ? (100 * (bq * bq) / (par.bias_thres_PFBQ2 * par.bias_thres_PFBQ2)) : 100);
+    int32_t f1, f2;
+    if ((uint32_t)bq < 128u) { f1 = v.pf_tab[bq]; f2 = v.pf_tab[128 + bq]; }
+    else {
+        f1 = ((bq < par.bias_thres_PFBQ1) ? (100 * (bq * bq) / (par.bias_thres_PFBQ1 * par.bias_thres_PFBQ1)) : 100);
+        f2 = ((bq < par.bias_thres_PFBQ2) ? (100 * (bq * bq) / (par.bias_thres_PFBQ2 * par.bias_thres_PFBQ2)) : 100);
+    }
     if (isGap) {
         a.s.aPF1 += tmin(100, f1);
         a.s.aPF2 += tmin(100, f2);
     } else {
         a.s.aPF1 += (100 * f1 / 100);
         a.s.aPF2 += (100 * f2 / 100);
-        a.s.a2XM2 += (D.xm1500 > 20 ? (100 * 400 / (D.xm1500 * D.xm1500)) : 100);
-        a.s.a2BM2 += (bm1500 > 20 ? (100 * 400 / (bm1500 * bm1500)) : 100);
+        a.s.a2XM2 += D.xm_term;
+        a.s.a2BM2 += bm_term;
     }
     if (((!isGap) && bq >= par.bias_thres_highBQ) || (isGap && dist_indel >= par.bias_thres_interfering_indel)) {
         const bool tier2 = (isGap || bq >= par.bias_thres_highBQ);
@@ -664,7 +671,8 @@ struct K2State {
     int64_t gp;
     int32_t p;
     int role, major;
-    const int32_t *baq, *baq2;
+    int32_t baq_p, baq2_p;          // baq[p], baq2[p]
+    int32_t noindel;                // min(indelphred[p - 1], indelphred[p]) of nogap_weight
     uvcgpu_thres_set th;
     SegAcc acc;
 };
@@ -673,8 +681,8 @@ UVC_HD void k2_begin(K2State & s, const BatchView & v, int64_t gp, int role) {
     const TileInfo & T = v.tiles[v.pos_tile[gp]];
     s.T = &T; s.gp = gp; s.role = role;
     s.p = (int32_t)(gp - T.pos_off) + T.ext_beg;
-    s.baq = v.baq + (T.pos_off - T.ext_beg);
-    s.baq2 = v.baq2 + (T.pos_off - T.ext_beg);
+    s.baq_p = v.baq[gp]; s.baq2_p = v.baq2[gp];
+    s.noindel = (role == 1 ? tmin(v.rtr[gp - 1].indelphred, v.rtr[gp].indelphred) : 0);
     s.th = v.thres[gp];
     s.major = (role == 0 ? (int)v.refsym[gp] : UVC_LINK_M);
     segacc_zero(s.acc);
@@ -690,20 +698,20 @@ UVC_HD void k2_read(K2State & s, const BatchView & v, const ReadRec & R, const R
     const int32_t dist = dist_to_interfering_indel(v, *s.T, D, L, s.th, p);
     if (s.role == 1) {
         if (!L.not_first) { return; }
-        const int32_t w = nogap_weight(v, s.gp, D);
+        const int32_t w = nnminus(tmin(80, s.noindel), D.micro_nogap_penal) + 1;   // nogap_weight
         s.acc.bqsum += w;
-        segbias<true>(s.acc, v, R, D, s.th, s.baq, s.baq2, w, p, 0 /* bm1500s[LINK_M] */, false, 0, dist);
+        segbias<true>(s.acc, v, R, D, s.th, s.baq_p, s.baq2_p, w, p, 100, false, 0, dist);
     } else {
         const int sym = base3(v.seq + R.seq_off, L.qpos);
         const int32_t bq = (int32_t)v.qual[R.qual_off + L.qpos] + v.par.bq_phred_added_misma;
         if (sym == s.major) {
             s.acc.bqsum += bq;
-            segbias<false>(s.acc, v, R, D, s.th, s.baq, s.baq2, bq, p, D.bm1500[sym], false, 0, dist);
+            segbias<false>(s.acc, v, R, D, s.th, s.baq_p, s.baq2_p, bq, p, D.bm_term[sym], false, 0, dist);
         } else {
             SegAcc one;
             segacc_zero(one);
             one.bqsum = bq;
-            segbias<false>(one, v, R, D, s.th, s.baq, s.baq2, bq, p, D.bm1500[sym], false, 0, dist);
+            segbias<false>(one, v, R, D, s.th, s.baq_p, s.baq2_p, bq, p, D.bm_term[sym], false, 0, dist);
             segacc_flush<false>(v, s.gp, sym, one);
         }
     }
@@ -833,7 +841,7 @@ UVC_HD void k2e_event(const BatchView & v, int64_t ei) {
             E.counted = 1;
             SegAcc a; segacc_zero(a);
             a.bqsum = E.incvalue;
-            segbias<true>(a, v, R, D, v.thres[po + rpos], baq, baq2, E.incvalue, rpos, 0, true, oplen, 10000);
+            segbias<true>(a, v, R, D, v.thres[po + rpos], baq[rpos], baq2[rpos], E.incvalue, rpos, 100, true, oplen, 10000);
             segacc_flush<true>(v, po + rpos, E.symbol, a);
         }
     } else {
@@ -878,7 +886,7 @@ UVC_HD void k2e_event(const BatchView & v, int64_t ei) {
             {
                 SegAcc a; segacc_zero(a);
                 a.bqsum = E.incvalue;
-                segbias<true>(a, v, R, D, v.thres[po + rpos], baq, baq2, E.incvalue, rpos, 0, false, oplen, 10000);
+                segbias<true>(a, v, R, D, v.thres[po + rpos], baq[rpos], baq2[rpos], E.incvalue, rpos, 100, false, oplen, 10000);
                 segacc_flush<true>(v, po + rpos, E.symbol, a);
             }
             // padded-deletion symbols: BASE_NN on every deleted base, LINK_NN on the junction after it (main.hpp:2219-2253)
@@ -889,7 +897,7 @@ UVC_HD void k2e_event(const BatchView & v, int64_t ei) {
                     if (p2 >= rend) { continue; }
                     SegAcc a; segacc_zero(a);
                     a.bqsum = E.incvalue;
-                    segbias<true>(a, v, R, D, v.thres[po + p2], baq, baq2, E.incvalue, p2, 0, false, oplen, (s == 0 ? c.prev_rpos : c.next_rpos));
+                    segbias<true>(a, v, R, D, v.thres[po + p2], baq[p2], baq2[p2], E.incvalue, p2, 100, false, oplen, (s == 0 ? c.prev_rpos : c.next_rpos));
                     segacc_flush<true>(v, po + p2, (s == 0 ? UVC_BASE_NN : UVC_LINK_NN), a);
                 }
             }
