@@ -199,7 +199,7 @@ def main():
                 "data": "synthetic", "config": {"workload": workload, "reference_sample": res["sample"]},
                 "cpu_baseline": {"value": res["value"], "unit": "reads/s", "cores": res["cores"], "kind": "reference", "sample": res["sample"]},
                 "e2e": {"value": res["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
         return
 
     import torch
@@ -345,6 +345,12 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         kernel_ms, wall_s = float(tt[0]), float(tt[1])
         dist.barrier()
+    for c in ctxs:                           # explicit teardown (contexts own CUDA streams and pool memory)
+        c.close()
+    rb.close()
+    bf.close()
+    if world > 1:
+        dist.destroy_process_group()
     if rank != 0:
         return
     n_reads = int(ds["n_reads"])             # primary mapped records of the BAM, each counted once, not once per overlapping tile
@@ -405,7 +411,7 @@ def main():
                                     "positions_per_s": res["positions_per_s"]}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % e}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -102,7 +102,8 @@ struct StageState {
     std::unordered_map<void*, size_t> pinned;         // every page-locked block (handed out or cached) -> its size class
     std::deque<size_t> wanted;                        // size classes the provisioning thread should page-lock
     size_t total_pinned = 0;
-    bool thread_started = false;
+    bool thread_started = false, stop = false;
+    std::thread worker;
 };
 StageState & stage_state() { static StageState *s = new StageState(); return *s; }   // leaked on purpose: used by a detached thread
 size_t stage_class(size_t bytes) {                    // next of {1, 1.25, 1.5, 1.75} x 2^k
@@ -118,7 +119,8 @@ void stage_provision_loop() {
         size_t cls = 0;
         {
             std::unique_lock<std::mutex> lk(st.mu);
-            st.cv.wait(lk, [&]() { return !st.wanted.empty(); });
+            st.cv.wait(lk, [&]() { return st.stop || !st.wanted.empty(); });
+            if (st.stop) { return; }
             cls = st.wanted.front(); st.wanted.pop_front();
             if (st.total_pinned + cls > kStageMaxPinned) { continue; }
             st.total_pinned += cls;
@@ -145,7 +147,12 @@ void *uvc_stage_alloc(size_t bytes) {
         auto it = st.free_blocks.find(cls);
         if (it != st.free_blocks.end()) { void *p = it->second; st.free_blocks.erase(it); return p; }
         st.wanted.push_back(cls);
-        if (!st.thread_started) { st.thread_started = true; std::thread(stage_provision_loop).detach(); }
+        if (!st.thread_started && !st.stop) {
+            st.thread_started = true;
+            st.worker = std::thread(stage_provision_loop);
+            // joined at exit, before the CUDA runtime (initialised earlier, hence torn down later) goes away
+            atexit([]() { StageState & s2 = stage_state(); { std::lock_guard<std::mutex> lk2(s2.mu); s2.stop = true; } s2.cv.notify_all(); if (s2.worker.joinable()) { s2.worker.join(); } });
+        }
     }
     st.cv.notify_one();
 #endif
