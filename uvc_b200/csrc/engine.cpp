@@ -201,43 +201,85 @@ __device__ __forceinline__ void uvc_warp_window(const BatchView & v, int64_t gp,
     }
 UVC_DEFINE_KERNEL(uvc_k0_read_consts, uvc::k0_read(v, i))
 UVC_DEFINE_POS_KERNEL(uvc_k1_prep_thres, uvc::k1_position(v, i, w))
-// Cooperative copy of n records of T from global to this warp's shared-memory slot (16-byte words, all 32 lanes).
-template <class T> __device__ __forceinline__ void uvc_warp_stage(T *dst, const T *src, int n, int lane) {
+// ---- warp-private staging of per-read records in shared memory, double-buffered with cp.async (LDGSTS)
+// A warp walks its union window in chunks of UVC_STAGE_READS reads. Chunk bases are multiples of 4 reads, so that every record array slice
+// starts on a 16-byte boundary (record sizes are multiples of 4 bytes) and is copied with 16-byte asynchronous copies; the copy of chunk
+// i + 1 is in flight while chunk i is processed.
+#define UVC_STAGE_READS 32
+__device__ __forceinline__ void uvc_cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void uvc_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void uvc_cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+// copies records [first, first + n) of src to dst (n <= UVC_STAGE_READS; first is a multiple of 4; the slice is rounded up to 16 bytes: the
+// arrays are allocated with slack)
+template <class T> __device__ __forceinline__ void uvc_warp_stage_async(T *dst, const T *src, int64_t first, int n, int lane) {
     static_assert(sizeof(T) % 4 == 0, "records are word multiples");
-    const int n_words = n * (int)(sizeof(T) / 4);
-    const uint32_t *s = (const uint32_t*)src;
-    uint32_t *d = (uint32_t*)dst;
-    for (int k = lane; k < n_words; k += 32) { d[k] = s[k]; }
+    const int n16 = (n * (int)sizeof(T) + 15) / 16;
+    const char *g = (const char*)(src + first);
+    char *d = (char*)dst;
+    for (int k = lane; k < n16; k += 32) { uvc_cp_async16(d + 16 * k, g + 16 * k); }
 }
 
-// both roles of a position sit in different warps of the same block: block = 64 positions x 2 roles.
-// Each warp stages the records (ReadRec + ReadDerived) of 32 reads of its union window in shared memory with one coalesced copy and then
-// walks them from there: the per-read loads of the inner loop become shared-memory broadcasts instead of dependent global loads.
-#define UVC_STAGE_READS 32
+// K2: both roles of a position sit in different warps of the same block: block = 64 positions x 2 roles.
+// Each warp stages the records (ReadRec + ReadDerived) of 32 reads of its union window in shared memory (asynchronously, one chunk ahead),
+// role 0 then gathers the (base, quality) byte pairs of the whole chunk with independent loads (memory-level parallelism instead of one
+// dependent load pair per read), and the per-read work runs entirely from shared memory.
+struct __align__(16) K2Stage {
+    ReadRec R[2][UVC_STAGE_READS];
+    ReadDerived D[2][UVC_STAGE_READS];           // 32 records = 3200 bytes: every buffer starts on a 16-byte boundary
+    uint16_t bq[UVC_STAGE_READS][32];
+};
 __global__ void __launch_bounds__(128) uvc_k2_bias_pileup(const BatchView v, int64_t n) {
-    __shared__ ReadRec sR[4][UVC_STAGE_READS];
-    __shared__ ReadDerived sD[4][UVC_STAGE_READS];
+    extern __shared__ __align__(16) unsigned char uvc_smem[];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gp = (i / 128) * 64 + (i % 64);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    K2Stage & S = ((K2Stage*)uvc_smem)[warp];
     const bool active = (gp < v.n_pos);
+    const int role = (int)((i % 128) / 64);
     uvc::Win w;
     uvc_warp_window(v, gp, active, w);
     uvc::K2State st;
-    if (active) { uvc::k2_begin(st, v, gp, (int)((i % 128) / 64)); }
-    for (int64_t cb = w.ulo; cb < w.uhi; cb += UVC_STAGE_READS) {
+    st.p = 0;
+    if (active) { uvc::k2_begin(st, v, gp, role); }
+    const int64_t c0 = w.ulo & ~(int64_t)3;
+    if (c0 < w.uhi) {
+        const int nc0 = (int)(w.uhi - c0 < UVC_STAGE_READS ? w.uhi - c0 : UVC_STAGE_READS);
+        uvc_warp_stage_async(S.R[0], v.reads, c0, nc0, lane);
+        uvc_warp_stage_async(S.D[0], v.rd, c0, nc0, lane);
+    }
+    uvc_cp_async_commit();
+    int buf = 0;
+    for (int64_t cb = c0; cb < w.uhi; cb += UVC_STAGE_READS, buf ^= 1) {
         const int nc = (int)(w.uhi - cb < UVC_STAGE_READS ? w.uhi - cb : UVC_STAGE_READS);
+        const int64_t nb = cb + UVC_STAGE_READS;
+        if (nb < w.uhi) {
+            const int nn = (int)(w.uhi - nb < UVC_STAGE_READS ? w.uhi - nb : UVC_STAGE_READS);
+            uvc_warp_stage_async(S.R[buf ^ 1], v.reads, nb, nn, lane);
+            uvc_warp_stage_async(S.D[buf ^ 1], v.rd, nb, nn, lane);
+        }
+        uvc_cp_async_commit();
+        uvc_cp_async_wait<1>();
         __syncwarp();
-        uvc_warp_stage(sR[warp], v.reads + cb, nc, lane);
-        uvc_warp_stage(sD[warp], v.rd + cb, nc, lane);
-        __syncwarp();
+        const ReadRec *sR = S.R[buf];
+        const ReadDerived *sD = S.D[buf];
+        if (role == 0) {
+            #pragma unroll 8
+            for (int k = 0; k < nc; k++) {
+                const int64_t ri = cb + k;
+                S.bq[k][lane] = (uint16_t)uvc::k2_fetch_base(st, v, sR[k], active && ri >= w.lo && ri < w.hi);
+            }
+        }
         if (active) {
             for (int k = 0; k < nc; k++) {
                 const int64_t ri = cb + k;
                 if (ri < w.lo || ri >= w.hi) { continue; }
-                uvc::k2_read(st, v, sR[warp][k], sD[warp][k]);
+                uvc::k2_read(st, v, sR[k], sD[k], (uint32_t)S.bq[k][lane]);
             }
         }
+        __syncwarp();
     }
     if (active) { uvc::k2_end(st, v); }
 }
@@ -247,7 +289,75 @@ UVC_DEFINE_KERNEL(uvc_k3a_fragment_stats, uvc::k3a_fragment(v, i))
 UVC_DEFINE_POS_KERNEL(uvc_k3b_fragment_consensus, uvc::k3b_position(v, i, w))
 UVC_DEFINE_KERNEL(uvc_km_family_columns, uvc::km_family_column(v, i))
 UVC_DEFINE_KERNEL(uvc_k4a_family_ends, uvc::k4a_family_strand(v, i))
-UVC_DEFINE_POS_KERNEL(uvc_k4_family_consensus, uvc::k4_position(v, i, w))
+// K4: the compact per-read family records (ReadFam, 32 B) of 32 reads are staged per warp (asynchronously, one chunk ahead); every lane then
+// gathers its own column entry of each read of the chunk with independent loads (consecutive lanes = consecutive addresses of one column) before
+// the per-read work runs from shared memory. Entries of single-fragment family-strands are the 8-byte fragment entries; the 32-byte entries of
+// multi-fragment (UMI) families are read in place.
+struct __align__(16) K4Stage {
+    ReadFam q[2][UVC_STAGE_READS];
+    FragCol e[UVC_STAGE_READS][32];
+};
+__global__ void __launch_bounds__(128) uvc_k4_family_consensus(const BatchView v, int64_t n) {
+    extern __shared__ __align__(16) unsigned char uvc_smem[];
+    const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    K4Stage & S = ((K4Stage*)uvc_smem)[warp];
+    const bool active = (gp < n);
+    uvc::Win w;
+    uvc_warp_window(v, gp, active, w);
+    uvc::K4State st;
+    st.p = 0; st.n_need2 = 0;
+    if (active) { uvc::k4_begin(st, v, gp); }
+    const int32_t p = st.p;
+    const int64_t c0 = w.ulo & ~(int64_t)3;
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) {
+            if (active) { uvc::k4_loop2_listed(st, v, w); }
+            if (!__any_sync(0xffffffffu, active && st.n_need2 > UVC_K4_LIST)) { break; }
+        }
+        if (c0 < w.uhi) { uvc_warp_stage_async(S.q[0], v.rfam, c0, (int)(w.uhi - c0 < UVC_STAGE_READS ? w.uhi - c0 : UVC_STAGE_READS), lane); }
+        uvc_cp_async_commit();
+        int buf = 0;
+        for (int64_t cb = c0; cb < w.uhi; cb += UVC_STAGE_READS, buf ^= 1) {
+            const int nc = (int)(w.uhi - cb < UVC_STAGE_READS ? w.uhi - cb : UVC_STAGE_READS);
+            const int64_t nb = cb + UVC_STAGE_READS;
+            if (nb < w.uhi) { uvc_warp_stage_async(S.q[buf ^ 1], v.rfam, nb, (int)(w.uhi - nb < UVC_STAGE_READS ? w.uhi - nb : UVC_STAGE_READS), lane); }
+            uvc_cp_async_commit();
+            uvc_cp_async_wait<1>();
+            __syncwarp();
+            const ReadFam *sq = S.q[buf];
+            if (pass == 0) {
+                #pragma unroll 8
+                for (int k = 0; k < nc; k++) {
+                    const int64_t ri = cb + k;
+                    const ReadFam & q = sq[k];
+                    // covered by this lane's window, first read of its (family, strand) at p, single-fragment strand: fetch the fragment entry
+                    if (active && ri >= w.lo && ri < w.hi && q.rend > p && q.famprev_maxrend <= p && (q.flags & UVC_RF_DIRECT)) { S.e[k][lane] = v.fcol[q.col_base + p]; }
+                }
+                if (active) {
+                    for (int k = 0; k < nc; k++) {
+                        const int64_t ri = cb + k;
+                        if (ri < w.lo || ri >= w.hi) { continue; }
+                        const ReadFam & q = sq[k];
+                        if (q.rend <= p || q.famprev_maxrend > p) { continue; }
+                        uvc::k4_loop1_read(st, v, q, (q.flags & UVC_RF_DIRECT) ? uvc::famcol_from_frag(S.e[k][lane], v.par) : v.mcol[q.col_base + p], ri - w.lo);
+                    }
+                }
+            } else if (active && st.n_need2 > UVC_K4_LIST) {
+                for (int k = 0; k < nc; k++) {
+                    const int64_t ri = cb + k;
+                    if (ri < w.lo || ri >= w.hi) { continue; }
+                    const ReadFam & q = sq[k];
+                    if (q.rend <= p) { continue; }
+                    uvc::k4_loop2_read(st, v, q);
+                }
+            }
+            __syncwarp();
+        }
+        uvc_cp_async_wait<0>();
+    }
+    if (active) { uvc::k4_end(st, v); }
+}
 UVC_DEFINE_KERNEL(uvc_k4c_family_haplotypes, uvc::k4c_family_strand(v, i))
 
 // scoring stage: K6 one thread per extended position, K5 one thread per zero-based position (heavy local state: 64 threads per block)
@@ -274,7 +384,7 @@ static void launch(uvc_kernel_t k, cudaStream_t s, const BatchView & v, int64_t 
 }
 
 static int backend_alloc(uvcgpu_ctx *ctx, BatchState & bs, void **out, size_t bytes, bool zero) {
-    if (0 == bytes) { bytes = 16; }
+    bytes += 64;     // slack: staged record slices are rounded up to 16 bytes, and clamped byte loads may touch offset 0 of an empty blob
     UVC_CUDA_CHECK(ctx, cudaMallocAsync(out, bytes, ctx->stream));   // stream-ordered pool: no device synchronisation, blocks are reused across batches
     bs.allocs.push_back(*out);
     if (zero) { UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, 0, bytes, ctx->stream)); }
@@ -300,14 +410,28 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     #define UVC_STAGE(kernel, n) { launch(kernel, ctx->stream, v, (n), launches); UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream)); }
     UVC_STAGE(uvc_k0_read_consts, v.n_reads)
     UVC_STAGE(uvc_k1_prep_thres, v.n_pos)
-    UVC_STAGE(uvc_k2_bias_pileup, ((v.n_pos + 63) / 64) * 128)
+    if (v.n_pos > 0) {
+        static_assert(sizeof(K2Stage) % 16 == 0, "per-warp staging slots keep 16-byte alignment");
+        const size_t smem = 4 * sizeof(K2Stage);
+        UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k2_bias_pileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        uvc_k2_bias_pileup<<<(unsigned)((v.n_pos + 63) / 64), 128, smem, ctx->stream>>>(v, v.n_pos);
+        launches++;
+    }
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
     UVC_STAGE(uvc_k2e_indel_events, v.n_ev)
     UVC_STAGE(uvc_kf_fragment_columns, v.n_fcol)
     UVC_STAGE(uvc_k3a_fragment_stats, v.n_frags)
     UVC_STAGE(uvc_k3b_fragment_consensus, v.n_pos)
     UVC_STAGE(uvc_km_family_columns, v.n_mcol)
     UVC_STAGE(uvc_k4a_family_ends, 2 * v.n_fams)
-    UVC_STAGE(uvc_k4_family_consensus, v.n_pos)
+    if (v.n_pos > 0) {
+        static_assert(sizeof(K4Stage) % 16 == 0, "per-warp staging slots keep 16-byte alignment");
+        const size_t smem = 4 * sizeof(K4Stage);
+        UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k4_family_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        uvc_k4_family_consensus<<<(unsigned)((v.n_pos + 127) / 128), 128, smem, ctx->stream>>>(v, v.n_pos);
+        launches++;
+    }
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
     UVC_STAGE(uvc_k4c_family_haplotypes, 2 * v.n_fams)
     #undef UVC_STAGE
     UVC_CUDA_CHECK(ctx, cudaGetLastError());

@@ -688,10 +688,32 @@ UVC_HD void k2_begin(K2State & s, const BatchView & v, int64_t gp, int role) {
     segacc_zero(s.acc);
 }
 
-// one read of the position's window (R, D may live in shared memory: the CUDA kernel stages the records of 32 reads per warp at a time)
-UVC_HD void k2_read(K2State & s, const BatchView & v, const ReadRec & R, const ReadDerived & D) {
+// What role 0 needs from a read's own bytes at p: (base symbol << 8) | raw-plus-fix-up quality, or UVC_K2_NOBASE when the read shows no aligned
+// base at p (or `mine` is false: the read lies outside this lane's own window). The two byte loads are unconditional (clamped index) so that
+// the CUDA kernel can issue them for a whole chunk of reads back to back instead of one dependent load pair per read.
+#define UVC_K2_NOBASE 0xffffu
+UVC_HD uint32_t k2_fetch_base(const K2State & s, const BatchView & v, const ReadRec & R, bool mine) {
+    const int32_t o = s.p - R.pos;
+    const bool cov = (mine && o >= 0 && s.p < R.rend && R.l_qseq > 0);
+    int32_t qpos = R.m_qoff + o;
+    bool is_m = cov;
+    if (!R.simple) {
+        qpos = 0;
+        if (cov) { const CxEntry e = v.cx[R.cx_off + o]; qpos = e.qpos; is_m = (e.flags & 1); }
+    }
+    qpos = tmax(0, tmin(qpos, R.l_qseq - 1));
+    const uint8_t *seq = v.seq + R.seq_off;
+    const uint8_t *qual = v.qual + R.qual_off;
+    const uint32_t pk = ((uint32_t)base3(seq, R.l_qseq > 0 ? qpos : 0) << 8) | (uint32_t)qual[R.l_qseq > 0 ? qpos : 0];
+    return (is_m ? pk : UVC_K2_NOBASE);
+}
+
+// one read of the position's window (R, D may live in shared memory: the CUDA kernel stages the records of 32 reads per warp at a time);
+// `packed` is k2_fetch_base of this read (role 0 only)
+UVC_HD void k2_read(K2State & s, const BatchView & v, const ReadRec & R, const ReadDerived & D, uint32_t packed) {
     const int32_t p = s.p;
     if (R.rend <= p) { return; }
+    if (s.role == 0 && packed == UVC_K2_NOBASE) { return; }
     const Locus L = locate(v, R, p);
     if (!L.is_m) { return; }
     if (primer_masked(v, R, D, p)) { return; }
@@ -702,17 +724,19 @@ UVC_HD void k2_read(K2State & s, const BatchView & v, const ReadRec & R, const R
         s.acc.bqsum += w;
         segbias<true>(s.acc, v, R, D, s.th, s.baq_p, s.baq2_p, w, p, 100, false, 0, dist);
     } else {
-        const int sym = base3(v.seq + R.seq_off, L.qpos);
-        const int32_t bq = (int32_t)v.qual[R.qual_off + L.qpos] + v.par.bq_phred_added_misma;
+        const int sym = (int)(packed >> 8);
+        const int32_t bq = (int32_t)(packed & 0xffu) + v.par.bq_phred_added_misma;
         if (sym == s.major) {
             s.acc.bqsum += bq;
             segbias<false>(s.acc, v, R, D, s.th, s.baq_p, s.baq2_p, bq, p, D.bm_term[sym], false, 0, dist);
         } else {
+            // a base that differs from the reference (rare): its own symbol's records are updated with fire-and-forget atomics, which do not
+            // stall the warp on ~40 dependent read-modify-writes (this thread is still the only writer of these records in this kernel)
             SegAcc one;
             segacc_zero(one);
             one.bqsum = bq;
             segbias<false>(one, v, R, D, s.th, s.baq_p, s.baq2_p, bq, p, D.bm_term[sym], false, 0, dist);
-            segacc_flush<false>(v, s.gp, sym, one);
+            segacc_flush<true>(v, s.gp, sym, one);
         }
     }
 }
@@ -726,7 +750,7 @@ UVC_HD void k2_position(const BatchView & v, int64_t gp, int role, const Win & w
     k2_begin(s, v, gp, role);
     for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
         if (ri < w.lo || ri >= w.hi) { continue; }
-        k2_read(s, v, v.reads[ri], v.rd[ri]);
+        k2_read(s, v, v.reads[ri], v.rd[ri], (role == 0 ? k2_fetch_base(s, v, v.reads[ri], true) : 0u));
     }
     k2_end(s, v);
 }
@@ -1372,141 +1396,191 @@ UVC_HD void k4a_family_strand(const BatchView & v, int64_t i) {
 // ------------------------------------------------------------------------------------------------ K4: one thread per position
 // updateByAlns3UsingFQ gathered per position: family loop 1 (main.hpp:2999-3355), then - because its only cross-family dependence, cDPM/cDPm,
 // is per position - family loop 2 (main.hpp:3392-3551) and the per-strand reduction of the quality buckets (main.hpp:3552-3591).
-UVC_HD void k4_position(const BatchView & v, int64_t gp, const Win & w) {
-    const TileInfo & T = v.tiles[v.pos_tile[gp]];
-    const int32_t p = (int32_t)(gp - T.pos_off) + T.ext_beg;
-    const uvcgpu_params & par = v.par;
-    const int64_t po = T.pos_off - T.ext_beg;
-    const int32_t *baq = v.baq + po;
-    const int32_t *baq2 = v.baq2 + po;
-    const int ref = v.refsym[gp];
+//
+// Loop 2 needs the completed cDPM/cDPm of loop 1 only for families that can enter a quality bucket (tot_nfrags >= fam_thres_dup1add) and its
+// single-strand / duplex consensus counters only for duplex-UMI families. For every other (family, strand) - all of them on non-UMI data - the
+// whole of loop 2 is "cDP1 += 1", which loop 1 does on the spot from the same column entry; the second pass over the window then only runs for
+// positions that saw a family it still has work for (need2).
+#define UVC_K4_LIST 24
+struct K4State {
+    const TileInfo *T;
+    int64_t gp;
+    int32_t p;
+    int ref;
+    int32_t baq_last, tn_add;
+    const int32_t *baq, *baq2;
+    uvcgpu_thres_set th;
+    uvcgpu_faminfo_set *finfo;
+    uint32_t touched;      // bit strand * 14 + symbol: facc / bucket rows that are live (rows are zeroed lazily on first touch, see K3b)
+    // reads (offsets from the start of the window) that loop 1 leaves work for; more than UVC_K4_LIST of them: the whole window is walked again
+    int32_t n_need2;
+    uint16_t need2[UVC_K4_LIST];
     // thread-private family depth counters (this thread is the position's only writer): stored once at the end
-    // zeroed lazily per (strand, symbol) on first touch (bit strand * 14 + symbol of `touched`), see K3b
     int32_t facc[2 * UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS];
     int32_t bucket[2 * UVC_NSYM * UVC_NUM_BUCKETS];
-    uint32_t touched = 0;
-    #define UVC_K4_TOUCH(strand_, sym_) { const int ix_ = (strand_) * UVC_NSYM + (sym_); if (!((touched >> ix_) & 1u)) { touched |= (1u << ix_); \
-        for (int k_ = 0; k_ < UVCGPU_NUM_FAM_DEPTHS; k_++) { facc[ix_ * UVCGPU_NUM_FAM_DEPTHS + k_] = 0; } \
-        for (int k_ = 0; k_ < UVC_NUM_BUCKETS; k_++) { bucket[ix_ * UVC_NUM_BUCKETS + k_] = 0; } } }
-    int32_t *fam0 = facc, *fam1 = facc + UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS;
-    uvcgpu_faminfo_set *finfo = v.faminfo + gp * UVC_NSYM;
-    int32_t *dup = v.duplex + gp * UVC_NSYM * UVCGPU_NUM_DUPLEX_DEPTHS;
-    int32_t *vq = v.vq + gp * UVC_NSYM * UVCGPU_NUM_VQ_TAGS;
-    const uvcgpu_thres_set th = v.thres[gp];
-    const int32_t baq_last = T.ext_end - 1;
-    enum { cDP1 = 0, cDP12 = 1, cDP2 = 2, cDP3 = 3, cDPM = 4, cDPm = 5, cDP21 = 6, cDPD = 7 };
+};
+enum { UVC_cDP1 = 0, UVC_cDP12 = 1, UVC_cDP2 = 2, UVC_cDP3 = 3, UVC_cDPM = 4, UVC_cDPm = 5, UVC_cDP21 = 6, UVC_cDPD = 7 };
 
-    // ---- loop 1
-    for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
-        if (ri < w.lo || ri >= w.hi) { continue; }
-        const ReadFam q = v.rfam[ri];
-        if (q.rend <= p || q.famprev_maxrend > p) { continue; }
-        const FamRec & F = v.fams[q.fam];      // only dereferenced on the tier-2 (UMI family) path
+UVC_HD void k4_touch(K4State & s, int strand, int sym) {
+    const int ix = strand * UVC_NSYM + sym;
+    if (!((s.touched >> ix) & 1u)) {
+        s.touched |= (1u << ix);
+        for (int k = 0; k < UVCGPU_NUM_FAM_DEPTHS; k++) { s.facc[ix * UVCGPU_NUM_FAM_DEPTHS + k] = 0; }
+        for (int k = 0; k < UVC_NUM_BUCKETS; k++) { s.bucket[ix * UVC_NUM_BUCKETS + k] = 0; }
+    }
+}
+
+UVC_HD void k4_begin(K4State & s, const BatchView & v, int64_t gp) {
+    const TileInfo & T = v.tiles[v.pos_tile[gp]];
+    s.T = &T; s.gp = gp;
+    s.p = (int32_t)(gp - T.pos_off) + T.ext_beg;
+    const int64_t po = T.pos_off - T.ext_beg;
+    s.baq = v.baq + po; s.baq2 = v.baq2 + po;
+    s.ref = v.refsym[gp];
+    s.baq_last = T.ext_end - 1;
+    s.tn_add = (v.par.is_tumor_vcf_provided ? 4 : 0);
+    s.th = v.thres[gp];
+    s.finfo = v.faminfo + gp * UVC_NSYM;
+    s.touched = 0;
+    s.n_need2 = 0;
+}
+
+// does loop 1 (with the loop-2 share described above) cover everything this (family, strand) entry asks of loop 2 for symbol type `type`?
+UVC_HD bool k4_loop2_done_in_loop1(const uvcgpu_params & par, const ReadFam & q, const FamCol & m, int type) {
+    return (0 == (q.flags & UVC_RF_DUPLEX_UMI)) && ((int32_t)m.tc1[type] < par.fam_thres_dup1add);
+}
+
+// loop 1 for the first read q of its (family, strand) that covers p; m is that (family, strand)'s column entry at p; woff = offset of the read
+// from the start of the position's window
+UVC_HD void k4_loop1_read(K4State & s, const BatchView & v, const ReadFam & q, const FamCol & m, int64_t woff) {
+    const uvcgpu_params & par = v.par;
+    const int32_t p = s.p;
+    const int64_t gp = s.gp;
+    const int32_t *baq = s.baq, *baq2 = s.baq2;
+    const uvcgpu_thres_set & th = s.th;
+    const FamRec & F = v.fams[q.fam];      // only dereferenced on the tier-2 (UMI family) path
+    const int strand = (int)(q.flags & UVC_RF_STRAND);
+    int32_t *fd = s.facc + strand * (UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS);
+    #pragma unroll
+    for (int type = 1; type >= 0; type--) {
+        const int a = m.a1[type]; const int32_t cc = m.cc1[type], tc = m.tc1[type];
+        if (0 == tc) { continue; }
+        k4_touch(s, strand, a);
+        fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDP12] += 1;
+        if (1 == tc) { fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDP21] += 1; }
+        const bool is_indel = (is_ins_symbol(a) || is_del_symbol(a));
+        int32_t fam_ev = -2;   // family-majority indel event, computed lazily
+        if (fam_is_good(par, F, cc, tc)) {
+            fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDP2] += 1;
+            if (is_indel) {
+                fam_ev = fam_indel_majority(v, F, strand, p, gp, a, NULL);
+                if (fam_ev >= 0) { rec_put6(v, UVC_REC_CDP2_INDEL, strand, a, p, fam_ev, 1); }
+            }
+            // family-level position / BAQ bias (main.hpp:3208-3318)
+            int32_t rbeg = tmin(F.nsb_min[strand], p);
+            int32_t rend = tmax(F.nsb_max[strand], p);
+            const int32_t l2r = F.l2r_end_median[strand], r2l = F.r2l_end_median[strand];
+            const bool nonconf_middle = (l2r <= (r2l + par.indel_adj_tracklen_dist));
+            if (nonconf_middle && p < r2l) { rend = tmax(tmin(l2r, tmin(r2l, rend)), p); }
+            if (nonconf_middle && l2r < p) { rbeg = tmin(tmax(l2r, tmax(r2l, rbeg)), p); }
+            uvcgpu_faminfo_set & fi = s.finfo[a];
+            const bool isGap = (type == 1);
+            const int32_t l_nb = nnminus(p + 1, rbeg);
+            const int32_t r_nb = nnminus(rend, p);
+            const int32_t LPxT = (isGap ? th.aLPxT : tmin(th.aLPxT, th.aRPxT));
+            int32_t indel_len = 0;
+            if (is_ins_symbol(a)) {
+                // QUIRK: the reference takes the majority COUNT of the family's inserted sequences as "indel_len" (main.hpp:3238-3244)
+                for (int sym = UVC_LINK_I3P; sym <= UVC_LINK_I1; sym++) { int32_t n = 0; fam_indel_majority(v, F, strand, p, gp, sym, &n); indel_len = tmax(indel_len, n); }
+            } else if (is_del_symbol(a)) {
+                for (int sym = UVC_LINK_D3P; sym <= UVC_LINK_D1; sym++) { int32_t n = 0; fam_indel_majority(v, F, strand, p, gp, sym, &n); indel_len = tmax(indel_len, n); }
+            }
+            const bool far_from_edge = (l_nb + (is_ins_symbol(a) ? nnminus(indel_len, par.microadjust_nobias_pos_indel_maxlen) : 0) >= LPxT) && (r_nb >= th.aRPxT);
+            if (far_from_edge) {
+                int64_t lpl = 0, rpl = 0;
+                bidir_bias(fi.c2LP1, fi.c2LP2, fi.c2RP1, fi.c2RP2, lpl, rpl, th.aLP1t, th.aLP2t, th.aRP1t, th.aRP2t, l_nb, r_nb, true, 0);
+                fi.c2LPL += (int32_t)lpl; fi.c2RPL += (int32_t)rpl;
+            }
+            if (nnminus(p + 1, F.nsb_min[strand]) >= par.bias_thres_strict_c2LRP0) { fi.c2LP0 += 1; }
+            if (nnminus(F.nsb_max[strand], p) >= par.bias_thres_strict_c2LRP0) { fi.c2RP0 += 1; }
+            const int32_t seg_l_baq = baq[p] - baq[tmax(rbeg, nnminus(p, UVC_MAX_STR_N_BASES))] + 1;
+            const int32_t ridx = tmin(rend - 1, tmin(p + UVC_MAX_STR_N_BASES, s.baq_last));
+            const int32_t seg_r_baq0 = baq[ridx] - baq[p] + 1;
+            const int32_t seg_r_baq = (isGap ? tmin(seg_r_baq0, baq2[ridx] - baq2[p] + 7) : seg_r_baq0);
+            const int32_t highBAQ = par.bias_thres_highBAQ + (isGap ? 0 : 3);
+            if (seg_l_baq >= highBAQ && seg_r_baq >= highBAQ) {
+                bidir_bias(fi.c2LB1, fi.c2LB2, fi.c2RB1, fi.c2RB2, fi.c2LBL, fi.c2RBL, par.bias_thres_BAQ1, par.bias_thres_BAQ2, par.bias_thres_BAQ1, par.bias_thres_BAQ2,
+                        seg_l_baq, seg_r_baq, true, 0);
+            }
+            fi.c2BQ2 += 1;
+        }
+        if (par.fam_thres_dup2add <= tc && (cc * 100 >= tc * par.fam_thres_dup2perc)) { fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDP3] += 1; }
+        if (is_indel) {
+            if (fam_ev == -2) { fam_ev = fam_indel_majority(v, F, strand, p, gp, a, NULL); }
+            if (fam_ev >= 0) { rec_put6(v, UVC_REC_FAM_INDEL, strand, a, p, fam_ev, 1); }
+        }
+        const bool is_subst = (a <= UVC_BASE_NN);
+        const int32_t flat = (is_subst ? par.fam_thres_emperr_all_flat_snv : par.fam_thres_emperr_all_flat_indel);
+        const int32_t perc = (is_subst ? par.fam_thres_emperr_con_perc_snv : par.fam_thres_emperr_con_perc_indel);
+        if (tc < flat) { continue; }
+        if (cc * 100 < tc * perc) { continue; }
+        // every other symbol of the type adds its own count to cDPm and, QUIRK, the whole total to cDPM (main.hpp:3343-3352)
+        const int32_t n_other = (type == 0 ? (UVC_BASE_NN - UVC_BASE_A) : (UVC_LINK_NN - UVC_LINK_M));
+        fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDPm] += tc - cc;
+        fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDPM] += tc * n_other;
+    }
+    // the share of loop 2 that needs nothing from the other families (see the header comment)
+    bool need2 = (0 != (q.flags & UVC_RF_DUPLEX_UMI));
+    #pragma unroll
+    for (int type = 1; type >= 0; type--) {
+        if (0 == m.mmm_tot[type]) { continue; }
+        if (k4_loop2_done_in_loop1(par, q, m, type)) {
+            const int a = m.a2[type];
+            k4_touch(s, strand, a);
+            fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDP1] += 1;
+        } else {
+            need2 = true;
+        }
+    }
+    if (need2) {
+        if (s.n_need2 < UVC_K4_LIST && woff < 65536) { s.need2[s.n_need2] = (uint16_t)woff; s.n_need2 += 1; } else { s.n_need2 = UVC_K4_LIST + 1; }
+    }
+}
+
+// loop 2 for a read q that covers p (q.rend > p), for what loop 1 left over. Only reads that loop 1 visited can have work here: the duplex
+// step wants the first read of the whole family at p, which is also the first read of its own strand.
+UVC_HD void k4_loop2_read(K4State & s, const BatchView & v, const ReadFam & q) {
+    const uvcgpu_params & par = v.par;
+    const int32_t p = s.p;
+    const int64_t gp = s.gp;
+    const FamRec & F = v.fams[q.fam];      // only dereferenced for indel identities and duplex families
+    const bool is_duplex_umi = (0 != (q.flags & UVC_RF_DUPLEX_UMI));
+    const bool will_inc_dscs = (is_duplex_umi && (q.flags & UVC_RF_BOTH_STRANDS));
+    const bool will_inc_sscs = (is_duplex_umi && !will_inc_dscs);
+    if (q.famprev_maxrend <= p) {   // first read of its (family, strand) that covers p
         const int strand = (int)(q.flags & UVC_RF_STRAND);
-        int32_t *fd = (strand ? fam1 : fam0);
+        int32_t *fd = s.facc + strand * (UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS);
         const FamCol m = fam_entry_of_read(v, q, p);
         #pragma unroll
         for (int type = 1; type >= 0; type--) {
-            const int a = m.a1[type]; const int32_t cc = m.cc1[type], tc = m.tc1[type];
-            if (0 == tc) { continue; }
-            UVC_K4_TOUCH(strand, a)
-            fd[a * UVCGPU_NUM_FAM_DEPTHS + cDP12] += 1;
-            if (1 == tc) { fd[a * UVCGPU_NUM_FAM_DEPTHS + cDP21] += 1; }
-            const bool is_indel = (is_ins_symbol(a) || is_del_symbol(a));
-            int32_t fam_ev = -2;   // family-majority indel event, computed lazily
-            if (fam_is_good(par, F, cc, tc)) {
-                fd[a * UVCGPU_NUM_FAM_DEPTHS + cDP2] += 1;
-                if (is_indel) {
-                    fam_ev = fam_indel_majority(v, F, strand, p, gp, a, NULL);
-                    if (fam_ev >= 0) { rec_put6(v, UVC_REC_CDP2_INDEL, strand, a, p, fam_ev, 1); }
+            const int a = m.a2[type]; const int32_t con_sumBQs = (int32_t)m.mmm_cc[type], tot_sumBQs = (int32_t)m.mmm_tot[type];
+            if (0 == tot_sumBQs) { continue; }
+            if (k4_loop2_done_in_loop1(par, q, m, type)) { continue; }
+            const int32_t con_nfrags = m.con_a2[type];
+            const int32_t tot_nfrags = m.tc1[type];
+            k4_touch(s, strand, a);
+            fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDP1] += 1;
+            if (will_inc_sscs && (tot_nfrags >= par.fam_thres_dup1add) && (con_nfrags * 100 >= tot_nfrags * par.fam_thres_dup1perc)) {
+                fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDPD] += 1;
+                if (is_ins_symbol(a) || is_del_symbol(a)) {
+                    const int32_t e = fam_indel_majority(v, F, strand, p, gp, a, NULL);
+                    if (e >= 0) { rec_put6(v, UVC_REC_C2D_INDEL, strand, a, p, e, 1); }
                 }
-                // family-level position / BAQ bias (main.hpp:3208-3318)
-                int32_t rbeg = tmin(F.nsb_min[strand], p);
-                int32_t rend = tmax(F.nsb_max[strand], p);
-                const int32_t l2r = F.l2r_end_median[strand], r2l = F.r2l_end_median[strand];
-                const bool nonconf_middle = (l2r <= (r2l + par.indel_adj_tracklen_dist));
-                if (nonconf_middle && p < r2l) { rend = tmax(tmin(l2r, tmin(r2l, rend)), p); }
-                if (nonconf_middle && l2r < p) { rbeg = tmin(tmax(l2r, tmax(r2l, rbeg)), p); }
-                uvcgpu_faminfo_set & fi = finfo[a];
-                const bool isGap = (type == 1);
-                const int32_t l_nb = nnminus(p + 1, rbeg);
-                const int32_t r_nb = nnminus(rend, p);
-                const int32_t LPxT = (isGap ? th.aLPxT : tmin(th.aLPxT, th.aRPxT));
-                int32_t indel_len = 0;
-                if (is_ins_symbol(a)) {
-                    // QUIRK: the reference takes the majority COUNT of the family's inserted sequences as "indel_len" (main.hpp:3238-3244)
-                    for (int sym = UVC_LINK_I3P; sym <= UVC_LINK_I1; sym++) { int32_t n = 0; fam_indel_majority(v, F, strand, p, gp, sym, &n); indel_len = tmax(indel_len, n); }
-                } else if (is_del_symbol(a)) {
-                    for (int sym = UVC_LINK_D3P; sym <= UVC_LINK_D1; sym++) { int32_t n = 0; fam_indel_majority(v, F, strand, p, gp, sym, &n); indel_len = tmax(indel_len, n); }
-                }
-                const bool far_from_edge = (l_nb + (is_ins_symbol(a) ? nnminus(indel_len, par.microadjust_nobias_pos_indel_maxlen) : 0) >= LPxT) && (r_nb >= th.aRPxT);
-                if (far_from_edge) {
-                    int64_t lpl = 0, rpl = 0;
-                    bidir_bias(fi.c2LP1, fi.c2LP2, fi.c2RP1, fi.c2RP2, lpl, rpl, th.aLP1t, th.aLP2t, th.aRP1t, th.aRP2t, l_nb, r_nb, true, 0);
-                    fi.c2LPL += (int32_t)lpl; fi.c2RPL += (int32_t)rpl;
-                }
-                if (nnminus(p + 1, F.nsb_min[strand]) >= par.bias_thres_strict_c2LRP0) { fi.c2LP0 += 1; }
-                if (nnminus(F.nsb_max[strand], p) >= par.bias_thres_strict_c2LRP0) { fi.c2RP0 += 1; }
-                const int32_t seg_l_baq = baq[p] - baq[tmax(rbeg, nnminus(p, UVC_MAX_STR_N_BASES))] + 1;
-                const int32_t ridx = tmin(rend - 1, tmin(p + UVC_MAX_STR_N_BASES, baq_last));
-                const int32_t seg_r_baq0 = baq[ridx] - baq[p] + 1;
-                const int32_t seg_r_baq = (isGap ? tmin(seg_r_baq0, baq2[ridx] - baq2[p] + 7) : seg_r_baq0);
-                const int32_t highBAQ = par.bias_thres_highBAQ + (isGap ? 0 : 3);
-                if (seg_l_baq >= highBAQ && seg_r_baq >= highBAQ) {
-                    bidir_bias(fi.c2LB1, fi.c2LB2, fi.c2RB1, fi.c2RB2, fi.c2LBL, fi.c2RBL, par.bias_thres_BAQ1, par.bias_thres_BAQ2, par.bias_thres_BAQ1, par.bias_thres_BAQ2,
-                            seg_l_baq, seg_r_baq, true, 0);
-                }
-                fi.c2BQ2 += 1;
             }
-            if (par.fam_thres_dup2add <= tc && (cc * 100 >= tc * par.fam_thres_dup2perc)) { fd[a * UVCGPU_NUM_FAM_DEPTHS + cDP3] += 1; }
-            if (is_indel) {
-                if (fam_ev == -2) { fam_ev = fam_indel_majority(v, F, strand, p, gp, a, NULL); }
-                if (fam_ev >= 0) { rec_put6(v, UVC_REC_FAM_INDEL, strand, a, p, fam_ev, 1); }
-            }
-            const bool is_subst = (a <= UVC_BASE_NN);
-            const int32_t flat = (is_subst ? par.fam_thres_emperr_all_flat_snv : par.fam_thres_emperr_all_flat_indel);
-            const int32_t perc = (is_subst ? par.fam_thres_emperr_con_perc_snv : par.fam_thres_emperr_con_perc_indel);
-            if (tc < flat) { continue; }
-            if (cc * 100 < tc * perc) { continue; }
-            // every other symbol of the type adds its own count to cDPm and, QUIRK, the whole total to cDPM (main.hpp:3343-3352)
-            const int32_t n_other = (type == 0 ? (UVC_BASE_NN - UVC_BASE_A) : (UVC_LINK_NN - UVC_LINK_M));
-            fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPm] += tc - cc;
-            fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPM] += tc * n_other;
-        }
-    }
-
-    // ---- loop 2
-    const int32_t tn_add = (par.is_tumor_vcf_provided ? 4 : 0);
-    for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
-        if (ri < w.lo || ri >= w.hi) { continue; }
-        const ReadFam q = v.rfam[ri];
-        if (q.rend <= p) { continue; }
-        const FamRec & F = v.fams[q.fam];      // only dereferenced for indel identities and duplex families
-        const bool is_duplex_umi = (0 != (q.flags & UVC_RF_DUPLEX_UMI));
-        const bool will_inc_dscs = (is_duplex_umi && (q.flags & UVC_RF_BOTH_STRANDS));
-        const bool will_inc_sscs = (is_duplex_umi && !will_inc_dscs);
-        if (q.famprev_maxrend <= p) {   // first read of its (family, strand) that covers p
-            const int strand = (int)(q.flags & UVC_RF_STRAND);
-            int32_t *fd = (strand ? fam1 : fam0);
-            const FamCol m = fam_entry_of_read(v, q, p);
-            #pragma unroll
-            for (int type = 1; type >= 0; type--) {
-                const int a = m.a2[type]; const int32_t con_sumBQs = (int32_t)m.mmm_cc[type], tot_sumBQs = (int32_t)m.mmm_tot[type];
-                if (0 == tot_sumBQs) { continue; }
-                const int32_t con_nfrags = m.con_a2[type];
-                const int32_t tot_nfrags = m.tc1[type];
-                UVC_K4_TOUCH(strand, a)
-                fd[a * UVCGPU_NUM_FAM_DEPTHS + cDP1] += 1;
-                if (will_inc_sscs && (tot_nfrags >= par.fam_thres_dup1add) && (con_nfrags * 100 >= tot_nfrags * par.fam_thres_dup1perc)) {
-                    fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPD] += 1;
-                    if (is_ins_symbol(a) || is_del_symbol(a)) {
-                        const int32_t e = fam_indel_majority(v, F, strand, p, gp, a, NULL);
-                        if (e >= 0) { rec_put6(v, UVC_REC_C2D_INDEL, strand, a, p, e, 1); }
-                    }
-                }
+            if (tot_nfrags >= par.fam_thres_dup1add) {     // the family's consensus quality only matters if it enters a bucket (main.hpp:3445-3455)
                 const int32_t avgBQ = ((0 == tot_nfrags) ? 1 : (con_sumBQs / tot_nfrags));
-                const int32_t majorcount = fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPM];
-                const int32_t minorcount = fd[a * UVCGPU_NUM_FAM_DEPTHS + cDPm];
+                const int32_t majorcount = fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDPM];
+                const int32_t minorcount = fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDPm];
                 const double prior_weight = 1.0 / (minorcount + 1.0);
                 const double p2p = v.phred2prob_tab[tmin(tmax(avgBQ, 0), 127)];
                 const double realphred = -10 * log((minorcount + prior_weight) / (majorcount + minorcount + prior_weight / p2p)) / v.ln10;
@@ -1517,63 +1591,94 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp, const Win & w) {
                 } else {
                     confam_qual = tmax(1, tmin(indep_frag_phred, (con_sumBQs * 2) - tot_sumBQs));
                 }
-                const int32_t max_qual = sscs_phred(par, ref, a) + tn_add;
+                const int32_t max_qual = sscs_phred(par, s.ref, a) + s.tn_add;
                 const int32_t confam_qual2 = tmin(confam_qual, max_qual);
-                if (tot_nfrags >= par.fam_thres_dup1add) {
-                    const int32_t pb = (max_qual - confam_qual2 + 2) / 4;
-                    if (pb >= 0 && pb < UVC_NUM_BUCKETS) { bucket[(strand * UVC_NSYM + a) * UVC_NUM_BUCKETS + pb] += 1; }
-                }
+                const int32_t pb = (max_qual - confam_qual2 + 2) / 4;
+                if (pb >= 0 && pb < UVC_NUM_BUCKETS) { s.bucket[(strand * UVC_NSYM + a) * UVC_NUM_BUCKETS + pb] += 1; }
             }
         }
-        if (will_inc_dscs && q.fambothprev_maxrend <= p) {   // first read of the duplex family that covers p
-            int32_t dcount[UVC_NSYM];
-            votes_zero(dcount);
-            int link_con[2] = {-1, -1};
-            for (int strand = 0; strand < 2; strand++) {
-                const FamCol m = fam_entry(v, F, strand, p);
-                for (int type = 1; type >= 0; type--) {
-                    const int a = m.a1[type]; const int32_t cc = m.cc1[type], tc = m.tc1[type];
-                    const int32_t adj = tmax(cc * 2, tc) - tc;
-                    if (adj >= 1 && adj > 0) { dcount[a] += 1; }
-                    if (type == 1 && cc > 0) { link_con[strand] = a; }
-                }
+    }
+    if (will_inc_dscs && q.fambothprev_maxrend <= p) {   // first read of the duplex family that covers p
+        int32_t *dup = v.duplex + gp * UVC_NSYM * UVCGPU_NUM_DUPLEX_DEPTHS;
+        int32_t dcount[UVC_NSYM];
+        votes_zero(dcount);
+        int link_con[2] = {-1, -1};
+        for (int strand = 0; strand < 2; strand++) {
+            const FamCol m = fam_entry(v, F, strand, p);
+            for (int type = 1; type >= 0; type--) {
+                const int a = m.a1[type]; const int32_t cc = m.cc1[type], tc = m.tc1[type];
+                const int32_t adj = tmax(cc * 2, tc) - tc;
+                if (adj >= 1 && adj > 0) { dcount[a] += 1; }
+                if (type == 1 && cc > 0) { link_con[strand] = a; }
             }
-            for (int type = 0; type < 2; type++) {
-                int a; int32_t cc, tc;
-                plain_consensus(dcount, type, a, cc, tc);
-                if (0 < tc) { dup[a * UVCGPU_NUM_DUPLEX_DEPTHS + 0] += 1; }
-                if (1 < tc) {
-                    dup[a * UVCGPU_NUM_DUPLEX_DEPTHS + 1] += 1;
-                    if (is_ins_symbol(a) || is_del_symbol(a)) {
-                        // majority identity of the duplex map: one entry per strand whose family link consensus is this symbol
-                        int32_t e0 = (link_con[0] == a ? fam_indel_majority(v, F, 0, p, gp, a, NULL) : -1);
-                        int32_t e1 = (link_con[1] == a ? fam_indel_majority(v, F, 1, p, gp, a, NULL) : -1);
-                        int32_t e = (e0 < 0 ? e1 : (e1 < 0 ? e0 : ((indel_cmp(v, v.ev[e0], v.ev[e1]) >= 0) ? e0 : e1)));
-                        if (e >= 0) { rec_put6(v, UVC_REC_C2D_INDEL, 0, a, p, e, 1); rec_put6(v, UVC_REC_C2D_INDEL, 1, a, p, e, 1); }
-                    }
+        }
+        for (int type = 0; type < 2; type++) {
+            int a; int32_t cc, tc;
+            plain_consensus(dcount, type, a, cc, tc);
+            if (0 < tc) { dup[a * UVCGPU_NUM_DUPLEX_DEPTHS + 0] += 1; }
+            if (1 < tc) {
+                dup[a * UVCGPU_NUM_DUPLEX_DEPTHS + 1] += 1;
+                if (is_ins_symbol(a) || is_del_symbol(a)) {
+                    // majority identity of the duplex map: one entry per strand whose family link consensus is this symbol
+                    int32_t e0 = (link_con[0] == a ? fam_indel_majority(v, F, 0, p, gp, a, NULL) : -1);
+                    int32_t e1 = (link_con[1] == a ? fam_indel_majority(v, F, 1, p, gp, a, NULL) : -1);
+                    int32_t e = (e0 < 0 ? e1 : (e1 < 0 ? e0 : ((indel_cmp(v, v.ev[e0], v.ev[e1]) >= 0) ? e0 : e1)));
+                    if (e >= 0) { rec_put6(v, UVC_REC_C2D_INDEL, 0, a, p, e, 1); rec_put6(v, UVC_REC_C2D_INDEL, 1, a, p, e, 1); }
                 }
             }
         }
     }
+}
 
-    // ---- per-strand reduction of the family quality buckets (main.hpp:3552-3591)
+// loop 2 over the short list of reads that loop 1 recorded (the common case on non-UMI data: a few multi-fragment families per position)
+UVC_HD void k4_loop2_listed(K4State & s, const BatchView & v, const Win & w) {
+    if (s.n_need2 > UVC_K4_LIST) { return; }
+    for (int32_t j = 0; j < s.n_need2; j++) { k4_loop2_read(s, v, v.rfam[w.lo + s.need2[j]]); }
+}
+
+// per-strand reduction of the family quality buckets (main.hpp:3552-3591) and the store of the position's family depth records
+UVC_HD void k4_end(K4State & s, const BatchView & v) {
+    const uvcgpu_params & par = v.par;
+    const int64_t gp = s.gp;
+    int32_t *vq = v.vq + gp * UVC_NSYM * UVCGPU_NUM_VQ_TAGS;
     for (int strand = 0; strand < 2; strand++) {
-        const int32_t *fd = (strand ? fam1 : fam0);
+        const int32_t *fd = s.facc + strand * (UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS);
         for (int type = 0; type < 2; type++) {
             const int s0 = (type == 0 ? UVC_BASE_A : UVC_LINK_M), s1 = (type == 0 ? UVC_BASE_NN : UVC_LINK_NN);
             int32_t totDP = 0;
-            for (int s = s0; s <= s1; s++) { if ((touched >> (strand * UVC_NSYM + s)) & 1u) { totDP += fd[s * UVCGPU_NUM_FAM_DEPTHS + cDP1]; } }
-            for (int s = s0; s <= s1; s++) {
-                if (!((touched >> (strand * UVC_NSYM + s)) & 1u)) { continue; }
+            for (int y = s0; y <= s1; y++) { if ((s.touched >> (strand * UVC_NSYM + y)) & 1u) { totDP += fd[y * UVCGPU_NUM_FAM_DEPTHS + UVC_cDP1]; } }
+            for (int y = s0; y <= s1; y++) {
+                if (!((s.touched >> (strand * UVC_NSYM + y)) & 1u)) { continue; }
                 int32_t q, ad, bq;
-                infer_max_qual(q, ad, bq, v, sscs_phred(par, ref, s) + tn_add, 4, bucket + (strand * UVC_NSYM + s) * UVC_NUM_BUCKETS, totDP);
-                vq[s * UVCGPU_NUM_VQ_TAGS + 8 + 3 * strand] = q; vq[s * UVCGPU_NUM_VQ_TAGS + 9 + 3 * strand] = ad; vq[s * UVCGPU_NUM_VQ_TAGS + 10 + 3 * strand] = bq;
-                int32_t *g = v.famdepth + ((strand * v.n_pos + gp) * UVC_NSYM + s) * UVCGPU_NUM_FAM_DEPTHS;
-                for (int k = 0; k < UVCGPU_NUM_FAM_DEPTHS; k++) { g[k] = fd[s * UVCGPU_NUM_FAM_DEPTHS + k]; }
+                infer_max_qual(q, ad, bq, v, sscs_phred(par, s.ref, y) + s.tn_add, 4, s.bucket + (strand * UVC_NSYM + y) * UVC_NUM_BUCKETS, totDP);
+                vq[y * UVCGPU_NUM_VQ_TAGS + 8 + 3 * strand] = q; vq[y * UVCGPU_NUM_VQ_TAGS + 9 + 3 * strand] = ad; vq[y * UVCGPU_NUM_VQ_TAGS + 10 + 3 * strand] = bq;
+                int32_t *g = v.famdepth + ((strand * v.n_pos + gp) * UVC_NSYM + y) * UVCGPU_NUM_FAM_DEPTHS;
+                for (int k = 0; k < UVCGPU_NUM_FAM_DEPTHS; k++) { g[k] = fd[y * UVCGPU_NUM_FAM_DEPTHS + k]; }
             }
         }
     }
-    #undef UVC_K4_TOUCH
+}
+
+UVC_HD void k4_position(const BatchView & v, int64_t gp, const Win & w) {
+    K4State s;
+    k4_begin(s, v, gp);
+    const int32_t p = s.p;
+    for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
+        if (ri < w.lo || ri >= w.hi) { continue; }
+        const ReadFam q = v.rfam[ri];
+        if (q.rend <= p || q.famprev_maxrend > p) { continue; }
+        k4_loop1_read(s, v, q, fam_entry_of_read(v, q, p), ri - w.lo);
+    }
+    k4_loop2_listed(s, v, w);
+    if (s.n_need2 > UVC_K4_LIST) {
+        for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
+            if (ri < w.lo || ri >= w.hi) { continue; }
+            const ReadFam q = v.rfam[ri];
+            if (q.rend <= p) { continue; }
+            k4_loop2_read(s, v, q);
+        }
+    }
+    k4_end(s, v);
 }
 
 // ------------------------------------------------------------------------------------------------ K4c: one thread per (family, strand)
