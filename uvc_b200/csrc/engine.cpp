@@ -266,10 +266,22 @@ __global__ void __launch_bounds__(128) uvc_k2_bias_pileup(const BatchView v, int
         const ReadRec *sR = S.R[buf];
         const ReadDerived *sD = S.D[buf];
         if (role == 0) {
-            #pragma unroll 8
-            for (int k = 0; k < nc; k++) {
-                const int64_t ri = cb + k;
-                S.bq[k][lane] = (uint16_t)uvc::k2_fetch_base(st, v, sR[k], active && ri >= w.lo && ri < w.hi);
+            // gather in groups of 8 reads: all 16 byte loads of a group are issued before the first one is consumed
+            for (int k0 = 0; k0 < nc; k0 += 8) {
+                int32_t qp[8];
+                uint32_t sb[8], qb[8];
+                #pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int k = (k0 + j < nc ? k0 + j : nc - 1);
+                    const int64_t ri = cb + k;
+                    const ReadRec & R = sR[k];
+                    qp[j] = uvc::k2_base_index(st, v, R, active && ri >= w.lo && ri < w.hi);
+                    const int32_t qc = (qp[j] > 0 ? qp[j] : 0);
+                    sb[j] = v.seq[R.seq_off + (uint32_t)(qc >> 1)];
+                    qb[j] = v.qual[R.qual_off + (uint32_t)qc];
+                }
+                #pragma unroll
+                for (int j = 0; j < 8; j++) { S.bq[k0 + j][lane] = (uint16_t)uvc::k2_pack_base(sb[j], qb[j], qp[j]); }
             }
         }
         if (active) {
@@ -327,12 +339,20 @@ __global__ void __launch_bounds__(128) uvc_k4_family_consensus(const BatchView v
             __syncwarp();
             const ReadFam *sq = S.q[buf];
             if (pass == 0) {
-                #pragma unroll 8
-                for (int k = 0; k < nc; k++) {
-                    const int64_t ri = cb + k;
-                    const ReadFam & q = sq[k];
-                    // covered by this lane's window, first read of its (family, strand) at p, single-fragment strand: fetch the fragment entry
-                    if (active && ri >= w.lo && ri < w.hi && q.rend > p && q.famprev_maxrend <= p && (q.flags & UVC_RF_DIRECT)) { S.e[k][lane] = v.fcol[q.col_base + p]; }
+                // gather in groups of 8 reads: the 8 entry loads of a group are issued before the first one is consumed. A lane fetches the
+                // entry of a read that lies in its own window, is the first read of its (family, strand) at p and belongs to a single-fragment strand.
+                for (int k0 = 0; k0 < nc; k0 += 8) {
+                    FragCol ent[8];
+                    #pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int k = (k0 + j < nc ? k0 + j : nc - 1);
+                        const int64_t ri = cb + k;
+                        const ReadFam & q = sq[k];
+                        const bool want = (active && ri >= w.lo && ri < w.hi && q.rend > p && q.famprev_maxrend <= p && (q.flags & UVC_RF_DIRECT));
+                        ent[j] = v.fcol[want ? q.col_base + p : 0];
+                    }
+                    #pragma unroll
+                    for (int j = 0; j < 8; j++) { S.e[k0 + j][lane] = ent[j]; }
                 }
                 if (active) {
                     for (int k = 0; k < nc; k++) {
@@ -479,7 +499,7 @@ static int backend_score(uvcgpu_ctx *ctx, BatchState & bs, const ScoreView & sv)
 #else // ------------------------------------------------------------------------------------------- emulation (tests only)
 
 static int backend_alloc(uvcgpu_ctx *, BatchState & bs, void **out, size_t bytes, bool) {
-    if (0 == bytes) { bytes = 16; }
+    bytes += 64;     // same slack as the CUDA build
     *out = calloc(1, bytes);
     if (NULL == *out) { return UVCGPU_ENOMEM; }
     bs.allocs.push_back(*out);

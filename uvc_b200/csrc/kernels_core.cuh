@@ -692,20 +692,23 @@ UVC_HD void k2_begin(K2State & s, const BatchView & v, int64_t gp, int role) {
 // base at p (or `mine` is false: the read lies outside this lane's own window). The two byte loads are unconditional (clamped index) so that
 // the CUDA kernel can issue them for a whole chunk of reads back to back instead of one dependent load pair per read.
 #define UVC_K2_NOBASE 0xffffu
-UVC_HD uint32_t k2_fetch_base(const K2State & s, const BatchView & v, const ReadRec & R, bool mine) {
+// index of the read's aligned base at s.p in its query sequence, -1 if there is none (or !mine)
+UVC_HD int32_t k2_base_index(const K2State & s, const BatchView & v, const ReadRec & R, bool mine) {
     const int32_t o = s.p - R.pos;
-    const bool cov = (mine && o >= 0 && s.p < R.rend && R.l_qseq > 0);
-    int32_t qpos = R.m_qoff + o;
-    bool is_m = cov;
-    if (!R.simple) {
-        qpos = 0;
-        if (cov) { const CxEntry e = v.cx[R.cx_off + o]; qpos = e.qpos; is_m = (e.flags & 1); }
-    }
-    qpos = tmax(0, tmin(qpos, R.l_qseq - 1));
-    const uint8_t *seq = v.seq + R.seq_off;
-    const uint8_t *qual = v.qual + R.qual_off;
-    const uint32_t pk = ((uint32_t)base3(seq, R.l_qseq > 0 ? qpos : 0) << 8) | (uint32_t)qual[R.l_qseq > 0 ? qpos : 0];
-    return (is_m ? pk : UVC_K2_NOBASE);
+    if (!(mine && o >= 0 && s.p < R.rend && R.l_qseq > 0)) { return -1; }
+    if (R.simple) { return tmin(R.m_qoff + o, R.l_qseq - 1); }
+    const CxEntry e = v.cx[(int64_t)R.cx_off + o];
+    return ((e.flags & 1) ? tmax(0, tmin((int32_t)e.qpos, R.l_qseq - 1)) : -1);
+}
+UVC_HD uint32_t k2_pack_base(uint32_t seq_byte, uint32_t qual_byte, int32_t qpos) {
+    const uint32_t b4 = (seq_byte >> ((~qpos & 1) << 2)) & 0xfu;
+    const uint32_t sym = (b4 == 1 ? 0u : (b4 == 2 ? 1u : (b4 == 4 ? 2u : (b4 == 8 ? 3u : 4u))));
+    return (qpos >= 0 ? ((sym << 8) | qual_byte) : UVC_K2_NOBASE);
+}
+UVC_HD uint32_t k2_fetch_base(const K2State & s, const BatchView & v, const ReadRec & R, bool mine) {
+    const int32_t qpos = k2_base_index(s, v, R, mine);
+    const int32_t qc = tmax(qpos, 0);
+    return k2_pack_base(v.seq[R.seq_off + (uint32_t)(qc >> 1)], v.qual[R.qual_off + (uint32_t)qc], qpos);
 }
 
 // one read of the position's window (R, D may live in shared memory: the CUDA kernel stages the records of 32 reads per warp at a time);
@@ -1402,6 +1405,8 @@ UVC_HD void k4a_family_strand(const BatchView & v, int64_t i) {
 // whole of loop 2 is "cDP1 += 1", which loop 1 does on the spot from the same column entry; the second pass over the window then only runs for
 // positions that saw a family it still has work for (need2).
 #define UVC_K4_LIST 24
+struct K4Hot { int32_t dp1, dp12, dp2, dp3, dpM, dpm, dp21; };   // cDP1, cDP12, cDP2, cDP3, cDPM, cDPm, cDP21 (cDPD: duplex-UMI families only, never hot)
+UVC_HD void k4hot_zero(K4Hot & h) { h.dp1 = h.dp12 = h.dp2 = h.dp3 = h.dpM = h.dpm = h.dp21 = 0; }
 struct K4State {
     const TileInfo *T;
     int64_t gp;
@@ -1415,7 +1420,10 @@ struct K4State {
     // reads (offsets from the start of the window) that loop 1 leaves work for; more than UVC_K4_LIST of them: the whole window is walked again
     int32_t n_need2;
     uint16_t need2[UVC_K4_LIST];
-    // thread-private family depth counters (this thread is the position's only writer): stored once at the end
+    // family depth counters of the two symbols nearly every family votes for - the reference base and LINK_M - per strand: registers
+    int hot[2];            // [type]
+    K4Hot h0[2], h1[2];    // strand 0 / strand 1, [type]
+    // thread-private family depth counters of every other symbol (this thread is the position's only writer): stored once at the end
     int32_t facc[2 * UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS];
     int32_t bucket[2 * UVC_NSYM * UVC_NUM_BUCKETS];
 };
@@ -1443,6 +1451,33 @@ UVC_HD void k4_begin(K4State & s, const BatchView & v, int64_t gp) {
     s.finfo = v.faminfo + gp * UVC_NSYM;
     s.touched = 0;
     s.n_need2 = 0;
+    s.hot[0] = s.ref; s.hot[1] = UVC_LINK_M;
+    for (int t = 0; t < 2; t++) { k4hot_zero(s.h0[t]); k4hot_zero(s.h1[t]); }
+}
+
+UVC_HD void k4hot_add(K4Hot & h, const K4Hot & d) {
+    h.dp1 += d.dp1; h.dp12 += d.dp12; h.dp2 += d.dp2; h.dp3 += d.dp3; h.dpM += d.dpM; h.dpm += d.dpm; h.dp21 += d.dp21;
+}
+// adds the increments d to the family depth counters of (strand, symbol a of type `type`)
+UVC_HD void k4_add(K4State & s, int strand, int type, int a, const K4Hot & d) {
+    if (a == s.hot[type]) {
+        if (strand) { k4hot_add(s.h1[type], d); } else { k4hot_add(s.h0[type], d); }
+    } else {
+        k4_touch(s, strand, a);
+        int32_t *fd = s.facc + (strand * UVC_NSYM + a) * UVCGPU_NUM_FAM_DEPTHS;
+        fd[UVC_cDP1] += d.dp1; fd[UVC_cDP12] += d.dp12; fd[UVC_cDP2] += d.dp2; fd[UVC_cDP3] += d.dp3; fd[UVC_cDPM] += d.dpM; fd[UVC_cDPm] += d.dpm; fd[UVC_cDP21] += d.dp21;
+    }
+}
+// current value of one family depth counter of (strand, symbol a)
+UVC_HD void k4_major_minor(const K4State & s, int strand, int type, int a, int32_t & major, int32_t & minor) {
+    if (a == s.hot[type]) {
+        const K4Hot & h = (strand ? s.h1[type] : s.h0[type]);
+        major = h.dpM; minor = h.dpm;
+    } else {
+        const int32_t *fd = s.facc + (strand * UVC_NSYM + a) * UVCGPU_NUM_FAM_DEPTHS;   // touched by loop 1 or zero
+        const bool live = ((s.touched >> (strand * UVC_NSYM + a)) & 1u);
+        major = (live ? fd[UVC_cDPM] : 0); minor = (live ? fd[UVC_cDPm] : 0);
+    }
 }
 
 // does loop 1 (with the loop-2 share described above) cover everything this (family, strand) entry asks of loop 2 for symbol type `type`?
@@ -1465,13 +1500,15 @@ UVC_HD void k4_loop1_read(K4State & s, const BatchView & v, const ReadFam & q, c
     for (int type = 1; type >= 0; type--) {
         const int a = m.a1[type]; const int32_t cc = m.cc1[type], tc = m.tc1[type];
         if (0 == tc) { continue; }
-        k4_touch(s, strand, a);
-        fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDP12] += 1;
-        if (1 == tc) { fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDP21] += 1; }
+        // the read (hence strand) is the same for all lanes of the warp: only `a == hot` can diverge
+        K4Hot d;
+        k4hot_zero(d);
+        d.dp12 = 1;
+        if (1 == tc) { d.dp21 = 1; }
         const bool is_indel = (is_ins_symbol(a) || is_del_symbol(a));
         int32_t fam_ev = -2;   // family-majority indel event, computed lazily
         if (fam_is_good(par, F, cc, tc)) {
-            fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDP2] += 1;
+            d.dp2 = 1;
             if (is_indel) {
                 fam_ev = fam_indel_majority(v, F, strand, p, gp, a, NULL);
                 if (fam_ev >= 0) { rec_put6(v, UVC_REC_CDP2_INDEL, strand, a, p, fam_ev, 1); }
@@ -1514,7 +1551,7 @@ UVC_HD void k4_loop1_read(K4State & s, const BatchView & v, const ReadFam & q, c
             }
             fi.c2BQ2 += 1;
         }
-        if (par.fam_thres_dup2add <= tc && (cc * 100 >= tc * par.fam_thres_dup2perc)) { fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDP3] += 1; }
+        if (par.fam_thres_dup2add <= tc && (cc * 100 >= tc * par.fam_thres_dup2perc)) { d.dp3 = 1; }
         if (is_indel) {
             if (fam_ev == -2) { fam_ev = fam_indel_majority(v, F, strand, p, gp, a, NULL); }
             if (fam_ev >= 0) { rec_put6(v, UVC_REC_FAM_INDEL, strand, a, p, fam_ev, 1); }
@@ -1522,12 +1559,13 @@ UVC_HD void k4_loop1_read(K4State & s, const BatchView & v, const ReadFam & q, c
         const bool is_subst = (a <= UVC_BASE_NN);
         const int32_t flat = (is_subst ? par.fam_thres_emperr_all_flat_snv : par.fam_thres_emperr_all_flat_indel);
         const int32_t perc = (is_subst ? par.fam_thres_emperr_con_perc_snv : par.fam_thres_emperr_con_perc_indel);
-        if (tc < flat) { continue; }
-        if (cc * 100 < tc * perc) { continue; }
-        // every other symbol of the type adds its own count to cDPm and, QUIRK, the whole total to cDPM (main.hpp:3343-3352)
-        const int32_t n_other = (type == 0 ? (UVC_BASE_NN - UVC_BASE_A) : (UVC_LINK_NN - UVC_LINK_M));
-        fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDPm] += tc - cc;
-        fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDPM] += tc * n_other;
+        if (tc >= flat && cc * 100 >= tc * perc) {
+            // every other symbol of the type adds its own count to cDPm and, QUIRK, the whole total to cDPM (main.hpp:3343-3352)
+            const int32_t n_other = (type == 0 ? (UVC_BASE_NN - UVC_BASE_A) : (UVC_LINK_NN - UVC_LINK_M));
+            d.dpm = tc - cc;
+            d.dpM = tc * n_other;
+        }
+        k4_add(s, strand, type, a, d);
     }
     // the share of loop 2 that needs nothing from the other families (see the header comment)
     bool need2 = (0 != (q.flags & UVC_RF_DUPLEX_UMI));
@@ -1535,9 +1573,10 @@ UVC_HD void k4_loop1_read(K4State & s, const BatchView & v, const ReadFam & q, c
     for (int type = 1; type >= 0; type--) {
         if (0 == m.mmm_tot[type]) { continue; }
         if (k4_loop2_done_in_loop1(par, q, m, type)) {
-            const int a = m.a2[type];
-            k4_touch(s, strand, a);
-            fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDP1] += 1;
+            K4Hot d;
+            k4hot_zero(d);
+            d.dp1 = 1;
+            k4_add(s, strand, type, m.a2[type], d);
         } else {
             need2 = true;
         }
@@ -1568,9 +1607,14 @@ UVC_HD void k4_loop2_read(K4State & s, const BatchView & v, const ReadFam & q) {
             if (k4_loop2_done_in_loop1(par, q, m, type)) { continue; }
             const int32_t con_nfrags = m.con_a2[type];
             const int32_t tot_nfrags = m.tc1[type];
-            k4_touch(s, strand, a);
-            fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDP1] += 1;
+            {
+                K4Hot d;
+                k4hot_zero(d);
+                d.dp1 = 1;
+                k4_add(s, strand, type, a, d);
+            }
             if (will_inc_sscs && (tot_nfrags >= par.fam_thres_dup1add) && (con_nfrags * 100 >= tot_nfrags * par.fam_thres_dup1perc)) {
+                k4_touch(s, strand, a);
                 fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDPD] += 1;
                 if (is_ins_symbol(a) || is_del_symbol(a)) {
                     const int32_t e = fam_indel_majority(v, F, strand, p, gp, a, NULL);
@@ -1579,8 +1623,8 @@ UVC_HD void k4_loop2_read(K4State & s, const BatchView & v, const ReadFam & q) {
             }
             if (tot_nfrags >= par.fam_thres_dup1add) {     // the family's consensus quality only matters if it enters a bucket (main.hpp:3445-3455)
                 const int32_t avgBQ = ((0 == tot_nfrags) ? 1 : (con_sumBQs / tot_nfrags));
-                const int32_t majorcount = fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDPM];
-                const int32_t minorcount = fd[a * UVCGPU_NUM_FAM_DEPTHS + UVC_cDPm];
+                int32_t majorcount, minorcount;
+                k4_major_minor(s, strand, type, a, majorcount, minorcount);
                 const double prior_weight = 1.0 / (minorcount + 1.0);
                 const double p2p = v.phred2prob_tab[tmin(tmax(avgBQ, 0), 127)];
                 const double realphred = -10 * log((minorcount + prior_weight) / (majorcount + minorcount + prior_weight / p2p)) / v.ln10;
@@ -1594,7 +1638,7 @@ UVC_HD void k4_loop2_read(K4State & s, const BatchView & v, const ReadFam & q) {
                 const int32_t max_qual = sscs_phred(par, s.ref, a) + s.tn_add;
                 const int32_t confam_qual2 = tmin(confam_qual, max_qual);
                 const int32_t pb = (max_qual - confam_qual2 + 2) / 4;
-                if (pb >= 0 && pb < UVC_NUM_BUCKETS) { s.bucket[(strand * UVC_NSYM + a) * UVC_NUM_BUCKETS + pb] += 1; }
+                if (pb >= 0 && pb < UVC_NUM_BUCKETS) { k4_touch(s, strand, a); s.bucket[(strand * UVC_NSYM + a) * UVC_NUM_BUCKETS + pb] += 1; }
             }
         }
     }
@@ -1641,6 +1685,15 @@ UVC_HD void k4_end(K4State & s, const BatchView & v) {
     const uvcgpu_params & par = v.par;
     const int64_t gp = s.gp;
     int32_t *vq = v.vq + gp * UVC_NSYM * UVCGPU_NUM_VQ_TAGS;
+    for (int strand = 0; strand < 2; strand++) {
+        for (int type = 0; type < 2; type++) {
+            const K4Hot & h = (strand ? s.h1[type] : s.h0[type]);
+            if (0 == (h.dp1 | h.dp12 | h.dp2 | h.dp3 | h.dpM | h.dpm | h.dp21)) { continue; }
+            k4_touch(s, strand, s.hot[type]);
+            int32_t *fd = s.facc + (strand * UVC_NSYM + s.hot[type]) * UVCGPU_NUM_FAM_DEPTHS;
+            fd[UVC_cDP1] += h.dp1; fd[UVC_cDP12] += h.dp12; fd[UVC_cDP2] += h.dp2; fd[UVC_cDP3] += h.dp3; fd[UVC_cDPM] += h.dpM; fd[UVC_cDPm] += h.dpm; fd[UVC_cDP21] += h.dp21;
+        }
+    }
     for (int strand = 0; strand < 2; strand++) {
         const int32_t *fd = s.facc + strand * (UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS);
         for (int type = 0; type < 2; type++) {
