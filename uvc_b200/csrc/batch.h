@@ -153,6 +153,15 @@ struct ReadFam {
     uint32_t flags;                    // UVC_RF_*
     int32_t pad;
 };
+// What the position kernel of the fragment stage (K3b) needs from a read, 32 B (instead of chasing ReadRec -> FragRec): written by K3a, which
+// computes the whole-fragment statistics.
+struct ReadFrag {
+    int32_t rend, fragprev_maxrend;
+    int64_t col_base;                  // the fragment's entry at position p is fcol[col_base + p]
+    int32_t n_cov, n_near_mut;         // bTA / bTB numerators of the fragment
+    int32_t mq_term;                   // normMQ^2 / UVC_SQR_QUAL_DIV
+    int32_t frag_strand;               // fragment index * 2 + strand
+};
 #define UVC_RF_STRAND 1u
 #define UVC_RF_DIRECT 2u               // col_base points into fcol (single-fragment family-strand)
 #define UVC_RF_DUPLEX_UMI 4u           // family has a duplex UMI (duplexflag & 0x2)
@@ -187,6 +196,7 @@ struct BatchView {
     const int32_t *frag_reads;
     FamRec *fams;
     const ReadFam *rfam;           // [n_reads]
+    ReadFrag *rfrag;               // [n_reads], kernel K3a
     // per-fragment and per-(family, strand) columns
     int64_t n_fcol, n_mcol;        // padded entry counts (multiples of UVC_COL_CHUNK)
     FragCol *fcol;

@@ -200,7 +200,6 @@ __device__ __forceinline__ void uvc_warp_window(const BatchView & v, int64_t gp,
         if (i < n) { call; } \
     }
 UVC_DEFINE_KERNEL(uvc_k0_read_consts, uvc::k0_read(v, i))
-UVC_DEFINE_POS_KERNEL(uvc_k1_prep_thres, uvc::k1_position(v, i, w))
 // ---- warp-private staging of per-read records in shared memory, double-buffered with cp.async (LDGSTS)
 // A warp walks its union window in chunks of UVC_STAGE_READS reads. Chunk bases are multiples of 4 reads, so that every record array slice
 // starts on a 16-byte boundary (record sizes are multiples of 4 bytes) and is copied with 16-byte asynchronous copies; the copy of chunk
@@ -220,6 +219,27 @@ template <class T> __device__ __forceinline__ void uvc_warp_stage_async(T *dst, 
     const char *g = (const char*)(src + first);
     char *d = (char*)dst;
     for (int k = lane; k < n16; k += 32) { uvc_cp_async16(d + 16 * k, g + 16 * k); }
+}
+
+// role-0 style gather of the (base, quality) byte pairs of a staged chunk, in groups of 8 reads: all 16 byte loads of a group are issued
+// before the first one is consumed (memory-level parallelism instead of one dependent load pair per read)
+__device__ __forceinline__ void uvc_gather_bases(const BatchView & v, const ReadRec *sR, uint16_t (*bq)[32], int nc, int64_t cb, const uvc::Win & w, int32_t p, bool active, int lane) {
+    for (int k0 = 0; k0 < nc; k0 += 8) {
+        int32_t qp[8];
+        uint32_t sb[8], qb[8];
+        #pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k = (k0 + j < nc ? k0 + j : nc - 1);
+            const int64_t ri = cb + k;
+            const ReadRec & R = sR[k];
+            qp[j] = uvc::base_index(v, R, p, active && ri >= w.lo && ri < w.hi);
+            const int32_t qc = (qp[j] > 0 ? qp[j] : 0);
+            sb[j] = v.seq[R.seq_off + (uint32_t)(qc >> 1)];
+            qb[j] = v.qual[R.qual_off + (uint32_t)qc];
+        }
+        #pragma unroll
+        for (int j = 0; j < 8; j++) { bq[k0 + j][lane] = (uint16_t)uvc::pack_base(sb[j], qb[j], qp[j]); }
+    }
 }
 
 // K2: both roles of a position sit in different warps of the same block: block = 64 positions x 2 roles.
@@ -265,25 +285,7 @@ __global__ void __launch_bounds__(128) uvc_k2_bias_pileup(const BatchView v, int
         __syncwarp();
         const ReadRec *sR = S.R[buf];
         const ReadDerived *sD = S.D[buf];
-        if (role == 0) {
-            // gather in groups of 8 reads: all 16 byte loads of a group are issued before the first one is consumed
-            for (int k0 = 0; k0 < nc; k0 += 8) {
-                int32_t qp[8];
-                uint32_t sb[8], qb[8];
-                #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int k = (k0 + j < nc ? k0 + j : nc - 1);
-                    const int64_t ri = cb + k;
-                    const ReadRec & R = sR[k];
-                    qp[j] = uvc::k2_base_index(st, v, R, active && ri >= w.lo && ri < w.hi);
-                    const int32_t qc = (qp[j] > 0 ? qp[j] : 0);
-                    sb[j] = v.seq[R.seq_off + (uint32_t)(qc >> 1)];
-                    qb[j] = v.qual[R.qual_off + (uint32_t)qc];
-                }
-                #pragma unroll
-                for (int j = 0; j < 8; j++) { S.bq[k0 + j][lane] = (uint16_t)uvc::k2_pack_base(sb[j], qb[j], qp[j]); }
-            }
-        }
+        if (role == 0) { uvc_gather_bases(v, sR, S.bq, nc, cb, w, st.p, active, lane); }
         if (active) {
             for (int k = 0; k < nc; k++) {
                 const int64_t ri = cb + k;
@@ -295,12 +297,110 @@ __global__ void __launch_bounds__(128) uvc_k2_bias_pileup(const BatchView v, int
     }
     if (active) { uvc::k2_end(st, v); }
 }
+// K1: one thread per position; same staging as K2 (the records of 32 reads per warp, one chunk ahead) and the same grouped byte gather
+__global__ void __launch_bounds__(128) uvc_k1_prep_thres(const BatchView v, int64_t n) {
+    extern __shared__ __align__(16) unsigned char uvc_smem[];
+    const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    K2Stage & S = ((K2Stage*)uvc_smem)[warp];
+    const bool active = (gp < n);
+    uvc::Win w;
+    uvc_warp_window(v, gp, active, w);
+    uvc::K1State st;
+    st.p = 0;
+    if (active) { uvc::k1_begin(st, v, gp); }
+    const int64_t c0 = w.ulo & ~(int64_t)3;
+    if (c0 < w.uhi) {
+        const int nc0 = (int)(w.uhi - c0 < UVC_STAGE_READS ? w.uhi - c0 : UVC_STAGE_READS);
+        uvc_warp_stage_async(S.R[0], v.reads, c0, nc0, lane);
+        uvc_warp_stage_async(S.D[0], v.rd, c0, nc0, lane);
+    }
+    uvc_cp_async_commit();
+    int buf = 0;
+    for (int64_t cb = c0; cb < w.uhi; cb += UVC_STAGE_READS, buf ^= 1) {
+        const int nc = (int)(w.uhi - cb < UVC_STAGE_READS ? w.uhi - cb : UVC_STAGE_READS);
+        const int64_t nb = cb + UVC_STAGE_READS;
+        if (nb < w.uhi) {
+            const int nn = (int)(w.uhi - nb < UVC_STAGE_READS ? w.uhi - nb : UVC_STAGE_READS);
+            uvc_warp_stage_async(S.R[buf ^ 1], v.reads, nb, nn, lane);
+            uvc_warp_stage_async(S.D[buf ^ 1], v.rd, nb, nn, lane);
+        }
+        uvc_cp_async_commit();
+        uvc_cp_async_wait<1>();
+        __syncwarp();
+        const ReadRec *sR = S.R[buf];
+        const ReadDerived *sD = S.D[buf];
+        uvc_gather_bases(v, sR, S.bq, nc, cb, w, st.p, active, lane);
+        if (active) {
+            for (int k = 0; k < nc; k++) { uvc::k1_read(st, v, sR[k], sD[k], (uint32_t)S.bq[k][lane]); }   // lanes outside their own window hold NOBASE
+        }
+        __syncwarp();
+    }
+    if (active) { uvc::k1_end(st, v); }
+}
 UVC_DEFINE_KERNEL(uvc_k2e_indel_events, uvc::k2e_event(v, i))
 UVC_DEFINE_KERNEL(uvc_kf_fragment_columns, uvc::kf_fragment_column(v, i))
 UVC_DEFINE_KERNEL(uvc_k3a_fragment_stats, uvc::k3a_fragment(v, i))
-UVC_DEFINE_POS_KERNEL(uvc_k3b_fragment_consensus, uvc::k3b_position(v, i, w))
 UVC_DEFINE_KERNEL(uvc_km_family_columns, uvc::km_family_column(v, i))
 UVC_DEFINE_KERNEL(uvc_k4a_family_ends, uvc::k4a_family_strand(v, i))
+// K3b: the compact per-read fragment records (ReadFrag, 32 B, written by K3a) of 32 reads are staged per warp (asynchronously, one chunk
+// ahead); every lane then gathers its own column entry of each read of the chunk in groups of 8 independent loads. The quality histograms of
+// the two hot symbols live in shared memory ([bucket][thread]: conflict-free), their depth counters in registers.
+struct __align__(16) K3bStage {
+    ReadFrag q[2][UVC_STAGE_READS];
+    FragCol e[UVC_STAGE_READS][32];
+};
+__global__ void __launch_bounds__(128) uvc_k3b_fragment_consensus(const BatchView v, int64_t n) {
+    extern __shared__ __align__(16) unsigned char uvc_smem[];
+    const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    K3bStage & S = ((K3bStage*)uvc_smem)[warp];
+    int32_t *hot_buckets = (int32_t*)(uvc_smem + 4 * sizeof(K3bStage)) + threadIdx.x;
+    const bool active = (gp < n);
+    uvc::Win w;
+    uvc_warp_window(v, gp, active, w);
+    uvc::K3bState st;
+    st.p = 0;
+    if (active) { uvc::k3b_begin(st, v, gp, hot_buckets, 128); }
+    const int32_t p = st.p;
+    const int64_t c0 = w.ulo & ~(int64_t)3;
+    if (c0 < w.uhi) { uvc_warp_stage_async(S.q[0], v.rfrag, c0, (int)(w.uhi - c0 < UVC_STAGE_READS ? w.uhi - c0 : UVC_STAGE_READS), lane); }
+    uvc_cp_async_commit();
+    int buf = 0;
+    for (int64_t cb = c0; cb < w.uhi; cb += UVC_STAGE_READS, buf ^= 1) {
+        const int nc = (int)(w.uhi - cb < UVC_STAGE_READS ? w.uhi - cb : UVC_STAGE_READS);
+        const int64_t nb = cb + UVC_STAGE_READS;
+        if (nb < w.uhi) { uvc_warp_stage_async(S.q[buf ^ 1], v.rfrag, nb, (int)(w.uhi - nb < UVC_STAGE_READS ? w.uhi - nb : UVC_STAGE_READS), lane); }
+        uvc_cp_async_commit();
+        uvc_cp_async_wait<1>();
+        __syncwarp();
+        const ReadFrag *sq = S.q[buf];
+        for (int k0 = 0; k0 < nc; k0 += 8) {
+            FragCol ent[8];
+            #pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int k = (k0 + j < nc ? k0 + j : nc - 1);
+                const int64_t ri = cb + k;
+                const ReadFrag & q = sq[k];
+                const bool want = (active && ri >= w.lo && ri < w.hi && q.rend > p && q.fragprev_maxrend <= p);
+                ent[j] = v.fcol[want ? q.col_base + p : 0];
+            }
+            #pragma unroll
+            for (int j = 0; j < 8; j++) { S.e[k0 + j][lane] = ent[j]; }
+        }
+        if (active) {
+            for (int k = 0; k < nc; k++) {
+                const int64_t ri = cb + k;
+                if (ri < w.lo || ri >= w.hi) { continue; }
+                const ReadFrag & q = sq[k];
+                if (q.rend <= p || q.fragprev_maxrend > p) { continue; }
+                uvc::k3b_read(st, v, q, S.e[k][lane]);
+            }
+        }
+        __syncwarp();
+    }
+    if (active) { uvc::k3b_end(st, v); }
+}
 // K4: the compact per-read family records (ReadFam, 32 B) of 32 reads are staged per warp (asynchronously, one chunk ahead); every lane then
 // gathers its own column entry of each read of the chunk with independent loads (consecutive lanes = consecutive addresses of one column) before
 // the per-read work runs from shared memory. Entries of single-fragment family-strands are the 8-byte fragment entries; the 32-byte entries of
@@ -429,7 +529,13 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
     #define UVC_STAGE(kernel, n) { launch(kernel, ctx->stream, v, (n), launches); UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream)); }
     UVC_STAGE(uvc_k0_read_consts, v.n_reads)
-    UVC_STAGE(uvc_k1_prep_thres, v.n_pos)
+    if (v.n_pos > 0) {
+        const size_t smem = 4 * sizeof(K2Stage);
+        UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k1_prep_thres, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        uvc_k1_prep_thres<<<(unsigned)((v.n_pos + 127) / 128), 128, smem, ctx->stream>>>(v, v.n_pos);
+        launches++;
+    }
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
     if (v.n_pos > 0) {
         static_assert(sizeof(K2Stage) % 16 == 0, "per-warp staging slots keep 16-byte alignment");
         const size_t smem = 4 * sizeof(K2Stage);
@@ -441,7 +547,14 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     UVC_STAGE(uvc_k2e_indel_events, v.n_ev)
     UVC_STAGE(uvc_kf_fragment_columns, v.n_fcol)
     UVC_STAGE(uvc_k3a_fragment_stats, v.n_frags)
-    UVC_STAGE(uvc_k3b_fragment_consensus, v.n_pos)
+    if (v.n_pos > 0) {
+        static_assert(sizeof(K3bStage) % 16 == 0, "per-warp staging slots keep 16-byte alignment");
+        const size_t smem = 4 * sizeof(K3bStage) + 2 * UVC_NUM_BUCKETS * 128 * sizeof(int32_t);
+        UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k3b_fragment_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        uvc_k3b_fragment_consensus<<<(unsigned)((v.n_pos + 127) / 128), 128, smem, ctx->stream>>>(v, v.n_pos);
+        launches++;
+    }
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
     UVC_STAGE(uvc_km_family_columns, v.n_mcol)
     UVC_STAGE(uvc_k4a_family_ends, 2 * v.n_fams)
     if (v.n_pos > 0) {
@@ -795,6 +908,7 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
     { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_fcol * sizeof(FragCol), false)); v.fcol = (FragCol*)d_; }
     { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_mcol * sizeof(FamCol), false)); v.mcol = (FamCol*)d_; }
     UVC_ZERO(rd, ReadDerived, v.n_reads)
+    UVC_ZERO(rfrag, ReadFrag, v.n_reads)
     UVC_ZERO(cx, CxEntry, v.n_cx)
     UVC_ZERO(ev, IndelEvent, v.n_ev)
     UVC_ZERO(prep, uvcgpu_prep_set, v.n_pos)

@@ -427,43 +427,77 @@ UVC_HD void k0_read(const BatchView & v, int64_t ri) {
     }
 }
 
+#define UVC_K2_NOBASE 0xffffu
+// index of the read's aligned base at p in its query sequence, -1 if there is none (or !mine)
+UVC_HD int32_t base_index(const BatchView & v, const ReadRec & R, int32_t p, bool mine) {
+    const int32_t o = p - R.pos;
+    if (!(mine && o >= 0 && p < R.rend && R.l_qseq > 0)) { return -1; }
+    if (R.simple) { return tmin(R.m_qoff + o, R.l_qseq - 1); }
+    const CxEntry e = v.cx[(int64_t)R.cx_off + o];
+    return ((e.flags & 1) ? tmax(0, tmin((int32_t)e.qpos, R.l_qseq - 1)) : -1);
+}
+UVC_HD uint32_t pack_base(uint32_t seq_byte, uint32_t qual_byte, int32_t qpos) {
+    const uint32_t b4 = (seq_byte >> ((~qpos & 1) << 2)) & 0xfu;
+    const uint32_t sym = (b4 == 1 ? 0u : (b4 == 2 ? 1u : (b4 == 4 ? 2u : (b4 == 8 ? 3u : 4u))));
+    return (qpos >= 0 ? ((sym << 8) | qual_byte) : UVC_K2_NOBASE);
+}
 // ------------------------------------------------------------------------------------------------ K1: one thread per position
 // Dense part of walk #1 (main.hpp:1006-1068) gathered per position, then the threshold pass (main.hpp:1206-1299).
-UVC_HD void k1_position(const BatchView & v, int64_t gp, const Win & w) {
+struct K1State {
+    int64_t gp;
+    int32_t p, baq_p;
+    uvcgpu_prep_set a;
+};
+UVC_HD void k1_begin(K1State & s, const BatchView & v, int64_t gp) {
     const TileInfo & T = v.tiles[v.pos_tile[gp]];
-    const int32_t p = (int32_t)(gp - T.pos_off) + T.ext_beg;
-    const uvcgpu_params & par = v.par;
-    const int32_t *baq = v.baq + (T.pos_off - T.ext_beg);
-    uvcgpu_prep_set a = v.prep[gp];     // starts from the rare-event contributions of K0
-    const int32_t baq_p = baq[p];
+    s.gp = gp;
+    s.p = (int32_t)(gp - T.pos_off) + T.ext_beg;
+    s.a = v.prep[gp];     // starts from the rare-event contributions of K0
+    s.baq_p = v.baq[gp];
+}
+// one read of the window; `packed` = (symbol << 8) | quality of its aligned base at p, UVC_K2_NOBASE if it shows none
+UVC_HD void k1_read(K1State & s, const BatchView & v, const ReadRec & R, const ReadDerived & D, uint32_t packed) {
+    if (packed == UVC_K2_NOBASE) { return; }
+    uvcgpu_prep_set & a = s.a;
+    const int32_t p = s.p;
+    const int32_t span = R.rend - R.pos;
+    a.a_pcr_dp += ((R.dflag & 0x4) ? 1 : 0);
+    a.a_umi_dp += ((R.dflag & 0x1) ? 1 : 0);
+    a.a_dp += 1;
+    a.a_qlen += span;
+    a.a_XM1500 += D.xm1500; a.a_GO1500 += D.go1500; a.a_GAPLEN += D.avg_gaplen;
+    if (R.isize != 0) {
+        const int32_t fl = tmin(R.pos, R.mpos);
+        if (R.flag & 0x10) { a.a_LI += tmin(p - fl + 1, UVC_MAX_INSERT_SIZE); a.a_LIDP += 1; }
+        else { a.a_RI += tmin(fl + iabs(R.isize) - p, UVC_MAX_INSERT_SIZE); a.a_RIDP += 1; }
+    }
+    if ((int32_t)(packed & 0xffu) >= v.par.bias_thres_highBQ) {
+        a.a_l_dist_sum += p - R.pos + 1;
+        a.a_r_dist_sum += R.rend - p;
+        a.a_inslen_sum += D.inslen_sum; a.a_dellen_sum += D.dellen_sum;
+        a.a_l_BAQ_sum += s.baq_p - D.baq_pos + 1;
+        a.a_r_BAQ_sum += D.baq_rend1 - s.baq_p + 1;
+        a.a_insBAQ_sum += D.insbaq_sum; a.a_delBAQ_sum += D.delbaq_sum;
+        a.a_highBQ_dp += 1;
+    }
+}
+UVC_HD void k1_end(K1State & s, const BatchView & v);
+UVC_HD void k1_position(const BatchView & v, int64_t gp, const Win & w) {
+    K1State s;
+    k1_begin(s, v, gp);
     for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
         if (ri < w.lo || ri >= w.hi) { continue; }
         const ReadRec & R = v.reads[ri];
-        if (R.rend <= p) { continue; }
-        const Locus L = locate(v, R, p);
-        if (!L.is_m) { continue; }
-        const ReadDerived & D = v.rd[ri];
-        const int32_t span = R.rend - R.pos;
-        a.a_pcr_dp += ((R.dflag & 0x4) ? 1 : 0);
-        a.a_umi_dp += ((R.dflag & 0x1) ? 1 : 0);
-        a.a_dp += 1;
-        a.a_qlen += span;
-        a.a_XM1500 += D.xm1500; a.a_GO1500 += D.go1500; a.a_GAPLEN += D.avg_gaplen;
-        if (R.isize != 0) {
-            const int32_t fl = tmin(R.pos, R.mpos);
-            if (R.flag & 0x10) { a.a_LI += tmin(p - fl + 1, UVC_MAX_INSERT_SIZE); a.a_LIDP += 1; }
-            else { a.a_RI += tmin(fl + iabs(R.isize) - p, UVC_MAX_INSERT_SIZE); a.a_RIDP += 1; }
-        }
-        if ((int32_t)v.qual[R.qual_off + L.qpos] >= par.bias_thres_highBQ) {
-            a.a_l_dist_sum += p - R.pos + 1;
-            a.a_r_dist_sum += R.rend - p;
-            a.a_inslen_sum += D.inslen_sum; a.a_dellen_sum += D.dellen_sum;
-            a.a_l_BAQ_sum += baq_p - D.baq_pos + 1;
-            a.a_r_BAQ_sum += D.baq_rend1 - baq_p + 1;
-            a.a_insBAQ_sum += D.insbaq_sum; a.a_delBAQ_sum += D.delbaq_sum;
-            a.a_highBQ_dp += 1;
-        }
+        const int32_t qpos = base_index(v, R, s.p, true);
+        k1_read(s, v, R, v.rd[ri], pack_base(0, v.qual[R.qual_off + (uint32_t)tmax(qpos, 0)], qpos));
     }
+    k1_end(s, v);
+}
+// the threshold pass (main.hpp:1206-1299) and the store of the position's prep set
+UVC_HD void k1_end(K1State & s, const BatchView & v) {
+    const uvcgpu_params & par = v.par;
+    const int64_t gp = s.gp;
+    const uvcgpu_prep_set & a = s.a;
     v.prep[gp] = a;
 
     uvcgpu_thres_set t;
@@ -659,7 +693,7 @@ UVC_HD int32_t dist_to_interfering_indel(const BatchView & v, const TileInfo & T
 
 // quality weight of "no indel" at the junction before an aligned base (main.hpp:1918-1924)
 UVC_HD int32_t nogap_weight(const BatchView & v, int64_t gp, const ReadDerived & D) {
-    const int32_t noindel = tmin(v.rtr[gp - 1].indelphred, v.rtr[gp].indelphred);
+    const int32_t noindel = tmin(v.rtr[gp > 0 ? gp - 1 : 0].indelphred, v.rtr[gp].indelphred);
     return nnminus(tmin(80, noindel), D.micro_nogap_penal) + 1;
 }
 
@@ -682,7 +716,7 @@ UVC_HD void k2_begin(K2State & s, const BatchView & v, int64_t gp, int role) {
     s.T = &T; s.gp = gp; s.role = role;
     s.p = (int32_t)(gp - T.pos_off) + T.ext_beg;
     s.baq_p = v.baq[gp]; s.baq2_p = v.baq2[gp];
-    s.noindel = (role == 1 ? tmin(v.rtr[gp - 1].indelphred, v.rtr[gp].indelphred) : 0);
+    s.noindel = (role == 1 ? tmin(v.rtr[gp > 0 ? gp - 1 : 0].indelphred, v.rtr[gp].indelphred) : 0);
     s.th = v.thres[gp];
     s.major = (role == 0 ? (int)v.refsym[gp] : UVC_LINK_M);
     segacc_zero(s.acc);
@@ -691,24 +725,10 @@ UVC_HD void k2_begin(K2State & s, const BatchView & v, int64_t gp, int role) {
 // What role 0 needs from a read's own bytes at p: (base symbol << 8) | raw-plus-fix-up quality, or UVC_K2_NOBASE when the read shows no aligned
 // base at p (or `mine` is false: the read lies outside this lane's own window). The two byte loads are unconditional (clamped index) so that
 // the CUDA kernel can issue them for a whole chunk of reads back to back instead of one dependent load pair per read.
-#define UVC_K2_NOBASE 0xffffu
-// index of the read's aligned base at s.p in its query sequence, -1 if there is none (or !mine)
-UVC_HD int32_t k2_base_index(const K2State & s, const BatchView & v, const ReadRec & R, bool mine) {
-    const int32_t o = s.p - R.pos;
-    if (!(mine && o >= 0 && s.p < R.rend && R.l_qseq > 0)) { return -1; }
-    if (R.simple) { return tmin(R.m_qoff + o, R.l_qseq - 1); }
-    const CxEntry e = v.cx[(int64_t)R.cx_off + o];
-    return ((e.flags & 1) ? tmax(0, tmin((int32_t)e.qpos, R.l_qseq - 1)) : -1);
-}
-UVC_HD uint32_t k2_pack_base(uint32_t seq_byte, uint32_t qual_byte, int32_t qpos) {
-    const uint32_t b4 = (seq_byte >> ((~qpos & 1) << 2)) & 0xfu;
-    const uint32_t sym = (b4 == 1 ? 0u : (b4 == 2 ? 1u : (b4 == 4 ? 2u : (b4 == 8 ? 3u : 4u))));
-    return (qpos >= 0 ? ((sym << 8) | qual_byte) : UVC_K2_NOBASE);
-}
 UVC_HD uint32_t k2_fetch_base(const K2State & s, const BatchView & v, const ReadRec & R, bool mine) {
-    const int32_t qpos = k2_base_index(s, v, R, mine);
+    const int32_t qpos = base_index(v, R, s.p, mine);
     const int32_t qc = tmax(qpos, 0);
-    return k2_pack_base(v.seq[R.seq_off + (uint32_t)(qc >> 1)], v.qual[R.qual_off + (uint32_t)qc], qpos);
+    return pack_base(v.seq[R.seq_off + (uint32_t)(qc >> 1)], v.qual[R.qual_off + (uint32_t)qc], qpos);
 }
 
 // one read of the position's window (R, D may live in shared memory: the CUDA kernel stages the records of 32 reads per warp at a time);
@@ -1163,6 +1183,18 @@ UVC_HD void k3a_fragment(const BatchView & v, int64_t fi) {
         }
     }
     G.n_cov = n_cov; G.n_near_mut = n_near;
+    // the compact per-read records that K3b stages
+    for (int32_t k = 0; k < G.n_reads; k++) {
+        const int32_t ri = v.frag_reads[G.read_off + k];
+        const ReadRec & R = v.reads[ri];
+        ReadFrag q;
+        q.rend = R.rend; q.fragprev_maxrend = R.fragprev_maxrend;
+        q.col_base = G.col_off - lo;
+        q.n_cov = n_cov; q.n_near_mut = n_near;
+        q.mq_term = (G.normMQ * G.normMQ) / UVC_SQR_QUAL_DIV;
+        q.frag_strand = (int32_t)(fi * 2 + (G.strand ? 1 : 0));
+        v.rfrag[ri] = q;
+    }
 }
 
 // infer_max_qual_assuming_independence (main_conversion.hpp:943-974)
@@ -1184,67 +1216,128 @@ UVC_HD void infer_max_qual(int32_t & maxvqual, int32_t & argmaxAD, int32_t & arg
 // ------------------------------------------------------------------------------------------------ K3b: one thread per position
 // Fragment-level consensus gathered per position (main.hpp:2620-2733, 2757-2828): bDP, bTA, bTB, bMQ, the quality-bucket histogram and its
 // reduction to bIAQb/bIADb/bIDQb, and the indel identities of fragments whose link consensus is an insertion or deletion.
-UVC_HD void k3b_position(const BatchView & v, int64_t gp, const Win & w) {
-    const TileInfo & T = v.tiles[v.pos_tile[gp]];
-    const int32_t p = (int32_t)(gp - T.pos_off) + T.ext_beg;
-    const uvcgpu_params & par = v.par;
-    // thread-private accumulators (this thread is the only writer of the position's records): counted here, stored once at the end
-    // Only a few of the 14 symbols ever occur at one position, so the private arrays are zeroed lazily, per symbol, on first touch
+struct K3bHot { int32_t n, cov, near; };       // bDP, bTA, bTB of one (strand, hot symbol)
+struct K3bState {
+    int64_t gp;
+    int32_t p;
+    int ref;
+    // the two symbols nearly every fragment votes for - the reference base and LINK_M: depths and MQ sums in registers, their quality
+    // histograms in a caller-provided array (shared memory in the CUDA kernel): hb[(type * UVC_NUM_BUCKETS + bucket) * hstride]
+    int hot[2];
+    int32_t hmaxq[2], hmq[2];
+    K3bHot h0[2], h1[2];
+    int32_t *hb; int hstride;
+    // thread-private accumulators of every other symbol (this thread is the only writer of the position's records): counted here, stored once
+    // at the end. Only a few of the 14 symbols ever occur at one position, so the private arrays are zeroed lazily, per symbol, on first touch
     // (bit s of `touched`), and only touched symbols are reduced and stored: the local-memory traffic follows the data, not the array size.
+    uint32_t touched;
     int32_t bucket[UVC_NSYM * UVC_NUM_BUCKETS];
     int32_t acc[2 * UVC_NSYM * UVCGPU_NUM_FRAG_DEPTHS];
     int32_t mq[UVC_NSYM], maxq[UVC_NSYM];
-    uint32_t touched = 0;
-    const int ref = v.refsym[gp];
-    for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
-        if (ri < w.lo || ri >= w.hi) { continue; }
-        const ReadRec & R = v.reads[ri];
-        if (R.rend <= p || R.fragprev_maxrend > p) { continue; }   // not covering, or an earlier read of the same fragment already handled p
-        const FragRec & G = v.frags[R.frag];
-        const FragCol e = v.fcol[G.col_off + (p - G.lo)];
-        int32_t *fd = acc + (G.strand ? UVC_NSYM * UVCGPU_NUM_FRAG_DEPTHS : 0);
-        for (int type = 1; type >= 0; type--) {
-            const int con = (type == 1 ? (e.link_sym & 0xf) : e.base_sym);
-            const int32_t cc = (type == 1 ? e.link_cc : e.base_cc), tc = (type == 1 ? e.link_cc : e.base_tc);
-            if (0 == tc) { continue; }
-            if (!((touched >> con) & 1u)) {
-                touched |= (1u << con);
-                for (int k = 0; k < UVC_NUM_BUCKETS; k++) { bucket[con * UVC_NUM_BUCKETS + k] = 0; }
-                for (int k = 0; k < UVCGPU_NUM_FRAG_DEPTHS; k++) { acc[con * UVCGPU_NUM_FRAG_DEPTHS + k] = 0; acc[(UVC_NSYM + con) * UVCGPU_NUM_FRAG_DEPTHS + k] = 0; }
-                mq[con] = 0; maxq[con] = 8 + avg_bq(v, gp, con);
-            }
-            const int32_t max_qual = maxq[con];
-            int32_t phredlike = tmin(cc * 2 - tc, max_qual);
-            if (0x1 & par.fam_flag) { phredlike = tmin(phredlike, sscs_phred(par, ref, con)); }
-            const int32_t pb = tmax(0, max_qual - phredlike);
-            if (pb < UVC_NUM_BUCKETS) { bucket[con * UVC_NUM_BUCKETS + pb] += 1; }
+};
+UVC_HD void k3b_touch(K3bState & s, const BatchView & v, int con) {
+    if (!((s.touched >> con) & 1u)) {
+        s.touched |= (1u << con);
+        for (int k = 0; k < UVC_NUM_BUCKETS; k++) { s.bucket[con * UVC_NUM_BUCKETS + k] = 0; }
+        for (int k = 0; k < UVCGPU_NUM_FRAG_DEPTHS; k++) { s.acc[con * UVCGPU_NUM_FRAG_DEPTHS + k] = 0; s.acc[(UVC_NSYM + con) * UVCGPU_NUM_FRAG_DEPTHS + k] = 0; }
+        s.mq[con] = 0; s.maxq[con] = 8 + avg_bq(v, s.gp, con);
+    }
+}
+UVC_HD void k3b_begin(K3bState & s, const BatchView & v, int64_t gp, int32_t *hot_buckets, int hstride) {
+    const TileInfo & T = v.tiles[v.pos_tile[gp]];
+    s.gp = gp;
+    s.p = (int32_t)(gp - T.pos_off) + T.ext_beg;
+    s.ref = v.refsym[gp];
+    s.touched = 0;
+    s.hot[0] = s.ref; s.hot[1] = UVC_LINK_M;
+    s.hb = hot_buckets; s.hstride = hstride;
+    for (int t = 0; t < 2; t++) {
+        s.hmaxq[t] = (s.hot[t] < UVC_NSYM ? 8 + avg_bq(v, gp, s.hot[t]) : 0);
+        s.hmq[t] = 0;
+        s.h0[t].n = s.h0[t].cov = s.h0[t].near = 0; s.h1[t].n = s.h1[t].cov = s.h1[t].near = 0;
+    }
+    for (int k = 0; k < 2 * UVC_NUM_BUCKETS; k++) { hot_buckets[k * hstride] = 0; }
+}
+// the first read q of its fragment that covers p; e is the fragment's column entry at p
+UVC_HD void k3b_read(K3bState & s, const BatchView & v, const ReadFrag & q, const FragCol & e) {
+    const uvcgpu_params & par = v.par;
+    const int strand = (q.frag_strand & 1);
+    #pragma unroll
+    for (int type = 1; type >= 0; type--) {
+        const int con = (type == 1 ? (e.link_sym & 0xf) : e.base_sym);
+        const int32_t cc = (type == 1 ? e.link_cc : e.base_cc), tc = (type == 1 ? e.link_cc : e.base_tc);
+        if (0 == tc) { continue; }
+        const bool is_hot = (con == s.hot[type]);
+        if (!is_hot) { k3b_touch(s, v, con); }
+        const int32_t max_qual = (is_hot ? s.hmaxq[type] : s.maxq[con]);
+        int32_t phredlike = tmin(cc * 2 - tc, max_qual);
+        if (0x1 & par.fam_flag) { phredlike = tmin(phredlike, sscs_phred(par, s.ref, con)); }
+        const int32_t pb = tmax(0, max_qual - phredlike);
+        if (is_hot) {
+            if (pb < UVC_NUM_BUCKETS) { s.hb[(type * UVC_NUM_BUCKETS + pb) * s.hstride] += 1; }
+            // the read (hence the strand) is the same for all lanes of the warp
+            if (strand) { s.h1[type].n += 1; s.h1[type].cov += q.n_cov; s.h1[type].near += q.n_near_mut; }
+            else { s.h0[type].n += 1; s.h0[type].cov += q.n_cov; s.h0[type].near += q.n_near_mut; }
+            s.hmq[type] += q.mq_term;
+        } else {
+            if (pb < UVC_NUM_BUCKETS) { s.bucket[con * UVC_NUM_BUCKETS + pb] += 1; }
+            int32_t *fd = s.acc + (strand ? UVC_NSYM * UVCGPU_NUM_FRAG_DEPTHS : 0);
             fd[con * UVCGPU_NUM_FRAG_DEPTHS + 0] += 1;
-            fd[con * UVCGPU_NUM_FRAG_DEPTHS + 1] += G.n_cov;
-            fd[con * UVCGPU_NUM_FRAG_DEPTHS + 2] += G.n_near_mut;
-            mq[con] += (G.normMQ * G.normMQ) / UVC_SQR_QUAL_DIV;
+            fd[con * UVCGPU_NUM_FRAG_DEPTHS + 1] += q.n_cov;
+            fd[con * UVCGPU_NUM_FRAG_DEPTHS + 2] += q.n_near_mut;
+            s.mq[con] += q.mq_term;
             if (is_ins_symbol(con) || is_del_symbol(con)) {
-                const int32_t e = indel_majority_of_reads(v, v.frag_reads + G.read_off, G.n_reads, p, con);
-                if (e >= 0) { rec_put6(v, UVC_REC_FRAG_INDEL, G.strand, con, p, e, 1); }
+                const FragRec & G = v.frags[q.frag_strand >> 1];
+                const int32_t ev = indel_majority_of_reads(v, v.frag_reads + G.read_off, G.n_reads, s.p, con);
+                if (ev >= 0) { rec_put6(v, UVC_REC_FRAG_INDEL, strand, con, s.p, ev, 1); }
             }
         }
     }
+}
+UVC_HD void k3b_end(K3bState & s, const BatchView & v) {
+    const int64_t gp = s.gp;
+    // fold the hot symbols into the private arrays
+    for (int type = 0; type < 2; type++) {
+        if (0 == (s.h0[type].n | s.h1[type].n)) { continue; }
+        const int con = s.hot[type];
+        k3b_touch(s, v, con);
+        for (int k = 0; k < UVC_NUM_BUCKETS; k++) { s.bucket[con * UVC_NUM_BUCKETS + k] += s.hb[(type * UVC_NUM_BUCKETS + k) * s.hstride]; }
+        int32_t *f0 = s.acc + con * UVCGPU_NUM_FRAG_DEPTHS, *f1 = s.acc + (UVC_NSYM + con) * UVCGPU_NUM_FRAG_DEPTHS;
+        f0[0] += s.h0[type].n; f0[1] += s.h0[type].cov; f0[2] += s.h0[type].near;
+        f1[0] += s.h1[type].n; f1[1] += s.h1[type].cov; f1[2] += s.h1[type].near;
+        s.mq[con] += s.hmq[type];
+    }
+    const uint32_t touched = s.touched;
+    const int32_t *acc = s.acc;
     int32_t *vq = v.vq + gp * UVC_NSYM * UVCGPU_NUM_VQ_TAGS;
     for (int type = 0; type < 2; type++) {
         const int s0 = (type == 0 ? UVC_BASE_A : UVC_LINK_M), s1 = (type == 0 ? UVC_BASE_NN : UVC_LINK_NN);
         int32_t totDP = 0;
-        for (int s = s0; s <= s1; s++) { if ((touched >> s) & 1u) { totDP += acc[s * UVCGPU_NUM_FRAG_DEPTHS] + acc[(UVC_NSYM + s) * UVCGPU_NUM_FRAG_DEPTHS]; } }
-        for (int s = s0; s <= s1; s++) {
-            if (!((touched >> s) & 1u)) { continue; }
+        for (int y = s0; y <= s1; y++) { if ((touched >> y) & 1u) { totDP += acc[y * UVCGPU_NUM_FRAG_DEPTHS] + acc[(UVC_NSYM + y) * UVCGPU_NUM_FRAG_DEPTHS]; } }
+        for (int y = s0; y <= s1; y++) {
+            if (!((touched >> y) & 1u)) { continue; }
             for (int strand = 0; strand < 2; strand++) {
-                int32_t *g = v.fragdepth + ((strand * v.n_pos + gp) * UVC_NSYM + s) * UVCGPU_NUM_FRAG_DEPTHS;
-                for (int k = 0; k < UVCGPU_NUM_FRAG_DEPTHS; k++) { g[k] = acc[(strand * UVC_NSYM + s) * UVCGPU_NUM_FRAG_DEPTHS + k]; }
+                int32_t *g = v.fragdepth + ((strand * v.n_pos + gp) * UVC_NSYM + y) * UVCGPU_NUM_FRAG_DEPTHS;
+                for (int k = 0; k < UVCGPU_NUM_FRAG_DEPTHS; k++) { g[k] = acc[(strand * UVC_NSYM + y) * UVCGPU_NUM_FRAG_DEPTHS + k]; }
             }
-            vq[s * UVCGPU_NUM_VQ_TAGS + 4] = mq[s];
+            vq[y * UVCGPU_NUM_VQ_TAGS + 4] = s.mq[y];
             int32_t q, ad, bq;
-            infer_max_qual(q, ad, bq, v, maxq[s], 1, bucket + s * UVC_NUM_BUCKETS, totDP);
-            vq[s * UVCGPU_NUM_VQ_TAGS + 5] = q; vq[s * UVCGPU_NUM_VQ_TAGS + 6] = ad; vq[s * UVCGPU_NUM_VQ_TAGS + 7] = bq;
+            infer_max_qual(q, ad, bq, v, s.maxq[y], 1, s.bucket + y * UVC_NUM_BUCKETS, totDP);
+            vq[y * UVCGPU_NUM_VQ_TAGS + 5] = q; vq[y * UVCGPU_NUM_VQ_TAGS + 6] = ad; vq[y * UVCGPU_NUM_VQ_TAGS + 7] = bq;
         }
     }
+}
+UVC_HD void k3b_position(const BatchView & v, int64_t gp, const Win & w) {
+    K3bState s;
+    int32_t hot_buckets[2 * UVC_NUM_BUCKETS];
+    k3b_begin(s, v, gp, hot_buckets, 1);
+    for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
+        if (ri < w.lo || ri >= w.hi) { continue; }
+        const ReadFrag q = v.rfrag[ri];
+        if (q.rend <= s.p || q.fragprev_maxrend > s.p) { continue; }   // not covering, or an earlier read of the same fragment already handled p
+        k3b_read(s, v, q, v.fcol[q.col_base + s.p]);
+    }
+    k3b_end(s, v);
 }
 
 // ------------------------------------------------------------------------------------------------ family-level helpers
