@@ -626,6 +626,7 @@ static int backend_download(uvcgpu_ctx *, void *dst, const void *src, size_t byt
 static void backend_free(uvcgpu_ctx *, BatchState & bs) { for (void *p : bs.allocs) { free(p); } bs.allocs.clear(); }
 static int backend_run(uvcgpu_ctx *, BatchState & bs) {
     const BatchView & v = bs.view;
+    if (getenv("UVC_EMU_PREP_ONLY")) { return 0; }   // host-staging profiling runs (tools/prep_profile.py)
     for (int64_t i = 0; i < v.n_reads; i++) { uvc::k0_read(v, i); }
     uvc::Win w;
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k1_position(v, i, w); }

@@ -503,6 +503,12 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
         // pack reads in file order
         int32_t max_span = 0;
         std::vector<int32_t> frag_maxrend(hb.frags.size(), INT32_MIN), fam_maxrend(2 * hb.fams.size(), INT32_MIN), famboth_maxrend(hb.fams.size(), INT32_MIN);
+        {
+            size_t n_seq = 0, n_qual = 0, n_cig = 0;
+            for (const Kept & k : kept) { n_seq += (size_t)(k.r.l_qseq + 1) / 2; n_qual += (size_t)k.r.l_qseq; n_cig += (size_t)k.r.n_cigar; }
+            hb.seq.reserve(hb.seq.size() + n_seq); hb.qual.reserve(hb.qual.size() + n_qual); hb.cigar.reserve(hb.cigar.size() + n_cig);
+            hb.reads.reserve(hb.reads.size() + kept.size()); hb.read_raw_index.reserve(hb.read_raw_index.size() + kept.size());
+        }
         for (size_t i = 0; i < kept.size(); i++) {
             const Kept & k = kept[i];
             ReadRec R;
@@ -591,6 +597,7 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
     for (int d = 0; d < 4; d++) { center_pow[d] = pow(par.dedup_center_mult, (double)d); }
     hb = HostBatch();
     const int n_threads = n_threads_req;
+    const int64_t wall0 = prof_now();
     // 1. every tile staged privately, on all host cores
     std::vector<HostBatch> part((size_t)n_tiles);
     std::vector<int> rcs((size_t)n_tiles, 0);
@@ -601,6 +608,7 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
         uvc_stage_thread_pinning(true);
     });
     for (int32_t ti = 0; ti < n_tiles; ti++) { if (rcs[ti] != 0) { msg = msgs[ti]; return rcs[ti]; } }
+    const int64_t wall1 = prof_now();
     // 2. offsets of every tile in the concatenated arrays
     struct Off { int64_t pos, read, frag, fam, fragread, seq, qual, cigar, cx, ev, fcol, mcol; };
     std::vector<Off> off((size_t)n_tiles + 1);
@@ -623,6 +631,7 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
     hb.frags.resize((size_t)tot.frag); hb.frag_reads.resize((size_t)tot.fragread); hb.fams.resize((size_t)tot.fam); hb.fam_umi.resize((size_t)tot.fam);
     hb.n_pos = tot.pos; hb.n_cx = tot.cx; hb.n_ev = tot.ev; hb.n_fcol = tot.fcol; hb.n_mcol = tot.mcol;
     hb.fchunk_frag.resize((size_t)(tot.fcol / UVC_COL_CHUNK)); hb.mchunk_fs.resize((size_t)(tot.mcol / UVC_COL_CHUNK));
+    const int64_t wall2 = prof_now();
     // 3. concatenation with the tile-local indices rebased, again on all cores (disjoint destination ranges)
     uvc_parallel_for(n_tiles, n_threads, [&](int32_t ti) {
         HostBatch & b = part[ti];
@@ -685,6 +694,7 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
         }
         b = HostBatch();   // release the private copy
     });
+    if (getenv("UVC_PREP_PROFILE")) { fprintf(stderr, "prep wall ms: tiles %.1f resize %.1f concat %.1f\n", (wall1 - wall0) / 1e6, (wall2 - wall1) / 1e6, (prof_now() - wall2) / 1e6); }
     if (getenv("UVC_PREP_PROFILE")) { fprintf(stderr, "prep ms: pass1 %.1f centers %.1f pass2 %.1f sort %.1f families %.1f pack %.1f P1 %.1f\n", g_prof[0] / 1e6, g_prof[1] / 1e6, g_prof[2] / 1e6, g_prof[3] / 1e6, g_prof[4] / 1e6, g_prof[5] / 1e6, g_prof[6] / 1e6); for (auto & x : g_prof) { x = 0; } }
     return 0;
 }

@@ -6,6 +6,8 @@
 #include "batch.h"
 
 #include <map>
+#include <new>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -20,6 +22,10 @@ template <class T> struct UvcStageAlloc {
     template <class U> UvcStageAlloc(const UvcStageAlloc<U> &) {}
     T *allocate(size_t n) { return (T*)uvc_stage_alloc(n * sizeof(T)); }
     void deallocate(T *p, size_t n) { uvc_stage_free((void*)p, n * sizeof(T)); }
+    // resize(n) default-initialises (no zero fill): staging arrays are written in full before they are uploaded, and a single-threaded memset of
+    // hundreds of megabytes per batch is not free
+    template <class U> void construct(U *p) { ::new ((void*)p) U; }
+    template <class U, class A0, class... Args> void construct(U *p, A0 && a0, Args &&... args) { ::new ((void*)p) U(std::forward<A0>(a0), std::forward<Args>(args)...); }
     template <class U> bool operator==(const UvcStageAlloc<U> &) const { return true; }
     template <class U> bool operator!=(const UvcStageAlloc<U> &) const { return false; }
 };
