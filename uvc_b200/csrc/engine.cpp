@@ -138,7 +138,7 @@ static thread_local bool g_stage_pinning = true;
 void uvc_stage_thread_pinning(bool enabled) { g_stage_pinning = enabled; }
 void *uvc_stage_alloc(size_t bytes) {
     if (0 == bytes) { bytes = 1; }
-    if (bytes < kStageSmall || !g_stage_pinning) { return malloc(bytes); }
+    if (bytes < kStageSmall || !g_stage_pinning) { return (getenv("UVC_DEBUG_FILL") ? memset(malloc(bytes), atoi(getenv("UVC_DEBUG_FILL")), bytes) : malloc(bytes)); }
 #if UVC_CUDA
     StageState & st = stage_state();
     const size_t cls = stage_class(bytes);
@@ -156,7 +156,7 @@ void *uvc_stage_alloc(size_t bytes) {
     }
     st.cv.notify_one();
 #endif
-    return malloc(bytes);
+    return (getenv("UVC_DEBUG_FILL") ? memset(malloc(bytes), atoi(getenv("UVC_DEBUG_FILL")), bytes) : malloc(bytes));   // debug aid: poison fresh staging memory
 }
 void uvc_stage_free(void *p, size_t bytes) {
     if (NULL == p) { return; }

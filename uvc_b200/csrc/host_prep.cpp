@@ -5,6 +5,9 @@
 // stage P1 (repeat context, BAQ offsets) restates main.hpp:699-721, 794-874 and main.cpp:400-429.
 // Reference quirks that change results are kept on purpose and marked QUIRK.
 #include "host_prep.h"
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -166,6 +169,7 @@ struct Kept {
     int strand;
     uint64_t qhash2;
     int32_t fam_local, frag_local;
+    int32_t simple, m_qoff, n_ev;   // CIGAR shape (see ReadRec), computed once in stage A
 };
 
 // main.hpp:699-721. QUIRK: rank2 is computed with rulen1 when rc2 <= 1.
@@ -187,24 +191,75 @@ int32_t slip_phred(double ampfact, int32_t unit, int32_t nunits) {
 }
 
 // main.hpp:803-874: best short-tandem-repeat (unit <= str_max) and any-tandem-repeat (unit <= vntr_max) track per reference base
-void repeat_context(StageVec<uvcgpu_rtr> & out, const char *ref, int32_t n, const uvcgpu_params & par) {
-    out.assign((size_t)n + 1, uvcgpu_rtr());
-    for (auto & t : out) { t.begpos = 0; t.tracklen = 0; t.unitlen = 0; t.indelphred = par.indel_BQ_max; t.anyTR_begpos = 0; t.anyTR_tracklen = 0; t.anyTR_unitlen = 0; }
+void repeat_context(uvcgpu_rtr *out, const char *ref, int32_t n, const uvcgpu_params & par) {   // out: n + 1 records
+    for (int32_t i = 0; i <= n; i++) { uvcgpu_rtr & t = out[i]; t.begpos = 0; t.tracklen = 0; t.unitlen = 0; t.indelphred = par.indel_BQ_max; t.anyTR_begpos = 0; t.anyTR_tracklen = 0; t.anyTR_unitlen = 0; }
     const int32_t str_max = par.indel_str_repeatsize_max, vntr_max = par.indel_vntr_repeatsize_max;
+    // cand[p] bit u (2 <= u <= umax): the period-u match run that starts at p is at least u long, i.e. unit u repeats (num >= 2). Units that do
+    // not repeat can never win (see below), so the walk only examines the set bits. One backward sweep keeps the 48 run lengths (saturating
+    // bytes) in three SSE registers: about 25 instructions per reference base instead of a 35-iteration scalar loop.
+    const int32_t umax = std::min(vntr_max, 49);
+    std::vector<uint64_t> cand((size_t)n + 1, 0);
+#if defined(__SSE2__)
+    {
+        std::string padded(ref, (size_t)n);
+        padded.append(64, '\0');                 // never equal to a reference character: comparisons past the end fail like `q + unit < n`
+        __m128i run[3], uvec[3];
+        for (int k = 0; k < 3; k++) {
+            run[k] = _mm_setzero_si128();
+            alignas(16) uint8_t uu[16];
+            for (int j = 0; j < 16; j++) { uu[j] = (uint8_t)(2 + 16 * k + j); }
+            uvec[k] = _mm_load_si128((const __m128i*)uu);
+        }
+        const __m128i one = _mm_set1_epi8(1);
+        const uint64_t keep = ((umax >= 63) ? ~(uint64_t)0 : (((uint64_t)1 << (umax + 1)) - 1)) & ~(uint64_t)3;
+        for (int32_t p = n - 1; p >= 0; p--) {
+            const __m128i c = _mm_set1_epi8(padded[(size_t)p]);
+            uint64_t m = 0;
+            for (int k = 0; k < 3; k++) {
+                const __m128i nxt = _mm_loadu_si128((const __m128i*)(padded.data() + p + 2 + 16 * k));
+                const __m128i eq = _mm_cmpeq_epi8(nxt, c);
+                run[k] = _mm_and_si128(_mm_adds_epu8(run[k], one), eq);
+                const __m128i ge = _mm_cmpeq_epi8(_mm_max_epu8(run[k], uvec[k]), run[k]);   // run >= u
+                m |= ((uint64_t)(uint32_t)_mm_movemask_epi8(ge)) << (2 + 16 * k);
+            }
+            cand[(size_t)p] = m & keep;
+        }
+    }
+#else
+    for (int32_t p = 0; p < n; p++) { cand[(size_t)p] = ((((uint64_t)1 << (umax + 1)) - 1) & ~(uint64_t)3); }    // no filter: every unit is examined
+#endif
     for (int32_t refpos = 0; refpos < n;) {
         int32_t best_unit = 0, best_num = 0, best_end = refpos;
         int32_t any_unit = 0, any_num = 0, any_end = refpos;
-        for (int32_t unit = 1; unit <= vntr_max; unit++) {
+        // units in increasing order: 1, then the repeating units among 2..umax (set bits of cand), then every unit above umax.
+        // A unit > 1 that does not repeat (num = 1, rank -unit) never beats what unit 1 already set (rank >= -1, or QUIRK -unit).
+        auto examine = [&](int32_t unit) {
             int32_t q = refpos;
             while (q + unit < n && ref[q] == ref[q + unit]) { q++; }
+            if (unit > 1 && q - refpos < unit) { return; }      // num = 1 again
             const int32_t num = (q - refpos) / unit + 1;
             if (unit <= str_max && more_str(unit, num, best_unit, best_num, str_max)) { best_unit = unit; best_num = num; best_end = q + unit; }
             if (more_str(unit, num, any_unit, any_num, vntr_max)) { any_unit = unit; any_num = num; any_end = q + unit; }
-        }
+        };
+        if (vntr_max >= 1) { examine(1); }
+        for (uint64_t todo = cand[(size_t)refpos]; todo; todo &= todo - 1) { examine(__builtin_ctzll(todo)); }
+        for (int32_t unit = std::max(2, umax + 1); unit <= vntr_max; unit++) { examine(unit); }
         {
             const int32_t stop = std::min(best_end, n);
             const int32_t tl = stop - refpos;
-            const int32_t dec = slip_phred(par.indel_polymerase_slip_rate * par.indel_del_to_ins_err_ratio, best_unit, tl / best_unit);
+            // slip_phred costs four libm calls; nearly every position asks for (unit 1, 1 repeat): memoised per thread for small arguments
+            const double ampfact = par.indel_polymerase_slip_rate * par.indel_del_to_ins_err_ratio;
+            static thread_local double memo_amp = -1;
+            static thread_local int32_t memo[40][64];
+            if (memo_amp != ampfact) { memo_amp = ampfact; for (auto & row : memo) { for (auto & x : row) { x = INT32_MIN; } } }
+            const int32_t nun = tl / best_unit;
+            int32_t dec;
+            if (best_unit < 40 && nun < 64) {
+                if (INT32_MIN == memo[best_unit][nun]) { memo[best_unit][nun] = slip_phred(ampfact, best_unit, nun); }
+                dec = memo[best_unit][nun];
+            } else {
+                dec = slip_phred(ampfact, best_unit, nun);
+            }
             for (int32_t i = refpos; i != stop; i++) {
                 if (tl > out[i].tracklen) {
                     out[i].begpos = refpos; out[i].tracklen = tl; out[i].unitlen = best_unit;
@@ -226,10 +281,10 @@ void repeat_context(StageVec<uvcgpu_rtr> & out, const char *ref, int32_t n, cons
 }
 
 // main.cpp:400-429. QUIRK: the any-tandem-repeat variant still divides by the STR unit length.
-void baq_prefix(StageVec<int32_t> & dst, size_t off, const StageVec<uvcgpu_rtr> & rtr, bool any_tr, const uvcgpu_params & par) {
+void baq_prefix(int32_t *dst, const uvcgpu_rtr *rtr, size_t n, bool any_tr, const uvcgpu_params & par) {
     int64_t sum = 0;
     const int32_t polsize = (int32_t)round(par.indel_polymerase_size);
-    for (size_t i = 0; i < rtr.size(); i++) {
+    for (size_t i = 0; i < n; i++) {
         const int32_t tl = (any_tr ? rtr[i].anyTR_tracklen : rtr[i].tracklen);
         const int32_t ul = rtr[i].unitlen;
         if (tl / ul >= 3 || (tl / ul >= 2 && tl >= polsize)) {
@@ -237,9 +292,9 @@ void baq_prefix(StageVec<int32_t> & dst, size_t off, const StageVec<uvcgpu_rtr> 
         } else {
             sum += par.indel_nonSTR_phred_per_base * 10;
         }
-        dst[off + i] = (int32_t)sum;
+        dst[i] = (int32_t)sum;
     }
-    for (size_t i = 0; i < rtr.size(); i++) { dst[off + i] = (int32_t)((int64_t)dst[off + i] / 10); }
+    for (size_t i = 0; i < n; i++) { dst[i] = (int32_t)((int64_t)dst[i] / 10); }
 }
 
 inline uint8_t char_to_symbol(char c) { // CHAR_TO_SYMBOL (main_conversion.hpp:473-486)
@@ -270,7 +325,16 @@ void uvc_fill_view_constants(BatchView & v, const uvcgpu_params & par) {
 // Stages ONE tile into a private HostBatch whose offsets are all tile-local (the tile keeps its global index ti in the
 // records). Tiles are independent (the reference runs them on different threads, main.cpp:1479), so the batch builder
 // below stages them on all host cores and then concatenates.
-static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<int32_t, HostContig> & contigs,
+// Stage A (everything that decides sizes: filter, family grouping, fragment/family records) keeps its kept reads in TileWork; after the batch
+// offsets are known, stage B packs the reads and the per-position reference context of the tile straight into the batch arrays (one copy of
+// the sequence/quality bytes instead of two).
+struct TileWork {
+    std::vector<Kept> kept;
+    size_t n_seq = 0, n_qual = 0, n_cig = 0;
+    int32_t ext_end_ref = 0;
+    const HostContig *contig = NULL;
+};
+static int build_tile_a(HostBatch & hb, TileWork & tw, const uvcgpu_params & par, const std::map<int32_t, HostContig> & contigs,
         int32_t ti, const uvcgpu_tile & ut, const uvcgpu_reads_soa & rs, const double *center_pow, bool pem, std::string & msg) {
     hb.tiles.resize(1);
     {
@@ -311,17 +375,23 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
                 if (vhash[(size_t)j] == h && 0 == strcmp(rs.qname + rs.qname_off[ut.read_begin + j], name)) { return; }
             }
         };
+        // what pass 1 learns about a read is kept for pass 2 (the classification, the template ends, whether the read itself put its name in the set)
+        struct Pass1 { int32_t rend, tBeg, tEnd; int8_t c; uint8_t keep, touches; };
+        std::vector<Pass1> p1((size_t)n_in);
         for (int64_t i = ut.read_begin; i < ut.read_end; i++) {
             const Raw r = get_raw(rs, i);
+            Pass1 & P = p1[(size_t)(i - ut.read_begin)];
+            P.rend = r.rend; P.keep = 0; P.touches = 0; P.c = 0; P.tBeg = P.tEnd = 0;
             vhash[(size_t)(i - ut.read_begin)] = name_hash(r.qname);
             bool isrc = false, isr2 = false; int32_t tBeg = 0, tEnd = 0;
             if (KEEP != classify(isrc, isr2, tBeg, tEnd, r, fetch_tbeg, fetch_tend, par, end2end, pem)) { continue; }
             const int c = isrc * 2 + isr2;
+            P.keep = 1; P.c = (int8_t)c; P.tBeg = tBeg; P.tEnd = tEnd;
             const int32_t bi = tBeg + ARRPOS_MARGIN - fetch_tbeg, ei = tEnd + ARRPOS_MARGIN - fetch_tbeg;
             if (bi >= 0 && bi < fetch_size) { beg_cnt[c][bi] += 1; }
             if (ei >= 0 && ei < fetch_size) { end_cnt[c][ei] += 1; }
             const int32_t lo = std::min(tBeg, tEnd), hi = std::max(tBeg, tEnd) + 2;
-            if (!((hi <= fetch_tbeg) || (fetch_tend <= lo))) { visited_insert(r.qname, vhash[(size_t)(i - ut.read_begin)], (int32_t)(i - ut.read_begin)); }
+            if (!((hi <= fetch_tbeg) || (fetch_tend <= lo))) { P.touches = 1; visited_insert(r.qname, vhash[(size_t)(i - ut.read_begin)], (int32_t)(i - ut.read_begin)); }
         }
         PROF(0)
         for (int c = 0; c < 4; c++) {
@@ -331,15 +401,18 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
 
         PROF(1)
         // pass 2 (grouping.cpp:731-977): family key of every kept read
-        std::vector<Kept> kept;
+        std::vector<Kept> & kept = tw.kept;
+        kept.reserve((size_t)n_in);
         int32_t bam_beg = INT32_MAX, bam_end = 0;
         int64_t pcrpassed = 0;
         for (int64_t i = ut.read_begin; i < ut.read_end; i++) {
+            const Pass1 & P = p1[(size_t)(i - ut.read_begin)];
+            // (the order of the reference's tests - position window, name set, classification - does not matter: all must hold)
+            if (!P.keep) { continue; }
+            if (rs.pos[i] < nnminus(fetch_tbeg, UVC_MAX_INSERT_SIZE + 1) || P.rend > (fetch_tend + UVC_MAX_INSERT_SIZE + 1)) { continue; }
+            if (!P.touches && !visited_find(rs.qname + rs.qname_off[i], vhash[(size_t)(i - ut.read_begin)])) { continue; }
             Raw r = get_raw(rs, i);
-            if (r.pos < nnminus(fetch_tbeg, UVC_MAX_INSERT_SIZE + 1) || r.rend > (fetch_tend + UVC_MAX_INSERT_SIZE + 1)) { continue; }
-            if (!visited_find(r.qname, vhash[(size_t)(i - ut.read_begin)])) { continue; }
-            bool isrc = false, isr2 = false; int32_t tBeg = 0, tEnd = 0;
-            if (KEEP != classify(isrc, isr2, tBeg, tEnd, r, fetch_tbeg, fetch_tend, par, end2end, pem)) { continue; }
+            const bool isrc = (P.c >> 1) & 1, isr2 = P.c & 1; const int32_t tBeg = P.tBeg, tEnd = P.tEnd;
             bam_beg = std::min(bam_beg, r.pos);
             bam_end = std::max(bam_end, r.rend);
             const char *qname = r.qname;
@@ -415,11 +488,14 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
         if (kept.empty()) { T.skipped = 1; T.ext_beg = T.ext_end = 0; return 0; }
         if (cit == contigs.end()) { msg = "contig of a tile was not set with uvcgpu_set_contig"; return UVCGPU_EINVAL; }
         const HostContig & contig = cit->second;
+        tw.contig = &contig;
         T.rpos_inclu_beg = std::max(ut.beg_pos, bam_beg);
         T.rpos_exclu_end = std::min(ut.end_pos, bam_end);
         T.ext_beg = (int32_t)std::max((int64_t)0, nnminus(std::min(ut.beg_pos, bam_beg), UVC_MAX_STR_N_BASES));
         const int32_t ext_end_ref = (int32_t)std::min((int64_t)ut.contig_len, (int64_t)std::max(ut.end_pos, bam_end) + UVC_MAX_STR_N_BASES);
         T.ext_end = ext_end_ref + 1;
+        tw.ext_end_ref = ext_end_ref;
+        if (contig.available && (int64_t)ext_end_ref > contig.len) { msg = "tile extends beyond the contig that was set"; return UVCGPU_EINVAL; }
 
         // families in MolecularBarcode order; fragments by qname hash inside (family, strand); reads in file order inside a fragment
         std::vector<int32_t> order(kept.size());
@@ -500,27 +576,10 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
         }
 
         PROF(4)
-        // pack reads in file order
+        // sizes of what stage B will write
         int32_t max_span = 0;
-        std::vector<int32_t> frag_maxrend(hb.frags.size(), INT32_MIN), fam_maxrend(2 * hb.fams.size(), INT32_MIN), famboth_maxrend(hb.fams.size(), INT32_MIN);
-        {
-            size_t n_seq = 0, n_qual = 0, n_cig = 0;
-            for (const Kept & k : kept) { n_seq += (size_t)(k.r.l_qseq + 1) / 2; n_qual += (size_t)k.r.l_qseq; n_cig += (size_t)k.r.n_cigar; }
-            hb.seq.reserve(hb.seq.size() + n_seq); hb.qual.reserve(hb.qual.size() + n_qual); hb.cigar.reserve(hb.cigar.size() + n_cig);
-            hb.reads.reserve(hb.reads.size() + kept.size()); hb.read_raw_index.reserve(hb.read_raw_index.size() + kept.size());
-        }
-        for (size_t i = 0; i < kept.size(); i++) {
-            const Kept & k = kept[i];
-            ReadRec R;
-            memset(&R, 0, sizeof(R));
-            R.pos = k.r.pos; R.rend = k.r.rend; R.mpos = k.r.mpos; R.isize = k.r.isize;
-            R.l_qseq = k.r.l_qseq; R.n_cigar = k.r.n_cigar; R.nm = k.r.nm;
-            R.flag = k.r.flag; R.mapq = k.r.mapq; R.strand = (uint8_t)k.strand;
-            R.dflag = k.key.duplexflag; R.tile = ti; R.frag = k.frag_local; R.fam = k.fam_local;
-            R.seq_off = hb.seq.size(); R.qual_off = hb.qual.size(); R.cigar_off = hb.cigar.size();
-            hb.seq.insert(hb.seq.end(), k.r.seq, k.r.seq + (k.r.l_qseq + 1) / 2);
-            hb.qual.insert(hb.qual.end(), k.r.qual, k.r.qual + k.r.l_qseq);
-            hb.cigar.insert(hb.cigar.end(), k.r.cigar, k.r.cigar + k.r.n_cigar);
+        for (Kept & k : kept) {
+            tw.n_seq += (size_t)(k.r.l_qseq + 1) / 2; tw.n_qual += (size_t)k.r.l_qseq; tw.n_cig += (size_t)k.r.n_cigar;
             // simple = [S|H|P]* (M|=|X) [S|H|P]*
             int lead = 0, a = 0, b = k.r.n_cigar;
             while (a < b && (cigar_op(k.r.cigar[a]) == UVC_CSOFT_CLIP || cigar_op(k.r.cigar[a]) == UVC_CHARD_CLIP || cigar_op(k.r.cigar[a]) == UVC_CPAD)) {
@@ -528,55 +587,83 @@ static int build_tile(HostBatch & hb, const uvcgpu_params & par, const std::map<
                 a++;
             }
             while (b > a && (cigar_op(k.r.cigar[b - 1]) == UVC_CSOFT_CLIP || cigar_op(k.r.cigar[b - 1]) == UVC_CHARD_CLIP || cigar_op(k.r.cigar[b - 1]) == UVC_CPAD)) { b--; }
-            R.simple = ((b - a == 1) && op_is_match(cigar_op(k.r.cigar[a])));
-            R.m_qoff = lead;
-            R.cx_off = -1; R.ev_off = (int32_t)hb.n_ev; R.n_ev = 0;
-            if (!R.simple) {
-                R.cx_off = (int32_t)hb.n_cx;
-                hb.n_cx += (R.rend - R.pos);
-                for (int c = 0; c < k.r.n_cigar; c++) { if (cigar_op(k.r.cigar[c]) == UVC_CINS || cigar_op(k.r.cigar[c]) == UVC_CDEL) { R.n_ev++; } }
-                hb.n_ev += R.n_ev;
+            k.simple = ((b - a == 1) && op_is_match(cigar_op(k.r.cigar[a])));
+            k.m_qoff = lead;
+            k.n_ev = 0;
+            if (!k.simple) {
+                hb.n_cx += (k.r.rend - k.r.pos);
+                for (int c = 0; c < k.r.n_cigar; c++) { if (cigar_op(k.r.cigar[c]) == UVC_CINS || cigar_op(k.r.cigar[c]) == UVC_CDEL) { k.n_ev++; } }
+                hb.n_ev += k.n_ev;
             }
-            R.fragprev_maxrend = frag_maxrend[(size_t)R.frag];
-            frag_maxrend[(size_t)R.frag] = std::max(frag_maxrend[(size_t)R.frag], R.rend);
-            const size_t fkey = (size_t)R.fam * 2 + R.strand;
-            R.famprev_maxrend = fam_maxrend[fkey];
-            fam_maxrend[fkey] = std::max(fam_maxrend[fkey], R.rend);
-            R.fambothprev_maxrend = famboth_maxrend[(size_t)R.fam];
-            famboth_maxrend[(size_t)R.fam] = std::max(famboth_maxrend[(size_t)R.fam], R.rend);
-            max_span = std::max(max_span, R.rend - R.pos);
-            hb.reads.push_back(R);
-            hb.read_raw_index.push_back(k.raw);
+            max_span = std::max(max_span, k.r.rend - k.r.pos);
         }
         T.n_reads = (int32_t)kept.size();
         T.n_frags = (int32_t)((int64_t)hb.frags.size() - T.frag_off);
         T.n_fams = (int32_t)((int64_t)hb.fams.size() - T.fam_off);
         T.max_read_span = max_span;
-
+        hb.n_pos = T.ext_end - T.ext_beg;
         PROF(5)
+    }
+    return 0;
+}
+
+struct BatchOff { int64_t pos, read, frag, fam, fragread, seq, qual, cigar, cx, ev, fcol, mcol; };
+
+// Stage B: the tile's reads (file order) and reference context written at their final places in the batch arrays.
+static void build_tile_b(HostBatch & hb, const TileWork & tw, const TileInfo & T, const BatchOff & o, const uvcgpu_params & par, int32_t ti,
+        size_t n_frags_tile, size_t n_fams_tile) {
+    int64_t prof_t = prof_now();
+    const std::vector<Kept> & kept = tw.kept;
+    if (kept.empty()) { return; }
+    {
+        std::vector<int32_t> frag_maxrend(n_frags_tile, INT32_MIN), fam_maxrend(2 * n_fams_tile, INT32_MIN), famboth_maxrend(n_fams_tile, INT32_MIN);
+        uint64_t seq_at = (uint64_t)o.seq, qual_at = (uint64_t)o.qual, cig_at = (uint64_t)o.cigar;
+        int64_t cx_at = o.cx, ev_at = o.ev;
+        for (size_t i = 0; i < kept.size(); i++) {
+            const Kept & k = kept[i];
+            ReadRec R;
+            memset(&R, 0, sizeof(R));
+            R.pos = k.r.pos; R.rend = k.r.rend; R.mpos = k.r.mpos; R.isize = k.r.isize;
+            R.l_qseq = k.r.l_qseq; R.n_cigar = k.r.n_cigar; R.nm = k.r.nm;
+            R.flag = k.r.flag; R.mapq = k.r.mapq; R.strand = (uint8_t)k.strand;
+            R.dflag = k.key.duplexflag; R.tile = ti; R.frag = k.frag_local + (int32_t)o.frag; R.fam = k.fam_local + (int32_t)o.fam;
+            R.seq_off = seq_at; R.qual_off = qual_at; R.cigar_off = cig_at;
+            memcpy(hb.seq.data() + seq_at, k.r.seq, (size_t)(k.r.l_qseq + 1) / 2); seq_at += (uint64_t)(k.r.l_qseq + 1) / 2;
+            memcpy(hb.qual.data() + qual_at, k.r.qual, (size_t)k.r.l_qseq); qual_at += (uint64_t)k.r.l_qseq;
+            memcpy(hb.cigar.data() + cig_at, k.r.cigar, (size_t)k.r.n_cigar * sizeof(uint32_t)); cig_at += (uint64_t)k.r.n_cigar;
+            R.simple = k.simple; R.m_qoff = k.m_qoff;
+            R.cx_off = -1; R.ev_off = (int32_t)ev_at; R.n_ev = k.n_ev;
+            if (!R.simple) { R.cx_off = (int32_t)cx_at; cx_at += (R.rend - R.pos); ev_at += R.n_ev; }
+            R.fragprev_maxrend = frag_maxrend[(size_t)k.frag_local];
+            frag_maxrend[(size_t)k.frag_local] = std::max(frag_maxrend[(size_t)k.frag_local], R.rend);
+            const size_t fkey = (size_t)k.fam_local * 2 + R.strand;
+            R.famprev_maxrend = fam_maxrend[fkey];
+            fam_maxrend[fkey] = std::max(fam_maxrend[fkey], R.rend);
+            R.fambothprev_maxrend = famboth_maxrend[(size_t)k.fam_local];
+            famboth_maxrend[(size_t)k.fam_local] = std::max(famboth_maxrend[(size_t)k.fam_local], R.rend);
+            hb.reads[(size_t)o.read + i] = R;
+            hb.read_raw_index[(size_t)o.read + i] = k.raw;
+        }
+    }
+    PROF(5)
+    {
         // stage P1: reference symbols, repeat context, BAQ prefix sums over [ext_beg, ext_end)
         const int32_t npos = T.ext_end - T.ext_beg;
         const int32_t nref = npos - 1;
         std::string refstring;
-        if (contig.available) {
-            if ((int64_t)ext_end_ref > contig.len) { msg = "tile extends beyond the contig that was set"; return UVCGPU_EINVAL; }
-            refstring.assign(contig.bases.data() + T.ext_beg, (size_t)nref);
-        } else {
-            refstring.assign((size_t)nref, 'n');
-        }
-        const size_t poff = (size_t)hb.n_pos;
-        hb.refsym.resize(poff + npos); hb.pos_tile.resize(poff + npos, ti); hb.baq.resize(poff + npos); hb.baq2.resize(poff + npos);
+        if (tw.contig->available) { refstring.assign(tw.contig->bases.data() + T.ext_beg, (size_t)nref); }
+        else { refstring.assign((size_t)nref, 'n'); }
+        const size_t poff = (size_t)o.pos;
+        std::fill(hb.pos_tile.begin() + poff, hb.pos_tile.begin() + poff + npos, ti);
         for (int32_t i = 0; i < nref; i++) { hb.refsym[poff + i] = char_to_symbol(refstring[i]); }
         hb.refsym[poff + nref] = UVC_BASE_N;
-        StageVec<uvcgpu_rtr> rtr;
-        repeat_context(rtr, refstring.data(), nref, par);
-        hb.rtr.insert(hb.rtr.end(), rtr.begin(), rtr.end());
-        baq_prefix(hb.baq, poff, rtr, false, par);
-        baq_prefix(hb.baq2, poff, rtr, true, par);
-        hb.n_pos += npos;
+        PROF(6)
+        repeat_context(hb.rtr.data() + poff, refstring.data(), nref, par);
+        PROF(7)
+        baq_prefix(hb.baq.data() + poff, hb.rtr.data() + poff, (size_t)npos, false, par);
+        baq_prefix(hb.baq2.data() + poff, hb.rtr.data() + poff, (size_t)npos, true, par);
         PROF(6)
     }
-    return 0;
 }
 
 int uvc_host_threads(int32_t n_tiles, int requested) {
@@ -600,24 +687,25 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
     const int64_t wall0 = prof_now();
     // 1. every tile staged privately, on all host cores
     std::vector<HostBatch> part((size_t)n_tiles);
+    std::vector<TileWork> work((size_t)n_tiles);
     std::vector<int> rcs((size_t)n_tiles, 0);
     std::vector<std::string> msgs((size_t)n_tiles);
     uvc_parallel_for(n_tiles, n_threads, [&](int32_t ti) {
         uvc_stage_thread_pinning(false);
-        rcs[ti] = build_tile(part[ti], par, contigs, ti, tiles[ti], sources[tile_source ? tile_source[ti] : 0], center_pow, pem, msgs[ti]);
+        rcs[ti] = build_tile_a(part[ti], work[ti], par, contigs, ti, tiles[ti], sources[tile_source ? tile_source[ti] : 0], center_pow, pem, msgs[ti]);
         uvc_stage_thread_pinning(true);
     });
     for (int32_t ti = 0; ti < n_tiles; ti++) { if (rcs[ti] != 0) { msg = msgs[ti]; return rcs[ti]; } }
     const int64_t wall1 = prof_now();
     // 2. offsets of every tile in the concatenated arrays
-    struct Off { int64_t pos, read, frag, fam, fragread, seq, qual, cigar, cx, ev, fcol, mcol; };
+    typedef BatchOff Off;
     std::vector<Off> off((size_t)n_tiles + 1);
     memset(&off[0], 0, sizeof(Off));
     for (int32_t ti = 0; ti < n_tiles; ti++) {
         const HostBatch & b = part[ti];
         Off o = off[ti];
-        o.pos += b.n_pos; o.read += (int64_t)b.reads.size(); o.frag += (int64_t)b.frags.size(); o.fam += (int64_t)b.fams.size();
-        o.fragread += (int64_t)b.frag_reads.size(); o.seq += (int64_t)b.seq.size(); o.qual += (int64_t)b.qual.size(); o.cigar += (int64_t)b.cigar.size();
+        o.pos += b.n_pos; o.read += (int64_t)work[ti].kept.size(); o.frag += (int64_t)b.frags.size(); o.fam += (int64_t)b.fams.size();
+        o.fragread += (int64_t)b.frag_reads.size(); o.seq += (int64_t)work[ti].n_seq; o.qual += (int64_t)work[ti].n_qual; o.cigar += (int64_t)work[ti].n_cig;
         o.cx += b.n_cx; o.ev += b.n_ev; o.fcol += b.n_fcol; o.mcol += b.n_mcol;
         off[ti + 1] = o;
         hb.n_reads_in += b.n_reads_in;
@@ -632,30 +720,16 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
     hb.n_pos = tot.pos; hb.n_cx = tot.cx; hb.n_ev = tot.ev; hb.n_fcol = tot.fcol; hb.n_mcol = tot.mcol;
     hb.fchunk_frag.resize((size_t)(tot.fcol / UVC_COL_CHUNK)); hb.mchunk_fs.resize((size_t)(tot.mcol / UVC_COL_CHUNK));
     const int64_t wall2 = prof_now();
-    // 3. concatenation with the tile-local indices rebased, again on all cores (disjoint destination ranges)
+    // 3. stage B of every tile and its fragment / family records with the tile-local indices rebased, again on all cores (disjoint destination ranges)
     uvc_parallel_for(n_tiles, n_threads, [&](int32_t ti) {
         HostBatch & b = part[ti];
         const Off & o = off[ti];
         TileInfo T = b.tiles[0];
         T.pos_off = o.pos; T.read_off = o.read; T.frag_off = o.frag; T.fam_off = o.fam;
         hb.tiles[ti] = T;
-        std::fill(hb.pos_tile.begin() + o.pos, hb.pos_tile.begin() + o.pos + b.n_pos, ti);
-        std::copy(b.refsym.begin(), b.refsym.end(), hb.refsym.begin() + o.pos);
-        std::copy(b.rtr.begin(), b.rtr.end(), hb.rtr.begin() + o.pos);
-        std::copy(b.baq.begin(), b.baq.end(), hb.baq.begin() + o.pos);
-        std::copy(b.baq2.begin(), b.baq2.end(), hb.baq2.begin() + o.pos);
-        std::copy(b.seq.begin(), b.seq.end(), hb.seq.begin() + o.seq);
-        std::copy(b.qual.begin(), b.qual.end(), hb.qual.begin() + o.qual);
-        std::copy(b.cigar.begin(), b.cigar.end(), hb.cigar.begin() + o.cigar);
-        std::copy(b.read_raw_index.begin(), b.read_raw_index.end(), hb.read_raw_index.begin() + o.read);
-        for (size_t i = 0; i < b.reads.size(); i++) {
-            ReadRec R = b.reads[i];
-            R.frag += (int32_t)o.frag; R.fam += (int32_t)o.fam;
-            R.seq_off += (uint64_t)o.seq; R.qual_off += (uint64_t)o.qual; R.cigar_off += (uint64_t)o.cigar;
-            if (R.cx_off >= 0) { R.cx_off += (int32_t)o.cx; }
-            R.ev_off += (int32_t)o.ev;
-            hb.reads[(size_t)o.read + i] = R;
-        }
+        uvc_stage_thread_pinning(false);
+        build_tile_b(hb, work[ti], T, o, par, ti, b.frags.size(), b.fams.size());
+        uvc_stage_thread_pinning(true);
         for (size_t i = 0; i < b.frags.size(); i++) {
             FragRec G = b.frags[i];
             G.fam += (int32_t)o.fam; G.read_off += (int32_t)o.fragread; G.col_off += o.fcol;
@@ -677,7 +751,7 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
             }
             hb.fam_umi[(size_t)o.fam + i].swap(b.fam_umi[i]);
         }
-        for (size_t i = 0; i < b.reads.size(); i++) {
+        for (size_t i = 0; i < work[ti].kept.size(); i++) {
             const ReadRec & R = hb.reads[(size_t)o.read + i];
             const FamRec & F = hb.fams[(size_t)R.fam];
             ReadFam q;
@@ -693,9 +767,10 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
             hb.rfam[(size_t)o.read + i] = q;
         }
         b = HostBatch();   // release the private copy
+        work[ti] = TileWork();
     });
     if (getenv("UVC_PREP_PROFILE")) { fprintf(stderr, "prep wall ms: tiles %.1f resize %.1f concat %.1f\n", (wall1 - wall0) / 1e6, (wall2 - wall1) / 1e6, (prof_now() - wall2) / 1e6); }
-    if (getenv("UVC_PREP_PROFILE")) { fprintf(stderr, "prep ms: pass1 %.1f centers %.1f pass2 %.1f sort %.1f families %.1f pack %.1f P1 %.1f\n", g_prof[0] / 1e6, g_prof[1] / 1e6, g_prof[2] / 1e6, g_prof[3] / 1e6, g_prof[4] / 1e6, g_prof[5] / 1e6, g_prof[6] / 1e6); for (auto & x : g_prof) { x = 0; } }
+    if (getenv("UVC_PREP_PROFILE")) { fprintf(stderr, "prep ms: pass1 %.1f centers %.1f pass2 %.1f sort %.1f families %.1f pack %.1f P1 %.1f (of which repeat context %.1f)\n", g_prof[0] / 1e6, g_prof[1] / 1e6, g_prof[2] / 1e6, g_prof[3] / 1e6, g_prof[4] / 1e6, g_prof[5] / 1e6, (g_prof[6] + g_prof[7]) / 1e6, g_prof[7] / 1e6); for (auto & x : g_prof) { x = 0; } }
     return 0;
 }
 
