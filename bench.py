@@ -50,8 +50,8 @@ def parse_args():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--scale", type=float, default=None, help="fraction of the named config's region (default: per-config)")
     ap.add_argument("--workdir", default=os.environ.get("UVC_BENCH_DIR", "/tmp/uvc_bench"))
-    ap.add_argument("--contexts", type=int, default=6, help="contexts (CUDA streams) the e2e step pipelines its sub-batches over")
-    ap.add_argument("--sub-batches", type=int, default=12)
+    ap.add_argument("--contexts", type=int, default=3, help="contexts (CUDA streams) the e2e step pipelines its sub-batches over")
+    ap.add_argument("--sub-batches", type=int, default=6)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -244,10 +244,14 @@ def main():
             ctx.set_contig_name(tid, cname)
         return ctx
 
-    def run_tiles(ctx, sub):
+    def submit_tiles(ctx, sub):
         t0 = time.time()
-        ticket = ctx.submit(sub, view)
-        t1 = time.time()
+        ticket = ctx.submit(sub, view)       # host staging (P0/P1), H2D copies and every pileup kernel enqueued on the context's stream
+        return (ticket, sub, t0, time.time())
+
+    def finish_tiles(ctx, pending):
+        ticket, sub, t0, t1 = pending
+        tw0 = time.time()
         ctx.collect(ticket)
         t2 = time.time()
         st = ctx.score(ticket)               # candidate scoring on the device + D2H of the kept records and block-line inputs
@@ -258,8 +262,11 @@ def main():
         t4 = time.time()
         ctx.release(ticket)
         st.vcf_bytes = nbytes
-        st.phase_s = (t1 - t0, t2 - t1, t3 - t2, t4 - t3, time.time() - t4)   # submit (staging + H2D enqueue), wait, score, text, release
+        st.phase_s = (t1 - t0, t2 - tw0, t3 - t2, t4 - t3, time.time() - t4)   # submit (staging + H2D enqueue), wait, score, text, release
         return st
+
+    def run_tiles(ctx, sub):
+        return finish_tiles(ctx, submit_tiles(ctx, sub))
 
     # ---- phase 1: device-resident throughput (`value`): one context, the whole batch per launch, CUDA-event time of every kernel
     ctx0 = make_ctx(host_threads)
@@ -300,13 +307,21 @@ def main():
 
         def work(ctx):
             try:
+                # two sub-batches in flight per context: the next one is staged and enqueued before the previous one is collected, so the
+                # stream always has work queued while the host stages
+                pending = None
                 while True:
                     with lock:
                         k = nxt[0]
                         nxt[0] += 1
-                    if k >= len(subs):
+                    nxt_pending = submit_tiles(ctx, subs[k]) if k < len(subs) else None
+                    if pending is None and nxt_pending is None:
                         return
-                    st = run_tiles(ctx, subs[k])
+                    if pending is None:
+                        pending = nxt_pending
+                        continue
+                    st = finish_tiles(ctx, pending)
+                    pending = nxt_pending
                     with lock:
                         acc["h2d"] += int(st.h2d_bytes)
                         acc["d2h"] += int(st.d2h_bytes)
@@ -389,7 +404,7 @@ def main():
                        "positions_per_step": n_positions, "ext_positions_per_step": int(last.n_ext_positions), "stages": STAGES_IMPLEMENTED,
                        "l2": "per-position state of a step (%.0f MB) is larger than L2, no flush needed" % (last.n_ext_positions * 6272 / 1e6),
                        "host_decode_s_untimed": decode_s, "dataset_generation_s_untimed": ds.get("gen_s"),
-                       "e2e_schedule": "%d sub-batches over %d contexts (streams), %d host threads" % (len(subs), len(ctxs), host_threads)},
+                       "e2e_schedule": "%d sub-batches over %d contexts (streams), two in flight per context, %d host threads" % (len(subs), len(ctxs), host_threads)},
             "e2e": {"value": e2e, "unit": "reads/s", "positions_per_s": units * n_positions * args.steps / wall_s,
                     "h2d_bytes_per_step": totals["h2d"] // args.steps, "d2h_bytes_per_step": totals["d2h"] // args.steps,
                     "vcf_bytes_per_step": totals["vcf"] // args.steps, "vcf_records_per_step": totals["rec"] // args.steps,
