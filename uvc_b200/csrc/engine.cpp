@@ -360,8 +360,9 @@ __global__ void __launch_bounds__(128) uvc_k3b_fragment_consensus(const BatchVie
     uvc::Win w;
     uvc_warp_window(v, gp, active, w);
     uvc::K3bState st;
+    uvc::K3bArrays arr;
     st.p = 0;
-    if (active) { uvc::k3b_begin(st, v, gp, hot_buckets, 128); }
+    if (active) { uvc::k3b_begin(st, arr, v, gp, hot_buckets, 128); }
     const int32_t p = st.p;
     const int64_t c0 = w.ulo & ~(int64_t)3;
     if (c0 < w.uhi) { uvc_warp_stage_async(S.q[0], v.rfrag, c0, (int)(w.uhi - c0 < UVC_STAGE_READS ? w.uhi - c0 : UVC_STAGE_READS), lane); }
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(128) uvc_k3b_fragment_consensus(const BatchVie
             for (int k = 0; k < nc; k++) {
                 const int64_t ri = cb + k;
                 if (ri < w.lo || ri >= w.hi) { continue; }
-                const ReadFrag & q = sq[k];
+                const ReadFrag q = sq[k];
                 if (q.rend <= p || q.fragprev_maxrend > p) { continue; }
                 uvc::k3b_read(st, v, q, S.e[k][lane]);
             }
@@ -418,8 +419,9 @@ __global__ void __launch_bounds__(128) uvc_k4_family_consensus(const BatchView v
     uvc::Win w;
     uvc_warp_window(v, gp, active, w);
     uvc::K4State st;
+    uvc::K4Arrays arr;
     st.p = 0; st.n_need2 = 0;
-    if (active) { uvc::k4_begin(st, v, gp); }
+    if (active) { uvc::k4_begin(st, arr, v, gp); }
     const int32_t p = st.p;
     const int64_t c0 = w.ulo & ~(int64_t)3;
     for (int pass = 0; pass < 2; pass++) {
@@ -458,7 +460,7 @@ __global__ void __launch_bounds__(128) uvc_k4_family_consensus(const BatchView v
                     for (int k = 0; k < nc; k++) {
                         const int64_t ri = cb + k;
                         if (ri < w.lo || ri >= w.hi) { continue; }
-                        const ReadFam & q = sq[k];
+                        const ReadFam q = sq[k];
                         if (q.rend <= p || q.famprev_maxrend > p) { continue; }
                         uvc::k4_loop1_read(st, v, q, (q.flags & UVC_RF_DIRECT) ? uvc::famcol_from_frag(S.e[k][lane], v.par) : v.mcol[q.col_base + p], ri - w.lo);
                     }

@@ -1227,14 +1227,46 @@ struct K3bState {
     int32_t hmaxq[2], hmq[2];
     K3bHot h0[2], h1[2];
     int32_t *hb; int hstride;
+    uint32_t hb_saddr;     // CUDA: shared-memory address of hb (histogram updates are shared-memory reductions that nothing waits for)
     // thread-private accumulators of every other symbol (this thread is the only writer of the position's records): counted here, stored once
     // at the end. Only a few of the 14 symbols ever occur at one position, so the private arrays are zeroed lazily, per symbol, on first touch
     // (bit s of `touched`), and only touched symbols are reduced and stored: the local-memory traffic follows the data, not the array size.
+    // (the arrays live in the caller's frame and are reached through pointers: a state struct made of scalars only stays in registers)
     uint32_t touched;
+    int32_t *bucket;       // [UVC_NSYM * UVC_NUM_BUCKETS]
+    int32_t *acc;          // [2 * UVC_NSYM * UVCGPU_NUM_FRAG_DEPTHS]
+    int32_t *mq, *maxq;    // [UVC_NSYM] each
+};
+struct K3bArrays {
     int32_t bucket[UVC_NSYM * UVC_NUM_BUCKETS];
     int32_t acc[2 * UVC_NSYM * UVCGPU_NUM_FRAG_DEPTHS];
     int32_t mq[UVC_NSYM], maxq[UVC_NSYM];
 };
+UVC_HD void k3b_hb_set(K3bState & s, int32_t *hot_buckets, int hstride) {
+    s.hb = hot_buckets; s.hstride = hstride; s.hb_saddr = 0;
+#if defined(__CUDA_ARCH__)
+    s.hb_saddr = (uint32_t)__cvta_generic_to_shared(hot_buckets);
+    for (int k = 0; k < 2 * UVC_NUM_BUCKETS; k++) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(s.hb_saddr + (uint32_t)(k * hstride * 4)), "r"(0) : "memory"); }
+#else
+    for (int k = 0; k < 2 * UVC_NUM_BUCKETS; k++) { hot_buckets[k * hstride] = 0; }
+#endif
+}
+UVC_HD void k3b_hb_inc(K3bState & s, int k) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(s.hb_saddr + (uint32_t)(k * s.hstride * 4)), "r"(1) : "memory");
+#else
+    s.hb[k * s.hstride] += 1;
+#endif
+}
+UVC_HD int32_t k3b_hb_get(const K3bState & s, int k) {
+#if defined(__CUDA_ARCH__)
+    int32_t x;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(s.hb_saddr + (uint32_t)(k * s.hstride * 4)) : "memory");
+    return x;
+#else
+    return s.hb[k * s.hstride];
+#endif
+}
 UVC_HD void k3b_touch(K3bState & s, const BatchView & v, int con) {
     if (!((s.touched >> con) & 1u)) {
         s.touched |= (1u << con);
@@ -1243,20 +1275,20 @@ UVC_HD void k3b_touch(K3bState & s, const BatchView & v, int con) {
         s.mq[con] = 0; s.maxq[con] = 8 + avg_bq(v, s.gp, con);
     }
 }
-UVC_HD void k3b_begin(K3bState & s, const BatchView & v, int64_t gp, int32_t *hot_buckets, int hstride) {
+UVC_HD void k3b_begin(K3bState & s, K3bArrays & arr, const BatchView & v, int64_t gp, int32_t *hot_buckets, int hstride) {
     const TileInfo & T = v.tiles[v.pos_tile[gp]];
+    s.bucket = arr.bucket; s.acc = arr.acc; s.mq = arr.mq; s.maxq = arr.maxq;
     s.gp = gp;
     s.p = (int32_t)(gp - T.pos_off) + T.ext_beg;
     s.ref = v.refsym[gp];
     s.touched = 0;
     s.hot[0] = s.ref; s.hot[1] = UVC_LINK_M;
-    s.hb = hot_buckets; s.hstride = hstride;
+    k3b_hb_set(s, hot_buckets, hstride);
     for (int t = 0; t < 2; t++) {
         s.hmaxq[t] = (s.hot[t] < UVC_NSYM ? 8 + avg_bq(v, gp, s.hot[t]) : 0);
         s.hmq[t] = 0;
         s.h0[t].n = s.h0[t].cov = s.h0[t].near = 0; s.h1[t].n = s.h1[t].cov = s.h1[t].near = 0;
     }
-    for (int k = 0; k < 2 * UVC_NUM_BUCKETS; k++) { hot_buckets[k * hstride] = 0; }
 }
 // the first read q of its fragment that covers p; e is the fragment's column entry at p
 UVC_HD void k3b_read(K3bState & s, const BatchView & v, const ReadFrag & q, const FragCol & e) {
@@ -1267,30 +1299,33 @@ UVC_HD void k3b_read(K3bState & s, const BatchView & v, const ReadFrag & q, cons
         const int con = (type == 1 ? (e.link_sym & 0xf) : e.base_sym);
         const int32_t cc = (type == 1 ? e.link_cc : e.base_cc), tc = (type == 1 ? e.link_cc : e.base_tc);
         if (0 == tc) { continue; }
-        const bool is_hot = (con == s.hot[type]);
-        if (!is_hot) { k3b_touch(s, v, con); }
-        const int32_t max_qual = (is_hot ? s.hmaxq[type] : s.maxq[con]);
-        int32_t phredlike = tmin(cc * 2 - tc, max_qual);
-        if (0x1 & par.fam_flag) { phredlike = tmin(phredlike, sscs_phred(par, s.ref, con)); }
-        const int32_t pb = tmax(0, max_qual - phredlike);
-        if (is_hot) {
-            if (pb < UVC_NUM_BUCKETS) { s.hb[(type * UVC_NUM_BUCKETS + pb) * s.hstride] += 1; }
+        if (con == s.hot[type]) {
+            const int32_t max_qual = s.hmaxq[type];
+            int32_t phredlike = tmin(cc * 2 - tc, max_qual);
+            if (0x1 & par.fam_flag) { phredlike = tmin(phredlike, sscs_phred(par, s.ref, con)); }
+            const int32_t pb = tmax(0, max_qual - phredlike);
+            if (pb < UVC_NUM_BUCKETS) { k3b_hb_inc(s, type * UVC_NUM_BUCKETS + pb); }
             // the read (hence the strand) is the same for all lanes of the warp
             if (strand) { s.h1[type].n += 1; s.h1[type].cov += q.n_cov; s.h1[type].near += q.n_near_mut; }
             else { s.h0[type].n += 1; s.h0[type].cov += q.n_cov; s.h0[type].near += q.n_near_mut; }
             s.hmq[type] += q.mq_term;
-        } else {
-            if (pb < UVC_NUM_BUCKETS) { s.bucket[con * UVC_NUM_BUCKETS + pb] += 1; }
-            int32_t *fd = s.acc + (strand ? UVC_NSYM * UVCGPU_NUM_FRAG_DEPTHS : 0);
-            fd[con * UVCGPU_NUM_FRAG_DEPTHS + 0] += 1;
-            fd[con * UVCGPU_NUM_FRAG_DEPTHS + 1] += q.n_cov;
-            fd[con * UVCGPU_NUM_FRAG_DEPTHS + 2] += q.n_near_mut;
-            s.mq[con] += q.mq_term;
-            if (is_ins_symbol(con) || is_del_symbol(con)) {
-                const FragRec & G = v.frags[q.frag_strand >> 1];
-                const int32_t ev = indel_majority_of_reads(v, v.frag_reads + G.read_off, G.n_reads, s.p, con);
-                if (ev >= 0) { rec_put6(v, UVC_REC_FRAG_INDEL, strand, con, s.p, ev, 1); }
-            }
+            continue;
+        }
+        k3b_touch(s, v, con);
+        const int32_t max_qual = s.maxq[con];
+        int32_t phredlike = tmin(cc * 2 - tc, max_qual);
+        if (0x1 & par.fam_flag) { phredlike = tmin(phredlike, sscs_phred(par, s.ref, con)); }
+        const int32_t pb = tmax(0, max_qual - phredlike);
+        if (pb < UVC_NUM_BUCKETS) { s.bucket[con * UVC_NUM_BUCKETS + pb] += 1; }
+        int32_t *fd = s.acc + (strand ? UVC_NSYM * UVCGPU_NUM_FRAG_DEPTHS : 0);
+        fd[con * UVCGPU_NUM_FRAG_DEPTHS + 0] += 1;
+        fd[con * UVCGPU_NUM_FRAG_DEPTHS + 1] += q.n_cov;
+        fd[con * UVCGPU_NUM_FRAG_DEPTHS + 2] += q.n_near_mut;
+        s.mq[con] += q.mq_term;
+        if (is_ins_symbol(con) || is_del_symbol(con)) {
+            const FragRec & G = v.frags[q.frag_strand >> 1];
+            const int32_t ev = indel_majority_of_reads(v, v.frag_reads + G.read_off, G.n_reads, s.p, con);
+            if (ev >= 0) { rec_put6(v, UVC_REC_FRAG_INDEL, strand, con, s.p, ev, 1); }
         }
     }
 }
@@ -1301,7 +1336,7 @@ UVC_HD void k3b_end(K3bState & s, const BatchView & v) {
         if (0 == (s.h0[type].n | s.h1[type].n)) { continue; }
         const int con = s.hot[type];
         k3b_touch(s, v, con);
-        for (int k = 0; k < UVC_NUM_BUCKETS; k++) { s.bucket[con * UVC_NUM_BUCKETS + k] += s.hb[(type * UVC_NUM_BUCKETS + k) * s.hstride]; }
+        for (int k = 0; k < UVC_NUM_BUCKETS; k++) { s.bucket[con * UVC_NUM_BUCKETS + k] += k3b_hb_get(s, type * UVC_NUM_BUCKETS + k); }
         int32_t *f0 = s.acc + con * UVCGPU_NUM_FRAG_DEPTHS, *f1 = s.acc + (UVC_NSYM + con) * UVCGPU_NUM_FRAG_DEPTHS;
         f0[0] += s.h0[type].n; f0[1] += s.h0[type].cov; f0[2] += s.h0[type].near;
         f1[0] += s.h1[type].n; f1[1] += s.h1[type].cov; f1[2] += s.h1[type].near;
@@ -1329,8 +1364,9 @@ UVC_HD void k3b_end(K3bState & s, const BatchView & v) {
 }
 UVC_HD void k3b_position(const BatchView & v, int64_t gp, const Win & w) {
     K3bState s;
+    K3bArrays arr;
     int32_t hot_buckets[2 * UVC_NUM_BUCKETS];
-    k3b_begin(s, v, gp, hot_buckets, 1);
+    k3b_begin(s, arr, v, gp, hot_buckets, 1);
     for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
         if (ri < w.lo || ri >= w.hi) { continue; }
         const ReadFrag q = v.rfrag[ri];
@@ -1512,13 +1548,19 @@ struct K4State {
     uint32_t touched;      // bit strand * 14 + symbol: facc / bucket rows that are live (rows are zeroed lazily on first touch, see K3b)
     // reads (offsets from the start of the window) that loop 1 leaves work for; more than UVC_K4_LIST of them: the whole window is walked again
     int32_t n_need2;
-    uint16_t need2[UVC_K4_LIST];
+    uint16_t *need2;       // [UVC_K4_LIST]
     // family depth counters of the two symbols nearly every family votes for - the reference base and LINK_M - per strand: registers
     int hot[2];            // [type]
     K4Hot h0[2], h1[2];    // strand 0 / strand 1, [type]
-    // thread-private family depth counters of every other symbol (this thread is the position's only writer): stored once at the end
+    // thread-private family depth counters of every other symbol (this thread is the position's only writer): stored once at the end.
+    // (the arrays live in the caller's frame and are reached through pointers: a state struct made of scalars only stays in registers)
+    int32_t *facc;         // [2 * UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS]
+    int32_t *bucket;       // [2 * UVC_NSYM * UVC_NUM_BUCKETS]
+};
+struct K4Arrays {
     int32_t facc[2 * UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS];
     int32_t bucket[2 * UVC_NSYM * UVC_NUM_BUCKETS];
+    uint16_t need2[UVC_K4_LIST];
 };
 enum { UVC_cDP1 = 0, UVC_cDP12 = 1, UVC_cDP2 = 2, UVC_cDP3 = 3, UVC_cDPM = 4, UVC_cDPm = 5, UVC_cDP21 = 6, UVC_cDPD = 7 };
 
@@ -1531,8 +1573,9 @@ UVC_HD void k4_touch(K4State & s, int strand, int sym) {
     }
 }
 
-UVC_HD void k4_begin(K4State & s, const BatchView & v, int64_t gp) {
+UVC_HD void k4_begin(K4State & s, K4Arrays & arr, const BatchView & v, int64_t gp) {
     const TileInfo & T = v.tiles[v.pos_tile[gp]];
+    s.facc = arr.facc; s.bucket = arr.bucket; s.need2 = arr.need2;
     s.T = &T; s.gp = gp;
     s.p = (int32_t)(gp - T.pos_off) + T.ext_beg;
     const int64_t po = T.pos_off - T.ext_beg;
@@ -1807,7 +1850,8 @@ UVC_HD void k4_end(K4State & s, const BatchView & v) {
 
 UVC_HD void k4_position(const BatchView & v, int64_t gp, const Win & w) {
     K4State s;
-    k4_begin(s, v, gp);
+    K4Arrays arr;
+    k4_begin(s, arr, v, gp);
     const int32_t p = s.p;
     for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
         if (ri < w.lo || ri >= w.hi) { continue; }
