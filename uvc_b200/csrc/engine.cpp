@@ -343,19 +343,32 @@ UVC_DEFINE_KERNEL(uvc_kf_fragment_columns, uvc::kf_fragment_column(v, i))
 UVC_DEFINE_KERNEL(uvc_k3a_fragment_stats, uvc::k3a_fragment(v, i))
 UVC_DEFINE_KERNEL(uvc_km_family_columns, uvc::km_family_column(v, i))
 UVC_DEFINE_KERNEL(uvc_k4a_family_ends, uvc::k4a_family_strand(v, i))
-// K3b: the compact per-read fragment records (ReadFrag, 32 B, written by K3a) of 32 reads are staged per warp (asynchronously, one chunk
-// ahead); every lane then gathers its own column entry of each read of the chunk in groups of 8 independent loads. The quality histograms of
-// the two hot symbols live in shared memory ([bucket][thread]: conflict-free), their depth counters in registers.
-struct __align__(16) K3bStage {
-    ReadFrag q[2][UVC_STAGE_READS];
-    FragCol e[UVC_STAGE_READS][32];
+// ---- column-entry pipeline of K3b and K4
+// Both kernels walk the warp's union window in chunks of UVC_COL_READS reads. Per chunk a warp needs (1) the compact 32-byte records of the
+// reads and (2) for every lane the 8-byte column entry of each read at the lane's position. Both are fetched with cp.async: records two chunks
+// ahead (ring of 3), entries one chunk ahead (ring of 2, issued as soon as the chunk's records have landed), so the entry loads of chunk
+// i + 1 are in flight during all of the work on chunk i. Commit order: R0 R1 E0 | R2 E1 | R3 E2 | ...; waiting for "all but the most recent
+// group" after committing R(i+2) guarantees R(i+1) and E(i).
+#define UVC_COL_READS 16
+__device__ __forceinline__ void uvc_cp_async8(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+template <class Q> struct __align__(16) ColStage {
+    Q q[3][UVC_COL_READS];
+    FragCol e[2][UVC_COL_READS][32];
 };
+__device__ __forceinline__ int uvc_chunk_len(int64_t cb, int64_t uhi) { return (int)(uhi - cb < UVC_COL_READS ? uhi - cb : UVC_COL_READS); }
+
+// K3b: records = ReadFrag (written by K3a). The quality histograms of the two hot symbols live in shared memory ([bucket][thread]: conflict-free,
+// updated with reductions), their depth counters in registers.
 __global__ void __launch_bounds__(128) uvc_k3b_fragment_consensus(const BatchView v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
+    typedef ColStage<ReadFrag> Stage;
     const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    K3bStage & S = ((K3bStage*)uvc_smem)[warp];
-    int32_t *hot_buckets = (int32_t*)(uvc_smem + 4 * sizeof(K3bStage)) + threadIdx.x;
+    Stage & S = ((Stage*)uvc_smem)[warp];
+    int32_t *hot_buckets = (int32_t*)(uvc_smem + 4 * sizeof(Stage)) + threadIdx.x;
     const bool active = (gp < n);
     uvc::Win w;
     uvc_warp_window(v, gp, active, w);
@@ -365,56 +378,53 @@ __global__ void __launch_bounds__(128) uvc_k3b_fragment_consensus(const BatchVie
     if (active) { uvc::k3b_begin(st, arr, v, gp, hot_buckets, 128); }
     const int32_t p = st.p;
     const int64_t c0 = w.ulo & ~(int64_t)3;
-    if (c0 < w.uhi) { uvc_warp_stage_async(S.q[0], v.rfrag, c0, (int)(w.uhi - c0 < UVC_STAGE_READS ? w.uhi - c0 : UVC_STAGE_READS), lane); }
-    uvc_cp_async_commit();
-    int buf = 0;
-    for (int64_t cb = c0; cb < w.uhi; cb += UVC_STAGE_READS, buf ^= 1) {
-        const int nc = (int)(w.uhi - cb < UVC_STAGE_READS ? w.uhi - cb : UVC_STAGE_READS);
-        const int64_t nb = cb + UVC_STAGE_READS;
-        if (nb < w.uhi) { uvc_warp_stage_async(S.q[buf ^ 1], v.rfrag, nb, (int)(w.uhi - nb < UVC_STAGE_READS ? w.uhi - nb : UVC_STAGE_READS), lane); }
+    auto issue_records = [&](int64_t cb, int slot) { if (cb < w.uhi) { uvc_warp_stage_async(S.q[slot], v.rfrag, cb, uvc_chunk_len(cb, w.uhi), lane); } uvc_cp_async_commit(); };
+    auto issue_entries = [&](int64_t cb, int rslot, int eslot) {
+        if (cb < w.uhi && active) {
+            const int nc = uvc_chunk_len(cb, w.uhi);
+            for (int k = 0; k < nc; k++) {
+                const int64_t ri = cb + k;
+                const ReadFrag & q = S.q[rslot][k];
+                if (ri >= w.lo && ri < w.hi && q.rend > p && q.fragprev_maxrend <= p) { uvc_cp_async8(&S.e[eslot][k][lane], v.fcol + (q.col_base + p)); }
+            }
+        }
         uvc_cp_async_commit();
+    };
+    issue_records(c0, 0);
+    issue_records(c0 + UVC_COL_READS, 1);
+    uvc_cp_async_wait<1>();
+    __syncwarp();
+    issue_entries(c0, 0, 0);
+    int i = 0;
+    for (int64_t cb = c0; cb < w.uhi; cb += UVC_COL_READS, i++) {
+        const int rs = i % 3, es = i & 1;
+        issue_records(cb + 2 * UVC_COL_READS, (i + 2) % 3);
         uvc_cp_async_wait<1>();
         __syncwarp();
-        const ReadFrag *sq = S.q[buf];
-        for (int k0 = 0; k0 < nc; k0 += 8) {
-            FragCol ent[8];
-            #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int k = (k0 + j < nc ? k0 + j : nc - 1);
-                const int64_t ri = cb + k;
-                const ReadFrag & q = sq[k];
-                const bool want = (active && ri >= w.lo && ri < w.hi && q.rend > p && q.fragprev_maxrend <= p);
-                ent[j] = v.fcol[want ? q.col_base + p : 0];
-            }
-            #pragma unroll
-            for (int j = 0; j < 8; j++) { S.e[k0 + j][lane] = ent[j]; }
-        }
+        issue_entries(cb + UVC_COL_READS, (i + 1) % 3, es ^ 1);
         if (active) {
+            const int nc = uvc_chunk_len(cb, w.uhi);
             for (int k = 0; k < nc; k++) {
                 const int64_t ri = cb + k;
                 if (ri < w.lo || ri >= w.hi) { continue; }
-                const ReadFrag q = sq[k];
+                const ReadFrag q = S.q[rs][k];
                 if (q.rend <= p || q.fragprev_maxrend > p) { continue; }
-                uvc::k3b_read(st, v, q, S.e[k][lane]);
+                uvc::k3b_read(st, v, q, S.e[es][k][lane]);
             }
         }
         __syncwarp();
     }
+    uvc_cp_async_wait<0>();
     if (active) { uvc::k3b_end(st, v); }
 }
-// K4: the compact per-read family records (ReadFam, 32 B) of 32 reads are staged per warp (asynchronously, one chunk ahead); every lane then
-// gathers its own column entry of each read of the chunk with independent loads (consecutive lanes = consecutive addresses of one column) before
-// the per-read work runs from shared memory. Entries of single-fragment family-strands are the 8-byte fragment entries; the 32-byte entries of
-// multi-fragment (UMI) families are read in place.
-struct __align__(16) K4Stage {
-    ReadFam q[2][UVC_STAGE_READS];
-    FragCol e[UVC_STAGE_READS][32];
-};
+// K4: records = ReadFam (built on the host). Entries of single-fragment family-strands are the 8-byte fragment entries, fetched through the
+// pipeline; the 32-byte entries of multi-fragment (UMI) families are read in place.
 __global__ void __launch_bounds__(128) uvc_k4_family_consensus(const BatchView v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
+    typedef ColStage<ReadFam> Stage;
     const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    K4Stage & S = ((K4Stage*)uvc_smem)[warp];
+    Stage & S = ((Stage*)uvc_smem)[warp];
     const bool active = (gp < n);
     uvc::Win w;
     uvc_warp_window(v, gp, active, w);
@@ -424,52 +434,61 @@ __global__ void __launch_bounds__(128) uvc_k4_family_consensus(const BatchView v
     if (active) { uvc::k4_begin(st, arr, v, gp); }
     const int32_t p = st.p;
     const int64_t c0 = w.ulo & ~(int64_t)3;
-    for (int pass = 0; pass < 2; pass++) {
-        if (pass == 1) {
-            if (active) { uvc::k4_loop2_listed(st, v, w); }
-            if (!__any_sync(0xffffffffu, active && st.n_need2 > UVC_K4_LIST)) { break; }
+    auto issue_records = [&](int64_t cb, int slot) { if (cb < w.uhi) { uvc_warp_stage_async(S.q[slot], v.rfam, cb, uvc_chunk_len(cb, w.uhi), lane); } uvc_cp_async_commit(); };
+    auto issue_entries = [&](int64_t cb, int rslot, int eslot) {
+        if (cb < w.uhi && active) {
+            const int nc = uvc_chunk_len(cb, w.uhi);
+            for (int k = 0; k < nc; k++) {
+                const int64_t ri = cb + k;
+                const ReadFam & q = S.q[rslot][k];
+                // a read of this lane's own window, first read of its (family, strand) at p, single-fragment strand
+                if (ri >= w.lo && ri < w.hi && q.rend > p && q.famprev_maxrend <= p && (q.flags & UVC_RF_DIRECT)) { uvc_cp_async8(&S.e[eslot][k][lane], v.fcol + (q.col_base + p)); }
+            }
         }
-        if (c0 < w.uhi) { uvc_warp_stage_async(S.q[0], v.rfam, c0, (int)(w.uhi - c0 < UVC_STAGE_READS ? w.uhi - c0 : UVC_STAGE_READS), lane); }
         uvc_cp_async_commit();
-        int buf = 0;
-        for (int64_t cb = c0; cb < w.uhi; cb += UVC_STAGE_READS, buf ^= 1) {
-            const int nc = (int)(w.uhi - cb < UVC_STAGE_READS ? w.uhi - cb : UVC_STAGE_READS);
-            const int64_t nb = cb + UVC_STAGE_READS;
-            if (nb < w.uhi) { uvc_warp_stage_async(S.q[buf ^ 1], v.rfam, nb, (int)(w.uhi - nb < UVC_STAGE_READS ? w.uhi - nb : UVC_STAGE_READS), lane); }
-            uvc_cp_async_commit();
+    };
+    // ---- loop 1 (with the share of loop 2 that needs nothing from other families)
+    issue_records(c0, 0);
+    issue_records(c0 + UVC_COL_READS, 1);
+    uvc_cp_async_wait<1>();
+    __syncwarp();
+    issue_entries(c0, 0, 0);
+    int i = 0;
+    for (int64_t cb = c0; cb < w.uhi; cb += UVC_COL_READS, i++) {
+        const int rs = i % 3, es = i & 1;
+        issue_records(cb + 2 * UVC_COL_READS, (i + 2) % 3);
+        uvc_cp_async_wait<1>();
+        __syncwarp();
+        issue_entries(cb + UVC_COL_READS, (i + 1) % 3, es ^ 1);
+        if (active) {
+            const int nc = uvc_chunk_len(cb, w.uhi);
+            for (int k = 0; k < nc; k++) {
+                const int64_t ri = cb + k;
+                if (ri < w.lo || ri >= w.hi) { continue; }
+                const ReadFam q = S.q[rs][k];
+                if (q.rend <= p || q.famprev_maxrend > p) { continue; }
+                uvc::k4_loop1_read(st, v, q, (q.flags & UVC_RF_DIRECT) ? uvc::famcol_from_frag(S.e[es][k][lane], v.par) : v.mcol[q.col_base + p], ri - w.lo);
+            }
+        }
+        __syncwarp();
+    }
+    uvc_cp_async_wait<0>();
+    // ---- loop 2 for what is left: the short list first; positions whose list overflowed (UMI data) walk the window again
+    if (active) { uvc::k4_loop2_listed(st, v, w); }
+    if (__any_sync(0xffffffffu, active && st.n_need2 > UVC_K4_LIST)) {
+        __syncwarp();
+        issue_records(c0, 0);
+        i = 0;
+        for (int64_t cb = c0; cb < w.uhi; cb += UVC_COL_READS, i++) {
+            issue_records(cb + UVC_COL_READS, (i + 1) & 1);
             uvc_cp_async_wait<1>();
             __syncwarp();
-            const ReadFam *sq = S.q[buf];
-            if (pass == 0) {
-                // gather in groups of 8 reads: the 8 entry loads of a group are issued before the first one is consumed. A lane fetches the
-                // entry of a read that lies in its own window, is the first read of its (family, strand) at p and belongs to a single-fragment strand.
-                for (int k0 = 0; k0 < nc; k0 += 8) {
-                    FragCol ent[8];
-                    #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const int k = (k0 + j < nc ? k0 + j : nc - 1);
-                        const int64_t ri = cb + k;
-                        const ReadFam & q = sq[k];
-                        const bool want = (active && ri >= w.lo && ri < w.hi && q.rend > p && q.famprev_maxrend <= p && (q.flags & UVC_RF_DIRECT));
-                        ent[j] = v.fcol[want ? q.col_base + p : 0];
-                    }
-                    #pragma unroll
-                    for (int j = 0; j < 8; j++) { S.e[k0 + j][lane] = ent[j]; }
-                }
-                if (active) {
-                    for (int k = 0; k < nc; k++) {
-                        const int64_t ri = cb + k;
-                        if (ri < w.lo || ri >= w.hi) { continue; }
-                        const ReadFam q = sq[k];
-                        if (q.rend <= p || q.famprev_maxrend > p) { continue; }
-                        uvc::k4_loop1_read(st, v, q, (q.flags & UVC_RF_DIRECT) ? uvc::famcol_from_frag(S.e[k][lane], v.par) : v.mcol[q.col_base + p], ri - w.lo);
-                    }
-                }
-            } else if (active && st.n_need2 > UVC_K4_LIST) {
+            if (active && st.n_need2 > UVC_K4_LIST) {
+                const int nc = uvc_chunk_len(cb, w.uhi);
                 for (int k = 0; k < nc; k++) {
                     const int64_t ri = cb + k;
                     if (ri < w.lo || ri >= w.hi) { continue; }
-                    const ReadFam & q = sq[k];
+                    const ReadFam q = S.q[i & 1][k];
                     if (q.rend <= p) { continue; }
                     uvc::k4_loop2_read(st, v, q);
                 }
@@ -550,8 +569,8 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     UVC_STAGE(uvc_kf_fragment_columns, v.n_fcol)
     UVC_STAGE(uvc_k3a_fragment_stats, v.n_frags)
     if (v.n_pos > 0) {
-        static_assert(sizeof(K3bStage) % 16 == 0, "per-warp staging slots keep 16-byte alignment");
-        const size_t smem = 4 * sizeof(K3bStage) + 2 * UVC_NUM_BUCKETS * 128 * sizeof(int32_t);
+        static_assert(sizeof(ColStage<ReadFrag>) % 16 == 0, "per-warp staging slots keep 16-byte alignment");
+        const size_t smem = 4 * sizeof(ColStage<ReadFrag>) + 2 * UVC_NUM_BUCKETS * 128 * sizeof(int32_t);
         UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k3b_fragment_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         uvc_k3b_fragment_consensus<<<(unsigned)((v.n_pos + 127) / 128), 128, smem, ctx->stream>>>(v, v.n_pos);
         launches++;
@@ -560,8 +579,8 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     UVC_STAGE(uvc_km_family_columns, v.n_mcol)
     UVC_STAGE(uvc_k4a_family_ends, 2 * v.n_fams)
     if (v.n_pos > 0) {
-        static_assert(sizeof(K4Stage) % 16 == 0, "per-warp staging slots keep 16-byte alignment");
-        const size_t smem = 4 * sizeof(K4Stage);
+        static_assert(sizeof(ColStage<ReadFam>) % 16 == 0, "per-warp staging slots keep 16-byte alignment");
+        const size_t smem = 4 * sizeof(ColStage<ReadFam>);
         UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k4_family_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         uvc_k4_family_consensus<<<(unsigned)((v.n_pos + 127) / 128), 128, smem, ctx->stream>>>(v, v.n_pos);
         launches++;
