@@ -204,7 +204,9 @@ UVC_DEFINE_KERNEL(uvc_k0_read_consts, uvc::k0_read(v, i))
 // A warp walks its union window in chunks of UVC_STAGE_READS reads. Chunk bases are multiples of 4 reads, so that every record array slice
 // starts on a 16-byte boundary (record sizes are multiples of 4 bytes) and is copied with 16-byte asynchronous copies; the copy of chunk
 // i + 1 is in flight while chunk i is processed.
-#define UVC_STAGE_READS 32
+#ifndef UVC_STAGE_READS
+#define UVC_STAGE_READS 24    // a multiple of 8 (gather groups) and of 4 (16-byte slices)
+#endif
 __device__ __forceinline__ void uvc_cp_async16(void *smem_dst, const void *gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
@@ -251,7 +253,10 @@ struct __align__(16) K2Stage {
     ReadDerived D[2][UVC_STAGE_READS];           // 32 records = 3200 bytes: every buffer starts on a 16-byte boundary
     uint16_t bq[UVC_STAGE_READS][32];
 };
-__global__ void __launch_bounds__(128) uvc_k2_bias_pileup(const BatchView v, int64_t n) {
+#ifndef UVC_K2_MINBLOCKS
+#define UVC_K2_MINBLOCKS 4    // 128 registers: four blocks per SM together with 24-read staging chunks
+#endif
+__global__ void __launch_bounds__(128, UVC_K2_MINBLOCKS) uvc_k2_bias_pileup(const BatchView v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gp = (i / 128) * 64 + (i % 64);
