@@ -128,6 +128,12 @@ struct FamCol {
     uint32_t mmm_cc[2], mmm_tot[2];
 };
 
+// per-chunk bit masks of the fragment columns: what the whole-fragment and whole-family scans (K3a, K4c) look for, so that they read 16 bytes per
+// 32 positions instead of 32 entries and 32 reference symbols
+#define UVC_FM_COV 0               // the fragment says something here (link_cc | base_tc)
+#define UVC_FM_MUT_LINK 1          // link consensus present and mutated w.r.t. the reference
+#define UVC_FM_MUT_BASE_HQ 2       // base consensus mutated and 2 * cc - tc >= bias_thres_highBQ
+#define UVC_FM_MUT_BASE_ANY 3      // base consensus mutated and 2 * cc - tc > 0
 #define UVC_COL_CHUNK 32           // column entries are laid out in chunks of one warp; a chunk belongs to one fragment / (family, strand)
 
 struct FamRec {
@@ -202,6 +208,7 @@ struct BatchView {
     FragCol *fcol;
     FamCol *mcol;
     const int32_t *fchunk_frag;    // [n_fcol / 32] fragment that owns each chunk of fcol
+    uint32_t *fmask;               // [n_fcol / 32][4] per chunk of fcol, one bit per entry (kernel KF): UVC_FM_*
     const int32_t *mchunk_fs;      // [n_mcol / 32] 2 * family + strand that owns each chunk of mcol
     // per-position state
     uvcgpu_prep_set *prep;

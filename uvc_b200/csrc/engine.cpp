@@ -344,7 +344,15 @@ __global__ void __launch_bounds__(128) uvc_k1_prep_thres(const BatchView v, int6
     if (active) { uvc::k1_end(st, v); }
 }
 UVC_DEFINE_KERNEL(uvc_k2e_indel_events, uvc::k2e_event(v, i))
-UVC_DEFINE_KERNEL(uvc_kf_fragment_columns, uvc::kf_fragment_column(v, i))
+// KF: a warp is one 32-entry chunk of one fragment's column; the chunk's four bit masks are four ballots
+__global__ void __launch_bounds__(128) uvc_kf_fragment_columns(const BatchView v, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // n is a multiple of 32: whole warps are in or out
+    if (i >= n) { return; }
+    const uint32_t bits = uvc::kf_fragment_column(v, i);
+    const uint32_t m0 = __ballot_sync(0xffffffffu, bits & 1u), m1 = __ballot_sync(0xffffffffu, bits & 2u);
+    const uint32_t m2 = __ballot_sync(0xffffffffu, bits & 4u), m3 = __ballot_sync(0xffffffffu, bits & 8u);
+    if (0 == (threadIdx.x & 31)) { *(uint4*)(v.fmask + (i / UVC_COL_CHUNK) * 4) = make_uint4(m0, m1, m2, m3); }
+}
 UVC_DEFINE_KERNEL(uvc_k3a_fragment_stats, uvc::k3a_fragment(v, i))
 UVC_DEFINE_KERNEL(uvc_km_family_columns, uvc::km_family_column(v, i))
 UVC_DEFINE_KERNEL(uvc_k4a_family_ends, uvc::k4a_family_strand(v, i))
@@ -658,7 +666,7 @@ static int backend_run(uvcgpu_ctx *, BatchState & bs) {
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k1_position(v, i, w); }
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k2_position(v, i, 0, w); uvc::k2_position(v, i, 1, w); }
     for (int64_t i = 0; i < v.n_ev; i++) { uvc::k2e_event(v, i); }
-    for (int64_t i = 0; i < v.n_fcol; i++) { uvc::kf_fragment_column(v, i); }
+    for (int64_t i = 0; i < v.n_fcol; i++) { uvc::kf_fold_bits(v, i, uvc::kf_fragment_column(v, i)); }
     for (int64_t i = 0; i < v.n_frags; i++) { uvc::k3a_fragment(v, i); }
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k3b_position(v, i, w); }
     for (int64_t i = 0; i < v.n_mcol; i++) { uvc::km_family_column(v, i); }
@@ -933,6 +941,7 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
     UVC_UP(mchunk_fs, int32_t, hb.mchunk_fs)
     v.n_fcol = hb.n_fcol; v.n_mcol = hb.n_mcol;
     { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_fcol * sizeof(FragCol), false)); v.fcol = (FragCol*)d_; }
+    UVC_ZERO(fmask, uint32_t, (v.n_fcol / UVC_COL_CHUNK) * 4)
     { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_mcol * sizeof(FamCol), false)); v.mcol = (FamCol*)d_; }
     UVC_ZERO(rd, ReadDerived, v.n_reads)
     UVC_ZERO(rfrag, ReadFrag, v.n_reads)

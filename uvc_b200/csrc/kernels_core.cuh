@@ -29,6 +29,20 @@ namespace uvc {
 template <class T> UVC_HD T tmin(T a, T b) { return a < b ? a : b; }
 template <class T> UVC_HD T tmax(T a, T b) { return a > b ? a : b; }
 UVC_HD int32_t nnminus(int32_t a, int32_t b) { return (a > b ? a - b : 0); }
+UVC_HD int32_t __popc_u32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+UVC_HD int32_t __ctz_u32(uint32_t x) {   // x != 0
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
 UVC_HD int32_t iabs(int32_t a) { return a < 0 ? -a : a; }
 UVC_HD int32_t between(int32_t v, int32_t lo, int32_t hi) { return tmin(tmax(lo, v), hi); }
 
@@ -1101,24 +1115,42 @@ UVC_HD int32_t indel_majority_of_reads(const BatchView & v, const int32_t *reads
 // The reference rebuilds the per-fragment symbol array three times (walks #3, #4, #5). Here it is evaluated once per (fragment, position):
 // a warp owns 32 consecutive positions of ONE fragment, so the fragment's read records are warp-uniform and its base qualities are read
 // as consecutive bytes; the entry keeps only what fillConsensusCounts (main.hpp:374-417) yields for the two symbol types.
-UVC_HD void kf_fragment_column(const BatchView & v, int64_t i) {
+// Returns the entry's UVC_FM_* bits; the caller folds the 32 results of a chunk into v.fmask (one ballot per mask in the CUDA kernel).
+UVC_HD uint32_t kf_fragment_column(const BatchView & v, int64_t i) {
     const FragRec & G = v.frags[v.fchunk_frag[i / UVC_COL_CHUNK]];
     const int32_t o = (int32_t)(i - G.col_off);
-    if (o >= G.hi - G.lo) { return; }
+    if (o >= G.hi - G.lo) { return 0; }
     const int32_t p = G.lo + o;
     const TileInfo & T = v.tiles[G.tile];
+    const int64_t gp = T.pos_off + (p - T.ext_beg);
     FragCol e;
     e.link_cc = 0; e.base_cc = 0; e.base_tc = 0; e.link_sym = UVC_LINK_NN; e.base_sym = UVC_BASE_NN;
+    uint32_t bits = 0;
     if (frag_covers(v, G, p)) {
         int32_t c[UVC_NSYM];
-        frag_votes(v, G, p, T.pos_off + (p - T.ext_beg), c);
+        frag_votes(v, G, p, gp, c);
         int a; int32_t cc, tc;
         link_consensus(c, true, a, cc, tc);
         e.link_sym = (uint8_t)(a | ((c[UVC_BASE_N] | c[UVC_BASE_NN]) ? 0x80 : 0)); e.link_cc = (uint16_t)cc;
+        const int ref = v.refsym[gp];
+        if (e.link_cc > 0 && symbols_mutated(ref, a)) { bits |= (1u << UVC_FM_MUT_LINK); }
         base_consensus(c, false, a, cc, tc);
         e.base_sym = (uint8_t)a; e.base_cc = (uint16_t)cc; e.base_tc = (uint16_t)tc;
+        // (the stored counts are 16-bit: the tests below use them as every later kernel reads them)
+        const int32_t con_qual = (int32_t)e.base_cc * 2 - (int32_t)e.base_tc;
+        if (e.base_tc > 0 && symbols_mutated(ref, a)) {
+            if (con_qual >= v.par.bias_thres_highBQ) { bits |= (1u << UVC_FM_MUT_BASE_HQ); }
+            if (con_qual > 0) { bits |= (1u << UVC_FM_MUT_BASE_ANY); }
+        }
+        if (e.link_cc | e.base_tc) { bits |= (1u << UVC_FM_COV); }
     }
     v.fcol[i] = e;
+    return bits;
+}
+// folds one entry's bits into the chunk masks (emulation / non-ballot path)
+UVC_HD void kf_fold_bits(const BatchView & v, int64_t i, uint32_t bits) {
+    uint32_t *m = v.fmask + (i / UVC_COL_CHUNK) * 4;
+    for (int k = 0; k < 4; k++) { if ((bits >> k) & 1u) { m[k] |= (1u << (uint32_t)(i % UVC_COL_CHUNK)); } }
 }
 
 // the fragment's entry at p (zero entry outside its covered extent)
@@ -1132,53 +1164,66 @@ UVC_HD FragCol frag_entry(const BatchView & v, const FragRec & G, int32_t p) {
 // +-syserr_mut_region_n_bases of a high-quality mutation, and the fragment's string of mutations (haplotype evidence).
 UVC_HD void k3a_fragment(const BatchView & v, int64_t fi) {
     FragRec & G = v.frags[fi];
-    const TileInfo & T = v.tiles[G.tile];
     const uvcgpu_params & par = v.par;
-    const int64_t po = T.pos_off - T.ext_beg;
     const int32_t lo = G.lo, hi = G.hi;
     const int32_t nb = par.syserr_mut_region_n_bases;
+    const int64_t c0 = G.col_off / UVC_COL_CHUNK;
+    const int32_t n_chunks = (hi - lo + UVC_COL_CHUNK - 1) / UVC_COL_CHUNK;
+    const uint32_t *fm = v.fmask + c0 * 4;
     int32_t n_cov = 0, n_near = 0, n_mut_entries = 0;
-    uint32_t hist = 0;                 // coverage flags of the previous nb positions (bit k = position p-1-k)
-    int32_t near_until = lo - nb - 2;  // positions <= near_until are within nb to the right of a mutation
-    for (int pass = 0; pass < 2; pass++) {
-        int32_t out = -1;
-        if (pass == 1) {
-            if (n_mut_entries <= 1) { break; }
-            out = rec_alloc(v, 4 + 2 * n_mut_entries);
-            if (out < 0) { break; }
+    if (nb >= 0 && nb <= 32) {
+        // n_near = covered positions within nb of a mutated position (each counted once, main.hpp:2747-2756): the covered bits of the mutation
+        // mask dilated by nb to both sides, evaluated chunk by chunk on a 96-bit window (previous | current | next chunk)
+        uint32_t prev = 0, cur = (n_chunks > 0 ? (fm[UVC_FM_MUT_LINK] | fm[UVC_FM_MUT_BASE_HQ]) : 0u);
+        for (int32_t c = 0; c < n_chunks; c++) {
+            const uint32_t *m = fm + c * 4;
+            const uint32_t nxt = (c + 1 < n_chunks ? (m[4 + UVC_FM_MUT_LINK] | m[4 + UVC_FM_MUT_BASE_HQ]) : 0u);
+            n_cov += __popc_u32(m[UVC_FM_COV]);
+            n_mut_entries += __popc_u32(m[UVC_FM_MUT_LINK]) + __popc_u32(m[UVC_FM_MUT_BASE_HQ]);
+            if (prev | cur | nxt) {
+                const uint64_t lowmid = (uint64_t)prev | ((uint64_t)cur << 32);      // bit 32 + k = position k of the current chunk
+                const uint64_t midhigh = (uint64_t)cur | ((uint64_t)nxt << 32);      // bit k = position k of the current chunk
+                uint64_t right = 0, left = 0;                                        // mutations reaching up (p .. p + nb) / down (p - nb .. p - 1)
+                for (int32_t k = 0; k <= nb; k++) { right |= (lowmid << k); }
+                for (int32_t k = 1; k <= nb; k++) { left |= (midhigh >> k); }
+                const uint32_t near = (uint32_t)(right >> 32) | (uint32_t)left;
+                n_near += __popc_u32(near & m[UVC_FM_COV]);
+            }
+            prev = cur; cur = nxt;
+        }
+    } else {
+        // (general nb: the plain scan over the entries)
+        uint32_t hist = 0;
+        int32_t near_until = lo - nb - 2;
+        for (int32_t p = lo; p < hi; p++) {
+            const uint32_t *m = fm + ((p - lo) / UVC_COL_CHUNK) * 4;
+            const uint32_t bit = 1u << (uint32_t)((p - lo) % UVC_COL_CHUNK);
+            const bool cov = (m[UVC_FM_COV] & bit), mut = ((m[UVC_FM_MUT_LINK] | m[UVC_FM_MUT_BASE_HQ]) & bit);
+            n_mut_entries += ((m[UVC_FM_MUT_LINK] & bit) ? 1 : 0) + ((m[UVC_FM_MUT_BASE_HQ] & bit) ? 1 : 0);
+            if (mut) {
+                const int32_t uncounted = tmin(nb, tmax(0, p - 1 - near_until));
+                if (uncounted > 0) { n_near += __popc_u32(hist & ((uncounted >= 32) ? 0xffffffffu : ((1u << uncounted) - 1u))); }
+                near_until = p + nb;
+            }
+            if (cov) { n_cov++; if (p <= near_until) { n_near++; } }
+            hist = ((hist << 1) | (cov ? 1u : 0u)) & ((nb >= 32) ? 0xffffffffu : ((1u << nb) - 1u));
+        }
+    }
+    // the fragment's haplotype string: its mutated high-quality consensus symbols in position order, link before base (main.hpp:2766-2800)
+    if (n_mut_entries > 1) {
+        int32_t out = rec_alloc(v, 4 + 2 * n_mut_entries);
+        if (out >= 0) {
             v.rec_buf[out] = UVC_REC_HAP_BQ; v.rec_buf[out + 1] = G.strand; v.rec_buf[out + 2] = n_mut_entries; v.rec_buf[out + 3] = (int32_t)fi;
             out += 4;
-        }
-        for (int32_t p = lo; p < hi; p++) {
-            const FragCol e = v.fcol[G.col_off + (p - lo)];
-            bool cov = false, mut = false;
-            if (e.link_cc | e.base_tc) {
-                const int ref = v.refsym[po + p];
-                for (int type = 1; type >= 0; type--) { // SYMBOL_TYPES_IN_VCF_ORDER: link first
-                    const int con = (type == 1 ? (e.link_sym & 0xf) : e.base_sym);
-                    const int32_t cc = (type == 1 ? e.link_cc : e.base_cc), tc = (type == 1 ? e.link_cc : e.base_tc);
-                    if (0 == tc) { continue; }
-                    cov = true;
-                    const int32_t con_qual = cc * 2 - tc;
-                    const bool high = ((type == 1) || con_qual >= par.bias_thres_highBQ);
-                    if (symbols_mutated(ref, con) && high) {
-                        mut = true;
-                        if (pass == 0) { n_mut_entries++; } else { v.rec_buf[out] = p; v.rec_buf[out + 1] = con; out += 2; }
-                    }
+            for (int32_t c = 0; c < n_chunks; c++) {
+                const uint32_t *m = fm + c * 4;
+                for (uint32_t todo = (m[UVC_FM_MUT_LINK] | m[UVC_FM_MUT_BASE_HQ]); todo; todo &= todo - 1) {
+                    const int32_t o = c * UVC_COL_CHUNK + __ctz_u32(todo);
+                    const uint32_t bit = todo & (0u - todo);
+                    const FragCol e = v.fcol[G.col_off + o];
+                    if (m[UVC_FM_MUT_LINK] & bit) { v.rec_buf[out] = lo + o; v.rec_buf[out + 1] = (e.link_sym & 0xf); out += 2; }
+                    if (m[UVC_FM_MUT_BASE_HQ] & bit) { v.rec_buf[out] = lo + o; v.rec_buf[out + 1] = e.base_sym; out += 2; }
                 }
-            }
-            if (pass == 0) {
-                if (mut) {
-                    const int32_t uncounted = tmin(nb, tmax(0, p - 1 - near_until));   // left neighbours not yet counted
-                    if (uncounted > 0) {
-                        const uint32_t m = hist & ((uncounted >= 32) ? 0xffffffffu : ((1u << uncounted) - 1u));
-                        int32_t pc = 0; for (uint32_t x = m; x; x &= (x - 1)) { pc++; }
-                        n_near += pc;
-                    }
-                    near_until = p + nb;
-                }
-                if (cov) { n_cov++; if (p <= near_until) { n_near++; } }
-                hist = ((hist << 1) | (cov ? 1u : 0u)) & ((nb >= 32) ? 0xffffffffu : ((1u << nb) - 1u));
             }
         }
     }
@@ -1897,7 +1942,22 @@ UVC_HD void k4c_family_strand(const BatchView & v, int64_t i) {
                 if (out_f2q >= 0) { int32_t *w = v.rec_buf + out_f2q; w[0] = UVC_REC_HAP_F2Q; w[1] = strand; w[2] = n_f2q; w[3] = (int32_t)(i >> 1); out_f2q += 4; }
             }
         }
+        // A strand with a single fragment (every strand of non-UMI data) can only contribute where that fragment's column has a mutated
+        // consensus: the scan visits the set bits of the fragment's chunk masks instead of every position.
+        const bool by_mask = (F.direct_frag[strand] >= 0);
+        const FragRec *Gd = (by_mask ? &v.frags[F.direct_frag[strand]] : NULL);
+        const uint32_t *fm = (by_mask ? v.fmask + (Gd->col_off / UVC_COL_CHUNK) * 4 : NULL);
+        const int32_t n_chunks = (by_mask ? (Gd->hi - Gd->lo + UVC_COL_CHUNK - 1) / UVC_COL_CHUNK : 0);
+        int32_t chunk = 0;
+        uint32_t todo = ((by_mask && n_chunks > 0) ? (fm[UVC_FM_MUT_LINK] | fm[UVC_FM_MUT_BASE_ANY]) : 0u);
         for (int32_t p = lo; p < hi; p++) {
+            if (by_mask) {
+                while (0 == todo && chunk + 1 < n_chunks) { chunk++; todo = (fm[chunk * 4 + UVC_FM_MUT_LINK] | fm[chunk * 4 + UVC_FM_MUT_BASE_ANY]); }
+                if (0 == todo) { break; }
+                p = Gd->lo + chunk * UVC_COL_CHUNK + __ctz_u32(todo);
+                todo &= todo - 1;
+                if (p < lo || p >= hi) { continue; }
+            }
             const int64_t gp = po + p;
             const int ref = v.refsym[gp];
             const FamCol m = fam_entry(v, F, strand, p);
