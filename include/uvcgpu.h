@@ -325,6 +325,11 @@ int uvcgpu_release(uvcgpu_ctx *ctx, uvcgpu_ticket ticket);
 
 int uvcgpu_device_count(void);
 
+/* Creates the CUDA context of a device ahead of the first uvcgpu_create (driver and context initialisation take a few hundred milliseconds: a
+ * host program calls this from a helper thread while it parses its inputs; the reference has no counterpart - its per-thread handles are opened
+ * in main.cpp:1297-1319). Returns UVCGPU_OK or UVCGPU_ENODEVICE / UVCGPU_ECUDA. */
+int uvcgpu_device_warmup(int device);
+
 /* sizeof(uvcgpu_params) as the library was compiled, so that foreign-language bindings can verify their mirror of the struct. */
 size_t uvcgpu_sizeof_params(void);
 

@@ -795,6 +795,18 @@ int uvcgpu_device_count(void) {
 #endif
 }
 
+int uvcgpu_device_warmup(int device) {
+#if UVC_CUDA
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { return UVCGPU_ENODEVICE; }
+    if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) { return UVCGPU_ECUDA; }
+    return UVCGPU_OK;
+#else
+    (void)device;
+    return UVCGPU_OK;
+#endif
+}
+
 int uvcgpu_create(uvcgpu_ctx **out, int device, const uvcgpu_params *params) {
     if (NULL == out || NULL == params || params->abi_version != UVCGPU_ABI_VERSION) { return UVCGPU_EINVAL; }
     *out = NULL;

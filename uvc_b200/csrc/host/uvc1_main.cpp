@@ -98,6 +98,7 @@ struct Shared {
     // totals
     std::atomic<int64_t> n_reads_kept{0}, n_positions{0}, n_records{0}, n_batches{0}, n_launches{0};
     std::atomic<int64_t> us_fetch{0}, us_prep{0}, us_gpu_wait{0}, us_score{0}, us_text{0}, us_compress{0};
+    std::atomic<int64_t> t_tiler_open{0}, t_tiler_done{0}, t_ctx_ready{0}, t_first_batch{0};   // --stats timeline (microsecond clock values)
     std::mutex kernel_ms_mutex;
     double kernel_ms = 0;
     void fail(const std::string & msg) {
@@ -220,6 +221,7 @@ void tiler_thread(Shared *sh, int scan_threads) {
     const Options & o = sh->opt;
     uvchost_tiler *t = uvchost_tiler_open(o.bam.c_str(), o.bed.c_str(), o.targets.c_str(), o.threads, o.mem_per_thread, o.bed_in_avg_sequencing_DP, 0);
     if (uvchost_tiler_error(t)[0]) { sh->fail(std::string("tiler: ") + uvchost_tiler_error(t)); uvchost_tiler_close(t); sh->batches.close(); return; }
+    sh->t_tiler_open = now_us();
     std::ofstream bed_out;
     if (!o.bed_out.empty() && o.bed_out != ".") { bed_out.open(o.bed_out.c_str(), std::ios::out); }
     BatchPacker packer(sh);
@@ -238,6 +240,7 @@ void tiler_thread(Shared *sh, int scan_threads) {
     }
     uvchost_tiler_close(t);
     sh->batches.close();
+    sh->t_tiler_done = now_us();
 }
 
 struct Lane {
@@ -252,6 +255,7 @@ void lane_thread(Lane lane) {
     int rc = uvcgpu_create(&ctx, lane.device, &sh->par);
     if (rc != 0) { sh->fail("uvcgpu_create failed on device " + std::to_string(lane.device) + " with code " + std::to_string(rc) + (rc == UVCGPU_ENODEVICE ? " (no CUDA device; there is no CPU fallback)" : "")); return; }
     uvcgpu_set_host_threads(ctx, lane.n_threads);
+    { int64_t z = 0; sh->t_ctx_ready.compare_exchange_strong(z, now_us()); }
     const int n_dec = std::max(1, lane.n_threads);
     std::vector<uvchost_bam*> bams((size_t)n_dec, NULL);
     std::vector<uvchost_readbuf*> rbs((size_t)n_dec, NULL);
@@ -338,6 +342,7 @@ void lane_thread(Lane lane) {
         {
             std::lock_guard<std::mutex> lk(sh->out_mutex);
             sh->done[b.seq].swap(outbytes);
+            { int64_t z = 0; sh->t_first_batch.compare_exchange_strong(z, now_us()); }
         }
         sh->out_cv.notify_all();
     }
@@ -366,6 +371,15 @@ int main(int argc, char **argv) {
     } else { o.fasta = ""; }
     if (o.threads < 1) { o.threads = 1; }
 
+    // the CUDA driver and the device contexts come up on a helper thread while the inputs are inspected and the tiler starts its scan
+    int n_dev = 0;
+    std::thread gpu_warmup([&]() {
+        n_dev = uvcgpu_device_count();
+        const int n = (o.gpus > 0 ? std::min(o.gpus, n_dev) : n_dev);
+        for (int d = 0; d < n; d++) { uvcgpu_device_warmup(d); }
+    });
+    struct Joiner { std::thread & t; ~Joiner() { if (t.joinable()) { t.join(); } } } warmup_joiner{gpu_warmup};
+
     // data-driven inference (CommandLineArgs::selfUpdateByPlatform, CmdLineArgs.cpp:36-136)
     {
         uvchost_bam *b = uvchost_bam_open(o.bam.c_str());
@@ -386,7 +400,10 @@ int main(int argc, char **argv) {
         sh.par.inferred_sequencing_platform = 1;
     }
 
-    const int n_dev = uvcgpu_device_count();
+    const int64_t t_setup = now_us();
+    std::thread tiler(tiler_thread, &sh, std::max(1, std::min(4, std::min(std::max(o.threads, 1), std::max(1, (int)std::thread::hardware_concurrency())) / 2)));
+    struct TilerGuard { Shared & sh; std::thread & t; ~TilerGuard() { if (t.joinable()) { sh.failed.store(true); sh.batches.abort(); t.join(); } } } tiler_guard{sh, tiler};   // early returns below
+    gpu_warmup.join();
 #ifdef UVC_EMU_HOST
     const int n_gpus = 1;
     (void)n_dev;
@@ -412,7 +429,6 @@ int main(int argc, char **argv) {
         else if (fout) { std::string z; uvchost_bgzf_compress(z, header.data(), header.size(), o.compress_level, 1); fwrite(z.data(), 1, z.size(), fout); }
     }
 
-    std::thread tiler(tiler_thread, &sh, std::max(1, std::min(4, cpu_budget / 2)));
     std::vector<std::thread> lanes;
     for (int k = 0; k < n_lanes; k++) {
         Lane l; l.sh = &sh; l.device = k % n_gpus; l.n_threads = threads_per_lane; l.index = k;
@@ -451,10 +467,13 @@ int main(int argc, char **argv) {
     if (o.stats) {
         fprintf(stderr, "uvc1-b200 stats: gpus=%d lanes=%d threads_per_lane=%d batches=%lld reads_kept=%lld positions=%lld records=%lld launches=%lld kernel_ms=%.1f\n"
                         "uvc1-b200 stage seconds summed over lanes: decode=%.2f stage+h2d=%.2f gpu_wait=%.2f score=%.2f text=%.2f compress=%.2f\n"
+                        "uvc1-b200 timeline seconds since start: inference+header %.2f, first context ready %.2f, tiler open %.2f, first batch out %.2f, tiler done %.2f, all written %.2f\n"
                         "uvc1-b200 throughput: %.0f reads/s %.0f positions/s\n",
                 n_gpus, n_lanes, threads_per_lane, (long long)sh.n_batches.load(), (long long)sh.n_reads_kept.load(), (long long)sh.n_positions.load(), (long long)sh.n_records.load(),
                 (long long)sh.n_launches.load(), sh.kernel_ms,
                 sh.us_fetch / 1e6, sh.us_prep / 1e6, sh.us_gpu_wait / 1e6, sh.us_score / 1e6, sh.us_text / 1e6, sh.us_compress / 1e6,
+                (t_setup - t_start) / 1e6, (sh.t_ctx_ready.load() - t_start) / 1e6, (sh.t_tiler_open.load() - t_start) / 1e6, (sh.t_first_batch.load() - t_start) / 1e6,
+                (sh.t_tiler_done.load() - t_start) / 1e6, wall,
                 sh.n_reads_kept.load() / wall, sh.n_positions.load() / wall);
     }
     fprintf(stderr, "CPU time used: %.2f seconds\nWall clock time passed: %.2f seconds\n", (double)(clock() - c_start) / CLOCKS_PER_SEC, wall);
