@@ -180,6 +180,11 @@ def kernel_algorithmic_bytes(stage: int, st, n_reads: int) -> float:
 
 def main():
     args = parse_args()
+    # stdout carries exactly one JSON line: libraries that print to file descriptor 1 (NCCL's version banner, ...) are sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    json_out = os.fdopen(json_fd, "w")
     name = args.config
     scale = args.scale if args.scale is not None else DEFAULT_SCALE.get(name, 1.0)
     rank = int(os.environ.get("RANK", "0"))
@@ -199,7 +204,8 @@ def main():
                 "data": "synthetic", "config": {"workload": workload, "reference_sample": res["sample"]},
                 "cpu_baseline": {"value": res["value"], "unit": "reads/s", "cores": res["cores"], "kind": "reference", "sample": res["sample"]},
                 "e2e": {"value": res["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
         return
 
     import torch
@@ -426,7 +432,8 @@ def main():
                                     "positions_per_s": res["positions_per_s"]}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % e}
-    print(json.dumps(line), flush=True)
+    json_out.write(json.dumps(line) + "\n")
+    json_out.flush()
 
 
 if __name__ == "__main__":
