@@ -375,7 +375,10 @@ __device__ __forceinline__ int uvc_chunk_len(int64_t cb, int64_t uhi) { return (
 
 // K3b: records = ReadFrag (written by K3a). The quality histograms of the two hot symbols live in shared memory ([bucket][thread]: conflict-free,
 // updated with reductions), their depth counters in registers.
-__global__ void __launch_bounds__(128) uvc_k3b_fragment_consensus(const BatchView v, int64_t n) {
+#ifndef UVC_K3B_MINBLOCKS
+#define UVC_K3B_MINBLOCKS 4    // 96 registers, no spills
+#endif
+__global__ void __launch_bounds__(128, UVC_K3B_MINBLOCKS) uvc_k3b_fragment_consensus(const BatchView v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
     typedef ColStage<ReadFrag> Stage;
     const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -432,7 +435,10 @@ __global__ void __launch_bounds__(128) uvc_k3b_fragment_consensus(const BatchVie
 }
 // K4: records = ReadFam (built on the host). Entries of single-fragment family-strands are the 8-byte fragment entries, fetched through the
 // pipeline; the 32-byte entries of multi-fragment (UMI) families are read in place.
-__global__ void __launch_bounds__(128) uvc_k4_family_consensus(const BatchView v, int64_t n) {
+#ifndef UVC_K4_MINBLOCKS
+#define UVC_K4_MINBLOCKS 4     // 128 registers: four blocks per SM
+#endif
+__global__ void __launch_bounds__(128, UVC_K4_MINBLOCKS) uvc_k4_family_consensus(const BatchView v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
     typedef ColStage<ReadFam> Stage;
     const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
