@@ -15,10 +15,10 @@ SECTIONS = ["meta", "families", "rtr_initial", "baq", "baq2", "prep", "thres", "
 IMPLEMENTED_VQ_TAGS = 14   # VQ_a1BQf .. VQ_cIDQr: everything updateByRegion3Aln fills (main_conversion.hpp:743-762)
 
 
-def _check(info, tiles, emulate, tmp_path, extra=()):
+def _check(info, tiles, emulate, tmp_path, extra=(), **params):
     if not pu.have_oracle():
         pytest.skip("oracle/_ref not built")
-    ours, stats = pu.run_tiles(info["bam"], info["fasta"], tiles, emulate, SECTIONS)
+    ours, stats = pu.run_tiles(info["bam"], info["fasta"], tiles, emulate, SECTIONS, **params)
     assert emulate or stats.gpu_launches > 0
     prev = (-1, 0, 0)
     for ti, (tid, beg, end, flag) in enumerate(tiles):
@@ -47,6 +47,23 @@ def test_emulated_pileup_matches_oracle_small(synth_small, tmp_path):
 
 def test_emulated_pileup_matches_oracle_umi(synth_umi, tmp_path):
     _check(synth_umi, [(0, 1000, 2500, 4), (0, 2500, 4000, 2)], True, tmp_path)
+
+
+# Non-default parameters that steer the kernels onto their general paths: a mutation neighbourhood wider than the 32-bit chunk masks
+# (K3a scans bit by bit), and fam_thres_dup1add = 1, with which every single-fragment family enters a quality bucket (K4 runs family loop 2
+# for every family: its need-list overflows and the window is walked a second time, log and all).
+GENERAL_PATH_ARGS = ["--syserr-mut-region-n-bases", "40", "--fam-thres-dup1add", "1"]
+GENERAL_PATH_PARAMS = dict(syserr_mut_region_n_bases=40, fam_thres_dup1add=1)
+
+
+def test_emulated_pileup_general_paths(synth_small, tmp_path):
+    _check(synth_small, [(0, 0, 6000, 4)], True, tmp_path, GENERAL_PATH_ARGS, **GENERAL_PATH_PARAMS)
+
+
+@pytest.mark.gpu
+def test_cuda_pileup_general_paths(synth_small, synth_umi, tmp_path):
+    _check(synth_small, [(0, 0, 6000, 4), (0, 6000, 11995, 2)], False, tmp_path, GENERAL_PATH_ARGS, **GENERAL_PATH_PARAMS)
+    _check(synth_umi, [(0, 1000, 2500, 4)], False, tmp_path, GENERAL_PATH_ARGS, **GENERAL_PATH_PARAMS)
 
 
 @pytest.mark.gpu

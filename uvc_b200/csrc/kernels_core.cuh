@@ -1228,21 +1228,26 @@ UVC_HD void k3a_fragment(const BatchView & v, int64_t fi) {
             prev = cur; cur = nxt;
         }
     } else {
-        // (general nb: the plain scan over the entries)
-        uint32_t hist = 0;
-        int32_t near_until = lo - nb - 2;
-        for (int32_t p = lo; p < hi; p++) {
-            const uint32_t *m = fm + ((p - lo) / UVC_COL_CHUNK) * 4;
-            const uint32_t bit = 1u << (uint32_t)((p - lo) % UVC_COL_CHUNK);
-            const bool cov = (m[UVC_FM_COV] & bit), mut = ((m[UVC_FM_MUT_LINK] | m[UVC_FM_MUT_BASE_HQ]) & bit);
+        // (a neighbourhood wider than one chunk: distance to the previous and to the next mutated position, bit by bit)
+        const int32_t n = hi - lo;
+        const int32_t far = 0x3fffffff;
+        int32_t prev = -far, nxt = -1;
+        for (int32_t i = 0; i < n; i++) {
+            const uint32_t *m = fm + (i / UVC_COL_CHUNK) * 4;
+            const uint32_t bit = 1u << (uint32_t)(i % UVC_COL_CHUNK);
             n_mut_entries += ((m[UVC_FM_MUT_LINK] & bit) ? 1 : 0) + ((m[UVC_FM_MUT_BASE_HQ] & bit) ? 1 : 0);
-            if (mut) {
-                const int32_t uncounted = tmin(nb, tmax(0, p - 1 - near_until));
-                if (uncounted > 0) { n_near += __popc_u32(hist & ((uncounted >= 32) ? 0xffffffffu : ((1u << uncounted) - 1u))); }
-                near_until = p + nb;
+            if ((m[UVC_FM_MUT_LINK] | m[UVC_FM_MUT_BASE_HQ]) & bit) { prev = i; }
+            if (nxt < i) {      // next mutated position at or after i
+                nxt = far;
+                for (int32_t j = i; j < n; j++) {
+                    const uint32_t *mj = fm + (j / UVC_COL_CHUNK) * 4;
+                    if ((mj[UVC_FM_MUT_LINK] | mj[UVC_FM_MUT_BASE_HQ]) & (1u << (uint32_t)(j % UVC_COL_CHUNK))) { nxt = j; break; }
+                }
             }
-            if (cov) { n_cov++; if (p <= near_until) { n_near++; } }
-            hist = ((hist << 1) | (cov ? 1u : 0u)) & ((nb >= 32) ? 0xffffffffu : ((1u << nb) - 1u));
+            if (m[UVC_FM_COV] & bit) {
+                n_cov++;
+                if (nb >= 0 && (i - prev <= nb || nxt - i <= nb)) { n_near++; }
+            }
         }
     }
     // the fragment's haplotype string: its mutated high-quality consensus symbols in position order, link before base (main.hpp:2766-2800)
