@@ -118,9 +118,17 @@ int32_t center_at(const std::vector<int32_t> & cnt, int32_t lo, const double *ce
 }
 
 // FNV-1a over a NUL-terminated name (only used to bucket names in the per-tile name set; equality is always checked on the strings)
-inline uint64_t name_hash(const char *s) {
+inline uint64_t name_hash(const char *s, size_t n) {
+    // 8 bytes per step over the known length (never reads past the name), then the tail byte by byte
     uint64_t h = 1469598103934665603ULL;
-    for (; *s; s++) { h = (h ^ (uint64_t)(uint8_t)*s) * 1099511628211ULL; }
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w;
+        memcpy(&w, s + i, 8);
+        h = (h ^ w) * 0x9E3779B97F4A7C15ULL;
+        h ^= h >> 29;
+    }
+    for (; i < n; i++) { h = (h ^ (uint64_t)(uint8_t)s[i]) * 1099511628211ULL; }
     return h;
 }
 
@@ -382,7 +390,7 @@ static int build_tile_a(HostBatch & hb, TileWork & tw, const uvcgpu_params & par
             const Raw r = get_raw(rs, i);
             Pass1 & P = p1[(size_t)(i - ut.read_begin)];
             P.rend = r.rend; P.keep = 0; P.touches = 0; P.c = 0; P.tBeg = P.tEnd = 0;
-            vhash[(size_t)(i - ut.read_begin)] = name_hash(r.qname);
+            vhash[(size_t)(i - ut.read_begin)] = name_hash(r.qname, strnlen(r.qname, (size_t)(rs.qname_off[i + 1] - rs.qname_off[i])));
             bool isrc = false, isr2 = false; int32_t tBeg = 0, tEnd = 0;
             if (KEEP != classify(isrc, isr2, tBeg, tEnd, r, fetch_tbeg, fetch_tend, par, end2end, pem)) { continue; }
             const int c = isrc * 2 + isr2;
@@ -507,6 +515,8 @@ static int build_tile_a(HostBatch & hb, TileWork & tw, const uvcgpu_params & par
         });
         PROF(3)
         const int64_t read_base = (int64_t)hb.reads.size();
+        std::vector<int32_t> l2r_end, r2l_end;      // (reused by every family: no allocation per family)
+        hb.frags.reserve(kept.size()); hb.fams.reserve(kept.size()); hb.frag_reads.reserve(kept.size()); hb.fam_umi.reserve(kept.size());
         for (size_t oi = 0; oi < order.size();) {
             size_t oj = oi;
             while (oj < order.size() && kept[order[oj]].key == kept[order[oi]].key) { oj++; }
@@ -527,7 +537,7 @@ static int build_tile_a(HostBatch & hb, TileWork & tw, const uvcgpu_params & par
             for (int strand = 0; strand < 2; strand++) {
                 F.frag_off[strand] = (int32_t)hb.frags.size();
                 int32_t s_beg = INT32_MAX, s_end = 0, s_hi = 0;
-                std::vector<int32_t> l2r_end, r2l_end;
+                l2r_end.clear(); r2l_end.clear();
                 int64_t qseqlen_sum = 0, n_qseqs = 0;
                 while (o < oj && kept[order[o]].strand == strand) {
                     size_t p = o;
