@@ -50,8 +50,8 @@ def parse_args():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--scale", type=float, default=None, help="fraction of the named config's region (default: per-config)")
     ap.add_argument("--workdir", default=os.environ.get("UVC_BENCH_DIR", "/tmp/uvc_bench"))
-    ap.add_argument("--contexts", type=int, default=3, help="contexts (CUDA streams) the e2e step pipelines its sub-batches over")
-    ap.add_argument("--sub-batches", type=int, default=6)
+    ap.add_argument("--contexts", type=int, default=4, help="contexts (CUDA streams) the e2e step pipelines its sub-batches over")
+    ap.add_argument("--sub-batches", type=int, default=8)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -305,7 +305,9 @@ def main():
     ctx0.lib.uvcgpu_set_host_threads(ctx0.handle, max(1, host_threads // n_ctx + 1))
     totals = {"h2d": 0, "d2h": 0, "vcf": 0, "rec": 0, "launch": 0, "prep_ms": 0.0, "submit_s": 0.0, "wait_s": 0.0, "score_s": 0.0, "text_s": 0.0, "release_s": 0.0}
 
-    def e2e_step():
+    def e2e_steps(n_steps):
+        # the n_steps passes over the workload are one continuous stream of sub-batches (no drain between steps), as in a long run of the uvc1 host
+        work_items = [sub for _ in range(n_steps) for sub in subs]
         nxt = [0]
         lock = threading.Lock()
         acc = {k: 0 for k in totals}
@@ -320,7 +322,7 @@ def main():
                     with lock:
                         k = nxt[0]
                         nxt[0] += 1
-                    nxt_pending = submit_tiles(ctx, subs[k]) if k < len(subs) else None
+                    nxt_pending = submit_tiles(ctx, work_items[k]) if k < len(work_items) else None
                     if pending is None and nxt_pending is None:
                         return
                     if pending is None:
@@ -348,16 +350,23 @@ def main():
             raise errs[0]
         return acc
 
-    for _ in range(n_warm):
-        e2e_step()
+    e2e_steps(n_warm)
+    # steady state: the library page-locks its staging blocks in the background; warm up until none is outstanding (bounded)
+    ctx0.lib.uvcgpu_staging_backlog.restype = C.c_int
+    for _ in range(8):
+        t_wait = time.time()
+        while ctx0.lib.uvcgpu_staging_backlog() > 0 and time.time() - t_wait < 10.0:
+            time.sleep(0.05)
+        e2e_steps(2)
+        if ctx0.lib.uvcgpu_staging_backlog() == 0:
+            break
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.time()
-    for _ in range(args.steps):
-        acc = e2e_step()
-        for k in totals:
-            totals[k] += acc[k]
+    acc = e2e_steps(args.steps)
+    for k in totals:
+        totals[k] += acc[k]
     torch.cuda.synchronize()
     wall_s = time.time() - t0
     sampler.stop_flag = True
@@ -410,7 +419,7 @@ def main():
                        "positions_per_step": n_positions, "ext_positions_per_step": int(last.n_ext_positions), "stages": STAGES_IMPLEMENTED,
                        "l2": "per-position state of a step (%.0f MB) is larger than L2, no flush needed" % (last.n_ext_positions * 6272 / 1e6),
                        "host_decode_s_untimed": decode_s, "dataset_generation_s_untimed": ds.get("gen_s"),
-                       "e2e_schedule": "%d sub-batches over %d contexts (streams), two in flight per context, %d host threads" % (len(subs), len(ctxs), host_threads)},
+                       "e2e_schedule": "%d sub-batches per step over %d contexts (streams), two in flight per context, steps back to back, %d host threads" % (len(subs), len(ctxs), host_threads)},
             "e2e": {"value": e2e, "unit": "reads/s", "positions_per_s": units * n_positions * args.steps / wall_s,
                     "h2d_bytes_per_step": totals["h2d"] // args.steps, "d2h_bytes_per_step": totals["d2h"] // args.steps,
                     "vcf_bytes_per_step": totals["vcf"] // args.steps, "vcf_records_per_step": totals["rec"] // args.steps,

@@ -330,6 +330,11 @@ int uvcgpu_device_count(void);
  * in main.cpp:1297-1319). Returns UVCGPU_OK or UVCGPU_ENODEVICE / UVCGPU_ECUDA. */
 int uvcgpu_device_warmup(int device);
 
+/* Number of host staging blocks that the library's background thread still has to page-lock (process-wide). Staging never waits for
+ * page-locking: a batch that finds no page-locked block of the size it needs stages through pageable memory (slower copies) and the block is
+ * provisioned for the next one. A benchmark polls this after its warm-up to know that the steady state has been reached. */
+int uvcgpu_staging_backlog(void);
+
 /* sizeof(uvcgpu_params) as the library was compiled, so that foreign-language bindings can verify their mirror of the struct. */
 size_t uvcgpu_sizeof_params(void);
 

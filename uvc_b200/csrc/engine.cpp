@@ -79,7 +79,9 @@ struct uvcgpu_ctx {
     std::vector<int32_t> slip_tab;
     int host_threads = 0;
 #if UVC_CUDA
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;        // submit: staging copies and the pileup kernels of every batch, in submission order
+    cudaStream_t post_stream = nullptr;   // everything after collect (scoring kernels, downloads) of a batch, so that it does not queue behind the next batch
+    cudaStream_t active = nullptr;        // the stream the backend helpers use: `stream`, or `post_stream` inside PostScope
 #endif
 };
 
@@ -102,6 +104,7 @@ struct StageState {
     std::unordered_map<void*, size_t> pinned;         // every page-locked block (handed out or cached) -> its size class
     std::deque<size_t> wanted;                        // size classes the provisioning thread should page-lock
     size_t total_pinned = 0;
+    int in_progress = 0;                              // blocks being page-locked right now
     bool thread_started = false, stop = false;
     std::thread worker;
 };
@@ -124,10 +127,12 @@ void stage_provision_loop() {
             cls = st.wanted.front(); st.wanted.pop_front();
             if (st.total_pinned + cls > kStageMaxPinned) { continue; }
             st.total_pinned += cls;
+            st.in_progress = 1;
         }
         void *p = NULL;
-        if (cudaHostAlloc(&p, cls, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); std::lock_guard<std::mutex> lk(st.mu); st.total_pinned -= cls; continue; }
+        if (cudaHostAlloc(&p, cls, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); std::lock_guard<std::mutex> lk(st.mu); st.total_pinned -= cls; st.in_progress = 0; continue; }
         std::lock_guard<std::mutex> lk(st.mu);
+        st.in_progress = 0;
         st.pinned[p] = cls;
         st.free_blocks.insert(std::make_pair(cls, p));
     }
@@ -147,6 +152,7 @@ void *uvc_stage_alloc(size_t bytes) {
         auto it = st.free_blocks.find(cls);
         if (it != st.free_blocks.end()) { void *p = it->second; st.free_blocks.erase(it); return p; }
         st.wanted.push_back(cls);
+        st.wanted.push_back(cls);      // and a spare: the number of batches alive at once varies with the caller's pipelining
         if (!st.thread_started && !st.stop) {
             st.thread_started = true;
             st.worker = std::thread(stage_provision_loop);
@@ -545,17 +551,17 @@ static void launch(uvc_kernel_t k, cudaStream_t s, const BatchView & v, int64_t 
 
 static int backend_alloc(uvcgpu_ctx *ctx, BatchState & bs, void **out, size_t bytes, bool zero) {
     bytes += 64;     // slack: staged record slices are rounded up to 16 bytes, and clamped byte loads may touch offset 0 of an empty blob
-    UVC_CUDA_CHECK(ctx, cudaMallocAsync(out, bytes, ctx->stream));   // stream-ordered pool: no device synchronisation, blocks are reused across batches
+    UVC_CUDA_CHECK(ctx, cudaMallocAsync(out, bytes, ctx->active));   // stream-ordered pool: no device synchronisation, blocks are reused across batches
     bs.allocs.push_back(*out);
-    if (zero) { UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, 0, bytes, ctx->stream)); }
+    if (zero) { UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, 0, bytes, ctx->active)); }
     return 0;
 }
 static int backend_upload(uvcgpu_ctx *ctx, BatchState & bs, void *dst, const void *src, size_t bytes) {
-    if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream)); bs.stats.h2d_bytes += (int64_t)bytes; }
+    if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->active)); bs.stats.h2d_bytes += (int64_t)bytes; }
     return 0;
 }
 static int backend_download(uvcgpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
-    if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream)); UVC_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); }
+    if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->active)); UVC_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->active)); }
     return 0;
 }
 static void backend_free(uvcgpu_ctx *ctx, BatchState & bs) { for (void *p : bs.allocs) { cudaFreeAsync(p, ctx->stream); } bs.allocs.clear(); }
@@ -613,7 +619,9 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
 }
 
 static int backend_wait(uvcgpu_ctx *ctx, BatchState & bs) {
-    UVC_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    // only this batch's last kernel is waited for: a later batch may already be queued on the stream
+    if (bs.have_events) { UVC_CUDA_CHECK(ctx, cudaEventSynchronize(bs.ev[UVC_N_PILEUP_STAGES])); }
+    else { UVC_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); }
     if (bs.have_events) {
         float ms = 0;
         double total = 0;
@@ -633,14 +641,14 @@ static int backend_score(uvcgpu_ctx *ctx, BatchState & bs, const ScoreView & sv)
     const BatchView & v = bs.view;
     cudaEvent_t e[3];
     for (int i = 0; i < 3; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreate(&e[i])); }
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(e[0], ctx->stream));
-    if (v.n_pos > 0) { uvc_k6_gvcf_inputs<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, ctx->stream>>>(v, sv, v.n_pos); }
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(e[1], ctx->stream));
-    if (v.n_pos > 0) { uvc_k5a_flag_candidates<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, ctx->stream>>>(v, sv, v.n_pos); }
-    if (v.n_pos > 0) { uvc_k5_score_candidates<<<(unsigned)((v.n_pos + 63) / 64), 64, 0, ctx->stream>>>(v, sv, v.n_pos); }
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(e[2], ctx->stream));
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(e[0], ctx->active));
+    if (v.n_pos > 0) { uvc_k6_gvcf_inputs<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, ctx->active>>>(v, sv, v.n_pos); }
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(e[1], ctx->active));
+    if (v.n_pos > 0) { uvc_k5a_flag_candidates<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, ctx->active>>>(v, sv, v.n_pos); }
+    if (v.n_pos > 0) { uvc_k5_score_candidates<<<(unsigned)((v.n_pos + 63) / 64), 64, 0, ctx->active>>>(v, sv, v.n_pos); }
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(e[2], ctx->active));
     UVC_CUDA_CHECK(ctx, cudaGetLastError());
-    UVC_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    UVC_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->active));
     float ms = 0;
     UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, e[0], e[1])); bs.stats.kernel_ms_by_stage[11] = ms; bs.stats.kernel_ms += ms;
     UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, e[1], e[2])); bs.stats.kernel_ms_by_stage[12] = ms; bs.stats.kernel_ms += ms;
@@ -801,6 +809,16 @@ int uvcgpu_device_count(void) {
 #endif
 }
 
+int uvcgpu_staging_backlog(void) {
+#if UVC_CUDA
+    StageState & st = stage_state();
+    std::lock_guard<std::mutex> lk(st.mu);
+    return (int)st.wanted.size() + st.in_progress;
+#else
+    return 0;
+#endif
+}
+
 int uvcgpu_device_warmup(int device) {
 #if UVC_CUDA
     int n = 0;
@@ -839,6 +857,8 @@ int uvcgpu_create(uvcgpu_ctx **out, int device, const uvcgpu_params *params) {
     }
 #if UVC_CUDA
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return UVCGPU_ECUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->post_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return UVCGPU_ECUDA; }
+    ctx->active = ctx->stream;
     {   // keep freed device blocks in the stream-ordered pool instead of returning them to the driver after every batch
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { uint64_t keep = UINT64_MAX; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
@@ -853,6 +873,7 @@ void uvcgpu_destroy(uvcgpu_ctx *ctx) {
     enter_ctx(ctx);
     for (auto & kv : ctx->batches) { backend_free(ctx, *kv.second); }
 #if UVC_CUDA
+    if (ctx->post_stream) { cudaStreamDestroy(ctx->post_stream); }
     if (ctx->stream) { cudaStreamDestroy(ctx->stream); }
 #endif
     delete ctx;
@@ -1006,8 +1027,21 @@ int uvcgpu_collect(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, uvcgpu_batch_stats *st
     return UVCGPU_OK;
 }
 
+// Work on a collected batch (downloads, scoring kernels and their allocations) goes to the context's second stream: the batch's own kernels
+// are complete (collect waited for its last event), and a later batch may already be queued on the submit stream.
+struct PostScope {
+#if UVC_CUDA
+    uvcgpu_ctx *c;
+    explicit PostScope(uvcgpu_ctx *ctx) : c(ctx) { c->active = c->post_stream; }
+    ~PostScope() { c->active = c->stream; }
+#else
+    explicit PostScope(uvcgpu_ctx *) {}
+#endif
+};
+
 static int ensure_sparse(uvcgpu_ctx *ctx, BatchState & bs) {
     if (bs.sparse_built) { return 0; }
+    PostScope post_scope(ctx);
     const BatchView & v = bs.view;
     int32_t cursor[4] = {0, 0, 0, 0};
     int rc = backend_download(ctx, cursor, v.rec_cursor, sizeof(cursor));
@@ -1029,6 +1063,7 @@ static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
     if (bs.scored) { return 0; }
     int rc = ensure_sparse(ctx, bs);
     if (rc != 0) { return rc; }
+    PostScope post_scope(ctx);
     const double t0 = now_ms();
     BatchView & v = bs.view;
     std::vector<IndelAllele> table;
@@ -1145,7 +1180,10 @@ int uvcgpu_release(uvcgpu_ctx *ctx, uvcgpu_ticket ticket) {
     if (NULL == ctx) { return UVCGPU_EINVAL; }
     auto it = ctx->batches.find(ticket);
     if (it == ctx->batches.end()) { return UVCGPU_EINVAL; }
-    backend_wait(ctx, *it->second);
+    if (!it->second->collected) { backend_wait(ctx, *it->second); }   // (a collected batch has nothing left on the submit stream)
+#if UVC_CUDA
+    cudaStreamSynchronize(ctx->post_stream);                           // idle unless a scoring call failed half-way
+#endif
     backend_free(ctx, *it->second);
     ctx->batches.erase(it);
     return UVCGPU_OK;
@@ -1159,6 +1197,7 @@ int uvcgpu_dump_counters(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_ind
     BatchState & bs = *it->second;
     if (!bs.collected) { ctx->err = "batch not collected yet"; return UVCGPU_EINVAL; }
     if (tile_index < 0 || tile_index >= (int32_t)bs.hb.tiles.size()) { return UVCGPU_EINVAL; }
+    PostScope post_scope(ctx);
     const TileInfo & T = bs.hb.tiles[tile_index];
     const BatchView & v = bs.view;
     const size_t npos = (size_t)(T.ext_end - T.ext_beg);
