@@ -68,9 +68,10 @@ UVC_HD bool is_ins_symbol(int s) { return s == UVC_LINK_I1 || s == UVC_LINK_I2 |
 UVC_HD bool is_del_symbol(int s) { return s == UVC_LINK_D1 || s == UVC_LINK_D2 || s == UVC_LINK_D3P; }
 
 // seq_nt16_int of the 4-bit base at query index i: A,C,G,T -> 0..3, anything else -> 4 (BASE_N) (main.hpp:1829-1833)
+// nibble k of the constant = symbol of the 4-bit code k (1, 2, 4, 8 -> A, C, G, T; everything else -> N): a shift instead of a branch chain
+UVC_HD int nt16_to_symbol(uint32_t b4) { return (int)((0x4444444344424104ULL >> ((b4 & 0xfu) * 4)) & 0xfu); }
 UVC_HD int base3(const uint8_t *seq, int32_t i) {
-    const int b4 = (seq[i >> 1] >> ((~i & 1) << 2)) & 0xf;
-    return (b4 == 1 ? 0 : (b4 == 2 ? 1 : (b4 == 4 ? 2 : (b4 == 8 ? 3 : 4))));
+    return nt16_to_symbol((uint32_t)(seq[i >> 1] >> ((~i & 1) << 2)));
 }
 UVC_HD int base4(const uint8_t *seq, int32_t i) { return (seq[i >> 1] >> ((~i & 1) << 2)) & 0xf; }
 
@@ -451,8 +452,7 @@ UVC_HD int32_t base_index(const BatchView & v, const ReadRec & R, int32_t p, boo
     return ((e.flags & 1) ? tmax(0, tmin((int32_t)e.qpos, R.l_qseq - 1)) : -1);
 }
 UVC_HD uint32_t pack_base(uint32_t seq_byte, uint32_t qual_byte, int32_t qpos) {
-    const uint32_t b4 = (seq_byte >> ((~qpos & 1) << 2)) & 0xfu;
-    const uint32_t sym = (b4 == 1 ? 0u : (b4 == 2 ? 1u : (b4 == 4 ? 2u : (b4 == 8 ? 3u : 4u))));
+    const uint32_t sym = (uint32_t)nt16_to_symbol(seq_byte >> ((~qpos & 1) << 2));
     return (qpos >= 0 ? ((sym << 8) | qual_byte) : UVC_K2_NOBASE);
 }
 // ------------------------------------------------------------------------------------------------ K1: one thread per position
