@@ -630,21 +630,28 @@ UVC_HD void segbias(SegAcc & a, const BatchView & v, const ReadRec & R, const Re
     const bool isrc = ((R.flag & 0x10) == 0x10);
     const bool strand = R.strand;
 
-    if (isrc) { a.a1BQr += bq; a.a2BQr += bq * bq / UVC_SQR_QUAL_DIV; } else { a.a1BQf += bq; a.a2BQf += bq * bq / UVC_SQR_QUAL_DIV; }
+    // From here on the updates are written without control flow (conditions become 0/1 addends, non-short-circuit & and |): the conditions on the
+    // read (strand, orientation, pairing) are the same for all lanes, but a taken-or-not branch per counter costs more than the add it guards
+    // when only a few warps are resident.
+    const int32_t rc = (isrc ? 1 : 0), fw = 1 - rc;
+    const int32_t has_isize = ((R.isize != 0) ? 1 : 0);
+    const int32_t sq = bq * bq / UVC_SQR_QUAL_DIV;
+    a.a1BQr += rc * bq; a.a2BQr += rc * sq; a.a1BQf += fw * bq; a.a2BQf += fw * sq;
     a.s.aMQs += R.mapq;
-    if (strand) { if (isrc) { a.s.aDPrr += 1; } else { a.s.aDPrf += 1; } } else { if (isrc) { a.s.aDPfr += 1; } else { a.s.aDPff += 1; } }
-    if (tmin(dist_indel, tmin(seg_l_nbases, seg_r_nbases)) >= par.bias_thres_interfering_indel) { a.s.aP3 += 1; }
-    if (0 == D.clip_cnt) { a.s.aNC += 1; }
-    if (isrc) { a.s.aLIT += ((R.isize != 0) ? frag_l_nb : 0); } else { a.s.aRIT += ((R.isize != 0) ? frag_r_nb : 0); }
+    const int32_t st1 = (strand ? 1 : 0), st0 = 1 - st1;
+    a.s.aDPrr += st1 * rc; a.s.aDPrf += st1 * fw; a.s.aDPfr += st0 * rc; a.s.aDPff += st0 * fw;
+    a.s.aP3 += ((tmin(dist_indel, tmin(seg_l_nbases, seg_r_nbases)) >= par.bias_thres_interfering_indel) ? 1 : 0);
+    a.s.aNC += ((0 == D.clip_cnt) ? 1 : 0);
+    a.s.aLIT += (int64_t)(rc * has_isize * frag_l_nb); a.s.aRIT += (int64_t)(fw * has_isize * frag_r_nb);
 
     const int32_t LPxT0 = th.aLPxT, RPxT = th.aRPxT;
     const int32_t LPxT = (isGap ? LPxT0 : tmin(LPxT0, RPxT));
-    const bool far_from_edge = (seg_l_nbases + (is_ins_op ? nnminus(indel_len, par.microadjust_nobias_pos_indel_maxlen) : 0) >= LPxT) && (seg_r_nbases >= RPxT);
+    const bool far_from_edge = (seg_l_nbases + (is_ins_op ? nnminus(indel_len, par.microadjust_nobias_pos_indel_maxlen) : 0) >= LPxT) & (seg_r_nbases >= RPxT);
     const int32_t highBAQ = par.bias_thres_highBAQ + (isGap ? 0 : 3);
-    const bool unaffected_by_edge = (seg_l_baq >= highBAQ && seg_r_baq >= highBAQ);
+    const bool unaffected_by_edge = (seg_l_baq >= highBAQ) & (seg_r_baq >= highBAQ);
     const int32_t min_dist2iend = ((R.flag & 0x1) ? tmin(frag_l_nb, frag_r_nb) : (isrc ? seg_r_nbases : seg_l_nbases));
-    if (far_from_edge && unaffected_by_edge && (min_dist2iend > par.primerlen2 || !is_assay_amplicon)) { a.s.aP1 += 1; }
-    if (is_assay_UMI || !is_assay_amplicon) { a.s.aP2 += 1; }
+    a.s.aP1 += ((far_from_edge & unaffected_by_edge & ((min_dist2iend > par.primerlen2) | !is_assay_amplicon)) ? 1 : 0);
+    a.s.aP2 += ((is_assay_UMI | !is_assay_amplicon) ? 1 : 0);
 
     int32_t f1, f2;
     if ((uint32_t)bq < 128u) { f1 = v.pf_tab[bq]; f2 = v.pf_tab[128 + bq]; }
@@ -661,33 +668,38 @@ UVC_HD void segbias(SegAcc & a, const BatchView & v, const ReadRec & R, const Re
         a.s.a2XM2 += D.xm_term;
         a.s.a2BM2 += bm_term;
     }
-    if (((!isGap) && bq >= par.bias_thres_highBQ) || (isGap && dist_indel >= par.bias_thres_interfering_indel)) {
-        const bool tier2 = (isGap || bq >= par.bias_thres_highBQ);
-        if (far_from_edge) {
-            int64_t lpl = 0, rpl = 0;
-            bidir_bias(a.s.aLP1, a.s.aLP2, a.s.aRP1, a.s.aRP2, lpl, rpl, th.aLP1t, th.aLP2t, th.aRP1t, th.aRP2t, seg_l_nbases, seg_r_nbases, tier2, indel_len);
-            a.s.aLPL += (int32_t)lpl; a.s.aRPL += (int32_t)rpl;
-        }
-        if (unaffected_by_edge) {
-            bidir_bias(a.s.aLB1, a.s.aLB2, a.s.aRB1, a.s.aRB2, a.s.aLBL, a.s.aRBL, par.bias_thres_BAQ1, par.bias_thres_BAQ2, par.bias_thres_BAQ1, par.bias_thres_BAQ2,
-                    seg_l_baq, seg_r_baq, tier2, 0);
-        }
-        a.s.aBQ2 += 1;
+    {
+        // update_bidirectional_bias (main.hpp:1318-1358) twice: position bias (if far from the edges) and BAQ bias (if unaffected by the edges)
+        const bool counted = (isGap ? (dist_indel >= par.bias_thres_interfering_indel) : (bq >= par.bias_thres_highBQ));
+        const bool tier2 = (isGap | (bq >= par.bias_thres_highBQ));
+        const int32_t gp_ = ((counted & far_from_edge) ? 1 : 0), gb_ = ((counted & unaffected_by_edge) ? 1 : 0), t2 = (tier2 ? 1 : 0);
+        const int32_t nl = seg_l_nbases, nr = seg_r_nbases;
+        a.s.aLP1 += gp_ * ((nl + indel_len >= th.aLP1t) ? 1 : 0);
+        a.s.aLP2 += gp_ * t2 * ((nl + indel_len >= th.aLP2t) ? 1 : 0);
+        a.s.aRP1 += gp_ * ((nr >= th.aRP1t) ? 1 : 0);
+        a.s.aRP2 += gp_ * t2 * ((nr >= th.aRP2t) ? 1 : 0);
+        a.s.aLPL += gp_ * nl; a.s.aRPL += gp_ * nr;
+        a.s.aLB1 += gb_ * ((seg_l_baq >= par.bias_thres_BAQ1) ? 1 : 0);
+        a.s.aLB2 += gb_ * t2 * ((seg_l_baq >= par.bias_thres_BAQ2) ? 1 : 0);
+        a.s.aRB1 += gb_ * ((seg_r_baq >= par.bias_thres_BAQ1) ? 1 : 0);
+        a.s.aRB2 += gb_ * t2 * ((seg_r_baq >= par.bias_thres_BAQ2) ? 1 : 0);
+        a.s.aLBL += (int64_t)(gb_ * seg_l_baq); a.s.aRBL += (int64_t)(gb_ * seg_r_baq);
+        a.s.aBQ2 += (counted ? 1 : 0);
     }
-    const bool mate_ok = ((0 == (R.flag & 0x8)) || (0 == (R.flag & 0x1)));
-    const bool l_nonbiased = (mate_ok && seg_l_nbases > seg_r_nbases);
-    const bool r_nonbiased = (mate_ok && seg_l_nbases < seg_r_nbases);
-    const bool pos_good = ((!is_assay_amplicon) || (!normal_filters_primers) || (far_from_edge && unaffected_by_edge));
-    if (isrc) {
-        const int32_t d = frag_l_nb;
-        if ((d >= th.aLI1t) && (d <= th.aLI1T || isGap) && (is_normal || (isGap && l_nonbiased))) { a.s.aLI1 += 1; }
-        if ((d >= th.aLI2t) && (d <= th.aLI2T || isGap) && (is_normal || (isGap && l_nonbiased))) { if (pos_good) { a.s.aLI2 += 1; } }
-        if (pos_good) { a.s.aLIr += 1; }
-    } else {
-        const int32_t d = frag_r_nb;
-        if ((d >= th.aRI1t) && (d <= th.aRI1T || isGap) && (is_normal || (isGap && r_nonbiased))) { a.s.aRI1 += 1; }
-        if ((d >= th.aRI2t) && (d <= th.aRI2T || isGap) && (is_normal || (isGap && r_nonbiased))) { if (pos_good) { a.s.aRI2 += 1; } }
-        if (pos_good) { a.s.aRIf += 1; }
+    {
+        // insert-size bias: the reverse-complemented read looks at its left fragment end, the forward read at its right one
+        const bool mate_ok = ((0 == (R.flag & 0x8)) | (0 == (R.flag & 0x1)));
+        const bool nonbiased = (mate_ok & (isrc ? (seg_l_nbases > seg_r_nbases) : (seg_l_nbases < seg_r_nbases)));
+        const bool pos_good = ((!is_assay_amplicon) | (!normal_filters_primers) | (far_from_edge & unaffected_by_edge));
+        const int32_t d = (isrc ? frag_l_nb : frag_r_nb);
+        const int32_t t1 = (isrc ? th.aLI1t : th.aRI1t), T1 = (isrc ? th.aLI1T : th.aRI1T);
+        const int32_t t2 = (isrc ? th.aLI2t : th.aRI2t), T2 = (isrc ? th.aLI2T : th.aRI2T);
+        const bool ok = (is_normal | (isGap & nonbiased));
+        const int32_t c1 = (((d >= t1) & ((d <= T1) | isGap) & ok) ? 1 : 0);
+        const int32_t c2 = (((d >= t2) & ((d <= T2) | isGap) & ok & pos_good) ? 1 : 0);
+        const int32_t c3 = (pos_good ? 1 : 0);
+        a.s.aLI1 += rc * c1; a.s.aLI2 += rc * c2; a.s.aLIr += rc * c3;
+        a.s.aRI1 += fw * c1; a.s.aRI2 += fw * c2; a.s.aRIf += fw * c3;
     }
 }
 
