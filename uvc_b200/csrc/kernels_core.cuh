@@ -1404,8 +1404,9 @@ UVC_HD void k3b_read(K3bState & s, const BatchView & v, const ReadFrag & q, cons
             const int32_t pb = tmax(0, max_qual - phredlike);
             if (pb < UVC_NUM_BUCKETS) { k3b_hb_inc(s, type * UVC_NUM_BUCKETS + pb); }
             // the read (hence the strand) is the same for all lanes of the warp
-            if (strand) { s.h1[type].n += 1; s.h1[type].cov += q.n_cov; s.h1[type].near += q.n_near_mut; }
-            else { s.h0[type].n += 1; s.h0[type].cov += q.n_cov; s.h0[type].near += q.n_near_mut; }
+            const int32_t s1 = strand, s0 = 1 - s1;      // (no branch on the strand)
+            s.h1[type].n += s1; s.h1[type].cov += s1 * q.n_cov; s.h1[type].near += s1 * q.n_near_mut;
+            s.h0[type].n += s0; s.h0[type].cov += s0 * q.n_cov; s.h0[type].near += s0 * q.n_near_mut;
             s.hmq[type] += q.mq_term;
             continue;
         }
@@ -1695,7 +1696,11 @@ UVC_HD void k4hot_add(K4Hot & h, const K4Hot & d) {
 // adds the increments d to the family depth counters of (strand, symbol a of type `type`)
 UVC_HD void k4_add(K4State & s, int strand, int type, int a, const K4Hot & d) {
     if (a == s.hot[type]) {
-        if (strand) { k4hot_add(s.h1[type], d); } else { k4hot_add(s.h0[type], d); }
+        // (no branch on the strand: both register sets take the increments, one of them multiplied by zero)
+        const int32_t s1 = (strand ? 1 : 0), s0 = 1 - s1;
+        K4Hot & h0 = s.h0[type]; K4Hot & h1 = s.h1[type];
+        h0.dp1 += s0 * d.dp1; h0.dp12 += s0 * d.dp12; h0.dp2 += s0 * d.dp2; h0.dp3 += s0 * d.dp3; h0.dpM += s0 * d.dpM; h0.dpm += s0 * d.dpm; h0.dp21 += s0 * d.dp21;
+        h1.dp1 += s1 * d.dp1; h1.dp12 += s1 * d.dp12; h1.dp2 += s1 * d.dp2; h1.dp3 += s1 * d.dp3; h1.dpM += s1 * d.dpM; h1.dpm += s1 * d.dpm; h1.dp21 += s1 * d.dp21;
     } else {
         k4_touch(s, strand, a);
         int32_t *fd = s.facc + (strand * UVC_NSYM + a) * UVCGPU_NUM_FAM_DEPTHS;
