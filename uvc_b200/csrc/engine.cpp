@@ -492,6 +492,7 @@ __global__ void __launch_bounds__(128, UVC_K4_MINBLOCKS) uvc_k4_family_consensus
                 if (ri < w.lo || ri >= w.hi) { continue; }
                 const ReadFam q = S.q[rs][k];
                 if (q.rend <= p || q.famprev_maxrend > p) { continue; }
+                if ((q.flags & UVC_RF_DIRECT) && uvc::k4_loop1_lone_fragment(st, v, q, S.e[es][k][lane])) { continue; }
                 uvc::k4_loop1_read(st, v, q, (q.flags & UVC_RF_DIRECT) ? uvc::famcol_from_frag(S.e[es][k][lane], v.par) : v.mcol[q.col_base + p], ri - w.lo);
             }
         }

@@ -1648,6 +1648,7 @@ struct K4State {
     // reads (offsets from the start of the window) that loop 1 leaves work for; more than UVC_K4_LIST of them: the whole window is walked again
     int32_t n_need2;
     uint16_t *need2;       // [UVC_K4_LIST]
+    bool lone_is_plain;    // a strand with one fragment (cc = tc = 1) can only count as cDP12 / cDP21 / cDP1 under the current thresholds
     // family depth counters of the two symbols nearly every family votes for - the reference base and LINK_M - per strand: registers
     int hot[2];            // [type]
     K4Hot h0[2], h1[2];    // strand 0 / strand 1, [type]
@@ -1688,6 +1689,11 @@ UVC_HD void k4_begin(K4State & s, K4Arrays & arr, const BatchView & v, int64_t g
     s.n_need2 = 0;
     s.hot[0] = s.ref; s.hot[1] = UVC_LINK_M;
     for (int t = 0; t < 2; t++) { k4hot_zero(s.h0[t]); k4hot_zero(s.h1[t]); }
+    const uvcgpu_params & par = v.par;
+    s.lone_is_plain = (par.fam_thres_dup1add > 1)
+            && !(par.fam_thres_dup2add <= 1 && 100 >= par.fam_thres_dup2perc)
+            && !(1 >= par.fam_thres_emperr_all_flat_snv && 100 >= par.fam_thres_emperr_con_perc_snv)
+            && !(1 >= par.fam_thres_emperr_all_flat_indel && 100 >= par.fam_thres_emperr_con_perc_indel);
 }
 
 UVC_HD void k4hot_add(K4Hot & h, const K4Hot & d) {
@@ -1722,6 +1728,31 @@ UVC_HD void k4_major_minor(const K4State & s, int strand, int type, int a, int32
 // does loop 1 (with the loop-2 share described above) cover everything this (family, strand) entry asks of loop 2 for symbol type `type`?
 UVC_HD bool k4_loop2_done_in_loop1(const uvcgpu_params & par, const ReadFam & q, const FamCol & m, int type) {
     return (0 == (q.flags & UVC_RF_DUPLEX_UMI)) && ((int32_t)m.tc1[type] < par.fam_thres_dup1add);
+}
+
+// Loop 1 (and its share of loop 2) for a single-fragment strand of a family without a duplex UMI, straight from the fragment's column entry:
+// every vote has cc = tc = 1, so under the usual thresholds (lone_is_plain) it is "cDP12, cDP21 and cDP1 of the symbol" and nothing else - the
+// same increments k4_loop1_read derives through famcol_from_frag. Returns false (nothing done) when the general path has to run: indel
+// symbols (their identities are recorded), duplex-UMI families, unusual thresholds.
+UVC_HD bool k4_loop1_lone_fragment(K4State & s, const BatchView & v, const ReadFam & q, const FragCol & e) {
+    if (!s.lone_is_plain || (q.flags & UVC_RF_DUPLEX_UMI)) { return false; }
+    const int la = (e.link_sym & 0xf);
+    if (e.link_cc > 0 && (is_ins_symbol(la) || is_del_symbol(la))) { return false; }
+    const int strand = (int)(q.flags & UVC_RF_STRAND);
+    K4Hot d;
+    if (e.link_cc > 0) {
+        k4hot_zero(d);
+        d.dp12 = 1; d.dp21 = 1; d.dp1 = 1;
+        k4_add(s, strand, 1, la, d);
+    }
+    const int32_t adj = tmax((int32_t)e.base_cc * 2, (int32_t)e.base_tc) - (int32_t)e.base_tc;
+    if (adj > 0) {
+        k4hot_zero(d);
+        d.dp1 = 1;
+        if (adj >= v.par.fam_thres_highBQ_snv) { d.dp12 = 1; d.dp21 = 1; }
+        k4_add(s, strand, 0, e.base_sym, d);
+    }
+    return true;
 }
 
 // loop 1 for the first read q of its (family, strand) that covers p; m is that (family, strand)'s column entry at p; woff = offset of the read
@@ -1960,6 +1991,7 @@ UVC_HD void k4_position(const BatchView & v, int64_t gp, const Win & w) {
         if (ri < w.lo || ri >= w.hi) { continue; }
         const ReadFam q = v.rfam[ri];
         if (q.rend <= p || q.famprev_maxrend > p) { continue; }
+        if ((q.flags & UVC_RF_DIRECT) && k4_loop1_lone_fragment(s, v, q, v.fcol[q.col_base + p])) { continue; }
         k4_loop1_read(s, v, q, fam_entry_of_read(v, q, p), ri - w.lo);
     }
     k4_loop2_listed(s, v, w);
