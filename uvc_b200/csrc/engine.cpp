@@ -350,14 +350,33 @@ __global__ void __launch_bounds__(128) uvc_k1_prep_thres(const BatchView v, int6
     if (active) { uvc::k1_end(st, v); }
 }
 UVC_DEFINE_KERNEL(uvc_k2e_indel_events, uvc::k2e_event(v, i))
-// KF: a warp is one 32-entry chunk of one fragment's column; the chunk's four bit masks are four ballots
-__global__ void __launch_bounds__(128) uvc_kf_fragment_columns(const BatchView v, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // n is a multiple of 32: whole warps are in or out
-    if (i >= n) { return; }
-    const uint32_t bits = uvc::kf_fragment_column(v, i);
-    const uint32_t m0 = __ballot_sync(0xffffffffu, bits & 1u), m1 = __ballot_sync(0xffffffffu, bits & 2u);
-    const uint32_t m2 = __ballot_sync(0xffffffffu, bits & 4u), m3 = __ballot_sync(0xffffffffu, bits & 8u);
-    if (0 == (threadIdx.x & 31)) { *(uint4*)(v.fmask + (i / UVC_COL_CHUNK) * 4) = make_uint4(m0, m1, m2, m3); }
+// KF: one warp per fragment walks the fragment's column chunk by chunk (lane = position within the chunk): the records of the fragment's
+// reads are loaded once per fragment instead of once per entry; a chunk's four bit masks are four ballots.
+__global__ void __launch_bounds__(128) uvc_kf_fragment_columns(const BatchView v, int64_t n_threads) {
+    const int64_t fi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (fi >= (n_threads >> 5)) { return; }
+    const FragRec & G = v.frags[fi];
+    const int32_t lo = G.lo, n = G.hi - G.lo;
+    const int64_t col_off = G.col_off;
+    const TileInfo & T = v.tiles[G.tile];
+    const int64_t gp0 = T.pos_off + (lo - T.ext_beg);
+    const bool plain = uvc::kf_fragment_is_plain(v, G);
+    const int32_t n_reads = G.n_reads;
+    uvc::KfRead rd[2];
+    if (plain) {
+        if (n_reads > 0) { uvc::kf_load_read(rd[0], v, v.frag_reads[G.read_off]); }
+        if (n_reads > 1) { uvc::kf_load_read(rd[1], v, v.frag_reads[G.read_off + 1]); }
+    }
+    for (int32_t c = 0; c * UVC_COL_CHUNK < n; c++) {
+        const int32_t o = c * UVC_COL_CHUNK + lane;
+        const int64_t i = col_off + o;
+        uint32_t bits = 0;
+        if (o < n) { bits = (plain ? uvc::kf_plain_entry(v, i, lo + o, gp0 + o, rd, n_reads) : uvc::kf_fragment_column(v, i)); }
+        const uint32_t m0 = __ballot_sync(0xffffffffu, bits & 1u), m1 = __ballot_sync(0xffffffffu, bits & 2u);
+        const uint32_t m2 = __ballot_sync(0xffffffffu, bits & 4u), m3 = __ballot_sync(0xffffffffu, bits & 8u);
+        if (0 == lane) { *(uint4*)(v.fmask + (i / UVC_COL_CHUNK) * 4) = make_uint4(m0, m1, m2, m3); }
+    }
 }
 UVC_DEFINE_KERNEL(uvc_k3a_fragment_stats, uvc::k3a_fragment(v, i))
 UVC_DEFINE_KERNEL(uvc_km_family_columns, uvc::km_family_column(v, i))
@@ -592,7 +611,7 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
     UVC_STAGE(uvc_k2e_indel_events, v.n_ev)
-    UVC_STAGE(uvc_kf_fragment_columns, v.n_fcol)
+    UVC_STAGE(uvc_kf_fragment_columns, v.n_frags * 32)
     UVC_STAGE(uvc_k3a_fragment_stats, v.n_frags)
     if (v.n_pos > 0) {
         static_assert(sizeof(ColStage<ReadFrag>) % 16 == 0, "per-warp staging slots keep 16-byte alignment");

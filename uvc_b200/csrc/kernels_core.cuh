@@ -1128,6 +1128,81 @@ UVC_HD int32_t indel_majority_of_reads(const BatchView & v, const int32_t *reads
 // a warp owns 32 consecutive positions of ONE fragment, so the fragment's read records are warp-uniform and its base qualities are read
 // as consecutive bytes; the entry keeps only what fillConsensusCounts (main.hpp:374-417) yields for the two symbol types.
 // Returns the entry's UVC_FM_* bits; the caller folds the 32 results of a chunk into v.fmask (one ballot per mask in the CUDA kernel).
+// What KF needs from one read of a plain fragment (a read whose CIGAR is [S|H] M [S|H]), loaded once per fragment
+struct KfRead {
+    int32_t pos, rend, m_qoff, ibeg, iend, nogap_penal;
+    bool mask_on;                  // primers of this read are masked outside [ibeg, iend) (primer_masked)
+    const uint8_t *seq, *qual;
+};
+UVC_HD void kf_load_read(KfRead & k, const BatchView & v, int64_t ri) {
+    const ReadRec & R = v.reads[ri];
+    const ReadDerived & D = v.rd[ri];
+    k.pos = R.pos; k.rend = R.rend; k.m_qoff = R.m_qoff; k.ibeg = D.ibeg; k.iend = D.iend; k.nogap_penal = D.micro_nogap_penal;
+    const bool is_assay_amplicon = ((R.dflag & 0x4) || ((v.par.primerlen > 0) && !(0x2 & v.par.primer_flag)));
+    const bool normal_filters_primers = (v.par.tn_is_paired && (0x1 & v.par.primer_flag));
+    k.mask_on = !(normal_filters_primers || !is_assay_amplicon);
+    k.seq = v.seq + R.seq_off; k.qual = v.qual + R.qual_off;
+}
+// true if the fragment is plain: one or two reads, none with indels or skips
+UVC_HD bool kf_fragment_is_plain(const BatchView & v, const FragRec & G) {
+    bool plain = (G.n_reads <= 2);
+    for (int32_t k = 0; plain && k < G.n_reads; k++) { plain = (0 != v.reads[v.frag_reads[G.read_off + k]].simple); }
+    return plain;
+}
+// stores the entry of a covered position from the two consensus triples and returns its UVC_FM_* bits
+UVC_HD uint32_t kf_store_entry(const BatchView & v, int64_t i, int64_t gp, bool covered, int la, int32_t lcc, int ba, int32_t bcc, int32_t btc, bool n_votes) {
+    FragCol e;
+    e.link_cc = 0; e.base_cc = 0; e.base_tc = 0; e.link_sym = UVC_LINK_NN; e.base_sym = UVC_BASE_NN;
+    uint32_t bits = 0;
+    if (covered) {
+        e.link_sym = (uint8_t)(la | (n_votes ? 0x80 : 0)); e.link_cc = (uint16_t)lcc;
+        const int ref = v.refsym[gp];
+        if (e.link_cc > 0 && symbols_mutated(ref, la)) { bits |= (1u << UVC_FM_MUT_LINK); }
+        e.base_sym = (uint8_t)ba; e.base_cc = (uint16_t)bcc; e.base_tc = (uint16_t)btc;
+        // (the stored counts are 16-bit: the tests below use them as every later kernel reads them)
+        const int32_t con_qual = (int32_t)e.base_cc * 2 - (int32_t)e.base_tc;
+        if (e.base_tc > 0 && symbols_mutated(ref, ba)) {
+            if (con_qual >= v.par.bias_thres_highBQ) { bits |= (1u << UVC_FM_MUT_BASE_HQ); }
+            if (con_qual > 0) { bits |= (1u << UVC_FM_MUT_BASE_ANY); }
+        }
+        if (e.link_cc | e.base_tc) { bits |= (1u << UVC_FM_COV); }
+    }
+    v.fcol[i] = e;
+    return bits;
+}
+// Entry i (position p, concatenated index gp) of a plain fragment with reads rd[0 .. n). Such a fragment votes for LINK_M and for at most two base
+// symbols: the consensus of both symbol types is written out directly (same results as the general path, which keeps a 14-entry vote array
+// in local memory).
+UVC_HD uint32_t kf_plain_entry(const BatchView & v, int64_t i, int32_t p, int64_t gp, const KfRead *rd, int32_t n) {
+    bool covered = false;
+    int32_t linkw = 0, q0 = 0, q1 = 0;
+    int s0 = -1, s1 = -1;
+    #pragma unroll
+    for (int32_t k = 0; k < 2; k++) {      // (n <= 2; constant indices keep rd in registers)
+        if (k >= n) { continue; }
+        const KfRead & R = rd[k];
+        if (p < R.pos || p >= R.rend) { continue; }
+        covered = true;
+        if (R.mask_on && !(R.ibeg <= p && p < R.iend)) { continue; }      // primer_masked
+        if (p > R.pos) {                                                    // nogap_weight
+            const int32_t noindel = tmin(v.rtr[gp > 0 ? gp - 1 : 0].indelphred, v.rtr[gp].indelphred);
+            linkw = tmax(linkw, nnminus(tmin(80, noindel), R.nogap_penal) + 1);
+        }
+        const int32_t qpos = R.m_qoff + (p - R.pos);
+        const int sym = base3(R.seq, qpos);
+        const int32_t q = tmax(0, (int32_t)R.qual[qpos] + v.par.bq_phred_added_misma);   // votes are max-merged into zeros
+        if (s0 < 0 || s0 == sym) { s0 = sym; q0 = tmax(q0, q); } else { s1 = sym; q1 = tmax(q1, q); }
+    }
+    int la = UVC_LINK_NN, ba = UVC_BASE_NN;
+    int32_t lcc = 0, bcc = 0;
+    if (linkw > 0) { la = UVC_LINK_M; lcc = linkw; }
+    if (s1 >= 0 && s1 < s0) { const int ts = s0; s0 = s1; s1 = ts; const int32_t tq = q0; q0 = q1; q1 = tq; }   // symbol order decides ties
+    if (s0 >= 0 && q0 > 0) { ba = s0; bcc = q0; }
+    if (s1 >= 0 && q1 > bcc) { ba = s1; bcc = q1; }
+    const bool n_votes = ((s0 == UVC_BASE_N && q0 > 0) || (s1 == UVC_BASE_N && q1 > 0));      // votes for BASE_N exist (bit 7 of link_sym)
+    return kf_store_entry(v, i, gp, covered, la, lcc, ba, bcc, q0 + q1, n_votes);
+}
+// Returns the entry's UVC_FM_* bits; the caller folds the 32 results of a chunk into v.fmask (one ballot per mask in the CUDA kernel).
 UVC_HD uint32_t kf_fragment_column(const BatchView & v, int64_t i) {
     const FragRec & G = v.frags[v.fchunk_frag[i / UVC_COL_CHUNK]];
     const int32_t o = (int32_t)(i - G.col_off);
@@ -1135,40 +1210,16 @@ UVC_HD uint32_t kf_fragment_column(const BatchView & v, int64_t i) {
     const int32_t p = G.lo + o;
     const TileInfo & T = v.tiles[G.tile];
     const int64_t gp = T.pos_off + (p - T.ext_beg);
-    FragCol e;
-    e.link_cc = 0; e.base_cc = 0; e.base_tc = 0; e.link_sym = UVC_LINK_NN; e.base_sym = UVC_BASE_NN;
-    uint32_t bits = 0;
-    // A fragment of one or two reads without indels or skips (98 % of them) votes for LINK_M and for at most two base symbols: the consensus of
-    // both symbol types is written out directly (same results as the general path below, which keeps a 14-entry vote array in local memory).
-    bool plain = (G.n_reads <= 2);
-    for (int32_t k = 0; plain && k < G.n_reads; k++) { plain = (0 != v.reads[v.frag_reads[G.read_off + k]].simple); }
+    if (kf_fragment_is_plain(v, G)) {
+        KfRead rd[2];
+        for (int32_t k = 0; k < G.n_reads; k++) { kf_load_read(rd[k], v, v.frag_reads[G.read_off + k]); }
+        return kf_plain_entry(v, i, p, gp, rd, G.n_reads);
+    }
     bool covered = false;
     int la = UVC_LINK_NN, ba = UVC_BASE_NN;
     int32_t lcc = 0, bcc = 0, btc = 0;
     bool n_votes = false;                 // votes for BASE_N / BASE_NN exist (bit 7 of link_sym)
-    if (plain) {
-        int32_t linkw = 0, q0 = 0, q1 = 0;
-        int s0 = -1, s1 = -1;
-        for (int32_t k = 0; k < G.n_reads; k++) {
-            const int64_t ri = v.frag_reads[G.read_off + k];
-            const ReadRec & R = v.reads[ri];
-            if (p < R.pos || p >= R.rend) { continue; }
-            covered = true;
-            const ReadDerived & D = v.rd[ri];
-            if (primer_masked(v, R, D, p)) { continue; }
-            if (p > R.pos) { linkw = tmax(linkw, nogap_weight(v, gp, D)); }
-            const int32_t qpos = R.m_qoff + (p - R.pos);
-            const int sym = base3(v.seq + R.seq_off, qpos);
-            const int32_t q = tmax(0, (int32_t)v.qual[R.qual_off + qpos] + v.par.bq_phred_added_misma);   // votes are max-merged into zeros
-            if (s0 < 0 || s0 == sym) { s0 = sym; q0 = tmax(q0, q); } else { s1 = sym; q1 = tmax(q1, q); }
-        }
-        if (linkw > 0) { la = UVC_LINK_M; lcc = linkw; }
-        if (s1 >= 0 && s1 < s0) { const int ts = s0; s0 = s1; s1 = ts; const int32_t tq = q0; q0 = q1; q1 = tq; }   // symbol order decides ties
-        if (s0 >= 0 && q0 > 0) { ba = s0; bcc = q0; }
-        if (s1 >= 0 && q1 > bcc) { ba = s1; bcc = q1; }
-        btc = q0 + q1;
-        n_votes = ((s0 == UVC_BASE_N && q0 > 0) || (s1 == UVC_BASE_N && q1 > 0));
-    } else if (frag_covers(v, G, p)) {
+    if (frag_covers(v, G, p)) {
         covered = true;
         int32_t c[UVC_NSYM];
         frag_votes(v, G, p, gp, c);
@@ -1177,23 +1228,7 @@ UVC_HD uint32_t kf_fragment_column(const BatchView & v, int64_t i) {
         n_votes = (0 != (c[UVC_BASE_N] | c[UVC_BASE_NN]));
         base_consensus(c, false, ba, bcc, btc);
     }
-    if (covered) {
-        int a = la; int32_t cc = lcc, tc = 0;
-        e.link_sym = (uint8_t)(a | (n_votes ? 0x80 : 0)); e.link_cc = (uint16_t)cc;
-        const int ref = v.refsym[gp];
-        if (e.link_cc > 0 && symbols_mutated(ref, a)) { bits |= (1u << UVC_FM_MUT_LINK); }
-        a = ba; cc = bcc; tc = btc;
-        e.base_sym = (uint8_t)a; e.base_cc = (uint16_t)cc; e.base_tc = (uint16_t)tc;
-        // (the stored counts are 16-bit: the tests below use them as every later kernel reads them)
-        const int32_t con_qual = (int32_t)e.base_cc * 2 - (int32_t)e.base_tc;
-        if (e.base_tc > 0 && symbols_mutated(ref, a)) {
-            if (con_qual >= v.par.bias_thres_highBQ) { bits |= (1u << UVC_FM_MUT_BASE_HQ); }
-            if (con_qual > 0) { bits |= (1u << UVC_FM_MUT_BASE_ANY); }
-        }
-        if (e.link_cc | e.base_tc) { bits |= (1u << UVC_FM_COV); }
-    }
-    v.fcol[i] = e;
-    return bits;
+    return kf_store_entry(v, i, gp, covered, la, lcc, ba, bcc, btc, n_votes);
 }
 // folds one entry's bits into the chunk masks (emulation / non-ballot path)
 UVC_HD void kf_fold_bits(const BatchView & v, int64_t i, uint32_t bits) {
