@@ -67,6 +67,14 @@ def test_cuda_pileup_general_paths(synth_small, synth_umi, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("block", ["64", "128"])
+def test_cuda_pileup_block_shapes(synth_small, tmp_path, block, monkeypatch):
+    """The position kernels pick 32, 64 or 128 threads per block from the batch size (small test tiles get 32): force the other shapes."""
+    monkeypatch.setenv("UVC_POS_BLOCK", block)
+    _check(synth_small, [(0, 0, 6000, 4), (0, 6000, 11995, 2)], False, tmp_path)
+
+
+@pytest.mark.gpu
 def test_cuda_pileup_matches_oracle_small(synth_small, tmp_path):
     _check(synth_small, [(0, 0, 6000, 4), (0, 6000, 11995, 2)], False, tmp_path)
 

@@ -265,11 +265,12 @@ struct __align__(16) K2Stage {
 __global__ void __launch_bounds__(128, UVC_K2_MINBLOCKS) uvc_k2_bias_pileup(const BatchView v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t gp = (i / 128) * 64 + (i % 64);
+    const int half = (int)(blockDim.x >> 1);                    // the block = `half` positions x 2 roles (64 or 128 threads)
+    const int64_t gp = (i / blockDim.x) * half + (i % half);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     K2Stage & S = ((K2Stage*)uvc_smem)[warp];
     const bool active = (gp < v.n_pos);
-    const int role = (int)((i % 128) / 64);
+    const int role = (int)((i % blockDim.x) / half);
     uvc::Win w;
     uvc_warp_window(v, gp, active, w);
     uvc::K2State st;
@@ -409,14 +410,14 @@ __global__ void __launch_bounds__(128, UVC_K3B_MINBLOCKS) uvc_k3b_fragment_conse
     const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Stage & S = ((Stage*)uvc_smem)[warp];
-    int32_t *hot_buckets = (int32_t*)(uvc_smem + 4 * sizeof(Stage)) + threadIdx.x;
+    int32_t *hot_buckets = (int32_t*)(uvc_smem + (blockDim.x >> 5) * sizeof(Stage)) + threadIdx.x;
     const bool active = (gp < n);
     uvc::Win w;
     uvc_warp_window(v, gp, active, w);
     uvc::K3bState st;
     uvc::K3bArrays arr;
     st.p = 0;
-    if (active) { uvc::k3b_begin(st, arr, v, gp, hot_buckets, 128); }
+    if (active) { uvc::k3b_begin(st, arr, v, gp, hot_buckets, (int)blockDim.x); }
     const int32_t p = st.p;
     const int64_t c0 = w.ulo & ~(int64_t)3;
     auto issue_records = [&](int64_t cb, int slot) { if (cb < w.uhi) { uvc_warp_stage_async(S.q[slot], v.rfrag, cb, uvc_chunk_len(cb, w.uhi), lane); } uvc_cp_async_commit(); };
@@ -592,13 +593,17 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     for (int i = 0; i < UVC_N_PILEUP_STAGES + 1; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreate(&bs.ev[i])); }
     bs.have_events = true;
     int e = 0;
+    // Threads per block of the position kernels (every warp is self-contained: its own staging slot, no block-wide synchronisation). A batch
+    // with few positions and deep windows (a small panel at very high depth) is cut into one-warp blocks so that every SM gets some.
+    int pb = (v.n_pos >= (int64_t)148 * 128 * 2 ? 128 : (v.n_pos >= (int64_t)148 * 64 * 2 ? 64 : 32));
+    { const char *f = getenv("UVC_POS_BLOCK"); if (f && (atoi(f) == 32 || atoi(f) == 64 || atoi(f) == 128)) { pb = atoi(f); } }   // tests force every shape
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
     #define UVC_STAGE(kernel, n) { launch(kernel, ctx->stream, v, (n), launches); UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream)); }
     UVC_STAGE(uvc_k0_read_consts, v.n_reads)
     if (v.n_pos > 0) {
         const size_t smem = 4 * sizeof(K2Stage);
         UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k1_prep_thres, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        uvc_k1_prep_thres<<<(unsigned)((v.n_pos + 127) / 128), 128, smem, ctx->stream>>>(v, v.n_pos);
+        uvc_k1_prep_thres<<<(unsigned)((v.n_pos + pb - 1) / pb), pb, smem * pb / 128, ctx->stream>>>(v, v.n_pos);
         launches++;
     }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
@@ -606,7 +611,8 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
         static_assert(sizeof(K2Stage) % 16 == 0, "per-warp staging slots keep 16-byte alignment");
         const size_t smem = 4 * sizeof(K2Stage);
         UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k2_bias_pileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        uvc_k2_bias_pileup<<<(unsigned)((v.n_pos + 63) / 64), 128, smem, ctx->stream>>>(v, v.n_pos);
+        const int pb2 = (pb < 64 ? 64 : pb);     // two roles: at least one warp each
+        uvc_k2_bias_pileup<<<(unsigned)((v.n_pos + pb2 / 2 - 1) / (pb2 / 2)), pb2, smem * pb2 / 128, ctx->stream>>>(v, v.n_pos);
         launches++;
     }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
@@ -615,9 +621,10 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     UVC_STAGE(uvc_k3a_fragment_stats, v.n_frags)
     if (v.n_pos > 0) {
         static_assert(sizeof(ColStage<ReadFrag>) % 16 == 0, "per-warp staging slots keep 16-byte alignment");
-        const size_t smem = 4 * sizeof(ColStage<ReadFrag>) + 2 * UVC_NUM_BUCKETS * 128 * sizeof(int32_t);
-        UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k3b_fragment_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        uvc_k3b_fragment_consensus<<<(unsigned)((v.n_pos + 127) / 128), 128, smem, ctx->stream>>>(v, v.n_pos);
+        const size_t smem = (pb / 32) * sizeof(ColStage<ReadFrag>) + 2 * UVC_NUM_BUCKETS * pb * sizeof(int32_t);
+        const size_t smem_max = 4 * sizeof(ColStage<ReadFrag>) + 2 * UVC_NUM_BUCKETS * 128 * sizeof(int32_t);   // (the attribute is shared by all contexts: always the largest shape)
+        UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k3b_fragment_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        uvc_k3b_fragment_consensus<<<(unsigned)((v.n_pos + pb - 1) / pb), pb, smem, ctx->stream>>>(v, v.n_pos);
         launches++;
     }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
@@ -627,7 +634,7 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
         static_assert(sizeof(ColStage<ReadFam>) % 16 == 0, "per-warp staging slots keep 16-byte alignment");
         const size_t smem = 4 * sizeof(ColStage<ReadFam>);
         UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k4_family_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        uvc_k4_family_consensus<<<(unsigned)((v.n_pos + 127) / 128), 128, smem, ctx->stream>>>(v, v.n_pos);
+        uvc_k4_family_consensus<<<(unsigned)((v.n_pos + pb - 1) / pb), pb, smem * pb / 128, ctx->stream>>>(v, v.n_pos);
         launches++;
     }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
