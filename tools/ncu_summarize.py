@@ -12,7 +12,7 @@ from collections import OrderedDict
 
 STAGE_OF = {"uvc_k0_read_consts": "K0 per-read", "uvc_k1_prep_thres": "K1 prep+thres", "uvc_k2_bias_pileup": "K2 bias pileup", "uvc_k2e_indel_events": "K2e indel events",
             "uvc_kf_fragment_columns": "KF fragment columns", "uvc_k3a_fragment_stats": "K3a fragment stats", "uvc_k3b_fragment_consensus": "K3b fragment consensus",
-            "uvc_km_family_columns": "KM family columns", "uvc_k4a_family_ends": "K4a family ends", "uvc_k4_family_consensus": "K4 family+duplex consensus",
+            "uvc_km_family_columns": "KM family columns", "uvc_k4a_family_ends": "K4a family ends", "uvc_k4_family_consensus": "K4 family+duplex consensus", "uvc_k4_family_consensus_umi": "K4 family+duplex consensus",
             "uvc_k4c_family_haplotypes": "K4c family haplotypes", "uvc_k6_gvcf_inputs": "K6 block-line inputs", "uvc_k5_score_candidates": "K5 candidate scoring",
             "uvc_k5a_flag_candidates": "K5 candidate scoring"}
 

@@ -89,6 +89,7 @@ struct uvcgpu_ctx {
 // Page-locking memory is slow (~1 GB/s), so it is never done on the critical path: a request that finds no cached page-locked block of its
 // size class is served from pageable memory at once, and a background thread page-locks a block of that class for the NEXT batch. Short
 // runs therefore start immediately, long runs converge to fully page-locked staging (asynchronous DMA both ways).
+#include <type_traits>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -459,14 +460,25 @@ __global__ void __launch_bounds__(128, UVC_K3B_MINBLOCKS) uvc_k3b_fragment_conse
     uvc_cp_async_wait<0>();
     if (active) { uvc::k3b_end(st, v); }
 }
-// K4: records = ReadFam (built on the host). Entries of single-fragment family-strands are the 8-byte fragment entries, fetched through the
-// pipeline; the 32-byte entries of multi-fragment (UMI) families are read in place.
+// K4: records = ReadFam (built on the host). Two shapes of the column-entry pipeline:
+//   narrow (non-UMI data: nearly every (family, strand) is a single fragment): 16 reads per chunk, 8-byte fragment entries through the
+//          pipeline, the few 32-byte entries of multi-fragment families read in place;
+//   wide   (UMI data: most strands hold several fragments): 8 reads per chunk, 32-byte slots that receive either entry kind, so that the
+//          family entries of both walks of the window are in flight one chunk ahead as well.
 #ifndef UVC_K4_MINBLOCKS
 #define UVC_K4_MINBLOCKS 4     // 128 registers: four blocks per SM
 #endif
-__global__ void __launch_bounds__(128, UVC_K4_MINBLOCKS) uvc_k4_family_consensus(const BatchView v, int64_t n) {
+template <bool kWide> struct __align__(16) K4StageT {
+    static const int kReads = (kWide ? 8 : UVC_COL_READS);
+    ReadFam q[3][kReads];
+    typename std::conditional<kWide, FamCol, FragCol>::type e[2][kReads][32];
+};
+__device__ __forceinline__ void uvc_cp_async16x2(void *smem_dst, const void *gmem_src) { uvc_cp_async16(smem_dst, gmem_src); uvc_cp_async16((char*)smem_dst + 16, (const char*)gmem_src + 16); }
+
+template <bool kWide> __device__ __forceinline__ void uvc_k4_body(const BatchView & v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
-    typedef ColStage<ReadFam> Stage;
+    typedef K4StageT<kWide> Stage;
+    const int kReads = Stage::kReads;
     const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Stage & S = ((Stage*)uvc_smem)[warp];
@@ -479,72 +491,76 @@ __global__ void __launch_bounds__(128, UVC_K4_MINBLOCKS) uvc_k4_family_consensus
     if (active) { uvc::k4_begin(st, arr, v, gp); }
     const int32_t p = st.p;
     const int64_t c0 = w.ulo & ~(int64_t)3;
-    auto issue_records = [&](int64_t cb, int slot) { if (cb < w.uhi) { uvc_warp_stage_async(S.q[slot], v.rfam, cb, uvc_chunk_len(cb, w.uhi), lane); } uvc_cp_async_commit(); };
-    auto issue_entries = [&](int64_t cb, int rslot, int eslot) {
-        if (cb < w.uhi && active) {
-            const int nc = uvc_chunk_len(cb, w.uhi);
+    auto chunk_len = [&](int64_t cb) { return (int)(w.uhi - cb < kReads ? w.uhi - cb : kReads); };
+    auto issue_records = [&](int64_t cb, int slot) { if (cb < w.uhi) { uvc_warp_stage_async(S.q[slot], v.rfam, cb, chunk_len(cb), lane); } uvc_cp_async_commit(); };
+    // entries of the reads of this lane's own window that are the first read of their (family, strand) at p
+    auto issue_entries = [&](int64_t cb, int rslot, int eslot, bool wanted) {
+        if (cb < w.uhi && wanted) {
+            const int nc = chunk_len(cb);
             for (int k = 0; k < nc; k++) {
                 const int64_t ri = cb + k;
                 const ReadFam & q = S.q[rslot][k];
-                // a read of this lane's own window, first read of its (family, strand) at p, single-fragment strand
-                if (ri >= w.lo && ri < w.hi && q.rend > p && q.famprev_maxrend <= p && (q.flags & UVC_RF_DIRECT)) { uvc_cp_async8(&S.e[eslot][k][lane], v.fcol + (q.col_base + p)); }
+                if (!(ri >= w.lo && ri < w.hi && q.rend > p && q.famprev_maxrend <= p)) { continue; }
+                if (q.flags & UVC_RF_DIRECT) { uvc_cp_async8(&S.e[eslot][k][lane], v.fcol + (q.col_base + p)); }
+                else if (kWide) { uvc_cp_async16x2(&S.e[eslot][k][lane], v.mcol + (q.col_base + p)); }
             }
         }
         uvc_cp_async_commit();
     };
-    // ---- loop 1 (with the share of loop 2 that needs nothing from other families)
-    issue_records(c0, 0);
-    issue_records(c0 + UVC_COL_READS, 1);
-    uvc_cp_async_wait<1>();
-    __syncwarp();
-    issue_entries(c0, 0, 0);
-    int i = 0;
-    for (int64_t cb = c0; cb < w.uhi; cb += UVC_COL_READS, i++) {
-        const int rs = i % 3, es = i & 1;
-        issue_records(cb + 2 * UVC_COL_READS, (i + 2) % 3);
+    // the (family, strand) entry of staged read q: from the slot, or (narrow shape, multi-fragment strand) from global memory
+    auto entry_of = [&](const ReadFam & q, int eslot, int k) -> FamCol {
+        if (q.flags & UVC_RF_DIRECT) { return uvc::famcol_from_frag(*(const FragCol*)&S.e[eslot][k][lane], v.par); }
+        if (kWide) { return *(const FamCol*)&S.e[eslot][k][lane]; }
+        return v.mcol[q.col_base + p];
+    };
+    // one walk of the window through the pipeline; pass 0 = loop 1 (with the share of loop 2 that needs nothing from other families),
+    // pass 1 = loop 2 for the positions whose need-list overflowed (UMI data)
+    auto walk = [&](const int pass) {
+        const bool mine = (active && (pass == 0 || st.n_need2 > UVC_K4_LIST));
+        issue_records(c0, 0);
+        issue_records(c0 + kReads, 1);
         uvc_cp_async_wait<1>();
         __syncwarp();
-        issue_entries(cb + UVC_COL_READS, (i + 1) % 3, es ^ 1);
-        if (active) {
-            const int nc = uvc_chunk_len(cb, w.uhi);
-            for (int k = 0; k < nc; k++) {
-                const int64_t ri = cb + k;
-                if (ri < w.lo || ri >= w.hi) { continue; }
-                const ReadFam q = S.q[rs][k];
-                if (q.rend <= p || q.famprev_maxrend > p) { continue; }
-                if ((q.flags & UVC_RF_DIRECT) && uvc::k4_loop1_lone_fragment(st, v, q, S.e[es][k][lane])) { continue; }
-                uvc::k4_loop1_read(st, v, q, (q.flags & UVC_RF_DIRECT) ? uvc::famcol_from_frag(S.e[es][k][lane], v.par) : v.mcol[q.col_base + p], ri - w.lo);
-            }
-        }
-        __syncwarp();
-    }
-    uvc_cp_async_wait<0>();
-    // ---- loop 2 for what is left: the short list first; positions whose list overflowed (UMI data) walk the window again
-    if (active) { uvc::k4_loop2_listed(st, v, w); }
-    if (__any_sync(0xffffffffu, active && st.n_need2 > UVC_K4_LIST)) {
-        __syncwarp();
-        issue_records(c0, 0);
-        i = 0;
-        for (int64_t cb = c0; cb < w.uhi; cb += UVC_COL_READS, i++) {
-            issue_records(cb + UVC_COL_READS, (i + 1) & 1);
+        issue_entries(c0, 0, 0, mine);
+        int i = 0;
+        for (int64_t cb = c0; cb < w.uhi; cb += kReads, i++) {
+            const int rs = i % 3, es = i & 1;
+            issue_records(cb + 2 * kReads, (i + 2) % 3);
             uvc_cp_async_wait<1>();
             __syncwarp();
-            if (active && st.n_need2 > UVC_K4_LIST) {
-                const int nc = uvc_chunk_len(cb, w.uhi);
+            issue_entries(cb + kReads, (i + 1) % 3, es ^ 1, mine);
+            if (mine) {
+                const int nc = chunk_len(cb);
                 for (int k = 0; k < nc; k++) {
                     const int64_t ri = cb + k;
                     if (ri < w.lo || ri >= w.hi) { continue; }
-                    const ReadFam q = S.q[i & 1][k];
+                    const ReadFam q = S.q[rs][k];
                     if (q.rend <= p) { continue; }
-                    uvc::k4_loop2_read(st, v, q);
+                    if (pass == 0) {
+                        if (q.famprev_maxrend > p) { continue; }
+                        if ((q.flags & UVC_RF_DIRECT) && uvc::k4_loop1_lone_fragment(st, v, q, *(const FragCol*)&S.e[es][k][lane])) { continue; }
+                        uvc::k4_loop1_read(st, v, q, entry_of(q, es, k), ri - w.lo);
+                    } else if (q.famprev_maxrend <= p) {
+                        const FamCol m = entry_of(q, es, k);
+                        uvc::k4_loop2_read(st, v, q, &m);
+                    } else {
+                        uvc::k4_loop2_read(st, v, q, NULL);     // (not the first read of its strand here: nothing to fetch, nothing to do)
+                    }
                 }
             }
             __syncwarp();
         }
         uvc_cp_async_wait<0>();
-    }
+        __syncwarp();
+    };
+    walk(0);
+    // loop 2 for what is left: the short list first; positions whose list overflowed walk the window again
+    if (active) { uvc::k4_loop2_listed(st, v, w); }
+    if (__any_sync(0xffffffffu, active && st.n_need2 > UVC_K4_LIST)) { walk(1); }
     if (active) { uvc::k4_end(st, v); }
 }
+__global__ void __launch_bounds__(128, UVC_K4_MINBLOCKS) uvc_k4_family_consensus(const BatchView v, int64_t n) { uvc_k4_body<false>(v, n); }
+__global__ void __launch_bounds__(128, 3) uvc_k4_family_consensus_umi(const BatchView v, int64_t n) { uvc_k4_body<true>(v, n); }
 UVC_DEFINE_KERNEL(uvc_k4c_family_haplotypes, uvc::k4c_family_strand(v, i))
 
 // scoring stage: K6 one thread per extended position, K5 one thread per zero-based position (heavy local state: 64 threads per block)
@@ -631,10 +647,14 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     UVC_STAGE(uvc_km_family_columns, v.n_mcol)
     UVC_STAGE(uvc_k4a_family_ends, 2 * v.n_fams)
     if (v.n_pos > 0) {
-        static_assert(sizeof(ColStage<ReadFam>) % 16 == 0, "per-warp staging slots keep 16-byte alignment");
-        const size_t smem = 4 * sizeof(ColStage<ReadFam>);
-        UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k4_family_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        uvc_k4_family_consensus<<<(unsigned)((v.n_pos + pb - 1) / pb), pb, smem * pb / 128, ctx->stream>>>(v, v.n_pos);
+        static_assert(sizeof(K4StageT<false>) % 16 == 0 && sizeof(K4StageT<true>) % 16 == 0, "per-warp staging slots keep 16-byte alignment");
+        // the wide shape when a good part of the column entries belongs to multi-fragment (UMI) families
+        const bool wide = (v.n_mcol * 16 >= v.n_fcol);
+        const size_t smem = 4 * (wide ? sizeof(K4StageT<true>) : sizeof(K4StageT<false>));
+        UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k4_family_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(K4StageT<false>))));
+        UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k4_family_consensus_umi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(K4StageT<true>))));
+        if (wide) { uvc_k4_family_consensus_umi<<<(unsigned)((v.n_pos + pb - 1) / pb), pb, smem * pb / 128, ctx->stream>>>(v, v.n_pos); }
+        else { uvc_k4_family_consensus<<<(unsigned)((v.n_pos + pb - 1) / pb), pb, smem * pb / 128, ctx->stream>>>(v, v.n_pos); }
         launches++;
     }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));

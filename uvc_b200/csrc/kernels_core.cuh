@@ -605,6 +605,15 @@ UVC_HD void bidir_bias(int32_t & lp1, int32_t & lp2, int32_t & rp1, int32_t & rp
     lpl += nl; rpl += nr;
 }
 
+// The same update on records in global memory that only this thread writes, as fire-and-forget reductions (no read-modify-write round trips)
+UVC_HD void bidir_bias_red(int32_t *lp1, int32_t *lp2, int32_t *rp1, int32_t *rp2, int32_t L1, int32_t L2, int32_t R1, int32_t R2,
+        int32_t nl, int32_t nr, bool tier2, int32_t n_indel) {
+    if (nl + n_indel >= L1) { atomic_add(lp1, 1); }
+    if ((nl + n_indel >= L2) && tier2) { atomic_add(lp2, 1); }
+    if (nr >= R1) { atomic_add(rp1, 1); }
+    if ((nr >= R2) && tier2) { atomic_add(rp2, 1); }
+}
+
 // One call of dealwith_segbias<isGap> (main.hpp:1360-1595) for read R at position rpos with quality bq, into accumulator a.
 template <bool isGap>
 UVC_HD void segbias(SegAcc & a, const BatchView & v, const ReadRec & R, const ReadDerived & D, const uvcgpu_thres_set & th,
@@ -1838,23 +1847,24 @@ UVC_HD void k4_loop1_read(K4State & s, const BatchView & v, const ReadFam & q, c
                 for (int sym = UVC_LINK_D3P; sym <= UVC_LINK_D1; sym++) { int32_t n = 0; fam_indel_majority(v, F, strand, p, gp, sym, &n); indel_len = tmax(indel_len, n); }
             }
             const bool far_from_edge = (l_nb + (is_ins_symbol(a) ? nnminus(indel_len, par.microadjust_nobias_pos_indel_maxlen) : 0) >= LPxT) && (r_nb >= th.aRPxT);
+            // (the family records of a position have this thread as their only writer; reductions instead of ~15 dependent read-modify-writes)
             if (far_from_edge) {
-                int64_t lpl = 0, rpl = 0;
-                bidir_bias(fi.c2LP1, fi.c2LP2, fi.c2RP1, fi.c2RP2, lpl, rpl, th.aLP1t, th.aLP2t, th.aRP1t, th.aRP2t, l_nb, r_nb, true, 0);
-                fi.c2LPL += (int32_t)lpl; fi.c2RPL += (int32_t)rpl;
+                bidir_bias_red(&fi.c2LP1, &fi.c2LP2, &fi.c2RP1, &fi.c2RP2, th.aLP1t, th.aLP2t, th.aRP1t, th.aRP2t, l_nb, r_nb, true, 0);
+                atomic_add(&fi.c2LPL, l_nb); atomic_add(&fi.c2RPL, r_nb);
             }
-            if (nnminus(p + 1, F.nsb_min[strand]) >= par.bias_thres_strict_c2LRP0) { fi.c2LP0 += 1; }
-            if (nnminus(F.nsb_max[strand], p) >= par.bias_thres_strict_c2LRP0) { fi.c2RP0 += 1; }
+            if (nnminus(p + 1, F.nsb_min[strand]) >= par.bias_thres_strict_c2LRP0) { atomic_add(&fi.c2LP0, 1); }
+            if (nnminus(F.nsb_max[strand], p) >= par.bias_thres_strict_c2LRP0) { atomic_add(&fi.c2RP0, 1); }
             const int32_t seg_l_baq = baq[p] - baq[tmax(rbeg, nnminus(p, UVC_MAX_STR_N_BASES))] + 1;
             const int32_t ridx = tmin(rend - 1, tmin(p + UVC_MAX_STR_N_BASES, s.baq_last));
             const int32_t seg_r_baq0 = baq[ridx] - baq[p] + 1;
             const int32_t seg_r_baq = (isGap ? tmin(seg_r_baq0, baq2[ridx] - baq2[p] + 7) : seg_r_baq0);
             const int32_t highBAQ = par.bias_thres_highBAQ + (isGap ? 0 : 3);
             if (seg_l_baq >= highBAQ && seg_r_baq >= highBAQ) {
-                bidir_bias(fi.c2LB1, fi.c2LB2, fi.c2RB1, fi.c2RB2, fi.c2LBL, fi.c2RBL, par.bias_thres_BAQ1, par.bias_thres_BAQ2, par.bias_thres_BAQ1, par.bias_thres_BAQ2,
+                bidir_bias_red(&fi.c2LB1, &fi.c2LB2, &fi.c2RB1, &fi.c2RB2, par.bias_thres_BAQ1, par.bias_thres_BAQ2, par.bias_thres_BAQ1, par.bias_thres_BAQ2,
                         seg_l_baq, seg_r_baq, true, 0);
+                atomic_add(&fi.c2LBL, (int64_t)seg_l_baq); atomic_add(&fi.c2RBL, (int64_t)seg_r_baq);
             }
-            fi.c2BQ2 += 1;
+            atomic_add(&fi.c2BQ2, 1);
         }
         if (par.fam_thres_dup2add <= tc && (cc * 100 >= tc * par.fam_thres_dup2perc)) { d.dp3 = 1; }
         if (is_indel) {
@@ -1893,7 +1903,7 @@ UVC_HD void k4_loop1_read(K4State & s, const BatchView & v, const ReadFam & q, c
 
 // loop 2 for a read q that covers p (q.rend > p), for what loop 1 left over. Only reads that loop 1 visited can have work here: the duplex
 // step wants the first read of the whole family at p, which is also the first read of its own strand.
-UVC_HD void k4_loop2_read(K4State & s, const BatchView & v, const ReadFam & q) {
+UVC_HD void k4_loop2_read(K4State & s, const BatchView & v, const ReadFam & q, const FamCol *pre = NULL) {   // pre: the read's (family, strand) entry at p, if the caller holds it
     const uvcgpu_params & par = v.par;
     const int32_t p = s.p;
     const int64_t gp = s.gp;
@@ -1904,7 +1914,7 @@ UVC_HD void k4_loop2_read(K4State & s, const BatchView & v, const ReadFam & q) {
     if (q.famprev_maxrend <= p) {   // first read of its (family, strand) that covers p
         const int strand = (int)(q.flags & UVC_RF_STRAND);
         int32_t *fd = s.facc + strand * (UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS);
-        const FamCol m = fam_entry_of_read(v, q, p);
+        const FamCol m = (pre ? *pre : fam_entry_of_read(v, q, p));
         #pragma unroll
         for (int type = 1; type >= 0; type--) {
             const int a = m.a2[type]; const int32_t con_sumBQs = (int32_t)m.mmm_cc[type], tot_sumBQs = (int32_t)m.mmm_tot[type];
