@@ -402,11 +402,17 @@ def main():
     step_ms = kernel_ms / args.steps
     path_bytes = last.n_reads_kept * (1.5 * 150 + 64) + last.n_ext_positions * 2 * 6272
     traffic = None
+    issue = None
     try:   # dram bytes of that kernel from the committed ncu --set full capture of the same workload (profiles/), per launch
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
         ent = tj.get("%s@%g" % (name, scale), {}).get(dom_name)
         if ent:
             traffic = ent["dram_bytes"]
+            if ent.get("ipc_per_sm"):
+                # the kernel is bound by instruction issue, not by bytes: the same capture's issue rate against the 4 warp
+                # instructions per cycle an SM can issue
+                issue = {"bound": "issue", "achieved": ent["ipc_per_sm"], "peak": 4.0, "unit": "warp instructions/cycle/SM", "frac": ent["ipc_per_sm"] / 4.0,
+                         "warp_instructions": ent.get("warp_instructions"), "resident_warps_pct": ent.get("resident_warps_pct"), "source": "profiles/r01_traffic.json (ncu --set full)"}
     except Exception:
         pass
     line = {"metric": metric, "value": value, "unit": "reads/s",
@@ -432,7 +438,8 @@ def main():
                          "kernel": dom_name, "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / step_ms, "algorithmic_bytes": dom_bytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "whole_path": {"algorithmic_bytes": path_bytes, "achieved": path_bytes / (step_ms / 1e3) / 1e9,
-                                        "frac": path_bytes / (step_ms / 1e3) / 1e9 / peak}},
+                                        "frac": path_bytes / (step_ms / 1e3) / 1e9 / peak},
+                         "issue": issue},
             "clocks": sampler.summary()}
     if not args.skip_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "uvc1")):
         try:

@@ -70,7 +70,11 @@ def full(rep, out, traffic_json, key):
                 u = units[ix[m]]
                 return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}.get(u, 1.0)
             if name in STAGE_OF:
+                def num(m):
+                    return float(r[ix[m]].replace(",", "")) if m in ix and r[ix[m]] else None
                 ent[STAGE_OF[name]] = {"dram_bytes": gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum"), "ms_under_profiler": float(r[ix["gpu__time_duration.sum"]].replace(",", "")),
+                                       "warp_instructions": num("smsp__inst_executed.sum"), "ipc_per_sm": num("sm__inst_executed.avg.per_cycle_elapsed"),
+                                       "resident_warps_pct": num("sm__warps_active.avg.pct_of_peak_sustained_active"), "registers": num("launch__registers_per_thread"),
                                        "source": rep.split("/")[-1]}
     json.dump(tj, open(traffic_json, "w"), indent=1, sort_keys=True)
 
