@@ -352,14 +352,23 @@ def main():
 
     e2e_steps(n_warm)
     # steady state: the library page-locks its staging blocks in the background; warm up until none is outstanding (bounded)
+    # (page-locking while batches are in flight also slows every CUDA call down, so the timed region must not trigger any: warm up until the
+    # cache has stopped growing for two rounds in a row)
     ctx0.lib.uvcgpu_staging_backlog.restype = C.c_int
-    for _ in range(8):
+    ctx0.lib.uvcgpu_staging_pinned_bytes.restype = C.c_int64
+    stable = 0
+    for _ in range(16):
         t_wait = time.time()
         while ctx0.lib.uvcgpu_staging_backlog() > 0 and time.time() - t_wait < 10.0:
             time.sleep(0.05)
+        before = int(ctx0.lib.uvcgpu_staging_pinned_bytes())
         e2e_steps(2)
-        if ctx0.lib.uvcgpu_staging_backlog() == 0:
+        grown = (ctx0.lib.uvcgpu_staging_backlog() > 0 or int(ctx0.lib.uvcgpu_staging_pinned_bytes()) != before)
+        stable = 0 if grown else stable + 1
+        if stable >= 2:
             break
+    backlog0 = int(ctx0.lib.uvcgpu_staging_backlog())
+    pinned0 = int(ctx0.lib.uvcgpu_staging_pinned_bytes())
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -369,6 +378,7 @@ def main():
         totals[k] += acc[k]
     torch.cuda.synchronize()
     wall_s = time.time() - t0
+    backlog1 = int(ctx0.lib.uvcgpu_staging_backlog())
     sampler.stop_flag = True
     if world > 1:
         tt = torch.tensor([kernel_ms, wall_s], device="cuda", dtype=torch.float64)
@@ -431,7 +441,9 @@ def main():
                     "vcf_bytes_per_step": totals["vcf"] // args.steps, "vcf_records_per_step": totals["rec"] // args.steps,
                     "host_prep_ms_per_step_summed_over_contexts": totals["prep_ms"] / args.steps,
                     "call_ms_per_step_summed_over_contexts": {k[:-2]: totals[k] * 1e3 / args.steps for k in ("submit_s", "wait_s", "score_s", "text_s", "release_s")},
-                    "wall_ms_per_step": wall_s * 1e3 / args.steps},
+                    "wall_ms_per_step": wall_s * 1e3 / args.steps,
+                    "staging_blocks_not_yet_page_locked": {"at_start": backlog0, "at_end": backlog1},
+                    "staging_page_locked_bytes": {"at_start": pinned0, "at_end": int(ctx0.lib.uvcgpu_staging_pinned_bytes())}},
             "gpu_launches": launches + totals["launch"],
             "stage_ms_per_step": {n: stage_ms[i] / args.steps for i, n in enumerate(STAGE_NAMES)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

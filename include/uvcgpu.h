@@ -334,6 +334,8 @@ int uvcgpu_device_warmup(int device);
  * page-locking: a batch that finds no page-locked block of the size it needs stages through pageable memory (slower copies) and the block is
  * provisioned for the next one. A benchmark polls this after its warm-up to know that the steady state has been reached. */
 int uvcgpu_staging_backlog(void);
+/* Bytes of host staging memory the library has page-locked so far (process-wide); constant once the cache has seen the caller's steady state. */
+int64_t uvcgpu_staging_pinned_bytes(void);
 
 /* sizeof(uvcgpu_params) as the library was compiled, so that foreign-language bindings can verify their mirror of the struct. */
 size_t uvcgpu_sizeof_params(void);

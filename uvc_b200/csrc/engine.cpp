@@ -866,6 +866,16 @@ int uvcgpu_staging_backlog(void) {
 #endif
 }
 
+int64_t uvcgpu_staging_pinned_bytes(void) {
+#if UVC_CUDA
+    StageState & st = stage_state();
+    std::lock_guard<std::mutex> lk(st.mu);
+    return (int64_t)st.total_pinned;
+#else
+    return 0;
+#endif
+}
+
 int uvcgpu_device_warmup(int device) {
 #if UVC_CUDA
     int n = 0;
