@@ -453,7 +453,7 @@ def main():
                                         "frac": path_bytes / (step_ms / 1e3) / 1e9 / peak},
                          "issue": issue},
             "clocks": sampler.summary()}
-    if not args.skip_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "uvc1")):
+    if world == 1 and not args.skip_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "uvc1")):   # (reported at N = 1 only)
         try:
             res = run_reference(args, ds, name)
             line["cpu_baseline"] = {"value": res["value"], "unit": "reads/s", "cores": res["cores"], "kind": "reference", "sample": res["sample"],
