@@ -252,7 +252,7 @@ __device__ __forceinline__ void uvc_gather_bases(const BatchView & v, const Read
 }
 
 // K2: both roles of a position sit in different warps of the same block: block = 64 positions x 2 roles.
-// Each warp stages the records (ReadRec + ReadDerived) of 32 reads of its union window in shared memory (asynchronously, one chunk ahead),
+// Each warp stages the records (ReadRec + ReadDerived) of UVC_STAGE_READS reads of its union window in shared memory (asynchronously, one chunk ahead),
 // role 0 then gathers the (base, quality) byte pairs of the whole chunk with independent loads (memory-level parallelism instead of one
 // dependent load pair per read), and the per-read work runs entirely from shared memory.
 struct __align__(16) K2Stage {
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(128, UVC_K2_MINBLOCKS) uvc_k2_bias_pileup(cons
     }
     if (active) { uvc::k2_end(st, v); }
 }
-// K1: one thread per position; same staging as K2 (the records of 32 reads per warp, one chunk ahead) and the same grouped byte gather
+// K1: one thread per position; same staging as K2 (the records of UVC_STAGE_READS reads per warp, one chunk ahead) and the same grouped byte gather
 __global__ void __launch_bounds__(128) uvc_k1_prep_thres(const BatchView v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
     const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -766,7 +766,7 @@ UVC_HD uint32_t k2_fetch_base(const K2State & s, const BatchView & v, const Read
     return pack_base(v.seq[R.seq_off + (uint32_t)(qc >> 1)], v.qual[R.qual_off + (uint32_t)qc], qpos);
 }
 
-// one read of the position's window (R, D may live in shared memory: the CUDA kernel stages the records of 32 reads per warp at a time);
+// one read of the position's window (R, D may live in shared memory: the CUDA kernel stages the records of UVC_STAGE_READS reads per warp at a time);
 // `packed` is k2_fetch_base of this read (role 0 only)
 UVC_HD void k2_read(K2State & s, const BatchView & v, const ReadRec & R, const ReadDerived & D, uint32_t packed) {
     const int32_t p = s.p;
