@@ -480,19 +480,23 @@ UVC_HD void k1_read(K1State & s, const BatchView & v, const ReadRec & R, const R
     a.a_dp += 1;
     a.a_qlen += span;
     a.a_XM1500 += D.xm1500; a.a_GO1500 += D.go1500; a.a_GAPLEN += D.avg_gaplen;
-    if (R.isize != 0) {
+    // (conditions as 0/1 factors instead of branches, as in segbias)
+    {
         const int32_t fl = tmin(R.pos, R.mpos);
-        if (R.flag & 0x10) { a.a_LI += tmin(p - fl + 1, UVC_MAX_INSERT_SIZE); a.a_LIDP += 1; }
-        else { a.a_RI += tmin(fl + iabs(R.isize) - p, UVC_MAX_INSERT_SIZE); a.a_RIDP += 1; }
+        const int32_t has = ((R.isize != 0) ? 1 : 0), rc = ((R.flag & 0x10) ? 1 : 0);
+        const int32_t li = has * rc, ri = has * (1 - rc);
+        a.a_LI += (int64_t)(li * tmin(p - fl + 1, UVC_MAX_INSERT_SIZE)); a.a_LIDP += li;
+        a.a_RI += (int64_t)(ri * tmin(fl + iabs(R.isize) - p, UVC_MAX_INSERT_SIZE)); a.a_RIDP += ri;
     }
-    if ((int32_t)(packed & 0xffu) >= v.par.bias_thres_highBQ) {
-        a.a_l_dist_sum += p - R.pos + 1;
-        a.a_r_dist_sum += R.rend - p;
-        a.a_inslen_sum += D.inslen_sum; a.a_dellen_sum += D.dellen_sum;
-        a.a_l_BAQ_sum += s.baq_p - D.baq_pos + 1;
-        a.a_r_BAQ_sum += D.baq_rend1 - s.baq_p + 1;
-        a.a_insBAQ_sum += D.insbaq_sum; a.a_delBAQ_sum += D.delbaq_sum;
-        a.a_highBQ_dp += 1;
+    {
+        const int32_t hq = (((int32_t)(packed & 0xffu) >= v.par.bias_thres_highBQ) ? 1 : 0);
+        a.a_l_dist_sum += hq * (p - R.pos + 1);
+        a.a_r_dist_sum += hq * (R.rend - p);
+        a.a_inslen_sum += hq * D.inslen_sum; a.a_dellen_sum += hq * D.dellen_sum;
+        a.a_l_BAQ_sum += (int64_t)(hq * (s.baq_p - D.baq_pos + 1));
+        a.a_r_BAQ_sum += (int64_t)(hq * (D.baq_rend1 - s.baq_p + 1));
+        a.a_insBAQ_sum += (int64_t)(hq * D.insbaq_sum); a.a_delBAQ_sum += (int64_t)(hq * D.delbaq_sum);
+        a.a_highBQ_dp += hq;
     }
 }
 UVC_HD void k1_end(K1State & s, const BatchView & v);
