@@ -206,7 +206,44 @@ __device__ __forceinline__ void uvc_warp_window(const BatchView & v, int64_t gp,
         uvc_warp_window(v, i, i < n, w); \
         if (i < n) { call; } \
     }
-UVC_DEFINE_KERNEL(uvc_k0_read_consts, uvc::k0_read(v, i))
+// K0: one thread per read, a warp = 32 consecutive reads. The per-base loops of a read (quality fix-ups, mismatch runs) touch its bases and
+// qualities byte by byte; a warp therefore first copies the bytes of its 32 reads into shared memory with coalesced loads (lane = byte), every
+// lane then works on its own row, and the corrected qualities go back with coalesced stores. Rows are padded to an odd number of words, so
+// that the 32 lanes reading byte i of their own rows hit different banks. Reads longer than the row work in place.
+#define UVC_K0_MAXQ 160
+#define UVC_K0_QSTRIDE 164      // 41 words
+#define UVC_K0_SSTRIDE 84       // 21 words (80 bytes of packed bases)
+__global__ void __launch_bounds__(128) uvc_k0_read_consts(const BatchView v, int64_t n) {
+    __shared__ __align__(16) uint8_t s_qual[4][32 * UVC_K0_QSTRIDE];
+    __shared__ __align__(16) uint8_t s_seq[4][32 * UVC_K0_SSTRIDE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t r0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane;     // first read of the warp
+    if (r0 >= n) { return; }
+    const int nr = (int)(n - r0 < 32 ? n - r0 : 32);
+    uint8_t *sq = s_qual[warp], *ss = s_seq[warp];
+    for (int k = 0; k < nr; k++) {
+        const ReadRec & R = v.reads[r0 + k];
+        const int32_t l = R.l_qseq;
+        if (l > UVC_K0_MAXQ) { continue; }
+        const uint8_t *gq = v.qual + R.qual_off, *gs = v.seq + R.seq_off;
+        for (int32_t i = lane; i < l; i += 32) { sq[k * UVC_K0_QSTRIDE + i] = gq[i]; }
+        for (int32_t i = lane; i < (l + 1) / 2; i += 32) { ss[k * UVC_K0_SSTRIDE + i] = gs[i]; }
+    }
+    __syncwarp();
+    const int64_t ri = r0 + lane;
+    if (lane < nr) {
+        const bool staged = (v.reads[ri].l_qseq <= UVC_K0_MAXQ);
+        uvc::k0_read(v, ri, staged ? ss + lane * UVC_K0_SSTRIDE : NULL, staged ? sq + lane * UVC_K0_QSTRIDE : NULL);
+    }
+    __syncwarp();
+    for (int k = 0; k < nr; k++) {
+        const ReadRec & R = v.reads[r0 + k];
+        const int32_t l = R.l_qseq;
+        if (l > UVC_K0_MAXQ) { continue; }
+        uint8_t *gq = v.qual + R.qual_off;
+        for (int32_t i = lane; i < l; i += 32) { gq[i] = sq[k * UVC_K0_QSTRIDE + i]; }
+    }
+}
 // ---- warp-private staging of per-read records in shared memory, double-buffered with cp.async (LDGSTS)
 // A warp walks its union window in chunks of UVC_STAGE_READS reads. Chunk bases are multiples of 4 reads, so that every record array slice
 // starts on a 16-byte boundary (record sizes are multiples of 4 bytes) and is copied with 16-byte asynchronous copies; the copy of chunk

@@ -191,14 +191,17 @@ UVC_HD void fix_base_qualities(uint8_t *q, const uint8_t *seq, const uint32_t *c
 // Read-level constants (main.hpp:937-998, 1789-1885), the per-reference-base expansion and the low-quality-indel
 // neighbours of complex reads (main.hpp:1817-1859, 1897-1916, 2219-2252), the list of indel events, and the rare
 // per-operation contributions to the prep sets (insertions, deletions, clips, mismatch runs; main.hpp:1025-1046, 1069-1199).
-UVC_HD void k0_read(const BatchView & v, int64_t ri) {
+// seq_ro / qual_rw: where the read's packed bases and its base qualities live for the duration of the call (NULL: in the batch arrays; the CUDA
+// kernel passes shared-memory copies that it loads and stores with coalesced accesses). The qualities are corrected in place.
+UVC_HD void k0_read(const BatchView & v, int64_t ri, const uint8_t *seq_ro = NULL, uint8_t *qual_rw = NULL) {
     const ReadRec & R = v.reads[ri];
     ReadDerived D;
     const TileInfo & T = v.tiles[R.tile];
     const uint32_t *cigar = v.cigar + R.cigar_off;
-    const uint8_t *seq = v.seq + R.seq_off;
-    fix_base_qualities(v.qual + R.qual_off, seq, cigar, R, par_of(v));
-    const uint8_t *qual = v.qual + R.qual_off;
+    const uint8_t *seq = (seq_ro ? seq_ro : v.seq + R.seq_off);
+    uint8_t *qual_w = (qual_rw ? qual_rw : v.qual + R.qual_off);
+    fix_base_qualities(qual_w, seq, cigar, R, par_of(v));
+    const uint8_t *qual = qual_w;
     const int64_t po = T.pos_off - T.ext_beg;        // concatenated index of reference position x is po + x
     const int32_t npos = T.ext_end - T.ext_beg;
     const int32_t *baq = v.baq + po;
