@@ -424,11 +424,16 @@ static int build_tile_a(HostBatch & hb, TileWork & tw, const uvcgpu_params & par
             bam_beg = std::min(bam_beg, r.pos);
             bam_end = std::max(bam_end, r.rend);
             const char *qname = r.qname;
-            const size_t qlen = strlen(qname);
-            const char *umi_beg1 = strchr(qname, '#');
-            const char *umi_beg = (umi_beg1 ? umi_beg1 + 1 : qname + qlen);
-            const char *umi_end1 = strchr(umi_beg, '#');
-            const char *umi_end = (umi_end1 ? umi_end1 : qname + qlen);
+            // one pass over the name: its length, the first two '#' and the order-defining hash (str_hash(qname, 17), MolecularID / grouping.cpp:932)
+            size_t qlen = 0;
+            const char *hash1 = NULL, *hash2 = NULL;
+            uint64_t qh2 = 0;
+            for (const char *c = qname; *c; c++, qlen++) {
+                qh2 = qh2 * 17 + (uint64_t)(int64_t)*c;
+                if ('#' == *c) { if (!hash1) { hash1 = c; } else if (!hash2) { hash2 = c; } }
+            }
+            const char *umi_beg = (hash1 ? hash1 + 1 : qname + qlen);
+            const char *umi_end = (hash2 ? hash2 : qname + qlen);
             const bool umi_found = ((umi_beg + 1 < umi_end) && (1 /* MOLECULE_TAG_NONE */ != par.molecule_tag));
             bool duplex_found = false;
             const size_t umi_len = umi_end - umi_beg;
@@ -473,7 +478,7 @@ static int build_tile_a(HostBatch & hb, TileWork & tw, const uvcgpu_params & par
             const tidpos_t begpair(begtid, preserved ? r.pos : (beg2 - ARRPOS_MARGIN + fetch_tbeg));
             const tidpos_t endpair(endtid, preserved ? r.mpos : (end2 - ARRPOS_MARGIN + fetch_tbeg));
             Kept k;
-            k.raw = i; k.r = r; k.strand = read_strand(r.flag); k.qhash2 = str_hash(qname, 17);
+            k.raw = i; k.r = r; k.strand = read_strand(r.flag); k.qhash2 = qh2;
             k.umi_full = (umi_found ? StrView(umi_beg, umi_len) : StrView());
             k.begpair = begpair; k.endpair = endpair;
             // MolecularBarcode::createKey (MolecularID.hpp:20-51)
@@ -631,7 +636,7 @@ static void build_tile_b(HostBatch & hb, const TileWork & tw, const TileInfo & T
         int64_t cx_at = o.cx, ev_at = o.ev;
         for (size_t i = 0; i < kept.size(); i++) {
             const Kept & k = kept[i];
-            ReadRec R;
+            ReadRec & R = hb.reads[(size_t)o.read + i];      // built in place
             memset(&R, 0, sizeof(R));
             R.pos = k.r.pos; R.rend = k.r.rend; R.mpos = k.r.mpos; R.isize = k.r.isize;
             R.l_qseq = k.r.l_qseq; R.n_cigar = k.r.n_cigar; R.nm = k.r.nm;
@@ -651,7 +656,6 @@ static void build_tile_b(HostBatch & hb, const TileWork & tw, const TileInfo & T
             fam_maxrend[fkey] = std::max(fam_maxrend[fkey], R.rend);
             R.fambothprev_maxrend = famboth_maxrend[(size_t)k.fam_local];
             famboth_maxrend[(size_t)k.fam_local] = std::max(famboth_maxrend[(size_t)k.fam_local], R.rend);
-            hb.reads[(size_t)o.read + i] = R;
             hb.read_raw_index[(size_t)o.read + i] = k.raw;
         }
     }

@@ -1816,7 +1816,6 @@ UVC_HD void k4_loop1_read(K4State & s, const BatchView & v, const ReadFam & q, c
     const uvcgpu_thres_set & th = s.th;
     const FamRec & F = v.fams[q.fam];      // only dereferenced on the tier-2 (UMI family) path
     const int strand = (int)(q.flags & UVC_RF_STRAND);
-    int32_t *fd = s.facc + strand * (UVC_NSYM * UVCGPU_NUM_FAM_DEPTHS);
     #pragma unroll
     for (int type = 1; type >= 0; type--) {
         const int a = m.a1[type]; const int32_t cc = m.cc1[type], tc = m.tc1[type];
