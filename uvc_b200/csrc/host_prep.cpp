@@ -10,6 +10,7 @@
 #endif
 
 #include <algorithm>
+#include <mutex>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -336,6 +337,16 @@ void uvc_fill_view_constants(BatchView & v, const uvcgpu_params & par) {
 // Stage A (everything that decides sizes: filter, family grouping, fragment/family records) keeps its kept reads in TileWork; after the batch
 // offsets are known, stage B packs the reads and the per-position reference context of the tile straight into the batch arrays (one copy of
 // the sequence/quality bytes instead of two).
+// The kept-read vectors (a few hundred kilobytes per tile) are recycled through a process-wide cache: a fresh allocation of that size is
+// mmap'ed, page-faulted in and unmapped again for every tile, which costs more than filling it.
+struct KeptCache {
+    std::mutex mu;
+    std::vector<std::vector<Kept>> free_list;
+    void take(std::vector<Kept> & v) { std::lock_guard<std::mutex> lk(mu); if (!free_list.empty()) { v.swap(free_list.back()); free_list.pop_back(); } v.clear(); }
+    void give(std::vector<Kept> & v) { v.clear(); std::lock_guard<std::mutex> lk(mu); if (free_list.size() < 4096 && v.capacity() > 0) { free_list.emplace_back(); free_list.back().swap(v); } }
+};
+static KeptCache & kept_cache() { static KeptCache *c = new KeptCache(); return *c; }
+
 struct TileWork {
     std::vector<Kept> kept;
     size_t n_seq = 0, n_qual = 0, n_cig = 0;
@@ -410,6 +421,7 @@ static int build_tile_a(HostBatch & hb, TileWork & tw, const uvcgpu_params & par
         PROF(1)
         // pass 2 (grouping.cpp:731-977): family key of every kept read
         std::vector<Kept> & kept = tw.kept;
+        kept_cache().take(kept);
         kept.reserve((size_t)n_in);
         int32_t bam_beg = INT32_MAX, bam_end = 0;
         int64_t pcrpassed = 0;
@@ -781,6 +793,7 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
             hb.rfam[(size_t)o.read + i] = q;
         }
         b = HostBatch();   // release the private copy
+        kept_cache().give(work[ti].kept);
         work[ti] = TileWork();
     });
     if (getenv("UVC_PREP_PROFILE")) { fprintf(stderr, "prep wall ms: tiles %.1f resize %.1f concat %.1f\n", (wall1 - wall0) / 1e6, (wall2 - wall1) / 1e6, (prof_now() - wall2) / 1e6); }
