@@ -347,6 +347,21 @@ struct KeptCache {
 };
 static KeptCache & kept_cache() { static KeptCache *c = new KeptCache(); return *c; }
 
+// The same for the tile-private staging batches of stage A (fragment / family records of one tile): recycled with their capacity.
+struct PartCache {
+    std::mutex mu;
+    std::vector<HostBatch> free_list;
+    static void reset(HostBatch & b) {
+        b.tiles.clear(); b.pos_tile.clear(); b.refsym.clear(); b.rtr.clear(); b.baq.clear(); b.baq2.clear(); b.reads.clear(); b.read_raw_index.clear();
+        b.seq.clear(); b.qual.clear(); b.cigar.clear(); b.frags.clear(); b.frag_reads.clear(); b.fams.clear(); b.rfam.clear(); b.fam_umi.clear();
+        b.fchunk_frag.clear(); b.mchunk_fs.clear();
+        b.n_fcol = b.n_mcol = 0; b.n_pos = b.n_cx = b.n_ev = 0; b.n_reads_in = 0;
+    }
+    void take(HostBatch & b) { std::lock_guard<std::mutex> lk(mu); if (!free_list.empty()) { b = std::move(free_list.back()); free_list.pop_back(); } reset(b); }
+    void give(HostBatch & b) { reset(b); std::lock_guard<std::mutex> lk(mu); if (free_list.size() < 4096) { free_list.emplace_back(std::move(b)); } b = HostBatch(); }
+};
+static PartCache & part_cache() { static PartCache *c = new PartCache(); return *c; }
+
 struct TileWork {
     std::vector<Kept> kept;
     size_t n_seq = 0, n_qual = 0, n_cig = 0;
@@ -533,7 +548,7 @@ static int build_tile_a(HostBatch & hb, TileWork & tw, const uvcgpu_params & par
         PROF(3)
         const int64_t read_base = (int64_t)hb.reads.size();
         std::vector<int32_t> l2r_end, r2l_end;      // (reused by every family: no allocation per family)
-        hb.frags.reserve(kept.size()); hb.fams.reserve(kept.size()); hb.frag_reads.reserve(kept.size()); hb.fam_umi.reserve(kept.size());
+        hb.frag_reads.reserve(kept.size());
         for (size_t oi = 0; oi < order.size();) {
             size_t oj = oi;
             while (oj < order.size() && kept[order[oj]].key == kept[order[oi]].key) { oj++; }
@@ -718,6 +733,7 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
     std::vector<std::string> msgs((size_t)n_tiles);
     uvc_parallel_for(n_tiles, n_threads, [&](int32_t ti) {
         uvc_stage_thread_pinning(false);
+        part_cache().take(part[ti]);
         rcs[ti] = build_tile_a(part[ti], work[ti], par, contigs, ti, tiles[ti], sources[tile_source ? tile_source[ti] : 0], center_pow, pem, msgs[ti]);
         uvc_stage_thread_pinning(true);
     });
@@ -792,7 +808,7 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
             }
             hb.rfam[(size_t)o.read + i] = q;
         }
-        b = HostBatch();   // release the private copy
+        part_cache().give(b);   // hand the private copy back (its vectors keep their capacity for the next tile)
         kept_cache().give(work[ti].kept);
         work[ti] = TileWork();
     });
