@@ -160,7 +160,9 @@ typedef struct uvcgpu_tile {
 } uvcgpu_tile;
 
 /* BAM records of all tiles of a batch, structure-of-arrays. For every tile the caller supplies what the reference
- * fetches with sam_itr_queryi(tid, beg-2000, end+2000) (grouping.cpp:664, 730), in file order, already decoded:
+ * fetches with sam_itr_queryi(tid, beg-2000, end+2000) (grouping.cpp:664, 730), in file order, already decoded (the slices of
+ * different tiles may overlap, and a slice may be a file-order superset of the window: records that end before it are dropped by the
+ * read filter like the reference's OUT_OF_RANGE test, grouping.cpp:408-409):
  * the fields of bam1_core_t, the NM aux tag (or -1), 4-bit packed bases, base qualities, CIGAR words, NUL-terminated qname.
  * Offsets are in bytes (seq, qual, qname) or 32-bit words (cigar). */
 typedef struct uvcgpu_reads_soa {

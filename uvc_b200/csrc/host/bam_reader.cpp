@@ -497,6 +497,46 @@ int64_t uvchost_bam_fetch_tiles(uvchost_bam *b, int32_t tid, int32_t n, const in
     return total;
 }
 
+int64_t uvchost_bam_fetch_span(uvchost_bam *b, int32_t tid, int32_t n, const int64_t *begs, const int64_t *ends, uvchost_readbuf *rb,
+        int64_t *read_begin, int64_t *read_end) {
+    if (n <= 0) { return 0; }
+    for (int32_t k = 0; k + 1 < n; k++) { if (begs[k] > begs[k + 1] || ends[k] > ends[k + 1]) { return -2; } }
+    const int64_t span_beg = (begs[0] < 0 ? 0 : begs[0]), span_end = ends[n - 1];
+    const int64_t base = uvchost_readbuf_size(rb);
+    std::vector<int32_t> & endpos = rb->endpos_scratch;
+    endpos.clear();
+    int64_t total = 0;
+    if (uvchost_bam_seek_region(b, tid, span_beg) == 0) {
+        Core c;
+        int32_t k_open = 0;      // first window that can still need a record (ascending begs)
+        for (;;) {
+            const int r = next_record(b, c);
+            if (r < 0) { return -1; }
+            if (0 == r) { break; }
+            if (c.tid != tid || c.pos >= span_end) {
+                if (c.tid >= 0 && c.tid < tid) { continue; }
+                break;
+            }
+            // keep the record if it overlaps some window: ends are ascending, so windows whose end <= pos are closed for good
+            while (k_open < n && ends[k_open] <= c.pos) { k_open++; }
+            bool wanted = false;
+            for (int32_t k = k_open; k < n && begs[k] < c.endpos; k++) { if (c.pos < ends[k]) { wanted = true; break; } }
+            if (wanted) { append_record(rb, b, c); endpos.push_back(c.endpos); total++; }
+        }
+    }
+    // slices: window k = [first kept record with endpos > beg, first kept record with pos >= end)
+    const size_t m = endpos.size();
+    size_t lo = 0, hi = 0;
+    for (int32_t k = 0; k < n; k++) {
+        const int64_t beg = (begs[k] < 0 ? 0 : begs[k]), end = ends[k];
+        while (lo < m && endpos[lo] <= beg) { lo++; }
+        if (hi < lo) { hi = lo; }
+        while (hi < m && rb->pos[(size_t)base + hi] < end) { hi++; }
+        read_begin[k] = base + (int64_t)lo; read_end[k] = base + (int64_t)(hi > lo ? hi : lo);
+    }
+    return total;
+}
+
 int uvchost_bam_scan(uvchost_bam *b, uvchost_scan_cb cb, void *user) {
     if (b->in.seek(b->first_record_voff) != 0) { return -1; }
     Core c;

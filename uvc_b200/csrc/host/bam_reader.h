@@ -41,6 +41,15 @@ int64_t uvchost_bam_fetch(uvchost_bam *b, int32_t tid, int64_t beg, int64_t end,
 int64_t uvchost_bam_fetch_tiles(uvchost_bam *b, int32_t tid, int32_t n, const int64_t *begs, const int64_t *ends, uvchost_readbuf *rb,
                                 int64_t *read_begin, int64_t *read_end);
 
+/* Like uvchost_bam_fetch_tiles for windows given in ascending order of BOTH begs and ends, but every record is appended ONCE: tile k's slice
+ * [read_begin[k], read_end[k]) runs from the first record that ends after begs[k] to the last record that starts before ends[k], so the slices
+ * of neighbouring tiles overlap (tile halos are not duplicated: five times fewer bytes on a dense panel). A slice is a file-order superset of
+ * what sam_itr_queryi yields for the window: the few extra records (pos < beg, end <= beg) start at least 2000 bases before the tile and are
+ * dropped by the read filter exactly like the reference's OUT_OF_RANGE test (grouping.cpp:408-409), so uvcgpu_submit gives identical results.
+ * Returns the number of records appended, -1 on a read error, -2 if the windows are not ascending. */
+int64_t uvchost_bam_fetch_span(uvchost_bam *b, int32_t tid, int32_t n, const int64_t *begs, const int64_t *ends, uvchost_readbuf *rb,
+                               int64_t *read_begin, int64_t *read_end);
+
 /* Sequential scan of core fields (for the region tiler): calls cb(tid, pos, endpos, flag, isize, user) for every record in file order
  * until cb returns non-zero or the file ends. */
 typedef int (*uvchost_scan_cb)(int32_t tid, int32_t pos, int32_t endpos, uint16_t flag, int32_t isize, int32_t l_qseq, uint8_t mapq, void *user);

@@ -295,7 +295,12 @@ void lane_thread(Lane lane) {
                 // sam_itr_queryi(tid, beg - MAX_INSERT_SIZE, end + MAX_INSERT_SIZE) of every tile (grouping.cpp:664, 730); a batch holds one contig
                 std::vector<int64_t> begs, ends, rb0((size_t)(k1 - k0)), rb1((size_t)(k1 - k0));
                 for (int32_t k = k0; k < k1; k++) { begs.push_back(std::max(0, b.tiles[k].beg_pos - 2000)); ends.push_back((int64_t)b.tiles[k].end_pos + 2000); }
-                if (k1 > k0 && uvchost_bam_fetch_tiles(bams[s], b.tiles[k0].tid, k1 - k0, begs.data(), ends.data(), rbs[s], rb0.data(), rb1.data()) < 0) { dec_failed.store(1); }
+                if (k1 > k0) {
+                    // every record decoded once, neighbouring tiles share their halos (overlapping slices); unsorted BED lines fall back to one copy per tile
+                    int64_t got = uvchost_bam_fetch_span(bams[s], b.tiles[k0].tid, k1 - k0, begs.data(), ends.data(), rbs[s], rb0.data(), rb1.data());
+                    if (-2 == got) { got = uvchost_bam_fetch_tiles(bams[s], b.tiles[k0].tid, k1 - k0, begs.data(), ends.data(), rbs[s], rb0.data(), rb1.data()); }
+                    if (got < 0) { dec_failed.store(1); }
+                }
                 for (int32_t k = k0; k < k1; k++) {
                     const uvchost_bedline & l = b.tiles[k];
                     uvcgpu_tile & T = tiles[k];
