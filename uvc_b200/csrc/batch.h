@@ -65,6 +65,7 @@ struct ReadRec {
     int32_t ev_off, n_ev;                              // indel events of this read
     int32_t fragprev_maxrend, famprev_maxrend;         // max rend over earlier reads of the same fragment / (family,strand); INT32_MIN if none
     int32_t fambothprev_maxrend;                       // same over both strands of the family
+    int32_t raw;                                       // index of the record in the batch's raw record arrays (the caller's SoA slices)
 };
 
 // Derived per-read constants (kernel K0).
@@ -97,6 +98,7 @@ struct IndelEvent {
     int32_t incvalue2;     // count added to the inserted-sequence map (MAX(1, incvalue2))
     int32_t counted;       // nbases2end >= indel_filter_edge_dist and not primer-masked
     int32_t cigar_idx;
+    int32_t tile, raw;     // tile of the read; index of the read in the batch's raw record arrays (the host reads inserted bases from the caller's SoA)
 };
 
 struct FragRec {
@@ -194,7 +196,9 @@ struct BatchView {
     const ReadRec *reads;
     ReadDerived *rd;
     const uint8_t *seq;
-    uint8_t *qual;                 // raw base qualities on upload; K0 applies the reference's quality fix-ups in place (grouping.cpp:459-543)
+    uint8_t *qual;                 // per kept read: its base qualities after the reference's quality fix-ups (grouping.cpp:459-543), written by K0
+    const uint8_t *qual_raw;       // base qualities as uploaded (a record that two tiles keep is shared here)
+    const uint64_t *raw_qual_off;  // offset of raw record i in qual_raw
     const uint32_t *cigar;
     CxEntry *cx;
     IndelEvent *ev;
@@ -229,7 +233,7 @@ struct BatchView {
 #define UVC_REC_FAM_INDEL 2      // family-level                    -> symbol_to_fam_format_depth_sets_2strand[strand] maps (main.hpp:3327-3336)
 #define UVC_REC_CDP2_INDEL 3     // tier-2 consensus families       -> pos2iseq2data_cDP2 / pos2dlen2data_cDP2 (main.hpp:3197-3206)
 #define UVC_REC_C2D_INDEL 4      // single-strand / duplex consensus -> pos2iseq2data_c2dDP / pos2dlen2data_c2dDP (main.hpp:3460-3469, 3536-3545)
-// haplotype strings are variable-length: {kind, strand, n, owner} followed by n pairs {pos, symbol}
+// haplotype strings are variable-length: {kind, strand, n, tile} followed by n pairs {pos, symbol}
 #define UVC_REC_HAP_BQ 10
 #define UVC_REC_HAP_FQ 11
 #define UVC_REC_HAP_F2Q 12

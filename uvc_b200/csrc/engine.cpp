@@ -9,6 +9,7 @@
 #include "batch.h"
 #include "host_prep.h"
 #include "kernels_core.cuh"
+#include "prep_core.cuh"
 #include "score_core.cuh"
 #include "sparse_out.h"
 #include "vcf_emit.h"
@@ -45,6 +46,11 @@ struct BatchState {
     HostBatch hb;
     BatchView view;                       // pointers valid on the compute side (device or, in the emulation, host)
     std::vector<void*> allocs;            // compute-side allocations
+    std::vector<void*> temp_allocs;       // scratch of the device staging (stages P0/P1), freed as soon as the staging kernels are enqueued
+    StageVec<uint8_t> raw_stage;          // page-locked copy of the caller's records that the batch needs (source of the one host-to-device copy)
+    uvc::PrepView prep_view;              // arrays of the staging kernels that outlive them (reads, fragments, families)
+    int32_t *indelphred0 = nullptr;       // compute side: indelphred of every position before the threshold pass adjusts it (dump hook)
+    bool groups_on_host = false;          // hb.reads / frags / fams / frag_reads downloaded (dump hook only)
     std::vector<std::pair<void*, size_t>> alloc_sizes;
     std::vector<uvcgpu_reads_soa> sources; // caller's SoA buffers (borrowed until release)
     std::vector<int32_t> tile_source;
@@ -73,6 +79,7 @@ struct uvcgpu_ctx {
     uvcgpu_params par;
     std::string err;
     std::map<int32_t, HostContig> contigs;
+    std::map<int32_t, char*> d_contigs;   // device copies of the contigs' bases (stage P1 reads the reference there); absent = not available
     std::map<int32_t, std::string> contig_names;
     std::map<uvcgpu_ticket, std::unique_ptr<BatchState>> batches;
     uvcgpu_ticket next_ticket = 1;
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__(128) uvc_k0_read_consts(const BatchView v, int
         const ReadRec & R = v.reads[r0 + k];
         const int32_t l = R.l_qseq;
         if (l > UVC_K0_MAXQ) { continue; }
-        const uint8_t *gq = v.qual + R.qual_off, *gs = v.seq + R.seq_off;
+        const uint8_t *gq = v.qual_raw + v.raw_qual_off[R.raw], *gs = v.seq + R.seq_off;
         for (int32_t i = lane; i < l; i += 32) { sq[k * UVC_K0_QSTRIDE + i] = gq[i]; }
         for (int32_t i = lane; i < (l + 1) / 2; i += 32) { ss[k * UVC_K0_SSTRIDE + i] = gs[i]; }
     }
@@ -638,7 +645,18 @@ static int backend_download(uvcgpu_ctx *ctx, void *dst, const void *src, size_t 
     if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->active)); UVC_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->active)); }
     return 0;
 }
-static void backend_free(uvcgpu_ctx *ctx, BatchState & bs) { for (void *p : bs.allocs) { cudaFreeAsync(p, ctx->stream); } bs.allocs.clear(); }
+static void backend_free_temps(uvcgpu_ctx *ctx, BatchState & bs) { for (void *p : bs.temp_allocs) { cudaFreeAsync(p, ctx->active); } bs.temp_allocs.clear(); }
+static void backend_free(uvcgpu_ctx *ctx, BatchState & bs) { backend_free_temps(ctx, bs); for (void *p : bs.allocs) { cudaFreeAsync(p, ctx->stream); } bs.allocs.clear(); }
+// scratch of the staging kernels; fill >= 0: every byte is set to it
+static int backend_alloc_temp(uvcgpu_ctx *ctx, BatchState & bs, void **out, size_t bytes, int fill = -1) {
+    bytes += 64;
+    UVC_CUDA_CHECK(ctx, cudaMallocAsync(out, bytes, ctx->active));
+    bs.temp_allocs.push_back(*out);
+    if (fill >= 0) { UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, fill, bytes, ctx->active)); }
+    return 0;
+}
+
+#include "prep_device.inc"
 
 static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     const BatchView & v = bs.view;
@@ -698,7 +716,7 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     UVC_STAGE(uvc_k4c_family_haplotypes, 2 * v.n_fams)
     #undef UVC_STAGE
     UVC_CUDA_CHECK(ctx, cudaGetLastError());
-    bs.stats.gpu_launches = launches;
+    bs.stats.gpu_launches += launches;
     return 0;
 }
 
@@ -755,7 +773,19 @@ static int backend_upload(uvcgpu_ctx *, BatchState & bs, void *dst, const void *
     return 0;
 }
 static int backend_download(uvcgpu_ctx *, void *dst, const void *src, size_t bytes) { if (bytes) { memcpy(dst, src, bytes); } return 0; }
-static void backend_free(uvcgpu_ctx *, BatchState & bs) { for (void *p : bs.allocs) { free(p); } bs.allocs.clear(); }
+static void backend_free_temps(uvcgpu_ctx *, BatchState & bs) { for (void *p : bs.temp_allocs) { free(p); } bs.temp_allocs.clear(); }
+static void backend_free(uvcgpu_ctx *ctx, BatchState & bs) { backend_free_temps(ctx, bs); for (void *p : bs.allocs) { free(p); } bs.allocs.clear(); }
+static int backend_alloc_temp(uvcgpu_ctx *, BatchState & bs, void **out, size_t bytes, int fill = -1) {
+    bytes += 64;
+    *out = malloc(bytes);
+    if (NULL == *out) { return UVCGPU_ENOMEM; }
+    memset(*out, (fill >= 0 ? fill : 0xA5), bytes);      // (unfilled scratch is poisoned: every element must be written before it is read)
+    bs.temp_allocs.push_back(*out);
+    return 0;
+}
+
+#include "prep_device.inc"
+
 static int backend_run(uvcgpu_ctx *, BatchState & bs) {
     const BatchView & v = bs.view;
     if (getenv("UVC_EMU_PREP_ONLY")) { return 0; }   // host-staging profiling runs (tools/prep_profile.py)
@@ -771,7 +801,6 @@ static int backend_run(uvcgpu_ctx *, BatchState & bs) {
     for (int64_t i = 0; i < 2 * v.n_fams; i++) { uvc::k4a_family_strand(v, i); }
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k4_position(v, i, w); }
     for (int64_t i = 0; i < 2 * v.n_fams; i++) { uvc::k4c_family_strand(v, i); }
-    bs.stats.gpu_launches = 0;
     return 0;
 }
 static int backend_wait(uvcgpu_ctx *, BatchState &) { return 0; }
@@ -967,6 +996,8 @@ void uvcgpu_destroy(uvcgpu_ctx *ctx) {
     enter_ctx(ctx);
     for (auto & kv : ctx->batches) { backend_free(ctx, *kv.second); }
 #if UVC_CUDA
+    cudaDeviceSynchronize();
+    for (auto & kv : ctx->d_contigs) { cudaFree(kv.second); }
     if (ctx->post_stream) { cudaStreamDestroy(ctx->post_stream); }
     if (ctx->stream) { cudaStreamDestroy(ctx->stream); }
 #endif
@@ -977,6 +1008,7 @@ const char *uvcgpu_last_error(const uvcgpu_ctx *ctx) { return (ctx ? ctx->err.c_
 
 int uvcgpu_set_contig(uvcgpu_ctx *ctx, int32_t tid, const char *bases, int64_t len) {
     if (NULL == ctx || tid < 0 || len < 0) { return UVCGPU_EINVAL; }
+    enter_ctx(ctx);
     HostContig & c = ctx->contigs[tid];
     c.len = len;
     c.available = (NULL != bases);
@@ -985,12 +1017,30 @@ int uvcgpu_set_contig(uvcgpu_ctx *ctx, int32_t tid, const char *bases, int64_t l
         c.bases.assign(bases, (size_t)len);
         for (auto & ch : c.bases) { ch = (char)toupper(ch); } // load_refstring (main.cpp:65-67)
     }
+#if UVC_CUDA
+    {   // the bases stay in HBM until the contig is unset: stage P1 reads the reference there
+        auto it = ctx->d_contigs.find(tid);
+        if (it != ctx->d_contigs.end()) { cudaStreamSynchronize(ctx->stream); cudaFree(it->second); ctx->d_contigs.erase(it); }
+        if (bases) {
+            char *d = NULL;
+            UVC_CUDA_CHECK(ctx, cudaMalloc((void**)&d, (size_t)len + 64));
+            cudaError_t e = cudaMemcpy(d, c.bases.data(), (size_t)len, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { cudaFree(d); ctx->err = std::string("cudaMemcpy of the contig: ") + cudaGetErrorString(e); return UVCGPU_ECUDA; }
+            ctx->d_contigs[tid] = d;
+        }
+    }
+#endif
     return UVCGPU_OK;
 }
 
 int uvcgpu_unset_contig(uvcgpu_ctx *ctx, int32_t tid) {
     if (NULL == ctx) { return UVCGPU_EINVAL; }
+    enter_ctx(ctx);
     ctx->contigs.erase(tid);
+#if UVC_CUDA
+    auto it = ctx->d_contigs.find(tid);
+    if (it != ctx->d_contigs.end()) { cudaStreamSynchronize(ctx->stream); cudaFree(it->second); ctx->d_contigs.erase(it); }
+#endif
     return UVCGPU_OK;
 }
 
@@ -1027,19 +1077,12 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
         }
     }
     const double t0 = now_ms();
-    std::string msg;
-    int rc = uvc_build_host_batch(bs->hb, ctx->par, ctx->contigs, n_tiles, tiles, bs->sources.data(), bs->tile_source.data(), ctx->host_threads, msg);
-    if (rc != 0) { ctx->err = msg; return rc; }
-    const double t1 = now_ms();
     HostBatch & hb = bs->hb;
     BatchView & v = bs->view;
     memset(&v, 0, sizeof(v));
     uvc_fill_view_constants(v, ctx->par);
     v.ten_over_ln10 = 10.0 / log(10.0);
     v.ln10 = log(10);
-    v.n_tiles = n_tiles;
-    v.n_pos = hb.n_pos; v.n_reads = (int64_t)hb.reads.size(); v.n_frags = (int64_t)hb.frags.size(); v.n_fams = (int64_t)hb.fams.size();
-    v.n_cx = hb.n_cx; v.n_ev = hb.n_ev;
 
 #define UVC_UP(field, type, vec) { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (vec).size() * sizeof(type), false)); \
         UVC_TRY(backend_upload(ctx, *bs, d_, (vec).data(), (vec).size() * sizeof(type))); v.field = (type*)d_; }
@@ -1055,23 +1098,9 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
         }
         UVC_UP(pf_tab, int32_t, pf)
     }
-    UVC_UP(tiles, TileInfo, hb.tiles)
-    UVC_UP(pos_tile, int32_t, hb.pos_tile)
-    UVC_UP(refsym, uint8_t, hb.refsym)
-    UVC_UP(rtr, uvcgpu_rtr, hb.rtr)
-    UVC_UP(baq, int32_t, hb.baq)
-    UVC_UP(baq2, int32_t, hb.baq2)
-    UVC_UP(reads, ReadRec, hb.reads)
-    UVC_UP(seq, uint8_t, hb.seq)
-    UVC_UP(qual, uint8_t, hb.qual)
-    UVC_UP(cigar, uint32_t, hb.cigar)
-    UVC_UP(frags, FragRec, hb.frags)
-    UVC_UP(frag_reads, int32_t, hb.frag_reads)
-    UVC_UP(fams, FamRec, hb.fams)
-    UVC_UP(rfam, ReadFam, hb.rfam)
-    UVC_UP(slip_tab, int32_t, ctx->slip_tab)
-    UVC_UP(fchunk_frag, int32_t, hb.fchunk_frag)
-    UVC_UP(mchunk_fs, int32_t, hb.mchunk_fs)
+    // stages P0 and P1 on the device: read filter, family segmentation, reference context (prep_device.inc); fills the view's input arrays
+    UVC_TRY(prep_on_device(ctx, *bs, n_tiles, tiles));
+    const double t1 = now_ms();
     v.n_fcol = hb.n_fcol; v.n_mcol = hb.n_mcol;
     { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_fcol * sizeof(FragCol), false)); v.fcol = (FragCol*)d_; }
     UVC_ZERO(fmask, uint32_t, (v.n_fcol / UVC_COL_CHUNK) * 4)
@@ -1099,8 +1128,8 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
     st.n_tiles = n_tiles; st.n_reads_in = hb.n_reads_in; st.n_reads_kept = v.n_reads; st.n_ext_positions = v.n_pos;
     st.n_families = v.n_fams; st.n_fragments = v.n_frags;
     for (const auto & T : hb.tiles) { st.n_positions += T.end_pos - T.beg_pos; }
-    st.host_prep_ms = t1 - t0;
-    st.h2d_ms = t2 - t1;
+    st.h2d_ms = (t1 - t0) - st.host_prep_ms;    // the rest of the staging call: uploads, staging kernels and their two synchronisations
+    (void)t2;
     *ticket = ctx->next_ticket++;
     ctx->batches[*ticket] = std::move(bs);
     return UVCGPU_OK;
@@ -1313,7 +1342,16 @@ int uvcgpu_dump_counters(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_ind
             host_side = true; break;
         }
         case UVCGPU_SEC_FAMILIES: {
-            const std::string s = uvc_families_text(bs.hb, tile_index, bs.sources[(size_t)bs.tile_source[(size_t)tile_index]]);
+            if (!bs.groups_on_host) {     // the segmentation lives on the device: fetched for this test hook only
+                bs.hb.reads.resize((size_t)v.n_reads); bs.hb.frags.resize((size_t)v.n_frags); bs.hb.fams.resize((size_t)v.n_fams); bs.hb.frag_reads.resize((size_t)v.n_reads);
+                int rc = backend_download(ctx, bs.hb.reads.data(), v.reads, bs.hb.reads.size() * sizeof(ReadRec));
+                if (0 == rc) { rc = backend_download(ctx, bs.hb.frags.data(), v.frags, bs.hb.frags.size() * sizeof(FragRec)); }
+                if (0 == rc) { rc = backend_download(ctx, bs.hb.fams.data(), v.fams, bs.hb.fams.size() * sizeof(FamRec)); }
+                if (0 == rc) { rc = backend_download(ctx, bs.hb.frag_reads.data(), v.frag_reads, bs.hb.frag_reads.size() * sizeof(int32_t)); }
+                if (rc != 0) { return rc; }
+                bs.groups_on_host = true;
+            }
+            const std::string s = uvc_families_text(bs.hb, tile_index);
             tmp.assign(s.begin(), s.end());
             host_side = true; break;
         }
@@ -1332,13 +1370,21 @@ int uvcgpu_dump_counters(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_ind
             host_side = true; break;
         }
         case UVCGPU_SEC_RTR_INITIAL: {
-            tmp.assign((const uint8_t*)(bs.hb.rtr.data() + off), (const uint8_t*)(bs.hb.rtr.data() + off + npos));
+            std::vector<uvcgpu_rtr> r(npos);
+            std::vector<int32_t> ip(npos);
+            int rc = (T.skipped ? 0 : backend_download(ctx, r.data(), v.rtr + off, npos * sizeof(uvcgpu_rtr)));
+            if (0 == rc && !T.skipped) { rc = backend_download(ctx, ip.data(), bs.indelphred0 + off, npos * sizeof(int32_t)); }
+            if (rc != 0) { return rc; }
+            for (size_t i = 0; i < npos; i++) { r[i].indelphred = ip[i]; }
+            tmp.assign((const uint8_t*)r.data(), (const uint8_t*)(r.data() + npos));
             host_side = true; break;
         }
         case UVCGPU_SEC_BAQ: case UVCGPU_SEC_BAQ2: {
-            const StageVec<int32_t> & b = (section == UVCGPU_SEC_BAQ ? bs.hb.baq : bs.hb.baq2);
+            std::vector<int32_t> b(npos);
+            int rc = (T.skipped ? 0 : backend_download(ctx, b.data(), (section == UVCGPU_SEC_BAQ ? v.baq : v.baq2) + off, npos * sizeof(int32_t)));
+            if (rc != 0) { return rc; }
             std::vector<int64_t> w(npos);
-            for (size_t i = 0; i < npos; i++) { w[i] = b[off + i]; }
+            for (size_t i = 0; i < npos; i++) { w[i] = b[i]; }
             tmp.assign((uint8_t*)w.data(), (uint8_t*)(w.data() + npos));
             host_side = true; break;
         }

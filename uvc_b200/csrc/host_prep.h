@@ -56,6 +56,17 @@ struct HostBatch {
     int64_t n_fcol = 0, n_mcol = 0;       // padded column entries
     int64_t n_pos = 0, n_cx = 0, n_ev = 0;
     int64_t n_reads_in = 0;
+    // where the batch's raw record arrays (device staging) came from: source s contributed its records [raw_host_begin[s], ...) as raw indices
+    // [raw_dev_begin[s], raw_dev_begin[s + 1]); the host reads inserted bases and names from the caller's SoA (borrowed until release)
+    std::vector<uvcgpu_reads_soa> raw_sources;
+    std::vector<int64_t> raw_host_begin, raw_dev_begin;
+    int64_t raw_to_host(int64_t raw, size_t & s) const {
+        s = 0;
+        while (s + 1 < raw_sources.size() && raw_dev_begin[s + 1] <= raw) { s++; }
+        return raw_host_begin[s] + (raw - raw_dev_begin[s]);
+    }
+    const uint8_t *raw_seq(int64_t raw) const { size_t s; const int64_t i = raw_to_host(raw, s); return raw_sources[s].seq + raw_sources[s].seq_off[i]; }
+    const char *raw_qname(int64_t raw) const { size_t s; const int64_t i = raw_to_host(raw, s); return raw_sources[s].qname + raw_sources[s].qname_off[i]; }
 };
 
 // Builds the staging arrays of one batch. Returns 0 or a negative uvcgpu_error; msg receives the reason.
@@ -64,7 +75,7 @@ int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::m
         int32_t n_tiles, const uvcgpu_tile *tiles, const uvcgpu_reads_soa *sources, const int32_t *tile_source, int n_threads, std::string & msg);
 
 // Text form of the family grouping of one tile (same format as oracle/harness_dump.cpp writes).
-std::string uvc_families_text(const HostBatch & hb, int32_t tile_index, const uvcgpu_reads_soa & rs);
+std::string uvc_families_text(const HostBatch & hb, int32_t tile_index);
 
 void uvc_fill_view_constants(BatchView & v, const uvcgpu_params & par);
 

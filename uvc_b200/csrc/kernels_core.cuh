@@ -200,6 +200,7 @@ UVC_HD void k0_read(const BatchView & v, int64_t ri, const uint8_t *seq_ro = NUL
     const uint32_t *cigar = v.cigar + R.cigar_off;
     const uint8_t *seq = (seq_ro ? seq_ro : v.seq + R.seq_off);
     uint8_t *qual_w = (qual_rw ? qual_rw : v.qual + R.qual_off);
+    if (!qual_rw) { const uint8_t *raw = v.qual_raw + v.raw_qual_off[R.raw]; for (int32_t i = 0; i < R.l_qseq; i++) { qual_w[i] = raw[i]; } }
     fix_base_qualities(qual_w, seq, cigar, R, par_of(v));
     const uint8_t *qual = qual_w;
     const int64_t po = T.pos_off - T.ext_beg;        // concatenated index of reference position x is po + x
@@ -338,7 +339,7 @@ UVC_HD void k0_read(const BatchView & v, int64_t ri, const uint8_t *seq_ro = NUL
                 }
                 if (!R.simple) {
                     IndelEvent & E = v.ev[R.ev_off + n_ev];
-                    E.read = (int32_t)ri; E.rpos = rpos; E.oplen = len; E.qpos = qpos; E.is_del = (op == UVC_CDEL); E.cigar_idx = i;
+                    E.read = (int32_t)ri; E.rpos = rpos; E.oplen = len; E.qpos = qpos; E.is_del = (op == UVC_CDEL); E.cigar_idx = i; E.tile = R.tile; E.raw = R.raw;
                     E.symbol = -1; E.incvalue = 0; E.incvalue2 = 0; E.counted = 0;
                     n_ev++;
                 }
@@ -1317,7 +1318,7 @@ UVC_HD void k3a_fragment(const BatchView & v, int64_t fi) {
     if (n_mut_entries > 1) {
         int32_t out = rec_alloc(v, 4 + 2 * n_mut_entries);
         if (out >= 0) {
-            v.rec_buf[out] = UVC_REC_HAP_BQ; v.rec_buf[out + 1] = G.strand; v.rec_buf[out + 2] = n_mut_entries; v.rec_buf[out + 3] = (int32_t)fi;
+            v.rec_buf[out] = UVC_REC_HAP_BQ; v.rec_buf[out + 1] = G.strand; v.rec_buf[out + 2] = n_mut_entries; v.rec_buf[out + 3] = G.tile;
             out += 4;
             for (int32_t c = 0; c < n_chunks; c++) {
                 const uint32_t *m = fm + c * 4;
@@ -2076,11 +2077,11 @@ UVC_HD void k4c_family_strand(const BatchView & v, int64_t i) {
             if (n_fq <= 1 && n_f2q <= 1) { break; }
             if (n_fq > 1) {
                 out_fq = rec_alloc(v, 4 + 2 * n_fq);
-                if (out_fq >= 0) { int32_t *w = v.rec_buf + out_fq; w[0] = UVC_REC_HAP_FQ; w[1] = strand; w[2] = n_fq; w[3] = (int32_t)(i >> 1); out_fq += 4; }
+                if (out_fq >= 0) { int32_t *w = v.rec_buf + out_fq; w[0] = UVC_REC_HAP_FQ; w[1] = strand; w[2] = n_fq; w[3] = F.tile; out_fq += 4; }
             }
             if (n_f2q > 1) {
                 out_f2q = rec_alloc(v, 4 + 2 * n_f2q);
-                if (out_f2q >= 0) { int32_t *w = v.rec_buf + out_f2q; w[0] = UVC_REC_HAP_F2Q; w[1] = strand; w[2] = n_f2q; w[3] = (int32_t)(i >> 1); out_f2q += 4; }
+                if (out_f2q >= 0) { int32_t *w = v.rec_buf + out_f2q; w[0] = UVC_REC_HAP_F2Q; w[1] = strand; w[2] = n_f2q; w[3] = F.tile; out_f2q += 4; }
             }
         }
         // A strand with a single fragment (every strand of non-UMI data) can only contribute where that fragment's column has a mutated

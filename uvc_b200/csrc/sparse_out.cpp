@@ -55,25 +55,23 @@ void uvc_build_sparse(std::vector<TileSparse> & out, const HostBatch & hb, const
         if (kind >= UVC_REC_FRAG_INDEL && kind <= UVC_REC_C2D_INDEL) {
             if (o + 6 > n_words) { break; }
             const IndelEvent & E = ev[rec[o + 4]];
-            const ReadRec & R = hb.reads[E.read];
             IndelKey k; k.kind = kind; k.strand = rec[o + 1]; k.symbol = rec[o + 2]; k.pos = rec[o + 3];
-            TileSparse & ts = out[R.tile];
+            TileSparse & ts = out[E.tile];
             if (E.is_del) {
                 IdCount & ic = ts.del[k][E.oplen]; ic.count += rec[o + 5]; if (ic.ev < 0) { ic.ev = rec[o + 4]; }
             } else {
                 std::string seq;
-                const uint8_t *s = hb.seq.data() + R.seq_off;
+                const uint8_t *s = hb.raw_seq(E.raw);
                 for (int32_t i = 0; i < E.oplen; i++) { const int32_t q = E.qpos + i; seq.push_back(nt16[(s[q >> 1] >> ((~q & 1) << 2)) & 0xf]); }
                 IdCount & ic = ts.ins[k][seq]; ic.count += rec[o + 5]; if (ic.ev < 0) { ic.ev = rec[o + 4]; }
             }
             o += 6;
         } else if (kind >= UVC_REC_HAP_BQ && kind <= UVC_REC_HAP_F2Q) {
             if (o + 4 > n_words) { break; }
-            const int32_t strand = rec[o + 1], n = rec[o + 2], owner = rec[o + 3];
+            const int32_t strand = rec[o + 1], n = rec[o + 2], tile = rec[o + 3];
             if (o + 4 + 2 * (int64_t)n > n_words) { break; }
             mutform_t mf;
             for (int32_t i = 0; i < n; i++) { mf.push_back(std::make_pair(rec[o + 4 + 2 * i], rec[o + 5 + 2 * i])); }
-            const int32_t tile = (kind == UVC_REC_HAP_BQ ? hb.frags[owner].tile : hb.fams[owner].tile);
             auto & m = (kind == UVC_REC_HAP_BQ ? hbq[tile] : (kind == UVC_REC_HAP_FQ ? hfq[tile] : hf2q[tile]));
             auto it = m.insert(std::make_pair(mf, std::array<int32_t, 2>{{0, 0}})).first;
             it->second[strand] += 1;

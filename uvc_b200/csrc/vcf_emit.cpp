@@ -33,8 +33,7 @@ std::string event_string(const HostBatch & hb, const StageVec<IndelEvent> & ev, 
     if (e < 0) { return ""; }
     const IndelEvent & E = ev[e];
     if (E.is_del) { return refstring.substr(E.rpos - ext_beg, E.oplen); }
-    const ReadRec & R = hb.reads[E.read];
-    const uint8_t *s = hb.seq.data() + R.seq_off;
+    const uint8_t *s = hb.raw_seq(E.raw);
     std::string out;
     for (int32_t i = 0; i < E.oplen; i++) { const int32_t q = E.qpos + i; out.push_back(nt16[(s[q >> 1] >> ((~q & 1) << 2)) & 0xf]); }
     return out;
