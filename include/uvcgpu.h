@@ -267,7 +267,8 @@ typedef struct uvcgpu_batch_stats {
     int64_t n_tiles, n_reads_in, n_reads_kept, n_positions, n_ext_positions, n_families, n_fragments;
     int64_t h2d_bytes, d2h_bytes, gpu_launches;
     double host_prep_ms, h2d_ms, kernel_ms, d2h_ms;
-    double kernel_ms_by_stage[16];   /* 0-10: K0, K1, K2, K2e, KF, K3a, K3b, KM, K4a, K4, K4c; 11: K6 block-line inputs; 12: K5 candidate scoring */
+    double kernel_ms_by_stage[16];   /* 0-10: K0, K1, K2, K2e, KF, K3a, K3b, KM, K4a, K4, K4c; 11: K6 block-line inputs; 12: K5 candidate scoring;
+                                        13: staging kernels (P0 read filter + family segmentation, P1 reference context) */
     int64_t n_vcf_records;           /* candidate records the scoring stage kept */
     double host_score_ms;            /* host part of the scoring stage (indel allele table, record ordering) */
     double reserved[6];

@@ -72,6 +72,29 @@ def test_cli_tiler_under_memory_pressure(synth_cli, tmp_path):
 
 
 @needs_ref
+def test_cli_platform_offsets_are_added_to_user_values(synth_cli, tmp_path):
+    """--syserr-minABQ-* given on the command line: the reference adds the Illumina offsets (200 / 100) to the user value (CmdLineArgs.cpp:127-134)."""
+    _compare(EMU, synth_cli, tmp_path, ["-t", "4", "--syserr-minABQ-pcr-snv", "50", "--syserr-minABQ-cap-snv", "50", "--syserr-minABQ-cap-indel", "20"], bed=False)
+
+
+def test_cli_fails_on_bad_index(synth_cli, tmp_path):
+    """A .bai with a foreign magic or a truncated .bai is an error (the reference: 'Failed to load BAM index'), not an empty VCF."""
+    import shutil
+    bam = str(tmp_path / "x.bam")
+    shutil.copy(synth_cli["bam"], bam)
+    bai = open(synth_cli["bam"] + ".bai", "rb").read()
+    for bad in (b"XXXX" + bai[4:], bai[:60]):
+        open(bam + ".bai", "wb").write(bad)
+        p = subprocess.run([EMU, bam, "-f", synth_cli["fasta"], "-o", str(tmp_path / "x.vcf.gz")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert p.returncode != 0 and "BAM index" in p.stderr
+
+
+def test_cli_rejects_germline_records(synth_cli, tmp_path):
+    p = subprocess.run([EMU, synth_cli["bam"], "-f", synth_cli["fasta"], "-o", str(tmp_path / "x.vcf.gz"), "--outvar-flag", "63"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 105 and "GERMLINE" in p.stderr
+
+
+@needs_ref
 def test_cli_output_independent_of_batching(synth_cli, tmp_path):
     a, b = str(tmp_path / "a.vcf.gz"), str(tmp_path / "b.vcf.gz")
     _run(EMU, synth_cli["bam"], synth_cli["fasta"], a, ["-t", "3", "--mem-per-thread", "30", "--gpu-batch-positions", "3000", "--lanes-per-gpu", "3"])

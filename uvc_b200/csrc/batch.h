@@ -80,6 +80,29 @@ struct ReadDerived {
     int32_t xm_term, bm_term[5];                       // (x > 20 ? 100 * 400 / (x * x) : 100) for x = xm1500, bm1500[b]
 };
 
+// What the bias pileup (kernel K2) needs from a read, 64 bytes, written by K0: the per-read terms of dealwith_segbias (main.hpp:1360-1595) that do
+// not depend on the position are evaluated once per read instead of once per (read, position), and a warp stages a chunk of these records
+// with one bulk asynchronous copy. bits: UVC_PR_* | mapq << 16 | micro_nogap_penal << 24.
+struct alignas(16) PileRec {
+    int32_t pos, rend, frag_l, frag_r;             // frag_l = min(pos, mpos), frag_r = frag_l + |isize|
+    int32_t baq_pos, baq_rend1, baq2_rend1; uint32_t bits;
+    uint32_t seq_off, qual_off; int32_t cx_off; uint32_t terms_lo;    // cx_off: simple reads keep m_qoff here; terms_lo = xm_term | bm_term[0] << 7 | bm_term[1] << 14 | bm_term[2] << 21
+    uint32_t terms_hi; int32_t ibeg, iend; int32_t l_qseq;           // terms_hi = bm_term[3] | bm_term[4] << 7
+};
+#define UVC_PR_ISRC 0x1u            // flag & 0x10
+#define UVC_PR_PAIRED 0x2u          // flag & 0x1
+#define UVC_PR_MATE_UNMAPPED 0x4u   // flag & 0x8
+#define UVC_PR_STRAND 0x8u          // bam_get_strand
+#define UVC_PR_HAS_ISIZE 0x10u      // isize != 0
+#define UVC_PR_AMPLICON 0x20u       // is_assay_amplicon (main.hpp:1385-1387)
+#define UVC_PR_UMI 0x40u            // duplexflag & 0x1
+#define UVC_PR_NOCLIP 0x80u         // no soft/hard clip
+#define UVC_PR_SIMPLE 0x100u        // CIGAR is [S|H] M [S|H]
+#define UVC_PR_HAS_GAPS 0x200u      // at least one inserted / deleted base
+#define UVC_PR_MASK_ON 0x400u       // primers of this read are masked outside [ibeg, iend)
+#define UVC_PR_IS_NORMAL 0x800u     // isize != 0 or not paired (main.hpp:1531)
+#define UVC_PR_MATE_OK 0x1000u      // mate mapped or not paired
+
 // Per-reference-base expansion entry of a complex read: what the read shows at reference offset o = p - pos.
 struct CxEntry {
     int32_t prev_rpos, next_rpos; // aligned bases: neighbouring entries of the low-quality-indel list (main.hpp:1902-1903);
@@ -195,6 +218,7 @@ struct BatchView {
     // reads
     const ReadRec *reads;
     ReadDerived *rd;
+    PileRec *prec;                 // [n_reads], kernel K0
     const uint8_t *seq;
     uint8_t *qual;                 // per kept read: its base qualities after the reference's quality fix-ups (grouping.cpp:459-543), written by K0
     const uint8_t *qual_raw;       // base qualities as uploaded (a record that two tiles keep is shared here)

@@ -69,6 +69,8 @@ struct BatchState {
 #if UVC_CUDA
     cudaEvent_t ev[UVC_N_PILEUP_STAGES + 1];
     bool have_events = false;
+    cudaEvent_t ev_prep[2];               // around the staging kernels (stages P0/P1)
+    bool have_prep_events = false;
 #endif
 };
 
@@ -87,6 +89,8 @@ struct uvcgpu_ctx {
     int host_threads = 0;
 #if UVC_CUDA
     cudaStream_t stream = nullptr;        // submit: staging copies and the pileup kernels of every batch, in submission order
+    cudaStream_t prep_stream = nullptr;   // staging kernels (stages P0/P1) of a batch and their two short synchronisations: they depend on nothing that the
+                                          // pileup kernels of the previous batch compute, so they do not queue behind them
     cudaStream_t post_stream = nullptr;   // everything after collect (scoring kernels, downloads) of a batch, so that it does not queue behind the next batch
     cudaStream_t active = nullptr;        // the stream the backend helpers use: `stream`, or `post_stream` inside PostScope
 #endif
@@ -295,14 +299,62 @@ __device__ __forceinline__ void uvc_gather_bases(const BatchView & v, const Read
     }
 }
 
+// ---- bulk asynchronous copies (TMA unit, cp.async.bulk) completed on an mbarrier: one elected lane moves a whole chunk of records
+__device__ __forceinline__ void uvc_mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void uvc_mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void uvc_mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+// bytes is a multiple of 16; source and destination are 16-byte aligned
+__device__ __forceinline__ void uvc_bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void uvc_mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+// gather of the (base, quality) byte pairs of a staged chunk of compact records, in groups of 8 reads (see uvc_gather_bases)
+__device__ __forceinline__ void uvc_gather_bases_p(const BatchView & v, const PileRec *sP, uint16_t (*bq)[32], int nc, int64_t cb, const uvc::Win & w, int32_t p, bool active, int lane) {
+    for (int k0 = 0; k0 < nc; k0 += 8) {
+        int32_t qp[8];
+        uint32_t sb[8], qb[8];
+        #pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k = (k0 + j < nc ? k0 + j : nc - 1);
+            const int64_t ri = cb + k;
+            const PileRec & P = sP[k];
+            qp[j] = uvc::base_index(v, P, p, active && ri >= w.lo && ri < w.hi);
+            const int32_t qc = (qp[j] > 0 ? qp[j] : 0);
+            sb[j] = v.seq[(uint64_t)P.seq_off + (uint32_t)(qc >> 1)];
+            qb[j] = v.qual[(uint64_t)P.qual_off + (uint32_t)qc];
+        }
+        #pragma unroll
+        for (int j = 0; j < 8; j++) { bq[k0 + j][lane] = (uint16_t)uvc::pack_base(sb[j], qb[j], qp[j]); }
+    }
+}
+
 // K2: both roles of a position sit in different warps of the same block: block = 64 positions x 2 roles.
-// Each warp stages the records (ReadRec + ReadDerived) of UVC_STAGE_READS reads of its union window in shared memory (asynchronously, one chunk ahead),
-// role 0 then gathers the (base, quality) byte pairs of the whole chunk with independent loads (memory-level parallelism instead of one
-// dependent load pair per read), and the per-read work runs entirely from shared memory.
-struct __align__(16) K2Stage {
-    ReadRec R[2][UVC_STAGE_READS];
-    ReadDerived D[2][UVC_STAGE_READS];           // 32 records = 3200 bytes: every buffer starts on a 16-byte boundary
+// Each warp stages the compact records (PileRec, 64 bytes, written by K0) of UVC_STAGE_READS reads of its union window in shared memory: ONE
+// elected lane issues one bulk asynchronous copy per chunk (cp.async.bulk, completion on the warp's mbarrier), one chunk ahead; role 0
+// then gathers the (base, quality) byte pairs of the whole chunk with independent loads (memory-level parallelism instead of one dependent
+// load pair per read), and the per-read work runs entirely from shared memory.
+struct __align__(16) K2StageP {
+    PileRec P[2][UVC_STAGE_READS];
     uint16_t bq[UVC_STAGE_READS][32];
+    uint64_t bar[2];
 };
 #ifndef UVC_K2_MINBLOCKS
 #define UVC_K2_MINBLOCKS 4    // 128 registers: four blocks per SM together with 24-read staging chunks
@@ -313,47 +365,50 @@ __global__ void __launch_bounds__(128, UVC_K2_MINBLOCKS) uvc_k2_bias_pileup(cons
     const int half = (int)(blockDim.x >> 1);                    // the block = `half` positions x 2 roles (64 or 128 threads)
     const int64_t gp = (i / blockDim.x) * half + (i % half);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    K2Stage & S = ((K2Stage*)uvc_smem)[warp];
+    K2StageP & S = ((K2StageP*)uvc_smem)[warp];
     const bool active = (gp < v.n_pos);
     const int role = (int)((i % blockDim.x) / half);
+    if (0 == lane) { uvc_mbar_init(&S.bar[0], 1); uvc_mbar_init(&S.bar[1], 1); uvc_mbar_fence_init(); }
+    __syncwarp();
     uvc::Win w;
     uvc_warp_window(v, gp, active, w);
     uvc::K2State st;
     st.p = 0;
     if (active) { uvc::k2_begin(st, v, gp, role); }
-    const int64_t c0 = w.ulo & ~(int64_t)3;
-    if (c0 < w.uhi) {
-        const int nc0 = (int)(w.uhi - c0 < UVC_STAGE_READS ? w.uhi - c0 : UVC_STAGE_READS);
-        uvc_warp_stage_async(S.R[0], v.reads, c0, nc0, lane);
-        uvc_warp_stage_async(S.D[0], v.rd, c0, nc0, lane);
-    }
-    uvc_cp_async_commit();
+    const int64_t c0 = w.ulo;
+    auto issue = [&](int64_t cb, int buf) {
+        if (cb < w.uhi && 0 == lane) {
+            const unsigned bytes = (unsigned)((w.uhi - cb < UVC_STAGE_READS ? w.uhi - cb : UVC_STAGE_READS) * sizeof(PileRec));
+            uvc_mbar_expect_tx(&S.bar[buf], bytes);
+            uvc_bulk_g2s(S.P[buf], v.prec + cb, bytes, &S.bar[buf]);
+        }
+    };
+    issue(c0, 0);
+    unsigned phase0 = 0, phase1 = 0;
     int buf = 0;
     for (int64_t cb = c0; cb < w.uhi; cb += UVC_STAGE_READS, buf ^= 1) {
         const int nc = (int)(w.uhi - cb < UVC_STAGE_READS ? w.uhi - cb : UVC_STAGE_READS);
-        const int64_t nb = cb + UVC_STAGE_READS;
-        if (nb < w.uhi) {
-            const int nn = (int)(w.uhi - nb < UVC_STAGE_READS ? w.uhi - nb : UVC_STAGE_READS);
-            uvc_warp_stage_async(S.R[buf ^ 1], v.reads, nb, nn, lane);
-            uvc_warp_stage_async(S.D[buf ^ 1], v.rd, nb, nn, lane);
-        }
-        uvc_cp_async_commit();
-        uvc_cp_async_wait<1>();
-        __syncwarp();
-        const ReadRec *sR = S.R[buf];
-        const ReadDerived *sD = S.D[buf];
-        if (role == 0) { uvc_gather_bases(v, sR, S.bq, nc, cb, w, st.p, active, lane); }
+        issue(cb + UVC_STAGE_READS, buf ^ 1);          // (every lane finished with that buffer before the __syncwarp that ended the previous iteration)
+        if (buf) { uvc_mbar_wait(&S.bar[1], phase1); phase1 ^= 1u; } else { uvc_mbar_wait(&S.bar[0], phase0); phase0 ^= 1u; }
+        const PileRec *sP = S.P[buf];
+        if (role == 0) { uvc_gather_bases_p(v, sP, S.bq, nc, cb, w, st.p, active, lane); }
         if (active) {
             for (int k = 0; k < nc; k++) {
                 const int64_t ri = cb + k;
                 if (ri < w.lo || ri >= w.hi) { continue; }
-                uvc::k2_read(st, v, sR[k], sD[k], (uint32_t)S.bq[k][lane]);
+                uvc::k2_read(st, v, sP[k], (uint32_t)S.bq[k][lane]);
             }
         }
         __syncwarp();
     }
     if (active) { uvc::k2_end(st, v); }
 }
+// staging slot of K1: full per-read records (ReadRec + ReadDerived), double-buffered with cp.async
+struct __align__(16) K2Stage {
+    ReadRec R[2][UVC_STAGE_READS];
+    ReadDerived D[2][UVC_STAGE_READS];
+    uint16_t bq[UVC_STAGE_READS][32];
+};
 // K1: one thread per position; same staging as K2 (the records of UVC_STAGE_READS reads per warp, one chunk ahead) and the same grouped byte gather
 __global__ void __launch_bounds__(128) uvc_k1_prep_thres(const BatchView v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
@@ -679,8 +734,8 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
     if (v.n_pos > 0) {
-        static_assert(sizeof(K2Stage) % 16 == 0, "per-warp staging slots keep 16-byte alignment");
-        const size_t smem = 4 * sizeof(K2Stage);
+        static_assert(sizeof(K2StageP) % 16 == 0 && sizeof(PileRec) == 64, "per-warp staging slots keep 16-byte alignment");
+        const size_t smem = 4 * sizeof(K2StageP);
         UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k2_bias_pileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int pb2 = (pb < 64 ? 64 : pb);     // two roles: at least one warp each
         uvc_k2_bias_pileup<<<(unsigned)((v.n_pos + pb2 / 2 - 1) / (pb2 / 2)), pb2, smem * pb2 / 128, ctx->stream>>>(v, v.n_pos);
@@ -735,6 +790,15 @@ static int backend_wait(uvcgpu_ctx *ctx, BatchState & bs) {
         bs.stats.kernel_ms = total;
         for (int i = 0; i < UVC_N_PILEUP_STAGES + 1; i++) { cudaEventDestroy(bs.ev[i]); }
         bs.have_events = false;
+    }
+    if (bs.have_prep_events) {
+        // the staging kernels (P0/P1): includes the two short host round trips inside them (sizes of the batch)
+        float ms = 0;
+        UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, bs.ev_prep[0], bs.ev_prep[1]));
+        bs.stats.kernel_ms_by_stage[13] = ms;
+        bs.stats.kernel_ms += ms;
+        cudaEventDestroy(bs.ev_prep[0]); cudaEventDestroy(bs.ev_prep[1]);
+        bs.have_prep_events = false;
     }
     return 0;
 }
@@ -966,6 +1030,7 @@ int uvcgpu_create(uvcgpu_ctx **out, int device, const uvcgpu_params *params) {
     ctx->device = device;
     ctx->par = *params;
     if (params->indel_str_repeatsize_max > UVC_SLIP_MAXUNIT) { delete ctx; return UVCGPU_EUNSUPPORTED; }
+    if (params->outvar_flag & 0x1u) { delete ctx; return UVCGPU_EUNSUPPORTED; }     // GERMLINE text records (main.hpp:5736-5773) are not emitted by this build
     // indel_phred (main.hpp:794-801) tabulated with the host libm so that device and reference agree on every floor()
     ctx->slip_tab.assign((size_t)2 * UVC_SLIP_MAXUNIT * UVC_SLIP_NMAX, 0);
     for (int variant = 0; variant < 2; variant++) {
@@ -981,6 +1046,7 @@ int uvcgpu_create(uvcgpu_ctx **out, int device, const uvcgpu_params *params) {
 #if UVC_CUDA
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return UVCGPU_ECUDA; }
     if (cudaStreamCreateWithFlags(&ctx->post_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return UVCGPU_ECUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->post_stream); delete ctx; return UVCGPU_ECUDA; }
     ctx->active = ctx->stream;
     {   // keep freed device blocks in the stream-ordered pool instead of returning them to the driver after every batch
         cudaMemPool_t pool;
@@ -999,6 +1065,7 @@ void uvcgpu_destroy(uvcgpu_ctx *ctx) {
     cudaDeviceSynchronize();
     for (auto & kv : ctx->d_contigs) { cudaFree(kv.second); }
     if (ctx->post_stream) { cudaStreamDestroy(ctx->post_stream); }
+    if (ctx->prep_stream) { cudaStreamDestroy(ctx->prep_stream); }
     if (ctx->stream) { cudaStreamDestroy(ctx->stream); }
 #endif
     delete ctx;
@@ -1099,13 +1166,24 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
         UVC_UP(pf_tab, int32_t, pf)
     }
     // stages P0 and P1 on the device: read filter, family segmentation, reference context (prep_device.inc); fills the view's input arrays
+#if UVC_CUDA
+    ctx->active = ctx->prep_stream;
+    {
+        const int rc_prep = prep_on_device(ctx, *bs, n_tiles, tiles);
+        ctx->active = ctx->stream;
+        if (rc_prep != 0) { cudaStreamSynchronize(ctx->prep_stream); backend_free(ctx, *bs); return rc_prep; }
+    }
+    UVC_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, bs->ev_prep[1], 0));     // the pileup kernels start when the staging kernels are done
+#else
     UVC_TRY(prep_on_device(ctx, *bs, n_tiles, tiles));
+#endif
     const double t1 = now_ms();
     v.n_fcol = hb.n_fcol; v.n_mcol = hb.n_mcol;
     { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_fcol * sizeof(FragCol), false)); v.fcol = (FragCol*)d_; }
     UVC_ZERO(fmask, uint32_t, (v.n_fcol / UVC_COL_CHUNK) * 4)
     { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_mcol * sizeof(FamCol), false)); v.mcol = (FamCol*)d_; }
     UVC_ZERO(rd, ReadDerived, v.n_reads)
+    { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_reads * sizeof(PileRec), false)); v.prec = (PileRec*)d_; }
     UVC_ZERO(rfrag, ReadFrag, v.n_reads)
     UVC_ZERO(cx, CxEntry, v.n_cx)
     UVC_ZERO(ev, IndelEvent, v.n_ev)

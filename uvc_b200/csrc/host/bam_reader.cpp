@@ -207,6 +207,7 @@ inline uint32_t le32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1]
 } // namespace
 
 struct uvchost_bam {
+    int index_status = 0;                      // 1: .bai loaded, 0: no index file, -1: index file present but invalid (bad magic, truncated, wrong number of references)
     BgzfIn in;
     std::string path;
     uvchost_readbuf *span = NULL;              // reusable span buffer of uvchost_bam_fetch_tiles
@@ -263,28 +264,41 @@ uvchost_bam *uvchost_bam_open(const char *path) {
         std::string alt(path);
         if (alt.size() > 4 && alt.substr(alt.size() - 4) == ".bam") { alt = alt.substr(0, alt.size() - 4) + ".bai"; f = fopen(alt.c_str(), "rb"); }
     }
+    b->index_status = 0;
     if (f) {
         fseek(f, 0, SEEK_END);
         const long sz = ftell(f);
         fseek(f, 0, SEEK_SET);
-        std::vector<uint8_t> d((size_t)sz);
-        if (fread(d.data(), 1, (size_t)sz, f) == (size_t)sz && sz >= 8 && memcmp(d.data(), "BAI\1", 4) == 0) {
-            size_t o = 4;
-            const uint32_t nr = le32(&d[o]); o += 4;
-            b->lidx.resize(nr);
-            for (uint32_t r = 0; r < nr && o + 4 <= d.size(); r++) {
-                const uint32_t n_bin = le32(&d[o]); o += 4;
-                for (uint32_t bi = 0; bi < n_bin; bi++) { const uint32_t n_chunk = le32(&d[o + 4]); o += 8 + (size_t)n_chunk * 16; }
-                const uint32_t n_intv = le32(&d[o]); o += 4;
-                b->lidx[r].resize(n_intv);
-                for (uint32_t i = 0; i < n_intv; i++) { b->lidx[r][i] = (uint64_t)le32(&d[o]) | ((uint64_t)le32(&d[o + 4]) << 32); o += 8; }
+        std::vector<uint8_t> d((size_t)(sz > 0 ? sz : 0));
+        // every offset is checked against the file size: a truncated or foreign file must not pass as "no reads anywhere"
+        bool ok = (sz >= 8 && fread(d.data(), 1, (size_t)sz, f) == (size_t)sz && memcmp(d.data(), "BAI\1", 4) == 0);
+        size_t o = 4;
+        uint32_t nr = 0;
+        if (ok) { nr = le32(&d[o]); o += 4; ok = (nr == (uint32_t)n_ref); }
+        if (ok) { b->lidx.resize(nr); }
+        for (uint32_t r = 0; ok && r < nr; r++) {
+            if (o + 4 > d.size()) { ok = false; break; }
+            const uint32_t n_bin = le32(&d[o]); o += 4;
+            for (uint32_t bi = 0; ok && bi < n_bin; bi++) {
+                if (o + 8 > d.size()) { ok = false; break; }
+                const uint32_t n_chunk = le32(&d[o + 4]);
+                if ((d.size() - (o + 8)) / 16 < (size_t)n_chunk) { ok = false; break; }
+                o += 8 + (size_t)n_chunk * 16;
             }
+            if (!ok || o + 4 > d.size()) { ok = false; break; }
+            const uint32_t n_intv = le32(&d[o]); o += 4;
+            if ((d.size() - o) / 8 < (size_t)n_intv) { ok = false; break; }
+            b->lidx[r].resize(n_intv);
+            for (uint32_t i = 0; i < n_intv; i++) { b->lidx[r][i] = (uint64_t)le32(&d[o]) | ((uint64_t)le32(&d[o + 4]) << 32); o += 8; }
         }
+        if (!ok) { b->lidx.clear(); }
+        b->index_status = (ok ? 1 : -1);
         fclose(f);
     }
     return b;
 }
 
+int uvchost_bam_index_status(const uvchost_bam *b) { return (b ? b->index_status : 0); }
 void uvchost_bam_close(uvchost_bam *b) { if (b) { delete b->span; } delete b; }
 int32_t uvchost_bam_n_targets(const uvchost_bam *b) { return (int32_t)b->names.size(); }
 const char *uvchost_bam_target_name(const uvchost_bam *b, int32_t tid) { return b->names[tid].c_str(); }
@@ -329,6 +343,10 @@ int next_record(uvchost_bam *b, Core & c) {
     b->rec.resize((size_t)bs);
     if (b->in.read(b->rec.data(), bs) != bs) { return -1; }
     const uint8_t *x = b->rec.data();
+    {   // the variable-length parts must fit the record (a corrupt file must not be read out of bounds)
+        const int64_t l_qname = x[8], n_cigar = (int64_t)(x[12] | (x[13] << 8)), l_qseq = (int64_t)(int32_t)le32(x + 16);
+        if (l_qseq < 0 || 32 + l_qname + 4 * n_cigar + (l_qseq + 1) / 2 + l_qseq > (int64_t)bs || l_qname < 1) { return -1; }
+    }
     c.tid = (int32_t)le32(x); c.pos = (int32_t)le32(x + 4);
     c.l_qname = x[8]; c.mapq = x[9];
     c.n_cigar = x[12] | (x[13] << 8); c.flag = x[14] | (x[15] << 8);
@@ -404,6 +422,7 @@ void append_record(uvchost_readbuf *rb, const uvchost_bam *b, const Core & c) {
 extern "C" {
 
 int64_t uvchost_bam_fetch(uvchost_bam *b, int32_t tid, int64_t beg, int64_t end, uvchost_readbuf *rb) {
+    if (b->index_status != 1) { return -1; }
     if (beg < 0) { beg = 0; }
     if (tid < 0 || (size_t)tid >= b->lidx.size() || beg >= end) { return 0; }
     const std::vector<uint64_t> & l = b->lidx[tid];
@@ -571,6 +590,7 @@ int uvchost_bam_next_core(uvchost_bam *b, uvchost_core *out) {
 }
 
 int uvchost_bam_seek_region(uvchost_bam *b, int32_t tid, int64_t beg) {
+    if (b->index_status != 1) { return -1; }
     if (beg < 0) { beg = 0; }
     if (tid < 0 || (size_t)tid >= b->lidx.size()) { return 1; }
     const std::vector<uint64_t> & l = b->lidx[tid];

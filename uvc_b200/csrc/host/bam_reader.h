@@ -18,6 +18,10 @@ typedef struct uvchost_readbuf uvchost_readbuf;
 typedef struct uvchost_fasta uvchost_fasta;
 
 uvchost_bam *uvchost_bam_open(const char *path);          /* also loads <path>.bai */
+/* 1: <path>.bai loaded and consistent with the BAM header; 0: no index file; -1: an index file exists but is invalid (bad magic, truncated, or a
+ * different number of reference sequences). Region queries fail without a valid index (the reference exits with "Failed to load BAM index",
+ * main.cpp:1307-1311). */
+int uvchost_bam_index_status(const uvchost_bam *b);
 void uvchost_bam_close(uvchost_bam *b);
 int32_t uvchost_bam_n_targets(const uvchost_bam *b);
 const char *uvchost_bam_target_name(const uvchost_bam *b, int32_t tid);

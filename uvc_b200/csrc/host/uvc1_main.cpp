@@ -126,6 +126,9 @@ bool file_exists(const std::string & f) { std::ifstream s(f.c_str()); return (bo
 // returns 0, or an exit code
 int parse_args(Options & o, uvcgpu_params & par, int argc, char **argv) {
     bool have_bam = false;
+    // uvcgpu_params_default() holds these four with the Illumina inference already applied; on the command line the user value comes first and
+    // the platform offsets are added to it afterwards (CmdLineArgs.hpp:288-291 default 0; CmdLineArgs.cpp:127-134 adds 200 / 100)
+    par.syserr_minABQ_pcr_snv = 0; par.syserr_minABQ_pcr_indel = 0; par.syserr_minABQ_cap_snv = 0; par.syserr_minABQ_cap_indel = 0;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         auto need = [&](const char *name) -> const char* { if (i + 1 >= argc) { fprintf(stderr, "option %s needs a value\n", name); exit(109); } return argv[++i]; };
@@ -169,6 +172,7 @@ int parse_args(Options & o, uvcgpu_params & par, int argc, char **argv) {
         else { fprintf(stderr, "unexpected argument %s\n", a.c_str()); return 109; }
     }
     if (!have_bam) { usage(argv[0]); return 106; }
+    if (par.outvar_flag & 0x1u) { fprintf(stderr, "--outvar-flag bit 0x1 (GERMLINE text records, main.hpp:5736-5773) is not implemented in this build\n"); return 105; }
     return 0;
 }
 
@@ -389,6 +393,8 @@ int main(int argc, char **argv) {
     {
         uvchost_bam *b = uvchost_bam_open(o.bam.c_str());
         if (NULL == b) { fprintf(stderr, "Failed to load BAM file %s\n", o.bam.c_str()); return -3; }
+        // the reference stops when the index cannot be loaded (main.cpp:1307-1311); a missing, truncated or foreign .bai must not end in an empty VCF
+        if (uvchost_bam_index_status(b) != 1) { fprintf(stderr, "Failed to load BAM index %s.bai (%s)\n", o.bam.c_str(), uvchost_bam_index_status(b) == 0 ? "not found" : "invalid or truncated"); uvchost_bam_close(b); return -5; }
         for (int32_t i = 0; i < uvchost_bam_n_targets(b); i++) { sh.contigs.push_back(std::make_pair(std::string(uvchost_bam_target_name(b, i)), uvchost_bam_target_len(b, i))); }
         uvchost_infer_stats is;
         if (uvchost_bam_infer(b, 5000, &is) != 0) { fprintf(stderr, "Failed to read %s\n", o.bam.c_str()); return -3; }
@@ -403,6 +409,8 @@ int main(int argc, char **argv) {
         fprintf(stderr, "Inferred_sequencing_platform=%s\n IsPairedEnd=%d\n", illumina ? "Illumina/BGI" : "IonTorrent/LifeTechnologies/ThermoFisher", (int)is_pe);
         if (!illumina) { fprintf(stderr, "The IonTorrent-specific code path (TIsProton) is not implemented in this build.\n"); return 105; }
         sh.par.inferred_sequencing_platform = 1;
+        // SYSERR_MINABQ_SNV_ILLUMINA / SYSERR_MINABQ_INDEL_ILLUMINA are added to whatever the command line set (CmdLineArgs.cpp:127-134)
+        sh.par.syserr_minABQ_pcr_snv += 200; sh.par.syserr_minABQ_pcr_indel += 100; sh.par.syserr_minABQ_cap_snv += 200; sh.par.syserr_minABQ_cap_indel += 100;
     }
 
     const int64_t t_setup = now_us();

@@ -1,5 +1,5 @@
-// host_prep.h - host-side staging of a batch: read filter + family grouping (stage P0), base-quality fix-ups,
-// reference repeat context (stage P1) and SoA packing. Shared by the CUDA library and the test-only emulation.
+// host_prep.h - host-side pieces of the batch staging: page-locked staging memory, the host mirror of a batch (tiles; the grouping only when a
+// test hook asks for it) and the host-thread policy. Stages P0 and P1 themselves run on the device (prep_core.cuh, prep_device.inc).
 #ifndef UVC_HOST_PREP_H_INCLUDED
 #define UVC_HOST_PREP_H_INCLUDED
 
@@ -68,11 +68,6 @@ struct HostBatch {
     const uint8_t *raw_seq(int64_t raw) const { size_t s; const int64_t i = raw_to_host(raw, s); return raw_sources[s].seq + raw_sources[s].seq_off[i]; }
     const char *raw_qname(int64_t raw) const { size_t s; const int64_t i = raw_to_host(raw, s); return raw_sources[s].qname + raw_sources[s].qname_off[i]; }
 };
-
-// Builds the staging arrays of one batch. Returns 0 or a negative uvcgpu_error; msg receives the reason.
-// Tile k reads its records from sources[tile_source[k]] (tile_source == NULL: all tiles use sources[0]). n_threads <= 0: all cores.
-int uvc_build_host_batch(HostBatch & hb, const uvcgpu_params & par, const std::map<int32_t, HostContig> & contigs,
-        int32_t n_tiles, const uvcgpu_tile *tiles, const uvcgpu_reads_soa *sources, const int32_t *tile_source, int n_threads, std::string & msg);
 
 // Text form of the family grouping of one tile (same format as oracle/harness_dump.cpp writes).
 std::string uvc_families_text(const HostBatch & hb, int32_t tile_index);

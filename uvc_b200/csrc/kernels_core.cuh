@@ -362,6 +362,25 @@ UVC_HD void k0_read(const BatchView & v, int64_t ri, const uint8_t *seq_ro = NUL
     D.xm_term = (D.xm1500 > 20 ? (100 * 400 / (D.xm1500 * D.xm1500)) : 100);
     D.baq_pos = baq[pos]; D.baq_rend1 = baq[rend - 1]; D.baq2_rend1 = (v.baq2 + po)[rend - 1];
     v.rd[ri] = D;
+    {
+        PileRec P;
+        P.pos = pos; P.rend = rend; P.frag_l = frag_pos_L; P.frag_r = frag_pos_R;
+        P.baq_pos = D.baq_pos; P.baq_rend1 = D.baq_rend1; P.baq2_rend1 = D.baq2_rend1;
+        const bool is_assay_amplicon = ((R.dflag & 0x4) || ((par.primerlen > 0) && !(0x2 & par.primer_flag)));
+        const bool normal_filters_primers = (par.tn_is_paired && (0x1 & par.primer_flag));
+        P.bits = (isrc ? UVC_PR_ISRC : 0u) | ((R.flag & 0x1) ? UVC_PR_PAIRED : 0u) | ((R.flag & 0x8) ? UVC_PR_MATE_UNMAPPED : 0u) | (R.strand ? UVC_PR_STRAND : 0u)
+            | ((R.isize != 0) ? UVC_PR_HAS_ISIZE : 0u) | (is_assay_amplicon ? UVC_PR_AMPLICON : 0u) | ((R.dflag & 0x1) ? UVC_PR_UMI : 0u)
+            | ((0 == D.clip_cnt) ? UVC_PR_NOCLIP : 0u) | (R.simple ? UVC_PR_SIMPLE : 0u) | ((D.nge_cnt > 0) ? UVC_PR_HAS_GAPS : 0u)
+            | ((!(normal_filters_primers || !is_assay_amplicon)) ? UVC_PR_MASK_ON : 0u)
+            | (((R.isize != 0) || (0 == (R.flag & 0x1))) ? UVC_PR_IS_NORMAL : 0u) | (((0 == (R.flag & 0x8)) || (0 == (R.flag & 0x1))) ? UVC_PR_MATE_OK : 0u)
+            | ((uint32_t)R.mapq << 16) | ((uint32_t)D.micro_nogap_penal << 24);
+        P.seq_off = (uint32_t)R.seq_off; P.qual_off = (uint32_t)R.qual_off; P.cx_off = (R.simple ? R.m_qoff : R.cx_off);
+        P.terms_lo = (uint32_t)D.xm_term | ((uint32_t)D.bm_term[0] << 7) | ((uint32_t)D.bm_term[1] << 14) | ((uint32_t)D.bm_term[2] << 21);
+        P.terms_hi = (uint32_t)D.bm_term[3] | ((uint32_t)D.bm_term[4] << 7);
+        P.ibeg = D.ibeg; P.iend = D.iend;
+        P.l_qseq = R.l_qseq;
+        v.prec[ri] = P;
+    }
 
     if (!R.simple) {
         // Replay of the bias walk's bookkeeping (main.hpp:1817-1859, 1886-2257): for every reference base of the read, what it
@@ -454,6 +473,13 @@ UVC_HD int32_t base_index(const BatchView & v, const ReadRec & R, int32_t p, boo
     if (R.simple) { return tmin(R.m_qoff + o, R.l_qseq - 1); }
     const CxEntry e = v.cx[(int64_t)R.cx_off + o];
     return ((e.flags & 1) ? tmax(0, tmin((int32_t)e.qpos, R.l_qseq - 1)) : -1);
+}
+UVC_HD int32_t base_index(const BatchView & v, const PileRec & P, int32_t p, bool mine) {
+    const int32_t o = p - P.pos;
+    if (!(mine && o >= 0 && p < P.rend && P.l_qseq > 0)) { return -1; }
+    if (P.bits & UVC_PR_SIMPLE) { return tmin(P.cx_off + o, P.l_qseq - 1); }
+    const CxEntry e = v.cx[(int64_t)P.cx_off + o];
+    return ((e.flags & 1) ? tmax(0, tmin((int32_t)e.qpos, P.l_qseq - 1)) : -1);
 }
 UVC_HD uint32_t pack_base(uint32_t seq_byte, uint32_t qual_byte, int32_t qpos) {
     const uint32_t sym = (uint32_t)nt16_to_symbol(seq_byte >> ((~qpos & 1) << 2));
@@ -774,34 +800,144 @@ UVC_HD uint32_t k2_fetch_base(const K2State & s, const BatchView & v, const Read
     return pack_base(v.seq[R.seq_off + (uint32_t)(qc >> 1)], v.qual[R.qual_off + (uint32_t)qc], qpos);
 }
 
-// one read of the position's window (R, D may live in shared memory: the CUDA kernel stages the records of UVC_STAGE_READS reads per warp at a time);
+// dealwith_segbias<isGap> (main.hpp:1360-1595) for an aligned base (isGap = false) or the gap-free junction before it (isGap = true), from the
+// compact record of the read (batch.h: PileRec): same arithmetic as segbias() with is_ins_op = false and indel_len = 0, with the per-read
+// conditions taken from P.bits.
+template <bool isGap>
+UVC_HD void segbias_dense(SegAcc & a, const BatchView & v, const PileRec & P, const uvcgpu_thres_set & th,
+        int32_t baq_rpos, int32_t baq2_rpos, int32_t bq, int32_t rpos, int32_t bm_term, int32_t xm_term, int32_t dist_indel, bool normal_filters_primers) {
+    const uvcgpu_params & par = v.par;
+    const uint32_t bits = P.bits;
+    const bool is_assay_amplicon = (bits & UVC_PR_AMPLICON);
+    const int32_t seg_l_baq1 = baq_rpos - P.baq_pos + 1;
+    const int32_t seg_r_baq0 = P.baq_rend1 - baq_rpos + 1;
+    const int32_t seg_r_baq1 = (isGap ? tmin(seg_r_baq0, P.baq2_rend1 - baq2_rpos + 7) : seg_r_baq0);
+    const int32_t seg_l_nbases = rpos - P.pos + 1;
+    const int32_t seg_r_nbases = P.rend - rpos;
+    const bool is_high_readlen = (par.central_readlen >= par.microadjust_median_readlen_thres);
+    const int32_t seg_l_baq = (is_high_readlen ? seg_l_baq1 : tmax(seg_l_baq1, seg_l_nbases * par.microadjust_BAQ_per_base_x1024 / 1024));
+    const int32_t seg_r_baq = (is_high_readlen ? seg_r_baq1 : tmax(seg_r_baq1, seg_r_nbases * par.microadjust_BAQ_per_base_x1024 / 1024));
+    const int32_t has_isize = ((bits & UVC_PR_HAS_ISIZE) ? 1 : 0);
+    const int32_t frag_l_nb = (has_isize ? tmin(rpos - P.frag_l + 1, UVC_MAX_INSERT_SIZE) : UVC_MAX_INSERT_SIZE);
+    const int32_t frag_r_nb = (has_isize ? tmin(P.frag_r - rpos, UVC_MAX_INSERT_SIZE) : UVC_MAX_INSERT_SIZE);
+    const bool isrc = (bits & UVC_PR_ISRC);
+
+    const int32_t rc = (isrc ? 1 : 0), fw = 1 - rc;
+    const int32_t sq = bq * bq / UVC_SQR_QUAL_DIV;
+    a.a1BQr += rc * bq; a.a2BQr += rc * sq; a.a1BQf += fw * bq; a.a2BQf += fw * sq;
+    a.s.aMQs += (int32_t)((bits >> 16) & 0xffu);
+    const int32_t st1 = ((bits & UVC_PR_STRAND) ? 1 : 0), st0 = 1 - st1;
+    a.s.aDPrr += st1 * rc; a.s.aDPrf += st1 * fw; a.s.aDPfr += st0 * rc; a.s.aDPff += st0 * fw;
+    a.s.aP3 += ((tmin(dist_indel, tmin(seg_l_nbases, seg_r_nbases)) >= par.bias_thres_interfering_indel) ? 1 : 0);
+    a.s.aNC += ((bits & UVC_PR_NOCLIP) ? 1 : 0);
+    a.s.aLIT += (int64_t)(rc * has_isize * frag_l_nb); a.s.aRIT += (int64_t)(fw * has_isize * frag_r_nb);
+
+    const int32_t LPxT0 = th.aLPxT, RPxT = th.aRPxT;
+    const int32_t LPxT = (isGap ? LPxT0 : tmin(LPxT0, RPxT));
+    const bool far_from_edge = (seg_l_nbases >= LPxT) & (seg_r_nbases >= RPxT);
+    const int32_t highBAQ = par.bias_thres_highBAQ + (isGap ? 0 : 3);
+    const bool unaffected_by_edge = (seg_l_baq >= highBAQ) & (seg_r_baq >= highBAQ);
+    const int32_t min_dist2iend = ((bits & UVC_PR_PAIRED) ? tmin(frag_l_nb, frag_r_nb) : (isrc ? seg_r_nbases : seg_l_nbases));
+    a.s.aP1 += ((far_from_edge & unaffected_by_edge & ((min_dist2iend > par.primerlen2) | !is_assay_amplicon)) ? 1 : 0);
+    a.s.aP2 += (((bits & UVC_PR_UMI) != 0) | !is_assay_amplicon) ? 1 : 0;
+
+    int32_t f1, f2;
+    if ((uint32_t)bq < 128u) { f1 = v.pf_tab[bq]; f2 = v.pf_tab[128 + bq]; }
+    else {
+        f1 = ((bq < par.bias_thres_PFBQ1) ? (100 * (bq * bq) / (par.bias_thres_PFBQ1 * par.bias_thres_PFBQ1)) : 100);
+        f2 = ((bq < par.bias_thres_PFBQ2) ? (100 * (bq * bq) / (par.bias_thres_PFBQ2 * par.bias_thres_PFBQ2)) : 100);
+    }
+    if (isGap) {
+        a.s.aPF1 += tmin(100, f1);
+        a.s.aPF2 += tmin(100, f2);
+    } else {
+        a.s.aPF1 += (100 * f1 / 100);
+        a.s.aPF2 += (100 * f2 / 100);
+        a.s.a2XM2 += xm_term;
+        a.s.a2BM2 += bm_term;
+    }
+    {
+        const bool counted = (isGap ? (dist_indel >= par.bias_thres_interfering_indel) : (bq >= par.bias_thres_highBQ));
+        const bool tier2 = (isGap | (bq >= par.bias_thres_highBQ));
+        const int32_t gp_ = ((counted & far_from_edge) ? 1 : 0), gb_ = ((counted & unaffected_by_edge) ? 1 : 0), t2 = (tier2 ? 1 : 0);
+        const int32_t nl = seg_l_nbases, nr = seg_r_nbases;
+        a.s.aLP1 += gp_ * ((nl >= th.aLP1t) ? 1 : 0);
+        a.s.aLP2 += gp_ * t2 * ((nl >= th.aLP2t) ? 1 : 0);
+        a.s.aRP1 += gp_ * ((nr >= th.aRP1t) ? 1 : 0);
+        a.s.aRP2 += gp_ * t2 * ((nr >= th.aRP2t) ? 1 : 0);
+        a.s.aLPL += gp_ * nl; a.s.aRPL += gp_ * nr;
+        a.s.aLB1 += gb_ * ((seg_l_baq >= par.bias_thres_BAQ1) ? 1 : 0);
+        a.s.aLB2 += gb_ * t2 * ((seg_l_baq >= par.bias_thres_BAQ2) ? 1 : 0);
+        a.s.aRB1 += gb_ * ((seg_r_baq >= par.bias_thres_BAQ1) ? 1 : 0);
+        a.s.aRB2 += gb_ * t2 * ((seg_r_baq >= par.bias_thres_BAQ2) ? 1 : 0);
+        a.s.aLBL += (int64_t)(gb_ * seg_l_baq); a.s.aRBL += (int64_t)(gb_ * seg_r_baq);
+        a.s.aBQ2 += (counted ? 1 : 0);
+    }
+    {
+        const bool mate_ok = (bits & UVC_PR_MATE_OK);
+        const bool nonbiased = (mate_ok & (isrc ? (seg_l_nbases > seg_r_nbases) : (seg_l_nbases < seg_r_nbases)));
+        const bool pos_good = ((!is_assay_amplicon) | (!normal_filters_primers) | (far_from_edge & unaffected_by_edge));
+        const int32_t d = (isrc ? frag_l_nb : frag_r_nb);
+        const int32_t t1 = (isrc ? th.aLI1t : th.aRI1t), T1 = (isrc ? th.aLI1T : th.aRI1T);
+        const int32_t t2 = (isrc ? th.aLI2t : th.aRI2t), T2 = (isrc ? th.aLI2T : th.aRI2T);
+        const bool ok = (((bits & UVC_PR_IS_NORMAL) != 0) | (isGap & nonbiased));
+        const int32_t c1 = (((d >= t1) & ((d <= T1) | isGap) & ok) ? 1 : 0);
+        const int32_t c2 = (((d >= t2) & ((d <= T2) | isGap) & ok & pos_good) ? 1 : 0);
+        const int32_t c3 = (pos_good ? 1 : 0);
+        a.s.aLI1 += rc * c1; a.s.aLI2 += rc * c2; a.s.aLIr += rc * c3;
+        a.s.aRI1 += fw * c1; a.s.aRI2 += fw * c2; a.s.aRIf += fw * c3;
+    }
+}
+
+// one read of the position's window, from its compact record (the CUDA kernel stages the records of UVC_STAGE_READS reads per warp at a time);
 // `packed` is k2_fetch_base of this read (role 0 only)
-UVC_HD void k2_read(K2State & s, const BatchView & v, const ReadRec & R, const ReadDerived & D, uint32_t packed) {
+UVC_HD void k2_read(K2State & s, const BatchView & v, const PileRec & P, uint32_t packed) {
     const int32_t p = s.p;
-    if (R.rend <= p) { return; }
+    if (P.rend <= p) { return; }
     if (s.role == 0 && packed == UVC_K2_NOBASE) { return; }
-    const Locus L = locate(v, R, p);
-    if (!L.is_m) { return; }
-    if (primer_masked(v, R, D, p)) { return; }
-    const int32_t dist = dist_to_interfering_indel(v, *s.T, D, L, s.th, p);
+    bool not_first;
+    int32_t prev_rpos = 0, next_rpos = INT32_MAX;
+    if (P.bits & UVC_PR_SIMPLE) { not_first = (p > P.pos); }
+    else {
+        const CxEntry e = v.cx[(int64_t)P.cx_off + (p - P.pos)];
+        if (!(e.flags & 1)) { return; }
+        not_first = (e.flags & 2); prev_rpos = e.prev_rpos; next_rpos = e.next_rpos;
+    }
+    if ((P.bits & UVC_PR_MASK_ON) && !(P.ibeg <= p && p < P.iend)) { return; }     // primer_masked
+    int32_t dist = 10000;
+    if (P.bits & UVC_PR_HAS_GAPS) {       // dist_to_interfering_indel
+        const TileInfo & T = *s.T;
+        const int32_t adj = v.par.indel_adj_tracklen_dist;
+        const int32_t npos = T.ext_end - T.ext_beg;
+        const uvcgpu_rtr *rtr = v.rtr + T.pos_off;
+        const int32_t ridx = p - T.ext_beg;
+        const uvcgpu_rtr rtr1 = rtr[tmax(ridx, adj) - adj];
+        const uvcgpu_rtr rtr2 = rtr[tmin(ridx + adj, npos - 1)];
+        const int32_t prevlen = nnminus(p - prev_rpos, tmax(p - (T.ext_beg + rtr1.begpos), s.th.aLP1t));
+        const int32_t nextlen = nnminus(next_rpos - p, tmax((T.ext_beg + rtr2.begpos + rtr2.tracklen) - p, s.th.aRP1t));
+        dist = tmin(prevlen, nextlen);
+    }
+    const bool nfp = (v.par.tn_is_paired && (0x1 & v.par.primer_flag));
     if (s.role == 1) {
-        if (!L.not_first) { return; }
-        const int32_t w = nnminus(tmin(80, s.noindel), D.micro_nogap_penal) + 1;   // nogap_weight
+        if (!not_first) { return; }
+        const int32_t w = nnminus(tmin(80, s.noindel), (int32_t)((P.bits >> 24) & 0xfu)) + 1;   // nogap_weight
         s.acc.bqsum += w;
-        segbias<true>(s.acc, v, R, D, s.th, s.baq_p, s.baq2_p, w, p, 100, false, 0, dist);
+        segbias_dense<true>(s.acc, v, P, s.th, s.baq_p, s.baq2_p, w, p, 100, 0, dist, nfp);
     } else {
         const int sym = (int)(packed >> 8);
         const int32_t bq = (int32_t)(packed & 0xffu) + v.par.bq_phred_added_misma;
+        const int32_t xm_term = (int32_t)(P.terms_lo & 127u);
+        const int32_t bm_term = (int32_t)((sym < 3 ? (P.terms_lo >> (7 * (sym + 1))) : (P.terms_hi >> (7 * (sym - 3)))) & 127u);
         if (sym == s.major) {
             s.acc.bqsum += bq;
-            segbias<false>(s.acc, v, R, D, s.th, s.baq_p, s.baq2_p, bq, p, D.bm_term[sym], false, 0, dist);
+            segbias_dense<false>(s.acc, v, P, s.th, s.baq_p, s.baq2_p, bq, p, bm_term, xm_term, dist, nfp);
         } else {
             // a base that differs from the reference (rare): its own symbol's records are updated with fire-and-forget atomics, which do not
             // stall the warp on ~40 dependent read-modify-writes (this thread is still the only writer of these records in this kernel)
             SegAcc one;
             segacc_zero(one);
             one.bqsum = bq;
-            segbias<false>(one, v, R, D, s.th, s.baq_p, s.baq2_p, bq, p, D.bm_term[sym], false, 0, dist);
+            segbias_dense<false>(one, v, P, s.th, s.baq_p, s.baq2_p, bq, p, bm_term, xm_term, dist, nfp);
             segacc_flush<true>(v, s.gp, sym, one);
         }
     }
@@ -816,7 +952,7 @@ UVC_HD void k2_position(const BatchView & v, int64_t gp, int role, const Win & w
     k2_begin(s, v, gp, role);
     for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
         if (ri < w.lo || ri >= w.hi) { continue; }
-        k2_read(s, v, v.reads[ri], v.rd[ri], (role == 0 ? k2_fetch_base(s, v, v.reads[ri], true) : 0u));
+        k2_read(s, v, v.prec[ri], (role == 0 ? k2_fetch_base(s, v, v.reads[ri], true) : 0u));
     }
     k2_end(s, v);
 }

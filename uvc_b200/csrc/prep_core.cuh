@@ -115,7 +115,7 @@ struct PrepView {
     const uvcgpu_tile *utiles;
     const PrepTile *pt;
     PairInfo *pair;
-    int32_t *hist; int32_t *psum; int32_t *nameset;
+    int32_t *hist; const int64_t *psum; int32_t *nameset;   // psum: exclusive prefix sum over the concatenated (tile, class) arrays of begin + end counts
     int32_t *keepflag; const int64_t *keepscan;       // [n_pairs + 1]
     int32_t *tile_bam_beg, *tile_bam_end, *tile_pcr, *tile_span;
     TileInfo *tiles;
@@ -310,19 +310,21 @@ struct P0bPair {
     }
 };
 
-// ------------------------------------------------------------------------------------------------ P0c: one thread per (tile, class)
-// border_psum (grouping.cpp:697-708): prefix sums of begin + end counts
-struct P0cPsum {
-    PrepView q;
+// ------------------------------------------------------------------------------------------------ P0c: one thread per histogram slot
+// border_psum (grouping.cpp:697-708): prefix sums of begin + end counts. The sums of all (tile, class) arrays are taken by ONE prefix sum over
+// their concatenation (only differences inside one array are ever used): this kernel writes its input, begin + end count per slot.
+struct P0cComb {
+    PrepView q; int32_t *comb;
     UVC_HD void operator()(int64_t k) const {
-        const int32_t t = (int32_t)(k >> 2), c = (int32_t)(k & 3);
-        const PrepTile & P = q.pt[t];
+        // slot k of the concatenation: tile t (by psum_off), class c, index i
+        int32_t a = 0, b = q.n_tiles;
+        while (b - a > 1) { const int32_t m = (a + b) >> 1; if (q.pt[m].psum_off <= k) { a = m; } else { b = m; } }
+        const PrepTile & P = q.pt[a];
         const int32_t fs = P.fetch_size;
+        const int64_t o = k - P.psum_off;
+        const int32_t c = (int32_t)(o / (fs + 1)), i = (int32_t)(o % (fs + 1));
         const int32_t *h = q.hist + P.hist_off;
-        int32_t *ps = q.psum + P.psum_off + (int64_t)c * (fs + 1);
-        int32_t sum = 0;
-        ps[0] = 0;
-        for (int32_t i = 0; i < fs; i++) { sum += h[(int64_t)c * fs + i] + h[(int64_t)(4 + c) * fs + i]; ps[i + 1] = sum; }
+        comb[k] = (i < fs ? h[(int64_t)c * fs + i] + h[(int64_t)(4 + c) * fs + i] : 0);
     }
 };
 
@@ -383,7 +385,7 @@ struct P0eKept {
         const int32_t fs = P.fetch_size;
         const int32_t fetch_tbeg = ut.beg_pos;
         const int32_t *beg_cnt = q.hist + P.hist_off + (int64_t)c * fs, *end_cnt = q.hist + P.hist_off + (int64_t)(4 + c) * fs;
-        const int32_t *psum = q.psum + P.psum_off + (int64_t)c * (fs + 1);
+        const int64_t *psum = q.psum + P.psum_off + (int64_t)c * (fs + 1);
         const int32_t pos = q.pos[i], mpos = q.mpos[i];
         const uint16_t flag = q.flag[i];
         atomic_min32(&q.tile_bam_beg[t], pos);
@@ -394,7 +396,7 @@ struct P0eKept {
         const int64_t beg2count = beg_cnt[beg2], end2count = end_cnt[end2];
         const int32_t insL = tmin(beg2 + 6, end2);
         const int32_t insR = (int32_t)tmax((int64_t)beg2, (int64_t)(end2 > 6 ? end2 - 6 : 0));
-        const int64_t tot = (int64_t)psum[insR] - (int64_t)psum[insL];
+        const int64_t tot = psum[insR] - psum[insL];
         const double begratio = (double)(beg2count * (insR - insL) + 1) / (double)(tot + (insR - insL) + 1);
         const double endratio = (double)(end2count * (insR - insL) + 1) / (double)(tot + (insR - insL) + 1);
         const bool beg_amp = (begratio > par.dedup_amplicon_border_to_insert_cov_weak_avgDP_ratio
