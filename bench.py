@@ -46,7 +46,9 @@ WORKLOADS = {"c1": "uvc1 tumor-only, synthetic 1 Mbp @100x, non-UMI (BASELINE.js
 # c3 at full size is 133 M reads (20 GB of BAM): benched on a stated fraction of its region, same depth and tile shapes.
 DEFAULT_SCALE = {"c1": 1.0, "c2": 1.0, "c3": 0.05}
 TILER_THREADS = 16
-SUB_BATCH_READS = 1_350_000
+# a sub-batch is full when it has enough positions to fill the GPU or when its reads reach the memory bound (the uvc1 host packs its batches the same way)
+SUB_BATCH_POSITIONS = 512_000
+SUB_BATCH_READS = 8_000_000
 # rough reference throughput on 16 cores (reads/s), only used to size the bounded CPU samples
 REF_RATE_GUESS = {"c1": 170e3, "c2": 95e3, "c3": 36e3}
 
@@ -61,7 +63,7 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=None, help="fraction of the named config's region (default: per-config)")
     ap.add_argument("--workdir", default=os.environ.get("UVC_BENCH_DIR", "/tmp/uvc_bench"))
     ap.add_argument("--contexts", type=int, default=4, help="contexts (CUDA streams) the e2e step pipelines its sub-batches over")
-    ap.add_argument("--sub-batches", type=int, default=0, help="sub-batches per step (0: ~1.35 M reads each)")
+    ap.add_argument("--sub-batches", type=int, default=0, help="sub-batches per step (0: packed to ~512 k positions or 8 M reads each)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-pipeline", action="store_true", help="do not time the whole uvc1 program")
     return ap.parse_args()
@@ -163,7 +165,7 @@ def tile_list(ds, nthreads: int = TILER_THREADS, bed=None):
             raise RuntimeError("tiler failed")
         if nreads == 0 and n.value == 0:
             break
-        tiles += [(p[i].tid, p[i].beg_pos, p[i].end_pos, p[i].region_flag) for i in range(n.value)]
+        tiles += [(p[i].tid, p[i].beg_pos, p[i].end_pos, p[i].region_flag, p[i].n_reads) for i in range(n.value)]
     lib.uvchost_tiler_close(t)
     return tiles
 
@@ -176,7 +178,22 @@ def decode_sub_batches(ds, tiles, n_sub, threads):
     lib = capi.load_host()
     lib.uvchost_bam_fetch_span.restype = C.c_int64
     lib.uvchost_bam_fetch_span.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
-    bounds = [len(tiles) * k // n_sub for k in range(n_sub + 1)]
+    if n_sub > 0:
+        bounds = [len(tiles) * k // n_sub for k in range(n_sub + 1)]
+    else:   # greedy packing by estimated positions (a read reaches about a fragment length beyond its tile) and reads, contig by contig
+        bounds = [0]
+        pos_sum = read_sum = 0
+        tile_bases = float(sum(t[2] - t[1] for t in tiles))
+        for k, t in enumerate(tiles):
+            # (BED lines carry no read count: estimated from the tile's share of the called positions)
+            lp, lr = (t[2] - t[1]) + 1000, (t[4] if t[4] > 0 else int(ds["n_reads"] * (t[2] - t[1]) / tile_bases))
+            if k > bounds[-1] and (pos_sum + lp > SUB_BATCH_POSITIONS or read_sum + lr > SUB_BATCH_READS or tiles[k - 1][0] != t[0]):
+                bounds.append(k)
+                pos_sum = read_sum = 0
+            pos_sum += lp
+            read_sum += lr
+        bounds.append(len(tiles))
+        n_sub = len(bounds) - 1
     subs = [None] * n_sub
     nxt = [0]
     lock = threading.Lock()
@@ -207,7 +224,7 @@ def decode_sub_batches(ds, tiles, n_sub, threads):
                     if lib.uvchost_bam_fetch_span(bf.handle, sl[i][0], n, begs, ends, rb.handle, rb0, rb1) < 0:
                         raise IOError("BAM fetch failed")
                     for q in range(n):
-                        tid, beg, end, flag = sl[i + q]
+                        tid, beg, end, flag = sl[i + q][:4]
                         ctiles.append(capi.make_tile(tid, beg, end, flag, ds["contigs"][tid][1], rb0[q], rb1[q], prev))
                         prev = (tid, beg, end)
                     i = j
@@ -399,11 +416,11 @@ def main():
     tiles = tile_list(ds)
     tile_s = time.time() - t_tile0
     n_reads = int(ds["n_reads"])             # primary mapped records of the BAM, each counted once, not once per overlapping tile
-    n_sub = args.sub_batches if args.sub_batches > 0 else max(min(8, len(tiles)), int(math.ceil(n_reads / float(SUB_BATCH_READS))))
-    n_sub = max(1, min(n_sub, len(tiles)))
+    n_sub = max(0, min(args.sub_batches, len(tiles)))       # 0: packed by positions and reads
     t_dec0 = time.time()
     subs = decode_sub_batches(ds, tiles, n_sub, host_threads)
     decode_s = time.time() - t_dec0
+    n_sub = len(subs)
     n_records = sum(len(s[1]) for s in subs)
     bam_bytes = os.path.getsize(ds["bam"])
     contig_bases = {tid: capi.read_fasta_contig(ds["fasta"], cname) for tid, (cname, _) in enumerate(ds["contigs"])}
@@ -648,7 +665,7 @@ def main():
                     "wall_ms_per_step": wall_s * 1e3 / args.steps,
                     "staging_blocks_not_yet_page_locked": {"at_start": backlog0, "at_end": backlog1},
                     "staging_page_locked_bytes": {"at_start": pinned0, "at_end": int(ctx0.lib.uvcgpu_staging_pinned_bytes())}},
-            "decode": {"seconds": decode_s, "threads": min(host_threads, n_sub), "records": n_records, "records_per_s": n_records / decode_s,
+            "decode": {"seconds": decode_s, "threads": min(host_threads, max(1, n_sub)), "records": n_records, "records_per_s": n_records / decode_s,
                        "bam_bytes": bam_bytes, "bam_MB_per_s": bam_bytes / decode_s / 1e6,
                        "what": "BGZF inflate + BAM record parsing into the SoA buffers of every tile's fetch window (each record stored once), untimed in `e2e`"},
             "gpu_launches": launches + totals["launch"],

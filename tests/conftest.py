@@ -42,3 +42,26 @@ def synth_umi(tmp_path_factory):
     cfg = synth.SynthConfig(name="umi", seed=4343, contigs=(("chrU", 5000),), depth=3000.0, umi=True, n_snv=4, n_indel=3,
                             vafs=(0.01, 0.05), targets=[(0, 1000, 4000)])
     return synth.generate(cfg, str(d))
+
+
+@pytest.fixture(scope="session")
+def synth_c2_depth(tmp_path_factory):
+    """BASELINE configs[1] shape at its real depth: 200 bp targets every 1000 bp at 2000x, half of them amplicon-like (shared fragment ends)."""
+    from uvc_b200 import synth
+    d = tmp_path_factory.mktemp("synth_c2_depth")
+    targets = [(0, 1000 + 1000 * i, 1200 + 1000 * i) for i in range(6)]
+    cfg = synth.SynthConfig(name="c2d", seed=1202, contigs=(("chrP", 8000),), depth=2000.0, targets=targets, amplicon_frac=0.5, n_snv=5, n_indel=3,
+                            vafs=(0.005, 0.01, 0.02, 0.05))
+    info = synth.generate(cfg, str(d))
+    info["targets"] = targets
+    return info
+
+
+@pytest.fixture(scope="session")
+def synth_c3_depth(tmp_path_factory):
+    """BASELINE configs[2] shape at its real depth: 20 000x raw depth, duplex UMIs, both the A+B and the B+A flavour of the bottom strand."""
+    from uvc_b200 import synth
+    d = tmp_path_factory.mktemp("synth_c3_depth")
+    cfg = synth.SynthConfig(name="c3d", seed=1303, contigs=(("chrD", 3000),), depth=20000.0, umi=True, n_snv=3, n_indel=2, vafs=(0.001, 0.005, 0.01),
+                            targets=[(0, 1000, 2000)], swapped_umi_frac=0.5)
+    return synth.generate(cfg, str(d))

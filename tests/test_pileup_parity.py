@@ -82,3 +82,18 @@ def test_cuda_pileup_matches_oracle_small(synth_small, tmp_path):
 @pytest.mark.gpu
 def test_cuda_pileup_matches_oracle_umi(synth_umi, tmp_path):
     _check(synth_umi, [(0, 1000, 2500, 4), (0, 2500, 4000, 2)], False, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cuda_pileup_c2_depth(synth_c2_depth, tmp_path):
+    """Panel tiles at 2000x (configs[1]): one tile per target, amplicon-like and capture-like targets, neighbouring tiles share their read halos."""
+    tiles = [(0, b, e, 8) for (_, b, e) in synth_c2_depth["targets"]]
+    st = _check(synth_c2_depth, tiles, False, tmp_path)
+    assert st.n_reads_kept > 10000
+
+
+@pytest.mark.gpu
+def test_cuda_pileup_c3_depth(synth_c3_depth, tmp_path):
+    """One tile at 20 000x raw depth with duplex UMIs (configs[2]): deep windows, multi-fragment families on both strands (the wide K4 shape)."""
+    st = _check(synth_c3_depth, [(0, 1000, 2000, 4)], False, tmp_path)
+    assert st.n_reads_kept > 100000 and st.n_families > 1000

@@ -26,6 +26,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #if defined(__CUDACC__) && !defined(UVC_EMU)
 #define UVC_CUDA 1
@@ -108,7 +109,19 @@ struct uvcgpu_ctx {
 #include <unordered_map>
 namespace {
 const size_t kStageSmall = (size_t)1 << 20;
-const size_t kStageMaxPinned = (size_t)24 << 30;
+// upper bound of page-locked staging memory: UVCGPU_MAX_PINNED_GB (default 24), never more than a quarter of the physical memory
+static size_t stage_max_pinned() {
+    static const size_t v = []() {
+        size_t gb = 24;
+        const char *e = getenv("UVCGPU_MAX_PINNED_GB");
+        if (e && atoi(e) >= 0) { gb = (size_t)atoi(e); }
+        size_t cap = gb << 30;
+        const long pages = sysconf(_SC_PHYS_PAGES), psz = sysconf(_SC_PAGE_SIZE);
+        if (pages > 0 && psz > 0) { cap = std::min(cap, (size_t)pages * (size_t)psz / 4); }
+        return cap;
+    }();
+    return v;
+}
 struct StageState {
     std::mutex mu;
     std::condition_variable cv;
@@ -137,7 +150,7 @@ void stage_provision_loop() {
             st.cv.wait(lk, [&]() { return st.stop || !st.wanted.empty(); });
             if (st.stop) { return; }
             cls = st.wanted.front(); st.wanted.pop_front();
-            if (st.total_pinned + cls > kStageMaxPinned) { continue; }
+            if (st.total_pinned + cls > stage_max_pinned()) { continue; }
             st.total_pinned += cls;
             st.in_progress = 1;
         }
@@ -163,8 +176,11 @@ void *uvc_stage_alloc(size_t bytes) {
         std::lock_guard<std::mutex> lk(st.mu);
         auto it = st.free_blocks.find(cls);
         if (it != st.free_blocks.end()) { void *p = it->second; st.free_blocks.erase(it); return p; }
-        st.wanted.push_back(cls);
-        st.wanted.push_back(cls);      // and a spare: the number of batches alive at once varies with the caller's pipelining
+        // one block for this request and a spare (the number of batches alive at once varies with the caller's pipelining), unless the same
+        // class is already queued twice: concurrent misses of one class must not queue a pile of blocks that nobody will use
+        int queued = 0;
+        for (size_t c : st.wanted) { if (c == cls) { queued++; } }
+        for (; queued < 2; queued++) { st.wanted.push_back(cls); }
         if (!st.thread_started && !st.stop) {
             st.thread_started = true;
             st.worker = std::thread(stage_provision_loop);
@@ -701,7 +717,10 @@ static int backend_download(uvcgpu_ctx *ctx, void *dst, const void *src, size_t 
     return 0;
 }
 static void backend_free_temps(uvcgpu_ctx *ctx, BatchState & bs) { for (void *p : bs.temp_allocs) { cudaFreeAsync(p, ctx->active); } bs.temp_allocs.clear(); }
-static void backend_free(uvcgpu_ctx *ctx, BatchState & bs) { backend_free_temps(ctx, bs); for (void *p : bs.allocs) { cudaFreeAsync(p, ctx->stream); } bs.allocs.clear(); }
+// A batch is released after everything of it has completed, while the submit stream may already hold the kernels of the next batch: freeing
+// there would make the blocks reusable only after those kernels (any stream that picks such a block up inherits the wait). The second stream of
+// the context is idle at that moment, so the blocks go back to the pool at once.
+static void backend_free(uvcgpu_ctx *ctx, BatchState & bs) { backend_free_temps(ctx, bs); for (void *p : bs.allocs) { cudaFreeAsync(p, ctx->post_stream); } bs.allocs.clear(); }
 // scratch of the staging kernels; fill >= 0: every byte is set to it
 static int backend_alloc_temp(uvcgpu_ctx *ctx, BatchState & bs, void **out, size_t bytes, int fill = -1) {
     bytes += 64;
@@ -1123,7 +1142,14 @@ int uvcgpu_set_contig_name(uvcgpu_ctx *ctx, int32_t tid, const char *name) {
     return UVCGPU_OK;
 }
 
-#define UVC_TRY(expr) { int rc_ = (expr); if (rc_ != 0) { backend_free(ctx, *bs); return rc_; } }
+// a failed submit: whatever was enqueued for the batch is drained before its memory goes back to the pool
+static void backend_abort(uvcgpu_ctx *ctx, BatchState & bs) {
+#if UVC_CUDA
+    cudaStreamSynchronize(ctx->prep_stream); cudaStreamSynchronize(ctx->stream);
+#endif
+    backend_free(ctx, bs);
+}
+#define UVC_TRY(expr) { int rc_ = (expr); if (rc_ != 0) { backend_abort(ctx, *bs); return rc_; } }
 
 int uvcgpu_submit(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, const uvcgpu_reads_soa *reads, uvcgpu_ticket *ticket) {
     return uvcgpu_submit_multi(ctx, n_tiles, tiles, 1, reads, NULL, ticket);
@@ -1171,7 +1197,7 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
     {
         const int rc_prep = prep_on_device(ctx, *bs, n_tiles, tiles);
         ctx->active = ctx->stream;
-        if (rc_prep != 0) { cudaStreamSynchronize(ctx->prep_stream); backend_free(ctx, *bs); return rc_prep; }
+        if (rc_prep != 0) { backend_abort(ctx, *bs); return rc_prep; }
     }
     UVC_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, bs->ev_prep[1], 0));     // the pileup kernels start when the staging kernels are done
 #else

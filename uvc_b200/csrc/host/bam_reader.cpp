@@ -461,6 +461,7 @@ static void copy_record(uvchost_readbuf *dst, const uvchost_readbuf *src, size_t
 int64_t uvchost_bam_fetch_tiles(uvchost_bam *b, int32_t tid, int32_t n, const int64_t *begs, const int64_t *ends, uvchost_readbuf *rb,
         int64_t *read_begin, int64_t *read_end) {
     if (n <= 0) { return 0; }
+    if (b->index_status != 1) { return -1; }
     int64_t span_beg = begs[0], span_end = ends[0], sum_len = 0;
     for (int32_t k = 0; k < n; k++) {
         if (begs[k] < span_beg) { span_beg = begs[k]; }
@@ -519,6 +520,7 @@ int64_t uvchost_bam_fetch_tiles(uvchost_bam *b, int32_t tid, int32_t n, const in
 int64_t uvchost_bam_fetch_span(uvchost_bam *b, int32_t tid, int32_t n, const int64_t *begs, const int64_t *ends, uvchost_readbuf *rb,
         int64_t *read_begin, int64_t *read_end) {
     if (n <= 0) { return 0; }
+    if (b->index_status != 1) { return -1; }
     for (int32_t k = 0; k + 1 < n; k++) { if (begs[k] > begs[k + 1] || ends[k] > ends[k + 1]) { return -2; } }
     const int64_t span_beg = (begs[0] < 0 ? 0 : begs[0]), span_end = ends[n - 1];
     const int64_t base = uvchost_readbuf_size(rb);

@@ -181,7 +181,9 @@ int64_t uvchost_tiler_next(uvchost_tiler *t, const uvchost_bedline **lines, int6
             uvchost_bedline l = t->given[t->given_idx];
             int64_t region_n_reads = t->bed_dp * (int64_t)(l.end_pos - l.beg_pos);
             if (-1 == t->bed_dp) { region_n_reads = (t->given_counts.empty() ? uvchost_bam_count(t->bam, l.tid, l.beg_pos, l.end_pos) : t->given_counts[t->given_idx]); }
-            t->emit(l);
+            // the tile list keeps the line as given (n_reads = 0 like the reference's BedLine); the callback gets the counted reads, which size the GPU batches
+            t->out.push_back(l);
+            if (t->cb) { uvchost_bedline lc = l; lc.n_reads = region_n_reads; t->cb(&lc, t->cb_user); }
             const int64_t region_n_rposs = l.end_pos - l.beg_pos;
             total_n_reads += region_n_reads; total_n_rposs += region_n_rposs;
             total_n_reads_sq += (int64_t)square_big(region_n_reads); total_n_rposs_sq += (int64_t)square_big(region_n_rposs);

@@ -46,7 +46,9 @@ struct Options {
     int64_t bed_in_avg_sequencing_DP = -1;
     int gpus = 0;                  // 0 = all visible
     int lanes_per_gpu = 0;         // 0 = automatic
-    int64_t batch_positions = 320 * 1000, batch_reads = 1500 * 1000;
+    // a batch is full when it has enough positions to fill the GPU (every position is a thread of the position kernels) or when its reads reach
+    // the memory bound (column caches and records grow with the reads): deep small panels need many reads per batch to get enough positions
+    int64_t batch_positions = 512 * 1000, batch_reads = 8 * 1000 * 1000;
     int compress_level = 5;
     bool stats = false;
 };
@@ -105,6 +107,7 @@ struct Shared {
         std::lock_guard<std::mutex> lk(fail_mutex);
         if (!failed.exchange(1)) { fail_msg = msg; }
         batches.abort();
+        { std::lock_guard<std::mutex> lk2(out_mutex); }     // the writer is either before its predicate check (it will see `failed`) or already waiting (it gets the notify)
         out_cv.notify_all();
     }
 };
@@ -213,7 +216,7 @@ struct BatchPacker {
     explicit BatchPacker(Shared *s) : sh(s) { prev.tid = -1; prev.beg_pos = 0; prev.end_pos = 0; prev.region_flag = 0; prev.n_reads = 0; }
     void flush() { if (!cur.tiles.empty()) { cur.seq = seq++; sh->batches.push(std::move(cur)); cur = Batch(); bp = 0; br = 0; } }
     void add(const uvchost_bedline & l) {
-        const int64_t lp = (int64_t)(l.end_pos - l.beg_pos) + 4200, lr = l.n_reads;
+        const int64_t lp = (int64_t)(l.end_pos - l.beg_pos) + 1000, lr = l.n_reads;     // (reads reach about a fragment length beyond the tile on either side)
         if (!cur.tiles.empty() && (bp + lp > sh->opt.batch_positions || br + lr > sh->opt.batch_reads || cur.tiles.back().tid != l.tid)) { flush(); }
         cur.tiles.push_back(l); cur.prevs.push_back(prev);
         prev = l; bp += lp; br += lr;
@@ -449,7 +452,7 @@ int main(int argc, char **argv) {
     }
     // writer: batches in tile order
     std::atomic<int> lanes_done(0);
-    std::thread joiner([&]() { for (auto & th : lanes) { th.join(); } lanes_done.store(1); sh.out_cv.notify_all(); });
+    std::thread joiner([&]() { for (auto & th : lanes) { th.join(); } { std::lock_guard<std::mutex> lk(sh.out_mutex); lanes_done.store(1); } sh.out_cv.notify_all(); });
     int64_t next_seq = 0, bytes_written = 0;
     for (;;) {
         std::string chunk;
