@@ -50,7 +50,6 @@ struct BatchState {
     std::vector<void*> temp_allocs;       // scratch of the device staging (stages P0/P1), freed as soon as the staging kernels are enqueued
     StageVec<uint8_t> raw_stage;          // page-locked copy of the caller's records that the batch needs (source of the one host-to-device copy)
     uvc::PrepView prep_view;              // arrays of the staging kernels that outlive them (reads, fragments, families)
-    BatchView *view_dev = nullptr;        // compute side: copy of `view` (out-of-line device functions read it there)
     int32_t *indelphred0 = nullptr;       // compute side: indelphred of every position before the threshold pass adjusts it (dump hook)
     bool groups_on_host = false;          // hb.reads / frags / fams / frag_reads downloaded (dump hook only)
     std::vector<std::pair<void*, size_t>> alloc_sizes;
@@ -368,20 +367,15 @@ __device__ __forceinline__ void uvc_gather_bases_p(const BatchView & v, const Pi
 // elected lane issues one bulk asynchronous copy per chunk (cp.async.bulk, completion on the warp's mbarrier), one chunk ahead; role 0
 // then gathers the (base, quality) byte pairs of the whole chunk with independent loads (memory-level parallelism instead of one dependent
 // load pair per read), and the per-read work runs entirely from shared memory.
-#define UVC_K2_QCAP 64
 struct __align__(16) K2StageP {
     PileRec P[2][UVC_STAGE_READS];
     uint16_t bq[UVC_STAGE_READS][32];
     uint64_t bar[2];
-    // queue of deferred mismatch events of the warp (role 0): a base that differs from the position's major symbol updates the records of its
-    // own symbol with ~40 reductions. Done inline, one such lane keeps the 31 others waiting; queued, 32 events are processed at once.
-    PileRec qP[UVC_K2_QCAP];
-    uint32_t qinfo[UVC_K2_QCAP];        // lane << 16 | packed (symbol, quality)
 };
 #ifndef UVC_K2_MINBLOCKS
 #define UVC_K2_MINBLOCKS 4    // 128 registers: four blocks per SM together with 24-read staging chunks
 #endif
-__global__ void __launch_bounds__(128, UVC_K2_MINBLOCKS) uvc_k2_bias_pileup(const BatchView v, const BatchView *vd /* the same view in global memory, for the out-of-line event handler */, int64_t n) {
+__global__ void __launch_bounds__(128, UVC_K2_MINBLOCKS) uvc_k2_bias_pileup(const BatchView v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int half = (int)(blockDim.x >> 1);                    // the block = `half` positions x 2 roles (64 or 128 threads)
@@ -405,16 +399,6 @@ __global__ void __launch_bounds__(128, UVC_K2_MINBLOCKS) uvc_k2_bias_pileup(cons
             uvc_bulk_g2s(S.P[buf], v.prec + cb, bytes, &S.bar[buf]);
         }
     };
-    // deferred mismatch events: entry e belongs to the position of lane (qinfo >> 16) of this warp; any lane can process it
-    int qn = 0;
-    auto drain = [&]() {
-        for (int e = lane; e < qn; e += 32) {
-            const uint32_t info = S.qinfo[e];
-            uvc::k2_mismatch_event(*vd, gp - lane + (int64_t)(info >> 16), S.qP[e], info & 0xffffu);
-        }
-        qn = 0;
-        __syncwarp();
-    };
     issue(c0, 0);
     unsigned phase0 = 0, phase1 = 0;
     int buf = 0;
@@ -423,35 +407,16 @@ __global__ void __launch_bounds__(128, UVC_K2_MINBLOCKS) uvc_k2_bias_pileup(cons
         issue(cb + UVC_STAGE_READS, buf ^ 1);          // (every lane finished with that buffer before the __syncwarp that ended the previous iteration)
         if (buf) { uvc_mbar_wait(&S.bar[1], phase1); phase1 ^= 1u; } else { uvc_mbar_wait(&S.bar[0], phase0); phase0 ^= 1u; }
         const PileRec *sP = S.P[buf];
-        if (role == 0) {
-            uvc_gather_bases_p(v, sP, S.bq, nc, cb, w, st.p, active, lane);
-            for (int k = 0; k < nc; k++) {
-                const int64_t ri = cb + k;
-                const uint32_t packed = (uint32_t)S.bq[k][lane];
-                const bool mm = ((active && ri >= w.lo && ri < w.hi) ? uvc::k2_read(st, v, sP[k], packed, true) : false);
-                const uint32_t mask = __ballot_sync(0xffffffffu, mm);
-                if (mask) {
-                    if (mm) {
-                        const int slot = qn + __popc(mask & ((1u << lane) - 1u));
-                        const uint4 *src = (const uint4*)&sP[k];
-                        uint4 *dst = (uint4*)&S.qP[slot];
-                        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
-                        S.qinfo[slot] = ((uint32_t)lane << 16) | packed;
-                    }
-                    qn += __popc(mask);
-                    if (qn > UVC_K2_QCAP - 32) { __syncwarp(); drain(); }
-                }
-            }
-        } else if (active) {
+        if (role == 0) { uvc_gather_bases_p(v, sP, S.bq, nc, cb, w, st.p, active, lane); }
+        if (active) {
             for (int k = 0; k < nc; k++) {
                 const int64_t ri = cb + k;
                 if (ri < w.lo || ri >= w.hi) { continue; }
-                uvc::k2_read(st, v, sP[k], 0u);
+                uvc::k2_read(st, v, sP[k], (uint32_t)S.bq[k][lane]);
             }
         }
         __syncwarp();
     }
-    if (role == 0) { drain(); }
     if (active) { uvc::k2_end(st, v); }
 }
 // staging slot of K1: full per-read records (ReadRec + ReadDerived), double-buffered with cp.async
@@ -792,7 +757,7 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
         const size_t smem = 4 * sizeof(K2StageP);
         UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k2_bias_pileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int pb2 = (pb < 64 ? 64 : pb);     // two roles: at least one warp each
-        uvc_k2_bias_pileup<<<(unsigned)((v.n_pos + pb2 / 2 - 1) / (pb2 / 2)), pb2, smem * pb2 / 128, ctx->stream>>>(v, bs.view_dev, v.n_pos);
+        uvc_k2_bias_pileup<<<(unsigned)((v.n_pos + pb2 / 2 - 1) / (pb2 / 2)), pb2, smem * pb2 / 128, ctx->stream>>>(v, v.n_pos);
         launches++;
     }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
@@ -1261,7 +1226,6 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
     v.rec_cap = (int32_t)std::min<int64_t>((int64_t)1 << 30, 16 * v.n_reads + (1 << 20));
     UVC_ZERO(rec_buf, int32_t, v.rec_cap)
     UVC_ZERO(rec_cursor, int32_t, 4)
-    { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, sizeof(BatchView), false)); UVC_TRY(backend_upload(ctx, *bs, d_, &v, sizeof(BatchView))); bs->view_dev = (BatchView*)d_; }
     const double t2 = now_ms();
     UVC_TRY(backend_run(ctx, *bs));
     uvcgpu_batch_stats & st = bs->stats;

@@ -891,21 +891,19 @@ UVC_HD void segbias_dense(SegAcc & a, const BatchView & v, const PileRec & P, co
 
 // one read of the position's window, from its compact record (the CUDA kernel stages the records of UVC_STAGE_READS reads per warp at a time);
 // `packed` is k2_fetch_base of this read (role 0 only)
-// defer_mismatch: a base that differs from the position's major symbol is not processed here; the function returns true and the caller handles
-// it later (the CUDA kernel queues such events per warp and processes them with all lanes busy, see uvc_k2_bias_pileup)
-UVC_HD bool k2_read(K2State & s, const BatchView & v, const PileRec & P, uint32_t packed, bool defer_mismatch = false) {
+UVC_HD void k2_read(K2State & s, const BatchView & v, const PileRec & P, uint32_t packed) {
     const int32_t p = s.p;
-    if (P.rend <= p) { return false; }
-    if (s.role == 0 && packed == UVC_K2_NOBASE) { return false; }
+    if (P.rend <= p) { return; }
+    if (s.role == 0 && packed == UVC_K2_NOBASE) { return; }
     bool not_first;
     int32_t prev_rpos = 0, next_rpos = INT32_MAX;
     if (P.bits & UVC_PR_SIMPLE) { not_first = (p > P.pos); }
     else {
         const CxEntry e = v.cx[(int64_t)P.cx_off + (p - P.pos)];
-        if (!(e.flags & 1)) { return false; }
+        if (!(e.flags & 1)) { return; }
         not_first = (e.flags & 2); prev_rpos = e.prev_rpos; next_rpos = e.next_rpos;
     }
-    if ((P.bits & UVC_PR_MASK_ON) && !(P.ibeg <= p && p < P.iend)) { return false; }     // primer_masked
+    if ((P.bits & UVC_PR_MASK_ON) && !(P.ibeg <= p && p < P.iend)) { return; }     // primer_masked
     int32_t dist = 10000;
     if (P.bits & UVC_PR_HAS_GAPS) {       // dist_to_interfering_indel
         const TileInfo & T = *s.T;
@@ -921,7 +919,7 @@ UVC_HD bool k2_read(K2State & s, const BatchView & v, const PileRec & P, uint32_
     }
     const bool nfp = (v.par.tn_is_paired && (0x1 & v.par.primer_flag));
     if (s.role == 1) {
-        if (!not_first) { return false; }
+        if (!not_first) { return; }
         const int32_t w = nnminus(tmin(80, s.noindel), (int32_t)((P.bits >> 24) & 0xfu)) + 1;   // nogap_weight
         s.acc.bqsum += w;
         segbias_dense<true>(s.acc, v, P, s.th, s.baq_p, s.baq2_p, w, p, 100, 0, dist, nfp);
@@ -934,7 +932,6 @@ UVC_HD bool k2_read(K2State & s, const BatchView & v, const PileRec & P, uint32_
             s.acc.bqsum += bq;
             segbias_dense<false>(s.acc, v, P, s.th, s.baq_p, s.baq2_p, bq, p, bm_term, xm_term, dist, nfp);
         } else {
-            if (defer_mismatch) { return true; }
             // a base that differs from the reference (rare): its own symbol's records are updated with fire-and-forget atomics, which do not
             // stall the warp on ~40 dependent read-modify-writes (this thread is still the only writer of these records in this kernel)
             SegAcc one;
@@ -944,20 +941,6 @@ UVC_HD bool k2_read(K2State & s, const BatchView & v, const PileRec & P, uint32_
             segacc_flush<true>(v, s.gp, sym, one);
         }
     }
-    return false;
-}
-
-// A deferred mismatch event of position gp (see k2_read): everything the position contributes is reloaded here, so that ANY lane can process
-// the event. Kept out of line: its registers must not add to the pressure of the pileup loop.
-#if defined(__CUDACC__)
-__device__ __noinline__
-#else
-inline
-#endif
-void k2_mismatch_event(const BatchView & v, int64_t gp, const PileRec & P, uint32_t packed) {
-    K2State t;
-    k2_begin(t, v, gp, 0);
-    k2_read(t, v, P, packed, false);
 }
 
 UVC_HD void k2_end(K2State & s, const BatchView & v) {
