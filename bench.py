@@ -500,7 +500,7 @@ def main():
     n_ctx = max(1, min(args.contexts, len(subs)))
     ctxs = [ctx0] + [make_ctx(max(1, host_threads // n_ctx + 1)) for _ in range(n_ctx - 1)]
     ctx0.lib.uvcgpu_set_host_threads(ctx0.handle, max(1, host_threads // n_ctx + 1))
-    totals = {"h2d": 0, "d2h": 0, "vcf": 0, "rec": 0, "launch": 0, "prep_ms": 0.0, "submit_s": 0.0, "wait_s": 0.0, "score_s": 0.0, "text_s": 0.0, "release_s": 0.0}
+    totals = {"h2d": 0, "d2h": 0, "vcf": 0, "rec": 0, "launch": 0, "prep_ms": 0.0, "sync_ms": 0.0, "stage_call_ms": 0.0, "submit_s": 0.0, "wait_s": 0.0, "score_s": 0.0, "text_s": 0.0, "release_s": 0.0}
     last_text = {}
 
     def e2e_steps(n_steps, keep_last=False):
@@ -540,6 +540,8 @@ def main():
                         acc["rec"] += int(st.n_vcf_records)
                         acc["launch"] += int(st.gpu_launches)
                         acc["prep_ms"] += st.host_prep_ms
+                        acc["sync_ms"] += st.reserved[0]
+                        acc["stage_call_ms"] += st.reserved[1]
                         for key, val in zip(("submit_s", "wait_s", "score_s", "text_s", "release_s"), st.phase_s):
                             acc[key] += val
             except Exception as e:  # noqa: BLE001
@@ -661,6 +663,8 @@ def main():
                     "vcf_body_sha1_last_step": shard_sha, "vcf_concatenation": concat,
                     "scope": "C ABI from decoded host SoA buffers: host staging + H2D + kernels + D2H + VCF text; excludes BAM decode (see `decode`) and BGZF output (see `pipeline`)",
                     "host_prep_ms_per_step_summed_over_contexts": totals["prep_ms"] / args.steps,
+                    "submit_wait_for_batch_sizes_ms_per_step_summed_over_contexts": totals["sync_ms"] / args.steps,
+                    "submit_staging_part_ms_per_step_summed_over_contexts": totals["stage_call_ms"] / args.steps,
                     "call_ms_per_step_summed_over_contexts": {k[:-2]: totals[k] * 1e3 / args.steps for k in ("submit_s", "wait_s", "score_s", "text_s", "release_s")},
                     "wall_ms_per_step": wall_s * 1e3 / args.steps,
                     "staging_blocks_not_yet_page_locked": {"at_start": backlog0, "at_end": backlog1},

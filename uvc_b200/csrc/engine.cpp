@@ -87,6 +87,9 @@ struct uvcgpu_ctx {
     std::map<uvcgpu_ticket, std::unique_ptr<BatchState>> batches;
     uvcgpu_ticket next_ticket = 1;
     std::vector<int32_t> slip_tab;
+    // compute-side copies of the per-context constant tables (uploaded once: a per-batch upload from pageable memory would make every submit
+    // wait for the stream to drain)
+    double *c_phred2prob = nullptr; int32_t *c_pf_tab = nullptr; int32_t *c_slip_tab = nullptr;
     int host_threads = 0;
 #if UVC_CUDA
     cudaStream_t stream = nullptr;        // submit: staging copies and the pileup kernels of every batch, in submission order
@@ -1062,10 +1065,36 @@ int uvcgpu_create(uvcgpu_ctx **out, int device, const uvcgpu_params *params) {
             }
         }
     }
+    std::vector<double> p2p(128);
+    for (int q = 0; q < 128; q++) { p2p[q] = pow(10, -((float)q) / 10); }   // phred2prob (main_conversion.hpp:885-888): float exponent, double pow
+    std::vector<int32_t> pf(256);
+    for (int k = 0; k < 2; k++) {
+        const int32_t t = (k ? params->bias_thres_PFBQ2 : params->bias_thres_PFBQ1);
+        for (int bq = 0; bq < 128; bq++) { pf[k * 128 + bq] = ((bq < t) ? (100 * (bq * bq) / (t * t)) : 100); }
+    }
 #if UVC_CUDA
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return UVCGPU_ECUDA; }
-    if (cudaStreamCreateWithFlags(&ctx->post_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return UVCGPU_ECUDA; }
-    if (cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->post_stream); delete ctx; return UVCGPU_ECUDA; }
+    {
+        bool ok = (cudaMalloc((void**)&ctx->c_phred2prob, p2p.size() * sizeof(double)) == cudaSuccess) && (cudaMalloc((void**)&ctx->c_pf_tab, pf.size() * sizeof(int32_t)) == cudaSuccess)
+            && (cudaMalloc((void**)&ctx->c_slip_tab, ctx->slip_tab.size() * sizeof(int32_t)) == cudaSuccess);
+        ok = ok && (cudaMemcpy(ctx->c_phred2prob, p2p.data(), p2p.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess)
+            && (cudaMemcpy(ctx->c_pf_tab, pf.data(), pf.size() * sizeof(int32_t), cudaMemcpyHostToDevice) == cudaSuccess)
+            && (cudaMemcpy(ctx->c_slip_tab, ctx->slip_tab.data(), ctx->slip_tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice) == cudaSuccess);
+        if (!ok) { cudaGetLastError(); delete ctx; return UVCGPU_ECUDA; }
+    }
+#else
+    ctx->c_phred2prob = (double*)malloc(p2p.size() * sizeof(double)); memcpy(ctx->c_phred2prob, p2p.data(), p2p.size() * sizeof(double));
+    ctx->c_pf_tab = (int32_t*)malloc(pf.size() * sizeof(int32_t)); memcpy(ctx->c_pf_tab, pf.data(), pf.size() * sizeof(int32_t));
+    ctx->c_slip_tab = (int32_t*)malloc(ctx->slip_tab.size() * sizeof(int32_t)); memcpy(ctx->c_slip_tab, ctx->slip_tab.data(), ctx->slip_tab.size() * sizeof(int32_t));
+#endif
+#if UVC_CUDA
+    // The host waits for the short staging and scoring kernels (sizes of the batch, kept records), never for the long pileup kernels: the
+    // streams of the short kernels get the higher priority, so that their blocks are scheduled ahead of the pending blocks of pileup kernels
+    // of other contexts on the same GPU instead of behind them.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete ctx; return UVCGPU_ECUDA; }
+    if (cudaStreamCreateWithPriority(&ctx->post_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return UVCGPU_ECUDA; }
+    if (cudaStreamCreateWithPriority(&ctx->prep_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->post_stream); delete ctx; return UVCGPU_ECUDA; }
     ctx->active = ctx->stream;
     {   // keep freed device blocks in the stream-ordered pool instead of returning them to the driver after every batch
         cudaMemPool_t pool;
@@ -1083,6 +1112,7 @@ void uvcgpu_destroy(uvcgpu_ctx *ctx) {
 #if UVC_CUDA
     cudaDeviceSynchronize();
     for (auto & kv : ctx->d_contigs) { cudaFree(kv.second); }
+    cudaFree(ctx->c_phred2prob); cudaFree(ctx->c_pf_tab); cudaFree(ctx->c_slip_tab);
     if (ctx->post_stream) { cudaStreamDestroy(ctx->post_stream); }
     if (ctx->prep_stream) { cudaStreamDestroy(ctx->prep_stream); }
     if (ctx->stream) { cudaStreamDestroy(ctx->stream); }
@@ -1180,17 +1210,7 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
 #define UVC_UP(field, type, vec) { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (vec).size() * sizeof(type), false)); \
         UVC_TRY(backend_upload(ctx, *bs, d_, (vec).data(), (vec).size() * sizeof(type))); v.field = (type*)d_; }
 #define UVC_ZERO(field, type, count) { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)(count) * sizeof(type), true)); v.field = (type*)d_; }
-    {
-        std::vector<double> tab(128);
-        for (int q = 0; q < 128; q++) { tab[q] = pow(10, -((float)q) / 10); }   // phred2prob (main_conversion.hpp:885-888): float exponent, double pow
-        UVC_UP(phred2prob_tab, double, tab)
-        std::vector<int32_t> pf(256);
-        for (int k = 0; k < 2; k++) {
-            const int32_t t = (k ? ctx->par.bias_thres_PFBQ2 : ctx->par.bias_thres_PFBQ1);
-            for (int bq = 0; bq < 128; bq++) { pf[k * 128 + bq] = ((bq < t) ? (100 * (bq * bq) / (t * t)) : 100); }
-        }
-        UVC_UP(pf_tab, int32_t, pf)
-    }
+    v.phred2prob_tab = ctx->c_phred2prob; v.pf_tab = ctx->c_pf_tab; v.slip_tab = ctx->c_slip_tab;
     // stages P0 and P1 on the device: read filter, family segmentation, reference context (prep_device.inc); fills the view's input arrays
 #if UVC_CUDA
     ctx->active = ctx->prep_stream;

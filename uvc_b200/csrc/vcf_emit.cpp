@@ -2,6 +2,7 @@
 // tags in FORMAT_VEC order, Number=R tags as "ref,alt", separator pseudo-tags printed as their own name, SSCS-only tags skipped
 // unless enable_tier2_consensus_format_tags) and append_vcf_record (main.hpp:6027-6272).
 #include "vcf_emit.h"
+#include <type_traits>
 
 #include <algorithm>
 #include <set>
@@ -39,17 +40,32 @@ std::string event_string(const HostBatch & hb, const StageVec<IndelEvent> & ev, 
     return out;
 }
 
+// decimal text of a number appended in place: integers by hand (the records are ~600 integers each; std::to_string allocates a temporary
+// string per number), everything else as std::to_string prints it
+template <class T> inline typename std::enable_if<std::is_integral<T>::value, void>::type append_num(std::string & s, T v) {
+    char buf[24];
+    char *e = buf + sizeof(buf), *p = e;
+    typedef typename std::make_unsigned<T>::type U;
+    U u = (U)v;
+    const bool neg = (std::is_signed<T>::value && v < 0);
+    if (neg) { u = (U)0 - u; }
+    do { *--p = (char)('0' + (int)(u % 10)); u /= 10; } while (u);
+    if (neg) { *--p = '-'; }
+    s.append(p, (size_t)(e - p));
+}
+template <class T> inline typename std::enable_if<!std::is_integral<T>::value, void>::type append_num(std::string & s, T v) { s += std::to_string(v); }
+
 struct Out {
     std::string & s;
     bool first = true;
     explicit Out(std::string & str) : s(str) {}
     void sepc() { if (!first) { s += ":"; } first = false; }
     void tag(const char *name) { sepc(); s += name; }
-    template <class T> void one(T v) { sepc(); s += std::to_string(v); }
-    template <class T> void pair(T a, T b) { sepc(); s += std::to_string(a); s += ","; s += std::to_string(b); }
-    template <class T> void arr(const T *v, int n) { sepc(); for (int i = 0; i < n; i++) { if (i) { s += ","; } s += std::to_string(v[i]); } }
+    template <class T> void one(T v) { sepc(); append_num(s, v); }
+    template <class T> void pair(T a, T b) { sepc(); append_num(s, a); s += ','; append_num(s, b); }
+    template <class T> void arr(const T *v, int n) { sepc(); for (int i = 0; i < n; i++) { if (i) { s += ','; } append_num(s, v[i]); } }
     void str(const std::string & v) { sepc(); if (v.empty()) { s += "."; } s += v; }
-    void ints_or_dot(const std::vector<int32_t> & v) { sepc(); if (v.empty()) { s += "."; } for (size_t i = 0; i < v.size(); i++) { if (i) { s += ","; } s += std::to_string(v[i]); } }
+    void ints_or_dot(const std::vector<int32_t> & v) { sepc(); if (v.empty()) { s += '.'; } for (size_t i = 0; i < v.size(); i++) { if (i) { s += ','; } append_num(s, v[i]); } }
     void strs_or_dot(const std::vector<std::string> & v) { sepc(); if (v.empty()) { s += "."; } for (size_t i = 0; i < v.size(); i++) { if (i) { s += ","; } s += v[i]; } }
 };
 
@@ -231,8 +247,8 @@ std::string uvc_tile_vcf_text(const HostBatch & hb, int32_t tile_index, const uv
                         const int32_t b = g.bdepth[k], c = g.cdepth[k], c12 = g.cdep12[k], q = g.refQ[k];
                         auto diff = [](int32_t cur, int32_t prev) { const int32_t lo = std::min(cur, prev), hi = std::max(cur, prev); if (lo * 130 >= hi * 100) { return false; } if (lo + 3 >= hi) { return false; } return true; };
                         if ((init_refQ == prev_refQ) || (abs(q - prev_refQ) > 10) || diff(b, prev_b) || diff(c, prev_c) || diff(c12, prev_c12)) {
-                            body += std::to_string(rp2 + ((0 == stype) ? 1 : 0)) + "," + std::to_string(1 + stype) + ",.," + std::to_string(b) + "," + std::to_string(c) + ","
-                                  + std::to_string(c12) + "," + std::to_string(q) + ",.,";
+                            append_num(body, rp2 + ((0 == stype) ? 1 : 0)); body += ','; append_num(body, 1 + stype); body += ",.,"; append_num(body, b); body += ',';
+                            append_num(body, c); body += ','; append_num(body, c12); body += ','; append_num(body, q); body += ",.,";
                             prev_b = b; prev_c = c; prev_c12 = c12; prev_refQ = q;
                         }
                     }
