@@ -180,3 +180,18 @@ def test_cuda_cli_matches_reference(synth_cli, synth_umi, tmp_path):
     bed = tmp_path / "r.bed"
     bed.write_text("chrU\t1200\t1500\nchrU\t2000\t2300\n")
     _compare(GPU, synth_umi, tmp_path / "c", ["-t", "2", "-R", str(bed)])
+
+
+@pytest.mark.gpu
+def test_gpu_cli_two_gpus_equal_one(synth_cli, tmp_path):
+    """Tiles sharded over the lanes of two GPUs, VCF text concatenated in tile order: byte-identical to the one-GPU run."""
+    import ctypes
+    from uvc_b200 import capi
+    if capi.load_gpu().uvcgpu_device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    outs = []
+    for n in (1, 2):
+        out = str(tmp_path / ("g%d.vcf.gz" % n))
+        _run(GPU, synth_cli["bam"], synth_cli["fasta"], out, ["-t", "4", "--mem-per-thread", "8", "--gpus", str(n), "--gpu-batch-positions", "3000"])
+        outs.append(_body(out))
+    assert len(outs[0]) > 1 and outs[0] == outs[1]
