@@ -365,9 +365,9 @@ __device__ __forceinline__ void uvc_gather_bases_p(const BatchView & v, const Pi
     }
 }
 
-// K2: both roles of a position sit in different warps of the same block: block = 64 positions x 2 roles.
+// K2: one thread per position (both dense symbols, see kernels_core.cuh: K2Merged).
 // Each warp stages the compact records (PileRec, 64 bytes, written by K0) of UVC_STAGE_READS reads of its union window in shared memory: ONE
-// elected lane issues one bulk asynchronous copy per chunk (cp.async.bulk, completion on the warp's mbarrier), one chunk ahead; role 0
+// elected lane issues one bulk asynchronous copy per chunk (cp.async.bulk, completion on the warp's mbarrier), one chunk ahead; the warp
 // then gathers the (base, quality) byte pairs of the whole chunk with independent loads (memory-level parallelism instead of one dependent
 // load pair per read), and the per-read work runs entirely from shared memory.
 struct __align__(16) K2StageP {
@@ -376,24 +376,21 @@ struct __align__(16) K2StageP {
     uint64_t bar[2];
 };
 #ifndef UVC_K2_MINBLOCKS
-#define UVC_K2_MINBLOCKS 4    // 128 registers: four blocks per SM together with 24-read staging chunks
+#define UVC_K2_MINBLOCKS 4
 #endif
 __global__ void __launch_bounds__(128, UVC_K2_MINBLOCKS) uvc_k2_bias_pileup(const BatchView v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int half = (int)(blockDim.x >> 1);                    // the block = `half` positions x 2 roles (64 or 128 threads)
-    const int64_t gp = (i / blockDim.x) * half + (i % half);
+    const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     K2StageP & S = ((K2StageP*)uvc_smem)[warp];
-    const bool active = (gp < v.n_pos);
-    const int role = (int)((i % blockDim.x) / half);
+    const bool active = (gp < n);
     if (0 == lane) { uvc_mbar_init(&S.bar[0], 1); uvc_mbar_init(&S.bar[1], 1); uvc_mbar_fence_init(); }
     __syncwarp();
     uvc::Win w;
     uvc_warp_window(v, gp, active, w);
-    uvc::K2State st;
+    uvc::K2Merged st;
     st.p = 0;
-    if (active) { uvc::k2_begin(st, v, gp, role); }
+    if (active) { uvc::k2m_begin(st, v, gp); }
     const int64_t c0 = w.ulo;
     auto issue = [&](int64_t cb, int buf) {
         if (cb < w.uhi && 0 == lane) {
@@ -405,22 +402,20 @@ __global__ void __launch_bounds__(128, UVC_K2_MINBLOCKS) uvc_k2_bias_pileup(cons
     issue(c0, 0);
     unsigned phase0 = 0, phase1 = 0;
     int buf = 0;
+    // the lane's own window relative to the chunk base, as 32-bit numbers
     for (int64_t cb = c0; cb < w.uhi; cb += UVC_STAGE_READS, buf ^= 1) {
         const int nc = (int)(w.uhi - cb < UVC_STAGE_READS ? w.uhi - cb : UVC_STAGE_READS);
         issue(cb + UVC_STAGE_READS, buf ^ 1);          // (every lane finished with that buffer before the __syncwarp that ended the previous iteration)
         if (buf) { uvc_mbar_wait(&S.bar[1], phase1); phase1 ^= 1u; } else { uvc_mbar_wait(&S.bar[0], phase0); phase0 ^= 1u; }
         const PileRec *sP = S.P[buf];
-        if (role == 0) { uvc_gather_bases_p(v, sP, S.bq, nc, cb, w, st.p, active, lane); }
+        uvc_gather_bases_p(v, sP, S.bq, nc, cb, w, st.p, active, lane);
         if (active) {
-            for (int k = 0; k < nc; k++) {
-                const int64_t ri = cb + k;
-                if (ri < w.lo || ri >= w.hi) { continue; }
-                uvc::k2_read(st, v, sP[k], (uint32_t)S.bq[k][lane]);
-            }
+            const int k_lo = (int)(w.lo - cb > 0 ? (w.lo - cb < nc ? w.lo - cb : nc) : 0), k_hi = (int)(w.hi - cb < nc ? (w.hi - cb > 0 ? w.hi - cb : 0) : nc);
+            for (int k = k_lo; k < k_hi; k++) { uvc::k2m_read(st, v, sP[k], (uint32_t)S.bq[k][lane]); }
         }
         __syncwarp();
     }
-    if (active) { uvc::k2_end(st, v); }
+    if (active) { uvc::k2m_flush(st, v); }
 }
 // staging slot of K1: full per-read records (ReadRec + ReadDerived), double-buffered with cp.async
 struct __align__(16) K2Stage {
@@ -759,8 +754,7 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
         static_assert(sizeof(K2StageP) % 16 == 0 && sizeof(PileRec) == 64, "per-warp staging slots keep 16-byte alignment");
         const size_t smem = 4 * sizeof(K2StageP);
         UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k2_bias_pileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int pb2 = (pb < 64 ? 64 : pb);     // two roles: at least one warp each
-        uvc_k2_bias_pileup<<<(unsigned)((v.n_pos + pb2 / 2 - 1) / (pb2 / 2)), pb2, smem * pb2 / 128, ctx->stream>>>(v, v.n_pos);
+        uvc_k2_bias_pileup<<<(unsigned)((v.n_pos + pb - 1) / pb), pb, smem * pb / 128, ctx->stream>>>(v, v.n_pos);
         launches++;
     }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
@@ -878,7 +872,7 @@ static int backend_run(uvcgpu_ctx *, BatchState & bs) {
     for (int64_t i = 0; i < v.n_reads; i++) { uvc::k0_read(v, i); }
     uvc::Win w;
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k1_position(v, i, w); }
-    for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k2_position(v, i, 0, w); uvc::k2_position(v, i, 1, w); }
+    for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k2m_position(v, i, w); }
     for (int64_t i = 0; i < v.n_ev; i++) { uvc::k2e_event(v, i); }
     for (int64_t i = 0; i < v.n_fcol; i++) { uvc::kf_fold_bits(v, i, uvc::kf_fragment_column(v, i)); }
     for (int64_t i = 0; i < v.n_frags; i++) { uvc::k3a_fragment(v, i); }

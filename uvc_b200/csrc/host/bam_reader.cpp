@@ -602,6 +602,30 @@ int uvchost_bam_seek_region(uvchost_bam *b, int32_t tid, int64_t beg) {
     return (b->in.seek((int64_t)l[w]) != 0 ? -1 : 0);
 }
 
+int64_t uvchost_bam_estimate_reads(const uvchost_bam *b, int32_t tid, int64_t beg, int64_t end) {
+    if (b->index_status != 1 || tid < 0 || (size_t)tid >= b->lidx.size() || beg >= end) { return 0; }
+    const std::vector<uint64_t> & l = b->lidx[tid];
+    if (l.empty()) { return 0; }
+    if (beg < 0) { beg = 0; }
+    size_t w0 = (size_t)(beg >> 14), w1 = (size_t)((end - 1) >> 14) + 1;
+    if (w0 >= l.size()) { return 0; }
+    // compressed bytes between the first record of window w0 and the first record of the window after w1 (or of the last window)
+    size_t a = w0, z = (w1 < l.size() ? w1 : l.size() - 1);
+    while (a < l.size() && 0 == l[a]) { a++; }
+    while (z > a && 0 == l[z]) { z--; }
+    if (a >= l.size() || z <= a) {
+        // a single window: fall back on the file's average density over the contig's windows
+        a = 0; z = l.size() - 1;
+        while (a < l.size() && 0 == l[a]) { a++; }
+        while (z > a && 0 == l[z]) { z--; }
+        if (a >= l.size() || z <= a) { return 0; }
+    }
+    const double bytes = (double)((l[z] >> 16) - (l[a] >> 16));
+    const double positions = (double)(z - a) * 16384.0;
+    const double density = bytes / positions;                     // compressed bytes per reference position
+    return (int64_t)(density * (double)(end - beg + 300) / 50.0) + 1;   // ~50 compressed bytes per record: errs on the high side
+}
+
 int64_t uvchost_bam_count(uvchost_bam *b, int32_t tid, int64_t beg, int64_t end) {
     if (uvchost_bam_seek_region(b, tid, beg) != 0) { return 0; }
     int64_t n = 0;

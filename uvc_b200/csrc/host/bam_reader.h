@@ -69,6 +69,9 @@ int uvchost_bam_next_core(uvchost_bam *b, uvchost_core *c);
 /* Positions the sequential reader at the first record that can overlap [beg, end) of tid (sam_itr_queryi); records are then pulled with
  * uvchost_bam_next_core and filtered by the caller. Returns 0, or 1 if the index has no data for the region. */
 int uvchost_bam_seek_region(uvchost_bam *b, int32_t tid, int64_t beg);
+/* Rough number of records that overlap [beg, end), from the linear index alone (compressed bytes per reference position of the surrounding
+ * 16 kbp windows): no record is read. Used to size GPU batches before (or without) counting; errs on the high side. */
+int64_t uvchost_bam_estimate_reads(const uvchost_bam *b, int32_t tid, int64_t beg, int64_t end);
 /* Number of records of tid that overlap [beg, end) (the count SamIter::iternext takes per BED line, grouping.cpp:178-195). */
 int64_t uvchost_bam_count(uvchost_bam *b, int32_t tid, int64_t beg, int64_t end);
 

@@ -169,6 +169,17 @@ uvchost_tiler *uvchost_tiler_open(const char *bam_path, const char *bed_fname, c
     return t;
 }
 
+int64_t uvchost_tiler_emit_given(uvchost_tiler *t) {
+    if (NULL == t || NULL == t->bam || t->given.empty() || NULL == t->cb) { return 0; }
+    for (const uvchost_bedline & l : t->given) {
+        uvchost_bedline lc = l;
+        if (lc.n_reads <= 0) { lc.n_reads = uvchost_bam_estimate_reads(t->bam, l.tid, l.beg_pos, l.end_pos); }
+        t->cb(&lc, t->cb_user);
+    }
+    t->cb = NULL;      // the iterations that follow (if the caller wants them) only report
+    return (int64_t)t->given.size();
+}
+
 int64_t uvchost_tiler_next(uvchost_tiler *t, const uvchost_bedline **lines, int64_t *n_lines) {
     t->out.clear();
     *lines = NULL; *n_lines = 0;

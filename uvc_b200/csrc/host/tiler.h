@@ -39,6 +39,12 @@ typedef void (*uvchost_tile_cb)(const uvchost_bedline *line, void *user);
 void uvchost_tiler_set_callback(uvchost_tiler *t, uvchost_tile_cb cb, void *user);
 void uvchost_tiler_set_scan_threads(uvchost_tiler *t, int32_t scan_threads);
 
+/* Given intervals (-R / --targets): the tiles are the intervals themselves, known before any record is read. Hands ALL of them to the callback
+ * at once, with read counts estimated from the index, and disables the callback; the tier-1 iterations (uvchost_tiler_next), which need the
+ * exact per-interval read counts of a whole-file pass and only decide how --bed-out-fname groups the tiles, can then run while the GPU works -
+ * or not at all. Returns the number of tiles handed out (0: no given intervals). */
+int64_t uvchost_tiler_emit_given(uvchost_tiler *t);
+
 /* One tier-1 iteration. Returns the iteration's total number of reads (the reference's iternext return value) or a negative error;
  * *lines / *n_lines point into the tiler and stay valid until the next call. */
 int64_t uvchost_tiler_next(uvchost_tiler *t, const uvchost_bedline **lines, int64_t *n_lines);

@@ -235,19 +235,22 @@ void tiler_thread(Shared *sh, int scan_threads) {
     uvchost_tiler_set_callback(t, BatchPacker::on_tile, &packer);
     uvchost_tiler_set_scan_threads(t, scan_threads);
     int64_t iter = 0;
-    for (;;) {
+    // -R / --targets: the tiles are known up front; the lanes get them all at once. The reference's tier-1 iterations (a pass over the whole BAM
+    // that counts the reads of every interval) only decide how --bed-out-fname groups the tiles: they run afterwards, and only if asked for.
+    const bool eager = (uvchost_tiler_emit_given(t) > 0);
+    if (eager) { packer.flush(); sh->batches.close(); sh->t_tiler_done = now_us(); }
+    for (; !eager || bed_out.is_open();) {
         const uvchost_bedline *lines = NULL; int64_t n = 0;
         const int64_t nreads = uvchost_tiler_next(t, &lines, &n);
         if (nreads < 0) { sh->fail(std::string("tiler: ") + uvchost_tiler_error(t)); break; }
         if (!(nreads > 0 || n > 0)) { break; }     // main.cpp:1339
-        packer.flush();
+        if (!eager) { packer.flush(); }
         if (bed_out.is_open()) { bed_out << bed_out_text(std::vector<uvchost_bedline>(lines, lines + n), sh->contigs, o.threads, iter); }
         iter++;
         if (sh->failed.load()) { break; }
     }
     uvchost_tiler_close(t);
-    sh->batches.close();
-    sh->t_tiler_done = now_us();
+    if (!eager) { sh->batches.close(); sh->t_tiler_done = now_us(); }
 }
 
 struct Lane {

@@ -766,40 +766,8 @@ UVC_HD int32_t nogap_weight(const BatchView & v, int64_t gp, const ReadDerived &
     return nnminus(tmin(80, noindel), D.micro_nogap_penal) + 1;
 }
 
-// ------------------------------------------------------------------------------------------------ K2: two threads per position
-// Walk #2 (updateByAln<SUM, bias> over aligned bases, main.hpp:1890-2008) gathered per position. role 0 owns the six base symbols,
-// role 1 owns LINK_M. The symbol that matches the reference (role 0) / LINK_M (role 1) is accumulated in registers.
-struct K2State {
-    const TileInfo *T;
-    int64_t gp;
-    int32_t p;
-    int role, major;
-    int32_t baq_p, baq2_p;          // baq[p], baq2[p]
-    int32_t noindel;                // min(indelphred[p - 1], indelphred[p]) of nogap_weight
-    uvcgpu_thres_set th;
-    SegAcc acc;
-};
-
-UVC_HD void k2_begin(K2State & s, const BatchView & v, int64_t gp, int role) {
-    const TileInfo & T = v.tiles[v.pos_tile[gp]];
-    s.T = &T; s.gp = gp; s.role = role;
-    s.p = (int32_t)(gp - T.pos_off) + T.ext_beg;
-    s.baq_p = v.baq[gp]; s.baq2_p = v.baq2[gp];
-    s.noindel = (role == 1 ? tmin(v.rtr[gp > 0 ? gp - 1 : 0].indelphred, v.rtr[gp].indelphred) : 0);
-    s.th = v.thres[gp];
-    s.major = (role == 0 ? (int)v.refsym[gp] : UVC_LINK_M);
-    segacc_zero(s.acc);
-}
-
-// What role 0 needs from a read's own bytes at p: (base symbol << 8) | raw-plus-fix-up quality, or UVC_K2_NOBASE when the read shows no aligned
-// base at p (or `mine` is false: the read lies outside this lane's own window). The two byte loads are unconditional (clamped index) so that
-// the CUDA kernel can issue them for a whole chunk of reads back to back instead of one dependent load pair per read.
-UVC_HD uint32_t k2_fetch_base(const K2State & s, const BatchView & v, const ReadRec & R, bool mine) {
-    const int32_t qpos = base_index(v, R, s.p, mine);
-    const int32_t qc = tmax(qpos, 0);
-    return pack_base(v.seq[R.seq_off + (uint32_t)(qc >> 1)], v.qual[R.qual_off + (uint32_t)qc], qpos);
-}
-
+// ------------------------------------------------------------------------------------------------ K2: bias pileup of the dense symbols
+// Walk #2 (updateByAln<SUM, bias> over aligned bases, main.hpp:1890-2008) gathered per position.
 // dealwith_segbias<isGap> (main.hpp:1360-1595) for an aligned base (isGap = false) or the gap-free junction before it (isGap = true), from the
 // compact record of the read (batch.h: PileRec): same arithmetic as segbias() with is_ins_op = false and indel_len = 0, with the per-read
 // conditions taken from P.bits.
@@ -889,12 +857,76 @@ UVC_HD void segbias_dense(SegAcc & a, const BatchView & v, const PileRec & P, co
     }
 }
 
-// one read of the position's window, from its compact record (the CUDA kernel stages the records of UVC_STAGE_READS reads per warp at a time);
-// `packed` is k2_fetch_base of this read (role 0 only)
-UVC_HD void k2_read(K2State & s, const BatchView & v, const PileRec & P, uint32_t packed) {
+// ------------------------------------------------------------------------------------------------ K2, merged roles: one thread per position
+// Both symbols that nearly every read votes for at a position - the reference base and LINK_M - are handled by ONE thread: what
+// dealwith_segbias derives from (read, position) alone (distances to the read and fragment ends, BAQ spans, threshold comparisons, strand and
+// orientation classes) is computed once and feeds both updates. The 23 pure event counters of the two symbols share registers: the base
+// symbol counts in the low and LINK_M in the high 16 bits of one word, so one predicated add updates both; the remaining sums are 32-bit per
+// symbol. Every 60 000 visited reads the accumulators are flushed (no half-word can overflow before that).
+#define UVC_K2M_FLUSH_EVERY 60000
+struct K2Merged {
+    const TileInfo *T;
+    int64_t gp;
+    int32_t p, major;
+    int32_t baq_p, baq2_p, noindel;
+    int32_t nvis;
+    uvcgpu_thres_set th;
+    // packed counters: base symbol | LINK_M << 16
+    uint32_t cP1, cP2, cP3, cNC, cDPff, cDPfr, cDPrf, cDPrr, cLP1, cLP2, cRP1, cRP2, cLB1, cLB2, cRB1, cRB2, cLI1, cLI2, cRI1, cRI2, cRIf, cLIr, cBQ2;
+    // sums, [0] = base symbol, [1] = LINK_M (separate scalars: indexing would force the struct into local memory)
+    int32_t MQs0, MQs1, LPL0, LPL1, RPL0, RPL1, PF10, PF11, PF20, PF21, XM2, BM2, LBL0, LBL1, RBL0, RBL1, LIT0, LIT1, RIT0, RIT1;
+    int32_t q1f0, q1f1, q1r0, q1r1, q2f0, q2f1, q2r0, q2r1, bqs0, bqs1;
+};
+UVC_HD void k2m_zero(K2Merged & s) {
+    s.nvis = 0;
+    s.cP1 = s.cP2 = s.cP3 = s.cNC = s.cDPff = s.cDPfr = s.cDPrf = s.cDPrr = s.cLP1 = s.cLP2 = s.cRP1 = s.cRP2 = 0;
+    s.cLB1 = s.cLB2 = s.cRB1 = s.cRB2 = s.cLI1 = s.cLI2 = s.cRI1 = s.cRI2 = s.cRIf = s.cLIr = s.cBQ2 = 0;
+    s.MQs0 = s.MQs1 = s.LPL0 = s.LPL1 = s.RPL0 = s.RPL1 = s.PF10 = s.PF11 = s.PF20 = s.PF21 = s.XM2 = s.BM2 = 0;
+    s.LBL0 = s.LBL1 = s.RBL0 = s.RBL1 = s.LIT0 = s.LIT1 = s.RIT0 = s.RIT1 = 0;
+    s.q1f0 = s.q1f1 = s.q1r0 = s.q1r1 = s.q2f0 = s.q2f1 = s.q2r0 = s.q2r1 = s.bqs0 = s.bqs1 = 0;
+}
+UVC_HD void k2m_begin(K2Merged & s, const BatchView & v, int64_t gp) {
+    const TileInfo & T = v.tiles[v.pos_tile[gp]];
+    s.T = &T; s.gp = gp;
+    s.p = (int32_t)(gp - T.pos_off) + T.ext_beg;
+    s.baq_p = v.baq[gp]; s.baq2_p = v.baq2[gp];
+    s.noindel = tmin(v.rtr[gp > 0 ? gp - 1 : 0].indelphred, v.rtr[gp].indelphred);
+    s.th = v.thres[gp];
+    s.major = (int)v.refsym[gp];
+    k2m_zero(s);
+}
+// adds the accumulators of both symbols to the position's records (atomic adds: rare events of other kernels' making and this thread's own
+// earlier reductions may be in flight to the same words) and clears them
+UVC_HD void k2m_flush(K2Merged & s, const BatchView & v) {
+    for (int r = 0; r < 2; r++) {
+        const int sym = (r ? UVC_LINK_M : s.major);
+        if (sym >= UVC_NSYM) { continue; }
+        const int sh = (r ? 16 : 0);
+        SegAcc a;
+        segacc_zero(a);
+        #define UVC_H(x) ((int32_t)(((x) >> sh) & 0xffffu))
+        a.s.aP1 = UVC_H(s.cP1); a.s.aP2 = UVC_H(s.cP2); a.s.aP3 = UVC_H(s.cP3); a.s.aNC = UVC_H(s.cNC);
+        a.s.aDPff = UVC_H(s.cDPff); a.s.aDPfr = UVC_H(s.cDPfr); a.s.aDPrf = UVC_H(s.cDPrf); a.s.aDPrr = UVC_H(s.cDPrr);
+        a.s.aLP1 = UVC_H(s.cLP1); a.s.aLP2 = UVC_H(s.cLP2); a.s.aRP1 = UVC_H(s.cRP1); a.s.aRP2 = UVC_H(s.cRP2);
+        a.s.aLB1 = UVC_H(s.cLB1); a.s.aLB2 = UVC_H(s.cLB2); a.s.aRB1 = UVC_H(s.cRB1); a.s.aRB2 = UVC_H(s.cRB2);
+        a.s.aLI1 = UVC_H(s.cLI1); a.s.aLI2 = UVC_H(s.cLI2); a.s.aRI1 = UVC_H(s.cRI1); a.s.aRI2 = UVC_H(s.cRI2);
+        a.s.aRIf = UVC_H(s.cRIf); a.s.aLIr = UVC_H(s.cLIr); a.s.aBQ2 = UVC_H(s.cBQ2);
+        #undef UVC_H
+        a.s.aMQs = (r ? s.MQs1 : s.MQs0); a.s.aLPL = (r ? s.LPL1 : s.LPL0); a.s.aRPL = (r ? s.RPL1 : s.RPL0);
+        a.s.aPF1 = (r ? s.PF11 : s.PF10); a.s.aPF2 = (r ? s.PF21 : s.PF20);
+        a.s.a2XM2 = (r ? 0 : s.XM2); a.s.a2BM2 = (r ? 0 : s.BM2);
+        a.s.aLBL = (r ? s.LBL1 : s.LBL0); a.s.aRBL = (r ? s.RBL1 : s.RBL0); a.s.aLIT = (r ? s.LIT1 : s.LIT0); a.s.aRIT = (r ? s.RIT1 : s.RIT0);
+        a.a1BQf = (r ? s.q1f1 : s.q1f0); a.a1BQr = (r ? s.q1r1 : s.q1r0); a.a2BQf = (r ? s.q2f1 : s.q2f0); a.a2BQr = (r ? s.q2r1 : s.q2r0);
+        a.bqsum = (r ? s.bqs1 : s.bqs0);
+        segacc_flush<true>(v, s.gp, sym, a);
+    }
+    k2m_zero(s);
+}
+// one read of the position's window: `packed` = (symbol << 8) | quality of its aligned base at p, or UVC_K2_NOBASE
+UVC_HD void k2m_read(K2Merged & s, const BatchView & v, const PileRec & P, uint32_t packed) {
+    const uvcgpu_params & par = v.par;
     const int32_t p = s.p;
     if (P.rend <= p) { return; }
-    if (s.role == 0 && packed == UVC_K2_NOBASE) { return; }
     bool not_first;
     int32_t prev_rpos = 0, next_rpos = INT32_MAX;
     if (P.bits & UVC_PR_SIMPLE) { not_first = (p > P.pos); }
@@ -907,7 +939,7 @@ UVC_HD void k2_read(K2State & s, const BatchView & v, const PileRec & P, uint32_
     int32_t dist = 10000;
     if (P.bits & UVC_PR_HAS_GAPS) {       // dist_to_interfering_indel
         const TileInfo & T = *s.T;
-        const int32_t adj = v.par.indel_adj_tracklen_dist;
+        const int32_t adj = par.indel_adj_tracklen_dist;
         const int32_t npos = T.ext_end - T.ext_beg;
         const uvcgpu_rtr *rtr = v.rtr + T.pos_off;
         const int32_t ridx = p - T.ext_beg;
@@ -917,44 +949,134 @@ UVC_HD void k2_read(K2State & s, const BatchView & v, const PileRec & P, uint32_
         const int32_t nextlen = nnminus(next_rpos - p, tmax((T.ext_beg + rtr2.begpos + rtr2.tracklen) - p, s.th.aRP1t));
         dist = tmin(prevlen, nextlen);
     }
-    const bool nfp = (v.par.tn_is_paired && (0x1 & v.par.primer_flag));
-    if (s.role == 1) {
-        if (!not_first) { return; }
-        const int32_t w = nnminus(tmin(80, s.noindel), (int32_t)((P.bits >> 24) & 0xfu)) + 1;   // nogap_weight
-        s.acc.bqsum += w;
-        segbias_dense<true>(s.acc, v, P, s.th, s.baq_p, s.baq2_p, w, p, 100, 0, dist, nfp);
-    } else {
-        const int sym = (int)(packed >> 8);
-        const int32_t bq = (int32_t)(packed & 0xffu) + v.par.bq_phred_added_misma;
+    const bool nfp = (par.tn_is_paired && (0x1 & par.primer_flag));
+    const bool has_base = (packed != UVC_K2_NOBASE);
+    const int sym = (int)(packed >> 8);
+    const int32_t bqB = (int32_t)(packed & 0xffu) + par.bq_phred_added_misma;
+    if (has_base && sym != s.major) {
+        // a base that differs from the reference (rare): its own symbol's records are updated with fire-and-forget atomics
         const int32_t xm_term = (int32_t)(P.terms_lo & 127u);
         const int32_t bm_term = (int32_t)((sym < 3 ? (P.terms_lo >> (7 * (sym + 1))) : (P.terms_hi >> (7 * (sym - 3)))) & 127u);
-        if (sym == s.major) {
-            s.acc.bqsum += bq;
-            segbias_dense<false>(s.acc, v, P, s.th, s.baq_p, s.baq2_p, bq, p, bm_term, xm_term, dist, nfp);
-        } else {
-            // a base that differs from the reference (rare): its own symbol's records are updated with fire-and-forget atomics, which do not
-            // stall the warp on ~40 dependent read-modify-writes (this thread is still the only writer of these records in this kernel)
-            SegAcc one;
-            segacc_zero(one);
-            one.bqsum = bq;
-            segbias_dense<false>(one, v, P, s.th, s.baq_p, s.baq2_p, bq, p, bm_term, xm_term, dist, nfp);
-            segacc_flush<true>(v, s.gp, sym, one);
+        SegAcc one;
+        segacc_zero(one);
+        one.bqsum = bqB;
+        segbias_dense<false>(one, v, P, s.th, s.baq_p, s.baq2_p, bqB, p, bm_term, xm_term, dist, nfp);
+        segacc_flush<true>(v, s.gp, sym, one);
+    }
+    // activity of the two symbols at this read: aB = the base equals the position's major symbol, aL = the junction before the base is inside the match run
+    const uint32_t aB = ((has_base && sym == s.major) ? 1u : 0u), aL = (not_first ? 1u : 0u);
+    const uint32_t A = aB | (aL << 16);
+    if (0 == A) { return; }
+    if (++s.nvis >= UVC_K2M_FLUSH_EVERY) { k2m_flush(s, v); s.nvis = 1; }
+    const uint32_t bits = P.bits;
+    const uvcgpu_thres_set & th = s.th;
+    const int32_t bqL = nnminus(tmin(80, s.noindel), (int32_t)((bits >> 24) & 0xfu)) + 1;      // nogap_weight
+    // ---- what depends on (read, position) only
+    const bool is_assay_amplicon = (bits & UVC_PR_AMPLICON);
+    const int32_t nl = p - P.pos + 1, nr = P.rend - p;
+    const int32_t seg_l_baq1 = s.baq_p - P.baq_pos + 1;
+    const int32_t seg_r_baq0 = P.baq_rend1 - s.baq_p + 1;
+    const int32_t seg_r_baqG = tmin(seg_r_baq0, P.baq2_rend1 - s.baq2_p + 7);
+    const bool is_high_readlen = (par.central_readlen >= par.microadjust_median_readlen_thres);
+    const int32_t seg_l_baq = (is_high_readlen ? seg_l_baq1 : tmax(seg_l_baq1, nl * par.microadjust_BAQ_per_base_x1024 / 1024));
+    const int32_t seg_r_baqB = (is_high_readlen ? seg_r_baq0 : tmax(seg_r_baq0, nr * par.microadjust_BAQ_per_base_x1024 / 1024));
+    const int32_t seg_r_baqL = (is_high_readlen ? seg_r_baqG : tmax(seg_r_baqG, nr * par.microadjust_BAQ_per_base_x1024 / 1024));
+    const bool has_isize = (bits & UVC_PR_HAS_ISIZE);
+    const int32_t frag_l_nb = (has_isize ? tmin(p - P.frag_l + 1, UVC_MAX_INSERT_SIZE) : UVC_MAX_INSERT_SIZE);
+    const int32_t frag_r_nb = (has_isize ? tmin(P.frag_r - p, UVC_MAX_INSERT_SIZE) : UVC_MAX_INSERT_SIZE);
+    const bool isrc = (bits & UVC_PR_ISRC);
+    const bool st1 = (bits & UVC_PR_STRAND);
+    const int32_t mapq = (int32_t)((bits >> 16) & 0xffu);
+    const int32_t iB = (int32_t)aB, iL = (int32_t)aL;
+    // ---- per symbol: counted / tier 2 / far from the edges / unaffected by the edges
+    const bool tier2B = (bqB >= par.bias_thres_highBQ), countedB = tier2B;
+    const bool countedL = (dist >= par.bias_thres_interfering_indel);
+    const int32_t LPxTL = th.aLPxT, RPxT = th.aRPxT, LPxTB = tmin(LPxTL, RPxT);
+    const bool farB = (nl >= LPxTB) & (nr >= RPxT), farL = (nl >= LPxTL) & (nr >= RPxT);
+    const bool unaffB = (seg_l_baq >= par.bias_thres_highBAQ + 3) & (seg_r_baqB >= par.bias_thres_highBAQ + 3);
+    const bool unaffL = (seg_l_baq >= par.bias_thres_highBAQ) & (seg_r_baqL >= par.bias_thres_highBAQ);
+    const uint32_t gpB = ((countedB & farB) ? aB : 0u), gpL = ((countedL & farL) ? aL : 0u);
+    const uint32_t gbB = ((countedB & unaffB) ? aB : 0u), gbL = ((countedL & unaffL) ? aL : 0u);
+    const uint32_t GP = gpB | (gpL << 16), GPT2 = (tier2B ? gpB : 0u) | (gpL << 16);       // (the gap symbol is always tier 2)
+    const uint32_t GB = gbB | (gbL << 16), GBT2 = (tier2B ? gbB : 0u) | (gbL << 16);
+    // ---- sums of the qualities
+    {
+        const int32_t sqB = bqB * bqB / UVC_SQR_QUAL_DIV, sqL = bqL * bqL / UVC_SQR_QUAL_DIV;
+        if (isrc) { s.q1r0 += iB * bqB; s.q2r0 += iB * sqB; s.q1r1 += iL * bqL; s.q2r1 += iL * sqL; }
+        else { s.q1f0 += iB * bqB; s.q2f0 += iB * sqB; s.q1f1 += iL * bqL; s.q2f1 += iL * sqL; }
+        s.bqs0 += iB * bqB; s.bqs1 += iL * bqL;
+        s.MQs0 += iB * mapq; s.MQs1 += iL * mapq;
+    }
+    // ---- strand x orientation depth, distance to interfering indels, clips, insert ends
+    if (st1) { if (isrc) { s.cDPrr += A; } else { s.cDPrf += A; } } else { if (isrc) { s.cDPfr += A; } else { s.cDPff += A; } }
+    if (tmin(dist, tmin(nl, nr)) >= par.bias_thres_interfering_indel) { s.cP3 += A; }
+    if (bits & UVC_PR_NOCLIP) { s.cNC += A; }
+    if (has_isize) { if (isrc) { s.LIT0 += iB * frag_l_nb; s.LIT1 += iL * frag_l_nb; } else { s.RIT0 += iB * frag_r_nb; s.RIT1 += iL * frag_r_nb; } }
+    {
+        const int32_t min_dist2iend = ((bits & UVC_PR_PAIRED) ? tmin(frag_l_nb, frag_r_nb) : (isrc ? nr : nl));
+        const bool x = ((min_dist2iend > par.primerlen2) | !is_assay_amplicon);
+        s.cP1 += ((farB & unaffB & x) ? aB : 0u) | ((farL & unaffL & x) ? (aL << 16) : 0u);
+        if (((bits & UVC_PR_UMI) != 0) | !is_assay_amplicon) { s.cP2 += A; }
+    }
+    // ---- passing-filter weights of the qualities
+    {
+        int32_t f1B, f2B, f1L, f2L;
+        if ((uint32_t)bqB < 128u) { f1B = v.pf_tab[bqB]; f2B = v.pf_tab[128 + bqB]; }
+        else {
+            f1B = ((bqB < par.bias_thres_PFBQ1) ? (100 * (bqB * bqB) / (par.bias_thres_PFBQ1 * par.bias_thres_PFBQ1)) : 100);
+            f2B = ((bqB < par.bias_thres_PFBQ2) ? (100 * (bqB * bqB) / (par.bias_thres_PFBQ2 * par.bias_thres_PFBQ2)) : 100);
         }
+        if ((uint32_t)bqL < 128u) { f1L = v.pf_tab[bqL]; f2L = v.pf_tab[128 + bqL]; }
+        else {
+            f1L = ((bqL < par.bias_thres_PFBQ1) ? (100 * (bqL * bqL) / (par.bias_thres_PFBQ1 * par.bias_thres_PFBQ1)) : 100);
+            f2L = ((bqL < par.bias_thres_PFBQ2) ? (100 * (bqL * bqL) / (par.bias_thres_PFBQ2 * par.bias_thres_PFBQ2)) : 100);
+        }
+        s.PF10 += iB * (100 * f1B / 100); s.PF20 += iB * (100 * f2B / 100);
+        s.PF11 += iL * tmin(100, f1L); s.PF21 += iL * tmin(100, f2L);
+        s.XM2 += iB * (int32_t)(P.terms_lo & 127u);
+        // (sym == major here whenever iB = 1)
+        s.BM2 += iB * (int32_t)((s.major < 3 ? (P.terms_lo >> (7 * (s.major + 1))) : (P.terms_hi >> (7 * ((s.major - 3) & 1)))) & 127u);
+    }
+    // ---- update_bidirectional_bias (main.hpp:1318-1358) twice: position bias and BAQ bias
+    if (nl >= th.aLP1t) { s.cLP1 += GP; }
+    if (nl >= th.aLP2t) { s.cLP2 += GPT2; }
+    if (nr >= th.aRP1t) { s.cRP1 += GP; }
+    if (nr >= th.aRP2t) { s.cRP2 += GPT2; }
+    s.LPL0 += (int32_t)gpB * nl; s.LPL1 += (int32_t)gpL * nl; s.RPL0 += (int32_t)gpB * nr; s.RPL1 += (int32_t)gpL * nr;
+    if (seg_l_baq >= par.bias_thres_BAQ1) { s.cLB1 += GB; }
+    if (seg_l_baq >= par.bias_thres_BAQ2) { s.cLB2 += GBT2; }
+    s.cRB1 += ((seg_r_baqB >= par.bias_thres_BAQ1) ? gbB : 0u) | ((seg_r_baqL >= par.bias_thres_BAQ1) ? (gbL << 16) : 0u);
+    s.cRB2 += (((seg_r_baqB >= par.bias_thres_BAQ2) & tier2B) ? gbB : 0u) | ((seg_r_baqL >= par.bias_thres_BAQ2) ? (gbL << 16) : 0u);
+    s.LBL0 += (int32_t)gbB * seg_l_baq; s.LBL1 += (int32_t)gbL * seg_l_baq; s.RBL0 += (int32_t)gbB * seg_r_baqB; s.RBL1 += (int32_t)gbL * seg_r_baqL;
+    s.cBQ2 += (countedB ? aB : 0u) | (countedL ? (aL << 16) : 0u);
+    // ---- insert-size bias: the reverse-complemented read looks at its left fragment end, the forward read at its right one
+    {
+        const bool mate_ok = (bits & UVC_PR_MATE_OK);
+        const bool nonbiased = (mate_ok & (isrc ? (nl > nr) : (nl < nr)));
+        const bool base_good = ((!is_assay_amplicon) | (!nfp));
+        const bool goodB = (base_good | (farB & unaffB)), goodL = (base_good | (farL & unaffL));
+        const int32_t d = (isrc ? frag_l_nb : frag_r_nb);
+        const int32_t t1 = (isrc ? th.aLI1t : th.aRI1t), T1 = (isrc ? th.aLI1T : th.aRI1T);
+        const int32_t t2 = (isrc ? th.aLI2t : th.aRI2t), T2 = (isrc ? th.aLI2T : th.aRI2T);
+        const bool normal = ((bits & UVC_PR_IS_NORMAL) != 0);
+        const bool okL = (normal | nonbiased);
+        const uint32_t c1 = (((d >= t1) & (d <= T1) & normal) ? aB : 0u) | (((d >= t1) & okL) ? (aL << 16) : 0u);
+        const uint32_t c2 = (((d >= t2) & (d <= T2) & normal & goodB) ? aB : 0u) | (((d >= t2) & okL & goodL) ? (aL << 16) : 0u);
+        const uint32_t c3 = (goodB ? aB : 0u) | (goodL ? (aL << 16) : 0u);
+        if (isrc) { s.cLI1 += c1; s.cLI2 += c2; s.cLIr += c3; } else { s.cRI1 += c1; s.cRI2 += c2; s.cRIf += c3; }
     }
 }
-
-UVC_HD void k2_end(K2State & s, const BatchView & v) {
-    if (s.major < UVC_NSYM) { segacc_flush<false>(v, s.gp, s.major, s.acc); }
-}
-
-UVC_HD void k2_position(const BatchView & v, int64_t gp, int role, const Win & w) {
-    K2State s;
-    k2_begin(s, v, gp, role);
+UVC_HD void k2m_position(const BatchView & v, int64_t gp, const Win & w) {
+    K2Merged s;
+    k2m_begin(s, v, gp);
     for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
         if (ri < w.lo || ri >= w.hi) { continue; }
-        k2_read(s, v, v.prec[ri], (role == 0 ? k2_fetch_base(s, v, v.reads[ri], true) : 0u));
+        const PileRec & P = v.prec[ri];
+        const int32_t qpos = base_index(v, P, s.p, true);
+        const int32_t qc = tmax(qpos, 0);
+        k2m_read(s, v, P, pack_base(v.seq[(uint64_t)P.seq_off + (uint32_t)(qc >> 1)], v.qual[(uint64_t)P.qual_off + (uint32_t)qc], qpos));
     }
-    k2_end(s, v);
+    k2m_flush(s, v);
 }
 
 // ------------------------------------------------------------------------------------------------ K2e: one thread per indel event
