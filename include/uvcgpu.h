@@ -323,6 +323,12 @@ int uvcgpu_tile_vcf(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_index, c
  * Returns the number of bytes the section needs in *needed; copies min(cap, needed) bytes into dst (dst may be NULL). */
 int uvcgpu_dump_counters(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_index, int32_t section, void *dst, size_t cap, size_t *needed);
 
+/* Test hook: evaluates scoring functions of the DEVICE code at caller-given points, so that the reference's compile-time known-answer checks
+ * (static_asserts of main_conversion.hpp:205-209, 251-254) can be run against the CUDA implementation itself. in holds n triples (x, a, b):
+ * which = 0: calc_binom_10log10_likeratio<false,false>(x, a, b) (main_conversion.hpp:222-237); which = 1: prob2odds(odds2prob(x));
+ * which = 2: odds2prob(prob2odds(x)); which = 3: logit2(a, b). out receives n doubles. */
+int uvcgpu_selftest_math(uvcgpu_ctx *ctx, int32_t which, const double *in, int32_t n, double *out);
+
 /* Frees the device/host state of a collected batch. */
 int uvcgpu_release(uvcgpu_ctx *ctx, uvcgpu_ticket ticket);
 

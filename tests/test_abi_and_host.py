@@ -86,3 +86,31 @@ def test_reference_static_asserts():
     odds2prob = lambda o: o / (o + 1.0)       # noqa: E731
     assert 0.99 < prob2odds(odds2prob(1)) < 1.01
     assert 0.65 < odds2prob(prob2odds(0.66)) < 0.67
+
+
+def _device_math(emulate):
+    """The reference's compile-time known-answer checks (main_conversion.hpp:205-209, 251-254) evaluated by the library's own scoring code."""
+    ctx = capi.Context(0, emulate=emulate)
+    ctx.lib.uvcgpu_selftest_math.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double)]
+
+    def ev(which, pts):
+        flat = (C.c_double * (3 * len(pts)))(*[x for p in pts for x in p])
+        out = (C.c_double * len(pts))()
+        assert ctx.lib.uvcgpu_selftest_math(ctx.handle, which, flat, len(pts), out) == 0
+        return list(out)
+    lr = ev(0, [(0.1, 10, 90), (0.1, 90, 10), (0.1, 1, 99)])
+    assert abs(lr[0]) < 1e-4 and 763 < lr[1] < 764 and abs(lr[2]) < 1e-4
+    assert abs(lr[1] - _binom_10log10_likeratio(0.1, 90, 10)) < 1e-9
+    assert 0.99 < ev(1, [(1.0, 0, 0)])[0] < 1.01
+    assert 0.65 < ev(2, [(0.66, 0, 0)])[0] < 0.67
+    assert abs(ev(3, [(0.0, 30.0, 10.0)])[0] - math.log(3.0)) < 1e-9
+    ctx.close()
+
+
+def test_emulated_scoring_math_known_answers():
+    _device_math(True)
+
+
+@pytest.mark.gpu
+def test_cuda_scoring_math_known_answers():
+    _device_math(False)

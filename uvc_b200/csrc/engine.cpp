@@ -691,6 +691,11 @@ __global__ void __launch_bounds__(64) uvc_k5_score_candidates(const BatchView v,
     if (i < n && i < (int64_t)*sv.cand_cursor) { uvc::k5_score_position(v, sv, (int64_t)sv.cand_list[i]); }
 }
 
+__global__ void uvc_selftest_math_kernel(const BatchView v, int32_t which, const double *in, int32_t n, double *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { out[i] = uvc::selftest_math(v, which, in[3 * i], in[3 * i + 1], in[3 * i + 2]); }
+}
+
 typedef void (*uvc_kernel_t)(const BatchView, int64_t);
 static void launch(uvc_kernel_t k, cudaStream_t s, const BatchView & v, int64_t n, int64_t & launches) {
     if (n <= 0) { return; }
@@ -1413,6 +1418,29 @@ int uvcgpu_tile_vcf(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_index, c
     if (rc != 0) { return rc; }
     *needed = s.size();
     if (dst && cap) { memcpy(dst, s.data(), s.size() < cap ? s.size() : cap); }
+    return UVCGPU_OK;
+}
+
+int uvcgpu_selftest_math(uvcgpu_ctx *ctx, int32_t which, const double *in, int32_t n, double *out) {
+    enter_ctx(ctx);
+    if (NULL == ctx || NULL == in || NULL == out || n <= 0 || which < 0 || which > 3) { return UVCGPU_EINVAL; }
+    BatchView v;
+    memset(&v, 0, sizeof(v));
+    uvc_fill_view_constants(v, ctx->par);
+    v.ten_over_ln10 = 10.0 / log(10.0);
+    v.ln10 = log(10);
+#if UVC_CUDA
+    double *d_in = NULL, *d_out = NULL;
+    UVC_CUDA_CHECK(ctx, cudaMalloc((void**)&d_in, (size_t)n * 3 * sizeof(double)));
+    if (cudaMalloc((void**)&d_out, (size_t)n * sizeof(double)) != cudaSuccess) { cudaFree(d_in); ctx->err = "cudaMalloc"; return UVCGPU_ECUDA; }
+    cudaMemcpy(d_in, in, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice);
+    uvc_selftest_math_kernel<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(v, which, d_in, n, d_out);
+    const cudaError_t e = cudaMemcpy(out, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) { ctx->err = std::string("uvcgpu_selftest_math: ") + cudaGetErrorString(e); return UVCGPU_ECUDA; }
+#else
+    for (int32_t i = 0; i < n; i++) { out[i] = uvc::selftest_math(v, which, in[3 * i], in[3 * i + 1], in[3 * i + 2]); }
+#endif
     return UVCGPU_OK;
 }
 

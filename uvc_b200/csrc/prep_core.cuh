@@ -388,9 +388,17 @@ struct P0eKept {
         const int64_t *psum = q.psum + P.psum_off + (int64_t)c * (fs + 1);
         const int32_t pos = q.pos[i], mpos = q.mpos[i];
         const uint16_t flag = q.flag[i];
+#if defined(__CUDA_ARCH__)
+        {   // thousands of reads of a tile update the same three words: one reduction per group of lanes with the same tile instead of one per read
+            const uint32_t peers = __match_any_sync(__activemask(), t);
+            const int32_t mn = __reduce_min_sync(peers, pos), mx = __reduce_max_sync(peers, d.rend), sp = __reduce_max_sync(peers, d.rend - pos);
+            if ((threadIdx.x & 31) == (uint32_t)(__ffs((int)peers) - 1)) { atomic_min32(&q.tile_bam_beg[t], mn); atomic_max32(&q.tile_bam_end[t], mx); atomic_max32(&q.tile_span[t], sp); }
+        }
+#else
         atomic_min32(&q.tile_bam_beg[t], pos);
         atomic_max32(&q.tile_bam_end[t], d.rend);
         atomic_max32(&q.tile_span[t], d.rend - pos);
+#endif
         const int32_t beg1 = I.tBeg + UVC_ARRPOS_MARGIN - fetch_tbeg, end1 = I.tEnd + UVC_ARRPOS_MARGIN - fetch_tbeg;
         const int32_t beg2 = center_at(beg_cnt, fs, beg1, q.center_pow), end2 = center_at(end_cnt, fs, end1, q.center_pow);
         const int64_t beg2count = beg_cnt[beg2], end2count = end_cnt[end2];
@@ -619,8 +627,16 @@ struct P0jFrag {
         G.beg = f_beg; G.end = f_end; G.lo = f_beg; G.hi = f_hi;
         q.frags[f] = G;
         q.fcol_len[f] = ((int64_t)(G.hi - G.lo) + UVC_COL_CHUNK - 1) / UVC_COL_CHUNK * UVC_COL_CHUNK;
+#if defined(__CUDA_ARCH__)
+        {
+            const uint32_t peers = __match_any_sync(__activemask(), G.tile);
+            const int32_t first = __reduce_min_sync(peers, (int32_t)f);
+            if ((threadIdx.x & 31) == (uint32_t)(__ffs((int)peers) - 1)) { atomic_add(&q.tiles[G.tile].n_frags, __popc(peers)); atomic_min64(&q.tiles[G.tile].frag_off, (int64_t)first); }
+        }
+#else
         atomic_add(&q.tiles[G.tile].n_frags, 1);
         atomic_min64(&q.tiles[G.tile].frag_off, f);
+#endif
     }
 };
 
@@ -676,8 +692,16 @@ struct P0kFam {
         }
         F.beg_both = both_beg; F.end_both = both_end;
         q.fams[fi] = F;
+#if defined(__CUDA_ARCH__)
+        {
+            const uint32_t peers = __match_any_sync(__activemask(), F.tile);
+            const int32_t first = __reduce_min_sync(peers, (int32_t)fi);
+            if ((threadIdx.x & 31) == (uint32_t)(__ffs((int)peers) - 1)) { atomic_add(&q.tiles[F.tile].n_fams, __popc(peers)); atomic_min64(&q.tiles[F.tile].fam_off, (int64_t)first); }
+        }
+#else
         atomic_add(&q.tiles[F.tile].n_fams, 1);
         atomic_min64(&q.tiles[F.tile].fam_off, fi);
+#endif
     }
 };
 

@@ -278,6 +278,17 @@ UVC_HD double binom_10log10_likeratio(const BatchView & v, double prob, double a
     return 0.0;
 }
 
+UVC_HD double odds2prob(double odds) { return odds / (odds + 1.0); }   // main_conversion.hpp:199-203
+// test hook (uvcgpu_selftest_math): one scoring function at one point
+UVC_HD double selftest_math(const BatchView & v, int32_t which, double x, double a, double b) {
+    switch (which) {
+        case 0: return binom_10log10_likeratio(v, x, a, b);
+        case 1: return prob2odds(odds2prob(x));
+        case 2: return odds2prob(prob2odds(x));
+        default: return logit2(a, b);
+    }
+}
+
 UVC_HD bool implies_short_frag(const GroupFmt & g, int32_t wgs_min_avg_fragsize) { // does_fmt_imply_short_frag (main.hpp:170-174)
     return (g.APLRI[0] + g.APLRI[2]) < (g.APLRI[1] + g.APLRI[3]) * (int64_t)wgs_min_avg_fragsize;
 }
