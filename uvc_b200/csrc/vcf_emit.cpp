@@ -69,24 +69,35 @@ struct Out {
     void strs_or_dot(const std::vector<std::string> & v) { sepc(); if (v.empty()) { s += "."; } for (size_t i = 0; i < v.size(); i++) { if (i) { s += ","; } s += v[i]; } }
 };
 
-// mutform2count4map_to_phase (main.hpp:5380-5404) restricted to the links that contain (refpos, symbol) and have at least two supporting fragments
-std::string phase_string(const std::vector<HapLinkOut> & links, int32_t refpos, int32_t symbol) {
-    std::string out;
-    for (const auto & h : links) {
+// mutform2count4map_to_phase (main.hpp:5380-5404) restricted to the links that contain (refpos, symbol) and have at least two supporting fragments.
+// A deep tile has thousands of links and a record per position: the links that contain a (position, symbol) are indexed once per tile, in link
+// order, so that a record only visits its own links.
+typedef std::map<std::pair<int32_t, int32_t>, std::vector<int32_t>> PhaseIndex;
+PhaseIndex phase_index(const std::vector<HapLinkOut> & links) {
+    PhaseIndex idx;
+    for (size_t i = 0; i < links.size(); i++) {
+        const HapLinkOut & h = links[i];
         if (h.fr_cnts[0] + h.fr_cnts[1] < 2) { continue; }
-        if (std::find(h.pos_symb.begin(), h.pos_symb.end(), std::make_pair(refpos, symbol)) == h.pos_symb.end()) { continue; }
-        if ((h.fr_cnts[0] + h.fr_cnts[1]) > 1) {
-            out += "(";
-            for (const auto & ps : h.pos_symb) {
-                const int32_t mutpos = ps.first + (sym_is_subst(ps.second) ? 1 : 0);
-                out += std::string("(") + std::to_string(mutpos) + "&" + SYMBOL_DESC[ps.second] + ")";
-            }
-            const std::string add = ((-1 < h.other_hap_cnts[0])
-                    ? ("&&" + std::to_string(h.other_hap_cnts[0] + h.fr_cnts[0]) + "&" + std::to_string(h.other_hap_cnts[1] + h.fr_cnts[1])) : "");
-            out += std::string("&") + std::to_string(h.fr_cnts[0]) + "&" + std::to_string(h.fr_cnts[1]) + add + ")";
+        for (const auto & ps : h.pos_symb) {
+            std::vector<int32_t> & v = idx[ps];
+            if (v.empty() || v.back() != (int32_t)i) { v.push_back((int32_t)i); }
         }
     }
-    return out;
+    return idx;
+}
+void append_phase_string(std::string & out, const std::vector<HapLinkOut> & links, const PhaseIndex & idx, int32_t refpos, int32_t symbol) {
+    auto it = idx.find(std::make_pair(refpos, symbol));
+    if (it == idx.end()) { return; }
+    for (int32_t li : it->second) {
+        const HapLinkOut & h = links[(size_t)li];
+        out += '(';
+        for (const auto & ps : h.pos_symb) {
+            out += '('; append_num(out, ps.first + (sym_is_subst(ps.second) ? 1 : 0)); out += '&'; out += SYMBOL_DESC[ps.second]; out += ')';
+        }
+        out += '&'; append_num(out, h.fr_cnts[0]); out += '&'; append_num(out, h.fr_cnts[1]);
+        if (-1 < h.other_hap_cnts[0]) { out += "&&"; append_num(out, h.other_hap_cnts[0] + h.fr_cnts[0]); out += '&'; append_num(out, h.other_hap_cnts[1] + h.fr_cnts[1]); }
+        out += ')';
+    }
 }
 
 std::string fts_string(const CandFmt & c) {
@@ -218,6 +229,8 @@ std::string uvc_tile_vcf_text(const HostBatch & hb, int32_t tile_index, const uv
     if (T.skipped) { return out; }
     const int32_t nref = (T.ext_end - T.ext_beg) - 1;
     const std::string refstring = (contig.available ? contig.bases.substr(T.ext_beg, nref) : std::string((size_t)nref, 'n'));
+    const PhaseIndex pidx_bq = phase_index(sparse.hap_bq), pidx_fq = phase_index(sparse.hap_fq), pidx_f2q = phase_index(sparse.hap_f2q);
+    out.reserve(recs.size() * 3200 + (size_t)(T.end_pos - T.beg_pos) * 24 + 4096);
     // records grouped by (zero-based position, symbol type) in the device's candidate order
     std::map<std::pair<int32_t, int32_t>, std::vector<const VarRec*>> by_zb;
     for (const auto & r : recs) { by_zb[std::make_pair(r.symboltype == 0 ? r.refpos + 1 : r.refpos, r.symboltype)].push_back(&r); }
@@ -303,30 +316,29 @@ std::string uvc_tile_vcf_text(const HostBatch & hb, int32_t tile_index, const uv
                     t2AD1 = 0;
                     if (site) { for (size_t i = 0; i < site->gapSeq.size(); i++) { if (site->gapSeq[i] == indelstring) { t2AD1 += site->gc2dAD[i]; } } }
                 }
-                out += tname + "\t" + std::to_string(vcfpos) + "\t.\t" + vcfref + "\t" + vcfalt + "\t" + std::to_string(vq) + "\t" + filter + "\t";
-                out += std::string("ANY_VAR") + ";SomaticQ=" + std::to_string(r.somaticq) + ";TLODQ=" + std::to_string(r.tlodq) + ";NLODQ=" + std::to_string(r.nlodq) + ";NLODV=<NONE>";
-                out += ";TNBQF=" + std::to_string(r.TNBQF[0]) + "," + std::to_string(r.TNBQF[1]) + "," + std::to_string(r.TNBQF[2]) + "," + std::to_string(r.TNBQF[3]);
-                out += ";TNCQF=" + std::to_string(r.TNCQF[0]) + "," + std::to_string(r.TNCQF[1]) + "," + std::to_string(r.TNCQF[2]) + "," + std::to_string(r.TNCQF[3]);
-                out += ";tbDP=" + std::to_string(r.tbDP) + ";tDP=" + std::to_string(r.tDP) + ";tAD=" + std::to_string(r.tAD[0]) + "," + std::to_string(r.tAD[1]);
-                out += ";t2DP=" + std::to_string(r.t2DP) + ";t2AD=" + std::to_string(r.t2AD[0]) + "," + std::to_string(t2AD1);
-                out += ";RU=" + repeatunit + ";RC=" + std::to_string(r.repeatnum);
-                out += ";R3X2=" + std::to_string(r.rtr_info[0]) + "," + std::to_string(r.rtr_info[1]) + "," + std::to_string(r.rtr_info[2]) + "," + std::to_string(r.rtr_info[3]) + ","
-                     + std::to_string(r.rtr_info[4]) + "," + std::to_string(r.rtr_info[5]);
+                out += tname; out += '\t'; append_num(out, vcfpos); out += "\t.\t"; out += vcfref; out += '\t'; out += vcfalt; out += '\t'; out += std::to_string(vq); out += '\t'; out += filter; out += '\t';
+                out += "ANY_VAR;SomaticQ="; append_num(out, r.somaticq); out += ";TLODQ="; append_num(out, r.tlodq); out += ";NLODQ="; append_num(out, r.nlodq); out += ";NLODV=<NONE>";
+                out += ";TNBQF="; append_num(out, r.TNBQF[0]); out += ','; append_num(out, r.TNBQF[1]); out += ','; append_num(out, r.TNBQF[2]); out += ','; append_num(out, r.TNBQF[3]);
+                out += ";TNCQF="; append_num(out, r.TNCQF[0]); out += ','; append_num(out, r.TNCQF[1]); out += ','; append_num(out, r.TNCQF[2]); out += ','; append_num(out, r.TNCQF[3]);
+                out += ";tbDP="; append_num(out, r.tbDP); out += ";tDP="; append_num(out, r.tDP); out += ";tAD="; append_num(out, r.tAD[0]); out += ','; append_num(out, r.tAD[1]);
+                out += ";t2DP="; append_num(out, r.t2DP); out += ";t2AD="; append_num(out, r.t2AD[0]); out += ','; append_num(out, t2AD1);
+                out += ";RU="; out += repeatunit; out += ";RC="; append_num(out, r.repeatnum);
+                out += ";R3X2="; append_num(out, r.rtr_info[0]); out += ','; append_num(out, r.rtr_info[1]); out += ','; append_num(out, r.rtr_info[2]); out += ','; append_num(out, r.rtr_info[3]); out += ',';
+                append_num(out, r.rtr_info[4]); out += ','; append_num(out, r.rtr_info[5]);
                 const bool sscs = (A.enable_tier2 != 0);
                 out += "\t";
-                {   // FORMAT key string
-                    std::string f = "GT:GQ:HQ:FT:FTS:_A_:DP:AD:bDP:bAD:c2DP:c2AD:_Aa:APDP:APXM:_Ab:APLRID:APLRI:APLRP:_Ac:ALRPxT:ALRIT:ALRIt:ALRPt:ALRBt:_AQ:aMQs:AMQs:a1BQf:A1BQf:a1BQr:A1BQr:"
+                {   // FORMAT key string (bcf_formats_generator1.cpp:599-622: with or without the tier-2 consensus tags)
+                    static const std::string f_head = "GT:GQ:HQ:FT:FTS:_A_:DP:AD:bDP:bAD:c2DP:c2AD:_Aa:APDP:APXM:_Ab:APLRID:APLRI:APLRP:_Ac:ALRPxT:ALRIT:ALRIt:ALRPt:ALRBt:_AQ:aMQs:AMQs:a1BQf:A1BQf:a1BQr:A1BQr:"
                         "_ADPf:aDPff:ADPff:aDPfr:ADPfr:_ADPr:aDPrf:ADPrf:aDPrr:ADPrr:_ALP:aLP1:ALP1:aLP2:ALP2:aLPL:ALPL:_ARP:aRP1:ARP1:aRP2:ARP2:aRPL:ARPL:_ALB:aLB1:aLB2:ALB2:aLBL:ALBL:"
                         "_ARB:aRB1:aRB2:ARB2:aRBL:ARBL:_ALI:aLI1:aLI2:ALI2:aLIr:ALIr:_ARI:aRI1:aRI2:ARI2:aRIf:ARIf:_AX:aBQ2:ABQ2:aPF2:APF2:aP1:AP1:aP2:AP2:_Ax:aPF1:aLIT:aRIT:aP3:aNC:"
                         "_BDP:bDPf:bDPr:BDPb:BDPd:bTAf:bTAr:BTAb:bTBf:bTBr:BTBb:_CDP1:cDP1f:cDP1r:CDP1b:CDP1d:cDP12f:cDP12r:CDP12b:_CDP2:cDP2f:cDP2r:CDP2b:CDP2d:";
-                    if (sscs) {
-                        f += "c2BQ2:C2BQ2:c2LP0:C2LP0:c2RP0:C2RP0:_C2XP:c2LP1:c2LP2:c2RP1:c2RP2:c2LPL:c2RPL:_C2XB:c2LB1:c2LB2:c2RB1:c2RB2:c2LBL:c2RBL:_CDPx:cDP3f:cDP3r:CDP3b:cDP21f:cDP21r:CDP21b:"
+                    static const std::string f_sscs = "c2BQ2:C2BQ2:c2LP0:C2LP0:c2RP0:C2RP0:_C2XP:c2LP1:c2LP2:c2RP1:c2RP2:c2LPL:c2RPL:_C2XB:c2LB1:c2LB2:c2RB1:c2RB2:c2LBL:c2RBL:_CDPx:cDP3f:cDP3r:CDP3b:cDP21f:cDP21r:CDP21b:"
                              "_cDPMm:cDPMf:cDPMr:CDPMb:cDPmf:cDPmr:CDPmb:";
-                    }
-                    f += "CDPDb:cDPDf:cDPDr:_DDP:DDP1:dDP1:DDP2:dDP2:_ea:aBQ:a2BQf:a2BQr:a2XM2:a2BM2:aBQQ:_eb:bMQ:aAaMQ:bNMQ:bNMa:bNMb:bMQQ:_eB:bIAQb:bIADb:bIDQb:_eC:cIAQf:cIADf:cIDQf:cIAQr:cIADr:cIDQr:"
+                    static const std::string f_tail = "CDPDb:cDPDf:cDPDr:_DDP:DDP1:dDP1:DDP2:dDP2:_ea:aBQ:a2BQf:a2BQr:a2XM2:a2BM2:aBQQ:_eb:bMQ:aAaMQ:bNMQ:bNMa:bNMb:bMQQ:_eB:bIAQb:bIADb:bIDQb:_eC:cIAQf:cIADf:cIDQf:cIAQr:cIADr:cIDQr:"
                          "_eE:bIAQ:cIAQ:bTINQ:cTINQ:_eQ1:cPCQ1:cPLQ1:cVQ1:gVQ1:_eQ2:cPCQ2:cPLQ2:cVQ2:cMmQ:dVQinc:_CDP1vx:cDP1v:CDP1v:cDP1w:CDP1w:cDP1x:CDP1x:_CDP2vx:cDP2v:CDP2v:cDP2w:CDP2w:cDP2x:CDP2x:"
                          "_f1:CONTQ:nPF:nNFA:nAFA:nBCFA:_g1:VTI:VTD:cVQ1M:cVQ2M:cVQAM:cVQSM:_g2:gapNf:gapNr:gapSeq:gapbAD1:gapcAD1:gc2AD:gc2dAD:_g3:bDPa:cDP0a:gapSa:_h1:bHap:cHap:c2Hap:_i1:vHGQ:vAC:vNLODQ:note";
-                    out += f + "\t";
+                    static const std::string f_with = f_head + f_sscs + f_tail + "\t", f_without = f_head + f_tail + "\t";
+                    out += (sscs ? f_with : f_without);
                 }
                 Out o(out);
                 #define RR(field) o.pair(R.field, A.field)
@@ -384,7 +396,11 @@ std::string uvc_tile_vcf_text(const HostBatch & hb, int32_t tile_index, const uv
                 RR(bDPa); RR(cDP0a);
                 o.sepc(); out += "," + indelstring;
                 o.tag("_h1");
-                o.str(phase_string(sparse.hap_bq, refpos, symbol)); o.str(phase_string(sparse.hap_fq, refpos, symbol)); o.str(phase_string(sparse.hap_f2q, refpos, symbol));
+                {
+                    const std::vector<HapLinkOut> *hl[3] = {&sparse.hap_bq, &sparse.hap_fq, &sparse.hap_f2q};
+                    const PhaseIndex *hi[3] = {&pidx_bq, &pidx_fq, &pidx_f2q};
+                    for (int k = 0; k < 3; k++) { o.sepc(); const size_t before = out.size(); append_phase_string(out, *hl[k], *hi[k], refpos, symbol); if (out.size() == before) { out += '.'; } }
+                }
                 o.tag("_i1");
                 o.one(r.vHGQ); o.arr(r.vAC, 2); o.arr(r.vNLODQ, 2); o.str("");
                 #undef RR
