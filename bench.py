@@ -170,7 +170,7 @@ def tile_list(ds, nthreads: int = TILER_THREADS, bed=None):
     return tiles
 
 
-def decode_sub_batches(ds, tiles, n_sub, threads):
+def decode_sub_batches(ds, tiles, n_sub, threads, only=None):
     """Host-side decode: BAM -> SoA records of every tile's fetch window (what sam_itr_queryi(tid, beg - 2000, end + 2000) yields), one read
     buffer per sub-batch, sub-batches decoded on `threads` threads (each with its own BAM handle). Every record is stored once: the slices of
     neighbouring tiles overlap (uvchost_bam_fetch_span)."""
@@ -208,6 +208,8 @@ def decode_sub_batches(ds, tiles, n_sub, threads):
                     nxt[0] += 1
                 if k >= n_sub:
                     return
+                if only is not None and not only(k):     # (a rank of the strong-scaling run decodes only its own share)
+                    continue
                 sl = tiles[bounds[k]:bounds[k + 1]]
                 rb = capi.ReadBuf()
                 ctiles = []
@@ -446,12 +448,10 @@ def main():
         t2 = time.time()
         st = ctx.score(ticket)               # candidate scoring on the device + D2H of the kept records and block-line inputs
         t3 = time.time()
-        nbytes = 0
-        for ti in range(len(sub[0])):        # the step's result: every tile's VCF body text
-            txt = ctx.tile_vcf(ticket, ti)
-            nbytes += len(txt)
-            if keep_text is not None:
-                keep_text.append(txt)
+        txt = ctx.batch_vcf(ticket)          # the step's result: the VCF body text of the sub-batch's tiles, in tile order
+        nbytes = len(txt)
+        if keep_text is not None:
+            keep_text.append(txt)
         t4 = time.time()
         ctx.release(ticket)
         st.vcf_bytes = nbytes
@@ -609,6 +609,77 @@ def main():
                 total += len(b)
             concat = {"shards": world, "bytes": total, "sha1": h.hexdigest()}
         dist.barrier()
+    strong = None
+    if world > 1:
+        # ---- strong scaling: ONE tile list (shard 0, the N = 1 workload) interleaved over the ranks' GPUs; rank 0 concatenates the VCF text in
+        # tile order (the reference's ordered flush, main.cpp:1541-1551) and compares it with its own single-GPU output of the same shard
+        ds0 = dataset(args.workdir, name, scale, 0, host_threads)
+        tiles0 = tile_list(ds0) if rank != 0 else tiles
+        subs0 = decode_sub_batches(ds0, tiles0, 0, host_threads, only=(lambda k: k % world == rank)) if rank != 0 else subs
+        mine0 = [(k, s0) for k, s0 in enumerate(subs0) if s0 is not None and k % world == rank]
+        if rank != 0:
+            bases0 = {tid: capi.read_fasta_contig(ds0["fasta"], cname) for tid, (cname, _) in enumerate(ds0["contigs"])}
+            for c in ctxs:
+                for tid, (cname, _) in enumerate(ds0["contigs"]):
+                    c.set_contig(tid, bases0[tid])
+                    c.set_contig_name(tid, cname)
+        texts0 = {}
+
+        def strong_pass(keep):
+            nxt0 = [0]
+            lock0 = threading.Lock()
+            errs0 = []
+
+            def work0(ctx):
+                try:
+                    pending = None
+                    while True:
+                        with lock0:
+                            i = nxt0[0]
+                            nxt0[0] += 1
+                        nxt_p = (mine0[i][0], submit_tiles(ctx, mine0[i][1])) if i < len(mine0) else None
+                        if pending is None and nxt_p is None:
+                            return
+                        if pending is not None:
+                            kk = [] if keep else None
+                            finish_tiles(ctx, pending[1], kk)
+                            if keep:
+                                texts0[pending[0]] = b"".join(kk)
+                        pending = nxt_p
+                except Exception as e:  # noqa: BLE001
+                    errs0.append(e)
+            ths0 = [threading.Thread(target=work0, args=(c,)) for c in ctxs]
+            for t in ths0:
+                t.start()
+            for t in ths0:
+                t.join()
+            if errs0:
+                raise errs0[0]
+        strong_pass(False)
+        n_strong = max(1, min(args.steps, 3))
+        dist.barrier()
+        torch.cuda.synchronize()
+        ts0 = time.time()
+        for it in range(n_strong):
+            strong_pass(it == n_strong - 1)
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.time() - ts0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        strong_s = float(tt[0])
+        with open(os.path.join(args.workdir, "vcf_strong_%d_of_%d.bin" % (rank, world)), "wb") as f:
+            import pickle
+            pickle.dump(texts0, f)
+        dist.barrier()
+        if rank == 0:
+            import pickle
+            allt = {}
+            for r in range(world):
+                allt.update(pickle.load(open(os.path.join(args.workdir, "vcf_strong_%d_of_%d.bin" % (r, world)), "rb")))
+            body0 = b"".join(allt[k] for k in sorted(allt))
+            strong = {"value": n_reads * n_strong / strong_s, "unit": "reads/s", "steps": n_strong, "wall_ms_per_step": strong_s * 1e3 / n_strong,
+                      "what": "the N = 1 workload (shard 0) with its sub-batches interleaved over the %d GPUs, one process per GPU, rank 0 concatenates the VCF text in tile order" % world,
+                      "vcf_body_sha1": hashlib.sha1(body0).hexdigest(), "identical_to_single_gpu_output": hashlib.sha1(body0).hexdigest() == shard_sha}
+        dist.barrier()
     for c in ctxs:                           # explicit teardown (contexts own CUDA streams and pool memory)
         c.close()
     if world > 1:
@@ -660,7 +731,7 @@ def main():
             "e2e": {"value": e2e, "unit": "reads/s", "positions_per_s": pos_all * args.steps / wall_s,
                     "h2d_bytes_per_step": totals["h2d"] // args.steps, "d2h_bytes_per_step": totals["d2h"] // args.steps,
                     "vcf_bytes_per_step": totals["vcf"] // args.steps, "vcf_records_per_step": totals["rec"] // args.steps,
-                    "vcf_body_sha1_last_step": shard_sha, "vcf_concatenation": concat,
+                    "vcf_body_sha1_last_step": shard_sha, "vcf_concatenation": concat, "strong_scaling": strong,
                     "scope": "C ABI from decoded host SoA buffers: host staging + H2D + kernels + D2H + VCF text; excludes BAM decode (see `decode`) and BGZF output (see `pipeline`)",
                     "host_prep_ms_per_step_summed_over_contexts": totals["prep_ms"] / args.steps,
                     "submit_wait_for_batch_sizes_ms_per_step_summed_over_contexts": totals["sync_ms"] / args.steps,

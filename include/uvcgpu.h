@@ -319,6 +319,10 @@ int uvcgpu_score(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, uvcgpu_batch_stats *stat
  * Returns the number of bytes in *needed; copies min(cap, needed) bytes into dst (dst may be NULL). */
 int uvcgpu_tile_vcf(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_index, char *dst, size_t cap, size_t *needed);
 
+/* The VCF bodies of ALL tiles of the batch, concatenated in tile order (what a caller appends to its output for the batch): one call instead of
+ * one per tile. Same conventions as uvcgpu_tile_vcf. */
+int uvcgpu_batch_vcf(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, char *dst, size_t cap, size_t *needed);
+
 /* Test hook: raw per-position arrays of one tile of a collected batch for bit-exact parity against the oracle.
  * Returns the number of bytes the section needs in *needed; copies min(cap, needed) bytes into dst (dst may be NULL). */
 int uvcgpu_dump_counters(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_index, int32_t section, void *dst, size_t cap, size_t *needed);

@@ -29,6 +29,7 @@ def _tiles_text(info, tile_groups, emulate, pipelined):
         st = ctx.collect(ticket)
         ctx.score(ticket)
         text = [ctx.tile_vcf(ticket, k).decode() for k in range(n)]
+        assert bytes(ctx.batch_vcf(ticket)).decode() == "".join(text)      # the batch-level call is the concatenation in tile order
         ctx.release(ticket)
         return text, st
 

@@ -87,7 +87,6 @@ def load_gpu(emulate: bool = False) -> C.CDLL:
     if emulate in _gpu_libs:
         return _gpu_libs[emulate]
     path = (os.path.join(ROOT, "tests", "emu", "libuvcgpu_emu.so") if emulate else os.path.join(LIBDIR, "libuvcgpu.so"))
-    path = os.environ.get("UVCGPU_EMU_LIB" if emulate else "UVCGPU_LIB", path)   # developer override of the library file (debug builds)
     if not os.path.exists(path):
         raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)" % path)
     lib = C.CDLL(path)
@@ -102,6 +101,7 @@ def load_gpu(emulate: bool = False) -> C.CDLL:
     lib.uvcgpu_set_contig_name.argtypes = [C.c_void_p, C.c_int32, C.c_char_p]
     lib.uvcgpu_score.argtypes = [C.c_void_p, C.c_int64, C.POINTER(BatchStats)]
     lib.uvcgpu_tile_vcf.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.uvcgpu_batch_vcf.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.uvcgpu_submit.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Tile), C.POINTER(ReadsSoA), C.POINTER(C.c_int64)]
     lib.uvcgpu_collect.argtypes = [C.c_void_p, C.c_int64, C.POINTER(BatchStats)]
     lib.uvcgpu_release.argtypes = [C.c_void_p, C.c_int64]
@@ -193,6 +193,18 @@ class Context:
         buf = C.create_string_buffer(max(1, need.value))
         self._check(self.lib.uvcgpu_tile_vcf(self.handle, ticket, tile_index, buf, need.value, C.byref(need)), "uvcgpu_tile_vcf")
         return buf.raw[:need.value]
+
+    def batch_vcf(self, ticket: int) -> bytearray:
+        """VCF bodies of all tiles of the batch in tile order (one copy into a bytearray)."""
+        need = C.c_size_t()
+        self._check(self.lib.uvcgpu_batch_vcf(self.handle, ticket, None, 0, C.byref(need)), "uvcgpu_batch_vcf")
+        out = bytearray(max(1, need.value))
+        buf = (C.c_char * len(out)).from_buffer(out)
+        self._check(self.lib.uvcgpu_batch_vcf(self.handle, ticket, buf, need.value, C.byref(need)), "uvcgpu_batch_vcf")
+        del buf
+        if need.value < len(out):
+            del out[need.value:]
+        return out
 
     def submit(self, tiles: Sequence[Tile], reads: ReadsSoA) -> int:
         arr = (Tile * len(tiles))(*tiles)

@@ -743,7 +743,8 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     int e = 0;
     // Threads per block of the position kernels (every warp is self-contained: its own staging slot, no block-wide synchronisation). A batch
     // with few positions and deep windows (a small panel at very high depth) is cut into one-warp blocks so that every SM gets some.
-    int pb = (v.n_pos >= (int64_t)148 * 128 * 2 ? 128 : (v.n_pos >= (int64_t)148 * 64 * 2 ? 64 : 32));
+    // (four 128-thread blocks are resident per SM: below 148 x 4 x 128 positions smaller blocks spread the warps over the SMs more evenly)
+    int pb = (v.n_pos >= (int64_t)148 * 128 * 4 ? 128 : (v.n_pos >= (int64_t)148 * 64 * 2 ? 64 : 32));
     { const char *f = getenv("UVC_POS_BLOCK"); if (f && (atoi(f) == 32 || atoi(f) == 64 || atoi(f) == 128)) { pb = atoi(f); } }   // tests force every shape
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
     #define UVC_STAGE(kernel, n) { launch(kernel, ctx->stream, v, (n), launches); UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream)); }
@@ -1418,6 +1419,30 @@ int uvcgpu_tile_vcf(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_index, c
     if (rc != 0) { return rc; }
     *needed = s.size();
     if (dst && cap) { memcpy(dst, s.data(), s.size() < cap ? s.size() : cap); }
+    return UVCGPU_OK;
+}
+
+int uvcgpu_batch_vcf(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, char *dst, size_t cap, size_t *needed) {
+    enter_ctx(ctx);
+    if (NULL == ctx || NULL == needed) { return UVCGPU_EINVAL; }
+    auto it = ctx->batches.find(ticket);
+    if (it == ctx->batches.end()) { ctx->err = "unknown ticket"; return UVCGPU_EINVAL; }
+    BatchState & bs = *it->second;
+    if (!bs.collected) { ctx->err = "batch not collected yet"; return UVCGPU_EINVAL; }
+    int rc = ensure_vcf_text(ctx, bs);
+    if (rc != 0) { return rc; }
+    size_t total = 0;
+    for (const auto & t : bs.vcf_text) { total += t.size(); }
+    *needed = total;
+    if (dst && cap) {
+        size_t at = 0;
+        for (const auto & t : bs.vcf_text) {
+            if (at >= cap) { break; }
+            const size_t n = (t.size() < cap - at ? t.size() : cap - at);
+            memcpy(dst + at, t.data(), n);
+            at += n;
+        }
+    }
     return UVCGPU_OK;
 }
 
