@@ -497,10 +497,13 @@ def main():
         agg[k] //= args.steps
 
     # ---- phase 2: end to end from host buffers: sub-batches pipelined over a few contexts (streams)
-    n_ctx = max(1, min(args.contexts, len(subs)))
+    # (two sub-batches are in flight per context: deep panels have few, large sub-batches - the contexts are limited so that about 12 M reads
+    #  are in flight at most, which keeps the column caches of all of them inside the 180 GB of HBM)
+    reads_per_sub = max(1, n_records // max(1, len(subs)))
+    n_ctx = max(1, min(args.contexts, len(subs), max(1, 6_000_000 // reads_per_sub)))
     ctxs = [ctx0] + [make_ctx(max(1, host_threads // n_ctx + 1)) for _ in range(n_ctx - 1)]
     ctx0.lib.uvcgpu_set_host_threads(ctx0.handle, max(1, host_threads // n_ctx + 1))
-    totals = {"h2d": 0, "d2h": 0, "vcf": 0, "rec": 0, "launch": 0, "prep_ms": 0.0, "sync_ms": 0.0, "stage_call_ms": 0.0, "submit_s": 0.0, "wait_s": 0.0, "score_s": 0.0, "text_s": 0.0, "release_s": 0.0}
+    totals = {"h2d": 0, "d2h": 0, "vcf": 0, "rec": 0, "launch": 0, "prep_ms": 0.0, "sync_ms": 0.0, "stage_call_ms": 0.0, "sc2": 0.0, "sc3": 0.0, "sc4": 0.0, "sc5": 0.0, "submit_s": 0.0, "wait_s": 0.0, "score_s": 0.0, "text_s": 0.0, "release_s": 0.0}
     last_text = {}
 
     def e2e_steps(n_steps, keep_last=False):
@@ -542,6 +545,8 @@ def main():
                         acc["prep_ms"] += st.host_prep_ms
                         acc["sync_ms"] += st.reserved[0]
                         acc["stage_call_ms"] += st.reserved[1]
+                        for j in (2, 3, 4, 5):
+                            acc["sc%d" % j] += st.reserved[j]
                         for key, val in zip(("submit_s", "wait_s", "score_s", "text_s", "release_s"), st.phase_s):
                             acc[key] += val
             except Exception as e:  # noqa: BLE001
@@ -736,6 +741,8 @@ def main():
                     "host_prep_ms_per_step_summed_over_contexts": totals["prep_ms"] / args.steps,
                     "submit_wait_for_batch_sizes_ms_per_step_summed_over_contexts": totals["sync_ms"] / args.steps,
                     "submit_staging_part_ms_per_step_summed_over_contexts": totals["stage_call_ms"] / args.steps,
+                    "score_parts_ms_per_step_summed_over_contexts": {"sparse_download": totals["sc2"] / args.steps, "sparse_maps_host": totals["sc3"] / args.steps,
+                                                                     "indel_table_host": totals["sc4"] / args.steps, "scoring_kernels_and_downloads": totals["sc5"] / args.steps},
                     "call_ms_per_step_summed_over_contexts": {k[:-2]: totals[k] * 1e3 / args.steps for k in ("submit_s", "wait_s", "score_s", "text_s", "release_s")},
                     "wall_ms_per_step": wall_s * 1e3 / args.steps,
                     "staging_blocks_not_yet_page_locked": {"at_start": backlog0, "at_end": backlog1},

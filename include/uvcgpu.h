@@ -271,7 +271,9 @@ typedef struct uvcgpu_batch_stats {
                                         13: staging kernels (P0 read filter + family segmentation, P1 reference context) */
     int64_t n_vcf_records;           /* candidate records the scoring stage kept */
     double host_score_ms;            /* host part of the scoring stage (indel allele table, record ordering) */
-    double reserved[6];              /* [0]: ms the submit call waited for the sizes of the batch (staging kernels), [1]: ms of the whole staging part of submit */
+    double reserved[6];              /* [0]: ms the submit call waited for the sizes of the batch (staging kernels), [1]: ms of the whole staging part of submit,
+                                        [2]: ms of the sparse-record downloads, [3]: ms of the host-side sparse maps, [4]: ms of the indel allele table,
+                                        [5]: ms of the scoring kernels and the downloads of their results */
 } uvcgpu_batch_stats;
 
 /* CommandLineArgs defaults (CmdLineArgs.hpp) with the Illumina inference applied (CmdLineArgs.cpp:127-134). */

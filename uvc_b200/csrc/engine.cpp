@@ -64,7 +64,8 @@ struct BatchState {
     StageVec<IndelEvent> ev_host;
     bool scored = false;
     std::vector<TileIndelSites> sites;
-    std::vector<std::vector<VarRec>> recs_by_tile;
+    StageVec<VarRec> recs;                               // candidate records as downloaded
+    std::vector<std::vector<const VarRec*>> recs_by_tile; // the records of every tile (pointers into recs: a record is ~2 KB)
     StageVec<GvcfPos> gvcf;
     StageVec<GvcfExtra> gextra;
 #if UVC_CUDA
@@ -1294,6 +1295,7 @@ static int ensure_sparse(uvcgpu_ctx *ctx, BatchState & bs) {
     int rc = backend_download(ctx, cursor, v.rec_cursor, sizeof(cursor));
     if (rc != 0) { return rc; }
     if (cursor[0] > v.rec_cap) { ctx->err = "sparse record stream overflow: submit a smaller batch"; return UVCGPU_ENOMEM; }
+    const double t_sp0 = now_ms();
     StageVec<int32_t> rec((size_t)cursor[0]);
     rc = backend_download(ctx, rec.data(), v.rec_buf, rec.size() * sizeof(int32_t));
     if (rc != 0) { return rc; }
@@ -1301,7 +1303,10 @@ static int ensure_sparse(uvcgpu_ctx *ctx, BatchState & bs) {
     rc = backend_download(ctx, bs.ev_host.data(), v.ev, bs.ev_host.size() * sizeof(IndelEvent));
     if (rc != 0) { return rc; }
     bs.stats.d2h_bytes += (int64_t)(rec.size() * sizeof(int32_t) + bs.ev_host.size() * sizeof(IndelEvent));
+    const double t_sp1 = now_ms();
     uvc_build_sparse(bs.sparse, bs.hb, ctx->par, rec.data(), (int64_t)rec.size(), bs.ev_host.data());
+    bs.stats.reserved[2] += t_sp1 - t_sp0;          // download of the sparse record stream and the indel events
+    bs.stats.reserved[3] += now_ms() - t_sp1;       // host: indel identity maps, haplotype links
     bs.sparse_built = true;
     return 0;
 }
@@ -1333,7 +1338,7 @@ static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
     if ((rc = backend_alloc(ctx, bs, &d, (size_t)v.n_pos * sizeof(int32_t), false)) != 0) { return rc; }
     sv.cand_list = (int32_t*)d;
     int64_t cap = v.n_pos / 16 + 4096;
-    StageVec<VarRec> recs;
+    StageVec<VarRec> & recs = bs.recs;
     for (int attempt = 0; attempt < 2; attempt++) {
         if ((rc = backend_alloc(ctx, bs, &d, (size_t)cap * sizeof(VarRec), false)) != 0) { return rc; }
         sv.out = (VarRec*)d; sv.out_cap = (int32_t)cap;
@@ -1355,10 +1360,12 @@ static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
     if ((rc = backend_download(ctx, bs.gextra.data(), sv.gextra, bs.gextra.size() * sizeof(GvcfExtra))) != 0) { return rc; }
     bs.stats.d2h_bytes += (int64_t)(recs.size() * sizeof(VarRec) + bs.gvcf.size() * sizeof(GvcfPos) + bs.gextra.size() * sizeof(GvcfExtra));
     const double t2 = now_ms();
-    bs.recs_by_tile.assign(bs.hb.tiles.size(), std::vector<VarRec>());
-    for (const auto & r : recs) { bs.recs_by_tile[(size_t)r.tile].push_back(r); }
+    bs.recs_by_tile.assign(bs.hb.tiles.size(), std::vector<const VarRec*>());
+    for (const auto & r : recs) { bs.recs_by_tile[(size_t)r.tile].push_back(&r); }
     bs.stats.n_vcf_records = (int64_t)recs.size();
     bs.stats.host_score_ms = (t1 - t0) + (now_ms() - t2);
+    bs.stats.reserved[4] += t1 - t0;                // host: indel allele table
+    bs.stats.reserved[5] += t2 - t1;                // scoring kernels and the downloads of their results
     bs.scored = true;
     return 0;
 }

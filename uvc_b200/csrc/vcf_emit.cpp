@@ -222,7 +222,7 @@ void uvc_build_indel_sites(std::vector<TileIndelSites> & sites, std::vector<Inde
 }
 
 std::string uvc_tile_vcf_text(const HostBatch & hb, int32_t tile_index, const uvcgpu_params & par, const std::string & tname, const HostContig & contig,
-        const std::vector<VarRec> & recs, const TileIndelSites & sites, const TileSparse & sparse, const StageVec<IndelEvent> & ev,
+        const std::vector<const VarRec*> & recs, const TileIndelSites & sites, const TileSparse & sparse, const StageVec<IndelEvent> & ev,
         const GvcfPos *gvcf, const GvcfExtra *gextra) {
     std::string out;
     const TileInfo & T = hb.tiles[tile_index];
@@ -233,7 +233,7 @@ std::string uvc_tile_vcf_text(const HostBatch & hb, int32_t tile_index, const uv
     out.reserve(recs.size() * 3200 + (size_t)(T.end_pos - T.beg_pos) * 24 + 4096);
     // records grouped by (zero-based position, symbol type) in the device's candidate order
     std::map<std::pair<int32_t, int32_t>, std::vector<const VarRec*>> by_zb;
-    for (const auto & r : recs) { by_zb[std::make_pair(r.symboltype == 0 ? r.refpos + 1 : r.refpos, r.symboltype)].push_back(&r); }
+    for (const VarRec *r : recs) { by_zb[std::make_pair(r->symboltype == 0 ? r->refpos + 1 : r->refpos, r->symboltype)].push_back(r); }
     for (auto & kv : by_zb) {
         // the device appends with an atomic cursor: restore the reference's candidate order
         std::stable_sort(kv.second.begin(), kv.second.end(), [](const VarRec *a, const VarRec *b) { return a->cand_index < b->cand_index; });

@@ -29,7 +29,7 @@ void uvc_build_indel_sites(std::vector<TileIndelSites> & sites, std::vector<Inde
 
 // The uncompressed VCF fragment of one tile (what process_batch appends to uncompressed_vcf_string, main.cpp:1184).
 std::string uvc_tile_vcf_text(const HostBatch & hb, int32_t tile_index, const uvcgpu_params & par, const std::string & tname, const HostContig & contig,
-        const std::vector<VarRec> & recs_of_tile, const TileIndelSites & sites, const TileSparse & sparse, const StageVec<IndelEvent> & ev,
+        const std::vector<const VarRec*> & recs_of_tile, const TileIndelSites & sites, const TileSparse & sparse, const StageVec<IndelEvent> & ev,
         const GvcfPos *gvcf, const GvcfExtra *gextra);
 
 #endif
