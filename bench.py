@@ -497,10 +497,10 @@ def main():
         agg[k] //= args.steps
 
     # ---- phase 2: end to end from host buffers: sub-batches pipelined over a few contexts (streams)
-    # (two sub-batches are in flight per context: deep panels have few, large sub-batches - the contexts are limited so that about 12 M reads
+    # (two sub-batches are in flight per context: deep panels have few, large sub-batches - the contexts are limited so that about 28 M reads
     #  are in flight at most, which keeps the column caches of all of them inside the 180 GB of HBM)
     reads_per_sub = max(1, n_records // max(1, len(subs)))
-    n_ctx = max(1, min(args.contexts, len(subs), max(1, 6_000_000 // reads_per_sub)))
+    n_ctx = max(1, min(args.contexts, len(subs), max(1, 14_000_000 // reads_per_sub)))
     ctxs = [ctx0] + [make_ctx(max(1, host_threads // n_ctx + 1)) for _ in range(n_ctx - 1)]
     ctx0.lib.uvcgpu_set_host_threads(ctx0.handle, max(1, host_threads // n_ctx + 1))
     totals = {"h2d": 0, "d2h": 0, "vcf": 0, "rec": 0, "launch": 0, "prep_ms": 0.0, "sync_ms": 0.0, "stage_call_ms": 0.0, "sc2": 0.0, "sc3": 0.0, "sc4": 0.0, "sc5": 0.0, "submit_s": 0.0, "wait_s": 0.0, "score_s": 0.0, "text_s": 0.0, "release_s": 0.0}
