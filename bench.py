@@ -246,6 +246,9 @@ def decode_sub_batches(ds, tiles, n_sub, threads, only=None):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of one GPU during the timed regions. In-process NVML queries (a few microseconds each): spawning
+    nvidia-smi ten times a second per rank takes driver-wide locks and measurably stalls the CUDA calls of every process on the box."""
+
     def __init__(self, gpu_index: int):
         super().__init__(daemon=True)
         self.gpu_index = gpu_index
@@ -253,8 +256,33 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.stop_flag = False
         self.sm_max = None
+        self.how = "nvml"
 
     def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu_index
+            if visible:      # NVML enumerates all GPUs of the box; map the CUDA ordinal through CUDA_VISIBLE_DEVICES when it is a list of indices
+                try:
+                    idx = int(visible.split(",")[self.gpu_index])
+                except Exception:
+                    idx = self.gpu_index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = [("hw_slowdown", pynvml.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", pynvml.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", pynvml.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", pynvml.nvmlClocksEventReasonSwPowerCap)]
+            while not self.stop_flag:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for n, bit in names:
+                    if r & bit:
+                        self.reasons.add(n)
+                time.sleep(0.1)
+            return
+        except Exception:
+            self.how = "nvidia-smi"
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -269,11 +297,11 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(1.0)
 
     def summary(self):
         s = sorted(self.samples)
-        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(s)}
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(s), "how": self.how}
 
 
 # ------------------------------------------------------------------------------------------------ reference arm / CPU baseline

@@ -503,7 +503,9 @@ UVC_DEFINE_KERNEL(uvc_k4a_family_ends, uvc::k4a_family_strand(v, i))
 // ahead (ring of 3), entries one chunk ahead (ring of 2, issued as soon as the chunk's records have landed), so the entry loads of chunk
 // i + 1 are in flight during all of the work on chunk i. Commit order: R0 R1 E0 | R2 E1 | R3 E2 | ...; waiting for "all but the most recent
 // group" after committing R(i+2) guarantees R(i+1) and E(i).
+#ifndef UVC_COL_READS
 #define UVC_COL_READS 16
+#endif
 __device__ __forceinline__ void uvc_cp_async8(void *smem_dst, const void *gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gmem_src) : "memory");
