@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(128) uvc_k0_read_consts(const BatchView v, int
 // starts on a 16-byte boundary (record sizes are multiples of 4 bytes) and is copied with 16-byte asynchronous copies; the copy of chunk
 // i + 1 is in flight while chunk i is processed.
 #ifndef UVC_STAGE_READS
-#define UVC_STAGE_READS 24    // a multiple of 8 (gather groups) and of 4 (16-byte slices)
+#define UVC_STAGE_READS 16    // a multiple of 8 (gather groups) and of 4 (16-byte slices)
 #endif
 __device__ __forceinline__ void uvc_cp_async16(void *smem_dst, const void *gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -504,7 +504,7 @@ UVC_DEFINE_KERNEL(uvc_k4a_family_ends, uvc::k4a_family_strand(v, i))
 // i + 1 are in flight during all of the work on chunk i. Commit order: R0 R1 E0 | R2 E1 | R3 E2 | ...; waiting for "all but the most recent
 // group" after committing R(i+2) guarantees R(i+1) and E(i).
 #ifndef UVC_COL_READS
-#define UVC_COL_READS 16
+#define UVC_COL_READS 8     // measured (tools/gpu_variants.sh): 8-read chunks leave room for five K3b blocks per SM (3.70 vs 4.05 ms per sub-batch)
 #endif
 __device__ __forceinline__ void uvc_cp_async8(void *smem_dst, const void *gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -519,7 +519,7 @@ __device__ __forceinline__ int uvc_chunk_len(int64_t cb, int64_t uhi) { return (
 // K3b: records = ReadFrag (written by K3a). The quality histograms of the two hot symbols live in shared memory ([bucket][thread]: conflict-free,
 // updated with reductions), their depth counters in registers.
 #ifndef UVC_K3B_MINBLOCKS
-#define UVC_K3B_MINBLOCKS 4    // 96 registers, no spills
+#define UVC_K3B_MINBLOCKS 5    // 88 registers; five blocks per SM with 8-read chunks
 #endif
 __global__ void __launch_bounds__(128, UVC_K3B_MINBLOCKS) uvc_k3b_fragment_consensus(const BatchView v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
