@@ -279,7 +279,7 @@ class ClockSampler(threading.Thread):
                 for n, bit in names:
                     if r & bit:
                         self.reasons.add(n)
-                time.sleep(0.1)
+                time.sleep(0.25)
             return
         except Exception:
             self.how = "nvidia-smi"

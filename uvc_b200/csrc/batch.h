@@ -89,6 +89,8 @@ struct alignas(16) PileRec {
     uint32_t seq_off, qual_off; int32_t cx_off; uint32_t terms_lo;    // cx_off: simple reads keep m_qoff here; terms_lo = xm_term | bm_term[0] << 7 | bm_term[1] << 14 | bm_term[2] << 21
     uint32_t terms_hi; int32_t ibeg, iend; int32_t l_qseq;           // terms_hi = bm_term[3] | bm_term[4] << 7
 };
+// What the prep-set walk (kernel K1) needs from a read beyond PileRec, 32 bytes, written by K0
+struct alignas(16) PrepRec { int32_t xm1500, go1500, avg_gaplen, inslen_sum, dellen_sum, insbaq_sum, delbaq_sum; uint32_t flags; };   // flags bit 0: duplexflag & 0x4
 #define UVC_PR_ISRC 0x1u            // flag & 0x10
 #define UVC_PR_PAIRED 0x2u          // flag & 0x1
 #define UVC_PR_MATE_UNMAPPED 0x4u   // flag & 0x8
@@ -219,6 +221,7 @@ struct BatchView {
     const ReadRec *reads;
     ReadDerived *rd;
     PileRec *prec;                 // [n_reads], kernel K0
+    PrepRec *qrec;                 // [n_reads], kernel K0
     const uint8_t *seq;
     uint8_t *qual;                 // per kept read: its base qualities after the reference's quality fix-ups (grouping.cpp:459-543), written by K0
     const uint8_t *qual_raw;       // base qualities as uploaded (a record that two tiles keep is shared here)

@@ -97,6 +97,7 @@ struct uvcgpu_ctx {
     cudaStream_t prep_stream = nullptr;   // staging kernels (stages P0/P1) of a batch and their two short synchronisations: they depend on nothing that the
                                           // pileup kernels of the previous batch compute, so they do not queue behind them
     cudaStream_t post_stream = nullptr;   // everything after collect (scoring kernels, downloads) of a batch, so that it does not queue behind the next batch
+    cudaEvent_t wait_ev[3] = {nullptr, nullptr, nullptr};   // blocking-sync events the host waits on (one per stream)
     cudaStream_t active = nullptr;        // the stream the backend helpers use: `stream`, or `post_stream` inside PostScope
 #endif
 };
@@ -298,27 +299,6 @@ template <class T> __device__ __forceinline__ void uvc_warp_stage_async(T *dst, 
     for (int k = lane; k < n16; k += 32) { uvc_cp_async16(d + 16 * k, g + 16 * k); }
 }
 
-// role-0 style gather of the (base, quality) byte pairs of a staged chunk, in groups of 8 reads: all 16 byte loads of a group are issued
-// before the first one is consumed (memory-level parallelism instead of one dependent load pair per read)
-__device__ __forceinline__ void uvc_gather_bases(const BatchView & v, const ReadRec *sR, uint16_t (*bq)[32], int nc, int64_t cb, const uvc::Win & w, int32_t p, bool active, int lane) {
-    for (int k0 = 0; k0 < nc; k0 += 8) {
-        int32_t qp[8];
-        uint32_t sb[8], qb[8];
-        #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int k = (k0 + j < nc ? k0 + j : nc - 1);
-            const int64_t ri = cb + k;
-            const ReadRec & R = sR[k];
-            qp[j] = uvc::base_index(v, R, p, active && ri >= w.lo && ri < w.hi);
-            const int32_t qc = (qp[j] > 0 ? qp[j] : 0);
-            sb[j] = v.seq[R.seq_off + (uint32_t)(qc >> 1)];
-            qb[j] = v.qual[R.qual_off + (uint32_t)qc];
-        }
-        #pragma unroll
-        for (int j = 0; j < 8; j++) { bq[k0 + j][lane] = (uint16_t)uvc::pack_base(sb[j], qb[j], qp[j]); }
-    }
-}
-
 // ---- bulk asynchronous copies (TMA unit, cp.async.bulk) completed on an mbarrier: one elected lane moves a whole chunk of records
 __device__ __forceinline__ void uvc_mbar_init(uint64_t *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
@@ -346,7 +326,8 @@ __device__ __forceinline__ void uvc_mbar_wait(uint64_t *bar, unsigned parity) {
                  "}" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
-// gather of the (base, quality) byte pairs of a staged chunk of compact records, in groups of 8 reads (see uvc_gather_bases)
+// gather of the (base, quality) byte pairs of a staged chunk of compact records, in groups of 8 reads: all 16 byte loads of a group are issued
+// before the first one is consumed (memory-level parallelism instead of one dependent load pair per read)
 __device__ __forceinline__ void uvc_gather_bases_p(const BatchView & v, const PileRec *sP, uint16_t (*bq)[32], int nc, int64_t cb, const uvc::Win & w, int32_t p, bool active, int lane) {
     for (int k0 = 0; k0 < nc; k0 += 8) {
         int32_t qp[8];
@@ -418,48 +399,48 @@ __global__ void __launch_bounds__(128, UVC_K2_MINBLOCKS) uvc_k2_bias_pileup(cons
     }
     if (active) { uvc::k2m_flush(st, v); }
 }
-// staging slot of K1: full per-read records (ReadRec + ReadDerived), double-buffered with cp.async
-struct __align__(16) K2Stage {
-    ReadRec R[2][UVC_STAGE_READS];
-    ReadDerived D[2][UVC_STAGE_READS];
+// K1: one thread per position; the compact records of UVC_STAGE_READS reads per warp (PileRec + PrepRec, two bulk asynchronous copies on one
+// mbarrier, one chunk ahead) and the same grouped byte gather as K2
+struct __align__(16) K1StageP {
+    PileRec P[2][UVC_STAGE_READS];
+    PrepRec Q[2][UVC_STAGE_READS];
     uint16_t bq[UVC_STAGE_READS][32];
+    uint64_t bar[2];
 };
-// K1: one thread per position; same staging as K2 (the records of UVC_STAGE_READS reads per warp, one chunk ahead) and the same grouped byte gather
 __global__ void __launch_bounds__(128) uvc_k1_prep_thres(const BatchView v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
     const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    K2Stage & S = ((K2Stage*)uvc_smem)[warp];
+    K1StageP & S = ((K1StageP*)uvc_smem)[warp];
     const bool active = (gp < n);
+    if (0 == lane) { uvc_mbar_init(&S.bar[0], 1); uvc_mbar_init(&S.bar[1], 1); uvc_mbar_fence_init(); }
+    __syncwarp();
     uvc::Win w;
     uvc_warp_window(v, gp, active, w);
     uvc::K1State st;
     st.p = 0;
     if (active) { uvc::k1_begin(st, v, gp); }
-    const int64_t c0 = w.ulo & ~(int64_t)3;
-    if (c0 < w.uhi) {
-        const int nc0 = (int)(w.uhi - c0 < UVC_STAGE_READS ? w.uhi - c0 : UVC_STAGE_READS);
-        uvc_warp_stage_async(S.R[0], v.reads, c0, nc0, lane);
-        uvc_warp_stage_async(S.D[0], v.rd, c0, nc0, lane);
-    }
-    uvc_cp_async_commit();
+    const int64_t c0 = w.ulo;
+    auto issue = [&](int64_t cb, int buf) {
+        if (cb < w.uhi && 0 == lane) {
+            const unsigned cnt = (unsigned)(w.uhi - cb < UVC_STAGE_READS ? w.uhi - cb : UVC_STAGE_READS);
+            uvc_mbar_expect_tx(&S.bar[buf], cnt * (unsigned)(sizeof(PileRec) + sizeof(PrepRec)));
+            uvc_bulk_g2s(S.P[buf], v.prec + cb, cnt * (unsigned)sizeof(PileRec), &S.bar[buf]);
+            uvc_bulk_g2s(S.Q[buf], v.qrec + cb, cnt * (unsigned)sizeof(PrepRec), &S.bar[buf]);
+        }
+    };
+    issue(c0, 0);
+    unsigned phase0 = 0, phase1 = 0;
     int buf = 0;
     for (int64_t cb = c0; cb < w.uhi; cb += UVC_STAGE_READS, buf ^= 1) {
         const int nc = (int)(w.uhi - cb < UVC_STAGE_READS ? w.uhi - cb : UVC_STAGE_READS);
-        const int64_t nb = cb + UVC_STAGE_READS;
-        if (nb < w.uhi) {
-            const int nn = (int)(w.uhi - nb < UVC_STAGE_READS ? w.uhi - nb : UVC_STAGE_READS);
-            uvc_warp_stage_async(S.R[buf ^ 1], v.reads, nb, nn, lane);
-            uvc_warp_stage_async(S.D[buf ^ 1], v.rd, nb, nn, lane);
-        }
-        uvc_cp_async_commit();
-        uvc_cp_async_wait<1>();
-        __syncwarp();
-        const ReadRec *sR = S.R[buf];
-        const ReadDerived *sD = S.D[buf];
-        uvc_gather_bases(v, sR, S.bq, nc, cb, w, st.p, active, lane);
+        issue(cb + UVC_STAGE_READS, buf ^ 1);
+        if (buf) { uvc_mbar_wait(&S.bar[1], phase1); phase1 ^= 1u; } else { uvc_mbar_wait(&S.bar[0], phase0); phase0 ^= 1u; }
+        const PileRec *sP = S.P[buf];
+        const PrepRec *sQ = S.Q[buf];
+        uvc_gather_bases_p(v, sP, S.bq, nc, cb, w, st.p, active, lane);
         if (active) {
-            for (int k = 0; k < nc; k++) { uvc::k1_read(st, v, sR[k], sD[k], (uint32_t)S.bq[k][lane]); }   // lanes outside their own window hold NOBASE
+            for (int k = 0; k < nc; k++) { uvc::k1_read(st, v, sP[k], sQ[k], (uint32_t)S.bq[k][lane]); }   // lanes outside their own window hold NOBASE
         }
         __syncwarp();
     }
@@ -707,6 +688,15 @@ static void launch(uvc_kernel_t k, cudaStream_t s, const BatchView & v, int64_t 
     launches++;
 }
 
+// Waits of the host for a stream go through an event created with cudaEventBlockingSync: the waiting thread sleeps instead of spinning on a
+// core (several contexts per GPU and several ranks per box wait at the same time, and the cores are needed for record copies and VCF text).
+static int backend_wait_stream(uvcgpu_ctx *ctx, cudaStream_t s) {
+    cudaEvent_t & e = (s == ctx->stream ? ctx->wait_ev[0] : (s == ctx->prep_stream ? ctx->wait_ev[1] : ctx->wait_ev[2]));
+    if (NULL == e) { UVC_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&e, cudaEventBlockingSync | cudaEventDisableTiming)); }
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(e, s));
+    UVC_CUDA_CHECK(ctx, cudaEventSynchronize(e));
+    return 0;
+}
 static int backend_alloc(uvcgpu_ctx *ctx, BatchState & bs, void **out, size_t bytes, bool zero) {
     bytes += 64;     // slack: staged record slices are rounded up to 16 bytes, and clamped byte loads may touch offset 0 of an empty blob
     UVC_CUDA_CHECK(ctx, cudaMallocAsync(out, bytes, ctx->active));   // stream-ordered pool: no device synchronisation, blocks are reused across batches
@@ -719,7 +709,7 @@ static int backend_upload(uvcgpu_ctx *ctx, BatchState & bs, void *dst, const voi
     return 0;
 }
 static int backend_download(uvcgpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
-    if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->active)); UVC_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->active)); }
+    if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->active)); const int rc_ = backend_wait_stream(ctx, ctx->active); if (rc_ != 0) { return rc_; } }
     return 0;
 }
 static void backend_free_temps(uvcgpu_ctx *ctx, BatchState & bs) { for (void *p : bs.temp_allocs) { cudaFreeAsync(p, ctx->active); } bs.temp_allocs.clear(); }
@@ -741,7 +731,7 @@ static int backend_alloc_temp(uvcgpu_ctx *ctx, BatchState & bs, void **out, size
 static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     const BatchView & v = bs.view;
     int64_t launches = 0;
-    for (int i = 0; i < UVC_N_PILEUP_STAGES + 1; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreate(&bs.ev[i])); }
+    for (int i = 0; i < UVC_N_PILEUP_STAGES + 1; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&bs.ev[i], cudaEventBlockingSync)); }
     bs.have_events = true;
     int e = 0;
     // Threads per block of the position kernels (every warp is self-contained: its own staging slot, no block-wide synchronisation). A batch
@@ -753,7 +743,8 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     #define UVC_STAGE(kernel, n) { launch(kernel, ctx->stream, v, (n), launches); UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream)); }
     UVC_STAGE(uvc_k0_read_consts, v.n_reads)
     if (v.n_pos > 0) {
-        const size_t smem = 4 * sizeof(K2Stage);
+        static_assert(sizeof(K1StageP) % 16 == 0 && sizeof(PrepRec) == 32, "per-warp staging slots keep 16-byte alignment");
+        const size_t smem = 4 * sizeof(K1StageP);
         UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k1_prep_thres, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         uvc_k1_prep_thres<<<(unsigned)((v.n_pos + pb - 1) / pb), pb, smem * pb / 128, ctx->stream>>>(v, v.n_pos);
         launches++;
@@ -803,7 +794,7 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
 static int backend_wait(uvcgpu_ctx *ctx, BatchState & bs) {
     // only this batch's last kernel is waited for: a later batch may already be queued on the stream
     if (bs.have_events) { UVC_CUDA_CHECK(ctx, cudaEventSynchronize(bs.ev[UVC_N_PILEUP_STAGES])); }
-    else { UVC_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); }
+    else { const int rc_ = backend_wait_stream(ctx, ctx->stream); if (rc_ != 0) { return rc_; } }
     if (bs.have_events) {
         float ms = 0;
         double total = 0;
@@ -831,7 +822,7 @@ static int backend_wait(uvcgpu_ctx *ctx, BatchState & bs) {
 static int backend_score(uvcgpu_ctx *ctx, BatchState & bs, const ScoreView & sv) {
     const BatchView & v = bs.view;
     cudaEvent_t e[3];
-    for (int i = 0; i < 3; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreate(&e[i])); }
+    for (int i = 0; i < 3; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&e[i], cudaEventBlockingSync)); }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(e[0], ctx->active));
     if (v.n_pos > 0) { uvc_k6_gvcf_inputs<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, ctx->active>>>(v, sv, v.n_pos); }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(e[1], ctx->active));
@@ -839,7 +830,7 @@ static int backend_score(uvcgpu_ctx *ctx, BatchState & bs, const ScoreView & sv)
     if (v.n_pos > 0) { uvc_k5_score_candidates<<<(unsigned)((v.n_pos + 63) / 64), 64, 0, ctx->active>>>(v, sv, v.n_pos); }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(e[2], ctx->active));
     UVC_CUDA_CHECK(ctx, cudaGetLastError());
-    UVC_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->active));
+    { const int rc_ = backend_wait_stream(ctx, ctx->active); if (rc_ != 0) { return rc_; } }
     float ms = 0;
     UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, e[0], e[1])); bs.stats.kernel_ms_by_stage[11] = ms; bs.stats.kernel_ms += ms;
     UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, e[1], e[2])); bs.stats.kernel_ms_by_stage[12] = ms; bs.stats.kernel_ms += ms;
@@ -1116,6 +1107,7 @@ void uvcgpu_destroy(uvcgpu_ctx *ctx) {
     cudaDeviceSynchronize();
     for (auto & kv : ctx->d_contigs) { cudaFree(kv.second); }
     cudaFree(ctx->c_phred2prob); cudaFree(ctx->c_pf_tab); cudaFree(ctx->c_slip_tab);
+    for (auto & e : ctx->wait_ev) { if (e) { cudaEventDestroy(e); } }
     if (ctx->post_stream) { cudaStreamDestroy(ctx->post_stream); }
     if (ctx->prep_stream) { cudaStreamDestroy(ctx->prep_stream); }
     if (ctx->stream) { cudaStreamDestroy(ctx->stream); }
@@ -1233,6 +1225,7 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
     { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_mcol * sizeof(FamCol), false)); v.mcol = (FamCol*)d_; }
     UVC_ZERO(rd, ReadDerived, v.n_reads)
     { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_reads * sizeof(PileRec), false)); v.prec = (PileRec*)d_; }
+    { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_reads * sizeof(PrepRec), false)); v.qrec = (PrepRec*)d_; }
     UVC_ZERO(rfrag, ReadFrag, v.n_reads)
     UVC_ZERO(cx, CxEntry, v.n_cx)
     UVC_ZERO(ev, IndelEvent, v.n_ev)
@@ -1485,7 +1478,7 @@ int uvcgpu_release(uvcgpu_ctx *ctx, uvcgpu_ticket ticket) {
     if (it == ctx->batches.end()) { return UVCGPU_EINVAL; }
     if (!it->second->collected) { backend_wait(ctx, *it->second); }   // (a collected batch has nothing left on the submit stream)
 #if UVC_CUDA
-    cudaStreamSynchronize(ctx->post_stream);                           // idle unless a scoring call failed half-way
+    backend_wait_stream(ctx, ctx->post_stream);                        // idle unless a scoring call failed half-way
 #endif
     backend_free(ctx, *it->second);
     ctx->batches.erase(it);

@@ -380,6 +380,10 @@ UVC_HD void k0_read(const BatchView & v, int64_t ri, const uint8_t *seq_ro = NUL
         P.ibeg = D.ibeg; P.iend = D.iend;
         P.l_qseq = R.l_qseq;
         v.prec[ri] = P;
+        PrepRec Q;
+        Q.xm1500 = D.xm1500; Q.go1500 = D.go1500; Q.avg_gaplen = D.avg_gaplen; Q.inslen_sum = D.inslen_sum; Q.dellen_sum = D.dellen_sum;
+        Q.insbaq_sum = D.insbaq_sum; Q.delbaq_sum = D.delbaq_sum; Q.flags = ((R.dflag & 0x4) ? 1u : 0u);
+        v.qrec[ri] = Q;
     }
 
     if (!R.simple) {
@@ -499,33 +503,32 @@ UVC_HD void k1_begin(K1State & s, const BatchView & v, int64_t gp) {
     s.a = v.prep[gp];     // starts from the rare-event contributions of K0
     s.baq_p = v.baq[gp];
 }
-// one read of the window; `packed` = (symbol << 8) | quality of its aligned base at p, UVC_K2_NOBASE if it shows none
-UVC_HD void k1_read(K1State & s, const BatchView & v, const ReadRec & R, const ReadDerived & D, uint32_t packed) {
+// one read of the window, from its compact records; `packed` = (symbol << 8) | quality of its aligned base at p, UVC_K2_NOBASE if it shows none
+UVC_HD void k1_read(K1State & s, const BatchView & v, const PileRec & P, const PrepRec & Q, uint32_t packed) {
     if (packed == UVC_K2_NOBASE) { return; }
     uvcgpu_prep_set & a = s.a;
     const int32_t p = s.p;
-    const int32_t span = R.rend - R.pos;
-    a.a_pcr_dp += ((R.dflag & 0x4) ? 1 : 0);
-    a.a_umi_dp += ((R.dflag & 0x1) ? 1 : 0);
+    const int32_t span = P.rend - P.pos;
+    a.a_pcr_dp += (int32_t)(Q.flags & 1u);
+    a.a_umi_dp += ((P.bits & UVC_PR_UMI) ? 1 : 0);
     a.a_dp += 1;
     a.a_qlen += span;
-    a.a_XM1500 += D.xm1500; a.a_GO1500 += D.go1500; a.a_GAPLEN += D.avg_gaplen;
+    a.a_XM1500 += Q.xm1500; a.a_GO1500 += Q.go1500; a.a_GAPLEN += Q.avg_gaplen;
     // (conditions as 0/1 factors instead of branches, as in segbias)
     {
-        const int32_t fl = tmin(R.pos, R.mpos);
-        const int32_t has = ((R.isize != 0) ? 1 : 0), rc = ((R.flag & 0x10) ? 1 : 0);
+        const int32_t has = ((P.bits & UVC_PR_HAS_ISIZE) ? 1 : 0), rc = ((P.bits & UVC_PR_ISRC) ? 1 : 0);
         const int32_t li = has * rc, ri = has * (1 - rc);
-        a.a_LI += (int64_t)(li * tmin(p - fl + 1, UVC_MAX_INSERT_SIZE)); a.a_LIDP += li;
-        a.a_RI += (int64_t)(ri * tmin(fl + iabs(R.isize) - p, UVC_MAX_INSERT_SIZE)); a.a_RIDP += ri;
+        a.a_LI += (int64_t)(li * tmin(p - P.frag_l + 1, UVC_MAX_INSERT_SIZE)); a.a_LIDP += li;
+        a.a_RI += (int64_t)(ri * tmin(P.frag_r - p, UVC_MAX_INSERT_SIZE)); a.a_RIDP += ri;
     }
     {
         const int32_t hq = (((int32_t)(packed & 0xffu) >= v.par.bias_thres_highBQ) ? 1 : 0);
-        a.a_l_dist_sum += hq * (p - R.pos + 1);
-        a.a_r_dist_sum += hq * (R.rend - p);
-        a.a_inslen_sum += hq * D.inslen_sum; a.a_dellen_sum += hq * D.dellen_sum;
-        a.a_l_BAQ_sum += (int64_t)(hq * (s.baq_p - D.baq_pos + 1));
-        a.a_r_BAQ_sum += (int64_t)(hq * (D.baq_rend1 - s.baq_p + 1));
-        a.a_insBAQ_sum += (int64_t)(hq * D.insbaq_sum); a.a_delBAQ_sum += (int64_t)(hq * D.delbaq_sum);
+        a.a_l_dist_sum += hq * (p - P.pos + 1);
+        a.a_r_dist_sum += hq * (P.rend - p);
+        a.a_inslen_sum += hq * Q.inslen_sum; a.a_dellen_sum += hq * Q.dellen_sum;
+        a.a_l_BAQ_sum += (int64_t)(hq * (s.baq_p - P.baq_pos + 1));
+        a.a_r_BAQ_sum += (int64_t)(hq * (P.baq_rend1 - s.baq_p + 1));
+        a.a_insBAQ_sum += (int64_t)(hq * Q.insbaq_sum); a.a_delBAQ_sum += (int64_t)(hq * Q.delbaq_sum);
         a.a_highBQ_dp += hq;
     }
 }
@@ -535,9 +538,9 @@ UVC_HD void k1_position(const BatchView & v, int64_t gp, const Win & w) {
     k1_begin(s, v, gp);
     for (int64_t ri = w.ulo; ri < w.uhi; ri++) {
         if (ri < w.lo || ri >= w.hi) { continue; }
-        const ReadRec & R = v.reads[ri];
-        const int32_t qpos = base_index(v, R, s.p, true);
-        k1_read(s, v, R, v.rd[ri], pack_base(0, v.qual[R.qual_off + (uint32_t)tmax(qpos, 0)], qpos));
+        const PileRec & P = v.prec[ri];
+        const int32_t qpos = base_index(v, P, s.p, true);
+        k1_read(s, v, P, v.qrec[ri], pack_base(0, v.qual[(uint64_t)P.qual_off + (uint32_t)tmax(qpos, 0)], qpos));
     }
     k1_end(s, v);
 }
