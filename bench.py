@@ -62,7 +62,7 @@ def parse_args():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--scale", type=float, default=None, help="fraction of the named config's region (default: per-config)")
     ap.add_argument("--workdir", default=os.environ.get("UVC_BENCH_DIR", "/tmp/uvc_bench"))
-    ap.add_argument("--contexts", type=int, default=4, help="contexts (CUDA streams) the e2e step pipelines its sub-batches over")
+    ap.add_argument("--contexts", type=int, default=8, help="contexts (CUDA streams) the e2e step pipelines its sub-batches over: a context spends most of a sub-batch waiting (staging kernels, pileup, downloads), so several are needed to keep the GPU fed")
     ap.add_argument("--sub-batches", type=int, default=0, help="sub-batches per step (0: packed to ~512 k positions or 8 M reads each)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-pipeline", action="store_true", help="do not time the whole uvc1 program")
