@@ -35,7 +35,7 @@
 #define UVC_CUDA 0
 #endif
 
-#define UVC_N_PILEUP_STAGES 11   // K0, K1, K2, K2e, KF, K3a, K3b, KM, K4a, K4, K4c (kernel_ms_by_stage[0..10]); [11] = K6, [12] = K5
+#define UVC_N_PILEUP_STAGES 12   // K0, K1, K2, K2e, KF, K3a, K3b, KM, K4a, K4, K4c, K6 (kernel_ms_by_stage[0..11]); [12] = K5
 
 namespace {
 
@@ -68,6 +68,10 @@ struct BatchState {
     std::vector<std::vector<const VarRec*>> recs_by_tile; // the records of every tile (pointers into recs: a record is ~2 KB)
     StageVec<GvcfPos> gvcf;
     StageVec<GvcfExtra> gextra;
+    // K6's outputs and the cursor of the sparse record stream travel to the host at the end of the batch's own kernels (one wait: collect)
+    GvcfPos *d_gvcf = nullptr; GvcfExtra *d_gextra = nullptr;
+    StageVec<int32_t> rec_cursor_host, score_cursor_host;
+    StageVec<IndelAllele> allele_table;
 #if UVC_CUDA
     cudaEvent_t ev[UVC_N_PILEUP_STAGES + 1];
     bool have_events = false;
@@ -688,13 +692,25 @@ static void launch(uvc_kernel_t k, cudaStream_t s, const BatchView & v, int64_t 
     launches++;
 }
 
-// Waits of the host for a stream go through an event created with cudaEventBlockingSync: the waiting thread sleeps instead of spinning on a
-// core (several contexts per GPU and several ranks per box wait at the same time, and the cores are needed for record copies and VCF text).
+// Waits of the host: the event is polled with sleeps in between whose length grows with the time already waited (20 - 250 us). Measured
+// alternatives: cudaEventSynchronize on a default event spins on a core per waiting thread (contexts x ranks threads wait at the same time and
+// starve the record copies and the VCF text: 2-GPU e2e 39.9 M reads/s instead of 68.7 M); cudaEventBlockingSync sleeps until the driver's
+// interrupt arrives, which took up to hundreds of milliseconds per wait on some boxes (1-GPU e2e 7.4 - 48.6 M reads/s from run to run).
+static cudaError_t uvc_event_wait(cudaEvent_t e) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        const cudaError_t q = cudaEventQuery(e);
+        if (q != cudaErrorNotReady) { return q; }
+        const int64_t us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        if (us < 30) { std::this_thread::yield(); continue; }
+        std::this_thread::sleep_for(std::chrono::microseconds(us / 8 < 20 ? 20 : (us / 8 > 250 ? 250 : us / 8)));
+    }
+}
 static int backend_wait_stream(uvcgpu_ctx *ctx, cudaStream_t s) {
     cudaEvent_t & e = (s == ctx->stream ? ctx->wait_ev[0] : (s == ctx->prep_stream ? ctx->wait_ev[1] : ctx->wait_ev[2]));
-    if (NULL == e) { UVC_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&e, cudaEventBlockingSync | cudaEventDisableTiming)); }
+    if (NULL == e) { UVC_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(e, s));
-    UVC_CUDA_CHECK(ctx, cudaEventSynchronize(e));
+    UVC_CUDA_CHECK(ctx, uvc_event_wait(e));
     return 0;
 }
 static int backend_alloc(uvcgpu_ctx *ctx, BatchState & bs, void **out, size_t bytes, bool zero) {
@@ -708,10 +724,18 @@ static int backend_upload(uvcgpu_ctx *ctx, BatchState & bs, void *dst, const voi
     if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->active)); bs.stats.h2d_bytes += (int64_t)bytes; }
     return 0;
 }
-static int backend_download(uvcgpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
-    if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->active)); const int rc_ = backend_wait_stream(ctx, ctx->active); if (rc_ != 0) { return rc_; } }
+// downloads are enqueued (page-locked destinations) and waited for together: every wait of the host costs the turn-around of the stream behind
+// the pileup blocks of other batches that occupy the SMs
+static int backend_download_async(uvcgpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->active)); }
     return 0;
 }
+static int backend_sync(uvcgpu_ctx *ctx) { return backend_wait_stream(ctx, ctx->active); }
+static int backend_download(uvcgpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (bytes) { int rc_ = backend_download_async(ctx, dst, src, bytes); if (0 == rc_) { rc_ = backend_sync(ctx); } if (rc_ != 0) { return rc_; } }
+    return 0;
+}
+static int backend_zero(uvcgpu_ctx *ctx, void *dst, size_t bytes) { UVC_CUDA_CHECK(ctx, cudaMemsetAsync(dst, 0, bytes, ctx->active)); return 0; }
 static void backend_free_temps(uvcgpu_ctx *ctx, BatchState & bs) { for (void *p : bs.temp_allocs) { cudaFreeAsync(p, ctx->active); } bs.temp_allocs.clear(); }
 // A batch is released after everything of it has completed, while the submit stream may already hold the kernels of the next batch: freeing
 // there would make the blocks reusable only after those kernels (any stream that picks such a block up inherits the wait). The second stream of
@@ -731,7 +755,7 @@ static int backend_alloc_temp(uvcgpu_ctx *ctx, BatchState & bs, void **out, size
 static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     const BatchView & v = bs.view;
     int64_t launches = 0;
-    for (int i = 0; i < UVC_N_PILEUP_STAGES + 1; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&bs.ev[i], cudaEventBlockingSync)); }
+    for (int i = 0; i < UVC_N_PILEUP_STAGES + 1; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreate(&bs.ev[i])); }
     bs.have_events = true;
     int e = 0;
     // Threads per block of the position kernels (every warp is self-contained: its own staging slot, no block-wide synchronisation). A batch
@@ -786,6 +810,18 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
     UVC_STAGE(uvc_k4c_family_haplotypes, 2 * v.n_fams)
     #undef UVC_STAGE
+    {
+        // K6 needs nothing from the host: it and the downloads of its outputs and of the sparse stream's cursor ride behind the batch's kernels
+        ScoreView sv6;
+        memset(&sv6, 0, sizeof(sv6));
+        sv6.gvcf = bs.d_gvcf; sv6.gextra = bs.d_gextra;
+        if (v.n_pos > 0) { uvc_k6_gvcf_inputs<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, ctx->stream>>>(v, sv6, v.n_pos); launches++; }
+        UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(bs.gvcf.data(), bs.d_gvcf, bs.gvcf.size() * sizeof(GvcfPos), cudaMemcpyDeviceToHost, ctx->stream));
+        UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(bs.gextra.data(), bs.d_gextra, bs.gextra.size() * sizeof(GvcfExtra), cudaMemcpyDeviceToHost, ctx->stream));
+        UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(bs.rec_cursor_host.data(), v.rec_cursor, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
+        bs.stats.d2h_bytes += (int64_t)(bs.gvcf.size() * sizeof(GvcfPos) + bs.gextra.size() * sizeof(GvcfExtra) + 16);
+    }
     UVC_CUDA_CHECK(ctx, cudaGetLastError());
     bs.stats.gpu_launches += launches;
     return 0;
@@ -793,7 +829,7 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
 
 static int backend_wait(uvcgpu_ctx *ctx, BatchState & bs) {
     // only this batch's last kernel is waited for: a later batch may already be queued on the stream
-    if (bs.have_events) { UVC_CUDA_CHECK(ctx, cudaEventSynchronize(bs.ev[UVC_N_PILEUP_STAGES])); }
+    if (bs.have_events) { UVC_CUDA_CHECK(ctx, uvc_event_wait(bs.ev[UVC_N_PILEUP_STAGES])); }
     else { const int rc_ = backend_wait_stream(ctx, ctx->stream); if (rc_ != 0) { return rc_; } }
     if (bs.have_events) {
         float ms = 0;
@@ -821,21 +857,22 @@ static int backend_wait(uvcgpu_ctx *ctx, BatchState & bs) {
 
 static int backend_score(uvcgpu_ctx *ctx, BatchState & bs, const ScoreView & sv) {
     const BatchView & v = bs.view;
-    cudaEvent_t e[3];
-    for (int i = 0; i < 3; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&e[i], cudaEventBlockingSync)); }
+    cudaEvent_t e[2];
+    for (int i = 0; i < 2; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreate(&e[i])); }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(e[0], ctx->active));
-    if (v.n_pos > 0) { uvc_k6_gvcf_inputs<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, ctx->active>>>(v, sv, v.n_pos); }
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(e[1], ctx->active));
     if (v.n_pos > 0) { uvc_k5a_flag_candidates<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, ctx->active>>>(v, sv, v.n_pos); }
     if (v.n_pos > 0) { uvc_k5_score_candidates<<<(unsigned)((v.n_pos + 63) / 64), 64, 0, ctx->active>>>(v, sv, v.n_pos); }
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(e[2], ctx->active));
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(e[1], ctx->active));
     UVC_CUDA_CHECK(ctx, cudaGetLastError());
-    { const int rc_ = backend_wait_stream(ctx, ctx->active); if (rc_ != 0) { return rc_; } }
+    // the results the host always needs ride behind the kernels: the cursors and the first records
+    { int rc_ = backend_download_async(ctx, bs.score_cursor_host.data(), sv.out_cursor, 4 * sizeof(int32_t));
+      if (0 == rc_) { rc_ = backend_download_async(ctx, bs.recs.data(), sv.out, bs.recs.size() * sizeof(VarRec)); }
+      if (0 == rc_) { rc_ = backend_sync(ctx); }
+      if (rc_ != 0) { return rc_; } }
     float ms = 0;
-    UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, e[0], e[1])); bs.stats.kernel_ms_by_stage[11] = ms; bs.stats.kernel_ms += ms;
-    UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, e[1], e[2])); bs.stats.kernel_ms_by_stage[12] = ms; bs.stats.kernel_ms += ms;
-    for (int i = 0; i < 3; i++) { cudaEventDestroy(e[i]); }
-    if (v.n_pos > 0) { bs.stats.gpu_launches += 3; }
+    UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, e[0], e[1])); bs.stats.kernel_ms_by_stage[12] = ms; bs.stats.kernel_ms += ms;
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(e[i]); }
+    if (v.n_pos > 0) { bs.stats.gpu_launches += 2; }
     return 0;
 }
 
@@ -853,6 +890,9 @@ static int backend_upload(uvcgpu_ctx *, BatchState & bs, void *dst, const void *
     return 0;
 }
 static int backend_download(uvcgpu_ctx *, void *dst, const void *src, size_t bytes) { if (bytes) { memcpy(dst, src, bytes); } return 0; }
+static int backend_download_async(uvcgpu_ctx *ctx, void *dst, const void *src, size_t bytes) { return backend_download(ctx, dst, src, bytes); }
+static int backend_sync(uvcgpu_ctx *) { return 0; }
+static int backend_zero(uvcgpu_ctx *, void *dst, size_t bytes) { memset(dst, 0, bytes); return 0; }
 static void backend_free_temps(uvcgpu_ctx *, BatchState & bs) { for (void *p : bs.temp_allocs) { free(p); } bs.temp_allocs.clear(); }
 static void backend_free(uvcgpu_ctx *ctx, BatchState & bs) { backend_free_temps(ctx, bs); for (void *p : bs.allocs) { free(p); } bs.allocs.clear(); }
 static int backend_alloc_temp(uvcgpu_ctx *, BatchState & bs, void **out, size_t bytes, int fill = -1) {
@@ -881,14 +921,21 @@ static int backend_run(uvcgpu_ctx *, BatchState & bs) {
     for (int64_t i = 0; i < 2 * v.n_fams; i++) { uvc::k4a_family_strand(v, i); }
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k4_position(v, i, w); }
     for (int64_t i = 0; i < 2 * v.n_fams; i++) { uvc::k4c_family_strand(v, i); }
+    ScoreView sv6;
+    memset(&sv6, 0, sizeof(sv6));
+    sv6.gvcf = bs.d_gvcf; sv6.gextra = bs.d_gextra;
+    for (int64_t i = 0; i < v.n_pos; i++) { uvc::k6_gvcf_position(v, sv6, i); }
+    memcpy(bs.gvcf.data(), bs.d_gvcf, bs.gvcf.size() * sizeof(GvcfPos)); memcpy(bs.gextra.data(), bs.d_gextra, bs.gextra.size() * sizeof(GvcfExtra));
+    memcpy(bs.rec_cursor_host.data(), v.rec_cursor, 4 * sizeof(int32_t));
     return 0;
 }
 static int backend_wait(uvcgpu_ctx *, BatchState &) { return 0; }
 static int backend_score(uvcgpu_ctx *, BatchState & bs, const ScoreView & sv) {
     const BatchView & v = bs.view;
-    for (int64_t i = 0; i < v.n_pos; i++) { uvc::k6_gvcf_position(v, sv, i); }
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::k5a_flag_position(v, sv, i); }
     for (int64_t i = 0; i < (int64_t)*sv.cand_cursor; i++) { uvc::k5_score_position(v, sv, (int64_t)sv.cand_list[i]); }
+    memcpy(bs.score_cursor_host.data(), sv.out_cursor, 4 * sizeof(int32_t));
+    memcpy(bs.recs.data(), sv.out, bs.recs.size() * sizeof(VarRec));
     return 0;
 }
 
@@ -1242,6 +1289,9 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
     v.rec_cap = (int32_t)std::min<int64_t>((int64_t)1 << 30, 16 * v.n_reads + (1 << 20));
     UVC_ZERO(rec_buf, int32_t, v.rec_cap)
     UVC_ZERO(rec_cursor, int32_t, 4)
+    { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_pos * sizeof(GvcfPos), true)); bs->d_gvcf = (GvcfPos*)d_; }
+    { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_pos * sizeof(GvcfExtra), true)); bs->d_gextra = (GvcfExtra*)d_; }
+    bs->gvcf.resize((size_t)v.n_pos); bs->gextra.resize((size_t)v.n_pos); bs->rec_cursor_host.assign(4, 0);
     const double t2 = now_ms();
     UVC_TRY(backend_run(ctx, *bs));
     uvcgpu_batch_stats & st = bs->stats;
@@ -1286,16 +1336,15 @@ static int ensure_sparse(uvcgpu_ctx *ctx, BatchState & bs) {
     if (bs.sparse_built) { return 0; }
     PostScope post_scope(ctx);
     const BatchView & v = bs.view;
-    int32_t cursor[4] = {0, 0, 0, 0};
-    int rc = backend_download(ctx, cursor, v.rec_cursor, sizeof(cursor));
-    if (rc != 0) { return rc; }
+    const int32_t *cursor = bs.rec_cursor_host.data();      // (arrived with the batch)
+    int rc = 0;
     if (cursor[0] > v.rec_cap) { ctx->err = "sparse record stream overflow: submit a smaller batch"; return UVCGPU_ENOMEM; }
     const double t_sp0 = now_ms();
     StageVec<int32_t> rec((size_t)cursor[0]);
-    rc = backend_download(ctx, rec.data(), v.rec_buf, rec.size() * sizeof(int32_t));
-    if (rc != 0) { return rc; }
     bs.ev_host.resize((size_t)v.n_ev);
-    rc = backend_download(ctx, bs.ev_host.data(), v.ev, bs.ev_host.size() * sizeof(IndelEvent));
+    rc = backend_download_async(ctx, rec.data(), v.rec_buf, rec.size() * sizeof(int32_t));
+    if (0 == rc) { rc = backend_download_async(ctx, bs.ev_host.data(), v.ev, bs.ev_host.size() * sizeof(IndelEvent)); }
+    if (0 == rc) { rc = backend_sync(ctx); }
     if (rc != 0) { return rc; }
     bs.stats.d2h_bytes += (int64_t)(rec.size() * sizeof(int32_t) + bs.ev_host.size() * sizeof(IndelEvent));
     const double t_sp1 = now_ms();
@@ -1313,8 +1362,10 @@ static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
     PostScope post_scope(ctx);
     const double t0 = now_ms();
     BatchView & v = bs.view;
-    std::vector<IndelAllele> table;
-    uvc_build_indel_sites(bs.sites, table, bs.hb, bs.sparse, ctx->contigs, bs.ev_host);
+    std::vector<IndelAllele> table_;
+    uvc_build_indel_sites(bs.sites, table_, bs.hb, bs.sparse, ctx->contigs, bs.ev_host);
+    StageVec<IndelAllele> & table = bs.allele_table;      // (page-locked and alive until release: its upload is asynchronous)
+    table.assign(table_.begin(), table_.end());
     const double t1 = now_ms();
     ScoreView sv;
     memset(&sv, 0, sizeof(sv));
@@ -1322,10 +1373,7 @@ static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
     if ((rc = backend_alloc(ctx, bs, &d, table.size() * sizeof(IndelAllele), false)) != 0) { return rc; }
     if ((rc = backend_upload(ctx, bs, d, table.data(), table.size() * sizeof(IndelAllele))) != 0) { return rc; }
     sv.alleles = (const IndelAllele*)d; sv.n_alleles = (int64_t)table.size();
-    if ((rc = backend_alloc(ctx, bs, &d, (size_t)v.n_pos * sizeof(GvcfPos), true)) != 0) { return rc; }
-    sv.gvcf = (GvcfPos*)d;
-    if ((rc = backend_alloc(ctx, bs, &d, (size_t)v.n_pos * sizeof(GvcfExtra), true)) != 0) { return rc; }
-    sv.gextra = (GvcfExtra*)d;
+    sv.gvcf = bs.d_gvcf; sv.gextra = bs.d_gextra;
     if ((rc = backend_alloc(ctx, bs, &d, 16, true)) != 0) { return rc; }
     sv.out_cursor = (int32_t*)d;
     sv.cand_cursor = sv.out_cursor + 1;
@@ -1334,26 +1382,25 @@ static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
     sv.cand_list = (int32_t*)d;
     int64_t cap = v.n_pos / 16 + 4096;
     StageVec<VarRec> & recs = bs.recs;
+    bs.score_cursor_host.assign(4, 0);
+    const size_t n_first = 256;       // records downloaded together with their count (most batches have fewer: one wait instead of two)
     for (int attempt = 0; attempt < 2; attempt++) {
         if ((rc = backend_alloc(ctx, bs, &d, (size_t)cap * sizeof(VarRec), false)) != 0) { return rc; }
         sv.out = (VarRec*)d; sv.out_cap = (int32_t)cap;
-        const int32_t zero4[4] = {0, 0, 0, 0};
-        if ((rc = backend_upload(ctx, bs, sv.out_cursor, zero4, sizeof(zero4))) != 0) { return rc; }
+        if ((rc = backend_zero(ctx, sv.out_cursor, 16)) != 0) { return rc; }
+        recs.resize(std::min<size_t>(n_first, (size_t)cap));
         if ((rc = backend_score(ctx, bs, sv)) != 0) { return rc; }
-        int32_t n = 0;
-        if ((rc = backend_download(ctx, &n, sv.out_cursor, sizeof(n))) != 0) { return rc; }
+        const int32_t n = bs.score_cursor_host[0];
         if (n <= cap) {
+            const size_t have = recs.size();
             recs.resize((size_t)n);
-            if ((rc = backend_download(ctx, recs.data(), sv.out, recs.size() * sizeof(VarRec))) != 0) { return rc; }
+            if ((size_t)n > have && (rc = backend_download(ctx, recs.data() + have, sv.out + have, ((size_t)n - have) * sizeof(VarRec))) != 0) { return rc; }
             break;
         }
         if (attempt == 1) { ctx->err = "candidate record buffer overflow"; return UVCGPU_ENOMEM; }
         cap = n;   // the kernel counted every record it wanted to write: run again with room for all of them
     }
-    bs.gvcf.resize((size_t)v.n_pos); bs.gextra.resize((size_t)v.n_pos);
-    if ((rc = backend_download(ctx, bs.gvcf.data(), sv.gvcf, bs.gvcf.size() * sizeof(GvcfPos))) != 0) { return rc; }
-    if ((rc = backend_download(ctx, bs.gextra.data(), sv.gextra, bs.gextra.size() * sizeof(GvcfExtra))) != 0) { return rc; }
-    bs.stats.d2h_bytes += (int64_t)(recs.size() * sizeof(VarRec) + bs.gvcf.size() * sizeof(GvcfPos) + bs.gextra.size() * sizeof(GvcfExtra));
+    bs.stats.d2h_bytes += (int64_t)(recs.size() * sizeof(VarRec));
     const double t2 = now_ms();
     bs.recs_by_tile.assign(bs.hb.tiles.size(), std::vector<const VarRec*>());
     for (const auto & r : recs) { bs.recs_by_tile[(size_t)r.tile].push_back(&r); }
