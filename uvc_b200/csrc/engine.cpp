@@ -16,6 +16,10 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <map>
 #include <memory>
 #include <string>
@@ -58,6 +62,9 @@ struct BatchState {
     std::vector<std::string> vcf_text;     // per-tile VCF body, formatted once on all host threads
     bool vcf_built = false;
     uvcgpu_batch_stats stats;
+    bool submitted = true;                 // false while the context's worker thread still stages the batch
+    int submit_rc = 0;
+    std::string submit_err;
     bool collected = false;
     bool sparse_built = false;
     std::vector<TileSparse> sparse;
@@ -82,6 +89,8 @@ struct BatchState {
 
 } // namespace
 
+struct SubmitJob { BatchState *bs; std::vector<uvcgpu_tile> tiles; };
+
 struct uvcgpu_ctx {
     int device = 0;
     uvcgpu_params par;
@@ -102,9 +111,24 @@ struct uvcgpu_ctx {
                                           // pileup kernels of the previous batch compute, so they do not queue behind them
     cudaStream_t post_stream = nullptr;   // everything after collect (scoring kernels, downloads) of a batch, so that it does not queue behind the next batch
     cudaEvent_t wait_ev[3] = {nullptr, nullptr, nullptr};   // blocking-sync events the host waits on (one per stream)
-    cudaStream_t active = nullptr;        // the stream the backend helpers use: `stream`, or `post_stream` inside PostScope
+    // Submits are asynchronous: the caller's thread copies nothing and waits for nothing, the context's worker thread stages the batch (record
+    // copy, upload, staging kernels and their two short waits, allocations, pileup launches) in submission order while the caller finishes
+    // the previous batch. Failures of the worker are reported by uvcgpu_collect.
+    std::thread worker;
+    std::mutex wmu;
+    std::condition_variable wcv, wdone;
+    std::deque<SubmitJob> wq;
+    bool wstop = false;
 #endif
 };
+#if UVC_CUDA
+// the stream the backend helpers use on this thread: `stream` (the default at every entry point), `prep_stream` / `stream` on the worker
+// thread, `post_stream` inside PostScope
+static thread_local cudaStream_t t_active = nullptr;
+#endif
+// where error messages of this thread go: the context's string, or the batch's own one on the worker thread
+static thread_local std::string *t_err = nullptr;
+#define UVC_ERR(ctx) (*(t_err ? t_err : &(ctx)->err))
 
 // ------------------------------------------------------------------------------------------------ staging memory (see host_prep.h)
 // Page-locking memory is slow (~1 GB/s), so it is never done on the critical path: a request that finds no cached page-locked block of its
@@ -218,7 +242,7 @@ void uvc_stage_free(void *p, size_t bytes) {
 // ------------------------------------------------------------------------------------------------ compute backend
 #if UVC_CUDA
 
-#define UVC_CUDA_CHECK(ctx, call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return UVCGPU_ECUDA; } }
+#define UVC_CUDA_CHECK(ctx, call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { UVC_ERR(ctx) = std::string(#call) + ": " + cudaGetErrorString(e_); return UVCGPU_ECUDA; } }
 
 // One named __global__ per stage (so that profiles list them by name); every thread handles one work item.
 #define UVC_DEFINE_KERNEL(name, call) \
@@ -715,28 +739,28 @@ static int backend_wait_stream(uvcgpu_ctx *ctx, cudaStream_t s) {
 }
 static int backend_alloc(uvcgpu_ctx *ctx, BatchState & bs, void **out, size_t bytes, bool zero) {
     bytes += 64;     // slack: staged record slices are rounded up to 16 bytes, and clamped byte loads may touch offset 0 of an empty blob
-    UVC_CUDA_CHECK(ctx, cudaMallocAsync(out, bytes, ctx->active));   // stream-ordered pool: no device synchronisation, blocks are reused across batches
+    UVC_CUDA_CHECK(ctx, cudaMallocAsync(out, bytes, t_active));   // stream-ordered pool: no device synchronisation, blocks are reused across batches
     bs.allocs.push_back(*out);
-    if (zero) { UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, 0, bytes, ctx->active)); }
+    if (zero) { UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, 0, bytes, t_active)); }
     return 0;
 }
 static int backend_upload(uvcgpu_ctx *ctx, BatchState & bs, void *dst, const void *src, size_t bytes) {
-    if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->active)); bs.stats.h2d_bytes += (int64_t)bytes; }
+    if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, t_active)); bs.stats.h2d_bytes += (int64_t)bytes; }
     return 0;
 }
 // downloads are enqueued (page-locked destinations) and waited for together: every wait of the host costs the turn-around of the stream behind
 // the pileup blocks of other batches that occupy the SMs
 static int backend_download_async(uvcgpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
-    if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->active)); }
+    if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, t_active)); }
     return 0;
 }
-static int backend_sync(uvcgpu_ctx *ctx) { return backend_wait_stream(ctx, ctx->active); }
+static int backend_sync(uvcgpu_ctx *ctx) { return backend_wait_stream(ctx, t_active); }
 static int backend_download(uvcgpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
     if (bytes) { int rc_ = backend_download_async(ctx, dst, src, bytes); if (0 == rc_) { rc_ = backend_sync(ctx); } if (rc_ != 0) { return rc_; } }
     return 0;
 }
-static int backend_zero(uvcgpu_ctx *ctx, void *dst, size_t bytes) { UVC_CUDA_CHECK(ctx, cudaMemsetAsync(dst, 0, bytes, ctx->active)); return 0; }
-static void backend_free_temps(uvcgpu_ctx *ctx, BatchState & bs) { for (void *p : bs.temp_allocs) { cudaFreeAsync(p, ctx->active); } bs.temp_allocs.clear(); }
+static int backend_zero(uvcgpu_ctx *ctx, void *dst, size_t bytes) { UVC_CUDA_CHECK(ctx, cudaMemsetAsync(dst, 0, bytes, t_active)); return 0; }
+static void backend_free_temps(uvcgpu_ctx *ctx, BatchState & bs) { for (void *p : bs.temp_allocs) { cudaFreeAsync(p, t_active); } bs.temp_allocs.clear(); }
 // A batch is released after everything of it has completed, while the submit stream may already hold the kernels of the next batch: freeing
 // there would make the blocks reusable only after those kernels (any stream that picks such a block up inherits the wait). The second stream of
 // the context is idle at that moment, so the blocks go back to the pool at once.
@@ -744,9 +768,9 @@ static void backend_free(uvcgpu_ctx *ctx, BatchState & bs) { backend_free_temps(
 // scratch of the staging kernels; fill >= 0: every byte is set to it
 static int backend_alloc_temp(uvcgpu_ctx *ctx, BatchState & bs, void **out, size_t bytes, int fill = -1) {
     bytes += 64;
-    UVC_CUDA_CHECK(ctx, cudaMallocAsync(out, bytes, ctx->active));
+    UVC_CUDA_CHECK(ctx, cudaMallocAsync(out, bytes, t_active));
     bs.temp_allocs.push_back(*out);
-    if (fill >= 0) { UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, fill, bytes, ctx->active)); }
+    if (fill >= 0) { UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, fill, bytes, t_active)); }
     return 0;
 }
 
@@ -859,10 +883,10 @@ static int backend_score(uvcgpu_ctx *ctx, BatchState & bs, const ScoreView & sv)
     const BatchView & v = bs.view;
     cudaEvent_t e[2];
     for (int i = 0; i < 2; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreate(&e[i])); }
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(e[0], ctx->active));
-    if (v.n_pos > 0) { uvc_k5a_flag_candidates<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, ctx->active>>>(v, sv, v.n_pos); }
-    if (v.n_pos > 0) { uvc_k5_score_candidates<<<(unsigned)((v.n_pos + 63) / 64), 64, 0, ctx->active>>>(v, sv, v.n_pos); }
-    UVC_CUDA_CHECK(ctx, cudaEventRecord(e[1], ctx->active));
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(e[0], t_active));
+    if (v.n_pos > 0) { uvc_k5a_flag_candidates<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, t_active>>>(v, sv, v.n_pos); }
+    if (v.n_pos > 0) { uvc_k5_score_candidates<<<(unsigned)((v.n_pos + 63) / 64), 64, 0, t_active>>>(v, sv, v.n_pos); }
+    UVC_CUDA_CHECK(ctx, cudaEventRecord(e[1], t_active));
     UVC_CUDA_CHECK(ctx, cudaGetLastError());
     // the results the host always needs ride behind the kernels: the cursors and the first records
     { int rc_ = backend_download_async(ctx, bs.score_cursor_host.data(), sv.out_cursor, 4 * sizeof(int32_t));
@@ -944,7 +968,7 @@ static int backend_score(uvcgpu_ctx *, BatchState & bs, const ScoreView & sv) {
 // Entry points may be called from any host thread: the context's device is made current first (CUDA's current device is per thread).
 static inline void enter_ctx(const uvcgpu_ctx *ctx) {
 #if UVC_CUDA
-    if (ctx) { cudaSetDevice(ctx->device); }
+    if (ctx) { cudaSetDevice(ctx->device); t_active = ctx->stream; }
 #else
     (void)ctx;
 #endif
@@ -952,6 +976,13 @@ static inline void enter_ctx(const uvcgpu_ctx *ctx) {
 
 // ------------------------------------------------------------------------------------------------ C ABI
 extern "C" {
+
+static int wait_submitted(uvcgpu_ctx *ctx, BatchState & bs);
+static void wait_worker_idle(uvcgpu_ctx *ctx);
+#if UVC_CUDA
+static void submit_worker(uvcgpu_ctx *ctx);
+#endif
+
 
 void uvcgpu_params_default(uvcgpu_params *p) {
     memset(p, 0, sizeof(*p));
@@ -1136,11 +1167,14 @@ int uvcgpu_create(uvcgpu_ctx **out, int device, const uvcgpu_params *params) {
     if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete ctx; return UVCGPU_ECUDA; }
     if (cudaStreamCreateWithPriority(&ctx->post_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return UVCGPU_ECUDA; }
     if (cudaStreamCreateWithPriority(&ctx->prep_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->post_stream); delete ctx; return UVCGPU_ECUDA; }
-    ctx->active = ctx->stream;
+    t_active = ctx->stream;
     {   // keep freed device blocks in the stream-ordered pool instead of returning them to the driver after every batch
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { uint64_t keep = UINT64_MAX; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
     }
+#endif
+#if UVC_CUDA
+    ctx->worker = std::thread(submit_worker, ctx);
 #endif
     *out = ctx;
     return UVCGPU_OK;
@@ -1149,6 +1183,12 @@ int uvcgpu_create(uvcgpu_ctx **out, int device, const uvcgpu_params *params) {
 void uvcgpu_destroy(uvcgpu_ctx *ctx) {
     if (NULL == ctx) { return; }
     enter_ctx(ctx);
+    wait_worker_idle(ctx);
+#if UVC_CUDA
+    { std::lock_guard<std::mutex> lk(ctx->wmu); ctx->wstop = true; }
+    ctx->wcv.notify_all();
+    if (ctx->worker.joinable()) { ctx->worker.join(); }
+#endif
     for (auto & kv : ctx->batches) { backend_free(ctx, *kv.second); }
 #if UVC_CUDA
     cudaDeviceSynchronize();
@@ -1167,6 +1207,7 @@ const char *uvcgpu_last_error(const uvcgpu_ctx *ctx) { return (ctx ? ctx->err.c_
 int uvcgpu_set_contig(uvcgpu_ctx *ctx, int32_t tid, const char *bases, int64_t len) {
     if (NULL == ctx || tid < 0 || len < 0) { return UVCGPU_EINVAL; }
     enter_ctx(ctx);
+    wait_worker_idle(ctx);
     HostContig & c = ctx->contigs[tid];
     c.len = len;
     c.available = (NULL != bases);
@@ -1183,7 +1224,7 @@ int uvcgpu_set_contig(uvcgpu_ctx *ctx, int32_t tid, const char *bases, int64_t l
             char *d = NULL;
             UVC_CUDA_CHECK(ctx, cudaMalloc((void**)&d, (size_t)len + 64));
             cudaError_t e = cudaMemcpy(d, c.bases.data(), (size_t)len, cudaMemcpyHostToDevice);
-            if (e != cudaSuccess) { cudaFree(d); ctx->err = std::string("cudaMemcpy of the contig: ") + cudaGetErrorString(e); return UVCGPU_ECUDA; }
+            if (e != cudaSuccess) { cudaFree(d); UVC_ERR(ctx) = std::string("cudaMemcpy of the contig: ") + cudaGetErrorString(e); return UVCGPU_ECUDA; }
             ctx->d_contigs[tid] = d;
         }
     }
@@ -1194,6 +1235,7 @@ int uvcgpu_set_contig(uvcgpu_ctx *ctx, int32_t tid, const char *bases, int64_t l
 int uvcgpu_unset_contig(uvcgpu_ctx *ctx, int32_t tid) {
     if (NULL == ctx) { return UVCGPU_EINVAL; }
     enter_ctx(ctx);
+    wait_worker_idle(ctx);
     ctx->contigs.erase(tid);
 #if UVC_CUDA
     auto it = ctx->d_contigs.find(tid);
@@ -1227,20 +1269,8 @@ int uvcgpu_submit(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, co
     return uvcgpu_submit_multi(ctx, n_tiles, tiles, 1, reads, NULL, ticket);
 }
 
-int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, int32_t n_sources, const uvcgpu_reads_soa *sources,
-        const int32_t *tile_source, uvcgpu_ticket *ticket) {
-    enter_ctx(ctx);
-    if (NULL == ctx || NULL == tiles || NULL == sources || NULL == ticket || n_tiles <= 0 || n_sources <= 0) { return UVCGPU_EINVAL; }
-    std::unique_ptr<BatchState> bs(new BatchState());
-    memset(&bs->stats, 0, sizeof(bs->stats));
-    bs->sources.assign(sources, sources + n_sources);
-    bs->tile_source.assign((size_t)n_tiles, 0);
-    if (tile_source) {
-        for (int32_t k = 0; k < n_tiles; k++) {
-            if (tile_source[k] < 0 || tile_source[k] >= n_sources) { ctx->err = "tile_source out of range"; return UVCGPU_EINVAL; }
-            bs->tile_source[(size_t)k] = tile_source[k];
-        }
-    }
+// the staging of a batch (on the context's worker thread in the CUDA build)
+static int submit_body(uvcgpu_ctx *ctx, BatchState *bs, int32_t n_tiles, const uvcgpu_tile *tiles) {
     const double t0 = now_ms();
     HostBatch & hb = bs->hb;
     BatchView & v = bs->view;
@@ -1255,10 +1285,10 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
     v.phred2prob_tab = ctx->c_phred2prob; v.pf_tab = ctx->c_pf_tab; v.slip_tab = ctx->c_slip_tab;
     // stages P0 and P1 on the device: read filter, family segmentation, reference context (prep_device.inc); fills the view's input arrays
 #if UVC_CUDA
-    ctx->active = ctx->prep_stream;
+    t_active = ctx->prep_stream;
     {
         const int rc_prep = prep_on_device(ctx, *bs, n_tiles, tiles);
-        ctx->active = ctx->stream;
+        t_active = ctx->stream;
         if (rc_prep != 0) { backend_abort(ctx, *bs); return rc_prep; }
     }
     UVC_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, bs->ev_prep[1], 0));     // the pileup kernels start when the staging kernels are done
@@ -1300,19 +1330,92 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
     for (const auto & T : hb.tiles) { st.n_positions += T.end_pos - T.beg_pos; }
     st.h2d_ms = (t1 - t0) - st.host_prep_ms;    // the rest of the staging call: uploads, staging kernels and their two synchronisations
     (void)t2;
+    return UVCGPU_OK;
+}
+
+#if UVC_CUDA
+static void submit_worker(uvcgpu_ctx *ctx) {
+    cudaSetDevice(ctx->device);
+    for (;;) {
+        SubmitJob job;
+        {
+            std::unique_lock<std::mutex> lk(ctx->wmu);
+            ctx->wcv.wait(lk, [&]() { return ctx->wstop || !ctx->wq.empty(); });
+            if (ctx->wq.empty()) { return; }
+            job = std::move(ctx->wq.front());
+            ctx->wq.pop_front();
+        }
+        t_active = ctx->stream;
+        t_err = &job.bs->submit_err;
+        const int rc = submit_body(ctx, job.bs, (int32_t)job.tiles.size(), job.tiles.data());
+        t_err = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(ctx->wmu);
+            job.bs->submit_rc = rc;
+            job.bs->submitted = true;
+        }
+        ctx->wdone.notify_all();
+    }
+}
+#endif
+// waits until the worker has staged the batch; returns the result of its staging
+static int wait_submitted(uvcgpu_ctx *ctx, BatchState & bs) {
+#if UVC_CUDA
+    std::unique_lock<std::mutex> lk(ctx->wmu);
+    ctx->wdone.wait(lk, [&]() { return bs.submitted; });
+#endif
+    if (bs.submit_rc != 0 && !bs.submit_err.empty()) { ctx->err = bs.submit_err; }
+    return bs.submit_rc;
+}
+// (contigs and parameters must not change under a batch that is being staged)
+static void wait_worker_idle(uvcgpu_ctx *ctx) {
+    for (auto & kv : ctx->batches) { wait_submitted(ctx, *kv.second); }
+}
+
+int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, int32_t n_sources, const uvcgpu_reads_soa *sources,
+        const int32_t *tile_source, uvcgpu_ticket *ticket) {
+    enter_ctx(ctx);
+    if (NULL == ctx || NULL == tiles || NULL == sources || NULL == ticket || n_tiles <= 0 || n_sources <= 0) { return UVCGPU_EINVAL; }
+    std::unique_ptr<BatchState> bs(new BatchState());
+    memset(&bs->stats, 0, sizeof(bs->stats));
+    bs->sources.assign(sources, sources + n_sources);
+    bs->tile_source.assign((size_t)n_tiles, 0);
+    if (tile_source) {
+        for (int32_t k = 0; k < n_tiles; k++) {
+            if (tile_source[k] < 0 || tile_source[k] >= n_sources) { UVC_ERR(ctx) = "tile_source out of range"; return UVCGPU_EINVAL; }
+            bs->tile_source[(size_t)k] = tile_source[k];
+        }
+    }
+    BatchState *raw = bs.get();
     *ticket = ctx->next_ticket++;
     ctx->batches[*ticket] = std::move(bs);
+#if UVC_CUDA
+    raw->submitted = false;
+    {
+        std::lock_guard<std::mutex> lk(ctx->wmu);
+        SubmitJob job;
+        job.bs = raw; job.tiles.assign(tiles, tiles + n_tiles);
+        ctx->wq.push_back(std::move(job));
+    }
+    ctx->wcv.notify_one();
     return UVCGPU_OK;
+#else
+    raw->submit_rc = submit_body(ctx, raw, n_tiles, tiles);
+    if (raw->submit_rc != 0) { const int rc = raw->submit_rc; ctx->batches.erase(*ticket); return rc; }
+    return UVCGPU_OK;
+#endif
 }
 
 int uvcgpu_collect(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, uvcgpu_batch_stats *stats) {
     enter_ctx(ctx);
     if (NULL == ctx) { return UVCGPU_EINVAL; }
     auto it = ctx->batches.find(ticket);
-    if (it == ctx->batches.end()) { ctx->err = "unknown ticket"; return UVCGPU_EINVAL; }
+    if (it == ctx->batches.end()) { UVC_ERR(ctx) = "unknown ticket"; return UVCGPU_EINVAL; }
     BatchState & bs = *it->second;
     if (!bs.collected) {
-        int rc = backend_wait(ctx, bs);
+        int rc = wait_submitted(ctx, bs);
+        if (rc != 0) { return rc; }
+        rc = backend_wait(ctx, bs);
         if (rc != 0) { return rc; }
         bs.collected = true;
     }
@@ -1325,8 +1428,8 @@ int uvcgpu_collect(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, uvcgpu_batch_stats *st
 struct PostScope {
 #if UVC_CUDA
     uvcgpu_ctx *c;
-    explicit PostScope(uvcgpu_ctx *ctx) : c(ctx) { c->active = c->post_stream; }
-    ~PostScope() { c->active = c->stream; }
+    explicit PostScope(uvcgpu_ctx *ctx) : c(ctx) { t_active = c->post_stream; }
+    ~PostScope() { t_active = c->stream; }
 #else
     explicit PostScope(uvcgpu_ctx *) {}
 #endif
@@ -1338,7 +1441,7 @@ static int ensure_sparse(uvcgpu_ctx *ctx, BatchState & bs) {
     const BatchView & v = bs.view;
     const int32_t *cursor = bs.rec_cursor_host.data();      // (arrived with the batch)
     int rc = 0;
-    if (cursor[0] > v.rec_cap) { ctx->err = "sparse record stream overflow: submit a smaller batch"; return UVCGPU_ENOMEM; }
+    if (cursor[0] > v.rec_cap) { UVC_ERR(ctx) = "sparse record stream overflow: submit a smaller batch"; return UVCGPU_ENOMEM; }
     const double t_sp0 = now_ms();
     StageVec<int32_t> rec((size_t)cursor[0]);
     bs.ev_host.resize((size_t)v.n_ev);
@@ -1377,7 +1480,7 @@ static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
     if ((rc = backend_alloc(ctx, bs, &d, 16, true)) != 0) { return rc; }
     sv.out_cursor = (int32_t*)d;
     sv.cand_cursor = sv.out_cursor + 1;
-    if (v.n_pos > INT32_MAX) { ctx->err = "batch too large: submit fewer tiles"; return UVCGPU_EINVAL; }
+    if (v.n_pos > INT32_MAX) { UVC_ERR(ctx) = "batch too large: submit fewer tiles"; return UVCGPU_EINVAL; }
     if ((rc = backend_alloc(ctx, bs, &d, (size_t)v.n_pos * sizeof(int32_t), false)) != 0) { return rc; }
     sv.cand_list = (int32_t*)d;
     int64_t cap = v.n_pos / 16 + 4096;
@@ -1397,7 +1500,7 @@ static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
             if ((size_t)n > have && (rc = backend_download(ctx, recs.data() + have, sv.out + have, ((size_t)n - have) * sizeof(VarRec))) != 0) { return rc; }
             break;
         }
-        if (attempt == 1) { ctx->err = "candidate record buffer overflow"; return UVCGPU_ENOMEM; }
+        if (attempt == 1) { UVC_ERR(ctx) = "candidate record buffer overflow"; return UVCGPU_ENOMEM; }
         cap = n;   // the kernel counted every record it wanted to write: run again with room for all of them
     }
     bs.stats.d2h_bytes += (int64_t)(recs.size() * sizeof(VarRec));
@@ -1416,9 +1519,9 @@ int uvcgpu_score(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, uvcgpu_batch_stats *stat
     enter_ctx(ctx);
     if (NULL == ctx) { return UVCGPU_EINVAL; }
     auto it = ctx->batches.find(ticket);
-    if (it == ctx->batches.end()) { ctx->err = "unknown ticket"; return UVCGPU_EINVAL; }
+    if (it == ctx->batches.end()) { UVC_ERR(ctx) = "unknown ticket"; return UVCGPU_EINVAL; }
     BatchState & bs = *it->second;
-    if (!bs.collected) { ctx->err = "batch not collected yet"; return UVCGPU_EINVAL; }
+    if (!bs.collected) { UVC_ERR(ctx) = "batch not collected yet"; return UVCGPU_EINVAL; }
     int rc = ensure_scored(ctx, bs);
     if (rc != 0) { return rc; }
     if (stats) { *stats = bs.stats; }
@@ -1434,7 +1537,7 @@ static int ensure_vcf_text(uvcgpu_ctx *ctx, BatchState & bs) {
     bs.vcf_text.assign((size_t)n_tiles, std::string());
     for (int32_t ti = 0; ti < n_tiles; ti++) {
         const TileInfo & T = bs.hb.tiles[ti];
-        if (!T.skipped && ctx->contigs.find(T.tid) == ctx->contigs.end()) { ctx->err = "contig of a tile was unset before its VCF text was requested"; return UVCGPU_EINVAL; }
+        if (!T.skipped && ctx->contigs.find(T.tid) == ctx->contigs.end()) { UVC_ERR(ctx) = "contig of a tile was unset before its VCF text was requested"; return UVCGPU_EINVAL; }
     }
     uvc_parallel_for(n_tiles, ctx->host_threads, [&](int32_t ti) {
         const TileInfo & T = bs.hb.tiles[ti];
@@ -1459,9 +1562,9 @@ int uvcgpu_tile_vcf(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_index, c
     enter_ctx(ctx);
     if (NULL == ctx || NULL == needed) { return UVCGPU_EINVAL; }
     auto it = ctx->batches.find(ticket);
-    if (it == ctx->batches.end()) { ctx->err = "unknown ticket"; return UVCGPU_EINVAL; }
+    if (it == ctx->batches.end()) { UVC_ERR(ctx) = "unknown ticket"; return UVCGPU_EINVAL; }
     BatchState & bs = *it->second;
-    if (!bs.collected) { ctx->err = "batch not collected yet"; return UVCGPU_EINVAL; }
+    if (!bs.collected) { UVC_ERR(ctx) = "batch not collected yet"; return UVCGPU_EINVAL; }
     if (tile_index < 0 || tile_index >= (int32_t)bs.hb.tiles.size()) { return UVCGPU_EINVAL; }
     std::string s;
     int rc = tile_vcf_text(ctx, bs, tile_index, s);
@@ -1475,9 +1578,9 @@ int uvcgpu_batch_vcf(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, char *dst, size_t ca
     enter_ctx(ctx);
     if (NULL == ctx || NULL == needed) { return UVCGPU_EINVAL; }
     auto it = ctx->batches.find(ticket);
-    if (it == ctx->batches.end()) { ctx->err = "unknown ticket"; return UVCGPU_EINVAL; }
+    if (it == ctx->batches.end()) { UVC_ERR(ctx) = "unknown ticket"; return UVCGPU_EINVAL; }
     BatchState & bs = *it->second;
-    if (!bs.collected) { ctx->err = "batch not collected yet"; return UVCGPU_EINVAL; }
+    if (!bs.collected) { UVC_ERR(ctx) = "batch not collected yet"; return UVCGPU_EINVAL; }
     int rc = ensure_vcf_text(ctx, bs);
     if (rc != 0) { return rc; }
     size_t total = 0;
@@ -1506,12 +1609,12 @@ int uvcgpu_selftest_math(uvcgpu_ctx *ctx, int32_t which, const double *in, int32
 #if UVC_CUDA
     double *d_in = NULL, *d_out = NULL;
     UVC_CUDA_CHECK(ctx, cudaMalloc((void**)&d_in, (size_t)n * 3 * sizeof(double)));
-    if (cudaMalloc((void**)&d_out, (size_t)n * sizeof(double)) != cudaSuccess) { cudaFree(d_in); ctx->err = "cudaMalloc"; return UVCGPU_ECUDA; }
+    if (cudaMalloc((void**)&d_out, (size_t)n * sizeof(double)) != cudaSuccess) { cudaFree(d_in); UVC_ERR(ctx) = "cudaMalloc"; return UVCGPU_ECUDA; }
     cudaMemcpy(d_in, in, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice);
     uvc_selftest_math_kernel<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(v, which, d_in, n, d_out);
     const cudaError_t e = cudaMemcpy(out, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(d_in); cudaFree(d_out);
-    if (e != cudaSuccess) { ctx->err = std::string("uvcgpu_selftest_math: ") + cudaGetErrorString(e); return UVCGPU_ECUDA; }
+    if (e != cudaSuccess) { UVC_ERR(ctx) = std::string("uvcgpu_selftest_math: ") + cudaGetErrorString(e); return UVCGPU_ECUDA; }
 #else
     for (int32_t i = 0; i < n; i++) { out[i] = uvc::selftest_math(v, which, in[3 * i], in[3 * i + 1], in[3 * i + 2]); }
 #endif
@@ -1523,7 +1626,7 @@ int uvcgpu_release(uvcgpu_ctx *ctx, uvcgpu_ticket ticket) {
     if (NULL == ctx) { return UVCGPU_EINVAL; }
     auto it = ctx->batches.find(ticket);
     if (it == ctx->batches.end()) { return UVCGPU_EINVAL; }
-    if (!it->second->collected) { backend_wait(ctx, *it->second); }   // (a collected batch has nothing left on the submit stream)
+    if (!it->second->collected && 0 == wait_submitted(ctx, *it->second)) { backend_wait(ctx, *it->second); }   // (a collected batch has nothing left on the submit stream)
 #if UVC_CUDA
     backend_wait_stream(ctx, ctx->post_stream);                        // idle unless a scoring call failed half-way
 #endif
@@ -1536,9 +1639,9 @@ int uvcgpu_dump_counters(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_ind
     enter_ctx(ctx);
     if (NULL == ctx || NULL == needed) { return UVCGPU_EINVAL; }
     auto it = ctx->batches.find(ticket);
-    if (it == ctx->batches.end()) { ctx->err = "unknown ticket"; return UVCGPU_EINVAL; }
+    if (it == ctx->batches.end()) { UVC_ERR(ctx) = "unknown ticket"; return UVCGPU_EINVAL; }
     BatchState & bs = *it->second;
-    if (!bs.collected) { ctx->err = "batch not collected yet"; return UVCGPU_EINVAL; }
+    if (!bs.collected) { UVC_ERR(ctx) = "batch not collected yet"; return UVCGPU_EINVAL; }
     if (tile_index < 0 || tile_index >= (int32_t)bs.hb.tiles.size()) { return UVCGPU_EINVAL; }
     PostScope post_scope(ctx);
     const TileInfo & T = bs.hb.tiles[tile_index];
@@ -1623,7 +1726,7 @@ int uvcgpu_dump_counters(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_ind
         }
         case UVCGPU_SEC_DUPLEX: src = v.duplex + off * UVC_NSYM * UVCGPU_NUM_DUPLEX_DEPTHS; bytes = npos * UVC_NSYM * UVCGPU_NUM_DUPLEX_DEPTHS * 4; break;
         case UVCGPU_SEC_VQ: src = v.vq + off * UVC_NSYM * UVCGPU_NUM_VQ_TAGS; bytes = npos * UVC_NSYM * UVCGPU_NUM_VQ_TAGS * 4; break;
-        default: ctx->err = "unknown section"; return UVCGPU_EINVAL;
+        default: UVC_ERR(ctx) = "unknown section"; return UVCGPU_EINVAL;
     }
     if (T.skipped && !host_side) { bytes = 0; }
     if (host_side) {
