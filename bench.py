@@ -245,6 +245,30 @@ def decode_sub_batches(ds, tiles, n_sub, threads, only=None):
     return subs
 
 
+def host_cpu_times():
+    """Aggregate jiffies of /proc/stat: (user + nice, system + irq + softirq, idle + iowait, steal)."""
+    try:
+        f = open("/proc/stat").readline().split()[1:]
+        v = [int(x) for x in f] + [0] * 8
+        return (v[0] + v[1], v[2] + v[5] + v[6], v[3] + v[4], v[7])
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def host_cpu_load(a, b):
+    """Share of the box's CPU time between two host_cpu_times() samples: the e2e number depends on how much of the host this process really
+    got (the GPU boxes are virtual machines: `steal` is time the hypervisor gave to somebody else)."""
+    if not a or not b:
+        return None
+    d = [y - x for x, y in zip(a, b)]
+    tot = max(1, sum(d))
+    try:
+        load = open("/proc/loadavg").read().split()[0]
+    except Exception:  # noqa: BLE001
+        load = None
+    return {"user": d[0] / tot, "system": d[1] / tot, "idle": d[2] / tot, "steal": d[3] / tot, "cores": os.cpu_count(), "loadavg_1min": load}
+
+
 class ClockSampler(threading.Thread):
     """SM clock and throttle reasons of one GPU during the timed regions. In-process NVML queries (a few microseconds each): spawning
     nvidia-smi ten times a second per rank takes driver-wide locks and measurably stalls the CUDA calls of every process on the box."""
@@ -610,12 +634,14 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    cpu0 = host_cpu_times()
     t0 = time.time()
     acc = e2e_steps(args.steps, keep_last=True)
     for k in totals:
         totals[k] += acc[k]
     torch.cuda.synchronize()
     wall_s = time.time() - t0
+    host_load = host_cpu_load(cpu0, host_cpu_times())
     backlog1 = int(ctx0.lib.uvcgpu_staging_backlog())
     sampler.stop_flag = True
     body = b"".join(last_text[k] for k in sorted(last_text))
@@ -773,6 +799,7 @@ def main():
                                                                      "indel_table_host": totals["sc4"] / args.steps, "scoring_kernels_and_downloads": totals["sc5"] / args.steps},
                     "call_ms_per_step_summed_over_contexts": {k[:-2]: totals[k] * 1e3 / args.steps for k in ("submit_s", "wait_s", "score_s", "text_s", "release_s")},
                     "wall_ms_per_step": wall_s * 1e3 / args.steps,
+                    "host_cpu_during_timed_region": host_load,
                     "staging_blocks_not_yet_page_locked": {"at_start": backlog0, "at_end": backlog1},
                     "staging_page_locked_bytes": {"at_start": pinned0, "at_end": int(ctx0.lib.uvcgpu_staging_pinned_bytes())}},
             "decode": {"seconds": decode_s, "threads": min(host_threads, max(1, n_sub)), "records": n_records, "records_per_s": n_records / decode_s,

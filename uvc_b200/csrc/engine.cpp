@@ -105,6 +105,7 @@ struct uvcgpu_ctx {
     // wait for the stream to drain)
     double *c_phred2prob = nullptr; int32_t *c_pf_tab = nullptr; int32_t *c_slip_tab = nullptr;
     int host_threads = 0;
+    double k5_groups_per_pos = 0.25, k5_cands_per_pos = 0.75;   // capacities of the scoring pipeline per position, grown to what the batches need
 #if UVC_CUDA
     cudaStream_t stream = nullptr;        // submit: staging copies and the pileup kernels of every batch, in submission order
     cudaStream_t prep_stream = nullptr;   // staging kernels (stages P0/P1) of a batch and their two short synchronisations: they depend on nothing that the
@@ -697,10 +698,31 @@ __global__ void __launch_bounds__(128) uvc_k5a_flag_candidates(const BatchView v
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { uvc::k5a_flag_position(v, sv, i); }
 }
-// runs over the compacted list of candidate positions (the grid is sized for the worst case; threads beyond the list exit at once)
-__global__ void __launch_bounds__(64) uvc_k5_score_candidates(const BatchView v, const ScoreView sv, int64_t n) {
+// The scoring pipeline (score_core.cuh): grids are sized for the capacities, threads beyond the counts exit at once. A kernel whose input
+// overflowed its capacity does nothing: the host sees the counts and runs the pipeline again with room for everything.
+__device__ __forceinline__ bool uvc_k5_fits(const ScoreView & sv) { return sv.out_cursor[2] <= sv.group_cap && sv.out_cursor[3] <= sv.cand_cap; }
+__global__ void __launch_bounds__(128) uvc_k5b_list_candidates(const BatchView v, const ScoreView sv, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && i < (int64_t)*sv.cand_cursor) { uvc::k5_score_position(v, sv, (int64_t)sv.cand_list[i]); }
+    if (i < n && i < (int64_t)*sv.cand_cursor) { uvc::k5b_list_position(v, sv, (int64_t)sv.cand_list[i]); }
+}
+__global__ void __launch_bounds__(128) uvc_k5g_group_init(const BatchView v, const ScoreView sv, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && i < (int64_t)sv.out_cursor[2] && uvc_k5_fits(sv)) { uvc::k5g_group(v, sv, i); }
+}
+#ifndef UVC_K5C_MINBLOCKS
+#define UVC_K5C_MINBLOCKS 2    // BcfFormat_symbol_calc_DPv is ~60 double-precision allele fractions per candidate
+#endif
+__global__ void __launch_bounds__(128, UVC_K5C_MINBLOCKS) uvc_k5c_candidate_depths(const BatchView v, const ScoreView sv, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && i < (int64_t)sv.out_cursor[3] && uvc_k5_fits(sv)) { uvc::k5c_candidate(v, sv, i); }
+}
+__global__ void __launch_bounds__(128) uvc_k5e_candidate_quals(const BatchView v, const ScoreView sv, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && i < (int64_t)sv.out_cursor[3] && uvc_k5_fits(sv)) { uvc::k5e_candidate(v, sv, i); }
+}
+__global__ void __launch_bounds__(128) uvc_k5f_group_records(const BatchView v, const ScoreView sv, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && i < (int64_t)sv.out_cursor[2] && uvc_k5_fits(sv)) { uvc::k5f_group(v, sv, i); }
 }
 
 __global__ void uvc_selftest_math_kernel(const BatchView v, int32_t which, const double *in, int32_t n, double *out) {
@@ -885,7 +907,13 @@ static int backend_score(uvcgpu_ctx *ctx, BatchState & bs, const ScoreView & sv)
     for (int i = 0; i < 2; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreate(&e[i])); }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(e[0], t_active));
     if (v.n_pos > 0) { uvc_k5a_flag_candidates<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, t_active>>>(v, sv, v.n_pos); }
-    if (v.n_pos > 0) { uvc_k5_score_candidates<<<(unsigned)((v.n_pos + 63) / 64), 64, 0, t_active>>>(v, sv, v.n_pos); }
+    if (v.n_pos > 0) {
+        uvc_k5b_list_candidates<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, t_active>>>(v, sv, v.n_pos);
+        uvc_k5g_group_init<<<(unsigned)((sv.group_cap + 127) / 128), 128, 0, t_active>>>(v, sv, sv.group_cap);
+        uvc_k5c_candidate_depths<<<(unsigned)((sv.cand_cap + 127) / 128), 128, 0, t_active>>>(v, sv, sv.cand_cap);
+        uvc_k5e_candidate_quals<<<(unsigned)((sv.cand_cap + 127) / 128), 128, 0, t_active>>>(v, sv, sv.cand_cap);
+        uvc_k5f_group_records<<<(unsigned)((sv.group_cap + 127) / 128), 128, 0, t_active>>>(v, sv, sv.group_cap);
+    }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(e[1], t_active));
     UVC_CUDA_CHECK(ctx, cudaGetLastError());
     // the results the host always needs ride behind the kernels: the cursors and the first records
@@ -896,7 +924,7 @@ static int backend_score(uvcgpu_ctx *ctx, BatchState & bs, const ScoreView & sv)
     float ms = 0;
     UVC_CUDA_CHECK(ctx, cudaEventElapsedTime(&ms, e[0], e[1])); bs.stats.kernel_ms_by_stage[12] = ms; bs.stats.kernel_ms += ms;
     for (int i = 0; i < 2; i++) { cudaEventDestroy(e[i]); }
-    if (v.n_pos > 0) { bs.stats.gpu_launches += 2; }
+    if (v.n_pos > 0) { bs.stats.gpu_launches += 6; }
     return 0;
 }
 
@@ -957,7 +985,13 @@ static int backend_wait(uvcgpu_ctx *, BatchState &) { return 0; }
 static int backend_score(uvcgpu_ctx *, BatchState & bs, const ScoreView & sv) {
     const BatchView & v = bs.view;
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::k5a_flag_position(v, sv, i); }
-    for (int64_t i = 0; i < (int64_t)*sv.cand_cursor; i++) { uvc::k5_score_position(v, sv, (int64_t)sv.cand_list[i]); }
+    for (int64_t i = 0; i < (int64_t)*sv.cand_cursor; i++) { uvc::k5b_list_position(v, sv, (int64_t)sv.cand_list[i]); }
+    if (sv.out_cursor[2] <= sv.group_cap && sv.out_cursor[3] <= sv.cand_cap) {
+        for (int64_t i = 0; i < (int64_t)sv.out_cursor[2]; i++) { uvc::k5g_group(v, sv, i); }
+        for (int64_t i = 0; i < (int64_t)sv.out_cursor[3]; i++) { uvc::k5c_candidate(v, sv, i); }
+        for (int64_t i = 0; i < (int64_t)sv.out_cursor[3]; i++) { uvc::k5e_candidate(v, sv, i); }
+        for (int64_t i = 0; i < (int64_t)sv.out_cursor[2]; i++) { uvc::k5f_group(v, sv, i); }
+    }
     memcpy(bs.score_cursor_host.data(), sv.out_cursor, 4 * sizeof(int32_t));
     memcpy(bs.recs.data(), sv.out, bs.recs.size() * sizeof(VarRec));
     return 0;
@@ -1484,25 +1518,38 @@ static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
     if ((rc = backend_alloc(ctx, bs, &d, (size_t)v.n_pos * sizeof(int32_t), false)) != 0) { return rc; }
     sv.cand_list = (int32_t*)d;
     int64_t cap = v.n_pos / 16 + 4096;
+    // groups and candidates per position: sized from what the context's earlier batches needed (a batch that needs more runs twice)
+    int64_t group_cap = (int64_t)(ctx->k5_groups_per_pos * (double)v.n_pos) + 1024, cand_cap = (int64_t)(ctx->k5_cands_per_pos * (double)v.n_pos) + 4096;
     StageVec<VarRec> & recs = bs.recs;
     bs.score_cursor_host.assign(4, 0);
     const size_t n_first = 256;       // records downloaded together with their count (most batches have fewer: one wait instead of two)
-    for (int attempt = 0; attempt < 2; attempt++) {
-        if ((rc = backend_alloc(ctx, bs, &d, (size_t)cap * sizeof(VarRec), false)) != 0) { return rc; }
+    for (int attempt = 0; attempt < 3; attempt++) {
+        if ((rc = backend_alloc_temp(ctx, bs, &d, (size_t)cap * sizeof(VarRec))) != 0) { return rc; }
         sv.out = (VarRec*)d; sv.out_cap = (int32_t)cap;
+        if ((rc = backend_alloc_temp(ctx, bs, &d, (size_t)group_cap * sizeof(GroupRec))) != 0) { return rc; }
+        sv.groups = (GroupRec*)d; sv.group_cap = (int32_t)group_cap;
+        if ((rc = backend_alloc_temp(ctx, bs, &d, (size_t)cand_cap * sizeof(CandDesc))) != 0) { return rc; }
+        sv.desc = (CandDesc*)d;
+        if ((rc = backend_alloc_temp(ctx, bs, &d, (size_t)cand_cap * sizeof(CandFmt))) != 0) { return rc; }
+        sv.cands = (CandFmt*)d; sv.cand_cap = (int32_t)cand_cap;
         if ((rc = backend_zero(ctx, sv.out_cursor, 16)) != 0) { return rc; }
         recs.resize(std::min<size_t>(n_first, (size_t)cap));
         if ((rc = backend_score(ctx, bs, sv)) != 0) { return rc; }
-        const int32_t n = bs.score_cursor_host[0];
-        if (n <= cap) {
+        const int32_t n = bs.score_cursor_host[0], n_groups = bs.score_cursor_host[2], n_cands = bs.score_cursor_host[3];
+        ctx->k5_groups_per_pos = std::max(ctx->k5_groups_per_pos, std::min(2.0, 1.25 * (double)n_groups / (double)std::max<int64_t>(1, v.n_pos)));
+        ctx->k5_cands_per_pos = std::max(ctx->k5_cands_per_pos, std::min(2.0 * UVC_MAX_GROUP_CANDS, 1.25 * (double)n_cands / (double)std::max<int64_t>(1, v.n_pos)));
+        if (n <= cap && n_groups <= group_cap && n_cands <= cand_cap) {
             const size_t have = recs.size();
             recs.resize((size_t)n);
             if ((size_t)n > have && (rc = backend_download(ctx, recs.data() + have, sv.out + have, ((size_t)n - have) * sizeof(VarRec))) != 0) { return rc; }
             break;
         }
-        if (attempt == 1) { UVC_ERR(ctx) = "candidate record buffer overflow"; return UVCGPU_ENOMEM; }
-        cap = n;   // the kernel counted every record it wanted to write: run again with room for all of them
+        if (attempt == 2) { UVC_ERR(ctx) = "candidate record buffer overflow"; return UVCGPU_ENOMEM; }
+        // the kernels counted everything they wanted to write: run again with room for all of it
+        cap = std::max<int64_t>(cap, n); group_cap = std::max<int64_t>(group_cap, n_groups); cand_cap = std::max<int64_t>(cand_cap, n_cands);
+        backend_free_temps(ctx, bs);
     }
+    backend_free_temps(ctx, bs);      // (stream-ordered: after the downloads above)
     bs.stats.d2h_bytes += (int64_t)(recs.size() * sizeof(VarRec));
     const double t2 = now_ms();
     bs.recs_by_tile.assign(bs.hb.tiles.size(), std::vector<const VarRec*>());

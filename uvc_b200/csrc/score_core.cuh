@@ -81,9 +81,22 @@ struct GvcfExtra { int32_t tracklen, repeatnum, unitlen, a_dp, a_clip; };
 // Candidate indel alleles of a (position, symbol), produced on the host from the indel identity maps exactly as indel_get_majority does.
 struct IndelAllele { int64_t key; int32_t bAD, cAD, ev, len; };   // key = gp * 16 + symbol; several alleles per key in output order
 
+// One (refpos, symbol type) group of a candidate position and the slots of its candidate alleles (kernels K5b ... K5f)
+struct GroupRec {
+    int64_t gp;                 // concatenated position index of refpos
+    int32_t tile, refpos, type, refsymbol;
+    int32_t first, n;           // candidates [first, first + n) in the reference's order
+    int32_t partner;            // the other group of the same zero-based position, or -1
+    int32_t ins_cdepth, del_cdepth, ins1_cdepth, del1_cdepth, repeatunit_len, repeatnum;
+    GroupFmt g;
+};
+// what BcfFormat_symbol_init needs to know about a candidate besides its position
+struct CandDesc { int32_t group, symbol, bDPa, cDP0a, ev, gap_len, minABQ, pad; };
+
 struct ScoreView {
     const IndelAllele *alleles; int64_t n_alleles;
-    VarRec *out; int32_t *out_cursor; int32_t out_cap;
+    VarRec *out; int32_t *out_cursor; int32_t out_cap;      // out_cursor[0..3]: records, candidate positions, groups, candidates
+    GroupRec *groups; CandDesc *desc; CandFmt *cands; int32_t group_cap, cand_cap;
     GvcfPos *gvcf;          // [n_pos]
     GvcfExtra *gextra;      // [n_pos]
     int32_t *cand_list;     // [n_pos] zero-based positions that have at least one candidate allele (compacted by K5a; order is irrelevant)
@@ -959,201 +972,277 @@ UVC_HD void k5a_flag_position(const BatchView & v, const ScoreView & sv, int64_t
     sv.cand_list[slot] = (int32_t)gp_zb;
 }
 
-// ------------------------------------------------------------------------------------------------ K5: one thread per zero-based position
-// One iteration of the reference's per-position loop (main.cpp:608-1172) without the text.
-UVC_HD void k5_score_position(const BatchView & v, const ScoreView & sv, int64_t gp_zb) {
-    const int32_t ti = v.pos_tile[gp_zb];
-    const TileInfo & T = v.tiles[ti];
-    if (T.skipped) { return; }
-    const int32_t zb = (int32_t)(gp_zb - T.pos_off) + T.ext_beg;
-    if (zb < T.rpos_inclu_beg || zb > T.rpos_exclu_end) { return; }
-    const uvcgpu_params & par = v.par;
-    const int32_t nref = (T.ext_end - T.ext_beg) - 1;      // refstring.size()
-    const int32_t rridx = zb - T.ext_beg;
-    int32_t repeatunit_len = 0, repeatnum = 0;
-    repeat_at(repeatunit_len, repeatnum, v, T, rridx);
-    const int32_t minABQ_snv = (T.is_amplicon_inferred ? par.syserr_minABQ_pcr_snv : par.syserr_minABQ_cap_snv);
-    const int32_t minABQ_indel = (T.is_amplicon_inferred ? par.syserr_minABQ_pcr_indel : par.syserr_minABQ_cap_indel);
-    const uint8_t *refsyms = v.refsym + T.pos_off;
-    const int refsym_base = ((nref == (zb - 1 - T.ext_beg)) || (-1 == (zb - 1 - T.ext_beg))) ? UVC_BASE_NN : (int)refsyms[zb - 1 - T.ext_beg];
-    const int32_t refidx = zb - T.ext_beg;
-    const int prev_base1 = ((refidx >= 2) ? (int)refsyms[refidx - 2] : UVC_BASE_NN);
-    const int prev_base2 = ((refidx >= 3) ? (int)refsyms[refidx - 3] : UVC_BASE_NN);
-    const int next_base1 = ((refidx < nref) ? (int)refsyms[refidx] : UVC_BASE_NN);
-    const int next_base2 = ((refidx + 1 < nref) ? (int)refsyms[refidx + 1] : UVC_BASE_NN);
+// ------------------------------------------------------------------------------------------------ K5: the reference's per-position loop as a pipeline
+// One iteration of the reference's per-position loop (main.cpp:608-1172) without the text, cut where its data dependences are:
+//   K5b  thread / candidate position : enumerates the candidate alleles of the two symbol types in the reference's order and reserves their slots
+//   K5g  thread / group              : BcfFormat_symboltype_init (the upper-case tags of one (refpos, symbol type))
+//   K5c  thread / candidate          : BcfFormat_symbol_init + BcfFormat_symbol_calc_DPv; BcfFormat_symbol_sum_DPv as integer atomic adds
+//   K5e  thread / candidate          : BcfFormat_symbol_calc_qual (needs the sums of all candidates of the group)
+//   K5f  thread / group              : output_germline's site likelihood, the top-2 alleles, append_vcf_record's qualities and keep decision
+// Candidates and groups live in global arrays between the kernels: a thread holds one candidate (no per-thread candidate tables), and every
+// candidate of the batch is a thread of its own instead of a loop iteration of its position's thread.
+UVC_HD int32_t atomic_add_i32(int32_t *p, int32_t x) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, x);
+#else
+    const int32_t old = *p; *p += x; return old;
+#endif
+}
 
-    GroupFmt G[2];
-    CandFmt C[2][UVC_MAX_GROUP_CANDS];
-    int ncand[2] = {0, 0};
+struct K5Site {
+    const TileInfo *T; int32_t ti, zb, nref, refsym_base, prev_base1, prev_base2, next_base1, next_base2, minABQ_snv, minABQ_indel;
+};
+UVC_HD bool k5_site(K5Site & S, const BatchView & v, int64_t gp_zb) {
+    S.ti = v.pos_tile[gp_zb];
+    const TileInfo & T = v.tiles[S.ti];
+    S.T = &T;
+    if (T.skipped) { return false; }
+    S.zb = (int32_t)(gp_zb - T.pos_off) + T.ext_beg;
+    if (S.zb < T.rpos_inclu_beg || S.zb > T.rpos_exclu_end) { return false; }
+    const uvcgpu_params & par = v.par;
+    S.nref = (T.ext_end - T.ext_beg) - 1;      // refstring.size()
+    S.minABQ_snv = (T.is_amplicon_inferred ? par.syserr_minABQ_pcr_snv : par.syserr_minABQ_cap_snv);
+    S.minABQ_indel = (T.is_amplicon_inferred ? par.syserr_minABQ_pcr_indel : par.syserr_minABQ_cap_indel);
+    const uint8_t *refsyms = v.refsym + T.pos_off;
+    const int32_t refidx = S.zb - T.ext_beg;
+    S.refsym_base = ((S.nref == (refidx - 1)) || (-1 == (refidx - 1))) ? UVC_BASE_NN : (int)refsyms[refidx - 1];
+    S.prev_base1 = ((refidx >= 2) ? (int)refsyms[refidx - 2] : UVC_BASE_NN);
+    S.prev_base2 = ((refidx >= 3) ? (int)refsyms[refidx - 3] : UVC_BASE_NN);
+    S.next_base1 = ((refidx < S.nref) ? (int)refsyms[refidx] : UVC_BASE_NN);
+    S.next_base2 = ((refidx + 1 < S.nref) ? (int)refsyms[refidx + 1] : UVC_BASE_NN);
+    return true;
+}
+
+// K5b. Pass 0 counts the candidates of the two groups, pass 1 writes their descriptors into the reserved slots (same enumeration twice: the
+// order of the candidates inside a group is the reference's, main.cpp:832-905).
+UVC_HD void k5b_list_position(const BatchView & v, const ScoreView & sv, int64_t gp_zb) {
+    K5Site S;
+    if (!k5_site(S, v, gp_zb)) { return; }
+    const TileInfo & T = *S.T;
+    const uvcgpu_params & par = v.par;
     int32_t ins_cdepth = 0, del_cdepth = 0, ins1_cdepth = 0, del1_cdepth = 0;
-    int32_t curr_vAC[2] = {0, 0};
-    int32_t nlodq_site[2] = {0, 0};
-    bool active[2] = {false, false};
+    int32_t ncand[2] = {0, 0}, first[2] = {0, 0}, gidx[2] = {-1, -1};
+    for (int pass = 0; pass < 2; pass++) {
+        if (1 == pass) {
+            const int32_t ng = (ncand[0] > 0 ? 1 : 0) + (ncand[1] > 0 ? 1 : 0);
+            if (0 == ng) { return; }
+            const int32_t g0 = atomic_add_i32(sv.out_cursor + 2, ng);
+            const int32_t c0 = atomic_add_i32(sv.out_cursor + 3, ncand[0] + ncand[1]);
+            if (g0 + ng > sv.group_cap || c0 + ncand[0] + ncand[1] > sv.cand_cap) { return; }     // (the host sees the totals and runs again with room for all)
+            int32_t gi = g0;
+            if (ncand[0] > 0) { gidx[0] = gi++; }
+            if (ncand[1] > 0) { gidx[1] = gi++; }
+            first[0] = c0; first[1] = c0 + ncand[0];
+            int32_t repeatunit_len = 0, repeatnum = 0;
+            repeat_at(repeatunit_len, repeatnum, v, T, S.zb - T.ext_beg);
+            for (int type = 0; type < 2; type++) {
+                if (gidx[type] < 0) { continue; }
+                GroupRec & G = sv.groups[gidx[type]];
+                const int32_t refpos = (type == 0 ? S.zb - 1 : S.zb);
+                G.gp = T.pos_off + (refpos - T.ext_beg);
+                G.tile = S.ti; G.refpos = refpos; G.type = type; G.refsymbol = (type == 0 ? S.refsym_base : UVC_LINK_M);
+                G.first = first[type]; G.n = ncand[type]; G.partner = gidx[1 - type];
+                G.ins_cdepth = ins_cdepth; G.del_cdepth = del_cdepth; G.ins1_cdepth = ins1_cdepth; G.del1_cdepth = del1_cdepth;
+                G.repeatunit_len = repeatunit_len; G.repeatnum = repeatnum;
+            }
+            ncand[0] = ncand[1] = 0;
+        }
+        for (int type = 0; type < 2; type++) {
+            if (S.zb == T.rpos_inclu_beg && type == 0) { continue; }
+            const int32_t refpos = (type == 0 ? S.zb - 1 : S.zb);
+            const int64_t gp = T.pos_off + (refpos - T.ext_beg);
+            const int refsymbol = (type == 0 ? S.refsym_base : UVC_LINK_M);
+            const PosPtrs P = pos_ptrs(v, gp);
+            int32_t BDP = 0;
+            for (int k = 0; k < type_nsym(type); k++) { const int sy = type_symbol(type, k); BDP += P.fd0[sy * 3] + P.fd1[sy * 3]; }
+            const int32_t ref_bdepth = P.fd0[refsymbol * 3] + P.fd1[refsymbol * 3];
+            for (int k = 0; k < type_nsym(type); k++) {
+                const int symbol = type_symbol(type, k);
+                const int32_t bdepth = P.fd0[symbol * 3] + P.fd1[symbol * 3];
+                const int32_t cdepth = tmax(P.fm0[symbol * UVCGPU_NUM_FAM_DEPTHS + 0], P.fm0[symbol * UVCGPU_NUM_FAM_DEPTHS + 1])
+                                     + tmax(P.fm1[symbol * UVCGPU_NUM_FAM_DEPTHS + 0], P.fm1[symbol * UVCGPU_NUM_FAM_DEPTHS + 1]);
+                if (0 == pass) {
+                    if (is_ins_symbol(symbol)) { ins_cdepth += cdepth; if (UVC_LINK_I1 == symbol) { ins1_cdepth += cdepth; } }
+                    else if (is_del_symbol(symbol)) { del_cdepth += cdepth; if (UVC_LINK_D1 == symbol) { del1_cdepth += cdepth; } }
+                }
+                if (!symbol_is_candidate(par, refsymbol, symbol, bdepth, BDP, ref_bdepth)) { continue; }
+                const bool is_homopol_1bp = (S.prev_base1 == refsymbol && S.next_base1 == refsymbol);
+                const bool is_homopol_2bp = (S.prev_base2 == refsymbol && S.next_base2 == refsymbol);
+                const int32_t minABQ = (is_subst(symbol) ? nnminus(S.minABQ_snv, (is_homopol_1bp ? (is_homopol_2bp ? 20 : 10) : 0)) : S.minABQ_indel);
+                #define UVC_K5B_ADD(bDPa_, cDP0a_, ev_, len_) { \
+                    if (ncand[type] < UVC_MAX_GROUP_CANDS) { \
+                        if (1 == pass) { CandDesc & d = sv.desc[first[type] + ncand[type]]; d.group = gidx[type]; d.symbol = symbol; d.bDPa = (bDPa_); d.cDP0a = (cDP0a_); d.ev = (ev_); d.gap_len = (len_); d.minABQ = minABQ; } \
+                        ncand[type]++; } }
+                if (is_ins_symbol(symbol) || is_del_symbol(symbol)) {
+                    int32_t na = 0;
+                    const IndelAllele *al = find_alleles(sv, gp, symbol, na);
+                    for (int32_t a = 0; a < na; a++) { UVC_K5B_ADD(al[a].bAD, al[a].cAD, al[a].ev, al[a].len) }
+                    if (0 == na) {
+                        // no read carries this indel symbol here (only reachable with all-out): one placeholder allele whose string is the symbol's
+                        // description, e.g. "<LI1>" (indel_get_majority, main.hpp:5412-5418)
+                        const int32_t desc_len = ((UVC_LINK_D3P == symbol || UVC_LINK_I3P == symbol) ? 6 : 5);
+                        UVC_K5B_ADD(0, 0, -1, desc_len)
+                    }
+                } else { UVC_K5B_ADD(bdepth, cdepth, -1, 0) }
+                #undef UVC_K5B_ADD
+            }
+        }
+    }
+}
+
+// K5g: BcfFormat_symboltype_init of one group
+UVC_HD void k5g_group(const BatchView & v, const ScoreView & sv, int64_t gi) {
+    GroupRec & G = sv.groups[gi];
+    group_init(G.g, pos_ptrs(v, G.gp), G.type);
+}
+
+// K5c: one candidate through BcfFormat_symbol_init and BcfFormat_symbol_calc_DPv; its six depth values are added to the group's sums
+// (BcfFormat_symbol_sum_DPv, main.hpp:4888-4906: integer adds, any order)
+UVC_HD void k5c_candidate(const BatchView & v, const ScoreView & sv, int64_t ci) {
+    const CandDesc d = sv.desc[ci];
+    GroupRec & G = sv.groups[d.group];
+    const TileInfo & T = v.tiles[G.tile];
     const uvcgpu_rtr *rtr = v.rtr + T.pos_off;
     const int32_t nrtr = T.ext_end - T.ext_beg;
-    for (int type = 0; type < 2; type++) {
-        if (zb == T.rpos_inclu_beg && type == 0) { continue; }
-        active[type] = true;
-        const int32_t refpos = (type == 0 ? zb - 1 : zb);
-        const int64_t gp = T.pos_off + (refpos - T.ext_beg);
-        const int refsymbol = (type == 0 ? refsym_base : UVC_LINK_M);
-        const PosPtrs P = pos_ptrs(v, gp);
-        group_init(G[type], P, type);
-        const int32_t BDP = G[type].BDPb[0] + G[type].BDPb[1];
-        const int32_t ref_bdepth = P.fd0[refsymbol * 3] + P.fd1[refsymbol * 3];
-        const uvcgpu_rtr & rtr1 = rtr[tmax(refpos - T.ext_beg, 3) - 3];
-        const uvcgpu_rtr & rtr2 = rtr[tmin(refpos - T.ext_beg + 3, nrtr - 1)];
-        for (int k = 0; k < type_nsym(type); k++) {
-            const int symbol = type_symbol(type, k);
-            const int32_t bdepth = P.fd0[symbol * 3] + P.fd1[symbol * 3];
-            const int32_t cdepth = tmax(P.fm0[symbol * UVCGPU_NUM_FAM_DEPTHS + 0], P.fm0[symbol * UVCGPU_NUM_FAM_DEPTHS + 1])
-                                 + tmax(P.fm1[symbol * UVCGPU_NUM_FAM_DEPTHS + 0], P.fm1[symbol * UVCGPU_NUM_FAM_DEPTHS + 1]);
-            if (is_ins_symbol(symbol)) { ins_cdepth += cdepth; if (UVC_LINK_I1 == symbol) { ins1_cdepth += cdepth; } }
-            else if (is_del_symbol(symbol)) { del_cdepth += cdepth; if (UVC_LINK_D1 == symbol) { del1_cdepth += cdepth; } }
-            if (!symbol_is_candidate(par, refsymbol, symbol, bdepth, BDP, ref_bdepth)) { continue; }
-            const bool is_homopol_1bp = (prev_base1 == refsymbol && next_base1 == refsymbol);
-            const bool is_homopol_2bp = (prev_base2 == refsymbol && next_base2 == refsymbol);
-            const int32_t minABQ = (is_subst(symbol) ? nnminus(minABQ_snv, (is_homopol_1bp ? (is_homopol_2bp ? 20 : 10) : 0)) : minABQ_indel);
-            if (is_ins_symbol(symbol) || is_del_symbol(symbol)) {
-                int32_t na = 0;
-                const IndelAllele *al = find_alleles(sv, gp, symbol, na);
-                for (int32_t a = 0; a < na && ncand[type] < UVC_MAX_GROUP_CANDS; a++) {
-                    CandFmt & c = C[type][ncand[type]++];
-                    cand_init(c, G[type], v, P, symbol, al[a].bAD, al[a].cAD, al[a].ev, al[a].len, minABQ);
-                    calc_DPv(c, G[type], v, *P.prep, rtr1, rtr2, refsymbol);
-                }
-                if (0 == na && ncand[type] < UVC_MAX_GROUP_CANDS) {
-                    // no read carries this indel symbol here (only reachable with all-out): one placeholder allele whose string is the symbol's
-                    // description, e.g. "<LI1>" (indel_get_majority, main.hpp:5412-5418)
-                    const int32_t desc_len = ((UVC_LINK_D3P == symbol || UVC_LINK_I3P == symbol) ? 6 : 5);
-                    CandFmt & c = C[type][ncand[type]++];
-                    cand_init(c, G[type], v, P, symbol, 0, 0, -1, desc_len, minABQ);
-                    calc_DPv(c, G[type], v, *P.prep, rtr1, rtr2, refsymbol);
-                }
-            } else if (ncand[type] < UVC_MAX_GROUP_CANDS) {
-                CandFmt & c = C[type][ncand[type]++];
-                cand_init(c, G[type], v, P, symbol, bdepth, cdepth, -1, 0, minABQ);
-                calc_DPv(c, G[type], v, *P.prep, rtr1, rtr2, refsymbol);
-            }
+    const uvcgpu_rtr & rtr1 = rtr[tmax(G.refpos - T.ext_beg, 3) - 3];
+    const uvcgpu_rtr & rtr2 = rtr[tmin(G.refpos - T.ext_beg + 3, nrtr - 1)];
+    const PosPtrs P = pos_ptrs(v, G.gp);
+    CandFmt c;
+    cand_init(c, G.g, v, P, d.symbol, d.bDPa, d.cDP0a, d.ev, d.gap_len, d.minABQ);
+    calc_DPv(c, G.g, v, *P.prep, rtr1, rtr2, G.refsymbol);
+    c.cMmQ = c.aAaMQ = c.bMQQ = c.bIAQ = c.cIAQ = c.cPCQ1 = c.cPLQ1 = c.cPCQ2 = c.cPLQ2 = c.bTINQ = c.cTINQ = c.gVQ1 = c.cVQ1 = c.cVQ2 = c.dVQinc = c.CONTQ = 0;
+    sv.cands[ci] = c;
+    atomic_add_i32(&G.g.CDP1v[0], c.cDP1v); atomic_add_i32(&G.g.CDP1w[0], c.cDP1w); atomic_add_i32(&G.g.CDP1x[0], c.cDP1x);
+    atomic_add_i32(&G.g.CDP2v[0], c.cDP2v); atomic_add_i32(&G.g.CDP2w[0], c.cDP2w); atomic_add_i32(&G.g.CDP2x[0], c.cDP2x);
+    if (UVC_BASE_NN == c.symbol || UVC_LINK_NN == c.symbol) {
+        G.g.CDP1v[1] = c.cDP1v; G.g.CDP1w[1] = c.cDP1w; G.g.CDP1x[1] = c.cDP1x; G.g.CDP2v[1] = c.cDP2v; G.g.CDP2w[1] = c.cDP2w; G.g.CDP2x[1] = c.cDP2x;
+    }
+}
+
+// K5e: BcfFormat_symbol_calc_qual of one candidate
+UVC_HD void k5e_candidate(const BatchView & v, const ScoreView & sv, int64_t ci) {
+    const CandDesc d = sv.desc[ci];
+    const GroupRec & G = sv.groups[d.group];
+    const TileInfo & T = v.tiles[G.tile];
+    const uvcgpu_rtr *rtr = v.rtr + T.pos_off;
+    const int32_t nrtr = T.ext_end - T.ext_beg;
+    const uvcgpu_rtr & rtr1 = rtr[tmax(G.refpos - T.ext_beg, 3) - 3];
+    const uvcgpu_rtr & rtr2 = rtr[tmin(G.refpos - T.ext_beg + 3, nrtr - 1)];
+    CandFmt c = sv.cands[ci];
+    calc_qual(c, G.g, v, v.prep[G.gp], rtr1, rtr2, G.refsymbol, G.ins_cdepth, G.del_cdepth, G.ins1_cdepth, G.del1_cdepth, G.repeatunit_len, G.repeatnum);
+    CandFmt & o = sv.cands[ci];
+    o.cMmQ = c.cMmQ; o.aAaMQ = c.aAaMQ; o.bMQQ = c.bMQQ; o.bIAQ = c.bIAQ; o.cIAQ = c.cIAQ; o.cPCQ1 = c.cPCQ1; o.cPLQ1 = c.cPLQ1; o.cPCQ2 = c.cPCQ2; o.cPLQ2 = c.cPLQ2;
+    o.bTINQ = c.bTINQ; o.cTINQ = c.cTINQ; o.gVQ1 = c.gVQ1; o.cVQ1 = c.cVQ1; o.cVQ2 = c.cVQ2; o.dVQinc = c.dVQinc; o.CONTQ = c.CONTQ;
+}
+
+// number of non-reference alleles of a group that reach the tri-allelic threshold (curr_vAC, main.cpp:975-980)
+UVC_HD int32_t k5_vac(const BatchView & v, const ScoreView & sv, int32_t gi) {
+    if (gi < 0) { return 0; }
+    const GroupRec & G = sv.groups[gi];
+    const int32_t het3al = (G.type == 0 ? v.par.germ_phred_het3al_snp : v.par.germ_phred_het3al_indel);
+    int32_t n = 0;
+    for (int i = 0; i < G.n; i++) { const CandFmt & c = sv.cands[G.first + i]; if (G.refsymbol != c.symbol && tmax(c.cVQ1, c.cVQ2) >= het3al) { n++; } }
+    return n;
+}
+
+// K5f: the records of one group (third loop, main.cpp:1073-1171 + append_vcf_record)
+UVC_HD void k5f_group(const BatchView & v, const ScoreView & sv, int64_t gi) {
+    const GroupRec & G = sv.groups[gi];
+    const uvcgpu_params & par = v.par;
+    const TileInfo & T = v.tiles[G.tile];
+    const int type = G.type, refsymbol = G.refsymbol;
+    const CandFmt *C = sv.cands + G.first;
+    const int ncand = G.n;
+    const GroupFmt & g = G.g;
+    int32_t curr_vAC[2];
+    curr_vAC[type] = k5_vac(v, sv, (int32_t)gi); curr_vAC[1 - type] = k5_vac(v, sv, G.partner);
+    int refi = -1;
+    for (int i = 0; i < ncand; i++) { if (C[i].symbol == refsymbol) { refi = i; } }
+    if (refi < 0) { return; }   // the reference aborts here ("has no REF allele")
+    const int32_t nlodq_site = germline_nlodq(v, C, ncand, type, refsymbol);
+    // top-2 non-reference alleles by (max(cVQ1, cVQ2), cVQ1, cVQ2, symbol, indel string) descending (main.cpp:1000):
+    int top[2] = {-1, -1};
+    for (int r = 0; r < 2; r++) {
+        for (int i = 0; i < ncand; i++) {
+            const CandFmt & c = C[i];
+            if (c.symbol == refsymbol || i == top[0]) { continue; }
+            if (top[r] < 0) { top[r] = i; continue; }
+            const CandFmt & b = C[top[r]];
+            const int32_t mc = tmax(c.cVQ1, c.cVQ2), mb = tmax(b.cVQ1, b.cVQ2);
+            if (mc > mb || (mc == mb && (c.cVQ1 > b.cVQ1 || (c.cVQ1 == b.cVQ1 && (c.cVQ2 > b.cVQ2 || (c.cVQ2 == b.cVQ2 && (c.symbol > b.symbol || (c.symbol == b.symbol && allele_string_cmp(v, c, b) > 0)))))))) { top[r] = i; }
         }
     }
-    for (int type = 0; type < 2; type++) {
-        if (!active[type] || 0 == ncand[type]) { continue; }
-        const int32_t refpos = (type == 0 ? zb - 1 : zb);
-        const int64_t gp = T.pos_off + (refpos - T.ext_beg);
-        const int refsymbol = (type == 0 ? refsym_base : UVC_LINK_M);
-        const uvcgpu_rtr & rtr1 = rtr[tmax(refpos - T.ext_beg, 3) - 3];
-        const uvcgpu_rtr & rtr2 = rtr[tmin(refpos - T.ext_beg + 3, nrtr - 1)];
-        GroupFmt & g = G[type];
-        // BcfFormat_symbol_sum_DPv
-        for (int i = 0; i < ncand[type]; i++) {
-            const CandFmt & c = C[type][i];
-            g.CDP1v[0] += c.cDP1v; g.CDP1w[0] += c.cDP1w; g.CDP1x[0] += c.cDP1x; g.CDP2v[0] += c.cDP2v; g.CDP2w[0] += c.cDP2w; g.CDP2x[0] += c.cDP2x;
-            if (UVC_BASE_NN == c.symbol || UVC_LINK_NN == c.symbol) { g.CDP1v[1] = c.cDP1v; g.CDP1w[1] = c.cDP1w; g.CDP1x[1] = c.cDP1x; g.CDP2v[1] = c.cDP2v; g.CDP2w[1] = c.cDP2w; g.CDP2x[1] = c.cDP2x; }
-        }
-        const int32_t het3al = (type == 0 ? par.germ_phred_het3al_snp : par.germ_phred_het3al_indel);
-        for (int i = 0; i < ncand[type]; i++) {
-            CandFmt & c = C[type][i];
-            calc_qual(c, g, v, v.prep[gp], rtr1, rtr2, refsymbol, ins_cdepth, del_cdepth, ins1_cdepth, del1_cdepth, repeatunit_len, repeatnum);
-            if (refsymbol != c.symbol && tmax(c.cVQ1, c.cVQ2) >= het3al) { curr_vAC[type] += 1; }
-        }
-        nlodq_site[type] = germline_nlodq(v, C[type], ncand[type], type, refsymbol);
-    }
-    // records (third loop, main.cpp:1073-1171 + append_vcf_record)
-    for (int type = 0; type < 2; type++) {
-        if (!active[type] || 0 == ncand[type]) { continue; }
-        const int32_t refpos = (type == 0 ? zb - 1 : zb);
-        const int64_t gp = T.pos_off + (refpos - T.ext_beg);
-        const int refsymbol = (type == 0 ? refsym_base : UVC_LINK_M);
-        const GroupFmt & g = G[type];
-        int refi = -1;
-        for (int i = 0; i < ncand[type]; i++) { if (C[type][i].symbol == refsymbol) { refi = i; } }
-        if (refi < 0) { continue; }   // the reference aborts here ("has no REF allele")
-        // top-2 non-reference alleles by (max(cVQ1, cVQ2), cVQ1, cVQ2, symbol, indel string) descending (main.cpp:1000): 
-        int top[2] = {-1, -1};
+    const CandFmt & R = C[refi];
+    const uvcgpu_rtr *rtr = v.rtr + T.pos_off;
+    const int32_t nrtr = T.ext_end - T.ext_beg;
+    const int32_t refpos = G.refpos;
+    for (int i = 0; i < ncand; i++) {
+        const CandFmt & c = C[i];
+        const int symbol = c.symbol;
+        if (!(par.outvar_flag & 0x4)) { continue; }
+        if (((UVC_BASE_NN == symbol) && !(0x20 & par.outvar_flag)) || ((UVC_LINK_NN == symbol) && !(0x40 & par.outvar_flag))) { continue; }
+        const int32_t germ_phred = (is_subst(symbol) ? par.germ_phred_hetero_snp : par.germ_phred_hetero_indel);
+        const int32_t nlodq1 = nlodq_site - 3 + germ_phred;
+        // fill_tki (a = 1: this allele) and fill_conditional_tki<true>
+        const int32_t tki_BDP = g.BDPb[0] + g.BDPb[1], tki_bDP = c.bDPf + c.bDPr;
+        const int32_t tki_CDP1x = g.CDP1x[0], tki_cDP1x = c.cDP1x, tki_CDP2x = g.CDP2x[0], tki_cDP2x = c.cDP2x;
+        const int32_t inc_snp = tmax(0, 2 * par.germ_phred_hetero_snp - par.germ_phred_het3al_snp - 0);
+        const int32_t inc_indel = tmax(0, 2 * par.germ_phred_hetero_indel - par.germ_phred_het3al_indel - 0);
+        int32_t het3al_inc = (is_subst(symbol) ? inc_snp : inc_indel);
+        if (is_ins_symbol(symbol) || is_del_symbol(symbol)) { het3al_inc = nnminus(inc_indel + 1, c.gap_len); }
+        const int32_t tn_dec_by_xm = between(tmin(c.bNMQ, c.bNMQ), par.microadjust_syserr_MQ_NMR_tn_syserr_no_penal_qual_min, par.microadjust_syserr_MQ_NMR_tn_syserr_no_penal_qual_max)
+                - par.microadjust_syserr_MQ_NMR_tn_syserr_no_penal_qual_min;
+        const int32_t prior_phred = 3;
+        int32_t bq4[4], cq4[4];
+        tn_quals(bq4, v, (tki_cDP1x + 0.5) / 100.0 + 0.0, (tki_CDP1x + 1.0) / 100.0 + 0.0, c.cVQ1, c.cPCQ1, (0 + 0.5) / 100.0 + 0.0, (0 + 1.0) / 100.0 + 0.0,
+                nnminus(0, het3al_inc), par.tn_syserr_norm_devqual, prior_phred, tn_dec_by_xm, par.powlaw_exponent);
+        // FORMAT_UNCOV: converted_nfm_cVQ2 = 0 - 3 * (0 + 1) / (0 + 1) = -3
+        tn_quals(cq4, v, (tki_cDP2x + 0.5) / 100.0 + 0.0, (tki_CDP2x + 1.0) / 100.0 + 0.0, c.cVQ2, c.cPCQ2, (0 + 0.5) / 100.0 + 0.0, (0 + 1.0) / 100.0 + 0.0,
+                nnminus(0, tmax(het3al_inc, 3) - 3), par.tn_syserr_norm_devqual, prior_phred, tmax(tn_dec_by_xm, tmin(tmax(0, -3), 8 + 4)), par.powlaw_exponent);
+        const int32_t tlodq1 = tmax(bq4[3], cq4[3]);
+        const bool is_CT = ((UVC_BASE_C == refsymbol && UVC_BASE_T == symbol) || (UVC_BASE_G == refsymbol && UVC_BASE_A == symbol));
+        const double b_min_tlodq = 2 + 3 - (-10 * log((tki_bDP + 1e-3) / (tki_BDP + 1)) / v.ln10) / 10.0;
+        const double c2v_min_tlodq = 2 + 5 - (-10 * log((tki_cDP2x * 0.01 + 1e-5) / (tki_CDP2x * 0.01 + 1) / (is_CT ? 5 : 1)) / v.ln10) / 10.0;
+        const float lowestVAQ = (float)dmax(b_min_tlodq, c2v_min_tlodq);
+        const int32_t tlodq = ((tlodq1 >= 10) ? tlodq1 : (tlodq1 * 3 - 20));
+        const int32_t nlodq = nlodq1;
+        const int32_t somaticq = tmin(tlodq, nlodq);
+        float vq = ((float)tlodq > lowestVAQ ? (float)tlodq : lowestVAQ);
+        if (vq < 10.0f) { const float base = (float)pow(10.0, 0.1); vq = log1pf(powf(base, vq)) / logf(base); }   // calc_non_negative<float>
+        const int32_t vad1curr = c.aBQ2, vdp1curr = g.ABQ2[0], vad2curr = tki_bDP, vdp2curr = tki_BDP;
+        const bool keep_var = (((vq >= par.vqual)
+                || ((vad1curr >= par.vad1 && vdp1curr >= par.vdp1 && (vdp1curr * par.vfa1) <= vad1curr)
+                 || (vad2curr >= par.vad2 && vdp2curr >= par.vdp2 && (vdp2curr * par.vfa2) <= vad2curr)))
+                && (symbol != refsymbol || (par.should_output_all)));
+        const int32_t min_ad = ((symbol == refsymbol) ? par.min_r_ad : par.min_a_ad);
+        if (!(keep_var && tki_bDP >= min_ad)) { continue; }
+        const int32_t slot = atomic_add_i32(sv.out_cursor, 1);
+        if (slot >= sv.out_cap) { continue; }
+        VarRec & o = sv.out[slot];
+        o.gp = G.gp; o.tile = G.tile; o.refpos = refpos; o.symboltype = type; o.refsymbol = refsymbol; o.cand_index = i; o.pad0 = 0;
+        o.g = g; o.ref = R; o.alt = c;
+        o.DP = g.CDP1b[0] + g.CDP1b[1]; o.bDP = g.BDPb[0] + g.BDPb[1]; o.c2DP = g.CDP2b[0] + g.CDP2b[1];
         for (int r = 0; r < 2; r++) {
-            for (int i = 0; i < ncand[type]; i++) {
-                const CandFmt & c = C[type][i];
-                if (c.symbol == refsymbol || i == top[0]) { continue; }
-                if (top[r] < 0) { top[r] = i; continue; }
-                const CandFmt & b = C[type][top[r]];
-                const int32_t mc = tmax(c.cVQ1, c.cVQ2), mb = tmax(b.cVQ1, b.cVQ2);
-                if (mc > mb || (mc == mb && (c.cVQ1 > b.cVQ1 || (c.cVQ1 == b.cVQ1 && (c.cVQ2 > b.cVQ2 || (c.cVQ2 == b.cVQ2 && (c.symbol > b.symbol || (c.symbol == b.symbol && allele_string_cmp(v, c, b) > 0)))))))) { top[r] = i; }
-            }
+            o.cVQ1M[r] = (top[r] >= 0 ? C[top[r]].cVQ1 : (r == 0 ? -999 : 0));
+            o.cVQ2M[r] = (top[r] >= 0 ? C[top[r]].cVQ2 : (r == 0 ? -999 : 0));
+            o.cVQAM[r] = (top[r] >= 0 ? C[top[r]].symbol : (r == 0 ? UVC_NSYM : -1));
+            o.cVQSM_ev[r] = (top[r] >= 0 ? C[top[r]].ev : -1);
         }
-        const CandFmt & R = C[type][refi];
-        for (int i = 0; i < ncand[type]; i++) {
-            const CandFmt & c = C[type][i];
-            const int symbol = c.symbol;
-            if (!(par.outvar_flag & 0x4)) { continue; }
-            if (((UVC_BASE_NN == symbol) && !(0x20 & par.outvar_flag)) || ((UVC_LINK_NN == symbol) && !(0x40 & par.outvar_flag))) { continue; }
-            const int32_t germ_phred = (is_subst(symbol) ? par.germ_phred_hetero_snp : par.germ_phred_hetero_indel);
-            const int32_t nlodq1 = nlodq_site[type] - 3 + germ_phred;
-            // fill_tki (a = 1: this allele) and fill_conditional_tki<true>
-            const int32_t tki_BDP = g.BDPb[0] + g.BDPb[1], tki_bDP = c.bDPf + c.bDPr;
-            const int32_t tki_CDP1x = g.CDP1x[0], tki_cDP1x = c.cDP1x, tki_CDP2x = g.CDP2x[0], tki_cDP2x = c.cDP2x;
-            const int32_t inc_snp = tmax(0, 2 * par.germ_phred_hetero_snp - par.germ_phred_het3al_snp - 0);
-            const int32_t inc_indel = tmax(0, 2 * par.germ_phred_hetero_indel - par.germ_phred_het3al_indel - 0);
-            int32_t het3al_inc = (is_subst(symbol) ? inc_snp : inc_indel);
-            if (is_ins_symbol(symbol) || is_del_symbol(symbol)) { het3al_inc = nnminus(inc_indel + 1, c.gap_len); }
-            const int32_t tn_dec_by_xm = between(tmin(c.bNMQ, c.bNMQ), par.microadjust_syserr_MQ_NMR_tn_syserr_no_penal_qual_min, par.microadjust_syserr_MQ_NMR_tn_syserr_no_penal_qual_max)
-                    - par.microadjust_syserr_MQ_NMR_tn_syserr_no_penal_qual_min;
-            const int32_t prior_phred = 3;
-            int32_t bq4[4], cq4[4];
-            tn_quals(bq4, v, (tki_cDP1x + 0.5) / 100.0 + 0.0, (tki_CDP1x + 1.0) / 100.0 + 0.0, c.cVQ1, c.cPCQ1, (0 + 0.5) / 100.0 + 0.0, (0 + 1.0) / 100.0 + 0.0,
-                    nnminus(0, het3al_inc), par.tn_syserr_norm_devqual, prior_phred, tn_dec_by_xm, par.powlaw_exponent);
-            // FORMAT_UNCOV: converted_nfm_cVQ2 = 0 - 3 * (0 + 1) / (0 + 1) = -3
-            tn_quals(cq4, v, (tki_cDP2x + 0.5) / 100.0 + 0.0, (tki_CDP2x + 1.0) / 100.0 + 0.0, c.cVQ2, c.cPCQ2, (0 + 0.5) / 100.0 + 0.0, (0 + 1.0) / 100.0 + 0.0,
-                    nnminus(0, tmax(het3al_inc, 3) - 3), par.tn_syserr_norm_devqual, prior_phred, tmax(tn_dec_by_xm, tmin(tmax(0, -3), 8 + 4)), par.powlaw_exponent);
-            const int32_t tlodq1 = tmax(bq4[3], cq4[3]);
-            const bool is_CT = ((UVC_BASE_C == refsymbol && UVC_BASE_T == symbol) || (UVC_BASE_G == refsymbol && UVC_BASE_A == symbol));
-            const double b_min_tlodq = 2 + 3 - (-10 * log((tki_bDP + 1e-3) / (tki_BDP + 1)) / v.ln10) / 10.0;
-            const double c2v_min_tlodq = 2 + 5 - (-10 * log((tki_cDP2x * 0.01 + 1e-5) / (tki_CDP2x * 0.01 + 1) / (is_CT ? 5 : 1)) / v.ln10) / 10.0;
-            const float lowestVAQ = (float)dmax(b_min_tlodq, c2v_min_tlodq);
-            const int32_t tlodq = ((tlodq1 >= 10) ? tlodq1 : (tlodq1 * 3 - 20));
-            const int32_t nlodq = nlodq1;
-            const int32_t somaticq = tmin(tlodq, nlodq);
-            float vq = ((float)tlodq > lowestVAQ ? (float)tlodq : lowestVAQ);
-            if (vq < 10.0f) { const float base = (float)pow(10.0, 0.1); vq = log1pf(powf(base, vq)) / logf(base); }   // calc_non_negative<float>
-            const int32_t vad1curr = c.aBQ2, vdp1curr = g.ABQ2[0], vad2curr = tki_bDP, vdp2curr = tki_BDP;
-            const bool keep_var = (((vq >= par.vqual)
-                    || ((vad1curr >= par.vad1 && vdp1curr >= par.vdp1 && (vdp1curr * par.vfa1) <= vad1curr)
-                     || (vad2curr >= par.vad2 && vdp2curr >= par.vdp2 && (vdp2curr * par.vfa2) <= vad2curr)))
-                    && (symbol != refsymbol || (par.should_output_all)));
-            const int32_t min_ad = ((symbol == refsymbol) ? par.min_r_ad : par.min_a_ad);
-            if (!(keep_var && tki_bDP >= min_ad)) { continue; }
-#if defined(__CUDA_ARCH__)
-            const int32_t slot = atomicAdd(sv.out_cursor, 1);
-#else
-            const int32_t slot = *sv.out_cursor; *sv.out_cursor += 1;
-#endif
-            if (slot >= sv.out_cap) { continue; }
-            VarRec & o = sv.out[slot];
-            o.gp = gp; o.tile = ti; o.refpos = refpos; o.symboltype = type; o.refsymbol = refsymbol; o.cand_index = i; o.pad0 = 0;
-            o.g = g; o.ref = R; o.alt = c;
-            o.DP = g.CDP1b[0] + g.CDP1b[1]; o.bDP = g.BDPb[0] + g.BDPb[1]; o.c2DP = g.CDP2b[0] + g.CDP2b[1];
-            for (int r = 0; r < 2; r++) {
-                o.cVQ1M[r] = (top[r] >= 0 ? C[type][top[r]].cVQ1 : (r == 0 ? -999 : 0));
-                o.cVQ2M[r] = (top[r] >= 0 ? C[type][top[r]].cVQ2 : (r == 0 ? -999 : 0));
-                o.cVQAM[r] = (top[r] >= 0 ? C[type][top[r]].symbol : (r == 0 ? UVC_NSYM : -1));
-                o.cVQSM_ev[r] = (top[r] >= 0 ? C[type][top[r]].ev : -1);
-            }
-            o.vHGQ = nlodq1; o.vAC[0] = curr_vAC[0]; o.vAC[1] = curr_vAC[1];
-            o.vNLODQ[0] = (type == 0 ? nlodq_site[0] : 0); o.vNLODQ[1] = (type == 1 ? nlodq_site[1] : 0);
-            o.tlodq = tlodq; o.nlodq = nlodq; o.somaticq = somaticq;
-            for (int r = 0; r < 4; r++) { o.TNBQF[r] = bq4[r]; o.TNCQF[r] = cq4[r]; }
-            o.tbDP = tki_BDP; o.tDP = o.DP; o.tAD[0] = R.AD; o.tAD[1] = c.AD;
-            o.t2DP = (g.CDPDb[0] + g.CDPDb[1]) + (g.DDP2[0] + g.DDP2[1]);
-            o.t2AD[0] = R.cDPDf + R.cDPDr + R.dDP2;
-            o.t2AD[1] = c.cDPDf + c.cDPDr + c.dDP2;   // indel alleles: replaced on the host by the allele's own gc2dAD sum
-            o.vcfqual = vq; o.lowestVAQ = lowestVAQ;
-            o.repeatnum = repeatnum; o.repeatunit_len = repeatunit_len;
-            const int32_t adj = par.indel_adj_tracklen_dist;
-            const uvcgpu_rtr & q1 = rtr[tmax(refpos - T.ext_beg, adj) - adj];
-            const uvcgpu_rtr & q2 = rtr[tmin(refpos - T.ext_beg + adj, nrtr - adj)];   // QUIRK: size - dist, not size - 1 (main.hpp:6101)
-            o.rtr_info[0] = ((0 == q1.tracklen) ? 0 : (T.ext_beg + q1.begpos)); o.rtr_info[1] = q1.tracklen; o.rtr_info[2] = q1.unitlen;
-            o.rtr_info[3] = ((0 == q2.tracklen) ? 0 : (T.ext_beg + q2.begpos)); o.rtr_info[4] = q2.tracklen; o.rtr_info[5] = q2.unitlen;
-        }
+        o.vHGQ = nlodq1; o.vAC[0] = curr_vAC[0]; o.vAC[1] = curr_vAC[1];
+        o.vNLODQ[0] = (type == 0 ? nlodq_site : 0); o.vNLODQ[1] = (type == 1 ? nlodq_site : 0);
+        o.tlodq = tlodq; o.nlodq = nlodq; o.somaticq = somaticq;
+        for (int r = 0; r < 4; r++) { o.TNBQF[r] = bq4[r]; o.TNCQF[r] = cq4[r]; }
+        o.tbDP = tki_BDP; o.tDP = o.DP; o.tAD[0] = R.AD; o.tAD[1] = c.AD;
+        o.t2DP = (g.CDPDb[0] + g.CDPDb[1]) + (g.DDP2[0] + g.DDP2[1]);
+        o.t2AD[0] = R.cDPDf + R.cDPDr + R.dDP2;
+        o.t2AD[1] = c.cDPDf + c.cDPDr + c.dDP2;   // indel alleles: replaced on the host by the allele's own gc2dAD sum
+        o.vcfqual = vq; o.lowestVAQ = lowestVAQ;
+        o.repeatnum = G.repeatnum; o.repeatunit_len = G.repeatunit_len;
+        const int32_t adj = par.indel_adj_tracklen_dist;
+        const uvcgpu_rtr & q1 = rtr[tmax(refpos - T.ext_beg, adj) - adj];
+        const uvcgpu_rtr & q2 = rtr[tmin(refpos - T.ext_beg + adj, nrtr - adj)];   // QUIRK: size - dist, not size - 1 (main.hpp:6101)
+        o.rtr_info[0] = ((0 == q1.tracklen) ? 0 : (T.ext_beg + q1.begpos)); o.rtr_info[1] = q1.tracklen; o.rtr_info[2] = q1.unitlen;
+        o.rtr_info[3] = ((0 == q2.tracklen) ? 0 : (T.ext_beg + q2.begpos)); o.rtr_info[4] = q2.tracklen; o.rtr_info[5] = q2.unitlen;
     }
 }
 
