@@ -245,6 +245,14 @@ def decode_sub_batches(ds, tiles, n_sub, threads, only=None):
     return subs
 
 
+def host_call_stats(lib):
+    """uvcgpu_host_call_stats: total ms, calls and longest call per kind of driver call, process-wide."""
+    buf = (C.c_double * 21)()
+    lib.uvcgpu_host_call_stats.restype = C.c_int
+    lib.uvcgpu_host_call_stats(buf, 21)
+    return list(buf)
+
+
 def host_cpu_times():
     """Aggregate jiffies of /proc/stat: (user + nice, system + irq + softirq, idle + iowait, steal)."""
     try:
@@ -619,7 +627,7 @@ def main():
     ctx0.lib.uvcgpu_staging_backlog.restype = C.c_int
     ctx0.lib.uvcgpu_staging_pinned_bytes.restype = C.c_int64
     stable = 0
-    for _ in range(8):
+    for _ in range(12):
         t_wait = time.time()
         while ctx0.lib.uvcgpu_staging_backlog() > 0 and time.time() - t_wait < 10.0:
             time.sleep(0.05)
@@ -627,7 +635,7 @@ def main():
         e2e_steps(1)
         grown = (ctx0.lib.uvcgpu_staging_backlog() > 0 or int(ctx0.lib.uvcgpu_staging_pinned_bytes()) != before)
         stable = 0 if grown else stable + 1
-        if stable >= 2:
+        if stable >= 3:
             break
     backlog0 = int(ctx0.lib.uvcgpu_staging_backlog())
     pinned0 = int(ctx0.lib.uvcgpu_staging_pinned_bytes())
@@ -635,6 +643,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     cpu0 = host_cpu_times()
+    calls0 = host_call_stats(ctx0.lib)
     t0 = time.time()
     acc = e2e_steps(args.steps, keep_last=True)
     for k in totals:
@@ -642,6 +651,10 @@ def main():
     torch.cuda.synchronize()
     wall_s = time.time() - t0
     host_load = host_cpu_load(cpu0, host_cpu_times())
+    calls1 = host_call_stats(ctx0.lib)
+    call_stats = {name: {"ms_per_step": (calls1[3 * i] - calls0[3 * i]) / args.steps, "calls_per_step": (calls1[3 * i + 1] - calls0[3 * i + 1]) / args.steps,
+                         "longest_ms_since_start": calls1[3 * i + 2]}
+                  for i, name in enumerate(("device_alloc", "device_free", "memset", "copy_enqueue", "kernel_launches", "event_waits"))}
     backlog1 = int(ctx0.lib.uvcgpu_staging_backlog())
     sampler.stop_flag = True
     body = b"".join(last_text[k] for k in sorted(last_text))
@@ -800,6 +813,7 @@ def main():
                     "call_ms_per_step_summed_over_contexts": {k[:-2]: totals[k] * 1e3 / args.steps for k in ("submit_s", "wait_s", "score_s", "text_s", "release_s")},
                     "wall_ms_per_step": wall_s * 1e3 / args.steps,
                     "host_cpu_during_timed_region": host_load,
+                    "driver_calls_summed_over_threads": call_stats,
                     "staging_blocks_not_yet_page_locked": {"at_start": backlog0, "at_end": backlog1},
                     "staging_page_locked_bytes": {"at_start": pinned0, "at_end": int(ctx0.lib.uvcgpu_staging_pinned_bytes())}},
             "decode": {"seconds": decode_s, "threads": min(host_threads, max(1, n_sub)), "records": n_records, "records_per_s": n_records / decode_s,

@@ -352,6 +352,12 @@ int uvcgpu_staging_backlog(void);
 /* Bytes of host staging memory the library has page-locked so far (process-wide); constant once the cache has seen the caller's steady state. */
 int64_t uvcgpu_staging_pinned_bytes(void);
 
+/* Where the host's time inside the library's driver calls went so far (process-wide, all contexts and threads): for each kind of call, in this
+ * order - device allocation, free, memset, copy enqueue, kernel launches, waits for events, reserved - three numbers: total milliseconds, number
+ * of calls, longest single call in milliseconds. Writes at most `cap` doubles to `out` (may be NULL) and returns how many there are (21).
+ * Diagnostics only (no reference counterpart): several contexts per GPU meet at the driver's locks, and this shows it. */
+int uvcgpu_host_call_stats(double *out, int32_t cap);
+
 /* sizeof(uvcgpu_params) as the library was compiled, so that foreign-language bindings can verify their mirror of the struct. */
 size_t uvcgpu_sizeof_params(void);
 

@@ -15,6 +15,7 @@
 #include "vcf_emit.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
@@ -39,6 +40,7 @@
 #define UVC_CUDA 0
 #endif
 
+#define UVC_CURSOR_SLOTS 64
 #define UVC_N_PILEUP_STAGES 12   // K0, K1, K2, K2e, KF, K3a, K3b, KM, K4a, K4, K4c, K6 (kernel_ms_by_stage[0..11]); [12] = K5
 
 namespace {
@@ -77,7 +79,7 @@ struct BatchState {
     StageVec<GvcfExtra> gextra;
     // K6's outputs and the cursor of the sparse record stream travel to the host at the end of the batch's own kernels (one wait: collect)
     GvcfPos *d_gvcf = nullptr; GvcfExtra *d_gextra = nullptr;
-    StageVec<int32_t> rec_cursor_host, score_cursor_host;
+    int32_t *rec_cursor_host = nullptr, *score_cursor_host = nullptr;   // 4 + 4 words of the context's page-locked cursor slab
     StageVec<IndelAllele> allele_table;
 #if UVC_CUDA
     cudaEvent_t ev[UVC_N_PILEUP_STAGES + 1];
@@ -105,6 +107,9 @@ struct uvcgpu_ctx {
     // wait for the stream to drain)
     double *c_phred2prob = nullptr; int32_t *c_pf_tab = nullptr; int32_t *c_slip_tab = nullptr;
     int host_threads = 0;
+    // page-locked words the small downloads of a batch land in (cursors of the sparse record stream and of the scoring pipeline): a download
+    // into pageable memory would block the enqueuing thread until the stream gets there. UVC_CURSOR_SLOTS batches may be alive per context.
+    int32_t *cursor_slab = nullptr;
     double k5_groups_per_pos = 0.25, k5_cands_per_pos = 0.75;   // capacities of the scoring pipeline per position, grown to what the batches need
 #if UVC_CUDA
     cudaStream_t stream = nullptr;        // submit: staging copies and the pileup kernels of every batch, in submission order
@@ -206,10 +211,15 @@ void *uvc_stage_alloc(size_t bytes) {
 #if UVC_CUDA
     StageState & st = stage_state();
     const size_t cls = stage_class(bytes);
+    void *larger = NULL;
     {
         std::lock_guard<std::mutex> lk(st.mu);
         auto it = st.free_blocks.find(cls);
         if (it != st.free_blocks.end()) { void *p = it->second; st.free_blocks.erase(it); return p; }
+        // no block of this class: a cached block of a somewhat larger class (up to 4x) serves too - page-locking a new one stalls every
+        // driver call of the process while it lasts, and pageable staging makes the copies synchronous. The class is provisioned all the same.
+        it = st.free_blocks.lower_bound(cls);
+        if (it != st.free_blocks.end() && it->first <= 4 * cls) { larger = it->second; st.free_blocks.erase(it); }
         // one block for this request and a spare (the number of batches alive at once varies with the caller's pipelining), unless the same
         // class is already queued twice: concurrent misses of one class must not queue a pile of blocks that nobody will use
         int queued = 0;
@@ -223,6 +233,7 @@ void *uvc_stage_alloc(size_t bytes) {
         }
     }
     st.cv.notify_one();
+    if (larger) { return larger; }
 #endif
     return (getenv("UVC_DEBUG_FILL") ? memset(malloc(bytes), atoi(getenv("UVC_DEBUG_FILL")), bytes) : malloc(bytes));   // debug aid: poison fresh staging memory
 }
@@ -239,6 +250,22 @@ void uvc_stage_free(void *p, size_t bytes) {
 #endif
     free(p);
 }
+
+// ------------------------------------------------------------------------------------------------ where the host's time goes
+// Process-wide totals of the time host threads spend inside the driver, by kind of call (uvcgpu_host_call_stats): with several contexts per GPU
+// the calls of all threads meet at the driver's locks, and an end-to-end run is as fast as these stay short.
+enum { UVC_T_MALLOC, UVC_T_FREE, UVC_T_MEMSET, UVC_T_COPY, UVC_T_LAUNCH, UVC_T_WAIT, UVC_T_HOSTCOPY, UVC_T_N };
+static std::atomic<int64_t> g_call_ns[UVC_T_N], g_call_n[UVC_T_N], g_call_max_ns[UVC_T_N];
+struct CallTimer {
+    int kind; std::chrono::steady_clock::time_point t0;
+    explicit CallTimer(int k) : kind(k), t0(std::chrono::steady_clock::now()) {}
+    ~CallTimer() {
+        const int64_t ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        g_call_ns[kind].fetch_add(ns, std::memory_order_relaxed); g_call_n[kind].fetch_add(1, std::memory_order_relaxed);
+        int64_t m = g_call_max_ns[kind].load(std::memory_order_relaxed);
+        while (ns > m && !g_call_max_ns[kind].compare_exchange_weak(m, ns, std::memory_order_relaxed)) {}
+    }
+};
 
 // ------------------------------------------------------------------------------------------------ compute backend
 #if UVC_CUDA
@@ -743,6 +770,7 @@ static void launch(uvc_kernel_t k, cudaStream_t s, const BatchView & v, int64_t 
 // starve the record copies and the VCF text: 2-GPU e2e 39.9 M reads/s instead of 68.7 M); cudaEventBlockingSync sleeps until the driver's
 // interrupt arrives, which took up to hundreds of milliseconds per wait on some boxes (1-GPU e2e 7.4 - 48.6 M reads/s from run to run).
 static cudaError_t uvc_event_wait(cudaEvent_t e) {
+    CallTimer ct(UVC_T_WAIT);
     const auto t0 = std::chrono::steady_clock::now();
     for (;;) {
         const cudaError_t q = cudaEventQuery(e);
@@ -761,19 +789,19 @@ static int backend_wait_stream(uvcgpu_ctx *ctx, cudaStream_t s) {
 }
 static int backend_alloc(uvcgpu_ctx *ctx, BatchState & bs, void **out, size_t bytes, bool zero) {
     bytes += 64;     // slack: staged record slices are rounded up to 16 bytes, and clamped byte loads may touch offset 0 of an empty blob
-    UVC_CUDA_CHECK(ctx, cudaMallocAsync(out, bytes, t_active));   // stream-ordered pool: no device synchronisation, blocks are reused across batches
+    { CallTimer ct(UVC_T_MALLOC); UVC_CUDA_CHECK(ctx, cudaMallocAsync(out, bytes, t_active)); }   // stream-ordered pool: no device synchronisation, blocks are reused across batches
     bs.allocs.push_back(*out);
-    if (zero) { UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, 0, bytes, t_active)); }
+    if (zero) { CallTimer ct(UVC_T_MEMSET); UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, 0, bytes, t_active)); }
     return 0;
 }
 static int backend_upload(uvcgpu_ctx *ctx, BatchState & bs, void *dst, const void *src, size_t bytes) {
-    if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, t_active)); bs.stats.h2d_bytes += (int64_t)bytes; }
+    if (bytes) { CallTimer ct(UVC_T_COPY); UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, t_active)); bs.stats.h2d_bytes += (int64_t)bytes; }
     return 0;
 }
 // downloads are enqueued (page-locked destinations) and waited for together: every wait of the host costs the turn-around of the stream behind
 // the pileup blocks of other batches that occupy the SMs
 static int backend_download_async(uvcgpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
-    if (bytes) { UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, t_active)); }
+    if (bytes) { CallTimer ct(UVC_T_COPY); UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, t_active)); }
     return 0;
 }
 static int backend_sync(uvcgpu_ctx *ctx) { return backend_wait_stream(ctx, t_active); }
@@ -781,24 +809,25 @@ static int backend_download(uvcgpu_ctx *ctx, void *dst, const void *src, size_t 
     if (bytes) { int rc_ = backend_download_async(ctx, dst, src, bytes); if (0 == rc_) { rc_ = backend_sync(ctx); } if (rc_ != 0) { return rc_; } }
     return 0;
 }
-static int backend_zero(uvcgpu_ctx *ctx, void *dst, size_t bytes) { UVC_CUDA_CHECK(ctx, cudaMemsetAsync(dst, 0, bytes, t_active)); return 0; }
-static void backend_free_temps(uvcgpu_ctx *ctx, BatchState & bs) { for (void *p : bs.temp_allocs) { cudaFreeAsync(p, t_active); } bs.temp_allocs.clear(); }
+static int backend_zero(uvcgpu_ctx *ctx, void *dst, size_t bytes) { CallTimer ct(UVC_T_MEMSET); UVC_CUDA_CHECK(ctx, cudaMemsetAsync(dst, 0, bytes, t_active)); return 0; }
+static void backend_free_temps(uvcgpu_ctx *ctx, BatchState & bs) { CallTimer ct(UVC_T_FREE); for (void *p : bs.temp_allocs) { cudaFreeAsync(p, t_active); } bs.temp_allocs.clear(); }
 // A batch is released after everything of it has completed, while the submit stream may already hold the kernels of the next batch: freeing
 // there would make the blocks reusable only after those kernels (any stream that picks such a block up inherits the wait). The second stream of
 // the context is idle at that moment, so the blocks go back to the pool at once.
-static void backend_free(uvcgpu_ctx *ctx, BatchState & bs) { backend_free_temps(ctx, bs); for (void *p : bs.allocs) { cudaFreeAsync(p, ctx->post_stream); } bs.allocs.clear(); }
+static void backend_free(uvcgpu_ctx *ctx, BatchState & bs) { backend_free_temps(ctx, bs); CallTimer ct(UVC_T_FREE); for (void *p : bs.allocs) { cudaFreeAsync(p, ctx->post_stream); } bs.allocs.clear(); }
 // scratch of the staging kernels; fill >= 0: every byte is set to it
 static int backend_alloc_temp(uvcgpu_ctx *ctx, BatchState & bs, void **out, size_t bytes, int fill = -1) {
     bytes += 64;
-    UVC_CUDA_CHECK(ctx, cudaMallocAsync(out, bytes, t_active));
+    { CallTimer ct(UVC_T_MALLOC); UVC_CUDA_CHECK(ctx, cudaMallocAsync(out, bytes, t_active)); }
     bs.temp_allocs.push_back(*out);
-    if (fill >= 0) { UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, fill, bytes, t_active)); }
+    if (fill >= 0) { CallTimer ct(UVC_T_MEMSET); UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, fill, bytes, t_active)); }
     return 0;
 }
 
 #include "prep_device.inc"
 
 static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
+    CallTimer ct_run(UVC_T_LAUNCH);      // (the pileup launches, their events and the three small downloads)
     const BatchView & v = bs.view;
     int64_t launches = 0;
     for (int i = 0; i < UVC_N_PILEUP_STAGES + 1; i++) { UVC_CUDA_CHECK(ctx, cudaEventCreate(&bs.ev[i])); }
@@ -864,7 +893,7 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
         if (v.n_pos > 0) { uvc_k6_gvcf_inputs<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, ctx->stream>>>(v, sv6, v.n_pos); launches++; }
         UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(bs.gvcf.data(), bs.d_gvcf, bs.gvcf.size() * sizeof(GvcfPos), cudaMemcpyDeviceToHost, ctx->stream));
         UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(bs.gextra.data(), bs.d_gextra, bs.gextra.size() * sizeof(GvcfExtra), cudaMemcpyDeviceToHost, ctx->stream));
-        UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(bs.rec_cursor_host.data(), v.rec_cursor, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(bs.rec_cursor_host, v.rec_cursor, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
         bs.stats.d2h_bytes += (int64_t)(bs.gvcf.size() * sizeof(GvcfPos) + bs.gextra.size() * sizeof(GvcfExtra) + 16);
     }
@@ -917,7 +946,7 @@ static int backend_score(uvcgpu_ctx *ctx, BatchState & bs, const ScoreView & sv)
     UVC_CUDA_CHECK(ctx, cudaEventRecord(e[1], t_active));
     UVC_CUDA_CHECK(ctx, cudaGetLastError());
     // the results the host always needs ride behind the kernels: the cursors and the first records
-    { int rc_ = backend_download_async(ctx, bs.score_cursor_host.data(), sv.out_cursor, 4 * sizeof(int32_t));
+    { int rc_ = backend_download_async(ctx, bs.score_cursor_host, sv.out_cursor, 4 * sizeof(int32_t));
       if (0 == rc_) { rc_ = backend_download_async(ctx, bs.recs.data(), sv.out, bs.recs.size() * sizeof(VarRec)); }
       if (0 == rc_) { rc_ = backend_sync(ctx); }
       if (rc_ != 0) { return rc_; } }
@@ -978,7 +1007,7 @@ static int backend_run(uvcgpu_ctx *, BatchState & bs) {
     sv6.gvcf = bs.d_gvcf; sv6.gextra = bs.d_gextra;
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::k6_gvcf_position(v, sv6, i); }
     memcpy(bs.gvcf.data(), bs.d_gvcf, bs.gvcf.size() * sizeof(GvcfPos)); memcpy(bs.gextra.data(), bs.d_gextra, bs.gextra.size() * sizeof(GvcfExtra));
-    memcpy(bs.rec_cursor_host.data(), v.rec_cursor, 4 * sizeof(int32_t));
+    memcpy(bs.rec_cursor_host, v.rec_cursor, 4 * sizeof(int32_t));
     return 0;
 }
 static int backend_wait(uvcgpu_ctx *, BatchState &) { return 0; }
@@ -992,7 +1021,7 @@ static int backend_score(uvcgpu_ctx *, BatchState & bs, const ScoreView & sv) {
         for (int64_t i = 0; i < (int64_t)sv.out_cursor[3]; i++) { uvc::k5e_candidate(v, sv, i); }
         for (int64_t i = 0; i < (int64_t)sv.out_cursor[2]; i++) { uvc::k5f_group(v, sv, i); }
     }
-    memcpy(bs.score_cursor_host.data(), sv.out_cursor, 4 * sizeof(int32_t));
+    memcpy(bs.score_cursor_host, sv.out_cursor, 4 * sizeof(int32_t));
     memcpy(bs.recs.data(), sv.out, bs.recs.size() * sizeof(VarRec));
     return 0;
 }
@@ -1134,6 +1163,17 @@ int64_t uvcgpu_staging_pinned_bytes(void) {
 #endif
 }
 
+int uvcgpu_host_call_stats(double *out, int32_t cap) {
+    // per kind (device allocation, free, memset, copy enqueue, kernel launches, waits for events, reserved): total ms, calls, longest call in ms
+    const int n = 3 * UVC_T_N;
+    if (out) {
+        for (int k = 0; k < UVC_T_N && 3 * k + 2 < cap; k++) {
+            out[3 * k] = (double)g_call_ns[k].load() * 1e-6; out[3 * k + 1] = (double)g_call_n[k].load(); out[3 * k + 2] = (double)g_call_max_ns[k].load() * 1e-6;
+        }
+    }
+    return n;
+}
+
 int uvcgpu_device_warmup(int device) {
 #if UVC_CUDA
     int n = 0;
@@ -1208,7 +1248,10 @@ int uvcgpu_create(uvcgpu_ctx **out, int device, const uvcgpu_params *params) {
     }
 #endif
 #if UVC_CUDA
+    if (cudaHostAlloc((void**)&ctx->cursor_slab, (size_t)UVC_CURSOR_SLOTS * 8 * sizeof(int32_t), cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); delete ctx; return UVCGPU_ECUDA; }
     ctx->worker = std::thread(submit_worker, ctx);
+#else
+    ctx->cursor_slab = (int32_t*)calloc((size_t)UVC_CURSOR_SLOTS * 8, sizeof(int32_t));
 #endif
     *out = ctx;
     return UVCGPU_OK;
@@ -1228,10 +1271,13 @@ void uvcgpu_destroy(uvcgpu_ctx *ctx) {
     cudaDeviceSynchronize();
     for (auto & kv : ctx->d_contigs) { cudaFree(kv.second); }
     cudaFree(ctx->c_phred2prob); cudaFree(ctx->c_pf_tab); cudaFree(ctx->c_slip_tab);
+    if (ctx->cursor_slab) { cudaFreeHost(ctx->cursor_slab); }
     for (auto & e : ctx->wait_ev) { if (e) { cudaEventDestroy(e); } }
     if (ctx->post_stream) { cudaStreamDestroy(ctx->post_stream); }
     if (ctx->prep_stream) { cudaStreamDestroy(ctx->prep_stream); }
     if (ctx->stream) { cudaStreamDestroy(ctx->stream); }
+#else
+    free(ctx->cursor_slab); free(ctx->c_phred2prob); free(ctx->c_pf_tab); free(ctx->c_slip_tab);
 #endif
     delete ctx;
 }
@@ -1355,7 +1401,7 @@ static int submit_body(uvcgpu_ctx *ctx, BatchState *bs, int32_t n_tiles, const u
     UVC_ZERO(rec_cursor, int32_t, 4)
     { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_pos * sizeof(GvcfPos), true)); bs->d_gvcf = (GvcfPos*)d_; }
     { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_pos * sizeof(GvcfExtra), true)); bs->d_gextra = (GvcfExtra*)d_; }
-    bs->gvcf.resize((size_t)v.n_pos); bs->gextra.resize((size_t)v.n_pos); bs->rec_cursor_host.assign(4, 0);
+    bs->gvcf.resize((size_t)v.n_pos); bs->gextra.resize((size_t)v.n_pos);
     const double t2 = now_ms();
     UVC_TRY(backend_run(ctx, *bs));
     uvcgpu_batch_stats & st = bs->stats;
@@ -1421,7 +1467,19 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
         }
     }
     BatchState *raw = bs.get();
+    if (ctx->batches.size() >= (size_t)UVC_CURSOR_SLOTS) { UVC_ERR(ctx) = "too many batches alive in one context"; return UVCGPU_EINVAL; }
     *ticket = ctx->next_ticket++;
+    {   // a free slot of the cursor slab
+        int slot = (int)(*ticket % UVC_CURSOR_SLOTS);
+        for (;;) {
+            bool used = false;
+            for (auto & kv : ctx->batches) { if (kv.second->rec_cursor_host == ctx->cursor_slab + 8 * slot) { used = true; break; } }
+            if (!used) { break; }
+            slot = (slot + 1) % UVC_CURSOR_SLOTS;
+        }
+        raw->rec_cursor_host = ctx->cursor_slab + 8 * slot; raw->score_cursor_host = raw->rec_cursor_host + 4;
+        memset(raw->rec_cursor_host, 0, 8 * sizeof(int32_t));
+    }
     ctx->batches[*ticket] = std::move(bs);
 #if UVC_CUDA
     raw->submitted = false;
@@ -1473,7 +1531,7 @@ static int ensure_sparse(uvcgpu_ctx *ctx, BatchState & bs) {
     if (bs.sparse_built) { return 0; }
     PostScope post_scope(ctx);
     const BatchView & v = bs.view;
-    const int32_t *cursor = bs.rec_cursor_host.data();      // (arrived with the batch)
+    const int32_t *cursor = bs.rec_cursor_host;      // (arrived with the batch)
     int rc = 0;
     if (cursor[0] > v.rec_cap) { UVC_ERR(ctx) = "sparse record stream overflow: submit a smaller batch"; return UVCGPU_ENOMEM; }
     const double t_sp0 = now_ms();
@@ -1521,7 +1579,6 @@ static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
     // groups and candidates per position: sized from what the context's earlier batches needed (a batch that needs more runs twice)
     int64_t group_cap = (int64_t)(ctx->k5_groups_per_pos * (double)v.n_pos) + 1024, cand_cap = (int64_t)(ctx->k5_cands_per_pos * (double)v.n_pos) + 4096;
     StageVec<VarRec> & recs = bs.recs;
-    bs.score_cursor_host.assign(4, 0);
     const size_t n_first = 256;       // records downloaded together with their count (most batches have fewer: one wait instead of two)
     for (int attempt = 0; attempt < 3; attempt++) {
         if ((rc = backend_alloc_temp(ctx, bs, &d, (size_t)cap * sizeof(VarRec))) != 0) { return rc; }
