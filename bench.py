@@ -62,7 +62,7 @@ def parse_args():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--scale", type=float, default=None, help="fraction of the named config's region (default: per-config)")
     ap.add_argument("--workdir", default=os.environ.get("UVC_BENCH_DIR", "/tmp/uvc_bench"))
-    ap.add_argument("--contexts", type=int, default=8, help="contexts (CUDA streams) the e2e step pipelines its sub-batches over: a context spends most of a sub-batch waiting (staging kernels, pileup, downloads), so several are needed to keep the GPU fed")
+    ap.add_argument("--contexts", type=int, default=6, help="contexts (CUDA streams) the e2e step pipelines its sub-batches over: a context spends most of a sub-batch waiting (staging kernels, pileup, downloads), so several are needed to keep the GPU fed")
     ap.add_argument("--sub-batches", type=int, default=0, help="sub-batches per step (0: packed to ~512 k positions or 8 M reads each)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-pipeline", action="store_true", help="do not time the whole uvc1 program")
@@ -652,6 +652,7 @@ def main():
     wall_s = time.time() - t0
     host_load = host_cpu_load(cpu0, host_cpu_times())
     calls1 = host_call_stats(ctx0.lib)
+    mem_free, mem_total = torch.cuda.mem_get_info()
     call_stats = {name: {"ms_per_step": (calls1[3 * i] - calls0[3 * i]) / args.steps, "calls_per_step": (calls1[3 * i + 1] - calls0[3 * i + 1]) / args.steps,
                          "longest_ms_since_start": calls1[3 * i + 2]}
                   for i, name in enumerate(("device_alloc", "device_free", "memset", "copy_enqueue", "kernel_launches", "event_waits"))}
@@ -814,6 +815,7 @@ def main():
                     "wall_ms_per_step": wall_s * 1e3 / args.steps,
                     "host_cpu_during_timed_region": host_load,
                     "driver_calls_summed_over_threads": call_stats,
+                    "device_memory_in_use_bytes": int(mem_total - mem_free),
                     "staging_blocks_not_yet_page_locked": {"at_start": backlog0, "at_end": backlog1},
                     "staging_page_locked_bytes": {"at_start": pinned0, "at_end": int(ctx0.lib.uvcgpu_staging_pinned_bytes())}},
             "decode": {"seconds": decode_s, "threads": min(host_threads, max(1, n_sub)), "records": n_records, "records_per_s": n_records / decode_s,

@@ -54,6 +54,11 @@ struct BatchState {
     BatchView view;                       // pointers valid on the compute side (device or, in the emulation, host)
     std::vector<void*> allocs;            // compute-side allocations
     std::vector<void*> temp_allocs;       // scratch of the device staging (stages P0/P1), freed as soon as the staging kernels are enqueued
+    // CUDA build: device memory of the batch is carved from slabs of the process-wide slab cache (see DevArena below)
+    struct Slab { char *base; size_t size; };
+    struct Arena { std::vector<Slab> slabs; size_t used = 0, requested = 0; };
+    Arena keep_arena, temp_arena;
+    bool temps_done = false;              // the scratch is no longer needed once the work enqueued so far has run: released at collect
     StageVec<uint8_t> raw_stage;          // page-locked copy of the caller's records that the batch needs (source of the one host-to-device copy)
     uvc::PrepView prep_view;              // arrays of the staging kernels that outlive them (reads, fragments, families)
     int32_t *indelphred0 = nullptr;       // compute side: indelphred of every position before the threshold pass adjusts it (dump hook)
@@ -110,6 +115,7 @@ struct uvcgpu_ctx {
     // page-locked words the small downloads of a batch land in (cursors of the sparse record stream and of the scoring pipeline): a download
     // into pageable memory would block the enqueuing thread until the stream gets there. UVC_CURSOR_SLOTS batches may be alive per context.
     int32_t *cursor_slab = nullptr;
+    std::atomic<size_t> keep_hint{0}, temp_hint{0}, score_hint{0};  // device bytes the context's batches needed so far: arrays, staging scratch, scoring scratch (size of the first slab a batch asks for)
     double k5_groups_per_pos = 0.25, k5_cands_per_pos = 0.75;   // capacities of the scoring pipeline per position, grown to what the batches need
 #if UVC_CUDA
     cudaStream_t stream = nullptr;        // submit: staging copies and the pileup kernels of every batch, in submission order
@@ -787,11 +793,58 @@ static int backend_wait_stream(uvcgpu_ctx *ctx, cudaStream_t s) {
     UVC_CUDA_CHECK(ctx, uvc_event_wait(e));
     return 0;
 }
+// Device memory. The stream-ordered pool (cudaMallocAsync) was measured at milliseconds per call with several contexts allocating and freeing
+// on two dozen streams (up to seconds for single calls: ~10 s of host-thread time per 26.7 M-read step), so batches carve their arrays from
+// big slabs instead. A slab cache per device keeps every slab the process ever allocated; a batch takes one slab sized like the context's
+// previous batches (more if it turns out larger), bump-allocates from it, and hands the slabs back when it is released - by then everything
+// that used them has completed (collect waited for the pileup kernels, scoring synchronises before it returns), so the next user needs no
+// stream ordering. In the steady state no driver call allocates or frees memory.
+struct SlabCache { std::mutex mu; std::multimap<size_t, char*> free_slabs; int live_contexts = 0; };
+static SlabCache & slab_cache(int device) { static SlabCache *c = new SlabCache[64]; return c[device & 63]; }
+static void slab_purge(SlabCache & sc) {       // (caller holds the lock)
+    for (auto & kv : sc.free_slabs) { cudaFree(kv.second); }
+    sc.free_slabs.clear();
+}
+static int slab_acquire(uvcgpu_ctx *ctx, size_t min_bytes, BatchState::Slab & out) {
+    CallTimer ct(UVC_T_MALLOC);
+    SlabCache & sc = slab_cache(ctx->device);
+    const size_t unit = (size_t)64 << 20;
+    const size_t want = (min_bytes + unit - 1) / unit * unit;
+    std::lock_guard<std::mutex> lk(sc.mu);
+    auto it = sc.free_slabs.lower_bound(want);
+    if (it != sc.free_slabs.end() && it->first <= 2 * want + 4 * unit) { out.base = it->second; out.size = it->first; sc.free_slabs.erase(it); return 0; }
+    void *p = NULL;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); slab_purge(sc); e = cudaMalloc(&p, want); }       // make room: give the cached slabs back and try once more
+    if (e != cudaSuccess) { cudaGetLastError(); UVC_ERR(ctx) = std::string("out of device memory: ") + cudaGetErrorString(e); return UVCGPU_ENOMEM; }
+    out.base = (char*)p; out.size = want;
+    return 0;
+}
+static void arena_release(uvcgpu_ctx *ctx, BatchState::Arena & a) {
+    if (a.slabs.empty()) { return; }
+    SlabCache & sc = slab_cache(ctx->device);
+    std::lock_guard<std::mutex> lk(sc.mu);
+    for (auto & sl : a.slabs) { sc.free_slabs.insert(std::make_pair(sl.size, sl.base)); }
+    a.slabs.clear(); a.used = 0; a.requested = 0;
+}
+static int arena_alloc(uvcgpu_ctx *ctx, BatchState::Arena & a, size_t hint, void **out, size_t bytes) {
+    bytes = (bytes + 64 + 255) / 256 * 256;     // slack: staged record slices are rounded up to 16 bytes, and clamped byte loads may touch offset 0 of an empty blob
+    a.requested += bytes;
+    if (a.slabs.empty() || a.used + bytes > a.slabs.back().size) {
+        BatchState::Slab sl;
+        const size_t next = (a.slabs.empty() ? std::max(bytes, hint) : std::max(bytes, std::max(hint / 4, (size_t)256 << 20)));
+        const int rc = slab_acquire(ctx, next, sl);
+        if (rc != 0) { return rc; }
+        a.slabs.push_back(sl); a.used = 0;
+    }
+    *out = a.slabs.back().base + a.used;
+    a.used += bytes;
+    return 0;
+}
 static int backend_alloc(uvcgpu_ctx *ctx, BatchState & bs, void **out, size_t bytes, bool zero) {
-    bytes += 64;     // slack: staged record slices are rounded up to 16 bytes, and clamped byte loads may touch offset 0 of an empty blob
-    { CallTimer ct(UVC_T_MALLOC); UVC_CUDA_CHECK(ctx, cudaMallocAsync(out, bytes, t_active)); }   // stream-ordered pool: no device synchronisation, blocks are reused across batches
-    bs.allocs.push_back(*out);
-    if (zero) { CallTimer ct(UVC_T_MEMSET); UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, 0, bytes, t_active)); }
+    const int rc = arena_alloc(ctx, bs.keep_arena, ctx->keep_hint.load(), out, bytes);
+    if (rc != 0) { return rc; }
+    if (zero) { CallTimer ct(UVC_T_MEMSET); UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, 0, bytes + 64, t_active)); }
     return 0;
 }
 static int backend_upload(uvcgpu_ctx *ctx, BatchState & bs, void *dst, const void *src, size_t bytes) {
@@ -810,17 +863,25 @@ static int backend_download(uvcgpu_ctx *ctx, void *dst, const void *src, size_t 
     return 0;
 }
 static int backend_zero(uvcgpu_ctx *ctx, void *dst, size_t bytes) { CallTimer ct(UVC_T_MEMSET); UVC_CUDA_CHECK(ctx, cudaMemsetAsync(dst, 0, bytes, t_active)); return 0; }
-static void backend_free_temps(uvcgpu_ctx *ctx, BatchState & bs) { CallTimer ct(UVC_T_FREE); for (void *p : bs.temp_allocs) { cudaFreeAsync(p, t_active); } bs.temp_allocs.clear(); }
-// A batch is released after everything of it has completed, while the submit stream may already hold the kernels of the next batch: freeing
-// there would make the blocks reusable only after those kernels (any stream that picks such a block up inherits the wait). The second stream of
-// the context is idle at that moment, so the blocks go back to the pool at once.
-static void backend_free(uvcgpu_ctx *ctx, BatchState & bs) { backend_free_temps(ctx, bs); CallTimer ct(UVC_T_FREE); for (void *p : bs.allocs) { cudaFreeAsync(p, ctx->post_stream); } bs.allocs.clear(); }
-// scratch of the staging kernels; fill >= 0: every byte is set to it
+// the scratch is not needed any more once the work enqueued so far has run (staging: released at collect; scoring: `now`, after its synchronisation)
+static void backend_free_temps(uvcgpu_ctx *ctx, BatchState & bs, bool now = false) {
+    std::atomic<size_t> & hint = (bs.collected ? ctx->score_hint : ctx->temp_hint);
+    const size_t need = bs.temp_arena.requested + bs.temp_arena.requested / 16;
+    if (need > hint.load()) { hint.store(need); }
+    if (now) { arena_release(ctx, bs.temp_arena); bs.temps_done = false; } else { bs.temps_done = true; }
+}
+// A batch is released after everything of it has completed: its slabs go straight back to the cache.
+static void backend_free(uvcgpu_ctx *ctx, BatchState & bs) {
+    CallTimer ct(UVC_T_FREE);
+    const size_t need = bs.keep_arena.requested + bs.keep_arena.requested / 16;
+    if (need > ctx->keep_hint.load()) { ctx->keep_hint.store(need); }
+    arena_release(ctx, bs.temp_arena); arena_release(ctx, bs.keep_arena);
+}
+// scratch of the staging and scoring kernels; fill >= 0: every byte is set to it
 static int backend_alloc_temp(uvcgpu_ctx *ctx, BatchState & bs, void **out, size_t bytes, int fill = -1) {
-    bytes += 64;
-    { CallTimer ct(UVC_T_MALLOC); UVC_CUDA_CHECK(ctx, cudaMallocAsync(out, bytes, t_active)); }
-    bs.temp_allocs.push_back(*out);
-    if (fill >= 0) { CallTimer ct(UVC_T_MEMSET); UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, fill, bytes, t_active)); }
+    const int rc = arena_alloc(ctx, bs.temp_arena, (bs.collected ? ctx->score_hint.load() : ctx->temp_hint.load()), out, bytes);
+    if (rc != 0) { return rc; }
+    if (fill >= 0) { CallTimer ct(UVC_T_MEMSET); UVC_CUDA_CHECK(ctx, cudaMemsetAsync(*out, fill, bytes + 64, t_active)); }
     return 0;
 }
 
@@ -974,7 +1035,7 @@ static int backend_download(uvcgpu_ctx *, void *dst, const void *src, size_t byt
 static int backend_download_async(uvcgpu_ctx *ctx, void *dst, const void *src, size_t bytes) { return backend_download(ctx, dst, src, bytes); }
 static int backend_sync(uvcgpu_ctx *) { return 0; }
 static int backend_zero(uvcgpu_ctx *, void *dst, size_t bytes) { memset(dst, 0, bytes); return 0; }
-static void backend_free_temps(uvcgpu_ctx *, BatchState & bs) { for (void *p : bs.temp_allocs) { free(p); } bs.temp_allocs.clear(); }
+static void backend_free_temps(uvcgpu_ctx *, BatchState & bs, bool = false) { for (void *p : bs.temp_allocs) { free(p); } bs.temp_allocs.clear(); }
 static void backend_free(uvcgpu_ctx *ctx, BatchState & bs) { backend_free_temps(ctx, bs); for (void *p : bs.allocs) { free(p); } bs.allocs.clear(); }
 static int backend_alloc_temp(uvcgpu_ctx *, BatchState & bs, void **out, size_t bytes, int fill = -1) {
     bytes += 64;
@@ -1248,6 +1309,7 @@ int uvcgpu_create(uvcgpu_ctx **out, int device, const uvcgpu_params *params) {
     }
 #endif
 #if UVC_CUDA
+    { SlabCache & sc = slab_cache(device); std::lock_guard<std::mutex> lk(sc.mu); sc.live_contexts++; }
     if (cudaHostAlloc((void**)&ctx->cursor_slab, (size_t)UVC_CURSOR_SLOTS * 8 * sizeof(int32_t), cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); delete ctx; return UVCGPU_ECUDA; }
     ctx->worker = std::thread(submit_worker, ctx);
 #else
@@ -1266,9 +1328,16 @@ void uvcgpu_destroy(uvcgpu_ctx *ctx) {
     ctx->wcv.notify_all();
     if (ctx->worker.joinable()) { ctx->worker.join(); }
 #endif
+#if UVC_CUDA
+    cudaStreamSynchronize(ctx->prep_stream); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->post_stream);   // (slabs go back to the cache only after their last use)
+#endif
     for (auto & kv : ctx->batches) { backend_free(ctx, *kv.second); }
 #if UVC_CUDA
-    cudaDeviceSynchronize();
+    {
+        SlabCache & sc = slab_cache(ctx->device);
+        std::lock_guard<std::mutex> lk(sc.mu);
+        if (--sc.live_contexts <= 0) { sc.live_contexts = 0; slab_purge(sc); }     // the last context of the device gives the memory back
+    }
     for (auto & kv : ctx->d_contigs) { cudaFree(kv.second); }
     cudaFree(ctx->c_phred2prob); cudaFree(ctx->c_pf_tab); cudaFree(ctx->c_slip_tab);
     if (ctx->cursor_slab) { cudaFreeHost(ctx->cursor_slab); }
@@ -1509,6 +1578,9 @@ int uvcgpu_collect(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, uvcgpu_batch_stats *st
         if (rc != 0) { return rc; }
         rc = backend_wait(ctx, bs);
         if (rc != 0) { return rc; }
+#if UVC_CUDA
+        if (bs.temps_done) { arena_release(ctx, bs.temp_arena); bs.temps_done = false; }     // the staging kernels ran before the pileup kernels
+#endif
         bs.collected = true;
     }
     if (stats) { *stats = bs.stats; }
@@ -1604,9 +1676,9 @@ static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
         if (attempt == 2) { UVC_ERR(ctx) = "candidate record buffer overflow"; return UVCGPU_ENOMEM; }
         // the kernels counted everything they wanted to write: run again with room for all of it
         cap = std::max<int64_t>(cap, n); group_cap = std::max<int64_t>(group_cap, n_groups); cand_cap = std::max<int64_t>(cand_cap, n_cands);
-        backend_free_temps(ctx, bs);
+        backend_free_temps(ctx, bs, true);
     }
-    backend_free_temps(ctx, bs);      // (stream-ordered: after the downloads above)
+    backend_free_temps(ctx, bs, true);      // (the scoring kernels and the downloads of their results have completed)
     bs.stats.d2h_bytes += (int64_t)(recs.size() * sizeof(VarRec));
     const double t2 = now_ms();
     bs.recs_by_tile.assign(bs.hb.tiles.size(), std::vector<const VarRec*>());
