@@ -632,7 +632,7 @@ def main():
         while ctx0.lib.uvcgpu_staging_backlog() > 0 and time.time() - t_wait < 10.0:
             time.sleep(0.05)
         before = int(ctx0.lib.uvcgpu_staging_pinned_bytes())
-        e2e_steps(1)
+        e2e_steps(2)      # (two steps back to back: the overlap across a step boundary needs its staging blocks too)
         grown = (ctx0.lib.uvcgpu_staging_backlog() > 0 or int(ctx0.lib.uvcgpu_staging_pinned_bytes()) != before)
         stable = 0 if grown else stable + 1
         if stable >= 3:

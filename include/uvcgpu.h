@@ -145,7 +145,13 @@ typedef struct uvcgpu_params {
     int32_t microadjust_strand_absence_snv_penalty, microadjust_dedup_absence_indel_penalty;
     int32_t lib_wgs_min_avg_fraglen, lib_nonwgs_clip_penal_min_indelsize, lib_nonwgs_normal_max_rescued_MQ, lib_wgs_normal_max_rescued_MQ;
     double lib_nonwgs_ad_pseudocount, lib_nonwgs_normal_full_self_rescue_fa, lib_nonwgs_normal_min_self_rescue_fa_ratio, lib_nonwgs_normal_add_mul_ad;
-    int32_t should_output_all_germline, reserved2[7];
+    int32_t should_output_all_germline;
+    /* Not a reference parameter. 0 (default): the position kernels that only feed the output (bias pileup, fragment and family consensus) run
+     * on the positions whose counters can reach it - the tile's own positions and one before them, plus the span the MGVCF block lines read
+     * ahead (main.cpp:666-667) - instead of on the whole extended range of the tile's reads; the VCF is the same. 1: every array holds what the
+     * reference's does over the whole extended range (uvcgpu_dump_counters then agrees with the reference everywhere; used by the parity tests). */
+    int32_t all_positions;
+    int32_t reserved2[6];
 } uvcgpu_params;
 
 /* One tier-3 region (the reference's BedLine, iohts.hpp:14-35) plus the previous one, as process_batch receives

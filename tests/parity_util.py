@@ -32,6 +32,10 @@ def run_tiles(bam: str, fasta: str, tiles: Sequence[Tuple[int, int, int, int]], 
     """tiles: (tid, beg, end, region_flag) in order; prev of tile k is tile k-1 (as main.cpp:1513-1515)."""
     bf = capi.BamFile(bam)
     rb = capi.ReadBuf()
+    # counter sections are compared with the reference's arrays over the whole extended range of a tile: the library fills them there only when
+    # asked to (all_positions); the VCF text is checked on the product's default path
+    if any(sec != "vcf" for sec in sections):
+        params.setdefault("all_positions", 1)
     ctx = capi.Context(0, emulate=emulate, **params)
     tids = sorted(set(t[0] for t in tiles))
     for tid in tids:

@@ -86,3 +86,28 @@ def test_cuda_vcf_vs_reference(synth_small, synth_umi, tmp_path):
     assert st.gpu_launches > 0
     (tmp_path / "u").mkdir()
     _vs_reference(synth_umi, "chrU", [(0, 1000, 4000, 0)], [], {}, False, tmp_path / "u")
+
+
+def _restricted_equals_full(paths, tiles, emulate, **params):
+    """The product computes the output-only position counters on the positions that can reach the output (all_positions = 0); the text must be
+    what the whole-extent run (the reference's arrays, all_positions = 1) gives."""
+    a, st = _our_lines(paths["bam"], paths["fasta"], tiles, emulate, all_positions=0, **params)
+    b, _ = _our_lines(paths["bam"], paths["fasta"], tiles, emulate, all_positions=1, **params)
+    assert len(a) > 0 and a == b
+    return st
+
+
+def test_emulation_vcf_needed_positions_equal_all_positions(synth_small, synth_umi):
+    # tiles much shorter than the extent of their reads (the halo is most of the tile's arrays), with MGVCF block lines that read 1000 positions ahead
+    _restricted_equals_full(synth_small, [(0, 3000, 3200, 0), (0, 3200, 3250, 0), (0, 5000, 5400, 0)], True)
+    _restricted_equals_full(synth_umi, [(0, 2000, 2300, 0)], True, should_output_all=1)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(pu.REF_UVC1), reason="oracle/_ref/uvc1 not built")
+def test_cuda_vcf_c2_depth_panel_vs_reference(synth_c2_depth, tmp_path):
+    """Panel tiles at 2000x (configs[1]): each target its own tile, so most of a tile's extended range is halo that the output-only kernels skip."""
+    tiles = [(0, b, e, 0) for (_, b, e) in synth_c2_depth["targets"]]
+    st = _vs_reference(synth_c2_depth, "chrP", tiles, [], {}, False, tmp_path)
+    assert st.gpu_launches > 0
+    _restricted_equals_full(synth_c2_depth, tiles, False)

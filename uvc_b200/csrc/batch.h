@@ -213,6 +213,12 @@ struct BatchView {
     int64_t n_pos, n_reads, n_frags, n_fams, n_cx, n_ev;
     const TileInfo *tiles;
     const int32_t *pos_tile;       // tile of each concatenated position
+    // Positions the output-only position kernels run on (par.all_positions = 0): list k (0: bias pileup K2, 1: fragment / family consensus K3b, K4)
+    // is the concatenation of one run of consecutive positions per tile, each padded to a multiple of 32 (a warp never straddles two tiles).
+    // NULL list_tile = every position.
+    int64_t n_list[2];
+    const int32_t *list_tile[2];   // [n_list / 32] tile of each chunk of 32 list entries
+    const int64_t *list_off[2];    // [n_tiles] first list entry of each tile
     // reference context
     const uint8_t *refsym;         // AlignmentSymbol of the reference base (CHAR_TO_SYMBOL, main_conversion.hpp:473-486)
     uvcgpu_rtr *rtr;

@@ -424,10 +424,12 @@ struct __align__(16) K2StageP {
 #endif
 __global__ void __launch_bounds__(128, UVC_K2_MINBLOCKS) uvc_k2_bias_pileup(const BatchView v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
-    const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gp_ = (idx < n ? uvc::list_position(v, 0, idx) : -1);
+    const bool active = (gp_ >= 0);
+    const int64_t gp = (active ? gp_ : 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     K2StageP & S = ((K2StageP*)uvc_smem)[warp];
-    const bool active = (gp < n);
     if (0 == lane) { uvc_mbar_init(&S.bar[0], 1); uvc_mbar_init(&S.bar[1], 1); uvc_mbar_fence_init(); }
     __syncwarp();
     uvc::Win w;
@@ -567,11 +569,13 @@ __device__ __forceinline__ int uvc_chunk_len(int64_t cb, int64_t uhi) { return (
 __global__ void __launch_bounds__(128, UVC_K3B_MINBLOCKS) uvc_k3b_fragment_consensus(const BatchView v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
     typedef ColStage<ReadFrag> Stage;
-    const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gp_ = (idx < n ? uvc::list_position(v, 1, idx) : -1);
+    const bool active = (gp_ >= 0);
+    const int64_t gp = (active ? gp_ : 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Stage & S = ((Stage*)uvc_smem)[warp];
     int32_t *hot_buckets = (int32_t*)(uvc_smem + (blockDim.x >> 5) * sizeof(Stage)) + threadIdx.x;
-    const bool active = (gp < n);
     uvc::Win w;
     uvc_warp_window(v, gp, active, w);
     uvc::K3bState st;
@@ -638,10 +642,12 @@ template <bool kWide> __device__ __forceinline__ void uvc_k4_body(const BatchVie
     extern __shared__ __align__(16) unsigned char uvc_smem[];
     typedef K4StageT<kWide> Stage;
     const int kReads = Stage::kReads;
-    const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gp_ = (idx < n ? uvc::list_position(v, 1, idx) : -1);
+    const bool active = (gp_ >= 0);
+    const int64_t gp = (active ? gp_ : 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Stage & S = ((Stage*)uvc_smem)[warp];
-    const bool active = (gp < n);
     uvc::Win w;
     uvc_warp_window(v, gp, active, w);
     uvc::K4State st;
@@ -799,20 +805,32 @@ static int backend_wait_stream(uvcgpu_ctx *ctx, cudaStream_t s) {
 // previous batches (more if it turns out larger), bump-allocates from it, and hands the slabs back when it is released - by then everything
 // that used them has completed (collect waited for the pileup kernels, scoring synchronises before it returns), so the next user needs no
 // stream ordering. In the steady state no driver call allocates or frees memory.
-struct SlabCache { std::mutex mu; std::multimap<size_t, char*> free_slabs; int live_contexts = 0; };
+struct SlabCache {
+    std::mutex mu;
+    std::multimap<size_t, std::pair<char*, uint64_t>> free_slabs;   // size -> (slab, tick at which it came back)
+    uint64_t tick = 0;                                              // counts acquisitions
+    int live_contexts = 0;
+};
 static SlabCache & slab_cache(int device) { static SlabCache *c = new SlabCache[64]; return c[device & 63]; }
 static void slab_purge(SlabCache & sc) {       // (caller holds the lock)
-    for (auto & kv : sc.free_slabs) { cudaFree(kv.second); }
+    for (auto & kv : sc.free_slabs) { cudaFree(kv.second.first); }
     sc.free_slabs.clear();
 }
 static int slab_acquire(uvcgpu_ctx *ctx, size_t min_bytes, BatchState::Slab & out) {
     CallTimer ct(UVC_T_MALLOC);
     SlabCache & sc = slab_cache(ctx->device);
-    const size_t unit = (size_t)64 << 20;
+    // size classes of 1/8 octave (and at least 64 MB): batches of slightly different sizes share slabs
+    size_t unit = (size_t)64 << 20;
+    while (unit * 16 <= min_bytes) { unit *= 2; }
     const size_t want = (min_bytes + unit - 1) / unit * unit;
     std::lock_guard<std::mutex> lk(sc.mu);
+    sc.tick++;
     auto it = sc.free_slabs.lower_bound(want);
-    if (it != sc.free_slabs.end() && it->first <= 2 * want + 4 * unit) { out.base = it->second; out.size = it->first; sc.free_slabs.erase(it); return 0; }
+    if (it != sc.free_slabs.end() && it->first <= 2 * want + ((size_t)256 << 20)) { out.base = it->second.first; out.size = it->first; sc.free_slabs.erase(it); return 0; }
+    // a miss (warm-up, or the batches grew): slabs nobody has asked for in a while (the sizes of the first batches) go back to the driver first
+    for (auto jt = sc.free_slabs.begin(); jt != sc.free_slabs.end(); ) {
+        if (sc.tick - jt->second.second > 48) { cudaFree(jt->second.first); jt = sc.free_slabs.erase(jt); } else { ++jt; }
+    }
     void *p = NULL;
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) { cudaGetLastError(); slab_purge(sc); e = cudaMalloc(&p, want); }       // make room: give the cached slabs back and try once more
@@ -824,7 +842,7 @@ static void arena_release(uvcgpu_ctx *ctx, BatchState::Arena & a) {
     if (a.slabs.empty()) { return; }
     SlabCache & sc = slab_cache(ctx->device);
     std::lock_guard<std::mutex> lk(sc.mu);
-    for (auto & sl : a.slabs) { sc.free_slabs.insert(std::make_pair(sl.size, sl.base)); }
+    for (auto & sl : a.slabs) { sc.free_slabs.insert(std::make_pair(sl.size, std::make_pair(sl.base, sc.tick))); }
     a.slabs.clear(); a.used = 0; a.requested = 0;
 }
 static int arena_alloc(uvcgpu_ctx *ctx, BatchState::Arena & a, size_t hint, void **out, size_t bytes) {
@@ -866,15 +884,15 @@ static int backend_zero(uvcgpu_ctx *ctx, void *dst, size_t bytes) { CallTimer ct
 // the scratch is not needed any more once the work enqueued so far has run (staging: released at collect; scoring: `now`, after its synchronisation)
 static void backend_free_temps(uvcgpu_ctx *ctx, BatchState & bs, bool now = false) {
     std::atomic<size_t> & hint = (bs.collected ? ctx->score_hint : ctx->temp_hint);
-    const size_t need = bs.temp_arena.requested + bs.temp_arena.requested / 16;
-    if (need > hint.load()) { hint.store(need); }
+    const size_t need = bs.temp_arena.requested + bs.temp_arena.requested / 8;
+    if (bs.temp_arena.requested > hint.load()) { hint.store(need); }
     if (now) { arena_release(ctx, bs.temp_arena); bs.temps_done = false; } else { bs.temps_done = true; }
 }
 // A batch is released after everything of it has completed: its slabs go straight back to the cache.
 static void backend_free(uvcgpu_ctx *ctx, BatchState & bs) {
     CallTimer ct(UVC_T_FREE);
-    const size_t need = bs.keep_arena.requested + bs.keep_arena.requested / 16;
-    if (need > ctx->keep_hint.load()) { ctx->keep_hint.store(need); }
+    const size_t need = bs.keep_arena.requested + bs.keep_arena.requested / 8;
+    if (bs.keep_arena.requested > ctx->keep_hint.load()) { ctx->keep_hint.store(need); }
     arena_release(ctx, bs.temp_arena); arena_release(ctx, bs.keep_arena);
 }
 // scratch of the staging and scoring kernels; fill >= 0: every byte is set to it
@@ -897,8 +915,15 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
     // Threads per block of the position kernels (every warp is self-contained: its own staging slot, no block-wide synchronisation). A batch
     // with few positions and deep windows (a small panel at very high depth) is cut into one-warp blocks so that every SM gets some.
     // (four 128-thread blocks are resident per SM: below 148 x 4 x 128 positions smaller blocks spread the warps over the SMs more evenly)
-    int pb = (v.n_pos >= (int64_t)148 * 128 * 4 ? 128 : (v.n_pos >= (int64_t)148 * 64 * 2 ? 64 : 32));
-    { const char *f = getenv("UVC_POS_BLOCK"); if (f && (atoi(f) == 32 || atoi(f) == 64 || atoi(f) == 128)) { pb = atoi(f); } }   // tests force every shape
+    auto pos_block = [](int64_t n) {
+        int b = (n >= (int64_t)148 * 128 * 4 ? 128 : (n >= (int64_t)148 * 64 * 2 ? 64 : 32));
+        const char *f = getenv("UVC_POS_BLOCK");      // tests force every shape
+        if (f && (atoi(f) == 32 || atoi(f) == 64 || atoi(f) == 128)) { b = atoi(f); }
+        return b;
+    };
+    // K1 runs on every position; K2 and K3b / K4 on their position lists (kernels_core.cuh: tile_need_range) unless par.all_positions
+    const int64_t n_k2 = (v.list_tile[0] ? v.n_list[0] : v.n_pos), n_k34 = (v.list_tile[1] ? v.n_list[1] : v.n_pos);
+    int pb = pos_block(v.n_pos);
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
     #define UVC_STAGE(kernel, n) { launch(kernel, ctx->stream, v, (n), launches); UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream)); }
     UVC_STAGE(uvc_k0_read_consts, v.n_reads)
@@ -910,37 +935,39 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
         launches++;
     }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
-    if (v.n_pos > 0) {
+    pb = pos_block(n_k2);
+    if (n_k2 > 0) {
         static_assert(sizeof(K2StageP) % 16 == 0 && sizeof(PileRec) == 64, "per-warp staging slots keep 16-byte alignment");
         const size_t smem = 4 * sizeof(K2StageP);
         UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k2_bias_pileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        uvc_k2_bias_pileup<<<(unsigned)((v.n_pos + pb - 1) / pb), pb, smem * pb / 128, ctx->stream>>>(v, v.n_pos);
+        uvc_k2_bias_pileup<<<(unsigned)((n_k2 + pb - 1) / pb), pb, smem * pb / 128, ctx->stream>>>(v, n_k2);
         launches++;
     }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
     UVC_STAGE(uvc_k2e_indel_events, v.n_ev)
     UVC_STAGE(uvc_kf_fragment_columns, v.n_frags * 32)
     UVC_STAGE(uvc_k3a_fragment_stats, v.n_frags)
-    if (v.n_pos > 0) {
+    pb = pos_block(n_k34);
+    if (n_k34 > 0) {
         static_assert(sizeof(ColStage<ReadFrag>) % 16 == 0, "per-warp staging slots keep 16-byte alignment");
         const size_t smem = (pb / 32) * sizeof(ColStage<ReadFrag>) + 2 * UVC_NUM_BUCKETS * pb * sizeof(int32_t);
         const size_t smem_max = 4 * sizeof(ColStage<ReadFrag>) + 2 * UVC_NUM_BUCKETS * 128 * sizeof(int32_t);   // (the attribute is shared by all contexts: always the largest shape)
         UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k3b_fragment_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-        uvc_k3b_fragment_consensus<<<(unsigned)((v.n_pos + pb - 1) / pb), pb, smem, ctx->stream>>>(v, v.n_pos);
+        uvc_k3b_fragment_consensus<<<(unsigned)((n_k34 + pb - 1) / pb), pb, smem, ctx->stream>>>(v, n_k34);
         launches++;
     }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
     UVC_STAGE(uvc_km_family_columns, v.n_mcol)
     UVC_STAGE(uvc_k4a_family_ends, 2 * v.n_fams)
-    if (v.n_pos > 0) {
+    if (n_k34 > 0) {
         static_assert(sizeof(K4StageT<false>) % 16 == 0 && sizeof(K4StageT<true>) % 16 == 0, "per-warp staging slots keep 16-byte alignment");
         // the wide shape when a good part of the column entries belongs to multi-fragment (UMI) families
         const bool wide = (v.n_mcol * 16 >= v.n_fcol);
         const size_t smem = 4 * (wide ? sizeof(K4StageT<true>) : sizeof(K4StageT<false>));
         UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k4_family_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(K4StageT<false>))));
         UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k4_family_consensus_umi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(K4StageT<true>))));
-        if (wide) { uvc_k4_family_consensus_umi<<<(unsigned)((v.n_pos + pb - 1) / pb), pb, smem * pb / 128, ctx->stream>>>(v, v.n_pos); }
-        else { uvc_k4_family_consensus<<<(unsigned)((v.n_pos + pb - 1) / pb), pb, smem * pb / 128, ctx->stream>>>(v, v.n_pos); }
+        if (wide) { uvc_k4_family_consensus_umi<<<(unsigned)((n_k34 + pb - 1) / pb), pb, smem * pb / 128, ctx->stream>>>(v, n_k34); }
+        else { uvc_k4_family_consensus<<<(unsigned)((n_k34 + pb - 1) / pb), pb, smem * pb / 128, ctx->stream>>>(v, n_k34); }
         launches++;
     }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
@@ -1054,14 +1081,15 @@ static int backend_run(uvcgpu_ctx *, BatchState & bs) {
     for (int64_t i = 0; i < v.n_reads; i++) { uvc::k0_read(v, i); }
     uvc::Win w;
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k1_position(v, i, w); }
-    for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k2m_position(v, i, w); }
+    const int64_t n_k2 = (v.list_tile[0] ? v.n_list[0] : v.n_pos), n_k34 = (v.list_tile[1] ? v.n_list[1] : v.n_pos);
+    for (int64_t j = 0; j < n_k2; j++) { const int64_t i = uvc::list_position(v, 0, j); if (i < 0) { continue; } uvc::position_window(v, i, w); uvc::k2m_position(v, i, w); }
     for (int64_t i = 0; i < v.n_ev; i++) { uvc::k2e_event(v, i); }
     for (int64_t i = 0; i < v.n_fcol; i++) { uvc::kf_fold_bits(v, i, uvc::kf_fragment_column(v, i)); }
     for (int64_t i = 0; i < v.n_frags; i++) { uvc::k3a_fragment(v, i); }
-    for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k3b_position(v, i, w); }
+    for (int64_t j = 0; j < n_k34; j++) { const int64_t i = uvc::list_position(v, 1, j); if (i < 0) { continue; } uvc::position_window(v, i, w); uvc::k3b_position(v, i, w); }
     for (int64_t i = 0; i < v.n_mcol; i++) { uvc::km_family_column(v, i); }
     for (int64_t i = 0; i < 2 * v.n_fams; i++) { uvc::k4a_family_strand(v, i); }
-    for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k4_position(v, i, w); }
+    for (int64_t j = 0; j < n_k34; j++) { const int64_t i = uvc::list_position(v, 1, j); if (i < 0) { continue; } uvc::position_window(v, i, w); uvc::k4_position(v, i, w); }
     for (int64_t i = 0; i < 2 * v.n_fams; i++) { uvc::k4c_family_strand(v, i); }
     ScoreView sv6;
     memset(&sv6, 0, sizeof(sv6));

@@ -769,6 +769,34 @@ UVC_HD int32_t nogap_weight(const BatchView & v, int64_t gp, const ReadDerived &
     return nnminus(tmin(80, noindel), D.micro_nogap_penal) + 1;
 }
 
+// ------------------------------------------------------------------------------------------------ positions whose counters can reach the output
+// The reference fills its per-position arrays over the whole extended range of a tile's reads (main.cpp:529-530, 569), because its loop nest
+// is read-major; it then reads them at the tile's own positions only: the per-position loop (main.cpp:608-1172) visits zerobased_pos in
+// [rpos_inclu_beg, rpos_exclu_end] and looks at refpos = zerobased_pos - 1 (base symbols) and zerobased_pos (link symbols); an MGVCF block line
+// started inside that range reads the fragment / family depths of up to 1000 positions ahead (main.cpp:666-667). Everything else that crosses
+// positions (fragment and family columns, haplotype strings, indel events, the tandem-repeat context, the adjusted indel qualities of K1)
+// comes from read-, fragment- or family-major kernels or from K1, which run in full.
+// kind 0: seginfo / bqsum / vq of the bias pileup (K2); kind 1: fragment and family depths (K3b, K4).
+UVC_HD void tile_need_range(const uvcgpu_params & par, const TileInfo & T, int kind, int32_t & b, int32_t & e) {
+    if (T.skipped) { b = e = T.ext_beg; return; }
+    b = tmax(T.ext_beg, T.rpos_inclu_beg - 1);
+    e = T.rpos_exclu_end + 1;
+    if (1 == kind && (par.outvar_flag & 0x8)) { e = T.rpos_exclu_end + 1002; }
+    e = tmin(T.ext_end, e);
+    if (e < b) { e = b; }
+}
+// concatenated position index of entry i of list `kind`, or -1 (padding / beyond the list)
+UVC_HD int64_t list_position(const BatchView & v, int kind, int64_t i) {
+    if (NULL == v.list_tile[kind]) { return (i < v.n_pos ? i : -1); }
+    if (i >= v.n_list[kind]) { return -1; }
+    const int32_t t = v.list_tile[kind][i >> 5];
+    const TileInfo & T = v.tiles[t];
+    int32_t b, e;
+    tile_need_range(v.par, T, kind, b, e);
+    const int64_t p = (int64_t)b + (i - v.list_off[kind][t]);
+    return (p < (int64_t)e ? T.pos_off + (p - T.ext_beg) : -1);
+}
+
 // ------------------------------------------------------------------------------------------------ K2: bias pileup of the dense symbols
 // Walk #2 (updateByAln<SUM, bias> over aligned bases, main.hpp:1890-2008) gathered per position.
 // dealwith_segbias<isGap> (main.hpp:1360-1595) for an aligned base (isGap = false) or the gap-free junction before it (isGap = true), from the

@@ -96,6 +96,7 @@ struct KeptRec {                // one read that passed the filter of its tile (
 
 struct PrepTotals {             // downloaded once per batch
     int64_t n_kept, n_frags, n_fams, n_fs, n_cx, n_ev, n_fcol, n_mcol, n_pos, n_qual;
+    int64_t n_list[2];          // lengths of the two position lists (kernels_core.cuh: tile_need_range)
     int32_t err;                // 1: a family strand has more than 65535 fragments
     int32_t pad;
 };
@@ -121,6 +122,8 @@ struct PrepView {
     TileInfo *tiles;
     int64_t *tile_len;          // [n_tiles] extended length of every tile
     const int64_t *tile_npos;   // [n_tiles + 1] exclusive scan of tile_len
+    int64_t *list_off[2];       // [n_tiles] per position list: first entry of each tile
+    int32_t *list_tile[2];      // [n_list / 32] per position list: tile of each chunk
     // kept reads
     int64_t n_kept;
     KeptRec *kept;
@@ -487,6 +490,34 @@ struct P0tTileOff {     // after the scan of tile_len; fragment / family ranges 
     UVC_HD void operator()(int64_t t) const {
         q.tiles[t].pos_off = q.tile_npos[t]; q.tiles[t].frag_off = INT64_MAX; q.tiles[t].fam_off = INT64_MAX;
         if (t == q.n_tiles - 1) { q.totals->n_pos = q.tile_npos[q.n_tiles]; }
+    }
+};
+// The two position lists (kernels_core.cuh: tile_need_range, list_position): offsets of the tiles' runs, each padded to a multiple of 32.
+// One thread: a batch has hundreds to a few thousand tiles.
+struct P0tNeedOff {
+    PrepView q;
+    UVC_HD void operator()(int64_t) const {
+        for (int kind = 0; kind < 2; kind++) {
+            int64_t off = 0;
+            for (int32_t t = 0; t < q.n_tiles; t++) {
+                int32_t b, e;
+                tile_need_range(q.par, q.tiles[t], kind, b, e);
+                q.list_off[kind][t] = off;
+                off += ((int64_t)(e - b) + 31) / 32 * 32;
+            }
+            q.totals->n_list[kind] = off;
+        }
+    }
+};
+struct P0tNeedChunks {  // one thread per (tile, kind): the owner of each chunk of 32 list entries
+    PrepView q;
+    UVC_HD void operator()(int64_t i) const {
+        const int kind = (int)(i & 1);
+        const int32_t t = (int32_t)(i >> 1);
+        int32_t b, e;
+        tile_need_range(q.par, q.tiles[t], kind, b, e);
+        const int64_t c0 = q.list_off[kind][t] / 32, c1 = c0 + ((int64_t)(e - b) + 31) / 32;
+        for (int64_t c = c0; c < c1; c++) { q.list_tile[kind][c] = t; }
     }
 };
 struct P0tTileFix {     // tiles without fragments
