@@ -409,9 +409,14 @@ def run_reference(ds, name, workdir, n_steps, n_warm, seconds_per_step):
                 positions_per_s=pos / secs, seconds_per_step=secs / max(1, len(per_step)), steps_run=len(per_step))
 
 
-def kernel_algorithmic_bytes(stage: int, n_ext_positions: float, n_reads: float) -> float:
-    """Compulsory bytes of one launch of a kernel: its inputs read once plus its outputs written once."""
+def kernel_algorithmic_bytes(stage: int, n_ext_positions: float, n_reads: float, n_pos_pileup: float = None, n_pos_consensus: float = None) -> float:
+    """Compulsory bytes of one launch of a kernel: its inputs read once plus its outputs written once. The output-only
+    position kernels (K2; K3b, K4) write the positions they run on (the needed ones, uvcgpu.h: all_positions)."""
     P, R = float(n_ext_positions), float(n_reads)
+    if stage == 2 and n_pos_pileup is not None:
+        P = float(n_pos_pileup)
+    if stage in (6, 9) and n_pos_consensus is not None:
+        P = float(n_pos_consensus)
     read_rec = 1.5 * 150 + 64                      # SURVEY 8d: packed bases + qualities + cigar + scalars of one read
     table = {
         1: R * read_rec + P * (208 + 72),                                   # K1: reads -> prep + thres
@@ -521,7 +526,7 @@ def main():
     # ---- phase 1: device-resident throughput (`value`): one context, one sub-batch per launch, CUDA-event time of every kernel
     ctx0 = make_ctx(host_threads)
     n_warm = max(args.warmup, 3)
-    agg = {"n_reads_kept": 0, "n_ext_positions": 0, "n_positions": 0, "n_reads_in": 0}
+    agg = {"n_reads_kept": 0, "n_ext_positions": 0, "n_positions": 0, "n_reads_in": 0, "n_positions_pileup": 0, "n_positions_consensus": 0}
 
     def device_pass(acc_stage=None):
         ms, launches = 0.0, 0
@@ -770,7 +775,7 @@ def main():
     dom = max(range(13), key=lambda i: stage_ms[i])
     dom_name = STAGE_NAMES[dom] if dom < len(STAGE_NAMES) else "stage%d" % dom
     dom_ms = stage_ms[dom] / args.steps                      # per step = per pass over the sub-batches (n_sub launches)
-    dom_bytes = kernel_algorithmic_bytes(dom, agg["n_ext_positions"], agg["n_reads_kept"])
+    dom_bytes = kernel_algorithmic_bytes(dom, agg["n_ext_positions"], agg["n_reads_kept"], agg["n_positions_pileup"], agg["n_positions_consensus"])
     achieved = dom_bytes / (dom_ms / 1e3) / 1e9
     step_ms = kernel_ms / args.steps
     path_bytes = agg["n_reads_kept"] * (1.5 * 150 + 64) + agg["n_ext_positions"] * 2 * 6272
@@ -794,7 +799,7 @@ def main():
             "data": "synthetic (tools/synthgen.cpp, seeded)",
             "config": {"workload": workload, "tiles": len(tiles), "tiler": "reference SamIter semantics, -t %d" % TILER_THREADS,
                        "reads_per_step": n_reads, "read_records_per_step_incl_tile_halos": agg["n_reads_kept"],
-                       "positions_per_step": agg["n_positions"], "ext_positions_per_step": agg["n_ext_positions"], "stages": STAGES_IMPLEMENTED,
+                       "positions_per_step": agg["n_positions"], "ext_positions_per_step": agg["n_ext_positions"], "pileup_positions_per_step": agg["n_positions_pileup"], "consensus_positions_per_step": agg["n_positions_consensus"], "stages": STAGES_IMPLEMENTED,
                        "sub_batches_per_step": len(subs),
                        "l2": "per-position state of a sub-batch (%.0f MB) is larger than L2, no flush needed" % (agg["n_ext_positions"] * 6272 / 1e6 / len(subs)),
                        "dataset_generation_s_untimed": ds.get("gen_s"), "tiler_s_untimed": tile_s, "host_threads": host_threads,

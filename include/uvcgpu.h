@@ -280,6 +280,8 @@ typedef struct uvcgpu_batch_stats {
     double reserved[6];              /* [0]: ms the submit call waited for the sizes of the batch (staging kernels), [1]: ms of the whole staging part of submit,
                                         [2]: ms of the sparse-record downloads, [3]: ms of the host-side sparse maps, [4]: ms of the indel allele table,
                                         [5]: ms of the scoring kernels and the downloads of their results */
+    int64_t n_positions_pileup;      /* positions the bias pileup (K2) ran on: n_ext_positions with all_positions, else the needed ones */
+    int64_t n_positions_consensus;   /* positions the fragment / family consensus kernels (K3b, K4) ran on */
 } uvcgpu_batch_stats;
 
 /* CommandLineArgs defaults (CmdLineArgs.hpp) with the Illumina inference applied (CmdLineArgs.cpp:127-134). */

@@ -88,6 +88,7 @@ struct BatchState {
     StageVec<IndelAllele> allele_table;
 #if UVC_CUDA
     cudaEvent_t ev[UVC_N_PILEUP_STAGES + 1];
+    cudaEvent_t ev_done;                  // after the downloads that ride behind the batch's kernels
     bool have_events = false;
     cudaEvent_t ev_prep[2];               // around the staging kernels (stages P0/P1)
     bool have_prep_events = false;
@@ -223,9 +224,9 @@ void *uvc_stage_alloc(size_t bytes) {
         auto it = st.free_blocks.find(cls);
         if (it != st.free_blocks.end()) { void *p = it->second; st.free_blocks.erase(it); return p; }
         // no block of this class: a cached block of a somewhat larger class (up to 4x) serves too - page-locking a new one stalls every
-        // driver call of the process while it lasts, and pageable staging makes the copies synchronous. The class is provisioned all the same.
+        // driver call of the process while it lasts, and pageable staging makes the copies synchronous
         it = st.free_blocks.lower_bound(cls);
-        if (it != st.free_blocks.end() && it->first <= 4 * cls) { larger = it->second; st.free_blocks.erase(it); }
+        if (it != st.free_blocks.end() && it->first <= 4 * cls) { larger = it->second; st.free_blocks.erase(it); return larger; }
         // one block for this request and a spare (the number of batches alive at once varies with the caller's pipelining), unless the same
         // class is already queued twice: concurrent misses of one class must not queue a pile of blocks that nobody will use
         int queued = 0;
@@ -239,7 +240,6 @@ void *uvc_stage_alloc(size_t bytes) {
         }
     }
     st.cv.notify_one();
-    if (larger) { return larger; }
 #endif
     return (getenv("UVC_DEBUG_FILL") ? memset(malloc(bytes), atoi(getenv("UVC_DEBUG_FILL")), bytes) : malloc(bytes));   // debug aid: poison fresh staging memory
 }
@@ -979,10 +979,12 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
         memset(&sv6, 0, sizeof(sv6));
         sv6.gvcf = bs.d_gvcf; sv6.gextra = bs.d_gextra;
         if (v.n_pos > 0) { uvc_k6_gvcf_inputs<<<(unsigned)((v.n_pos + 127) / 128), 128, 0, ctx->stream>>>(v, sv6, v.n_pos); launches++; }
+        UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
         UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(bs.gvcf.data(), bs.d_gvcf, bs.gvcf.size() * sizeof(GvcfPos), cudaMemcpyDeviceToHost, ctx->stream));
         UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(bs.gextra.data(), bs.d_gextra, bs.gextra.size() * sizeof(GvcfExtra), cudaMemcpyDeviceToHost, ctx->stream));
         UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(bs.rec_cursor_host, v.rec_cursor, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
+        UVC_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&bs.ev_done, cudaEventDisableTiming));
+        UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev_done, ctx->stream));      // (the batch is complete when its downloads are)
         bs.stats.d2h_bytes += (int64_t)(bs.gvcf.size() * sizeof(GvcfPos) + bs.gextra.size() * sizeof(GvcfExtra) + 16);
     }
     UVC_CUDA_CHECK(ctx, cudaGetLastError());
@@ -992,7 +994,7 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
 
 static int backend_wait(uvcgpu_ctx *ctx, BatchState & bs) {
     // only this batch's last kernel is waited for: a later batch may already be queued on the stream
-    if (bs.have_events) { UVC_CUDA_CHECK(ctx, uvc_event_wait(bs.ev[UVC_N_PILEUP_STAGES])); }
+    if (bs.have_events) { UVC_CUDA_CHECK(ctx, uvc_event_wait(bs.ev_done)); cudaEventDestroy(bs.ev_done); }
     else { const int rc_ = backend_wait_stream(ctx, ctx->stream); if (rc_ != 0) { return rc_; } }
     if (bs.have_events) {
         float ms = 0;
@@ -1504,6 +1506,7 @@ static int submit_body(uvcgpu_ctx *ctx, BatchState *bs, int32_t n_tiles, const u
     uvcgpu_batch_stats & st = bs->stats;
     st.n_tiles = n_tiles; st.n_reads_in = hb.n_reads_in; st.n_reads_kept = v.n_reads; st.n_ext_positions = v.n_pos;
     st.n_families = v.n_fams; st.n_fragments = v.n_frags;
+    st.n_positions_pileup = (v.list_tile[0] ? v.n_list[0] : v.n_pos); st.n_positions_consensus = (v.list_tile[1] ? v.n_list[1] : v.n_pos);
     for (const auto & T : hb.tiles) { st.n_positions += T.end_pos - T.beg_pos; }
     st.h2d_ms = (t1 - t0) - st.host_prep_ms;    // the rest of the staging call: uploads, staging kernels and their two synchronisations
     (void)t2;
