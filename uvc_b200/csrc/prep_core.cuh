@@ -765,7 +765,8 @@ struct P0kPrevMax {
 // column offsets (after the scans of fcol_len / mcol_len), chunk owners and the compact per-read family records
 struct P0lFragCol {
     PrepView q;
-    UVC_HD void operator()(int64_t f) const {
+    UVC_HD void operator()(int64_t f) const {     // (launched for the upper bound n_kept)
+        if (f >= q.totals->n_frags) { return; }
         FragRec & G = q.frags[f];
         G.col_off = q.scan_fcol[f];
         if (f == q.totals->n_frags - 1) { q.totals->n_fcol = q.scan_fcol[f + 1]; }
@@ -773,7 +774,8 @@ struct P0lFragCol {
 };
 struct P0lFamCol {
     PrepView q;
-    UVC_HD void operator()(int64_t fs) const {
+    UVC_HD void operator()(int64_t fs) const {    // (launched for the upper bound 2 * n_kept)
+        if (fs >= 2 * q.totals->n_fams) { return; }
         FamRec & F = q.fams[fs >> 1];
         F.col_off[fs & 1] = q.scan_mcol[fs];
         if (fs == 2 * q.totals->n_fams - 1) { q.totals->n_mcol = q.scan_mcol[fs + 1]; }
