@@ -214,7 +214,9 @@ static thread_local bool g_stage_pinning = true;
 void uvc_stage_thread_pinning(bool enabled) { g_stage_pinning = enabled; }
 void *uvc_stage_alloc(size_t bytes) {
     if (0 == bytes) { bytes = 1; }
-    if (bytes < kStageSmall || !g_stage_pinning) { return (getenv("UVC_DEBUG_FILL") ? memset(malloc(bytes), atoi(getenv("UVC_DEBUG_FILL")), bytes) : malloc(bytes)); }
+    // (small blocks are page-locked too, in the smallest class: they are the targets of asynchronous downloads - sparse records, indel events,
+    //  candidate records - and a download into pageable memory blocks the enqueuing thread inside the driver)
+    if (!g_stage_pinning) { return (getenv("UVC_DEBUG_FILL") ? memset(malloc(bytes), atoi(getenv("UVC_DEBUG_FILL")), bytes) : malloc(bytes)); }
 #if UVC_CUDA
     StageState & st = stage_state();
     const size_t cls = stage_class(bytes);
@@ -876,8 +878,27 @@ static int backend_download_async(uvcgpu_ctx *ctx, void *dst, const void *src, s
     return 0;
 }
 static int backend_sync(uvcgpu_ctx *ctx) { return backend_wait_stream(ctx, t_active); }
+// A synchronous download of a few bytes up to a few megabytes (sizes of a batch, its tiles, ...) lands in a page-locked bounce buffer of the
+// calling thread: a copy into pageable memory makes the driver spin inside the call until the stream gets there (measured: ~0.5 s of a core per
+// 26.7 M-read step, with the driver's lock held against every other thread).
+static void *uvc_bounce(size_t bytes) {
+    static thread_local void *p = nullptr;
+    static thread_local size_t cap = 0;
+    if (bytes > cap) {
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        const size_t want = std::max(bytes, (size_t)256 << 10);
+        if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); p = nullptr; return nullptr; }
+        cap = want;
+    }
+    return p;
+}
 static int backend_download(uvcgpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
-    if (bytes) { int rc_ = backend_download_async(ctx, dst, src, bytes); if (0 == rc_) { rc_ = backend_sync(ctx); } if (rc_ != 0) { return rc_; } }
+    if (0 == bytes) { return 0; }
+    void *b = (bytes <= ((size_t)4 << 20) ? uvc_bounce(bytes) : nullptr);
+    int rc_ = backend_download_async(ctx, (b ? b : dst), src, bytes);
+    if (0 == rc_) { rc_ = backend_sync(ctx); }
+    if (rc_ != 0) { return rc_; }
+    if (b) { memcpy(dst, b, bytes); }
     return 0;
 }
 static int backend_zero(uvcgpu_ctx *ctx, void *dst, size_t bytes) { CallTimer ct(UVC_T_MEMSET); UVC_CUDA_CHECK(ctx, cudaMemsetAsync(dst, 0, bytes, t_active)); return 0; }
