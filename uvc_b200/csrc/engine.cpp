@@ -515,7 +515,10 @@ __global__ void __launch_bounds__(128) uvc_k1_prep_thres(const BatchView v, int6
 UVC_DEFINE_KERNEL(uvc_k2e_indel_events, uvc::k2e_event(v, i))
 // KF: one warp per fragment walks the fragment's column chunk by chunk (lane = position within the chunk): the records of the fragment's
 // reads are loaded once per fragment instead of once per entry; a chunk's four bit masks are four ballots.
-__global__ void __launch_bounds__(128) uvc_kf_fragment_columns(const BatchView v, int64_t n_threads) {
+#ifndef UVC_KF_MINBLOCKS
+#define UVC_KF_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, UVC_KF_MINBLOCKS) uvc_kf_fragment_columns(const BatchView v, int64_t n_threads) {
     const int64_t fi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (fi >= (n_threads >> 5)) { return; }

@@ -122,7 +122,7 @@ struct PrepView {
     TileInfo *tiles;
     int64_t *tile_len;          // [n_tiles] extended length of every tile
     const int64_t *tile_npos;   // [n_tiles + 1] exclusive scan of tile_len
-    int64_t *list_off[2];       // [n_tiles] per position list: first entry of each tile
+    int64_t *list_off[2];       // [n_tiles + 1] per position list: first entry of each tile
     int32_t *list_tile[2];      // [n_list / 32] per position list: tile of each chunk
     // kept reads
     int64_t n_kept;
@@ -492,22 +492,21 @@ struct P0tTileOff {     // after the scan of tile_len; fragment / family ranges 
         if (t == q.n_tiles - 1) { q.totals->n_pos = q.tile_npos[q.n_tiles]; }
     }
 };
-// The two position lists (kernels_core.cuh: tile_need_range, list_position): offsets of the tiles' runs, each padded to a multiple of 32.
-// One thread: a batch has hundreds to a few thousand tiles.
-struct P0tNeedOff {
-    PrepView q;
-    UVC_HD void operator()(int64_t) const {
-        for (int kind = 0; kind < 2; kind++) {
-            int64_t off = 0;
-            for (int32_t t = 0; t < q.n_tiles; t++) {
-                int32_t b, e;
-                tile_need_range(q.par, q.tiles[t], kind, b, e);
-                q.list_off[kind][t] = off;
-                off += ((int64_t)(e - b) + 31) / 32 * 32;
-            }
-            q.totals->n_list[kind] = off;
-        }
+// The two position lists (kernels_core.cuh: tile_need_range, list_position): lengths of the tiles' runs, each padded to a multiple of 32
+// (their exclusive scans are the tiles' offsets in the lists)
+struct P0tNeedLen {
+    PrepView q; int64_t *len0, *len1;
+    UVC_HD void operator()(int64_t t) const {
+        int32_t b, e;
+        tile_need_range(q.par, q.tiles[t], 0, b, e);
+        len0[t] = ((int64_t)(e - b) + 31) / 32 * 32;
+        tile_need_range(q.par, q.tiles[t], 1, b, e);
+        len1[t] = ((int64_t)(e - b) + 31) / 32 * 32;
     }
+};
+struct P0tNeedTot {
+    PrepView q;
+    UVC_HD void operator()(int64_t k) const { q.totals->n_list[k] = q.list_off[k][q.n_tiles]; }
 };
 struct P0tNeedChunks {  // one thread per (tile, kind): the owner of each chunk of 32 list entries
     PrepView q;
