@@ -14,7 +14,7 @@ STAGE_OF = {"uvc_k0_read_consts": "K0 per-read", "uvc_k1_prep_thres": "K1 prep+t
             "uvc_kf_fragment_columns": "KF fragment columns", "uvc_k3a_fragment_stats": "K3a fragment stats", "uvc_k3b_fragment_consensus": "K3b fragment consensus",
             "uvc_km_family_columns": "KM family columns", "uvc_k4a_family_ends": "K4a family ends", "uvc_k4_family_consensus": "K4 family+duplex consensus", "uvc_k4_family_consensus_umi": "K4 family+duplex consensus",
             "uvc_k4c_family_haplotypes": "K4c family haplotypes", "uvc_k6_gvcf_inputs": "K6 block-line inputs", "uvc_k5_score_candidates": "K5 candidate scoring",
-            "uvc_k5a_flag_candidates": "K5 candidate scoring"}
+            "uvc_k5a_flag_candidates": "K5 candidate scoring", "uvc_k5c_candidate_depths": "K5 candidate scoring"}
 
 
 def launches(path, out):
@@ -26,6 +26,8 @@ def launches(path, out):
         if len(r) <= iv:
             continue
         name = r[ik].split("(")[0]
+        if name.startswith("void "):        # templated kernels: "void uvc_for_each<uvc::P0eKept>"
+            name = name[5:]
         v = float(r[iv].replace(",", ""))
         v = v / 1e6 if r[iu] in ("ns", "nsecond") else (v / 1e3 if r[iu] in ("us", "usecond") else v)
         a = agg.setdefault(name, [0, 0.0])
@@ -35,7 +37,7 @@ def launches(path, out):
     tot = sum(v[1] for v in ours.values())
     with open(out, "w") as f:
         f.write("| kernel | launches | mean ms | share of our kernels |\n|---|---|---|---|\n")
-        for k, (n, ms) in ours.items():
+        for k, (n, ms) in sorted(ours.items(), key=lambda kv: -kv[1][1]):
             f.write("| %s | %d | %.3f | %.1f%% |\n" % (k, n, ms / n, 100 * ms / tot))
         others = {k: v for k, v in agg.items() if not k.startswith("uvc_")}
         f.write("\nOther launches in the process (torch/driver): %d kernels, %.3f ms in total.\n" % (sum(v[0] for v in others.values()), sum(v[1] for v in others.values())))

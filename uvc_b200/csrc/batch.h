@@ -223,6 +223,8 @@ struct BatchView {
     const uint8_t *refsym;         // AlignmentSymbol of the reference base (CHAR_TO_SYMBOL, main_conversion.hpp:473-486)
     uvcgpu_rtr *rtr;
     const int32_t *baq, *baq2;     // BAQ prefix sums (main.cpp:400-429); values fit 32 bits
+    int32_t *noindel;              // [n_pos] min(indelphred of the position before, indelphred of the position) after K1's adjustment: the
+                                   // quality of "no indel at the junction before this base" (main.hpp:1918-1924), one coalesced word instead of two 28-byte records
     // reads
     const ReadRec *reads;
     ReadDerived *rd;

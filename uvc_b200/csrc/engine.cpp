@@ -473,7 +473,10 @@ struct __align__(16) K1StageP {
     uint16_t bq[UVC_STAGE_READS][32];
     uint64_t bar[2];
 };
-__global__ void __launch_bounds__(128) uvc_k1_prep_thres(const BatchView v, int64_t n) {
+#ifndef UVC_K1_MINBLOCKS
+#define UVC_K1_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, UVC_K1_MINBLOCKS) uvc_k1_prep_thres(const BatchView v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
     const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -512,11 +515,12 @@ __global__ void __launch_bounds__(128) uvc_k1_prep_thres(const BatchView v, int6
     }
     if (active) { uvc::k1_end(st, v); }
 }
+UVC_DEFINE_KERNEL(uvc_k1b_noindel, uvc::k1b_noindel(v, i))
 UVC_DEFINE_KERNEL(uvc_k2e_indel_events, uvc::k2e_event(v, i))
 // KF: one warp per fragment walks the fragment's column chunk by chunk (lane = position within the chunk): the records of the fragment's
 // reads are loaded once per fragment instead of once per entry; a chunk's four bit masks are four ballots.
 #ifndef UVC_KF_MINBLOCKS
-#define UVC_KF_MINBLOCKS 1
+#define UVC_KF_MINBLOCKS 8     // latency-bound on the loads of base qualities and indel qualities: 64 registers and eight blocks per SM measured 2.41 ms per sub-batch, 93 registers 3.10 ms
 #endif
 __global__ void __launch_bounds__(128, UVC_KF_MINBLOCKS) uvc_kf_fragment_columns(const BatchView v, int64_t n_threads) {
     const int64_t fi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -957,6 +961,7 @@ static int backend_run(uvcgpu_ctx *ctx, BatchState & bs) {
         UVC_CUDA_CHECK(ctx, cudaFuncSetAttribute(uvc_k1_prep_thres, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         uvc_k1_prep_thres<<<(unsigned)((v.n_pos + pb - 1) / pb), pb, smem * pb / 128, ctx->stream>>>(v, v.n_pos);
         launches++;
+        launch(uvc_k1b_noindel, ctx->stream, v, v.n_pos, launches);
     }
     UVC_CUDA_CHECK(ctx, cudaEventRecord(bs.ev[e++], ctx->stream));
     pb = pos_block(n_k2);
@@ -1107,6 +1112,7 @@ static int backend_run(uvcgpu_ctx *, BatchState & bs) {
     for (int64_t i = 0; i < v.n_reads; i++) { uvc::k0_read(v, i); }
     uvc::Win w;
     for (int64_t i = 0; i < v.n_pos; i++) { uvc::position_window(v, i, w); uvc::k1_position(v, i, w); }
+    for (int64_t i = 0; i < v.n_pos; i++) { uvc::k1b_noindel(v, i); }
     const int64_t n_k2 = (v.list_tile[0] ? v.n_list[0] : v.n_pos), n_k34 = (v.list_tile[1] ? v.n_list[1] : v.n_pos);
     for (int64_t j = 0; j < n_k2; j++) { const int64_t i = uvc::list_position(v, 0, j); if (i < 0) { continue; } uvc::position_window(v, i, w); uvc::k2m_position(v, i, w); }
     for (int64_t i = 0; i < v.n_ev; i++) { uvc::k2e_event(v, i); }
@@ -1522,6 +1528,7 @@ static int submit_body(uvcgpu_ctx *ctx, BatchState *bs, int32_t n_tiles, const u
     v.rec_cap = (int32_t)std::min<int64_t>((int64_t)1 << 30, 16 * v.n_reads + (1 << 20));
     UVC_ZERO(rec_buf, int32_t, v.rec_cap)
     UVC_ZERO(rec_cursor, int32_t, 4)
+    { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_pos * sizeof(int32_t), false)); v.noindel = (int32_t*)d_; }
     { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_pos * sizeof(GvcfPos), true)); bs->d_gvcf = (GvcfPos*)d_; }
     { void *d_ = NULL; UVC_TRY(backend_alloc(ctx, *bs, &d_, (size_t)v.n_pos * sizeof(GvcfExtra), true)); bs->d_gextra = (GvcfExtra*)d_; }
     bs->gvcf.resize((size_t)v.n_pos); bs->gextra.resize((size_t)v.n_pos);

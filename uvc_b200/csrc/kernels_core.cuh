@@ -763,9 +763,13 @@ UVC_HD int32_t dist_to_interfering_indel(const BatchView & v, const TileInfo & T
     return tmin(prevlen, nextlen);
 }
 
+// K1b, one thread per position (after K1 has adjusted every indelphred): the junction quality both neighbours agree on
+UVC_HD void k1b_noindel(const BatchView & v, int64_t gp) {
+    v.noindel[gp] = tmin(v.rtr[gp > 0 ? gp - 1 : 0].indelphred, v.rtr[gp].indelphred);
+}
 // quality weight of "no indel" at the junction before an aligned base (main.hpp:1918-1924)
 UVC_HD int32_t nogap_weight(const BatchView & v, int64_t gp, const ReadDerived & D) {
-    const int32_t noindel = tmin(v.rtr[gp > 0 ? gp - 1 : 0].indelphred, v.rtr[gp].indelphred);
+    const int32_t noindel = v.noindel[gp];
     return nnminus(tmin(80, noindel), D.micro_nogap_penal) + 1;
 }
 
@@ -921,7 +925,7 @@ UVC_HD void k2m_begin(K2Merged & s, const BatchView & v, int64_t gp) {
     s.T = &T; s.gp = gp;
     s.p = (int32_t)(gp - T.pos_off) + T.ext_beg;
     s.baq_p = v.baq[gp]; s.baq2_p = v.baq2[gp];
-    s.noindel = tmin(v.rtr[gp > 0 ? gp - 1 : 0].indelphred, v.rtr[gp].indelphred);
+    s.noindel = v.noindel[gp];
     s.th = v.thres[gp];
     s.major = (int)v.refsym[gp];
     k2m_zero(s);
@@ -1491,7 +1495,7 @@ UVC_HD uint32_t kf_plain_entry(const BatchView & v, int64_t i, int32_t p, int64_
         covered = true;
         if (R.mask_on && !(R.ibeg <= p && p < R.iend)) { continue; }      // primer_masked
         if (p > R.pos) {                                                    // nogap_weight
-            const int32_t noindel = tmin(v.rtr[gp > 0 ? gp - 1 : 0].indelphred, v.rtr[gp].indelphred);
+            const int32_t noindel = v.noindel[gp];
             linkw = tmax(linkw, nnminus(tmin(80, noindel), R.nogap_penal) + 1);
         }
         const int32_t qpos = R.m_qoff + (p - R.pos);
