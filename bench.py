@@ -660,7 +660,7 @@ def main():
     mem_free, mem_total = torch.cuda.mem_get_info()
     call_stats = {name: {"ms_per_step": (calls1[3 * i] - calls0[3 * i]) / args.steps, "calls_per_step": (calls1[3 * i + 1] - calls0[3 * i + 1]) / args.steps,
                          "longest_ms_since_start": calls1[3 * i + 2]}
-                  for i, name in enumerate(("device_alloc", "device_free", "memset", "copy_enqueue", "kernel_launches", "event_waits"))}
+                  for i, name in enumerate(("device_alloc", "device_free", "memset", "download_enqueue", "kernel_launches", "event_waits", "upload_enqueue"))}
     backlog1 = int(ctx0.lib.uvcgpu_staging_backlog())
     sampler.stop_flag = True
     body = b"".join(last_text[k] for k in sorted(last_text))

@@ -361,7 +361,7 @@ int uvcgpu_staging_backlog(void);
 int64_t uvcgpu_staging_pinned_bytes(void);
 
 /* Where the host's time inside the library's driver calls went so far (process-wide, all contexts and threads): for each kind of call, in this
- * order - device allocation, free, memset, copy enqueue, kernel launches, waits for events, reserved - three numbers: total milliseconds, number
+ * order - device allocation, free, memset, download enqueue, kernel launches, waits for events, upload enqueue - three numbers: total milliseconds, number
  * of calls, longest single call in milliseconds. Writes at most `cap` doubles to `out` (may be NULL) and returns how many there are (21).
  * Diagnostics only (no reference counterpart): several contexts per GPU meet at the driver's locks, and this shows it. */
 int uvcgpu_host_call_stats(double *out, int32_t cap);

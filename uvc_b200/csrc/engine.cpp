@@ -520,7 +520,7 @@ UVC_DEFINE_KERNEL(uvc_k2e_indel_events, uvc::k2e_event(v, i))
 // KF: one warp per fragment walks the fragment's column chunk by chunk (lane = position within the chunk): the records of the fragment's
 // reads are loaded once per fragment instead of once per entry; a chunk's four bit masks are four ballots.
 #ifndef UVC_KF_MINBLOCKS
-#define UVC_KF_MINBLOCKS 8     // latency-bound on the loads of base qualities and indel qualities: 64 registers and eight blocks per SM measured 2.41 ms per sub-batch, 93 registers 3.10 ms
+#define UVC_KF_MINBLOCKS 12    // latency-bound on the loads of base qualities: measured per sub-batch 3.10 ms at 93 registers, 2.41 at 64 (8 blocks per SM), 2.01 at 42 (12 blocks)
 #endif
 __global__ void __launch_bounds__(128, UVC_KF_MINBLOCKS) uvc_kf_fragment_columns(const BatchView v, int64_t n_threads) {
     const int64_t fi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -573,7 +573,7 @@ __device__ __forceinline__ int uvc_chunk_len(int64_t cb, int64_t uhi) { return (
 // K3b: records = ReadFrag (written by K3a). The quality histograms of the two hot symbols live in shared memory ([bucket][thread]: conflict-free,
 // updated with reductions), their depth counters in registers.
 #ifndef UVC_K3B_MINBLOCKS
-#define UVC_K3B_MINBLOCKS 5    // 88 registers; five blocks per SM with 8-read chunks
+#define UVC_K3B_MINBLOCKS 6    // 80 registers; six blocks per SM with 8-read chunks (2.88 vs 3.05 ms per sub-batch at five)
 #endif
 __global__ void __launch_bounds__(128, UVC_K3B_MINBLOCKS) uvc_k3b_fragment_consensus(const BatchView v, int64_t n) {
     extern __shared__ __align__(16) unsigned char uvc_smem[];
@@ -875,7 +875,7 @@ static int backend_alloc(uvcgpu_ctx *ctx, BatchState & bs, void **out, size_t by
     return 0;
 }
 static int backend_upload(uvcgpu_ctx *ctx, BatchState & bs, void *dst, const void *src, size_t bytes) {
-    if (bytes) { CallTimer ct(UVC_T_COPY); UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, t_active)); bs.stats.h2d_bytes += (int64_t)bytes; }
+    if (bytes) { CallTimer ct(UVC_T_HOSTCOPY); UVC_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, t_active)); bs.stats.h2d_bytes += (int64_t)bytes; }
     return 0;
 }
 // downloads are enqueued (page-locked destinations) and waited for together: every wait of the host costs the turn-around of the stream behind
@@ -1285,7 +1285,7 @@ int64_t uvcgpu_staging_pinned_bytes(void) {
 }
 
 int uvcgpu_host_call_stats(double *out, int32_t cap) {
-    // per kind (device allocation, free, memset, copy enqueue, kernel launches, waits for events, reserved): total ms, calls, longest call in ms
+    // per kind (device allocation, free, memset, download enqueue, kernel launches, waits for events, upload enqueue): total ms, calls, longest call in ms
     const int n = 3 * UVC_T_N;
     if (out) {
         for (int k = 0; k < UVC_T_N && 3 * k + 2 < cap; k++) {
