@@ -360,6 +360,15 @@ int uvcgpu_staging_backlog(void);
 /* Bytes of host staging memory the library has page-locked so far (process-wide); constant once the cache has seen the caller's steady state. */
 int64_t uvcgpu_staging_pinned_bytes(void);
 
+/* Page-locks every array of a caller's SoA buffer (cudaHostRegister), so that uvcgpu_submit uploads the records straight from it instead of
+ * copying them into the library's own page-locked staging first (which costs a core about 0.1 s per gigabyte and the same again in host memory
+ * traffic). Worth it for buffers that are submitted more than once or stay alive for a while (page-locking costs about as much as one copy);
+ * a buffer that is not registered works the same, through the staging copy. The arrays must not be reallocated while registered (a
+ * uvchost_readbuf may not grow); unregister before freeing them. No reference counterpart (htslib hands out one bam1_t at a time).
+ * Returns UVCGPU_OK, or UVCGPU_ECUDA if an array could not be page-locked (the buffer then simply takes the staging path). */
+int uvcgpu_host_register_reads(const uvcgpu_reads_soa *reads);
+int uvcgpu_host_unregister_reads(const uvcgpu_reads_soa *reads);
+
 /* Where the host's time inside the library's driver calls went so far (process-wide, all contexts and threads): for each kind of call, in this
  * order - device allocation, free, memset, download enqueue, kernel launches, waits for events, upload enqueue - three numbers: total milliseconds, number
  * of calls, longest single call in milliseconds. Writes at most `cap` doubles to `out` (may be NULL) and returns how many there are (21).

@@ -7,7 +7,7 @@ import parity_util as pu
 from uvc_b200 import capi
 
 
-def _tiles_text(info, tile_groups, emulate, pipelined):
+def _tiles_text(info, tile_groups, emulate, pipelined, register=False):
     bf = capi.BamFile(info["bam"])
     rb = capi.ReadBuf()
     ctx = capi.Context(0, emulate=emulate)
@@ -24,6 +24,10 @@ def _tiles_text(info, tile_groups, emulate, pipelined):
             prev = (tid, beg, end)
         groups.append(ct)
     view = rb.view()
+    if register:        # page-locked caller buffers: the library uploads the records straight from them (no staging copy)
+        import ctypes as C
+        ctx.lib.uvcgpu_host_register_reads.argtypes = [C.c_void_p]
+        assert ctx.lib.uvcgpu_host_register_reads(C.byref(view)) == 0
 
     def finish(ticket, n):
         st = ctx.collect(ticket)
@@ -45,6 +49,9 @@ def _tiles_text(info, tile_groups, emulate, pipelined):
             text, st = finish(ctx.submit(g, view), len(g))
             out += text
             launches += int(st.gpu_launches)
+    if register:
+        ctx.lib.uvcgpu_host_unregister_reads.argtypes = [C.c_void_p]
+        ctx.lib.uvcgpu_host_unregister_reads(C.byref(view))
     ctx.close()
     rb.close()
     bf.close()
@@ -66,3 +73,13 @@ def test_cuda_tickets_in_flight(synth_small):
     b, lb = _tiles_text(synth_small, GROUPS, False, True)
     assert la > 0 and lb > 0
     assert a == b and any(len(t) > 0 for t in a)
+
+
+@pytest.mark.gpu
+def test_cuda_registered_host_buffers(synth_small, synth_umi):
+    """Records uploaded straight from page-locked caller buffers (several tiles per batch share one source; the offsets are rebased on the device)."""
+    a, _ = _tiles_text(synth_small, GROUPS, False, True)
+    b, lb = _tiles_text(synth_small, GROUPS, False, True, register=True)
+    assert lb > 0 and a == b and any(len(t) > 0 for t in a)
+    g = [[(0, 1000, 2500, 0)], [(0, 2500, 4000, 0)]]
+    assert _tiles_text(synth_umi, g, False, False)[0] == _tiles_text(synth_umi, g, False, True, register=True)[0]

@@ -1284,6 +1284,32 @@ int64_t uvcgpu_staging_pinned_bytes(void) {
 #endif
 }
 
+// page-locks (or releases) every array of a caller's SoA buffer
+static int host_register_reads(const uvcgpu_reads_soa *r, bool on) {
+    if (NULL == r) { return UVCGPU_EINVAL; }
+#if UVC_CUDA
+    const int64_t n = r->n_reads;
+    if (n <= 0) { return UVCGPU_OK; }
+    const void *ptrs[17] = {r->pos, r->mpos, r->isize, r->mtid, r->l_qseq, r->n_cigar, r->nm, r->flag, r->mapq, r->seq_off, r->qual_off, r->cigar_off, r->qname_off,
+                            r->seq, r->qual, r->cigar, r->qname};
+    const size_t bytes[17] = {(size_t)n * 4, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4, (size_t)n * 2, (size_t)n,
+                              (size_t)(n + 1) * 8, (size_t)(n + 1) * 8, (size_t)(n + 1) * 8, (size_t)(n + 1) * 8,
+                              (size_t)r->seq_off[n], (size_t)r->qual_off[n], (size_t)r->cigar_off[n] * 4, (size_t)r->qname_off[n]};
+    int rc = UVCGPU_OK;
+    for (int k = 0; k < 17; k++) {
+        if (NULL == ptrs[k] || 0 == bytes[k]) { continue; }
+        const cudaError_t e = (on ? cudaHostRegister((void*)ptrs[k], bytes[k], cudaHostRegisterPortable) : cudaHostUnregister((void*)ptrs[k]));
+        if (e != cudaSuccess) { cudaGetLastError(); if (e != cudaErrorHostMemoryAlreadyRegistered && e != cudaErrorHostMemoryNotRegistered) { rc = UVCGPU_ECUDA; } }
+    }
+    return rc;
+#else
+    (void)on;
+    return UVCGPU_OK;
+#endif
+}
+int uvcgpu_host_register_reads(const uvcgpu_reads_soa *reads) { return host_register_reads(reads, true); }
+int uvcgpu_host_unregister_reads(const uvcgpu_reads_soa *reads) { return host_register_reads(reads, false); }
+
 int uvcgpu_host_call_stats(double *out, int32_t cap) {
     // per kind (device allocation, free, memset, download enqueue, kernel launches, waits for events, upload enqueue): total ms, calls, longest call in ms
     const int n = 3 * UVC_T_N;

@@ -165,6 +165,21 @@ UVC_HD int32_t pair_tile(const PrepView & q, int64_t pi) {
     return a;
 }
 
+// ------------------------------------------------------------------------------------------------ P0z: offsets of directly uploaded sources
+// When the caller's SoA buffers are page-locked, the record arrays of every source go to the device straight from them (no staging copy on the
+// host); the four offset arrays then still count from the start of their own source's byte arrays. One thread per entry adds its source's
+// displacement in the concatenated arrays. tab: [n_src + 1] first raw index of each source, then [n_src][4] displacements (seq, qual, cigar, name).
+struct P0zRebase {
+    uint64_t *so, *qo, *co, *no; const int64_t *tab; int32_t n_src; int64_t n_raw;
+    UVC_HD void operator()(int64_t r) const {
+        int32_t s = 0;
+        if (r >= n_raw) { s = n_src - 1; while (s > 0 && tab[s] == tab[s + 1]) { s--; } }          // the end entry belongs to the last source that has records
+        else { int32_t a = 0, b = n_src; while (b - a > 1) { const int32_t m = (a + b) >> 1; if (tab[m] <= r) { a = m; } else { b = m; } } s = a; }
+        const int64_t *d = tab + (n_src + 1) + 4 * (int64_t)s;
+        so[r] += (uint64_t)d[0]; qo[r] += (uint64_t)d[1]; co[r] += (uint64_t)d[2]; no[r] += (uint64_t)d[3];
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ P0a: one thread per raw record
 struct P0aRaw {
     PrepView q;
