@@ -27,6 +27,7 @@ import json
 import math
 import os
 import re
+import resource
 import subprocess
 import sys
 import threading
@@ -658,6 +659,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     cpu0 = host_cpu_times()
+    ru0 = resource.getrusage(resource.RUSAGE_SELF)
     calls0 = host_call_stats(ctx0.lib)
     t0 = time.time()
     acc = e2e_steps(args.steps, keep_last=True)
@@ -666,6 +668,9 @@ def main():
     torch.cuda.synchronize()
     wall_s = time.time() - t0
     host_load = host_cpu_load(cpu0, host_cpu_times())
+    ru1 = resource.getrusage(resource.RUSAGE_SELF)
+    if host_load is not None:
+        host_load["this_process_cpu_seconds_per_step"] = ((ru1.ru_utime - ru0.ru_utime) + (ru1.ru_stime - ru0.ru_stime)) / args.steps
     calls1 = host_call_stats(ctx0.lib)
     mem_free, mem_total = torch.cuda.mem_get_info()
     call_stats = {name: {"ms_per_step": (calls1[3 * i] - calls0[3 * i]) / args.steps, "calls_per_step": (calls1[3 * i + 1] - calls0[3 * i + 1]) / args.steps,
