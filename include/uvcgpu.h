@@ -308,7 +308,11 @@ int uvcgpu_set_contig_name(uvcgpu_ctx *ctx, int32_t tid, const char *name);
 
 /* Replaces the body of process_batch up to scoring for a batch of tiles (main.cpp:481-591:
  * grouping.cpp:608-997 read filter + family grouping, :459-567 BQ fix-ups, main.hpp:803-874 repeat context,
- * main.cpp:400-429 BAQ offsets, main.hpp:3665-3742 updateByRegion3Aln). Asynchronous on the context's stream. */
+ * main.cpp:400-429 BAQ offsets, main.hpp:3665-3742 updateByRegion3Aln). Asynchronous: the call registers the batch and returns; a worker
+ * thread of the context stages it (upload, staging kernels, pileup launches) in submission order while the caller goes on - typically to
+ * finish the previous batch. Arguments are checked and `tiles` is copied before the call returns; the SoA buffers are borrowed until
+ * uvcgpu_release. Whatever goes wrong during staging (an invalid tile, a contig that was not set, out of memory) is reported by
+ * uvcgpu_collect of the ticket, with uvcgpu_last_error set. */
 int uvcgpu_submit(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *tiles, const uvcgpu_reads_soa *reads, uvcgpu_ticket *ticket);
 
 /* Same as uvcgpu_submit, but the records of the tiles come from several SoA buffers (the uvc1 host decodes the tiles of a batch on several
