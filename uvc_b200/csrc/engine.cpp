@@ -317,11 +317,20 @@ __global__ void __launch_bounds__(128) uvc_k0_read_consts(const BatchView v, int
     if (r0 >= n) { return; }
     const int nr = (int)(n - r0 < 32 ? n - r0 : 32);
     uint8_t *sq = s_qual[warp], *ss = s_seq[warp];
+    // every lane fetches the length and the byte addresses of its own read once; the copy loop takes them from there by shuffle, so that its
+    // iterations carry no dependent loads and the byte loads of several reads are in flight together
+    int32_t my_l = 0;
+    const uint8_t *my_gq = v.qual_raw, *my_gs = v.seq;
+    uint8_t *my_out = v.qual;
+    if (lane < nr) {
+        const ReadRec & R = v.reads[r0 + lane];
+        my_l = R.l_qseq; my_gq = v.qual_raw + v.raw_qual_off[R.raw]; my_gs = v.seq + R.seq_off; my_out = v.qual + R.qual_off;
+    }
+    #pragma unroll 4
     for (int k = 0; k < nr; k++) {
-        const ReadRec & R = v.reads[r0 + k];
-        const int32_t l = R.l_qseq;
+        const int32_t l = __shfl_sync(0xffffffffu, my_l, k);
+        const uint8_t *gq = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)my_gq, k), *gs = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)my_gs, k);
         if (l > UVC_K0_MAXQ) { continue; }
-        const uint8_t *gq = v.qual_raw + v.raw_qual_off[R.raw], *gs = v.seq + R.seq_off;
         for (int32_t i = lane; i < l; i += 32) { sq[k * UVC_K0_QSTRIDE + i] = gq[i]; }
         for (int32_t i = lane; i < (l + 1) / 2; i += 32) { ss[k * UVC_K0_SSTRIDE + i] = gs[i]; }
     }
@@ -333,10 +342,9 @@ __global__ void __launch_bounds__(128) uvc_k0_read_consts(const BatchView v, int
     }
     __syncwarp();
     for (int k = 0; k < nr; k++) {
-        const ReadRec & R = v.reads[r0 + k];
-        const int32_t l = R.l_qseq;
+        const int32_t l = __shfl_sync(0xffffffffu, my_l, k);
+        uint8_t *gq = (uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)my_out, k);
         if (l > UVC_K0_MAXQ) { continue; }
-        uint8_t *gq = v.qual + R.qual_off;
         for (int32_t i = lane; i < l; i += 32) { gq[i] = sq[k * UVC_K0_QSTRIDE + i]; }
     }
 }
