@@ -1811,14 +1811,45 @@ static int ensure_vcf_text(uvcgpu_ctx *ctx, BatchState & bs) {
         const TileInfo & T = bs.hb.tiles[ti];
         if (!T.skipped && ctx->contigs.find(T.tid) == ctx->contigs.end()) { UVC_ERR(ctx) = "contig of a tile was unset before its VCF text was requested"; return UVCGPU_EINVAL; }
     }
+    // Tiles are independent, and so are the positions of a tile: a tile is cut into ranges of positions with about the same number of records
+    // (a deep tile of a small panel has a record per position and symbol: its text alone is hundreds of megabytes), every range is formatted
+    // by one thread, and the ranges' strings are concatenated in order.
+    std::vector<TileTextPlan*> plans((size_t)n_tiles, NULL);
     uvc_parallel_for(n_tiles, ctx->host_threads, [&](int32_t ti) {
+        if (!bs.hb.tiles[ti].skipped) { plans[ti] = uvc_tile_text_plan_new(bs.hb, ti, ctx->contigs.at(bs.hb.tiles[ti].tid), bs.recs_by_tile[ti], bs.sparse[ti]); }
+    });
+    struct Range { int32_t ti, zb0, zb1; };
+    std::vector<Range> ranges;
+    const size_t kRecsPerRange = 512;
+    for (int32_t ti = 0; ti < n_tiles; ti++) {
         const TileInfo & T = bs.hb.tiles[ti];
-        if (T.skipped) { return; }
+        if (T.skipped) { continue; }
+        // cut after the position at which the running record count passes a multiple of kRecsPerRange (records are listed by refpos: close enough to zb)
+        std::vector<int32_t> zbs;
+        for (const VarRec *r : bs.recs_by_tile[ti]) { zbs.push_back(r->symboltype == 0 ? r->refpos + 1 : r->refpos); }
+        std::sort(zbs.begin(), zbs.end());
+        int32_t zb0 = T.rpos_inclu_beg;
+        for (size_t k = kRecsPerRange; k < zbs.size(); k += kRecsPerRange) {
+            const int32_t cut = zbs[k] + 1;
+            if (cut > zb0 && cut <= T.rpos_exclu_end) { ranges.push_back(Range{ti, zb0, cut}); zb0 = cut; }
+        }
+        ranges.push_back(Range{ti, zb0, T.rpos_exclu_end + 1});
+    }
+    std::vector<std::string> parts(ranges.size());
+    uvc_parallel_for((int32_t)ranges.size(), ctx->host_threads, [&](int32_t k) {
+        const Range & R = ranges[(size_t)k];
+        const TileInfo & T = bs.hb.tiles[R.ti];
         auto nm = ctx->contig_names.find(T.tid);
         const std::string tname = (nm == ctx->contig_names.end() ? std::to_string(T.tid) : nm->second);
-        bs.vcf_text[ti] = uvc_tile_vcf_text(bs.hb, ti, ctx->par, tname, ctx->contigs.at(T.tid), bs.recs_by_tile[ti], bs.sites[ti],
-                bs.sparse[ti], bs.ev_host, bs.gvcf.data(), bs.gextra.data());
+        parts[(size_t)k] = uvc_tile_vcf_text_range(*plans[R.ti], bs.hb, R.ti, ctx->par, tname, bs.sites[R.ti], bs.sparse[R.ti], bs.ev_host, bs.gvcf.data(), bs.gextra.data(), R.zb0, R.zb1);
     });
+    {
+        std::vector<size_t> total((size_t)n_tiles, 0);
+        for (size_t k = 0; k < ranges.size(); k++) { total[(size_t)ranges[k].ti] += parts[k].size(); }
+        for (int32_t ti = 0; ti < n_tiles; ti++) { bs.vcf_text[(size_t)ti].reserve(total[(size_t)ti]); }
+        for (size_t k = 0; k < ranges.size(); k++) { bs.vcf_text[(size_t)ranges[k].ti] += parts[k]; std::string().swap(parts[k]); }
+    }
+    for (TileTextPlan *pl : plans) { if (pl) { uvc_tile_text_plan_free(pl); } }
     bs.vcf_built = true;
     return 0;
 }

@@ -221,25 +221,61 @@ void uvc_build_indel_sites(std::vector<TileIndelSites> & sites, std::vector<Inde
     (void)ev;
 }
 
-std::string uvc_tile_vcf_text(const HostBatch & hb, int32_t tile_index, const uvcgpu_params & par, const std::string & tname, const HostContig & contig,
-        const std::vector<const VarRec*> & recs, const TileIndelSites & sites, const TileSparse & sparse, const StageVec<IndelEvent> & ev,
-        const GvcfPos *gvcf, const GvcfExtra *gextra) {
-    std::string out;
+// What the text of every position of a tile needs: built once per tile, then the tile's positions are formatted in independent ranges
+struct TileTextPlan {
+    int32_t nref = 0;
+    std::string refstring;
+    PhaseIndex pidx_bq, pidx_fq, pidx_f2q;
+    std::map<std::pair<int32_t, int32_t>, std::vector<const VarRec*>> by_zb;   // records grouped by (zero-based position, symbol type)
+    size_t n_recs = 0;
+};
+TileTextPlan *uvc_tile_text_plan_new(const HostBatch & hb, int32_t tile_index, const HostContig & contig, const std::vector<const VarRec*> & recs, const TileSparse & sparse) {
+    TileTextPlan *plan = new TileTextPlan();
     const TileInfo & T = hb.tiles[tile_index];
-    if (T.skipped) { return out; }
-    const int32_t nref = (T.ext_end - T.ext_beg) - 1;
-    const std::string refstring = (contig.available ? contig.bases.substr(T.ext_beg, nref) : std::string((size_t)nref, 'n'));
-    const PhaseIndex pidx_bq = phase_index(sparse.hap_bq), pidx_fq = phase_index(sparse.hap_fq), pidx_f2q = phase_index(sparse.hap_f2q);
-    out.reserve(recs.size() * 3200 + (size_t)(T.end_pos - T.beg_pos) * 24 + 4096);
-    // records grouped by (zero-based position, symbol type) in the device's candidate order
-    std::map<std::pair<int32_t, int32_t>, std::vector<const VarRec*>> by_zb;
-    for (const VarRec *r : recs) { by_zb[std::make_pair(r->symboltype == 0 ? r->refpos + 1 : r->refpos, r->symboltype)].push_back(r); }
-    for (auto & kv : by_zb) {
+    if (T.skipped) { return plan; }
+    plan->nref = (T.ext_end - T.ext_beg) - 1;
+    plan->refstring = (contig.available ? contig.bases.substr(T.ext_beg, plan->nref) : std::string((size_t)plan->nref, 'n'));
+    plan->pidx_bq = phase_index(sparse.hap_bq); plan->pidx_fq = phase_index(sparse.hap_fq); plan->pidx_f2q = phase_index(sparse.hap_f2q);
+    for (const VarRec *r : recs) { plan->by_zb[std::make_pair(r->symboltype == 0 ? r->refpos + 1 : r->refpos, r->symboltype)].push_back(r); }
+    for (auto & kv : plan->by_zb) {
         // the device appends with an atomic cursor: restore the reference's candidate order
         std::stable_sort(kv.second.begin(), kv.second.end(), [](const VarRec *a, const VarRec *b) { return a->cand_index < b->cand_index; });
     }
-    int32_t prev_tracklen = 0;
-    for (int32_t zb = T.rpos_inclu_beg; zb <= T.rpos_exclu_end; zb++) {
+    plan->n_recs = recs.size();
+    return plan;
+}
+void uvc_tile_text_plan_free(TileTextPlan *plan) { delete plan; }
+
+std::string uvc_tile_vcf_text(const HostBatch & hb, int32_t tile_index, const uvcgpu_params & par, const std::string & tname, const HostContig & contig,
+        const std::vector<const VarRec*> & recs, const TileIndelSites & sites, const TileSparse & sparse, const StageVec<IndelEvent> & ev,
+        const GvcfPos *gvcf, const GvcfExtra *gextra) {
+    const TileInfo & T = hb.tiles[tile_index];
+    if (T.skipped) { return std::string(); }
+    TileTextPlan *plan = uvc_tile_text_plan_new(hb, tile_index, contig, recs, sparse);
+    std::string out = uvc_tile_vcf_text_range(*plan, hb, tile_index, par, tname, sites, sparse, ev, gvcf, gextra, T.rpos_inclu_beg, T.rpos_exclu_end + 1);
+    uvc_tile_text_plan_free(plan);
+    return out;
+}
+
+// the text of the zero-based positions [zb_begin, zb_end) of a tile (a sub-range of [rpos_inclu_beg, rpos_exclu_end]): ranges are independent
+std::string uvc_tile_vcf_text_range(const TileTextPlan & plan, const HostBatch & hb, int32_t tile_index, const uvcgpu_params & par, const std::string & tname,
+        const TileIndelSites & sites, const TileSparse & sparse, const StageVec<IndelEvent> & ev, const GvcfPos *gvcf, const GvcfExtra *gextra,
+        int32_t zb_begin, int32_t zb_end) {
+    std::string out;
+    const TileInfo & T = hb.tiles[tile_index];
+    if (T.skipped || zb_end <= zb_begin) { return out; }
+    const int32_t nref = plan.nref;
+    const std::string & refstring = plan.refstring;
+    const PhaseIndex & pidx_bq = plan.pidx_bq, & pidx_fq = plan.pidx_fq, & pidx_f2q = plan.pidx_f2q;
+    const auto & by_zb = plan.by_zb;
+    {
+        size_t n_here = 0;
+        for (auto it = by_zb.lower_bound(std::make_pair(zb_begin, 0)); it != by_zb.end() && it->first.first < zb_end; ++it) { n_here += it->second.size(); }
+        out.reserve(n_here * 3200 + (size_t)(zb_end - zb_begin) * 24 + 4096);
+    }
+    // (the tracklen of the position before the range: what the loop carries from one position to the next)
+    int32_t prev_tracklen = (zb_begin > T.rpos_inclu_beg ? gextra[T.pos_off + (zb_begin - 1 - T.ext_beg)].tracklen : 0);
+    for (int32_t zb = zb_begin; zb < zb_end; zb++) {
         const int64_t gp_zb = T.pos_off + (zb - T.ext_beg);
         const GvcfExtra & X = gextra[gp_zb];
         const int32_t curr_tracklen = X.tracklen;

@@ -27,6 +27,15 @@ typedef std::map<std::pair<int32_t, int32_t>, IndelSite> TileIndelSites;   // (r
 void uvc_build_indel_sites(std::vector<TileIndelSites> & sites, std::vector<IndelAllele> & table, const HostBatch & hb,
         const std::vector<TileSparse> & sparse, const std::map<int32_t, HostContig> & contigs, const StageVec<IndelEvent> & ev);
 
+// Shared state of a tile's text (reference string, haplotype indices, records by position), and the text of a range of its positions: a deep
+// tile is formatted by several threads (uvcgpu_tile_vcf / uvcgpu_batch_vcf), each on its own range; the concatenation is the tile's text.
+struct TileTextPlan;
+TileTextPlan *uvc_tile_text_plan_new(const HostBatch & hb, int32_t tile_index, const HostContig & contig, const std::vector<const VarRec*> & recs, const TileSparse & sparse);
+void uvc_tile_text_plan_free(TileTextPlan *plan);
+std::string uvc_tile_vcf_text_range(const TileTextPlan & plan, const HostBatch & hb, int32_t tile_index, const uvcgpu_params & par, const std::string & tname,
+        const TileIndelSites & sites, const TileSparse & sparse, const StageVec<IndelEvent> & ev, const GvcfPos *gvcf, const GvcfExtra *gextra,
+        int32_t zb_begin, int32_t zb_end);
+
 // The uncompressed VCF fragment of one tile (what process_batch appends to uncompressed_vcf_string, main.cpp:1184).
 std::string uvc_tile_vcf_text(const HostBatch & hb, int32_t tile_index, const uvcgpu_params & par, const std::string & tname, const HostContig & contig,
         const std::vector<const VarRec*> & recs_of_tile, const TileIndelSites & sites, const TileSparse & sparse, const StageVec<IndelEvent> & ev,
