@@ -577,6 +577,11 @@ def main():
     #  are in flight at most, which keeps the column caches of all of them inside the 180 GB of HBM)
     reads_per_sub = max(1, n_records // max(1, len(subs)))
     n_ctx = max(1, min(args.contexts, len(subs), max(1, 14_000_000 // reads_per_sub)))
+    # ... and by what one context was seen to hold on the device during the phase above (its slabs: one sub-batch at a time there, two in
+    # flight per context here, with their size classes): four fifths of the HBM at most
+    mem_free1, mem_total1 = torch.cuda.mem_get_info()
+    one_ctx_bytes = max(1, int(mem_total1 - mem_free1))
+    n_ctx = max(1, min(n_ctx, int(0.8 * mem_total1 / (2.0 * one_ctx_bytes))))
     ctxs = [ctx0] + [make_ctx(max(1, host_threads // n_ctx + 1)) for _ in range(n_ctx - 1)]
     ctx0.lib.uvcgpu_set_host_threads(ctx0.handle, max(1, host_threads // n_ctx + 1))
     totals = {"h2d": 0, "d2h": 0, "vcf": 0, "rec": 0, "launch": 0, "prep_ms": 0.0, "sync_ms": 0.0, "stage_call_ms": 0.0, "sc2": 0.0, "sc3": 0.0, "sc4": 0.0, "sc5": 0.0, "submit_s": 0.0, "wait_s": 0.0, "score_s": 0.0, "text_s": 0.0, "release_s": 0.0}
@@ -822,6 +827,7 @@ def main():
                        "sub_batches_per_step": len(subs),
                        "l2": "per-position state of a sub-batch (%.0f MB) is larger than L2, no flush needed" % (agg["n_ext_positions"] * 6272 / 1e6 / len(subs)),
                        "dataset_generation_s_untimed": ds.get("gen_s"), "tiler_s_untimed": tile_s, "host_threads": host_threads,
+                       "device_bytes_held_by_one_context_after_the_kernel_phase": one_ctx_bytes,
                        "host_inputs": ("%d of %d decoded sub-batch buffers page-locked with uvcgpu_host_register_reads (%.1f s, untimed): uploaded straight from them" % (n_registered, len(subs), register_s)
                                        if n_registered else "pageable: staged through the library's page-locked copy"),
                        "multi_gpu": ("rank r processes shard r (same shape, seed + r) of an %d-shard job; no data-path collective; rank 0 concatenates the VCF bodies" % world
