@@ -111,3 +111,15 @@ def test_cuda_vcf_c2_depth_panel_vs_reference(synth_c2_depth, tmp_path):
     st = _vs_reference(synth_c2_depth, "chrP", tiles, [], {}, False, tmp_path)
     assert st.gpu_launches > 0
     _restricted_equals_full(synth_c2_depth, tiles, False)
+
+
+def test_emulation_vcf_text_in_many_ranges(synth_small, synth_umi, monkeypatch):
+    """The text of a tile is formatted in independent ranges of positions (512 records each by default): tiny ranges must give the same bytes,
+    including the MGVCF block lines, the additional-indel-candidate lines (they look at the position before the range) and empty ranges."""
+    tiles = [(0, 0, 6000, 0), (0, 6000, 12000, 0)]
+    a, _ = _our_lines(synth_small["bam"], synth_small["fasta"], tiles, True, should_output_all=1)
+    u, _ = _our_lines(synth_umi["bam"], synth_umi["fasta"], [(0, 1500, 2500, 0)], True)
+    monkeypatch.setenv("UVC_TEXT_RECS_PER_RANGE", "3")
+    b, _ = _our_lines(synth_small["bam"], synth_small["fasta"], tiles, True, should_output_all=1)
+    w, _ = _our_lines(synth_umi["bam"], synth_umi["fasta"], [(0, 1500, 2500, 0)], True)
+    assert len(a) > 1000 and a == b and len(u) > 0 and u == w

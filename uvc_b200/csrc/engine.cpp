@@ -1820,7 +1820,8 @@ static int ensure_vcf_text(uvcgpu_ctx *ctx, BatchState & bs) {
     });
     struct Range { int32_t ti, zb0, zb1; };
     std::vector<Range> ranges;
-    const size_t kRecsPerRange = 512;
+    size_t kRecsPerRange = 512;
+    { const char *f = getenv("UVC_TEXT_RECS_PER_RANGE"); if (f && atoi(f) > 0) { kRecsPerRange = (size_t)atoi(f); } }      // tests force many small ranges
     for (int32_t ti = 0; ti < n_tiles; ti++) {
         const TileInfo & T = bs.hb.tiles[ti];
         if (T.skipped) { continue; }
