@@ -66,7 +66,7 @@ struct BatchState {
     std::vector<std::pair<void*, size_t>> alloc_sizes;
     std::vector<uvcgpu_reads_soa> sources; // caller's SoA buffers (borrowed until release)
     std::vector<int32_t> tile_source;
-    std::vector<std::string> vcf_text;     // per-tile VCF body, formatted once on all host threads
+    std::vector<std::vector<std::string>> vcf_text;   // per tile: its VCF body as the strings of its position ranges, in order (formatted once on all host threads)
     bool vcf_built = false;
     uvcgpu_batch_stats stats;
     bool submitted = true;                 // false while the context's worker thread still stages the batch
@@ -1806,7 +1806,7 @@ static int ensure_vcf_text(uvcgpu_ctx *ctx, BatchState & bs) {
     int rc = ensure_scored(ctx, bs);
     if (rc != 0) { return rc; }
     const int32_t n_tiles = (int32_t)bs.hb.tiles.size();
-    bs.vcf_text.assign((size_t)n_tiles, std::string());
+    bs.vcf_text.assign((size_t)n_tiles, std::vector<std::string>());
     for (int32_t ti = 0; ti < n_tiles; ti++) {
         const TileInfo & T = bs.hb.tiles[ti];
         if (!T.skipped && ctx->contigs.find(T.tid) == ctx->contigs.end()) { UVC_ERR(ctx) = "contig of a tile was unset before its VCF text was requested"; return UVCGPU_EINVAL; }
@@ -1844,12 +1844,7 @@ static int ensure_vcf_text(uvcgpu_ctx *ctx, BatchState & bs) {
         const std::string tname = (nm == ctx->contig_names.end() ? std::to_string(T.tid) : nm->second);
         parts[(size_t)k] = uvc_tile_vcf_text_range(*plans[R.ti], bs.hb, R.ti, ctx->par, tname, bs.sites[R.ti], bs.sparse[R.ti], bs.ev_host, bs.gvcf.data(), bs.gextra.data(), R.zb0, R.zb1);
     });
-    {
-        std::vector<size_t> total((size_t)n_tiles, 0);
-        for (size_t k = 0; k < ranges.size(); k++) { total[(size_t)ranges[k].ti] += parts[k].size(); }
-        for (int32_t ti = 0; ti < n_tiles; ti++) { bs.vcf_text[(size_t)ti].reserve(total[(size_t)ti]); }
-        for (size_t k = 0; k < ranges.size(); k++) { bs.vcf_text[(size_t)ranges[k].ti] += parts[k]; std::string().swap(parts[k]); }
-    }
+    for (size_t k = 0; k < ranges.size(); k++) { bs.vcf_text[(size_t)ranges[k].ti].emplace_back(std::move(parts[k])); }     // (no concatenation: the callers copy the parts out)
     for (TileTextPlan *pl : plans) { if (pl) { uvc_tile_text_plan_free(pl); } }
     bs.vcf_built = true;
     return 0;
@@ -1858,7 +1853,11 @@ static int ensure_vcf_text(uvcgpu_ctx *ctx, BatchState & bs) {
 static int tile_vcf_text(uvcgpu_ctx *ctx, BatchState & bs, int32_t tile_index, std::string & out) {
     int rc = ensure_vcf_text(ctx, bs);
     if (rc != 0) { return rc; }
-    out = bs.vcf_text[tile_index];
+    out.clear();
+    size_t total = 0;
+    for (const auto & t : bs.vcf_text[tile_index]) { total += t.size(); }
+    out.reserve(total);
+    for (const auto & t : bs.vcf_text[tile_index]) { out += t; }
     return 0;
 }
 
@@ -1870,11 +1869,20 @@ int uvcgpu_tile_vcf(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, int32_t tile_index, c
     BatchState & bs = *it->second;
     if (!bs.collected) { UVC_ERR(ctx) = "batch not collected yet"; return UVCGPU_EINVAL; }
     if (tile_index < 0 || tile_index >= (int32_t)bs.hb.tiles.size()) { return UVCGPU_EINVAL; }
-    std::string s;
-    int rc = tile_vcf_text(ctx, bs, tile_index, s);
+    int rc = ensure_vcf_text(ctx, bs);
     if (rc != 0) { return rc; }
-    *needed = s.size();
-    if (dst && cap) { memcpy(dst, s.data(), s.size() < cap ? s.size() : cap); }
+    size_t total = 0;
+    for (const auto & t : bs.vcf_text[tile_index]) { total += t.size(); }
+    *needed = total;
+    if (dst && cap) {
+        size_t at = 0;
+        for (const auto & t : bs.vcf_text[tile_index]) {
+            if (at >= cap) { break; }
+            const size_t n = (t.size() < cap - at ? t.size() : cap - at);
+            memcpy(dst + at, t.data(), n);
+            at += n;
+        }
+    }
     return UVCGPU_OK;
 }
 
@@ -1888,16 +1896,16 @@ int uvcgpu_batch_vcf(uvcgpu_ctx *ctx, uvcgpu_ticket ticket, char *dst, size_t ca
     int rc = ensure_vcf_text(ctx, bs);
     if (rc != 0) { return rc; }
     size_t total = 0;
-    for (const auto & t : bs.vcf_text) { total += t.size(); }
+    std::vector<std::pair<const std::string*, size_t>> pieces;     // (part, its offset in the batch's text)
+    for (const auto & tile : bs.vcf_text) { for (const auto & t : tile) { pieces.push_back(std::make_pair(&t, total)); total += t.size(); } }
     *needed = total;
     if (dst && cap) {
-        size_t at = 0;
-        for (const auto & t : bs.vcf_text) {
-            if (at >= cap) { break; }
-            const size_t n = (t.size() < cap - at ? t.size() : cap - at);
-            memcpy(dst + at, t.data(), n);
-            at += n;
-        }
+        uvc_parallel_for((int32_t)pieces.size(), (total >= ((size_t)8 << 20) ? ctx->host_threads : 1), [&](int32_t k) {
+            const std::string & t = *pieces[(size_t)k].first;
+            const size_t at = pieces[(size_t)k].second;
+            if (at >= cap) { return; }
+            memcpy(dst + at, t.data(), (t.size() < cap - at ? t.size() : cap - at));
+        });
     }
     return UVCGPU_OK;
 }
