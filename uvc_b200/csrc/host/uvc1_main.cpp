@@ -336,13 +336,10 @@ void lane_thread(Lane lane) {
         if (0 == rc) { rc = uvcgpu_score(ctx, ticket, &st); }
         const int64_t t4 = now_us();
         std::string text;
-        if (0 == rc) {
-            std::vector<size_t> need((size_t)n_tiles, 0);
+        if (0 == rc) {      // the bodies of the batch's tiles in tile order (formatted and copied out on the lane's host threads)
             size_t total = 0;
-            for (int32_t k = 0; k < n_tiles && 0 == rc; k++) { rc = uvcgpu_tile_vcf(ctx, ticket, k, NULL, 0, &need[k]); total += need[k]; }
-            text.resize(total);
-            size_t off = 0;
-            for (int32_t k = 0; k < n_tiles && 0 == rc; k++) { size_t n2 = 0; rc = uvcgpu_tile_vcf(ctx, ticket, k, &text[off], need[k], &n2); off += need[k]; }
+            rc = uvcgpu_batch_vcf(ctx, ticket, NULL, 0, &total);
+            if (0 == rc && total > 0) { text.resize(total); rc = uvcgpu_batch_vcf(ctx, ticket, &text[0], total, &total); }
         }
         const int64_t t5 = now_us();
         if (rc != 0) { sh->fail(std::string("batch ") + std::to_string(b.seq) + " failed (" + std::to_string(rc) + "): " + uvcgpu_last_error(ctx)); break; }
