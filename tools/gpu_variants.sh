@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 for V in "$@"; do
   touch uvc_b200/csrc/engine.cpp
   make -C uvc_b200/csrc EXTRA_DEFS="$V" "$PWD/uvc_b200/lib/libuvcgpu.so" -j4 > gpurun_out/variant_build.log 2>&1 || { echo "build failed"; tail -5 gpurun_out/variant_build.log; continue; }
-  echo "=== variant [$V]"; grep -E "uvc_k1_prep|uvc_kf_frag|uvc_k3b|uvc_k4_family_consensus9" -A3 uvc_b200/lib/engine.ptxas.log | grep -E "Used|spill" | head -8
+  echo "=== variant [$V]"; grep -E "uvc_k2_bias|uvc_k3b|uvc_k4_family_consensus9" -A3 uvc_b200/lib/engine.ptxas.log | grep -E "Used|spill" | head -8
   python bench.py --config c2 --scale 0.05 --steps 5 --warmup 3 --sub-batches 1 --contexts 1 --skip-cpu-baseline --skip-pipeline 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())

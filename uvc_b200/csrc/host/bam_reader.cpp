@@ -1,6 +1,7 @@
 // bam_reader.cpp - BGZF/BAM/BAI and FASTA/FAI decoding into SoA buffers (see bam_reader.h).
 // Formats follow the SAM/BAM specification (sections 4.1 BGZF, 4.2 BAM, 5.2 BAI) and the samtools faidx five-column index.
 #include "bam_reader.h"
+#include "inflate_fast.h"
 
 #include <zlib.h>
 
@@ -47,13 +48,9 @@ struct SeqInflater {
         for (int t = 0; t < n_threads; t++) { pool.emplace_back([this]() { worker(); }); }
     }
     static void inflate_slot(Slot & s) {
-        z_stream zs;
-        memset(&zs, 0, sizeof(zs));
-        if (inflateInit2(&zs, -15) != Z_OK) { s.ok = false; return; }
-        zs.next_in = s.c.data(); zs.avail_in = s.clen; zs.next_out = s.u.data(); zs.avail_out = kMaxBlock;
-        s.ok = (inflate(&zs, Z_FINISH) == Z_STREAM_END);
-        s.ulen = (int)zs.total_out;
-        inflateEnd(&zs);
+        const int64_t n = uvc_inflate_member(s.c.data(), (size_t)s.clen, s.u.data(), (size_t)kMaxBlock);    // (s.c holds the footer and 56 bytes of slack after the stream)
+        s.ok = (n >= 0);
+        s.ulen = (int)(n >= 0 ? n : 0);
     }
     void worker() {
         int seen = 0;
@@ -96,6 +93,7 @@ struct SeqInflater {
             }
             if (bsize < 0) { failed = true; break; }
             s.clen = bsize - 12 - xlen - 8;
+            if (s.clen < 0) { failed = true; break; }
             if (fread(s.c.data(), 1, s.clen + 8, fp) != (size_t)(s.clen + 8)) { failed = true; break; }
             s.addr = next_addr; s.bsize = bsize;
             next_addr += bsize;
@@ -165,12 +163,12 @@ struct BgzfIn {
         }
         if (bsize < 0) { return -1; }
         const int clen = bsize - 12 - xlen - 8;
+        if (clen < 0) { return -1; }
         if (fread(cbuf.data(), 1, clen + 8, fp) != (size_t)(clen + 8)) { return -1; }
         ubuf.resize(kMaxBlock);
-        if (!zs_init) { memset(&zs, 0, sizeof(zs)); if (inflateInit2(&zs, -15) != Z_OK) { return -1; } zs_init = true; } else { inflateReset(&zs); }
-        zs.next_in = cbuf.data(); zs.avail_in = clen; zs.next_out = ubuf.data(); zs.avail_out = kMaxBlock;
-        if (inflate(&zs, Z_FINISH) != Z_STREAM_END) { return -1; }
-        ulen = (int)zs.total_out; uoff = 0; block_addr = caddr; block_clen = bsize;
+        const int64_t n_out = uvc_inflate_member(cbuf.data(), (size_t)clen, ubuf.data(), (size_t)kMaxBlock);     // (cbuf holds the footer and 56 bytes of slack after the stream)
+        if (n_out < 0) { return -1; }
+        ulen = (int)n_out; uoff = 0; block_addr = caddr; block_clen = bsize;
         return 0;
     }
     int seek(int64_t voff) {
