@@ -18,6 +18,8 @@ const int LT_SIZE = (1 << LT_BITS) + 1024, DT_SIZE = (1 << DT_BITS) + 512;    //
 // table entry: bits 0-7 code length to consume (second level: the bits beyond the primary index), bits 8-12 extra bits (or second-level index
 // bits), bits 16-31 value (literal, base length, base distance, or start of the second-level table); flags in bits 13-15
 const uint32_t F_LITERAL = 1u << 13, F_EOB = 1u << 14, F_SUB = 1u << 15;
+// literal entries of the primary literal/length table may carry TWO literals (bit 12 set; value = first | second << 8, length = both codes): see pair_literals
+const uint32_t F_LIT2 = 1u << 12;
 
 const uint16_t LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
 const uint8_t LEN_XBITS[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -98,6 +100,22 @@ bool build_table(uint32_t *tab, int tab_size, int root_bits, const uint8_t *lens
     return true;
 }
 
+// Quality strings and 4-bit packed bases are literal-heavy: most of a BAM's deflate symbols are literals with short codes. Wherever the bits of
+// a primary index that follow a literal's code decide a second literal completely, the entry is replaced by one that yields both.
+void pair_literals(uint32_t *tab) {
+    uint32_t one[1 << LT_BITS];
+    memcpy(one, tab, sizeof(one));
+    for (uint32_t i = 0; i < (1u << LT_BITS); i++) {
+        const uint32_t e = one[i];
+        if (!(e & F_LITERAL) || (e & F_SUB)) { continue; }
+        const int l1 = (int)(e & 0xff), rem = LT_BITS - l1;
+        if (rem < 1) { continue; }
+        const uint32_t e2 = one[i >> l1];               // (the missing high bits read as zeros: fine for a code of at most `rem` bits)
+        if (!(e2 & F_LITERAL) || (e2 & F_SUB) || (int)(e2 & 0xff) > rem) { continue; }
+        tab[i] = F_LITERAL | F_LIT2 | (((e >> 16) & 0xffu) << 16) | (((e2 >> 16) & 0xffu) << 24) | (uint32_t)(l1 + (int)(e2 & 0xff));
+    }
+}
+
 struct FixedTables {      // the fixed code of block type 1 (RFC 1951, 3.2.6): both codes contain reserved symbols, so they are filled in directly
     uint32_t lt[LT_SIZE], dt[DT_SIZE];
     FixedTables() {
@@ -128,6 +146,7 @@ struct FixedTables {      // the fixed code of block type 1 (RFC 1951, 3.2.6): b
             e |= 5u;
             for (uint32_t k = reverse_bits((uint32_t)i, 5); k < (1u << DT_BITS); k += 32) { dt[k] = e; }
         }
+        pair_literals(lt);
     }
 };
 const FixedTables & fixed_tables() { static const FixedTables t; return t; }
@@ -215,11 +234,57 @@ int64_t uvc_inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t o
             }
             if (0 == lens[256]) { return -1; }      // no end-of-block code
             if (!build_table(lt_dyn, LT_SIZE, LT_BITS, lens, hlit, 0)) { return -1; }
+            pair_literals(lt_dyn);
             if (!build_table(dt_dyn, DT_SIZE, DT_BITS, lens + hlit, hdist, 1)) { return -1; }
             lt = lt_dyn; dt = dt_dyn;
         } else { return -1; }
         // ---- the symbols of the block
-        for (;;) {
+        bool eob = false;
+        while (!eob) {
+            // far from both ends: a symbol reads at most 8 bytes beyond ip and writes at most 258 + 8 bytes beyond op, so nothing is checked but the
+            // match distance
+            while (ip + 16 <= in_end && (size_t)(out_end - op) >= 274) {
+                REFILL();
+                uint32_t e = lt[bb & ((1u << LT_BITS) - 1)];
+                if (e & F_LITERAL) {
+                    // up to three table entries (one or two literals each) per refill: at least 56 - 3 * 15 bits remain for the next lookup
+                    op[0] = (uint8_t)(e >> 16); op[1] = (uint8_t)(e >> 24); op += 1 + ((e >> 12) & 1u); DROP((int)(e & 0xff));
+                    e = lt[bb & ((1u << LT_BITS) - 1)];
+                    if (e & F_LITERAL) {
+                        op[0] = (uint8_t)(e >> 16); op[1] = (uint8_t)(e >> 24); op += 1 + ((e >> 12) & 1u); DROP((int)(e & 0xff));
+                        e = lt[bb & ((1u << LT_BITS) - 1)];
+                        if (e & F_LITERAL) { op[0] = (uint8_t)(e >> 16); op[1] = (uint8_t)(e >> 24); op += 1 + ((e >> 12) & 1u); DROP((int)(e & 0xff)); }
+                    }
+                    continue;
+                }
+                if (e & F_SUB) { e = lt[(e >> 16) + ((bb >> LT_BITS) & ((1u << ((e >> 8) & 31)) - 1))]; DROP(LT_BITS); }
+                int l = (int)(e & 0xff);
+                if (0 == l) { return -1; }
+                DROP(l);
+                if (e & F_LITERAL) { *op++ = (uint8_t)(e >> 16); continue; }      // (a literal with a long code, from a second-level table)
+                if (e & F_EOB) { eob = true; break; }
+                const int xb = (int)((e >> 8) & 31);
+                const uint32_t len = (e >> 16) + (uint32_t)(bb & ((1u << xb) - 1));
+                DROP(xb);
+                uint32_t d = dt[bb & ((1u << DT_BITS) - 1)];
+                if (d & F_SUB) { d = dt[(d >> 16) + ((bb >> DT_BITS) & ((1u << ((d >> 8) & 31)) - 1))]; DROP(DT_BITS); }
+                l = (int)(d & 0xff);
+                if (0 == l) { return -1; }
+                DROP(l);
+                const int dxb = (int)((d >> 8) & 31);
+                const uint32_t dist = (d >> 16) + (uint32_t)(bb & ((1u << dxb) - 1));
+                DROP(dxb);
+                if (dist > (size_t)(op - out)) { return -1; }
+                const uint8_t *src = op - dist;
+                uint8_t *dst = op;
+                const uint8_t *const stop = op + len;
+                if (dist >= 8) { do { memcpy(dst, src, 8); dst += 8; src += 8; } while (dst < stop); }
+                else if (1 == dist) { memset(op, *src, len); }
+                else { do { *dst++ = *src++; } while (dst < stop); }
+                op += len;
+            }
+            if (eob) { break; }
+            // near an end: one symbol with every check
             if (ip > in_end + 8) { return -1; }
             REFILL();
             uint32_t e = lt[bb & ((1u << LT_BITS) - 1)];
@@ -228,15 +293,11 @@ int64_t uvc_inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t o
             if (0 == l) { return -1; }
             DROP(l);
             if (e & F_LITERAL) {
-                if (op >= out_end) { return -1; }
-                *op++ = (uint8_t)(e >> 16);
-                // a second and a third literal without a refill (at least 56 - 15 bits are left)
-                e = lt[bb & ((1u << LT_BITS) - 1)];
-                if ((e & F_LITERAL) && op < out_end) {
-                    DROP((int)(e & 0xff)); *op++ = (uint8_t)(e >> 16);
-                    e = lt[bb & ((1u << LT_BITS) - 1)];
-                    if ((e & F_LITERAL) && op < out_end) { DROP((int)(e & 0xff)); *op++ = (uint8_t)(e >> 16); }
-                }
+                const size_t n_lit = 1 + ((e >> 12) & 1u);
+                if ((size_t)(out_end - op) < n_lit) { return -1; }
+                op[0] = (uint8_t)(e >> 16);
+                if (2 == n_lit) { op[1] = (uint8_t)(e >> 24); }
+                op += n_lit;
                 continue;
             }
             if (e & F_EOB) { break; }
@@ -254,15 +315,7 @@ int64_t uvc_inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t o
             DROP(dxb);
             if (dist > (size_t)(op - out) || len > (size_t)(out_end - op)) { return -1; }
             const uint8_t *src = op - dist;
-            if (dist >= 8 && (size_t)(out_end - op) >= len + 8) {
-                uint8_t *dst = op;
-                const uint8_t *const stop = op + len;
-                do { memcpy(dst, src, 8); dst += 8; src += 8; } while (dst < stop);
-            } else if (1 == dist) {
-                memset(op, *src, len);
-            } else {
-                for (uint32_t k = 0; k < len; k++) { op[k] = src[k]; }
-            }
+            for (uint32_t k = 0; k < len; k++) { op[k] = src[k]; }
             op += len;
         }
         if (last) { break; }
