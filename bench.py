@@ -863,7 +863,11 @@ def main():
                                         "frac": path_bytes / (step_ms / 1e3) / 1e9 / peak},
                          "issue": issue},
             "clocks": sampler.summary()}
+    if n_registered:
+        capi.load_gpu().uvcgpu_host_unregister_reads.argtypes = [C.c_void_p]
     for s in subs:
+        if n_registered and s is not None:
+            capi.load_gpu().uvcgpu_host_unregister_reads(C.byref(s[2]))
         s[1].close()
     have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "uvc1"))
     if world == 1 and not args.skip_pipeline:
@@ -871,9 +875,13 @@ def main():
         try:
             exe = os.path.join(ROOT, "uvc_b200", "bin", "uvc1")
             extra = (["-R", ds["bed"]] if ds.get("bed") else [])
-            t_ref, wall, _ = run_uvc1(exe, ds, extra, os.path.join(args.workdir, "ours_%s.vcf.gz" % name), TILER_THREADS, ["--gpus", "1"])
-            line["pipeline"] = {"seconds": wall, "reads_per_s": n_reads / wall, "positions_per_s": n_positions_of(ds) / wall,
-                                "what": "uvc_b200/bin/uvc1 -t %d --gpus 1 on the whole bench BAM, process start to exit (CUDA start-up, tiling, decode, kernels, VCF text, BGZF output)" % TILER_THREADS}
+            walls = []
+            for _ in range(3):     # a 3 s process on a shared box: run to run 2.7 - 3.8 s (tools/gpu_pipeline_check.sh); the median of three is reported
+                t_ref, wall, _ = run_uvc1(exe, ds, extra, os.path.join(args.workdir, "ours_%s.vcf.gz" % name), TILER_THREADS, ["--gpus", "1"])
+                walls.append(wall)
+            wall = sorted(walls)[1]
+            line["pipeline"] = {"seconds": wall, "seconds_of_every_run": walls, "reads_per_s": n_reads / wall, "positions_per_s": n_positions_of(ds) / wall,
+                                "what": "uvc_b200/bin/uvc1 -t %d --gpus 1 on the whole bench BAM, process start to exit (CUDA start-up, tiling, decode, kernels, VCF text, BGZF output); median of three runs" % TILER_THREADS}
         except Exception as e:  # noqa: BLE001
             line["pipeline"] = {"seconds": None, "what": "failed: %s" % e}
     if world == 1 and not args.skip_cpu_baseline and have_ref:   # (reported at N = 1 only)
