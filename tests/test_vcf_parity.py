@@ -123,3 +123,17 @@ def test_emulation_vcf_text_in_many_ranges(synth_small, synth_umi, monkeypatch):
     b, _ = _our_lines(synth_small["bam"], synth_small["fasta"], tiles, True, should_output_all=1)
     w, _ = _our_lines(synth_umi["bam"], synth_umi["fasta"], [(0, 1500, 2500, 0)], True)
     assert len(a) > 1000 and a == b and len(u) > 0 and u == w
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_emulation_needed_positions_random_tilings(synth_small, seed):
+    """Random cuts of a region into tiles of 1 to ~900 bases (tiny tiles, tiles that start where the previous one ends, gaps between tiles): the
+    text with the output-only counters restricted to the needed positions must equal the whole-extent text."""
+    import random
+    rnd = random.Random(seed)
+    tiles, pos = [], rnd.randint(0, 300)
+    while pos < 5200 and len(tiles) < 9:
+        length = rnd.choice([1, 2, 3, 17, 64, 200, 333, 900])
+        tiles.append((0, pos, pos + length, 0))
+        pos += length + rnd.choice([0, 0, 1, 50, 700])
+    _restricted_equals_full(synth_small, tiles, True)
