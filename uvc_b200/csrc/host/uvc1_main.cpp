@@ -268,18 +268,71 @@ void lane_thread(Lane lane) {
     { int64_t z = 0; sh->t_ctx_ready.compare_exchange_strong(z, now_us()); }
     const int n_dec = std::max(1, lane.n_threads);
     std::vector<uvchost_bam*> bams((size_t)n_dec, NULL);
-    std::vector<uvchost_readbuf*> rbs((size_t)n_dec, NULL);
-    for (int k = 0; k < n_dec; k++) { bams[k] = uvchost_bam_open(o.bam.c_str()); rbs[k] = uvchost_readbuf_new(); if (NULL == bams[k]) { sh->fail("failed to open " + o.bam); } }
+    // Two sets of read buffers: uvcgpu_submit is asynchronous, so the lane decodes batch k+1 into one set while the GPU works on batch k, whose
+    // records stay in the other set until it is released.
+    std::vector<uvchost_readbuf*> rbs2[2];
+    for (int k = 0; k < n_dec; k++) { bams[k] = uvchost_bam_open(o.bam.c_str()); if (NULL == bams[k]) { sh->fail("failed to open " + o.bam); } }
+    for (int h = 0; h < 2; h++) { for (int k = 0; k < n_dec; k++) { rbs2[h].push_back(uvchost_readbuf_new()); } }
     uvchost_fasta *fa = NULL;
     if (!o.fasta.empty()) { fa = uvchost_fasta_open(o.fasta.c_str()); if (NULL == fa) { sh->fail("failed to open " + o.fasta + " (or its .fai)"); } }
     std::set<int32_t> loaded;
+    struct InFlight {
+        bool active = false;
+        uvcgpu_ticket ticket = 0;
+        int64_t seq = 0;
+        int32_t n_tiles = 0;
+        std::set<int32_t> contigs;
+        std::vector<uvcgpu_tile> tiles; std::vector<int32_t> tile_source; std::vector<uvcgpu_reads_soa> sources;
+        int64_t us_fetch = 0, us_prep = 0;
+    };
+    InFlight fl[2];
+    // collect, score, text, release, compress and publish a submitted batch
+    auto finish = [&](InFlight & f) -> bool {
+        if (!f.active) { return true; }
+        f.active = false;
+        uvcgpu_batch_stats st;
+        const int64_t t2 = now_us();
+        int rc2 = uvcgpu_collect(ctx, f.ticket, &st);
+        const int64_t t3 = now_us();
+        if (0 == rc2) { rc2 = uvcgpu_score(ctx, f.ticket, &st); }
+        const int64_t t4 = now_us();
+        std::string text;
+        if (0 == rc2) {      // the bodies of the batch's tiles in tile order (formatted and copied out on the lane's host threads)
+            size_t total = 0;
+            rc2 = uvcgpu_batch_vcf(ctx, f.ticket, NULL, 0, &total);
+            if (0 == rc2 && total > 0) { text.resize(total); rc2 = uvcgpu_batch_vcf(ctx, f.ticket, &text[0], total, &total); }
+        }
+        const int64_t t5 = now_us();
+        if (rc2 != 0) { sh->fail(std::string("batch ") + std::to_string(f.seq) + " failed (" + std::to_string(rc2) + "): " + uvcgpu_last_error(ctx)); return false; }
+        uvcgpu_release(ctx, f.ticket);
+        std::string outbytes;
+        if (o.out == "-") { outbytes.swap(text); }
+        else if (uvchost_bgzf_compress(outbytes, text.data(), text.size(), o.compress_level, lane.n_threads) != 0) { sh->fail("BGZF compression failed"); return false; }
+        const int64_t t6 = now_us();
+        sh->n_reads_kept += st.n_reads_kept; sh->n_positions += st.n_positions; sh->n_records += st.n_vcf_records; sh->n_batches += 1; sh->n_launches += st.gpu_launches;
+        sh->us_fetch += f.us_fetch; sh->us_prep += f.us_prep; sh->us_gpu_wait += t3 - t2; sh->us_score += t4 - t3; sh->us_text += t5 - t4; sh->us_compress += t6 - t5;
+        { std::lock_guard<std::mutex> lk(sh->kernel_ms_mutex); sh->kernel_ms += st.kernel_ms; }
+        {
+            std::lock_guard<std::mutex> lk(sh->out_mutex);
+            sh->done[f.seq].swap(outbytes);
+            { int64_t z = 0; sh->t_first_batch.compare_exchange_strong(z, now_us()); }
+        }
+        sh->out_cv.notify_all();
+        return true;
+    };
     Batch b;
+    int cur = 0;
     while (!sh->failed.load() && sh->batches.pop(b)) {
+        InFlight & f = fl[cur];
+        InFlight & prev = fl[cur ^ 1];
+        std::vector<uvchost_readbuf*> & rbs = rbs2[cur];
         const int32_t n_tiles = (int32_t)b.tiles.size();
-        // reference bases of the contigs this batch touches (load_refstring, main.cpp:54-70)
+        // reference bases of the contigs this batch touches (load_refstring, main.cpp:54-70); the batch in flight keeps its own
         std::set<int32_t> needed;
         for (const auto & l : b.tiles) { needed.insert(l.tid); }
-        for (auto it = loaded.begin(); it != loaded.end();) { if (!needed.count(*it)) { uvcgpu_unset_contig(ctx, *it); it = loaded.erase(it); } else { ++it; } }
+        for (auto it = loaded.begin(); it != loaded.end();) {
+            if (!needed.count(*it) && !(prev.active && prev.contigs.count(*it))) { uvcgpu_unset_contig(ctx, *it); it = loaded.erase(it); } else { ++it; }
+        }
         for (int32_t tid : needed) {
             if (loaded.count(tid)) { continue; }
             int64_t len = 0;
@@ -293,8 +346,10 @@ void lane_thread(Lane lane) {
         if (sh->failed.load()) { break; }
         // decode: the tiles are cut into n_dec runs of consecutive tiles, one decode thread and one SoA buffer per run
         const int64_t t0 = now_us();
-        std::vector<uvcgpu_tile> tiles((size_t)n_tiles);
-        std::vector<int32_t> tile_source((size_t)n_tiles, 0);
+        f.tiles.assign((size_t)n_tiles, uvcgpu_tile());
+        f.tile_source.assign((size_t)n_tiles, 0);
+        std::vector<uvcgpu_tile> & tiles = f.tiles;
+        std::vector<int32_t> & tile_source = f.tile_source;
         const int n_src = std::min(n_dec, (int)n_tiles);
         std::vector<std::thread> pool;
         std::atomic<int> dec_failed(0);
@@ -324,41 +379,21 @@ void lane_thread(Lane lane) {
         }
         for (auto & th : pool) { th.join(); }
         if (dec_failed.load()) { sh->fail("error while reading " + o.bam); break; }
-        std::vector<uvcgpu_reads_soa> sources((size_t)n_src);
-        for (int s = 0; s < n_src; s++) { uvchost_readbuf_view(rbs[s], &sources[s]); }
+        f.sources.assign((size_t)n_src, uvcgpu_reads_soa());
+        for (int s = 0; s < n_src; s++) { uvchost_readbuf_view(rbs[s], &f.sources[s]); }
         const int64_t t1 = now_us();
-        uvcgpu_ticket ticket = 0;
-        uvcgpu_batch_stats st;
-        rc = uvcgpu_submit_multi(ctx, n_tiles, tiles.data(), n_src, sources.data(), tile_source.data(), &ticket);
+        rc = uvcgpu_submit_multi(ctx, n_tiles, tiles.data(), n_src, f.sources.data(), tile_source.data(), &f.ticket);
         const int64_t t2 = now_us();
-        if (0 == rc) { rc = uvcgpu_collect(ctx, ticket, &st); }
-        const int64_t t3 = now_us();
-        if (0 == rc) { rc = uvcgpu_score(ctx, ticket, &st); }
-        const int64_t t4 = now_us();
-        std::string text;
-        if (0 == rc) {      // the bodies of the batch's tiles in tile order (formatted and copied out on the lane's host threads)
-            size_t total = 0;
-            rc = uvcgpu_batch_vcf(ctx, ticket, NULL, 0, &total);
-            if (0 == rc && total > 0) { text.resize(total); rc = uvcgpu_batch_vcf(ctx, ticket, &text[0], total, &total); }
-        }
-        const int64_t t5 = now_us();
-        if (rc != 0) { sh->fail(std::string("batch ") + std::to_string(b.seq) + " failed (" + std::to_string(rc) + "): " + uvcgpu_last_error(ctx)); break; }
-        uvcgpu_release(ctx, ticket);
-        std::string outbytes;
-        if (o.out == "-") { outbytes.swap(text); }
-        else if (uvchost_bgzf_compress(outbytes, text.data(), text.size(), o.compress_level, lane.n_threads) != 0) { sh->fail("BGZF compression failed"); break; }
-        const int64_t t6 = now_us();
-        sh->n_reads_kept += st.n_reads_kept; sh->n_positions += st.n_positions; sh->n_records += st.n_vcf_records; sh->n_batches += 1; sh->n_launches += st.gpu_launches;
-        sh->us_fetch += t1 - t0; sh->us_prep += t2 - t1; sh->us_gpu_wait += t3 - t2; sh->us_score += t4 - t3; sh->us_text += t5 - t4; sh->us_compress += t6 - t5;
-        { std::lock_guard<std::mutex> lk(sh->kernel_ms_mutex); sh->kernel_ms += st.kernel_ms; }
-        {
-            std::lock_guard<std::mutex> lk(sh->out_mutex);
-            sh->done[b.seq].swap(outbytes);
-            { int64_t z = 0; sh->t_first_batch.compare_exchange_strong(z, now_us()); }
-        }
-        sh->out_cv.notify_all();
+        if (rc != 0) { sh->fail(std::string("batch ") + std::to_string(b.seq) + " could not be submitted (" + std::to_string(rc) + "): " + uvcgpu_last_error(ctx)); break; }
+        f.active = true; f.seq = b.seq; f.n_tiles = n_tiles; f.contigs = needed; f.us_fetch = t1 - t0; f.us_prep = t2 - t1;
+        // the batch before this one had the GPU while this one was decoded: finish it now
+        if (!finish(prev)) { break; }
+        cur ^= 1;
     }
-    for (int k = 0; k < n_dec; k++) { if (bams[k]) { uvchost_bam_close(bams[k]); } uvchost_readbuf_free(rbs[k]); }
+    for (int h = 0; h < 2; h++) { if (!sh->failed.load()) { finish(fl[cur ^ 1 ^ h]); } }
+    for (int h = 0; h < 2; h++) { if (fl[h].active) { uvcgpu_release(ctx, fl[h].ticket); fl[h].active = false; } }     // (after a failure)
+    for (int h = 0; h < 2; h++) { for (uvchost_readbuf *r : rbs2[h]) { uvchost_readbuf_free(r); } }
+    for (int k = 0; k < n_dec; k++) { if (bams[k]) { uvchost_bam_close(bams[k]); } }
     if (fa) { uvchost_fasta_close(fa); }
     uvcgpu_destroy(ctx);
 }
