@@ -137,3 +137,30 @@ def test_emulation_needed_positions_random_tilings(synth_small, seed):
         tiles.append((0, pos, pos + length, 0))
         pos += length + rnd.choice([0, 0, 1, 50, 700])
     _restricted_equals_full(synth_small, tiles, True)
+
+
+def _two_allele_site(tmp_path_factory_dir):
+    """configs[0] as the bench generates it has a site (chrS1:78101) with two different insertions of the same length class: the reference formats
+    the alleles of one indel symbol on one object, and the second allele's record repeats the first one's nNFA / nAFA / nBCFA in front of its own."""
+    import bench
+    ds = bench.dataset(str(tmp_path_factory_dir), "c1", 1.0, 0, 4)
+    return ds, [(0, 77000, 79500, 0)]
+
+
+@pytest.mark.skipif(not os.path.exists(pu.REF_UVC1), reason="oracle/_ref/uvc1 not built")
+def test_emulation_two_alleles_of_one_indel_symbol(tmp_path_factory, tmp_path):
+    ds, tiles = _two_allele_site(tmp_path_factory.mktemp("c1_full"))
+    _vs_reference({"bam": ds["bam"], "fasta": ds["fasta"]}, "chrS1", tiles, [], {}, True, tmp_path)
+    ours, _ = _our_lines(ds["bam"], ds["fasta"], tiles, True)
+    site = [l.split("\t") for l in ours if l.split("\t")[1] == "78101" and len(l.split("\t")[4]) > 1]
+    assert len(site) == 2
+    n_nfa = [len(dict(zip(f[8].split(":"), f[9].split(":")))["nNFA"].split(",")) for f in site]
+    assert sorted(n_nfa) == [6, 12]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(pu.REF_UVC1), reason="oracle/_ref/uvc1 not built")
+def test_cuda_two_alleles_of_one_indel_symbol(tmp_path_factory, tmp_path):
+    ds, tiles = _two_allele_site(tmp_path_factory.mktemp("c1_full_gpu"))
+    st = _vs_reference({"bam": ds["bam"], "fasta": ds["fasta"]}, "chrS1", tiles, [], {}, False, tmp_path)
+    assert st.gpu_launches > 0

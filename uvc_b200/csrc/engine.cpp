@@ -41,6 +41,7 @@
 #endif
 
 #define UVC_CURSOR_SLOTS 64
+#define UVC_CURSOR_WORDS 16     // per slot: 4 words of the sparse stream's cursor, 8 of the scoring pipeline's counters
 #define UVC_N_PILEUP_STAGES 12   // K0, K1, K2, K2e, KF, K3a, K3b, KM, K4a, K4, K4c, K6 (kernel_ms_by_stage[0..11]); [12] = K5
 
 namespace {
@@ -86,6 +87,7 @@ struct BatchState {
     GvcfPos *d_gvcf = nullptr; GvcfExtra *d_gextra = nullptr;
     int32_t *rec_cursor_host = nullptr, *score_cursor_host = nullptr;   // 4 + 4 words of the context's page-locked cursor slab
     StageVec<IndelAllele> allele_table;
+    std::vector<PrevAllele> prev_alleles;                 // sorted by (record slot, allele order): see score_core.cuh
 #if UVC_CUDA
     cudaEvent_t ev[UVC_N_PILEUP_STAGES + 1];
     cudaEvent_t ev_done;                  // after the downloads that ride behind the batch's kernels
@@ -1073,7 +1075,7 @@ static int backend_score(uvcgpu_ctx *ctx, BatchState & bs, const ScoreView & sv)
     UVC_CUDA_CHECK(ctx, cudaEventRecord(e[1], t_active));
     UVC_CUDA_CHECK(ctx, cudaGetLastError());
     // the results the host always needs ride behind the kernels: the cursors and the first records
-    { int rc_ = backend_download_async(ctx, bs.score_cursor_host, sv.out_cursor, 4 * sizeof(int32_t));
+    { int rc_ = backend_download_async(ctx, bs.score_cursor_host, sv.out_cursor, 8 * sizeof(int32_t));
       if (0 == rc_) { rc_ = backend_download_async(ctx, bs.recs.data(), sv.out, bs.recs.size() * sizeof(VarRec)); }
       if (0 == rc_) { rc_ = backend_sync(ctx); }
       if (rc_ != 0) { return rc_; } }
@@ -1150,7 +1152,7 @@ static int backend_score(uvcgpu_ctx *, BatchState & bs, const ScoreView & sv) {
         for (int64_t i = 0; i < (int64_t)sv.out_cursor[3]; i++) { uvc::k5e_candidate(v, sv, i); }
         for (int64_t i = 0; i < (int64_t)sv.out_cursor[2]; i++) { uvc::k5f_group(v, sv, i); }
     }
-    memcpy(bs.score_cursor_host, sv.out_cursor, 4 * sizeof(int32_t));
+    memcpy(bs.score_cursor_host, sv.out_cursor, 8 * sizeof(int32_t));
     memcpy(bs.recs.data(), sv.out, bs.recs.size() * sizeof(VarRec));
     return 0;
 }
@@ -1404,10 +1406,10 @@ int uvcgpu_create(uvcgpu_ctx **out, int device, const uvcgpu_params *params) {
 #endif
 #if UVC_CUDA
     { SlabCache & sc = slab_cache(device); std::lock_guard<std::mutex> lk(sc.mu); sc.live_contexts++; }
-    if (cudaHostAlloc((void**)&ctx->cursor_slab, (size_t)UVC_CURSOR_SLOTS * 8 * sizeof(int32_t), cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); delete ctx; return UVCGPU_ECUDA; }
+    if (cudaHostAlloc((void**)&ctx->cursor_slab, (size_t)UVC_CURSOR_SLOTS * UVC_CURSOR_WORDS * sizeof(int32_t), cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); delete ctx; return UVCGPU_ECUDA; }
     ctx->worker = std::thread(submit_worker, ctx);
 #else
-    ctx->cursor_slab = (int32_t*)calloc((size_t)UVC_CURSOR_SLOTS * 8, sizeof(int32_t));
+    ctx->cursor_slab = (int32_t*)calloc((size_t)UVC_CURSOR_SLOTS * UVC_CURSOR_WORDS, sizeof(int32_t));
 #endif
     *out = ctx;
     return UVCGPU_OK;
@@ -1638,12 +1640,12 @@ int uvcgpu_submit_multi(uvcgpu_ctx *ctx, int32_t n_tiles, const uvcgpu_tile *til
         int slot = (int)(*ticket % UVC_CURSOR_SLOTS);
         for (;;) {
             bool used = false;
-            for (auto & kv : ctx->batches) { if (kv.second->rec_cursor_host == ctx->cursor_slab + 8 * slot) { used = true; break; } }
+            for (auto & kv : ctx->batches) { if (kv.second->rec_cursor_host == ctx->cursor_slab + UVC_CURSOR_WORDS * slot) { used = true; break; } }
             if (!used) { break; }
             slot = (slot + 1) % UVC_CURSOR_SLOTS;
         }
-        raw->rec_cursor_host = ctx->cursor_slab + 8 * slot; raw->score_cursor_host = raw->rec_cursor_host + 4;
-        memset(raw->rec_cursor_host, 0, 8 * sizeof(int32_t));
+        raw->rec_cursor_host = ctx->cursor_slab + UVC_CURSOR_WORDS * slot; raw->score_cursor_host = raw->rec_cursor_host + 4;
+        memset(raw->rec_cursor_host, 0, UVC_CURSOR_WORDS * sizeof(int32_t));
     }
     ctx->batches[*ticket] = std::move(bs);
 #if UVC_CUDA
@@ -1737,13 +1739,13 @@ static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
     if ((rc = backend_upload(ctx, bs, d, table.data(), table.size() * sizeof(IndelAllele))) != 0) { return rc; }
     sv.alleles = (const IndelAllele*)d; sv.n_alleles = (int64_t)table.size();
     sv.gvcf = bs.d_gvcf; sv.gextra = bs.d_gextra;
-    if ((rc = backend_alloc(ctx, bs, &d, 16, true)) != 0) { return rc; }
+    if ((rc = backend_alloc(ctx, bs, &d, 32, true)) != 0) { return rc; }
     sv.out_cursor = (int32_t*)d;
     sv.cand_cursor = sv.out_cursor + 1;
     if (v.n_pos > INT32_MAX) { UVC_ERR(ctx) = "batch too large: submit fewer tiles"; return UVCGPU_EINVAL; }
     if ((rc = backend_alloc(ctx, bs, &d, (size_t)v.n_pos * sizeof(int32_t), false)) != 0) { return rc; }
     sv.cand_list = (int32_t*)d;
-    int64_t cap = v.n_pos / 16 + 4096;
+    int64_t cap = v.n_pos / 16 + 4096, prev_cap = v.n_pos / 256 + 1024;
     // groups and candidates per position: sized from what the context's earlier batches needed (a batch that needs more runs twice)
     int64_t group_cap = (int64_t)(ctx->k5_groups_per_pos * (double)v.n_pos) + 1024, cand_cap = (int64_t)(ctx->k5_cands_per_pos * (double)v.n_pos) + 4096;
     StageVec<VarRec> & recs = bs.recs;
@@ -1757,21 +1759,26 @@ static int ensure_scored(uvcgpu_ctx *ctx, BatchState & bs) {
         sv.desc = (CandDesc*)d;
         if ((rc = backend_alloc_temp(ctx, bs, &d, (size_t)cand_cap * sizeof(CandFmt))) != 0) { return rc; }
         sv.cands = (CandFmt*)d; sv.cand_cap = (int32_t)cand_cap;
-        if ((rc = backend_zero(ctx, sv.out_cursor, 16)) != 0) { return rc; }
+        if ((rc = backend_alloc_temp(ctx, bs, &d, (size_t)prev_cap * sizeof(PrevAllele))) != 0) { return rc; }
+        sv.prev = (PrevAllele*)d; sv.prev_cap = (int32_t)prev_cap;
+        if ((rc = backend_zero(ctx, sv.out_cursor, 32)) != 0) { return rc; }
         recs.resize(std::min<size_t>(n_first, (size_t)cap));
         if ((rc = backend_score(ctx, bs, sv)) != 0) { return rc; }
-        const int32_t n = bs.score_cursor_host[0], n_groups = bs.score_cursor_host[2], n_cands = bs.score_cursor_host[3];
+        const int32_t n = bs.score_cursor_host[0], n_groups = bs.score_cursor_host[2], n_cands = bs.score_cursor_host[3], n_prev = bs.score_cursor_host[4];
         ctx->k5_groups_per_pos = std::max(ctx->k5_groups_per_pos, std::min(2.0, 1.25 * (double)n_groups / (double)std::max<int64_t>(1, v.n_pos)));
         ctx->k5_cands_per_pos = std::max(ctx->k5_cands_per_pos, std::min(2.0 * UVC_MAX_GROUP_CANDS, 1.25 * (double)n_cands / (double)std::max<int64_t>(1, v.n_pos)));
-        if (n <= cap && n_groups <= group_cap && n_cands <= cand_cap) {
+        if (n <= cap && n_groups <= group_cap && n_cands <= cand_cap && n_prev <= prev_cap) {
             const size_t have = recs.size();
             recs.resize((size_t)n);
             if ((size_t)n > have && (rc = backend_download(ctx, recs.data() + have, sv.out + have, ((size_t)n - have) * sizeof(VarRec))) != 0) { return rc; }
+            bs.prev_alleles.resize((size_t)n_prev);
+            if (n_prev > 0 && (rc = backend_download(ctx, bs.prev_alleles.data(), sv.prev, (size_t)n_prev * sizeof(PrevAllele))) != 0) { return rc; }
+            std::sort(bs.prev_alleles.begin(), bs.prev_alleles.end(), [](const PrevAllele & a, const PrevAllele & b) { return a.rec_slot != b.rec_slot ? a.rec_slot < b.rec_slot : a.order > b.order; });
             break;
         }
         if (attempt == 2) { UVC_ERR(ctx) = "candidate record buffer overflow"; return UVCGPU_ENOMEM; }
         // the kernels counted everything they wanted to write: run again with room for all of it
-        cap = std::max<int64_t>(cap, n); group_cap = std::max<int64_t>(group_cap, n_groups); cand_cap = std::max<int64_t>(cand_cap, n_cands);
+        cap = std::max<int64_t>(cap, n); group_cap = std::max<int64_t>(group_cap, n_groups); cand_cap = std::max<int64_t>(cand_cap, n_cands); prev_cap = std::max<int64_t>(prev_cap, n_prev);
         backend_free_temps(ctx, bs, true);
     }
     backend_free_temps(ctx, bs, true);      // (the scoring kernels and the downloads of their results have completed)
@@ -1842,7 +1849,7 @@ static int ensure_vcf_text(uvcgpu_ctx *ctx, BatchState & bs) {
         const TileInfo & T = bs.hb.tiles[R.ti];
         auto nm = ctx->contig_names.find(T.tid);
         const std::string tname = (nm == ctx->contig_names.end() ? std::to_string(T.tid) : nm->second);
-        parts[(size_t)k] = uvc_tile_vcf_text_range(*plans[R.ti], bs.hb, R.ti, ctx->par, tname, bs.sites[R.ti], bs.sparse[R.ti], bs.ev_host, bs.gvcf.data(), bs.gextra.data(), R.zb0, R.zb1);
+        parts[(size_t)k] = uvc_tile_vcf_text_range(*plans[R.ti], bs.hb, R.ti, ctx->par, tname, bs.sites[R.ti], bs.sparse[R.ti], bs.ev_host, bs.gvcf.data(), bs.gextra.data(), R.zb0, R.zb1, &bs.prev_alleles);
     });
     for (size_t k = 0; k < ranges.size(); k++) { bs.vcf_text[(size_t)ranges[k].ti].emplace_back(std::move(parts[k])); }     // (no concatenation: the callers copy the parts out)
     for (TileTextPlan *pl : plans) { if (pl) { uvc_tile_text_plan_free(pl); } }

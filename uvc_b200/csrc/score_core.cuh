@@ -93,9 +93,16 @@ struct GroupRec {
 // what BcfFormat_symbol_init needs to know about a candidate besides its position
 struct CandDesc { int32_t group, symbol, bDPa, cDP0a, ev, gap_len, minABQ, pad; };
 
+// QUIRK: the reference runs BcfFormat_symbol_init + BcfFormat_symbol_calc_DPv for every allele of an indel symbol on ONE format object
+// (main.cpp:850, 905-946), and calc_DPv appends to nNFA / nAFA / nBCFA and to the last FTS string without clearing them (main.hpp:4261-4268,
+// 4737-4769): the record of the second allele of a symbol prints the first allele's values in front of its own. A kept record therefore comes
+// with one of these per earlier allele of its symbol (rare: a site with two different insertions or deletions of the same length class).
+struct PrevAllele { int32_t rec_slot, order; int32_t nNFA[6], nAFA[9], nBCFA[10]; uint32_t fts_mask; int32_t fts_pct[UVC_NUM_FTS]; };
+
 struct ScoreView {
     const IndelAllele *alleles; int64_t n_alleles;
-    VarRec *out; int32_t *out_cursor; int32_t out_cap;      // out_cursor[0..3]: records, candidate positions, groups, candidates
+    VarRec *out; int32_t *out_cursor; int32_t out_cap;      // out_cursor[0..4]: records, candidate positions, groups, candidates, earlier-allele records
+    PrevAllele *prev; int32_t prev_cap;
     GroupRec *groups; CandDesc *desc; CandFmt *cands; int32_t group_cap, cand_cap;
     GvcfPos *gvcf;          // [n_pos]
     GvcfExtra *gextra;      // [n_pos]
@@ -1219,7 +1226,18 @@ UVC_HD void k5f_group(const BatchView & v, const ScoreView & sv, int64_t gi) {
         const int32_t slot = atomic_add_i32(sv.out_cursor, 1);
         if (slot >= sv.out_cap) { continue; }
         VarRec & o = sv.out[slot];
-        o.gp = G.gp; o.tile = G.tile; o.refpos = refpos; o.symboltype = type; o.refsymbol = refsymbol; o.cand_index = i; o.pad0 = 0;
+        o.gp = G.gp; o.tile = G.tile; o.refpos = refpos; o.symboltype = type; o.refsymbol = refsymbol; o.cand_index = i; o.pad0 = slot;
+        for (int j = i - 1; j >= 0 && C[j].symbol == symbol; j--) {     // earlier alleles of the same symbol (see PrevAllele); order = distance back
+            const int32_t ps = atomic_add_i32(sv.out_cursor + 4, 1);
+            if (ps >= sv.prev_cap) { continue; }
+            PrevAllele & q = sv.prev[ps];
+            q.rec_slot = slot; q.order = i - j;
+            for (int k = 0; k < 6; k++) { q.nNFA[k] = C[j].nNFA[k]; }
+            for (int k = 0; k < 9; k++) { q.nAFA[k] = C[j].nAFA[k]; }
+            for (int k = 0; k < 10; k++) { q.nBCFA[k] = C[j].nBCFA[k]; }
+            q.fts_mask = C[j].fts_mask;
+            for (int k = 0; k < UVC_NUM_FTS; k++) { q.fts_pct[k] = C[j].fts_pct[k]; }
+        }
         o.g = g; o.ref = R; o.alt = c;
         o.DP = g.CDP1b[0] + g.CDP1b[1]; o.bDP = g.BDPb[0] + g.BDPb[1]; o.c2DP = g.CDP2b[0] + g.CDP2b[1];
         for (int r = 0; r < 2; r++) {

@@ -100,15 +100,21 @@ void append_phase_string(std::string & out, const std::vector<HapLinkOut> & link
     }
 }
 
-std::string fts_string(const CandFmt & c) {
-    std::string out;
+// One allele's pass over the FTS string (fmt_bias_push, main.hpp:4258-4272, and the PASS default :4771-4773): the failed filters are appended
+// to the string the format object already holds (QUIRK: the alleles of an indel symbol share the object, see PrevAllele), "PASS" if it stays empty
+void fts_append(std::string & out, uint32_t fts_mask, const int32_t *fts_pct) {
     for (int k = 0; k < UVC_NUM_FTS; k++) {
-        if (c.fts_mask & (1u << k)) {
+        if (fts_mask & (1u << k)) {
             if (!out.empty()) { out += "|"; }
-            out += std::string(FTS_NAMES[k]) + "-" + std::to_string(c.fts_pct[k]);
+            out += std::string(FTS_NAMES[k]) + "-" + std::to_string(fts_pct[k]);
         }
     }
-    return out.empty() ? std::string("PASS") : out;
+    if (out.empty()) { out = "PASS"; }
+}
+std::string fts_string(const CandFmt & c) {
+    std::string out;
+    fts_append(out, c.fts_mask, c.fts_pct);
+    return out;
 }
 
 } // namespace
@@ -260,7 +266,7 @@ std::string uvc_tile_vcf_text(const HostBatch & hb, int32_t tile_index, const uv
 // the text of the zero-based positions [zb_begin, zb_end) of a tile (a sub-range of [rpos_inclu_beg, rpos_exclu_end]): ranges are independent
 std::string uvc_tile_vcf_text_range(const TileTextPlan & plan, const HostBatch & hb, int32_t tile_index, const uvcgpu_params & par, const std::string & tname,
         const TileIndelSites & sites, const TileSparse & sparse, const StageVec<IndelEvent> & ev, const GvcfPos *gvcf, const GvcfExtra *gextra,
-        int32_t zb_begin, int32_t zb_end) {
+        int32_t zb_begin, int32_t zb_end, const std::vector<PrevAllele> *prev_alleles) {
     std::string out;
     const TileInfo & T = hb.tiles[tile_index];
     if (T.skipped || zb_end <= zb_begin) { return out; }
@@ -378,7 +384,18 @@ std::string uvc_tile_vcf_text_range(const TileTextPlan & plan, const HostBatch &
                 }
                 Out o(out);
                 #define RR(field) o.pair(R.field, A.field)
-                o.str("./1"); o.one(0); o.pair(0, 0); o.str(""); o.str(fts_string(A)); o.tag("_A_");
+                // earlier alleles of the same indel symbol (rare; see PrevAllele in score_core.cuh): their values come first
+                const PrevAllele *pa0 = NULL, *pa1 = NULL;
+                if (prev_alleles && !prev_alleles->empty()) {
+                    auto lo = std::lower_bound(prev_alleles->begin(), prev_alleles->end(), r.pad0, [](const PrevAllele & a, int32_t slot) { return a.rec_slot < slot; });
+                    auto hi = lo;
+                    while (hi != prev_alleles->end() && hi->rec_slot == r.pad0) { ++hi; }
+                    if (hi != lo) { pa0 = &*lo; pa1 = pa0 + (hi - lo); }
+                }
+                std::string fts;
+                for (const PrevAllele *pa = pa0; pa != pa1; pa++) { fts_append(fts, pa->fts_mask, pa->fts_pct); }
+                fts_append(fts, A.fts_mask, A.fts_pct);
+                o.str("./1"); o.one(0); o.pair(0, 0); o.str(""); o.str(fts); o.tag("_A_");
                 o.one(r.DP); RR(AD); o.one(r.bDP); RR(bAD); o.one(r.c2DP); RR(c2AD); o.tag("_Aa");
                 o.arr(g.APDP, 12); o.arr(g.APXM, 8); o.tag("_Ab"); o.arr(g.APLRID, 4); o.arr(g.APLRI, 4); o.arr(g.APLRP, 4); o.tag("_Ac");
                 o.arr(g.ALRPxT, 2); o.arr(g.ALRIT, 4); o.arr(g.ALRIt, 4); o.arr(g.ALRPt, 4); o.arr(g.ALRBt, 4); o.tag("_AQ");
@@ -413,7 +430,17 @@ std::string uvc_tile_vcf_text_range(const TileTextPlan & plan, const HostBatch &
                 RR(cPCQ2); RR(cPLQ2); RR(cVQ2); RR(cMmQ); RR(dVQinc); o.tag("_CDP1vx");
                 RR(cDP1v); o.arr(g.CDP1v, 2); RR(cDP1w); o.one(g.CDP1w[0]); RR(cDP1x); o.one(g.CDP1x[0]); o.tag("_CDP2vx");
                 RR(cDP2v); o.arr(g.CDP2v, 2); RR(cDP2w); o.one(g.CDP2w[0]); RR(cDP2x); o.one(g.CDP2x[0]); o.tag("_f1");
-                RR(CONTQ); o.arr(A.nPF, 2); o.arr(A.nNFA, 6); o.arr(A.nAFA, 9); o.arr(A.nBCFA, 10); o.tag("_g1");
+                RR(CONTQ); o.arr(A.nPF, 2);
+                if (pa0 == pa1) { o.arr(A.nNFA, 6); o.arr(A.nAFA, 9); o.arr(A.nBCFA, 10); }
+                else {
+                    o.sepc(); for (const PrevAllele *pa = pa0; pa != pa1; pa++) { for (int k = 0; k < 6; k++) { append_num(out, pa->nNFA[k]); out += ','; } }
+                    for (int k = 0; k < 6; k++) { if (k) { out += ','; } append_num(out, A.nNFA[k]); }
+                    o.sepc(); for (const PrevAllele *pa = pa0; pa != pa1; pa++) { for (int k = 0; k < 9; k++) { append_num(out, pa->nAFA[k]); out += ','; } }
+                    for (int k = 0; k < 9; k++) { if (k) { out += ','; } append_num(out, A.nAFA[k]); }
+                    o.sepc(); for (const PrevAllele *pa = pa0; pa != pa1; pa++) { for (int k = 0; k < 10; k++) { append_num(out, pa->nBCFA[k]); out += ','; } }
+                    for (int k = 0; k < 10; k++) { if (k) { out += ','; } append_num(out, A.nBCFA[k]); }
+                }
+                o.tag("_g1");
                 o.pair(R.symbol, A.symbol);
                 o.sepc(); out += std::string(SYMBOL_DESC[R.symbol]) + "," + SYMBOL_DESC[A.symbol];
                 o.arr(r.cVQ1M, 2); o.arr(r.cVQ2M, 2);

@@ -34,7 +34,7 @@ TileTextPlan *uvc_tile_text_plan_new(const HostBatch & hb, int32_t tile_index, c
 void uvc_tile_text_plan_free(TileTextPlan *plan);
 std::string uvc_tile_vcf_text_range(const TileTextPlan & plan, const HostBatch & hb, int32_t tile_index, const uvcgpu_params & par, const std::string & tname,
         const TileIndelSites & sites, const TileSparse & sparse, const StageVec<IndelEvent> & ev, const GvcfPos *gvcf, const GvcfExtra *gextra,
-        int32_t zb_begin, int32_t zb_end);
+        int32_t zb_begin, int32_t zb_end, const std::vector<PrevAllele> *prev_alleles = NULL);
 
 // The uncompressed VCF fragment of one tile (what process_batch appends to uncompressed_vcf_string, main.cpp:1184).
 std::string uvc_tile_vcf_text(const HostBatch & hb, int32_t tile_index, const uvcgpu_params & par, const std::string & tname, const HostContig & contig,
