@@ -522,6 +522,23 @@ int64_t uvchost_bam_fetch_span(uvchost_bam *b, int32_t tid, int32_t n, const int
     for (int32_t k = 0; k + 1 < n; k++) { if (begs[k] > begs[k + 1] || ends[k] > ends[k + 1]) { return -2; } }
     const int64_t span_beg = (begs[0] < 0 ? 0 : begs[0]), span_end = ends[n - 1];
     const int64_t base = uvchost_readbuf_size(rb);
+    {   // room for the records the index says the span holds: growing the arrays by doubling copies every byte about once more and faults its pages in
+        const int64_t est = uvchost_bam_estimate_reads(b, tid, span_beg, span_end);
+        if (est > 4096 && est < ((int64_t)1 << 28)) {
+            const size_t m = (size_t)base + (size_t)est + (size_t)est / 8;
+            if (m > rb->pos.capacity()) {
+                rb->pos.reserve(m); rb->mpos.reserve(m); rb->isize.reserve(m); rb->mtid.reserve(m); rb->l_qseq.reserve(m); rb->n_cigar.reserve(m); rb->nm.reserve(m);
+                rb->flag.reserve(m); rb->mapq.reserve(m);
+                rb->seq_off.reserve(m + 1); rb->qual_off.reserve(m + 1); rb->cigar_off.reserve(m + 1); rb->qname_off.reserve(m + 1);
+                // (bytes per record from what the buffer already holds, else typical short-read sizes)
+                const size_t have = (size_t)base;
+                const size_t seq_b = (have > 1000 ? rb->seq.size() / have + 1 : 80), qual_b = (have > 1000 ? rb->qual.size() / have + 1 : 160);
+                const size_t cig_w = (have > 1000 ? rb->cigar.size() / have + 1 : 3), name_b = (have > 1000 ? rb->qname.size() / have + 1 : 48);
+                rb->seq.reserve(rb->seq.size() + ((size_t)est + (size_t)est / 8) * seq_b); rb->qual.reserve(rb->qual.size() + ((size_t)est + (size_t)est / 8) * qual_b);
+                rb->cigar.reserve(rb->cigar.size() + ((size_t)est + (size_t)est / 8) * cig_w); rb->qname.reserve(rb->qname.size() + ((size_t)est + (size_t)est / 8) * name_b);
+            }
+        }
+    }
     std::vector<int32_t> & endpos = rb->endpos_scratch;
     endpos.clear();
     int64_t total = 0;
